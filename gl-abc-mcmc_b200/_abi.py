@@ -1,0 +1,160 @@
+"""ctypes mirror of include/glabc.h (the C-ABI boundary) and the loader of libglabc.so.
+
+The library is the product: there is no CPU fallback.  `load()` raises if the shared object is
+missing (run `python -c "import __graft_entry__ as g; g.build()"`), and `Context()` raises if no
+CUDA device is usable.
+"""
+import ctypes as C
+import os
+
+MAX_DIM = 8
+MAX_MODES = 8
+MAX_K = 16
+AUX_SLOTS = 8
+AUX_LOGW, AUX_LOCAL = 0, 1
+DEBUG_SLOTS = 4 + MAX_K
+
+OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = range(5)
+
+MODEL_ABS_NORMAL, MODEL_ID_NORMAL = 1, 2
+DIST_NONE, DIST_DIAG_GAUSSIAN, DIST_UNIFORM, DIST_GAMMA, DIST_GAUSSIAN_MIXTURE = range(5)
+SLOT_LOCAL, SLOT_GLOBAL, SLOT_IMPORTANCE = range(3)
+RNG_NATIVE, RNG_REPLAY = 0, 1
+ARITH_FAST, ARITH_STRICT = 0, 1
+TRACE_NONE, TRACE_TIME_MAJOR, TRACE_CHAIN_MAJOR = 0, 1, 2
+
+STAT_STEPS, STAT_GLOBAL_STEPS, STAT_ACC_LOCAL, STAT_ACC_GLOBAL, STAT_SUM = 0, 1, 2, 3, 4
+
+
+def nstats(d):
+    return 4 + 2 * d + (d * (d + 1)) // 2
+
+
+def tape_global_slots(d, yd):
+    return 2 + d + yd
+
+
+def tape_isir_slots(d, yd, k):
+    return 2 + k * (d + yd)
+
+
+_F8 = C.c_float * MAX_DIM
+
+
+class ModelPOD(C.Structure):
+    """glabc_model_t"""
+    _fields_ = [("family", C.c_int32), ("theta_dim", C.c_int32), ("y_dim", C.c_int32), ("reserved", C.c_int32),
+                ("y_obs", _F8), ("noise_loc", _F8), ("noise_scale", _F8), ("prior_loc", _F8),
+                ("prior_log_scale", _F8), ("prior_scale", _F8),
+                ("eps_log_scale", C.c_float), ("eps_scale", C.c_float)]
+
+
+class DistPOD(C.Structure):
+    """glabc_dist_t"""
+    _fields_ = [("kind", C.c_int32), ("dim", C.c_int32), ("n_modes", C.c_int32), ("reserved", C.c_int32),
+                ("a", _F8), ("b", _F8), ("c", _F8),
+                ("mix_loc", _F8 * MAX_MODES), ("mix_log_scale", _F8 * MAX_MODES), ("mix_scale", _F8 * MAX_MODES),
+                ("mix_log_w", C.c_float * MAX_MODES), ("mix_w", C.c_float * MAX_MODES)]
+
+
+class RunPOD(C.Structure):
+    """glabc_run_t"""
+    _fields_ = [("n_chains", C.c_int64), ("n_steps", C.c_int64), ("step_base", C.c_int64),
+                ("chain_id_base", C.c_int64), ("seed", C.c_uint64), ("global_frequency", C.c_float),
+                ("rng_mode", C.c_int32), ("arith_mode", C.c_int32), ("trace_layout", C.c_int32),
+                ("write_row0", C.c_int32), ("block_threads", C.c_int32), ("n_candidates", C.c_int32),
+                ("num_grad", C.c_int32), ("tau", C.c_float),
+                ("trace_rows", C.c_int64), ("trace_chains", C.c_int64), ("trace_chain_off", C.c_int64),
+                ("theta", C.c_void_p), ("y", C.c_void_p), ("aux", C.c_void_p), ("trace", C.c_void_p),
+                ("stats", C.c_void_p), ("tape32", C.c_void_p), ("tape64", C.c_void_p), ("debug", C.c_void_p),
+                ("stream", C.c_void_p)]
+
+
+def fill(arr, values):
+    values = [float(v) for v in values]
+    if len(values) > len(arr):
+        raise ValueError(f"at most {len(arr)} values fit, got {len(values)}")
+    for i, v in enumerate(values):
+        arr[i] = v
+
+
+LIB_NAME = "libglabc.so"
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", LIB_NAME)
+
+# every symbol include/glabc.h declares (tests/test_abi_symbols.py parses the header and checks)
+_SIGNATURES = {
+    "glabc_version": (C.c_int, []),
+    "glabc_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "glabc_ctx_destroy": (C.c_int, [C.c_void_p]),
+    "glabc_last_error": (C.c_char_p, [C.c_void_p]),
+    "glabc_status_string": (C.c_char_p, [C.c_int]),
+    "glabc_device_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "glabc_model_set": (C.c_int, [C.c_void_p, C.POINTER(ModelPOD), C.c_size_t]),
+    "glabc_dist_set": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(DistPOD), C.c_size_t]),
+    "glabc_run_global": (C.c_int, [C.c_void_p, C.POINTER(RunPOD)]),
+    "glabc_run_global_host": (C.c_int, [C.c_void_p, C.POINTER(RunPOD), C.c_int64]),
+    "glabc_esjd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "glabc_philox_kat": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+
+
+class GlabcError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"glabc status {status}: {message}")
+        self.status = status
+
+
+def load(path=None):
+    """dlopen libglabc.so and bind the signatures.  Loading needs no GPU; running does."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise ImportError(
+            f"{p} is missing: the CUDA extension has not been built. Build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). "
+            "There is no CPU fallback.")
+    lib = C.CDLL(p)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+class Context:
+    """glabc_ctx: one per (thread, device)."""
+
+    def __init__(self, device=-1):
+        self.lib = load()
+        h = C.c_void_p()
+        st = self.lib.glabc_ctx_create(int(device), C.byref(h))
+        if st != OK:
+            raise GlabcError(st, self.lib.glabc_status_string(st).decode() +
+                             " — glabc needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.handle = h
+
+    def check(self, st):
+        if st != OK:
+            raise GlabcError(st, self.lib.glabc_last_error(self.handle).decode())
+
+    def device_info(self):
+        sm, khz, cc = C.c_int32(), C.c_int32(), C.c_int32()
+        self.check(self.lib.glabc_device_info(self.handle, C.byref(sm), C.byref(khz), C.byref(cc)))
+        return dict(sm_count=sm.value, clock_khz=khz.value, cc=cc.value)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.glabc_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,221 @@
+/*
+ * glabc.h — C-ABI of the B200-native GL-ABC-MCMC sampler inner loop.
+ *
+ * The reference (caofff/GL-ABC-MCMC, `glabcmcmc` 1.0.1) is pure Python and has no FFI; its operator
+ * boundary for this path is the set of duck-typed Python calls the sampler loops make
+ * (SURVEY.md §8(b)).  This header is the boundary a maintainer would bind instead (ctypes stub in
+ * INTEGRATION.md).  Every entry point names the reference loop it replaces.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no C++/torch types; every function returns a glabc_status (0 = OK);
+ *     glabc_last_error(ctx) gives the message of the last failure on that context.
+ *   - `*_dev` pointers are CUDA device pointers on the context's device; `*_host` are host pointers
+ *     (pinned memory makes the copies asynchronous, pageable memory works too).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Device entry
+ *     points only enqueue work; host entry points return when the result is in the host buffers.
+ *   - no hidden global state: one context per (thread, device); a context is not thread-safe.
+ *   - all floating-point parameters are float32 values the host evaluated the way the reference
+ *     does (e.g. scale = exp(log_scale) in float32, distribution.py:170), so device code never has to
+ *     re-derive a constant with a different libm.
+ */
+#ifndef GLABC_H
+#define GLABC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLABC_ABI_VERSION 1
+#define GLABC_MAX_DIM 8      /* theta_dim and y_dim of a fused model family               */
+#define GLABC_MAX_MODES 8    /* GaussianMixture components                                  */
+#define GLABC_MAX_K 16       /* iSIR candidates per global move (reference `batch_size`)    */
+
+typedef enum {
+    GLABC_OK = 0,
+    GLABC_ERR_INVALID = 1,       /* bad argument (message says which)                       */
+    GLABC_ERR_UNSUPPORTED = 2,   /* model family / distribution kind / dim not fused        */
+    GLABC_ERR_CUDA = 3,          /* a CUDA runtime call failed                              */
+    GLABC_ERR_NO_DEVICE = 4      /* no usable CUDA device — there is no CPU fallback        */
+} glabc_status;
+
+/* ---- ABC model plugin (reference: examples/Mixture.py:5-53, README.md:66-104) -------------- */
+typedef enum {
+    /* y = |theta| + noise_loc + noise_scale * eps   (Mixture.py:19-23), y_dim == theta_dim    */
+    GLABC_MODEL_ABS_NORMAL = 1,
+    /* y = theta + noise_loc + noise_scale * eps     (Gaussian location model)                 */
+    GLABC_MODEL_ID_NORMAL = 2
+} glabc_model_family;
+
+typedef struct {
+    int32_t family;                        /* glabc_model_family                                */
+    int32_t theta_dim;
+    int32_t y_dim;
+    int32_t reserved;
+    float y_obs[GLABC_MAX_DIM];            /* Mixture.py:9                                      */
+    float noise_loc[GLABC_MAX_DIM];        /* Mixture.py:19 (0)                                 */
+    float noise_scale[GLABC_MAX_DIM];      /* exp(log(sqrt(0.05))) in float32, Mixture.py:19    */
+    float prior_loc[GLABC_MAX_DIM];        /* Mixture.py:30                                     */
+    float prior_log_scale[GLABC_MAX_DIM];
+    float prior_scale[GLABC_MAX_DIM];      /* exp(prior_log_scale) in float32                   */
+    float eps_log_scale;                   /* log(epsilon) in float32, Mixture.py:43            */
+    float eps_scale;                       /* exp(log(epsilon)) in float32 (0.05 -> 0.049999997)*/
+} glabc_model_t;
+
+/* ---- proposal / prior distributions (reference: distribution.py:50,90,143,206) ------------- */
+typedef enum {
+    GLABC_DIST_NONE = 0,
+    GLABC_DIST_DIAG_GAUSSIAN = 1,          /* distribution.py:143-181                           */
+    GLABC_DIST_UNIFORM = 2,                /* distribution.py:50-86                             */
+    GLABC_DIST_GAMMA = 3,                  /* distribution.py:90-137                            */
+    GLABC_DIST_GAUSSIAN_MIXTURE = 4        /* distribution.py:206-293                           */
+} glabc_dist_kind;
+
+typedef struct {
+    int32_t kind;                          /* glabc_dist_kind                                   */
+    int32_t dim;
+    int32_t n_modes;                       /* GaussianMixture only                              */
+    int32_t reserved;
+    /* DiagGaussian: a = loc, b = log_scale, c = exp(log_scale).
+       Uniform:      a = low, b = high,      c[0] = log_prob_val (distribution.py:71).
+       Gamma:        a = shape, b = rate.                                                       */
+    float a[GLABC_MAX_DIM];
+    float b[GLABC_MAX_DIM];
+    float c[GLABC_MAX_DIM];
+    /* GaussianMixture: loc / log_scale / scale per mode, log of the soft-maxed weights.        */
+    float mix_loc[GLABC_MAX_MODES][GLABC_MAX_DIM];
+    float mix_log_scale[GLABC_MAX_MODES][GLABC_MAX_DIM];
+    float mix_scale[GLABC_MAX_MODES][GLABC_MAX_DIM];
+    float mix_log_w[GLABC_MAX_MODES];
+    float mix_w[GLABC_MAX_MODES];
+} glabc_dist_t;
+
+typedef enum { GLABC_SLOT_LOCAL = 0, GLABC_SLOT_GLOBAL = 1, GLABC_SLOT_IMPORTANCE = 2,
+               GLABC_SLOT_COUNT = 3 } glabc_slot;
+
+/* ---- run description -------------------------------------------------------------------- */
+typedef enum {
+    GLABC_RNG_NATIVE = 0,   /* per-thread Philox4x32-10, counter = (global chain id, step, slot)  */
+    GLABC_RNG_REPLAY = 1    /* consume a tape of the reference's own draws (parity mode)          */
+} glabc_rng_mode;
+
+typedef enum {
+    GLABC_ARITH_FAST = 0,   /* FMA contraction, reciprocal multiplies, MUFU approximations        */
+    GLABC_ARITH_STRICT = 1  /* the reference's float32 operation order, IEEE div/sqrt, no FMA     */
+} glabc_arith_mode;
+
+typedef enum {
+    GLABC_TRACE_NONE = 0,        /* statistics only                                               */
+    GLABC_TRACE_TIME_MAJOR = 1,  /* trace[row][chain][d]                                          */
+    GLABC_TRACE_CHAIN_MAJOR = 2  /* trace[chain][row][d] — out[c] is a reference-shaped chain,
+                                    rows staged through shared memory (GlobalMCMC.py:34,98)       */
+} glabc_trace_layout;
+
+/* Per-chain statistics accumulated in-kernel (replaces the reference's unused `num_acc`,
+ * GlobalMCMC.py:33,50,65, and feeds esjd(), ESJD.py:17-24, without re-reading the trace).       */
+#define GLABC_STAT_STEPS 0          /* transitions performed                                      */
+#define GLABC_STAT_GLOBAL_STEPS 1   /* of which took the global branch                            */
+#define GLABC_STAT_ACC_LOCAL 2      /* accepted local moves                                       */
+#define GLABC_STAT_ACC_GLOBAL 3     /* accepted / switched global moves                           */
+#define GLABC_STAT_SUM 4            /* + i            : sum_t theta_i          (i < d)            */
+/*                     4 + d + i          : sum_t theta_i^2                                       */
+/*                     4 + 2d + tri(i,j)  : sum_t delta_i delta_j, i <= j (row-major upper tri)   */
+#define GLABC_NSTATS(d) (4 + 2 * (d) + ((d) * ((d) + 1)) / 2)
+
+#define GLABC_AUX_SLOTS 8
+#define GLABC_AUX_LOGW 0            /* iSIR: cached log-weight of the current state               */
+#define GLABC_AUX_LOCAL 1           /* iSIR: 1.0 if a local move was accepted since (init 1.0)    */
+
+/* Common fields of every sampler launch.  One launch advances `n_chains` independent chains by
+ * `n_steps` transitions (loop iterations i = step_base+1 .. step_base+n_steps of the reference's
+ * `for i in range(1, num_ite)`), so a run can be cut into time chunks or resumed.                */
+typedef struct {
+    int64_t n_chains;         /* chains in this launch (this rank's shard)                        */
+    int64_t n_steps;          /* transitions to perform                                           */
+    int64_t step_base;        /* transitions already performed (0 for a fresh chain)              */
+    int64_t chain_id_base;    /* global id of chain 0 of this shard: Philox streams are keyed by
+                                 the global id, so traces do not depend on the GPU count          */
+    uint64_t seed;
+    float global_frequency;   /* compared in float32, strict <                    */
+    int32_t rng_mode;         /* glabc_rng_mode                                                   */
+    int32_t arith_mode;       /* glabc_arith_mode                                                 */
+    int32_t trace_layout;     /* glabc_trace_layout                                               */
+    int32_t write_row0;       /* also store the incoming state as trace row `step_base`           */
+    int32_t block_threads;    /* 0 = library default                                              */
+    int32_t n_candidates;     /* iSIR K = reference `batch_size` (run_isir / run_mala only)       */
+    int32_t num_grad;         /* GLMALA gradient sample count (run_mala only)                     */
+    float tau;                /* GLMALA step size (run_mala only)                                 */
+    int64_t trace_rows;       /* rows of the full trace buffer (num_ite); row index = step index  */
+    int64_t trace_chains;     /* chains of the full trace buffer (>= n_chains)                    */
+    int64_t trace_chain_off;  /* first chain of this launch inside the trace buffer               */
+    /* state, updated in place: theta[C][d], y[C][y_dim] (float32)                                */
+    float* theta;
+    float* y;
+    float* aux;               /* [C][GLABC_AUX_SLOTS] sampler-specific carried state (iSIR: cached
+                                 log-weight + `local` flag, GLMCMC.py:51-55,60-65), or NULL       */
+    float* trace;             /* NULL iff GLABC_TRACE_NONE                                        */
+    float* stats;             /* [n_chains][GLABC_NSTATS(d)], accumulated (+=); may be NULL       */
+    /* replay mode only */
+    const float* tape32;      /* [n_steps][tape_slots][n_chains] float32 draws                    */
+    const double* tape64;     /* [n_steps][n_chains] float64 draws (np.random.uniform), or NULL   */
+    float* debug;             /* [n_steps][GLABC_DEBUG_SLOTS][n_chains] per-step quantities/NULL  */
+    void* stream;
+} glabc_run_t;
+
+/* replay tape slots for run_global: U_b, eps_prop[d], eps_sim[y_dim], U_a         */
+#define GLABC_TAPE_GLOBAL_SLOTS(d, yd) (2 + (d) + (yd))
+/* replay tape slots for run_isir: U_b, eps_prop[K][d], eps_sim[K][y_dim], U_a (local); the
+ * float64 resampling uniform is in tape64                                          */
+#define GLABC_TAPE_ISIR_SLOTS(d, yd, K) (2 + (K) * ((d) + (yd)))
+/* debug slots (float32; slot 0 holds an integer value):
+ *   0 flags: bit0 global branch, bit1 state changed, bits 8.. iSIR resample index + 1 (0 = None)
+ *   GlobalMCMC / local moves: 1 log prior(theta'), 2 log kernel(y'), 3 log_acc
+ *   iSIR global move:         1 log-weight of the current state, 2 sum of the K+1 weights,
+ *                             3 normalised weight of the current state, 4+j log-weight of
+ *                             candidate j (j < K)                                                 */
+#define GLABC_DEBUG_SLOTS (4 + GLABC_MAX_K)
+
+typedef struct glabc_ctx glabc_ctx;
+
+/* ---- lifecycle --------------------------------------------------------------------------- */
+int glabc_version(void);
+/* device < 0: use the current CUDA device. Fails with GLABC_ERR_NO_DEVICE when no GPU is present. */
+int glabc_ctx_create(int device, glabc_ctx** out);
+int glabc_ctx_destroy(glabc_ctx* ctx);
+const char* glabc_last_error(const glabc_ctx* ctx);
+const char* glabc_status_string(int status);
+/* multiprocessor count, SM clock (kHz) and the library's default block size, for roofline math   */
+int glabc_device_info(const glabc_ctx* ctx, int32_t* sm_count, int32_t* clock_khz, int32_t* cc);
+
+/* ---- plugin binding ------------------------------------------------------------------------ */
+/* replaces the `ABCset` argument of every sampler (GlobalMCMC.py:6, GLMCMC.py:24, ...)           */
+int glabc_model_set(glabc_ctx* ctx, const glabc_model_t* model, size_t nbytes);
+/* replaces Local_Proposal / Global_Proposal / Importance_Proposal (GlobalMCMC.py:6-7,
+ * GLMCMC.py:24-25)                                                                               */
+int glabc_dist_set(glabc_ctx* ctx, int slot, const glabc_dist_t* dist, size_t nbytes);
+
+/* ---- samplers: device buffers, asynchronous on `stream` ------------------------------------- */
+/* GlobalMCMC loop body, GlobalMCMC.py:37-68 (local RW-MH / global independence-MH mixture)       */
+int glabc_run_global(glabc_ctx* ctx, const glabc_run_t* run);
+
+/* ---- samplers: host buffers (the reference-facing call: H2D state, run, D2H trace + stats) --- */
+/* `run->theta`, `y`, `trace`, `stats` are HOST pointers here; the trace is copied back in
+ * `chunk_steps`-row chunks overlapped with the next chunk's kernel (0 = library default).        */
+int glabc_run_global_host(glabc_ctx* ctx, const glabc_run_t* run, int64_t chunk_steps);
+
+/* ---- diagnostics --------------------------------------------------------------------------- */
+/* esjd(), ESJD.py:2-25, for every chain of a device trace: out[c] = det(D^T D/(N-1))^(1/d).
+ * layout = glabc_trace_layout of `trace` ([rows][chains][d] or [chains][rows][d]).                */
+int glabc_esjd(glabc_ctx* ctx, const float* trace, int32_t layout, int64_t rows, int64_t chains,
+               int32_t dim, float* out, void* stream);
+
+/* raw Philox4x32-10 blocks for known-answer tests: out[n][4] = philox(ctr[n][4], key[n][2])       */
+int glabc_philox_kat(glabc_ctx* ctx, const uint32_t* ctr, const uint32_t* key, int64_t n,
+                     uint32_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLABC_H */

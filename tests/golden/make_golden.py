@@ -1,0 +1,418 @@
+#!/usr/bin/env python
+"""Generate the golden vectors under tests/golden/ by RUNNING THE REFERENCE ITSELF.
+
+Runs only in the build container (needs /root/reference).  The reference has no tests and no
+golden vectors; parity is pinned by executing its own Python with
+
+  * the process-global RNG entry points it uses (torch.rand, torch.randn, np.random.uniform,
+    secrets.randbelow, torch.multinomial) wrapped so every draw is recorded ("the tape"), and
+  * the ABC model / proposal objects wrapped so every plugin call's output is recorded
+    (log prior, log kernel, simulated y, proposal log-density ...).
+
+The structured tapes + per-step records are what the C oracle (oracle/glabc_oracle.c) and the CUDA
+kernels (replay mode) must reproduce.  Usage:
+
+    python tests/golden/make_golden.py            # writes tests/golden/*.npz
+
+Nothing here is imported by the test-suite at run time; the .npz files are committed.
+"""
+import contextlib
+import io
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference"
+
+
+def import_reference():
+    for name in ("normflows", "matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.path[:0] = [REF, os.path.join(REF, "glabcmcmc", "examples")]
+    import glabcmcmc  # noqa: F401
+    for mod in ("GlobalMCMC", "GLMCMC", "GLMALA", "AGLMCMC", "GLMCMC_NFs"):
+        sys.modules["glabcmcmc." + mod].tqdm = lambda it, *a, **k: it
+    torch.set_num_threads(1)
+
+
+class Tape:
+    """Records every draw of the global RNG entry points, in call order."""
+
+    def __init__(self):
+        self.events = []  # (kind, np.ndarray)
+        self._orig = {}
+
+    def __enter__(self):
+        import secrets
+        self._orig = dict(rand=torch.rand, randn=torch.randn, uniform=np.random.uniform,
+                          randbelow=secrets.randbelow, multinomial=torch.multinomial)
+        tape = self
+
+        def rand(*a, **k):
+            out = tape._orig["rand"](*a, **k)
+            tape.events.append(("U32", out.detach().cpu().numpy().copy()))
+            return out
+
+        def randn(*a, **k):
+            out = tape._orig["randn"](*a, **k)
+            tape.events.append(("N32", out.detach().cpu().numpy().copy()))
+            return out
+
+        def uniform(*a, **k):
+            out = tape._orig["uniform"](*a, **k)
+            tape.events.append(("U64", np.asarray(out, dtype=np.float64).copy()))
+            return out
+
+        def randbelow(n):
+            out = tape._orig["randbelow"](n)
+            tape.events.append(("SEED", np.asarray(out, dtype=np.int64)))
+            return out
+
+        def multinomial(*a, **k):
+            out = tape._orig["multinomial"](*a, **k)
+            tape.events.append(("MULTI", out.detach().cpu().numpy().copy()))
+            return out
+
+        torch.rand, torch.randn, np.random.uniform = rand, randn, uniform
+        secrets.randbelow, torch.multinomial = randbelow, multinomial
+        return self
+
+    def __exit__(self, *exc):
+        import secrets
+        torch.rand, torch.randn = self._orig["rand"], self._orig["randn"]
+        np.random.uniform = self._orig["uniform"]
+        secrets.randbelow, torch.multinomial = self._orig["randbelow"], self._orig["multinomial"]
+
+
+class CallLog:
+    """Wraps an object; records (tag, method, output) of the listed methods into a shared list."""
+
+    def __init__(self, obj, tag, methods, log):
+        object.__setattr__(self, "_obj", obj)
+        object.__setattr__(self, "_tag", tag)
+        object.__setattr__(self, "_methods", set(methods))
+        object.__setattr__(self, "_log", log)
+
+    def __getattr__(self, name):
+        attr = getattr(self._obj, name)
+        if name in self._methods:
+            tag, log = self._tag, self._log
+
+            def wrapped(*a, **k):
+                out = attr(*a, **k)
+                if isinstance(out, tuple):
+                    rec = tuple(o.detach().cpu().numpy().copy() for o in out)
+                else:
+                    rec = out.detach().cpu().numpy().copy()
+                log.append((tag, name, rec))
+                return out
+
+            return wrapped
+        return attr
+
+    def __setattr__(self, name, value):
+        setattr(self._obj, name, value)
+
+
+def f32(x):
+    return np.asarray(x, dtype=np.float32)
+
+
+def model_params(model):
+    """The POD constants the way the reference evaluates them (float32 torch ops)."""
+    eps_t = torch.tensor([model.epsilon])
+    noise_ls = torch.log(torch.tensor([0.05, 0.05]).sqrt())
+    return dict(
+        epsilon=np.float64(model.epsilon),
+        y_obs=f32(model.y_obs.view(-1).numpy()),
+        noise_loc=f32([0.0, 0.0]),
+        noise_log_scale=f32(noise_ls.numpy()),
+        noise_scale=f32(torch.exp(noise_ls).numpy()),
+        prior_loc=f32([0.0, 0.0]),
+        prior_log_scale=f32([0.0, 0.0]),
+        prior_scale=f32(torch.exp(torch.tensor([0.0, 0.0])).numpy()),
+        eps_log_scale=f32(torch.log(eps_t).numpy())[0],
+        eps_scale=f32(torch.exp(torch.log(eps_t)).numpy())[0],
+    )
+
+
+def dist_params(dist, prefix):
+    ls = dist.log_scale.view(-1).float()
+    return {prefix + "_loc": f32(dist.loc.view(-1).numpy()), prefix + "_log_scale": f32(ls.numpy()),
+            prefix + "_scale": f32(torch.exp(ls).numpy())}
+
+
+def quiet():
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+# ----------------------------------------------------------------------------------------------
+# GlobalMCMC (GlobalMCMC.py:37-68)
+# ----------------------------------------------------------------------------------------------
+def golden_global(cases, T, out_path):
+    import glabcmcmc.distribution as distribution
+    from Mixture import Mixture_set
+    GlobalMCMC = sys.modules["glabcmcmc.GlobalMCMC"].GlobalMCMC
+    blobs = {}
+    for ci, case in enumerate(cases):
+        C = case["chains"]
+        model = Mixture_set(case["epsilon"])
+        lp = distribution.DiagGaussian(2, loc=torch.tensor(case["lp_loc"]).view(1, 2),
+                                       log_scale=torch.log(torch.tensor(case["lp_sigma"])))
+        gp = distribution.DiagGaussian(2, torch.tensor(case["gp_loc"]), torch.tensor(case["gp_log_scale"]))
+        gf = case["gf"]
+        tape32 = np.zeros((T - 1, 6, C), np.float32)
+        trace = np.zeros((T, C, 2), np.float32)
+        theta0s = np.zeros((C, 2), np.float32)
+        y0s = np.zeros((C, 2), np.float32)
+        # per-step records: flags, prior', kernel', log_acc, y'[2], theta'[2]
+        rec = np.zeros((T - 1, 8, C), np.float32)
+        for c in range(C):
+            torch.manual_seed(1000 * ci + c)
+            np.random.seed(1000 * ci + c)
+            theta0 = torch.tensor(case["theta0"])
+            y0 = model.generate_samples(theta0)
+            log = []
+            pm = CallLog(model, "model", ("generate_samples", "prior_log_prob", "calculate_log_kernel"), log)
+            plp = CallLog(lp, "lp", ("sample",), log)
+            pgp = CallLog(gp, "gp", ("forward", "log_prob"), log)
+            with Tape() as tape, quiet():
+                chain = GlobalMCMC(pm, T, theta0, y0, pgp, None, gf, plp)
+            ev = tape.events
+            assert len(ev) == 4 * (T - 1), len(ev)
+            theta0s[c], y0s[c] = theta0.numpy(), y0.view(-1).numpy()
+            trace[:, c] = chain.numpy()
+            li = 0
+            for s in range(T - 1):
+                u_b, n_p, n_s, u_a = ev[4 * s: 4 * s + 4]
+                assert u_b[0] == "U32" and n_p[0] == "N32" and n_s[0] == "N32" and u_a[0] == "U32"
+                tape32[s, :, c] = [u_b[1][0], n_p[1][0, 0], n_p[1][0, 1], n_s[1][0, 0], n_s[1][0, 1], u_a[1][0]]
+                is_global = bool(np.float32(u_b[1][0]) < np.float32(gf))
+                if is_global:
+                    names = [x[:2] for x in log[li:li + 8]]
+                    assert names == [("gp", "forward"), ("model", "generate_samples"), ("model", "prior_log_prob"),
+                                     ("model", "calculate_log_kernel"), ("gp", "log_prob"), ("model", "prior_log_prob"),
+                                     ("model", "calculate_log_kernel")] + names[7:], names
+                    (th_p, lq_p), y_p, pr_p, k_p, lq_o, pr_o, k_o = [x[2] for x in log[li:li + 7]]
+                    li += 7
+                    acc = np.float32(pr_p[0]) + np.float32(k_p[0])
+                    acc = acc + np.float32(lq_o[0])
+                    acc = acc - np.float32(lq_p[0])
+                    acc = acc - np.float32(pr_o[0])
+                    acc = acc - np.float32(k_o[0])
+                else:
+                    names = [x[:2] for x in log[li:li + 6]]
+                    assert names == [("lp", "sample"), ("model", "generate_samples"), ("model", "prior_log_prob"),
+                                     ("model", "calculate_log_kernel"), ("model", "prior_log_prob"),
+                                     ("model", "calculate_log_kernel")], names
+                    z, y_p, pr_p, k_p, pr_o, k_o = [x[2] for x in log[li:li + 6]]
+                    li += 6
+                    th_p = trace[s, c][None, :] + z  # recorded for information only
+                    acc = np.float32(pr_p[0]) + np.float32(k_p[0])
+                    acc = acc - np.float32(pr_o[0])
+                    acc = acc - np.float32(k_o[0])
+                accepted = bool(np.any(trace[s + 1, c] != trace[s, c]))
+                rec[s, 0, c] = int(is_global) | (int(accepted) << 1)
+                rec[s, 1, c], rec[s, 2, c], rec[s, 3, c] = pr_p[0], k_p[0], acc
+                rec[s, 4:6, c] = np.asarray(y_p).reshape(-1)
+                rec[s, 6:8, c] = np.asarray(th_p).reshape(-1)
+            assert li == len(log)
+        blob = dict(tape32=tape32, trace=trace, theta0=theta0s, y0=y0s, rec=rec, gf=np.float64(gf), T=np.int64(T))
+        blob.update(model_params(model))
+        blob.update(dist_params(lp, "lp"))
+        blob.update(dist_params(gp, "gp"))
+        for k, v in blob.items():
+            blobs[f"case{ci}/{k}"] = v
+        print(f"global case {ci}: gf={gf} eps={case['epsilon']} accept rate "
+              f"{np.mean((rec[:, 0] .astype(int) >> 1) & 1):.4f}")
+    blobs["n_cases"] = np.int64(len(cases))
+    np.savez_compressed(out_path, **blobs)
+
+
+# ----------------------------------------------------------------------------------------------
+# GLMCMC (GLMCMC.py:58-104)
+# ----------------------------------------------------------------------------------------------
+def golden_isir(cases, T, out_path):
+    import glabcmcmc.distribution as distribution
+    from Mixture import Mixture_set
+    GLMCMC = sys.modules["glabcmcmc.GLMCMC"].GLMCMC
+    blobs = {}
+    for ci, case in enumerate(cases):
+        C, K = case["chains"], case["K"]
+        model = Mixture_set(case["epsilon"])
+        lp = distribution.DiagGaussian(2, loc=torch.tensor(case["lp_loc"]).view(1, 2),
+                                       log_scale=torch.log(torch.tensor(case["lp_sigma"])))
+        ip = distribution.DiagGaussian(2, torch.tensor(case["ip_loc"]), torch.tensor(case["ip_log_scale"]))
+        gf = case["gf"]
+        slots = 2 + 4 * K
+        tape32 = np.zeros((T - 1, slots, C), np.float32)
+        tape64 = np.zeros((T - 1, C), np.float64)
+        trace = np.zeros((T, C, 2), np.float32)
+        theta0s = np.zeros((C, 2), np.float32)
+        y0s = np.zeros((C, 2), np.float32)
+        # flags, (lw_old | prior'), (S | kernel'), (w0 | log_acc), lw_1..K
+        rec = np.zeros((T - 1, 4 + K, C), np.float32)
+        for c in range(C):
+            torch.manual_seed(5000 + 1000 * ci + c)
+            np.random.seed(5000 + 1000 * ci + c)
+            theta0 = torch.tensor(case["theta0"])
+            y0 = model.generate_samples(theta0)
+            log = []
+            pm = CallLog(model, "model", ("generate_samples", "prior_log_prob", "calculate_log_kernel"), log)
+            plp = CallLog(lp, "lp", ("sample",), log)
+            pip = CallLog(ip, "ip", ("forward", "log_prob"), log)
+            with Tape() as tape, quiet():
+                chain = GLMCMC(pm, T, theta0, y0, plp, None, gf, pip, K)
+            ev = tape.events
+            assert len(ev) == 4 * (T - 1), len(ev)
+            theta0s[c], y0s[c] = theta0.numpy(), y0.view(-1).numpy()
+            trace[:, c] = chain.numpy()
+            li = 3  # initial log_weight_old: calculate_log_kernel, prior_log_prob, ip.log_prob (GLMCMC.py:52-55)
+            assert [x[:2] for x in log[:3]] == [("model", "calculate_log_kernel"), ("model", "prior_log_prob"), ("ip", "log_prob")]
+            lw_old = np.float32(log[1][2][0]) + np.float32(log[0][2][0]) - np.float32(log[2][2][0])
+            local = True
+            for s in range(T - 1):
+                e0, e1, e2, e3 = ev[4 * s: 4 * s + 4]
+                assert e0[0] == "U32" and e1[0] == "N32" and e2[0] == "N32"
+                u_b = np.float32(e0[1][0])
+                is_global = bool(u_b < np.float32(gf))
+                tape32[s, 0, c] = u_b
+                changed = bool(np.any(trace[s + 1, c] != trace[s, c]))
+                if is_global:
+                    assert e3[0] == "U64" and e1[1].shape == (K, 2)
+                    tape32[s, 1:1 + 2 * K, c] = e1[1].reshape(-1)
+                    tape32[s, 1 + 2 * K:1 + 4 * K, c] = e2[1].reshape(-1)
+                    tape64[s, c] = e3[1]
+                    if local:
+                        names = [x[:2] for x in log[li:li + 3]]
+                        assert names == [("model", "calculate_log_kernel"), ("model", "prior_log_prob"), ("ip", "log_prob")], names
+                        lw_old = np.float32(log[li + 1][2][0]) + np.float32(log[li][2][0]) - np.float32(log[li + 2][2][0])
+                        li += 3
+                    local = False
+                    names = [x[:2] for x in log[li:li + 4]]
+                    assert names == [("ip", "forward"), ("model", "generate_samples"), ("model", "calculate_log_kernel"),
+                                     ("model", "prior_log_prob")], names
+                    (th, lq), x, kern, prior = [v[2] for v in log[li:li + 4]]
+                    li += 4
+                    lw = (prior.astype(np.float32) + kern.astype(np.float32)) - lq.astype(np.float32)
+                    allw = np.concatenate([[lw_old], lw]).astype(np.float32)
+                    w = torch.exp(torch.from_numpy(allw))
+                    w[torch.isnan(w)] = 0.0
+                    S = torch.sum(w)
+                    wn = (w / S).numpy()
+                    # replicate weight_sampling to learn the index the reference drew
+                    ind, sw = None, 0.0
+                    for j in range(K + 1):
+                        sw += float(wn[j])
+                        if float(e3[1]) < sw:
+                            ind = j
+                            break
+                    rec[s, 1, c], rec[s, 2, c], rec[s, 3, c] = lw_old, S.item(), wn[0]
+                    rec[s, 4:4 + K, c] = lw
+                    if ind is not None and ind != 0:
+                        assert changed or np.all(th[ind - 1] == trace[s, c]), (s, c)
+                        assert np.all(th[ind - 1] == trace[s + 1, c])
+                        lw_old = lw[ind - 1]
+                    else:
+                        assert not changed
+                    rec[s, 0, c] = 1 | (int(changed) << 1) | ((0 if ind is None else ind + 1) << 8)
+                else:
+                    assert e3[0] == "U32"
+                    tape32[s, 1:3, c] = e1[1].reshape(-1)
+                    tape32[s, 1 + 2 * K:3 + 2 * K, c] = e2[1].reshape(-1)
+                    tape32[s, 1 + 4 * K, c] = e3[1][0]
+                    names = [x[:2] for x in log[li:li + 7]]
+                    assert names == [("lp", "sample"), ("model", "prior_log_prob"), ("model", "generate_samples"),
+                                     ("model", "prior_log_prob"), ("model", "calculate_log_kernel"),
+                                     ("model", "prior_log_prob"), ("model", "calculate_log_kernel")], names
+                    _, _, y_p, pr_p, k_p, pr_o, k_o = [v[2] for v in log[li:li + 7]]
+                    li += 7
+                    acc = np.float32(pr_p[0]) + np.float32(k_p[0])
+                    acc = acc - np.float32(pr_o[0])
+                    acc = acc - np.float32(k_o[0])
+                    if changed:
+                        local = True
+                    rec[s, 0, c] = (int(changed) << 1)
+                    rec[s, 1, c], rec[s, 2, c], rec[s, 3, c] = pr_p[0], k_p[0], acc
+            assert li == len(log), (li, len(log))
+        blob = dict(tape32=tape32, tape64=tape64, trace=trace, theta0=theta0s, y0=y0s, rec=rec,
+                    gf=np.float64(gf), T=np.int64(T), K=np.int64(K))
+        blob.update(model_params(model))
+        blob.update(dist_params(lp, "lp"))
+        blob.update(dist_params(ip, "ip"))
+        for k, v in blob.items():
+            blobs[f"case{ci}/{k}"] = v
+        fl = rec[:, 0].astype(int)
+        print(f"isir case {ci}: gf={gf} K={K} move rate {np.mean((fl >> 1) & 1):.4f} "
+              f"None-rate {np.mean(((fl & 1) == 1) & ((fl >> 8) == 0)):.4f}")
+    blobs["n_cases"] = np.int64(len(cases))
+    np.savez_compressed(out_path, **blobs)
+
+
+# ----------------------------------------------------------------------------------------------
+# esjd (ESJD.py) and the distribution classes (distribution.py) — small deterministic fixtures
+# ----------------------------------------------------------------------------------------------
+def golden_misc(out_path):
+    import glabcmcmc.distribution as distribution
+    from glabcmcmc.ESJD import esjd
+    g = torch.Generator().manual_seed(7)
+    blobs = {}
+    chains = torch.cumsum(torch.randn(6, 400, 2, generator=g) * (torch.rand(6, 400, 1, generator=g) < 0.1), dim=1)
+    blobs["esjd/chains"] = chains.numpy()
+    blobs["esjd/values"] = np.stack([esjd(chains[i]) for i in range(6)])
+    z = torch.randn(64, 2, generator=g) * 2
+    dg = distribution.DiagGaussian(2, torch.tensor([0.3, -0.2]), torch.log(torch.tensor([0.35, 1.7])))
+    blobs["diag/z"], blobs["diag/log_prob"] = z.numpy(), dg.log_prob(z).numpy()
+    blobs["diag/loc"], blobs["diag/log_scale"] = dg.loc.numpy(), dg.log_scale.numpy()
+    with Tape() as tape:
+        torch.manual_seed(3)
+        zz, lp = dg.forward(32)
+    blobs["diag/fwd_eps"], blobs["diag/fwd_z"], blobs["diag/fwd_log_p"] = tape.events[0][1], zz.numpy(), lp.numpy()
+    un = distribution.Uniform(2, torch.tensor([-2.0, -1.0]), torch.tensor([2.0, 3.0]))
+    zu = torch.randn(64, 2, generator=g) * 2
+    blobs["uniform/z"], blobs["uniform/log_prob"] = zu.numpy(), un.log_prob(zu).numpy()
+    blobs["uniform/low"], blobs["uniform/high"] = un.low.numpy(), un.high.numpy()
+    ga = distribution.Gamma(torch.tensor([2.0, 3.5]), torch.tensor([1.5, 0.7]))
+    zg = torch.rand(64, 2, generator=g, dtype=torch.float64) * 6 - 0.5
+    blobs["gamma/z"], blobs["gamma/log_prob"] = zg.numpy(), ga.log_prob(zg).numpy()
+    blobs["gamma/shape"], blobs["gamma/rate"] = ga.Shape, ga.Rate
+    gm = distribution.GaussianMixture(3, 2, loc=[[0.0, 1.0], [2.0, -1.0], [-2.0, 0.5]],
+                                      scale=[[0.5, 0.5], [1.0, 0.3], [0.2, 2.0]], weights=[0.2, 0.5, 0.3])
+    zm = torch.randn(64, 2, generator=g, dtype=torch.float64) * 2
+    blobs["mix/z"], blobs["mix/log_prob"] = zm.numpy(), gm.log_prob(zm).detach().numpy()
+    blobs["mix/loc"], blobs["mix/log_scale"] = gm.loc.detach().numpy()[0], gm.log_scale.detach().numpy()[0]
+    blobs["mix/weight_scores"] = gm.weight_scores.detach().numpy()[0]
+    np.savez_compressed(out_path, **blobs)
+
+
+def main():
+    import_reference()
+    base = dict(chains=4, epsilon=0.05, theta0=[0.0, 0.0], lp_loc=[0.0, 0.0], lp_sigma=[0.35, 0.35],
+                gp_loc=[0.0, 0.0], gp_log_scale=[0.0, 0.0])
+    cases = [
+        dict(base, chains=8, gf=0.5),                                   # README / config 1-2
+        dict(base, gf=0.0),                                             # never global
+        dict(base, gf=1.0),                                             # always global
+        dict(base, gf=0.3, epsilon=0.2, theta0=[1.2, -1.4], lp_sigma=[0.2, 0.5],
+             gp_loc=[0.5, -0.25], gp_log_scale=[0.4, 0.2], lp_loc=[0.01, -0.02]),
+    ]
+    golden_global(cases, 1500, os.path.join(HERE, "global_mcmc.npz"))
+    ibase = dict(chains=4, epsilon=0.05, theta0=[0.0, 0.0], lp_loc=[0.0, 0.0], lp_sigma=[0.35, 0.35],
+                 ip_loc=[0.0, 0.0], ip_log_scale=[0.0, 0.0])
+    icases = [
+        dict(ibase, chains=8, gf=0.9, K=5),                             # Mixture.py:73 / config 3
+        dict(ibase, gf=1.0, K=3),
+        dict(ibase, gf=0.5, K=8),
+        dict(ibase, gf=0.7, K=12, epsilon=0.2, theta0=[1.2, -1.4], ip_loc=[0.5, -0.25], ip_log_scale=[0.4, 0.2]),
+    ]
+    golden_isir(icases, 1200, os.path.join(HERE, "glmcmc.npz"))
+    golden_misc(os.path.join(HERE, "misc.npz"))
+
+
+if __name__ == "__main__":
+    main()
