@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""Headline benchmark: ABC-MCMC chain-steps/s of the fused GlobalMCMC step kernel on the README
+Mixture_set workload (BASELINE.json configs[1]: 65,536 independent chains x 1e4 iterations per GPU,
+gf=0.5, local sigma 0.35, global N(0,I), epsilon 0.05), full float32 trace written.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]           # this repo's CUDA path
+  python bench.py --impl reference [...]                          # the CPU port of the reference path
+
+One "step" = one pass of the hot path over the whole batch (C chains x (T-1) transitions).  Prints
+ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALG_INST_PER_STEP = 186      # thread-instructions per chain-step (Philox4x32-10 + Box-Muller floor)
+ALG_BYTES_PER_STEP = 8       # one float32 trace row of d=2
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="native", choices=["native", "reference"])
+    p.add_argument("--chains", type=int, default=65536, help="chains per GPU (weak scaling)")
+    p.add_argument("--iters", type=int, default=10000, help="num_ite per chain (trace rows)")
+    p.add_argument("--layout", default="chain", choices=["chain", "time", "none"])
+    p.add_argument("--block", type=int, default=0)
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-cpu", action="store_true")
+    p.add_argument("--cpu-seconds", type=float, default=12.0)
+    return p.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        med = sm[len(sm) // 2] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def workload_objects():
+    import torch
+    import glabc_b200 as g
+    model = g.Mixture_set(0.05)
+    lp = g.DiagGaussian(2, torch.zeros(1, 2), torch.log(torch.tensor([0.35, 0.35])))   # README.md:120
+    gp = g.DiagGaussian(2, torch.tensor([0.0, 0.0]), torch.tensor([0.0, 0.0]))
+    return model, lp, gp
+
+
+def cpu_port_rate(chains, iters, seconds, threads=0):
+    """The oracle (C restatement of GlobalMCMC.py:37-68, native Philox mode) on the host cores, on a
+    bounded sample of the workload sized to ~`seconds` of wall time.  Returns (steps/s, cores, sample)."""
+    import numpy as np
+    from glabc_b200 import _abi as abi
+    from glabc_b200.models import lower_model, lower_proposal
+    from oracle import oracle
+    model, lp, gp = workload_objects()
+    mp, lpp, gpp = lower_model(model), lower_proposal(lp), lower_proposal(gp)
+    oracle.lib().oracle_set_num_threads(threads)
+    cores = oracle.lib().oracle_num_threads()
+
+    def run(c, t):
+        theta = np.zeros((c, 2), np.float32)
+        y = (np.random.default_rng(0).standard_normal((c, 2)) * 0.2236).astype(np.float32)
+        trace = np.zeros((c, t + 1, 2), np.float32)
+        t0 = time.perf_counter()
+        oracle.run("global", mp, lpp, gpp, theta=theta, y=y, n_steps=t, gf=0.5, seed=0, trace=trace,
+                   trace_layout=abi.TRACE_CHAIN_MAJOR, threads=threads)
+        return time.perf_counter() - t0
+
+    c = max(cores * 8, 64)
+    dt = run(c, 2000)                       # calibration
+    rate = c * 2000 / dt
+    t = min(iters - 1, 9999)
+    c = int(max(cores, min(chains, rate * seconds / t)))
+    dt = run(c, t)
+    return c * t / dt, cores, f"{c} chains x {t} transitions of the same workload, full trace in host memory, {dt:.1f} s"
+
+
+def bench_reference(a, rank):
+    if rank != 0:
+        return
+    rates = []
+    sample = ""
+    per_step = max(2.0, min(a.cpu_seconds, 120.0 / max(1, a.steps + a.warmup)))
+    for i in range(a.warmup + a.steps):
+        r, cores, sample = cpu_port_rate(a.chains, a.iters, per_step)
+        if i >= a.warmup:
+            rates.append(r)
+    value = sum(rates) / len(rates)
+    line = {"impl": "reference", "metric": "abc_mcmc_chain_steps_per_sec", "value": value, "unit": "chain-steps/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": None, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(a),
+            "cpu_baseline": {"value": value, "unit": "chain-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(a):
+    return {"workload": "README Mixture_set GlobalMCMC (BASELINE configs[1])", "chains_per_gpu": a.chains,
+            "iterations": a.iters, "theta_dim": 2, "epsilon": 0.05, "global_frequency": 0.5,
+            "local_sigma": 0.35, "global_proposal": "N(0,I)", "trace": {"chain": "full float32 [C,T,2]",
+            "time": "full float32 [T,C,2]", "none": "statistics only"}[a.layout], "rng": "philox4x32-10 native",
+            "arith": "fast", "l2": "no re-read inputs; 5.2 GB trace written per step >> 126 MB L2",
+            "parallelism": f"chains sharded over {a.gpus} GPU(s), no data-path collective"}
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        bench_reference(a, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import glabc_b200 as g  # noqa: F401
+    from glabc_b200 import _abi as abi
+    from glabc_b200 import sharding
+    from glabc_b200.engine import RunStats, get_engine
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    eng = get_engine()
+    model, lp, gp = workload_objects()
+    eng.bind_model(model)
+    eng.bind_proposal(abi.SLOT_LOCAL, lp)
+    eng.bind_proposal(abi.SLOT_GLOBAL, gp)
+    info = eng.ctx.device_info()
+
+    C, T, d = a.chains, a.iters, 2
+    layout = {"chain": abi.TRACE_CHAIN_MAJOR, "time": abi.TRACE_TIME_MAJOR, "none": abi.TRACE_NONE}[a.layout]
+    chain_base = rank * C
+    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    theta0 = torch.zeros(C, d, device="cuda")
+    y0 = torch.randn(C, d, device="cuda", generator=gen) * 0.22360679507255554
+    trace = None
+    if layout != abi.TRACE_NONE:
+        trace = torch.empty((C, T, d) if layout == abi.TRACE_CHAIN_MAJOR else (T, C, d), device="cuda")
+    theta, y = theta0.clone(), y0.clone()
+    stats = torch.zeros(C, abi.nstats(d), device="cuda")
+    summary = None
+
+    def one_step(step_idx):
+        nonlocal summary
+        theta.copy_(theta0)
+        y.copy_(y0)
+        stats.zero_()
+        eng.run("global", theta=theta, y=y, n_steps=T - 1, gf=0.5, seed=step_idx, chain_id_base=chain_base,
+                trace_layout=layout, trace=trace, trace_rows=T, stats=stats, block_threads=a.block)
+        rs = RunStats(stats, d)
+        summary = sharding.allreduce_summary(sharding.summarize(rs))   # NCCL only for N > 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for w in range(a.warmup):
+        one_step(w)
+    # kernel-only duration of the dominant kernel, CUDA events on the launching stream
+    barrier()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = []
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(a.steps):
+        one_step(a.warmup + s)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    steps_per_pass = C * (T - 1) * world
+    value = steps_per_pass * a.steps / (total_ms * 1e-3)
+
+    # the step kernel alone (no state reset / summary kernels around it)
+    for s in range(a.steps):
+        theta.copy_(theta0)
+        y.copy_(y0)
+        k0.record()
+        eng.run("global", theta=theta, y=y, n_steps=T - 1, gf=0.5, seed=s, chain_id_base=chain_base,
+                trace_layout=layout, trace=trace, trace_rows=T, stats=stats, block_threads=a.block)
+        k1.record()
+        torch.cuda.synchronize()
+        kernel_ms.append(k0.elapsed_time(k1))
+    kms = sum(kernel_ms) / len(kernel_ms)
+    kernel_rate = C * (T - 1) / (kms * 1e-3)
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    sm_max_mhz = float(peaks.get("sm_max_mhz", clocks.get("sm_max_mhz") or 1965.0))
+    inst_peak = info["sm_count"] * 128 * sm_max_mhz * 1e6 / 1e9            # G thread-inst/s at max clock
+    inst_ach = kernel_rate * ALG_INST_PER_STEP / 1e9
+    hbm_ach = kernel_rate * ALG_BYTES_PER_STEP / 1e9 if layout != abi.TRACE_NONE else 0.0
+    roofline = {"bound": "alu-issue", "achieved": inst_ach, "peak": inst_peak, "unit": "Gthread-inst/s",
+                "frac": inst_ach / inst_peak, "traffic": None,
+                "note": f"{ALG_INST_PER_STEP} algorithmic thread-instructions per chain-step (SURVEY.md 8(d)); peak = "
+                        f"{info['sm_count']} SMs x 128 lanes x {sm_max_mhz:.0f} MHz; kernel {kms:.3f} ms per launch",
+                "hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+                "kernel_ms": kms, "kernel_chain_steps_per_sec": kernel_rate}
+
+    line = {"metric": "abc_mcmc_chain_steps_per_sec", "value": value, "unit": "chain-steps/s", "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": total_ms / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a),
+            "clocks": clocks, "gpu_launches": a.steps, "roofline": roofline}
+    if summary is not None:
+        desc = sharding.describe(summary.cpu(), d)
+        line["esjd"] = {"mean_per_chain": desc["mean_esjd"], "aggregate_esjd_per_sec": desc["mean_esjd"] * value,
+                        "move_rate": desc["move_rate"]}
+
+    # end-to-end through the reference-facing call with HOST buffers (pinned): H2D state, kernels in time
+    # chunks, D2H of the full trace overlapped, D2H state + stats — every step.
+    if not a.no_e2e:
+        e_steps = max(1, min(a.steps, 3))
+        h_theta0, h_y0 = theta0.cpu().pin_memory(), y0.cpu().pin_memory()
+        h_theta, h_y = torch.empty_like(h_theta0).pin_memory(), torch.empty_like(h_y0).pin_memory()
+        h_stats = torch.zeros(C, abi.nstats(d)).pin_memory()
+        h_layout = abi.TRACE_TIME_MAJOR if layout != abi.TRACE_NONE else abi.TRACE_NONE
+        del trace
+        torch.cuda.empty_cache()
+        h_trace = torch.empty((T, C, d)).pin_memory() if h_layout != abi.TRACE_NONE else None
+
+        def e2e_step(i):
+            h_theta.copy_(h_theta0)
+            h_y.copy_(h_y0)
+            h_stats.zero_()
+            eng.run_host("global", theta=h_theta, y=h_y, n_steps=T - 1, gf=0.5, seed=i, chain_id_base=chain_base,
+                         trace=h_trace, trace_layout=h_layout, stats=h_stats, block_threads=a.block)
+        e2e_step(0)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e_steps):
+            e2e_step(1 + i)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        h2d = (h_theta.numel() + h_y.numel() + h_stats.numel()) * 4
+        d2h = h2d + (h_trace.numel() * 4 if h_trace is not None else 0)
+        line["e2e"] = {"value": steps_per_pass * e_steps / float(dt.item()), "unit": "chain-steps/s",
+                       "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e_steps,
+                       "note": "glabc_run_global_host: pinned host buffers, full trace copied back in time chunks "
+                               "overlapped with the kernels; host view [T,C,2] (chain c = trace[:, c])"}
+
+    if rank == 0 and not a.no_cpu:
+        r, cores, sample = cpu_port_rate(C, T, a.cpu_seconds)
+        line["cpu_baseline"] = {"value": r, "unit": "chain-steps/s", "cores": cores, "kind": "port", "sample": sample}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,22 @@
+"""MCMCRunner — the façade of reference glabcmcmc/MCMCRunner.py:6-121: joins `output_dir` and
+forwards the positional arguments to the sampler functions.  Extra keyword arguments (num_chains,
+seed, ...) are forwarded to the fused samplers."""
+import os
+
+
+class MCMCRunner:
+    def __init__(self, abc_set, output_dir="./"):
+        self.abc_set = abc_set
+        self.output_dir = output_dir
+        os.makedirs(output_dir, exist_ok=True)
+
+    def _path(self, output_file):
+        return None if output_file is None else os.path.join(self.output_dir, output_file)
+
+    def run_global_mcmc(self, num_iterations, initial_theta, initial_y, global_frequency, local_proposal,
+                        global_proposal, output_file="global_mcmc_results.csv", **kw):
+        """reference MCMCRunner.py:17-33"""
+        from .GlobalMCMC import GlobalMCMC
+        return GlobalMCMC(ABCset=self.abc_set, num_ite=num_iterations, Initial_theta=initial_theta,
+                          Initial_y=initial_y, Global_Proposal=global_proposal, filelocation=self._path(output_file),
+                          global_frequency=global_frequency, Local_Proposal=local_proposal, **kw)

@@ -65,9 +65,10 @@ class RunPOD(C.Structure):
                 ("write_row0", C.c_int32), ("block_threads", C.c_int32), ("n_candidates", C.c_int32),
                 ("num_grad", C.c_int32), ("tau", C.c_float),
                 ("trace_rows", C.c_int64), ("trace_chains", C.c_int64), ("trace_chain_off", C.c_int64),
+                ("trace_row_base", C.c_int64),
                 ("theta", C.c_void_p), ("y", C.c_void_p), ("aux", C.c_void_p), ("trace", C.c_void_p),
                 ("stats", C.c_void_p), ("tape32", C.c_void_p), ("tape64", C.c_void_p), ("debug", C.c_void_p),
-                ("stream", C.c_void_p)]
+                ("tape_dump", C.c_void_p), ("stream", C.c_void_p)]
 
 
 def fill(arr, values):

@@ -1,0 +1,66 @@
+"""In-tree build of the CUDA extension: nvcc -> gl-abc-mcmc_b200/csrc/libglabc.so (sm_100a only).
+
+The .so is git-ignored but travels to the GPU box with the repo snapshot; nothing is JIT-compiled
+at import time.  `python -m gl-abc-mcmc_b200.build` is not spellable (hyphen), use
+`python -c "import __graft_entry__ as g; g.build()"`.
+"""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+ROOT = os.path.dirname(HERE)
+SOURCES = ["abi.cu", "step_global.cu", "diag.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xptxas", "-v",
+              "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "include")]
+LIB = os.path.join(CSRC, "libglabc.so")
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _deps():
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))] + \
+           [os.path.join(ROOT, "include", "glabc.h")]
+
+
+def build(force=False, verbose=False):
+    newest = max(os.path.getmtime(p) for p in _deps())
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest:
+        return LIB
+    nvcc = _nvcc()
+    logs = {}
+
+    def compile_one(src):
+        obj = os.path.join(CSRC, src[:-3] + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        p = subprocess.run(cmd, capture_output=True, text=True)
+        logs[src] = p.stderr + p.stdout
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{logs[src]}")
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    # -cudart static (nvcc default): the library loads on a box without a GPU or libcudart.so
+    p = subprocess.run([nvcc, "-shared", "-o", LIB, *objs, "-Xcompiler", "-fvisibility=hidden"], capture_output=True, text=True)
+    if p.returncode != 0:
+        raise RuntimeError("link failed:\n" + p.stderr)
+    with open(os.path.join(CSRC, "ptxas.log"), "w") as f:
+        for src in SOURCES:
+            f.write(f"==== {src}\n{logs[src]}\n")
+    if verbose:
+        for src in SOURCES:
+            sys.stderr.write(logs[src])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

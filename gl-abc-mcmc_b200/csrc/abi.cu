@@ -1,0 +1,463 @@
+// The C-ABI of include/glabc.h: context, plugin binding, argument validation, the device and
+// host-buffer sampler entry points.  No torch, no C++ types across the boundary.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "launch.cuh"
+
+using namespace glabc;
+
+struct glabc_ctx {
+    int device = 0;
+    int sm_count = 0, clock_khz = 0, cc = 0;
+    std::string err;
+    glabc_model_t model{};
+    bool has_model = false;
+    glabc_dist_t dist[GLABC_SLOT_COUNT]{};
+    bool has_dist[GLABC_SLOT_COUNT] = {false, false, false};
+    // scratch of the host-buffer entry points
+    float* d_state = nullptr;  // theta | y | aux | stats
+    size_t state_cap = 0;
+    float* d_trace[2] = {nullptr, nullptr};
+    size_t trace_cap = 0;
+    cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+};
+
+static int fail(glabc_ctx* ctx, int status, const char* fmt, ...)
+{
+    if (ctx) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        ctx->err = buf;
+    }
+    return status;
+}
+
+#define CUDA_TRY(ctx, expr)                                                                         \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail((ctx), GLABC_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_));   \
+    } while (0)
+
+extern "C" {
+
+int glabc_version(void) { return GLABC_ABI_VERSION; }
+
+const char* glabc_status_string(int status)
+{
+    switch (status) {
+    case GLABC_OK: return "ok";
+    case GLABC_ERR_INVALID: return "invalid argument";
+    case GLABC_ERR_UNSUPPORTED: return "model family / distribution / dimension not fused";
+    case GLABC_ERR_CUDA: return "CUDA runtime error";
+    case GLABC_ERR_NO_DEVICE: return "no usable CUDA device";
+    default: return "unknown status";
+    }
+}
+
+int glabc_ctx_create(int device, glabc_ctx** out)
+{
+    if (!out) return GLABC_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        (void)cudaGetLastError();
+        return GLABC_ERR_NO_DEVICE;
+    }
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return GLABC_ERR_NO_DEVICE;
+    if (device >= n) return GLABC_ERR_INVALID;
+    glabc_ctx* ctx = new (std::nothrow) glabc_ctx();
+    if (!ctx) return GLABC_ERR_INVALID;
+    ctx->device = device;
+    int major = 0, minor = 0;
+    if (cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
+        cudaDeviceGetAttribute(&ctx->clock_khz, cudaDevAttrClockRate, device) != cudaSuccess ||
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess ||
+        cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device) != cudaSuccess) {
+        delete ctx;
+        return GLABC_ERR_CUDA;
+    }
+    ctx->cc = major * 10 + minor;
+    *out = ctx;
+    return GLABC_OK;
+}
+
+int glabc_ctx_destroy(glabc_ctx* ctx)
+{
+    if (!ctx) return GLABC_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->d_state) cudaFree(ctx->d_state);
+    for (int b = 0; b < 2; ++b) {
+        if (ctx->d_trace[b]) cudaFree(ctx->d_trace[b]);
+        if (ctx->ev_done[b]) cudaEventDestroy(ctx->ev_done[b]);
+        if (ctx->ev_free[b]) cudaEventDestroy(ctx->ev_free[b]);
+    }
+    if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
+    if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
+    delete ctx;
+    return GLABC_OK;
+}
+
+const char* glabc_last_error(const glabc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int glabc_device_info(const glabc_ctx* ctx, int32_t* sm_count, int32_t* clock_khz, int32_t* cc)
+{
+    if (!ctx) return GLABC_ERR_INVALID;
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (clock_khz) *clock_khz = ctx->clock_khz;
+    if (cc) *cc = ctx->cc;
+    return GLABC_OK;
+}
+
+int glabc_model_set(glabc_ctx* ctx, const glabc_model_t* model, size_t nbytes)
+{
+    if (!ctx) return GLABC_ERR_INVALID;
+    if (!model || nbytes != sizeof(glabc_model_t))
+        return fail(ctx, GLABC_ERR_INVALID, "glabc_model_set: struct size %zu, expected %zu (ABI mismatch)", nbytes,
+                    sizeof(glabc_model_t));
+    if (model->family != GLABC_MODEL_ABS_NORMAL && model->family != GLABC_MODEL_ID_NORMAL)
+        return fail(ctx, GLABC_ERR_UNSUPPORTED, "model family %d is not fused", model->family);
+    if (model->theta_dim < 1 || model->theta_dim > 4 || model->y_dim != model->theta_dim)
+        return fail(ctx, GLABC_ERR_UNSUPPORTED, "theta_dim=%d y_dim=%d: fused kernels exist for theta_dim == y_dim in 1..4",
+                    model->theta_dim, model->y_dim);
+    if (!(model->eps_scale > 0.0f)) return fail(ctx, GLABC_ERR_INVALID, "epsilon must be positive");
+    for (int i = 0; i < model->theta_dim; ++i)
+        if (!(model->prior_scale[i] > 0.0f)) return fail(ctx, GLABC_ERR_INVALID, "prior scale must be positive");
+    ctx->model = *model;
+    ctx->has_model = true;
+    return GLABC_OK;
+}
+
+int glabc_dist_set(glabc_ctx* ctx, int slot, const glabc_dist_t* dist, size_t nbytes)
+{
+    if (!ctx) return GLABC_ERR_INVALID;
+    if (slot < 0 || slot >= GLABC_SLOT_COUNT) return fail(ctx, GLABC_ERR_INVALID, "bad proposal slot %d", slot);
+    if (!dist || nbytes != sizeof(glabc_dist_t))
+        return fail(ctx, GLABC_ERR_INVALID, "glabc_dist_set: struct size %zu, expected %zu (ABI mismatch)", nbytes,
+                    sizeof(glabc_dist_t));
+    if (dist->kind != GLABC_DIST_DIAG_GAUSSIAN)
+        return fail(ctx, GLABC_ERR_UNSUPPORTED, "distribution kind %d is not fused as a proposal (DiagGaussian is)", dist->kind);
+    if (dist->dim < 1 || dist->dim > 4) return fail(ctx, GLABC_ERR_UNSUPPORTED, "proposal dim %d outside 1..4", dist->dim);
+    for (int i = 0; i < dist->dim; ++i)
+        if (!(dist->c[i] > 0.0f)) return fail(ctx, GLABC_ERR_INVALID, "proposal scale must be positive");
+    ctx->dist[slot] = *dist;
+    ctx->has_dist[slot] = true;
+    return GLABC_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// lowering of the PODs to kernel constants
+// ---------------------------------------------------------------------------------------------
+static float half_log_2pi(int d) { return static_cast<float>(-0.5 * d * std::log(2.0 * M_PI)); }
+
+static GaussConsts make_gauss(const float* loc, const float* log_scale, const float* scale, int d)
+{
+    GaussConsts g{};
+    double sum_ls = 0.0;
+    for (int i = 0; i < d; ++i) {
+        g.loc[i] = loc[i];
+        g.log_scale[i] = log_scale[i];
+        g.scale[i] = scale[i];
+        g.inv_scale[i] = 1.0f / scale[i];
+        g.nloc_inv[i] = -loc[i] / scale[i];
+        sum_ls += log_scale[i];
+    }
+    g.c = half_log_2pi(d);
+    g.c_fast = static_cast<float>(static_cast<double>(g.c) - sum_ls);
+    return g;
+}
+
+static ModelConsts make_model(const glabc_model_t& m)
+{
+    ModelConsts k{};
+    k.family = m.family;
+    for (int i = 0; i < m.y_dim; ++i) {
+        k.y_obs[i] = m.y_obs[i];
+        k.noise_loc[i] = m.noise_loc[i];
+        k.noise_scale[i] = m.noise_scale[i];
+    }
+    k.eps_log_scale = m.eps_log_scale;
+    k.eps_scale = m.eps_scale;
+    k.c_kern = half_log_2pi(1);
+    k.kern_fast_c = k.c_kern - m.eps_log_scale;
+    k.kern_fast_m = static_cast<float>(-0.5 / (static_cast<double>(m.eps_scale) * m.eps_scale));
+    k.prior = make_gauss(m.prior_loc, m.prior_log_scale, m.prior_scale, m.theta_dim);
+    return k;
+}
+
+static uint32_t gf_threshold(float gf)
+{
+    // u = k * 2^-24 (k < 2^24);  u < gf  <=>  k < ceil(gf * 2^24)   (float32 compare)
+    if (!(gf > 0.0f)) return 0u;
+    if (gf >= 1.0f) return 1u << 24;
+    return static_cast<uint32_t>(std::ceil(static_cast<double>(gf) * 16777216.0));
+}
+
+static int make_run_params(glabc_ctx* ctx, const glabc_run_t* run, int dim, int tape_slots, RunParams* out, int* block)
+{
+    if (!run) return fail(ctx, GLABC_ERR_INVALID, "null run description");
+    if (run->n_chains < 0 || run->n_chains > INT32_MAX) return fail(ctx, GLABC_ERR_INVALID, "n_chains out of range");
+    if (run->n_steps < 0 || run->step_base < 0 || run->step_base + run->n_steps >= 0xFFFFFFF0ll)
+        return fail(ctx, GLABC_ERR_INVALID, "step_base + n_steps must stay below 2^32 (Philox block counter)");
+    if (!run->theta || !run->y) return fail(ctx, GLABC_ERR_INVALID, "theta / y state pointers are required");
+    if (run->trace_layout < GLABC_TRACE_NONE || run->trace_layout > GLABC_TRACE_CHAIN_MAJOR)
+        return fail(ctx, GLABC_ERR_INVALID, "bad trace_layout %d", run->trace_layout);
+    if (run->trace_layout != GLABC_TRACE_NONE) {
+        if (!run->trace) return fail(ctx, GLABC_ERR_INVALID, "trace pointer required for this trace_layout");
+        const int64_t lo = run->step_base + (run->write_row0 ? 0 : 1) - run->trace_row_base;
+        const int64_t hi = run->step_base + run->n_steps - run->trace_row_base;
+        if (run->n_steps + (run->write_row0 ? 1 : 0) > 0 && (lo < 0 || hi >= run->trace_rows))
+            return fail(ctx, GLABC_ERR_INVALID, "trace rows [%lld, %lld] fall outside the %lld-row buffer",
+                        (long long)lo, (long long)hi, (long long)run->trace_rows);
+        if (run->trace_chain_off < 0 || run->trace_chain_off + run->n_chains > run->trace_chains)
+            return fail(ctx, GLABC_ERR_INVALID, "chains [%lld, +%lld) fall outside the %lld-chain trace buffer",
+                        (long long)run->trace_chain_off, (long long)run->n_chains, (long long)run->trace_chains);
+    }
+    if (run->rng_mode != GLABC_RNG_NATIVE && run->rng_mode != GLABC_RNG_REPLAY)
+        return fail(ctx, GLABC_ERR_INVALID, "bad rng_mode %d", run->rng_mode);
+    if (run->arith_mode != GLABC_ARITH_FAST && run->arith_mode != GLABC_ARITH_STRICT)
+        return fail(ctx, GLABC_ERR_INVALID, "bad arith_mode %d", run->arith_mode);
+    if (run->rng_mode == GLABC_RNG_REPLAY && !run->tape32)
+        return fail(ctx, GLABC_ERR_INVALID, "replay mode needs tape32 [n_steps][%d][n_chains]", tape_slots);
+    int b = run->block_threads == 0 ? 64 : run->block_threads;
+    if (b < 32 || b > 256 || (b & 31)) return fail(ctx, GLABC_ERR_INVALID, "block_threads must be a multiple of 32 in [32, 256]");
+    *block = b;
+
+    RunParams r{};
+    r.n_chains = static_cast<int32_t>(run->n_chains);
+    r.first_step = static_cast<uint32_t>(run->step_base + 1);
+    r.last_step = static_cast<uint32_t>(run->step_base + run->n_steps);
+    r.chain_lo0 = static_cast<uint32_t>(static_cast<uint64_t>(run->chain_id_base));
+    r.chain_hi0 = static_cast<uint32_t>(static_cast<uint64_t>(run->chain_id_base) >> 32);
+    r.rk = expand_key(make_uint2(static_cast<uint32_t>(run->seed), static_cast<uint32_t>(run->seed >> 32)));
+    r.gf = run->global_frequency;
+    r.gf_threshold = gf_threshold(run->global_frequency);
+    r.write_row0 = run->write_row0 && run->trace_layout != GLABC_TRACE_NONE;
+    r.trace_rows = run->trace_rows;
+    r.trace_chains = run->trace_chains;
+    r.trace_chain_off = run->trace_chain_off;
+    r.trace_row_base = run->trace_row_base;
+    r.theta = run->theta;
+    r.y = run->y;
+    r.aux = run->aux;
+    r.trace = run->trace;
+    r.stats = run->stats;
+    r.tape32 = run->tape32;
+    r.tape64 = run->tape64;
+    r.debug = run->debug;
+    r.tape_dump = run->tape_dump;
+    r.n_candidates = run->n_candidates;
+    (void)dim;
+    *out = r;
+    return GLABC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sampler dispatch (device buffers)
+// ---------------------------------------------------------------------------------------------
+enum SamplerKind { SAMPLER_GLOBAL = 0 };
+
+static int run_device(glabc_ctx* ctx, SamplerKind kind, const glabc_run_t* run)
+{
+    if (!ctx) return GLABC_ERR_INVALID;
+    if (!ctx->has_model) return fail(ctx, GLABC_ERR_INVALID, "no model bound: call glabc_model_set first");
+    const int d = ctx->model.theta_dim;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    RunParams R;
+    int block = 0;
+    switch (kind) {
+    case SAMPLER_GLOBAL: {
+        if (!ctx->has_dist[GLABC_SLOT_LOCAL] || !ctx->has_dist[GLABC_SLOT_GLOBAL])
+            return fail(ctx, GLABC_ERR_INVALID, "run_global needs the LOCAL and GLOBAL proposal slots bound");
+        const glabc_dist_t& lp = ctx->dist[GLABC_SLOT_LOCAL];
+        const glabc_dist_t& gp = ctx->dist[GLABC_SLOT_GLOBAL];
+        if (lp.dim != d || gp.dim != d) return fail(ctx, GLABC_ERR_INVALID, "proposal dim does not match theta_dim %d", d);
+        int st = make_run_params(ctx, run, d, GLABC_TAPE_GLOBAL_SLOTS(d, d), &R, &block);
+        if (st) return st;
+        if (R.n_chains == 0) return GLABC_OK;
+        CUDA_TRY(ctx, launch_global_mcmc(make_model(ctx->model), make_gauss(lp.a, lp.b, lp.c, d), make_gauss(gp.a, gp.b, gp.c, d),
+                                         d, R, run->arith_mode == GLABC_ARITH_STRICT, run->rng_mode == GLABC_RNG_REPLAY,
+                                         run->trace_layout, block, static_cast<cudaStream_t>(run->stream)));
+        return GLABC_OK;
+    }
+    }
+    return fail(ctx, GLABC_ERR_INVALID, "unknown sampler");
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-buffer driver: H2D state, kernels in time chunks, D2H of each chunk's trace rows on a second
+// stream overlapped with the next chunk's kernel, D2H state + stats.
+// ---------------------------------------------------------------------------------------------
+static int ensure_host_scratch(glabc_ctx* ctx, size_t state_floats, size_t trace_floats)
+{
+    if (!ctx->s_compute) {
+        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking));
+        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_done[b], cudaEventDisableTiming));
+            CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_free[b], cudaEventDisableTiming));
+        }
+    }
+    if (state_floats > ctx->state_cap) {
+        if (ctx->d_state) cudaFree(ctx->d_state);
+        ctx->d_state = nullptr;
+        ctx->state_cap = 0;
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_state, state_floats * sizeof(float)));
+        ctx->state_cap = state_floats;
+    }
+    if (trace_floats > ctx->trace_cap) {
+        for (int b = 0; b < 2; ++b) {
+            if (ctx->d_trace[b]) cudaFree(ctx->d_trace[b]);
+            ctx->d_trace[b] = nullptr;
+        }
+        ctx->trace_cap = 0;
+        for (int b = 0; b < 2; ++b) CUDA_TRY(ctx, cudaMalloc(&ctx->d_trace[b], trace_floats * sizeof(float)));
+        ctx->trace_cap = trace_floats;
+    }
+    return GLABC_OK;
+}
+
+static int run_host(glabc_ctx* ctx, SamplerKind kind, const glabc_run_t* run, int64_t chunk_steps)
+{
+    if (!ctx) return GLABC_ERR_INVALID;
+    if (!ctx->has_model) return fail(ctx, GLABC_ERR_INVALID, "no model bound: call glabc_model_set first");
+    if (!run) return fail(ctx, GLABC_ERR_INVALID, "null run description");
+    if (run->rng_mode != GLABC_RNG_NATIVE) return fail(ctx, GLABC_ERR_INVALID, "host entry points run the native RNG only");
+    if (!run->theta || !run->y) return fail(ctx, GLABC_ERR_INVALID, "theta / y state pointers are required");
+    if (run->n_chains <= 0 || run->n_steps < 0) return run->n_chains == 0 ? GLABC_OK : fail(ctx, GLABC_ERR_INVALID, "bad sizes");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int d = ctx->model.theta_dim, yd = ctx->model.y_dim;
+    const int64_t C = run->n_chains;
+    const int ns = GLABC_NSTATS(d);
+    const bool traced = run->trace_layout != GLABC_TRACE_NONE;
+    if (traced && !run->trace) return fail(ctx, GLABC_ERR_INVALID, "trace pointer required for this trace_layout");
+
+    int64_t chunk = chunk_steps > 0 ? chunk_steps : (int64_t(64) << 20) / (C * d * int64_t(sizeof(float)));
+    chunk = ((chunk + 31) / 32) * 32;
+    if (chunk < 32) chunk = 32;
+    if (chunk > run->n_steps) chunk = run->n_steps > 0 ? run->n_steps : 1;
+    const int64_t buf_rows = chunk + 1;  // +1: the first chunk may carry row 0
+
+    const size_t n_theta = size_t(C) * d, n_y = size_t(C) * yd, n_aux = run->aux ? size_t(C) * GLABC_AUX_SLOTS : 0,
+                 n_stats = run->stats ? size_t(C) * ns : 0;
+    int st = ensure_host_scratch(ctx, n_theta + n_y + n_aux + n_stats, traced ? size_t(buf_rows) * C * d : 0);
+    if (st) return st;
+    float* d_theta = ctx->d_state;
+    float* d_y = d_theta + n_theta;
+    float* d_aux = n_aux ? d_y + n_y : nullptr;
+    float* d_stats = n_stats ? d_y + n_y + n_aux : nullptr;
+
+    cudaStream_t sc = ctx->s_compute, sx = ctx->s_copy;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_theta, run->theta, n_theta * sizeof(float), cudaMemcpyHostToDevice, sc));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_y, run->y, n_y * sizeof(float), cudaMemcpyHostToDevice, sc));
+    if (d_aux) CUDA_TRY(ctx, cudaMemcpyAsync(d_aux, run->aux, n_aux * sizeof(float), cudaMemcpyHostToDevice, sc));
+    if (d_stats) CUDA_TRY(ctx, cudaMemcpyAsync(d_stats, run->stats, n_stats * sizeof(float), cudaMemcpyHostToDevice, sc));
+
+    int64_t done = 0;
+    int b = 0;
+    bool used[2] = {false, false};
+    bool first_chunk = true;
+    do {
+        const int64_t n = std::min<int64_t>(chunk, run->n_steps - done);
+        glabc_run_t dev = *run;
+        dev.n_steps = n;
+        dev.step_base = run->step_base + done;
+        dev.write_row0 = first_chunk && run->write_row0;
+        dev.theta = d_theta;
+        dev.y = d_y;
+        dev.aux = d_aux;
+        dev.stats = d_stats;
+        dev.stream = sc;
+        dev.tape_dump = nullptr;
+        dev.debug = nullptr;
+        const int64_t row_lo = dev.step_base + (dev.write_row0 ? 0 : 1);  // first absolute row this chunk writes
+        const int64_t n_rows = n + (dev.write_row0 ? 1 : 0);
+        if (traced) {
+            if (used[b]) CUDA_TRY(ctx, cudaStreamWaitEvent(sc, ctx->ev_free[b], 0));
+            dev.trace = ctx->d_trace[b];
+            dev.trace_rows = buf_rows;
+            dev.trace_chains = C;
+            dev.trace_chain_off = 0;
+            dev.trace_row_base = row_lo;
+        }
+        st = run_device(ctx, kind, &dev);
+        if (st) return st;
+        if (traced && n_rows > 0) {
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_done[b], sc));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(sx, ctx->ev_done[b], 0));
+            const int64_t host_row = row_lo - run->trace_row_base;
+            if (host_row < 0 || host_row + n_rows > run->trace_rows)
+                return fail(ctx, GLABC_ERR_INVALID, "trace rows fall outside the host buffer");
+            if (run->trace_layout == GLABC_TRACE_TIME_MAJOR) {
+                float* dst = run->trace + (host_row * run->trace_chains + run->trace_chain_off) * d;
+                CUDA_TRY(ctx, cudaMemcpy2DAsync(dst, size_t(run->trace_chains) * d * sizeof(float), ctx->d_trace[b],
+                                                size_t(C) * d * sizeof(float), size_t(C) * d * sizeof(float), size_t(n_rows),
+                                                cudaMemcpyDeviceToHost, sx));
+            } else {
+                float* dst = run->trace + (run->trace_chain_off * run->trace_rows + host_row) * d;
+                CUDA_TRY(ctx, cudaMemcpy2DAsync(dst, size_t(run->trace_rows) * d * sizeof(float), ctx->d_trace[b],
+                                                size_t(buf_rows) * d * sizeof(float), size_t(n_rows) * d * sizeof(float), size_t(C),
+                                                cudaMemcpyDeviceToHost, sx));
+            }
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_free[b], sx));
+            used[b] = true;
+            b ^= 1;
+        }
+        done += n;
+        first_chunk = false;
+    } while (done < run->n_steps);
+
+    CUDA_TRY(ctx, cudaMemcpyAsync(run->theta, d_theta, n_theta * sizeof(float), cudaMemcpyDeviceToHost, sc));
+    CUDA_TRY(ctx, cudaMemcpyAsync(run->y, d_y, n_y * sizeof(float), cudaMemcpyDeviceToHost, sc));
+    if (d_aux) CUDA_TRY(ctx, cudaMemcpyAsync(run->aux, d_aux, n_aux * sizeof(float), cudaMemcpyDeviceToHost, sc));
+    if (d_stats) CUDA_TRY(ctx, cudaMemcpyAsync(run->stats, d_stats, n_stats * sizeof(float), cudaMemcpyDeviceToHost, sc));
+    CUDA_TRY(ctx, cudaStreamSynchronize(sc));
+    CUDA_TRY(ctx, cudaStreamSynchronize(sx));
+    return GLABC_OK;
+}
+
+extern "C" {
+
+int glabc_run_global(glabc_ctx* ctx, const glabc_run_t* run) { return run_device(ctx, SAMPLER_GLOBAL, run); }
+
+int glabc_run_global_host(glabc_ctx* ctx, const glabc_run_t* run, int64_t chunk_steps)
+{
+    return run_host(ctx, SAMPLER_GLOBAL, run, chunk_steps);
+}
+
+int glabc_esjd(glabc_ctx* ctx, const float* trace, int32_t layout, int64_t rows, int64_t chains, int32_t dim, float* out,
+               void* stream)
+{
+    if (!ctx) return GLABC_ERR_INVALID;
+    if (!trace || !out) return fail(ctx, GLABC_ERR_INVALID, "glabc_esjd: null pointer");
+    if (layout != GLABC_TRACE_TIME_MAJOR && layout != GLABC_TRACE_CHAIN_MAJOR)
+        return fail(ctx, GLABC_ERR_INVALID, "glabc_esjd: bad layout %d", layout);
+    if (rows < 2) return fail(ctx, GLABC_ERR_INVALID, "glabc_esjd: needs at least 2 rows");
+    if (dim < 1 || dim > 3) return fail(ctx, GLABC_ERR_UNSUPPORTED, "glabc_esjd: dim %d outside 1..3", dim);
+    if (chains <= 0) return GLABC_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, launch_esjd(trace, layout, rows, chains, dim, out, static_cast<cudaStream_t>(stream)));
+    return GLABC_OK;
+}
+
+int glabc_philox_kat(glabc_ctx* ctx, const uint32_t* ctr, const uint32_t* key, int64_t n, uint32_t* out, void* stream)
+{
+    if (!ctx) return GLABC_ERR_INVALID;
+    if (!ctr || !key || !out) return fail(ctx, GLABC_ERR_INVALID, "glabc_philox_kat: null pointer");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, launch_philox_kat(ctr, key, n, out, static_cast<cudaStream_t>(stream)));
+    return GLABC_OK;
+}
+
+}  // extern "C"

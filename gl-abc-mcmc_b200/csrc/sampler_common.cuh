@@ -1,0 +1,209 @@
+// Pieces shared by the sampler kernels: the launch description, the trace writers and the
+// per-chain statistics accumulators.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/glabc.h"
+#include "model.cuh"
+#include "philox.cuh"
+
+namespace glabc {
+
+// device view of glabc_run_t (validated and narrowed by the host side)
+struct RunParams {
+    int32_t n_chains;
+    uint32_t first_step;   // first loop index i to perform (= step_base + 1)
+    uint32_t last_step;    // last loop index (inclusive); last < first means no transition
+    uint32_t chain_lo0, chain_hi0;  // global id of chain 0 (low/high words)
+    RoundKeys rk;          // Philox round keys of the run's seed
+    float gf;
+    uint32_t gf_threshold;  // native mode: global iff (w >> 8) < gf_threshold   (B-15/B-16)
+    int32_t write_row0;
+    int64_t trace_rows, trace_chains, trace_chain_off, trace_row_base;
+    float* theta;
+    float* y;
+    float* aux;
+    float* trace;
+    float* stats;
+    const float* tape32;
+    const double* tape64;
+    float* debug;
+    float* tape_dump;
+    int32_t n_candidates;
+};
+
+__device__ __forceinline__ Stream chain_stream(const RunParams& r, int32_t chain)
+{
+    // 64-bit add of the chain index to the global base id
+    const uint64_t gid = (static_cast<uint64_t>(r.chain_hi0) << 32 | r.chain_lo0) + static_cast<uint64_t>(chain);
+    return Stream{static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32)};
+}
+
+// ---------------------------------------------------------------------------------------------
+// Trace writers.  Row index = the reference's loop index i (row 0 = initial theta,
+// GlobalMCMC.py:34-35); rows are relative to trace_row_base so a run can be chunked.
+// ---------------------------------------------------------------------------------------------
+template <int D>
+struct VecOf { using type = float; };
+template <> struct VecOf<2> { using type = float2; };
+template <> struct VecOf<4> { using type = float4; };
+
+template <int D>
+__device__ __forceinline__ void store_row(float* dst, const float (&v)[D])
+{
+    if constexpr (D == 2) {
+        *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
+    } else if constexpr (D == 4) {
+        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < D; ++k) dst[k] = v[k];
+    }
+}
+
+// TIME_MAJOR: trace[row][chain][d] — a warp's 32 chains are contiguous, one vector store per row.
+template <int D>
+struct TimeMajorWriter {
+    float* next;  // &trace[next row][chain][0]; rows are written consecutively
+    bool active;
+    __device__ __forceinline__ TimeMajorWriter(const RunParams& r, int32_t chain, bool act, float*)
+        : active(act)
+    {
+        const int64_t first_row = static_cast<int64_t>(r.first_step) - (r.write_row0 ? 1 : 0) - r.trace_row_base;
+        next = r.trace + (first_row * r.trace_chains + r.trace_chain_off + chain) * D;
+    }
+    __device__ __forceinline__ void put(const RunParams& r, uint32_t, const float (&v)[D])
+    {
+        if (active) store_row<D>(next, v);
+        next += r.trace_chains * D;
+    }
+    __device__ __forceinline__ void finish(const RunParams&) {}
+    static constexpr int smem_floats_per_warp = 0;
+};
+
+// CHAIN_MAJOR: trace[chain][row][d] — out[c] is a reference-shaped [num_ite, d] chain.  A thread
+// per chain would store with a stride of a whole chain, so each warp stages up to 32 rows of its
+// 32 chains in shared memory (component-planar, row pitch 33 words: conflict-free both ways) and
+// flushes them as 32 runs of 32*D contiguous floats, 128 B per store instruction.
+template <int D>
+struct ChainMajorWriter {
+    static constexpr int kPitch = 33;
+    static constexpr int kPlane = 32 * kPitch + (D > 1 ? 32 / D : 0);  // plane skew spreads banks on read
+    static constexpr int smem_floats_per_warp = D * kPlane;
+    float* tile;       // this warp's tile
+    float* out;        // &trace[chain0_of_warp][0][0]
+    int64_t chain_stride;
+    uint32_t row0;     // absolute row of tile slot 0
+    int32_t count;     // buffered rows
+    int32_t lane;
+    int32_t chains_in_warp;  // valid chains of this warp (tail warp may have < 32)
+
+    __device__ __forceinline__ ChainMajorWriter(const RunParams& r, int32_t chain, bool, float* smem_warp)
+        : tile(smem_warp), chain_stride(r.trace_rows * D), row0(0), count(0), lane(threadIdx.x & 31)
+    {
+        const int32_t chain0 = chain - lane;
+        out = r.trace + (r.trace_chain_off + chain0) * chain_stride;
+        chains_in_warp = min(32, r.n_chains - chain0);
+    }
+
+    __device__ __forceinline__ void put(const RunParams& r, uint32_t row, const float (&v)[D])
+    {
+        if (count == 0) row0 = row;
+#pragma unroll
+        for (int k = 0; k < D; ++k) tile[k * kPlane + count * kPitch + lane] = v[k];
+        ++count;
+        // flush on a 32-row boundary of the absolute row index so runs are 128B-aligned
+        if (((row + 1u) & 31u) == 0u || count == 32) flush(r);
+    }
+
+    __device__ __forceinline__ void flush(const RunParams& r)
+    {
+        __syncwarp();
+        const int32_t n = count * D;  // floats per chain in this tile
+        const int64_t off = (static_cast<int64_t>(row0) - r.trace_row_base) * D;
+        for (int32_t c = 0; c < chains_in_warp; ++c) {
+            float* dst = out + c * chain_stride + off;
+            for (int32_t e = lane; e < n; e += 32) {
+                const int32_t s = e / D, k = e - s * D;
+                dst[e] = tile[k * kPlane + s * kPitch + c];
+            }
+        }
+        __syncwarp();
+        count = 0;
+    }
+
+    __device__ __forceinline__ void finish(const RunParams& r)
+    {
+        if (count > 0) flush(r);
+    }
+};
+
+struct NoTraceWriter {
+    __device__ __forceinline__ NoTraceWriter(const RunParams&, int32_t, bool, float*) {}
+    template <int D>
+    __device__ __forceinline__ void put(const RunParams&, uint32_t, const float (&)[D]) {}
+    __device__ __forceinline__ void finish(const RunParams&) {}
+    static constexpr int smem_floats_per_warp = 0;
+};
+
+template <int D, int LAYOUT> struct WriterFor;
+template <int D> struct WriterFor<D, GLABC_TRACE_NONE> { using type = NoTraceWriter; };
+template <int D> struct WriterFor<D, GLABC_TRACE_TIME_MAJOR> { using type = TimeMajorWriter<D>; };
+template <int D> struct WriterFor<D, GLABC_TRACE_CHAIN_MAJOR> { using type = ChainMajorWriter<D>; };
+
+// ---------------------------------------------------------------------------------------------
+// Per-chain statistics (layout: GLABC_STAT_* in glabc.h)
+// ---------------------------------------------------------------------------------------------
+template <int D>
+struct ChainStats {
+    static constexpr int kTri = D * (D + 1) / 2;
+    uint32_t n_global, acc_local, acc_global;
+    float sum[D], sumsq[D], gram[kTri];
+
+    __device__ __forceinline__ ChainStats() : n_global(0), acc_local(0), acc_global(0)
+    {
+#pragma unroll
+        for (int i = 0; i < D; ++i) sum[i] = sumsq[i] = 0.0f;
+#pragma unroll
+        for (int i = 0; i < kTri; ++i) gram[i] = 0.0f;
+    }
+
+    // theta_new is the post-decision state; delta = theta_new - theta_prev (zero unless moved)
+    __device__ __forceinline__ void update(bool is_global, bool moved, const float (&theta_new)[D],
+                                           const float (&theta_prev)[D])
+    {
+        n_global += is_global;
+        acc_global += (moved && is_global);
+        acc_local += (moved && !is_global);
+        float dl[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            sum[i] += theta_new[i];
+            sumsq[i] = fmaf(theta_new[i], theta_new[i], sumsq[i]);
+            dl[i] = theta_new[i] - theta_prev[i];
+        }
+        int t = 0;
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = i; j < D; ++j, ++t) gram[t] = fmaf(dl[i], dl[j], gram[t]);
+    }
+
+    __device__ __forceinline__ void store(float* st, uint32_t n_steps) const
+    {
+        st[GLABC_STAT_STEPS] += static_cast<float>(n_steps);
+        st[GLABC_STAT_GLOBAL_STEPS] += static_cast<float>(n_global);
+        st[GLABC_STAT_ACC_LOCAL] += static_cast<float>(acc_local);
+        st[GLABC_STAT_ACC_GLOBAL] += static_cast<float>(acc_global);
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            st[GLABC_STAT_SUM + i] += sum[i];
+            st[GLABC_STAT_SUM + D + i] += sumsq[i];
+        }
+#pragma unroll
+        for (int i = 0; i < kTri; ++i) st[GLABC_STAT_SUM + 2 * D + i] += gram[i];
+    }
+};
+
+}  // namespace glabc

@@ -1,0 +1,187 @@
+"""Host side of the fused samplers: torch tensors <-> the C-ABI of libglabc.so.
+
+PyTorch is plumbing here (device memory, the current stream); all sampler arithmetic runs in the
+hand-written kernels behind `glabc_run_*`.  There is no CPU path: `Engine()` raises without a GPU.
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _abi
+from .models import lower_model, lower_proposal
+
+
+@dataclass
+class RunStats:
+    """Per-chain accumulators the kernels keep (include/glabc.h GLABC_STAT_*), as float64 tensors."""
+    raw: torch.Tensor  # [C, nstats] float32, device
+    dim: int
+
+    @property
+    def steps(self):
+        return self.raw[:, _abi.STAT_STEPS].double()
+
+    @property
+    def global_steps(self):
+        return self.raw[:, _abi.STAT_GLOBAL_STEPS].double()
+
+    @property
+    def accepted_local(self):
+        return self.raw[:, _abi.STAT_ACC_LOCAL].double()
+
+    @property
+    def accepted_global(self):
+        return self.raw[:, _abi.STAT_ACC_GLOBAL].double()
+
+    @property
+    def move_rate(self):
+        return (self.accepted_local + self.accepted_global) / self.steps.clamp(min=1)
+
+    @property
+    def mean(self):
+        d = self.dim
+        return self.raw[:, _abi.STAT_SUM:_abi.STAT_SUM + d].double() / self.steps.clamp(min=1)[:, None]
+
+    @property
+    def second_moment(self):
+        d = self.dim
+        return self.raw[:, _abi.STAT_SUM + d:_abi.STAT_SUM + 2 * d].double() / self.steps.clamp(min=1)[:, None]
+
+    def gram(self):
+        """[C, d, d] sum of delta delta^T (ESJD.py:17-21 numerator)."""
+        d = self.dim
+        tri = self.raw[:, _abi.STAT_SUM + 2 * d:_abi.STAT_SUM + 2 * d + d * (d + 1) // 2].double()
+        g = torch.zeros(self.raw.shape[0], d, d, dtype=torch.float64, device=self.raw.device)
+        t = 0
+        for i in range(d):
+            for j in range(i, d):
+                g[:, i, j] = tri[:, t]
+                g[:, j, i] = tri[:, t]
+                t += 1
+        return g
+
+    def esjd(self):
+        """per-chain det(sum delta delta^T / n_delta)^(1/d) — ESJD.py:21-24 without re-reading the trace"""
+        g = self.gram() / self.steps.clamp(min=1)[:, None, None]
+        return torch.linalg.det(g).clamp(min=0) ** (1.0 / self.dim)
+
+
+class Engine:
+    """One glabc context on the current CUDA device."""
+
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("glabc-b200 needs a CUDA device (sm_100a): there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.ctx = _abi.Context(self.device.index if self.device.index is not None else torch.cuda.current_device())
+        self.lib = self.ctx.lib
+        self.dim = None
+
+    # -- plugin binding -------------------------------------------------------------------------
+    def bind_model(self, abc_set):
+        pod = lower_model(abc_set)
+        self.ctx.check(self.lib.glabc_model_set(self.ctx.handle, C.byref(pod), C.sizeof(pod)))
+        self.dim = pod.theta_dim
+        return pod
+
+    def bind_proposal(self, slot, dist):
+        pod = lower_proposal(dist)
+        self.ctx.check(self.lib.glabc_dist_set(self.ctx.handle, slot, C.byref(pod), C.sizeof(pod)))
+        return pod
+
+    # -- helpers --------------------------------------------------------------------------------
+    def _f32(self, t, shape=None):
+        t = torch.as_tensor(t, dtype=torch.float32, device=self.device).contiguous()
+        return t if shape is None else t.reshape(shape)
+
+    @staticmethod
+    def _ptr(t):
+        return None if t is None else C.c_void_p(t.data_ptr())
+
+    def run(self, sampler, *, theta, y, n_steps, gf, step_base=0, chain_id_base=0, seed=0,
+            rng_mode=_abi.RNG_NATIVE, arith=_abi.ARITH_FAST, trace_layout=_abi.TRACE_CHAIN_MAJOR, trace=None,
+            trace_rows=None, trace_chains=None, trace_chain_off=0, trace_row_base=0, write_row0=True,
+            stats=None, aux=None, tape32=None, tape64=None, debug=None, tape_dump=None, K=0, block_threads=0):
+        """Enqueue `n_steps` transitions of every chain on the current stream (device tensors,
+        state updated in place).  Returns the trace tensor (allocated here unless given)."""
+        cn, d = theta.shape
+        for t in (theta, y, stats, aux, tape32, tape64, debug, tape_dump, trace):
+            if t is not None and (not t.is_cuda or not t.is_contiguous()):
+                raise ValueError("device entry point takes contiguous CUDA tensors")
+        rows = trace_rows if trace_rows is not None else step_base + n_steps + 1 - trace_row_base
+        tchains = trace_chains if trace_chains is not None else cn
+        if trace is None and trace_layout != _abi.TRACE_NONE:
+            shape = (rows, tchains, d) if trace_layout == _abi.TRACE_TIME_MAJOR else (tchains, rows, d)
+            trace = torch.empty(shape, dtype=torch.float32, device=self.device)
+        r = _abi.RunPOD(n_chains=cn, n_steps=n_steps, step_base=step_base, chain_id_base=chain_id_base,
+                        seed=int(seed) & 0xFFFFFFFFFFFFFFFF, global_frequency=float(gf), rng_mode=rng_mode,
+                        arith_mode=arith, trace_layout=trace_layout, write_row0=int(write_row0),
+                        block_threads=block_threads, n_candidates=K, trace_rows=rows, trace_chains=tchains,
+                        trace_chain_off=trace_chain_off, trace_row_base=trace_row_base,
+                        theta=self._ptr(theta), y=self._ptr(y), aux=self._ptr(aux), trace=self._ptr(trace),
+                        stats=self._ptr(stats), tape32=self._ptr(tape32), tape64=self._ptr(tape64),
+                        debug=self._ptr(debug), tape_dump=self._ptr(tape_dump),
+                        stream=C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        fn = getattr(self.lib, "glabc_run_" + sampler)
+        self.ctx.check(fn(self.ctx.handle, C.byref(r)))
+        return trace
+
+    def run_host(self, sampler, *, theta, y, n_steps, gf, trace, step_base=0, chain_id_base=0, seed=0,
+                 arith=_abi.ARITH_FAST, trace_layout=_abi.TRACE_TIME_MAJOR, write_row0=True, stats=None,
+                 aux=None, K=0, chunk_steps=0, block_threads=0):
+        """The reference-facing call on HOST buffers (numpy-compatible CPU tensors, ideally pinned):
+        H2D of the state, kernels, D2H of trace/state/stats — returns when the host buffers hold the
+        result."""
+        cn, d = theta.shape
+        for t in (theta, y, stats, aux, trace):
+            if t is not None and (t.is_cuda or not t.is_contiguous() or t.dtype != torch.float32):
+                raise ValueError("host entry point takes contiguous float32 CPU tensors")
+        if trace_layout == _abi.TRACE_NONE:
+            rows, tchains = 0, cn
+        elif trace_layout == _abi.TRACE_TIME_MAJOR:
+            rows, tchains = trace.shape[0], trace.shape[1]
+        else:
+            tchains, rows = trace.shape[0], trace.shape[1]
+        r = _abi.RunPOD(n_chains=cn, n_steps=n_steps, step_base=step_base, chain_id_base=chain_id_base,
+                        seed=int(seed) & 0xFFFFFFFFFFFFFFFF, global_frequency=float(gf), rng_mode=_abi.RNG_NATIVE,
+                        arith_mode=arith, trace_layout=trace_layout, write_row0=int(write_row0),
+                        block_threads=block_threads, n_candidates=K, trace_rows=rows, trace_chains=tchains,
+                        trace_chain_off=0, trace_row_base=0, theta=self._ptr(theta), y=self._ptr(y),
+                        aux=self._ptr(aux), trace=self._ptr(trace), stats=self._ptr(stats))
+        fn = getattr(self.lib, f"glabc_run_{sampler}_host")
+        self.ctx.check(fn(self.ctx.handle, C.byref(r), int(chunk_steps)))
+        return trace
+
+    def esjd(self, trace, layout):
+        """per-chain esjd of a device trace ([rows, C, d] time-major / [C, rows, d] chain-major)."""
+        if layout == _abi.TRACE_TIME_MAJOR:
+            rows, chains, d = trace.shape
+        else:
+            chains, rows, d = trace.shape
+        out = torch.empty(chains, dtype=torch.float32, device=self.device)
+        self.ctx.check(self.lib.glabc_esjd(self.ctx.handle, self._ptr(trace), layout, rows, chains, d, self._ptr(out),
+                                           C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        return out
+
+    def philox(self, ctr, key):
+        ctr = torch.as_tensor(ctr, dtype=torch.int64).to(self.device).to(torch.int32).contiguous()   # wraps mod 2^32
+        key = torch.as_tensor(key, dtype=torch.int64).to(self.device).to(torch.int32).contiguous()
+        out = torch.empty_like(ctr)
+        self.ctx.check(self.lib.glabc_philox_kat(self.ctx.handle, self._ptr(ctr), self._ptr(key), ctr.shape[0],
+                                                 self._ptr(out), None))
+        torch.cuda.synchronize(self.device)
+        return out.to(torch.int64) & 0xFFFFFFFF
+
+
+_engines = {}
+
+
+def get_engine(device=None):
+    """process-wide engine per device (contexts are cheap but hold scratch buffers)"""
+    if not torch.cuda.is_available():
+        raise RuntimeError("glabc-b200 needs a CUDA device (sm_100a): there is no CPU fallback")
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index
+    if idx not in _engines:
+        _engines[idx] = Engine(torch.device("cuda", idx))
+    return _engines[idx]

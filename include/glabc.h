@@ -150,6 +150,8 @@ typedef struct {
     int64_t trace_rows;       /* rows of the full trace buffer (num_ite); row index = step index  */
     int64_t trace_chains;     /* chains of the full trace buffer (>= n_chains)                    */
     int64_t trace_chain_off;  /* first chain of this launch inside the trace buffer               */
+    int64_t trace_row_base;   /* step index stored in row 0 of the trace buffer (0 unless the buffer
+                                 holds a time chunk of a longer run)                               */
     /* state, updated in place: theta[C][d], y[C][y_dim] (float32)                                */
     float* theta;
     float* y;
@@ -161,6 +163,9 @@ typedef struct {
     const float* tape32;      /* [n_steps][tape_slots][n_chains] float32 draws                    */
     const double* tape64;     /* [n_steps][n_chains] float64 draws (np.random.uniform), or NULL   */
     float* debug;             /* [n_steps][GLABC_DEBUG_SLOTS][n_chains] per-step quantities/NULL  */
+    /* native mode only */
+    float* tape_dump;         /* [n_steps][tape_slots][n_chains]: the draws the kernel used, in tape
+                                 layout, so a replay (or the CPU oracle) can re-run the same chain */
     void* stream;
 } glabc_run_t;
 
@@ -179,40 +184,46 @@ typedef struct {
 
 typedef struct glabc_ctx glabc_ctx;
 
+#if defined(__GNUC__)
+#define GLABC_API __attribute__((visibility("default")))
+#else
+#define GLABC_API
+#endif
+
 /* ---- lifecycle --------------------------------------------------------------------------- */
-int glabc_version(void);
+GLABC_API int glabc_version(void);
 /* device < 0: use the current CUDA device. Fails with GLABC_ERR_NO_DEVICE when no GPU is present. */
-int glabc_ctx_create(int device, glabc_ctx** out);
-int glabc_ctx_destroy(glabc_ctx* ctx);
-const char* glabc_last_error(const glabc_ctx* ctx);
-const char* glabc_status_string(int status);
+GLABC_API int glabc_ctx_create(int device, glabc_ctx** out);
+GLABC_API int glabc_ctx_destroy(glabc_ctx* ctx);
+GLABC_API const char* glabc_last_error(const glabc_ctx* ctx);
+GLABC_API const char* glabc_status_string(int status);
 /* multiprocessor count, SM clock (kHz) and the library's default block size, for roofline math   */
-int glabc_device_info(const glabc_ctx* ctx, int32_t* sm_count, int32_t* clock_khz, int32_t* cc);
+GLABC_API int glabc_device_info(const glabc_ctx* ctx, int32_t* sm_count, int32_t* clock_khz, int32_t* cc);
 
 /* ---- plugin binding ------------------------------------------------------------------------ */
 /* replaces the `ABCset` argument of every sampler (GlobalMCMC.py:6, GLMCMC.py:24, ...)           */
-int glabc_model_set(glabc_ctx* ctx, const glabc_model_t* model, size_t nbytes);
+GLABC_API int glabc_model_set(glabc_ctx* ctx, const glabc_model_t* model, size_t nbytes);
 /* replaces Local_Proposal / Global_Proposal / Importance_Proposal (GlobalMCMC.py:6-7,
  * GLMCMC.py:24-25)                                                                               */
-int glabc_dist_set(glabc_ctx* ctx, int slot, const glabc_dist_t* dist, size_t nbytes);
+GLABC_API int glabc_dist_set(glabc_ctx* ctx, int slot, const glabc_dist_t* dist, size_t nbytes);
 
 /* ---- samplers: device buffers, asynchronous on `stream` ------------------------------------- */
 /* GlobalMCMC loop body, GlobalMCMC.py:37-68 (local RW-MH / global independence-MH mixture)       */
-int glabc_run_global(glabc_ctx* ctx, const glabc_run_t* run);
+GLABC_API int glabc_run_global(glabc_ctx* ctx, const glabc_run_t* run);
 
 /* ---- samplers: host buffers (the reference-facing call: H2D state, run, D2H trace + stats) --- */
 /* `run->theta`, `y`, `trace`, `stats` are HOST pointers here; the trace is copied back in
  * `chunk_steps`-row chunks overlapped with the next chunk's kernel (0 = library default).        */
-int glabc_run_global_host(glabc_ctx* ctx, const glabc_run_t* run, int64_t chunk_steps);
+GLABC_API int glabc_run_global_host(glabc_ctx* ctx, const glabc_run_t* run, int64_t chunk_steps);
 
 /* ---- diagnostics --------------------------------------------------------------------------- */
 /* esjd(), ESJD.py:2-25, for every chain of a device trace: out[c] = det(D^T D/(N-1))^(1/d).
  * layout = glabc_trace_layout of `trace` ([rows][chains][d] or [chains][rows][d]).                */
-int glabc_esjd(glabc_ctx* ctx, const float* trace, int32_t layout, int64_t rows, int64_t chains,
+GLABC_API int glabc_esjd(glabc_ctx* ctx, const float* trace, int32_t layout, int64_t rows, int64_t chains,
                int32_t dim, float* out, void* stream);
 
 /* raw Philox4x32-10 blocks for known-answer tests: out[n][4] = philox(ctr[n][4], key[n][2])       */
-int glabc_philox_kat(glabc_ctx* ctx, const uint32_t* ctr, const uint32_t* key, int64_t n,
+GLABC_API int glabc_philox_kat(glabc_ctx* ctx, const uint32_t* ctr, const uint32_t* key, int64_t n,
                      uint32_t* out, void* stream);
 
 #ifdef __cplusplus

@@ -465,7 +465,7 @@ static void run_isir_range(void* vctx, int64_t c_begin, int64_t c_end)
                 }
                 local = 0;
                 float th[(GLABC_MAX_K + 1) * GLABC_MAX_DIM], x[(GLABC_MAX_K + 1) * GLABC_MAX_DIM];
-                float lw[GLABC_MAX_K + 1], w[GLABC_MAX_K + 1];
+                float lw[GLABC_MAX_K + 1], w[GLABC_MAX_K + 1] = {0};
                 memcpy(th, theta, sizeof(float) * d);
                 memcpy(x, y, sizeof(float) * yd);
                 lw[0] = lw_old;

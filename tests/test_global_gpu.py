@@ -1,0 +1,293 @@
+"""GPU parity tests of K1 (GlobalMCMC step kernel) through the C-ABI, against the golden vectors
+recorded from the reference and against the CPU oracle on seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import abi, gauss_pod, load_cases, model_pod, rel_err
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from glabc_b200.engine import Engine
+    return Engine()
+
+
+def bind(eng, model, lp, gp):
+    import ctypes as C
+    eng.ctx.check(eng.lib.glabc_model_set(eng.ctx.handle, C.byref(model), C.sizeof(model)))
+    eng.ctx.check(eng.lib.glabc_dist_set(eng.ctx.handle, abi.SLOT_LOCAL, C.byref(lp), C.sizeof(lp)))
+    eng.ctx.check(eng.lib.glabc_dist_set(eng.ctx.handle, abi.SLOT_GLOBAL, C.byref(gp), C.sizeof(gp)))
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ---- Philox known answers ------------------------------------------------------------------------
+KAT = [  # Random123 kat_vectors, philox4x32-10
+    ([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+    ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c9, 0x6d5451fd]),
+    ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+     [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]),
+]
+
+
+def test_philox_known_answers(eng):
+    ctr = [k[0] for k in KAT]
+    key = [k[1] for k in KAT]
+    out = eng.philox(ctr, key).cpu().tolist()
+    for (c, k, want), got in zip(KAT, out):
+        assert got == want
+        assert oracle.philox(c, k) == want
+    rng = np.random.default_rng(0)
+    ctr = rng.integers(0, 2**32, size=(4096, 4), dtype=np.int64)
+    key = rng.integers(0, 2**32, size=(4096, 2), dtype=np.int64)
+    out = eng.philox(ctr, key).cpu().numpy()
+    for i in range(0, 4096, 97):
+        assert out[i].tolist() == oracle.philox(ctr[i], key[i])
+
+
+# ---- replay of the reference's own draws ----------------------------------------------------------
+@pytest.mark.parametrize("arith", [abi.ARITH_STRICT, abi.ARITH_FAST])
+@pytest.mark.parametrize("ci", range(4))
+def test_replay_golden(eng, ci, arith):
+    case = load_cases("global_mcmc.npz")[ci]
+    T, C = int(case["T"]), case["theta0"].shape[0]
+    bind(eng, model_pod(case), gauss_pod(case, "lp"), gauss_pod(case, "gp"))
+    theta, y = dev(case["theta0"]), dev(case["y0"])
+    debug = torch.zeros(T - 1, abi.DEBUG_SLOTS, C, device="cuda")
+    stats = torch.zeros(C, abi.nstats(2), device="cuda")
+    trace = eng.run("global", theta=theta, y=y, n_steps=T - 1, gf=float(case["gf"]), rng_mode=abi.RNG_REPLAY,
+                    arith=arith, trace_layout=abi.TRACE_TIME_MAJOR, tape32=dev(case["tape32"]), debug=debug, stats=stats)
+    torch.cuda.synchronize()
+    dbg, rec = debug.cpu().numpy(), case["rec"]
+    # accept/branch decisions bit-exact (north_star), hence the whole trace
+    assert np.array_equal(dbg[:, 0].astype(np.int32), rec[:, 0].astype(np.int32))
+    assert np.array_equal(trace.cpu().numpy(), case["trace"])
+    # log-densities and the kernel within 1e-5 relative (north_star)
+    for k in (1, 2, 3):
+        assert rel_err(dbg[:, k], rec[:, k]).max() <= 1e-5
+    if arith == abi.ARITH_STRICT:
+        assert np.array_equal(dbg[:, 1], rec[:, 1])  # prior: +,-,*,/ only -> identical bits
+    flags = rec[:, 0].astype(np.int32)
+    st = stats.cpu().numpy()
+    assert np.array_equal(st[:, abi.STAT_STEPS], np.full(C, T - 1, np.float32))
+    assert np.array_equal(st[:, abi.STAT_GLOBAL_STEPS], (flags & 1).sum(0))
+    assert np.array_equal(st[:, abi.STAT_ACC_GLOBAL], ((flags & 3) == 3).sum(0))
+    assert np.array_equal(st[:, abi.STAT_ACC_LOCAL], ((flags & 3) == 2).sum(0))
+
+
+def synthetic_case(d, C, T, seed, family=abi.MODEL_ABS_NORMAL):
+    rng = np.random.default_rng(seed)
+    f = lambda *s: rng.standard_normal(s).astype(np.float32)  # noqa: E731
+    case = dict(y_obs=(1.0 + 0.5 * rng.random(d)).astype(np.float32), noise_loc=0.05 * f(d),
+                noise_scale=(0.2 + 0.2 * rng.random(d)).astype(np.float32), prior_loc=0.1 * f(d),
+                prior_log_scale=0.2 * f(d), eps_log_scale=np.float32(np.log(0.3)), lp_loc=0.01 * f(d),
+                lp_log_scale=np.log(0.2 + 0.3 * rng.random(d)).astype(np.float32), gp_loc=0.2 * f(d),
+                gp_log_scale=0.3 * f(d))
+    case["prior_scale"] = np.exp(case["prior_log_scale"])
+    case["eps_scale"] = np.exp(case["eps_log_scale"])
+    case["lp_scale"], case["gp_scale"] = np.exp(case["lp_log_scale"]), np.exp(case["gp_log_scale"])
+    tape = f(T, 2 + 2 * d, C)
+    tape[:, 0] = rng.random((T, C), dtype=np.float32)
+    tape[:, 1 + 2 * d] = rng.random((T, C), dtype=np.float32)
+    tape[0, 1 + 2 * d, 0] = 0.0  # log(0) = -inf must accept (B-16)
+    return case, tape, f(C, d), 1.0 + 0.3 * f(C, d)
+
+
+@pytest.mark.parametrize("d", [1, 2, 3, 4])
+@pytest.mark.parametrize("layout", [abi.TRACE_TIME_MAJOR, abi.TRACE_CHAIN_MAJOR])
+def test_replay_matches_oracle_all_dims(eng, d, layout):
+    """ragged chain count (tail warp), every fused dimension, both trace layouts, both families"""
+    C, T = 1000 + 37, 150
+    family = abi.MODEL_ABS_NORMAL if d % 2 == 0 else abi.MODEL_ID_NORMAL
+    case, tape, theta0, y0 = synthetic_case(d, C, T, seed=d, family=family)
+    m, lp, gp = model_pod(case, family), gauss_pod(case, "lp"), gauss_pod(case, "gp")
+    th_o, y_o = theta0.copy(), y0.copy()
+    st_o = np.zeros((C, abi.nstats(d)), np.float32)
+    want = oracle.run("global", m, lp, gp, theta=th_o, y=y_o, n_steps=T, gf=0.4, rng_mode=abi.RNG_REPLAY,
+                      tape32=tape, trace_layout=layout, stats=st_o)
+    bind(eng, m, lp, gp)
+    theta, y = dev(theta0), dev(y0)
+    stats = torch.zeros(C, abi.nstats(d), device="cuda")
+    got = eng.run("global", theta=theta, y=y, n_steps=T, gf=0.4, rng_mode=abi.RNG_REPLAY, arith=abi.ARITH_STRICT,
+                  trace_layout=layout, tape32=dev(tape), stats=stats, block_threads=96)
+    torch.cuda.synchronize()
+    assert np.array_equal(got.cpu().numpy(), want)
+    assert np.array_equal(theta.cpu().numpy(), th_o) and np.array_equal(y.cpu().numpy(), y_o)
+    st = stats.cpu().numpy()
+    assert np.array_equal(st[:, :4], st_o[:, :4])
+    assert np.allclose(st[:, 4:], st_o[:, 4:], rtol=1e-5, atol=1e-5)
+
+
+# ---- native RNG -----------------------------------------------------------------------------------
+def readme_pods():
+    case = load_cases("global_mcmc.npz")[0]
+    return case, model_pod(case), gauss_pod(case, "lp"), gauss_pod(case, "gp")
+
+
+def test_native_draws_replayed_by_oracle(eng):
+    """the kernel dumps the Philox/Box-Muller draws it used; the CPU oracle replays them and must land
+    on the same chain (strict arithmetic) — ties the native path to the same restatement."""
+    case, m, lp, gp = readme_pods()
+    C, T, d = 777, 400, 2
+    bind(eng, m, lp, gp)
+    theta0 = np.zeros((C, d), np.float32)
+    y0 = (np.random.default_rng(1).standard_normal((C, d)) * 0.2236).astype(np.float32)
+    theta, y = dev(theta0), dev(y0)
+    dump = torch.zeros(T, 6, C, device="cuda")
+    got = eng.run("global", theta=theta, y=y, n_steps=T, gf=0.5, seed=11, chain_id_base=5, arith=abi.ARITH_STRICT,
+                  trace_layout=abi.TRACE_TIME_MAJOR, tape_dump=dump)
+    torch.cuda.synchronize()
+    th_o, y_o = theta0.copy(), y0.copy()
+    want = oracle.run("global", m, lp, gp, theta=th_o, y=y_o, n_steps=T, gf=0.5, rng_mode=abi.RNG_REPLAY,
+                      tape32=dump.cpu().numpy())
+    assert np.array_equal(got.cpu().numpy(), want)
+    # and the fast-arithmetic kernel takes the same decisions on the same draws
+    theta, y = dev(theta0), dev(y0)
+    fast = eng.run("global", theta=theta, y=y, n_steps=T, gf=0.5, seed=11, chain_id_base=5, arith=abi.ARITH_FAST,
+                   trace_layout=abi.TRACE_TIME_MAJOR)
+    moved_f = (fast[1:] != fast[:-1]).any(-1).cpu().numpy()
+    moved_s = (want[1:] != want[:-1]).any(-1)
+    assert (moved_f != moved_s).mean() < 1e-4
+    # the oracle's own native mode draws the same Philox streams (normals differ in the last bits only:
+    # libm vs MUFU), so its uniforms agree exactly with the dump
+    th_n, y_n = theta0.copy(), y0.copy()
+    nat = oracle.run("global", m, lp, gp, theta=th_n, y=y_n, n_steps=T, gf=0.5, seed=11, chain_id_base=5)
+    dn = dump.cpu().numpy()
+    agree = ((nat[1:] != nat[:-1]).any(-1) == moved_s).mean()
+    assert agree > 0.999
+    assert np.abs(dn[:, 1:5]).max() < 6.5 and abs(dn[:, 1:5].mean()) < 0.01 and abs(dn[:, 1:5].std() - 1) < 0.01
+
+
+def test_native_invariances(eng):
+    """time chunking / resume, sharding by chain_id_base, trace layouts and the host-buffer entry
+    point all give the same chains."""
+    case, m, lp, gp = readme_pods()
+    C, T, d = 300, 257, 2
+    bind(eng, m, lp, gp)
+    theta0 = torch.zeros(C, d, device="cuda")
+    y0 = (torch.randn(C, d, generator=torch.Generator().manual_seed(3)) * 0.2236).cuda()
+    run = lambda **kw: eng.run("global", gf=0.5, seed=99, **kw)  # noqa: E731
+    th, yy = theta0.clone(), y0.clone()
+    st_full = torch.zeros(C, abi.nstats(d), device="cuda")
+    full = run(theta=th, y=yy, n_steps=T - 1, trace_layout=abi.TRACE_TIME_MAJOR, stats=st_full)
+    # chain-major layout
+    th2, yy2 = theta0.clone(), y0.clone()
+    cm = run(theta=th2, y=yy2, n_steps=T - 1, trace_layout=abi.TRACE_CHAIN_MAJOR)
+    assert torch.equal(cm.permute(1, 0, 2), full)
+    # three time chunks (odd boundaries) into one buffer, chain-major, plus accumulated stats
+    th3, yy3 = theta0.clone(), y0.clone()
+    buf = torch.zeros(C, T, d, device="cuda")
+    st = torch.zeros(C, abi.nstats(d), device="cuda")
+    base = 0
+    for n in (37, 100, T - 1 - 137):
+        run(theta=th3, y=yy3, n_steps=n, step_base=base, trace=buf, trace_rows=T, trace_layout=abi.TRACE_CHAIN_MAJOR,
+            write_row0=(base == 0), stats=st)
+        base += n
+    assert torch.equal(buf, cm) and torch.equal(th3, th) and torch.equal(yy3, yy)
+    assert torch.equal(st[:, :4], st_full[:, :4]) and torch.allclose(st, st_full, rtol=1e-5, atol=1e-5)
+    # two shards keyed by global chain id
+    h = 128
+    parts = []
+    for lo, hi in ((0, h), (h, C)):
+        t, yv = theta0[lo:hi].clone(), y0[lo:hi].clone()
+        parts.append(run(theta=t, y=yv, n_steps=T - 1, chain_id_base=lo, trace_layout=abi.TRACE_TIME_MAJOR))
+    assert torch.equal(torch.cat(parts, dim=1), full)
+    # host-buffer entry point (pinned), both layouts, small chunks so the double buffering cycles
+    for layout, ref in ((abi.TRACE_TIME_MAJOR, full), (abi.TRACE_CHAIN_MAJOR, cm)):
+        shape = (T, C, d) if layout == abi.TRACE_TIME_MAJOR else (C, T, d)
+        host = torch.zeros(shape).pin_memory()
+        hth, hy = theta0.cpu().clone(), y0.cpu().clone()
+        hst = torch.zeros(C, abi.nstats(d))
+        eng.run_host("global", theta=hth, y=hy, n_steps=T - 1, gf=0.5, seed=99, trace=host, trace_layout=layout,
+                     stats=hst, chunk_steps=64)
+        assert torch.equal(host, ref.cpu()) and torch.equal(hth, th.cpu()) and torch.equal(hst, st_full.cpu())
+
+
+def test_native_posterior_matches_closed_form(eng):
+    """README model: |theta_i| ~ N(1.42518, 0.049881), four equal modes."""
+    from scipy import stats as sst
+    case, m, lp, gp = readme_pods()
+    C, T, d = 32768, 6000, 2
+    bind(eng, m, lp, gp)
+    theta = torch.zeros(C, d, device="cuda")
+    y = torch.randn(C, d, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5)) * 0.2236
+    eng.run("global", theta=theta, y=y, n_steps=T, gf=0.5, seed=2024, trace_layout=abi.TRACE_NONE)  # burn-in
+    st = torch.zeros(C, abi.nstats(d), device="cuda")
+    eng.run("global", theta=theta, y=y, n_steps=T, step_base=T, gf=0.5, seed=2024, trace_layout=abi.TRACE_NONE, stats=st)
+    torch.cuda.synchronize()
+    a = theta.abs().cpu().numpy().astype(np.float64)
+    for i in range(d):  # chains are independent: the final states are an i.i.d. sample of the posterior
+        ks = sst.kstest(a[:, i], "norm", args=(1.42518, np.sqrt(0.049881))).statistic
+        assert ks < 0.015, ks
+        assert abs(a[:, i].mean() - 1.42518) < 0.006 and abs(a[:, i].var() - 0.049881) < 0.003
+    quad = ((theta[:, 0] > 0).long() * 2 + (theta[:, 1] > 0).long()).bincount(minlength=4).cpu().numpy() / C
+    assert np.abs(quad - 0.25).max() < 0.02
+    s = st.cpu().numpy().astype(np.float64)
+    move = (s[:, abi.STAT_ACC_LOCAL] + s[:, abi.STAT_ACC_GLOBAL]).sum() / s[:, abi.STAT_STEPS].sum()
+    assert 0.009 < move < 0.014   # reference: 1.14 % +- 0.04
+    assert abs(s[:, abi.STAT_GLOBAL_STEPS].sum() / s[:, abi.STAT_STEPS].sum() - 0.5) < 1e-3
+
+
+def test_native_matches_oracle_native_distribution(eng):
+    """same sampler, same Philox streams, CPU libm vs GPU MUFU normals: two-sample KS on |theta|."""
+    from scipy import stats as sst
+    case, m, lp, gp = readme_pods()
+    C, T, d = 4096, 3000, 2
+    bind(eng, m, lp, gp)
+    theta0 = np.zeros((C, d), np.float32)
+    y0 = (np.random.default_rng(8).standard_normal((C, d)) * 0.2236).astype(np.float32)
+    theta, y = dev(theta0), dev(y0)
+    st = torch.zeros(C, abi.nstats(d), device="cuda")
+    eng.run("global", theta=theta, y=y, n_steps=T, gf=0.5, seed=77, trace_layout=abi.TRACE_NONE, stats=st)
+    th_o, y_o = theta0.copy(), y0.copy()
+    st_o = np.zeros((C, abi.nstats(d)), np.float32)
+    oracle.run("global", m, lp, gp, theta=th_o, y=y_o, n_steps=T, gf=0.5, seed=77, trace_layout=abi.TRACE_NONE, stats=st_o)
+    g = theta.abs().cpu().numpy()
+    for i in range(d):
+        assert sst.ks_2samp(g[:, i], np.abs(th_o[:, i])).statistic < 0.03
+    sg = st.cpu().numpy().astype(np.float64)
+    acc_g = (sg[:, 2] + sg[:, 3]).sum() / (C * T)
+    acc_o = (st_o[:, 2].astype(np.float64) + st_o[:, 3]).sum() / (C * T)
+    assert abs(acc_g - acc_o) < 5e-4
+    assert np.array_equal(sg[:, abi.STAT_GLOBAL_STEPS], st_o[:, abi.STAT_GLOBAL_STEPS])  # same uniforms exactly
+
+
+# ---- esjd ------------------------------------------------------------------------------------------
+def test_esjd_kernel(eng):
+    z = np.load(__import__("os").path.join(__import__("helpers").GOLDEN, "misc.npz"))
+    chains = torch.from_numpy(z["esjd/chains"]).cuda()          # [6, 400, 2]
+    got = eng.esjd(chains.contiguous(), abi.TRACE_CHAIN_MAJOR).cpu().numpy()
+    assert np.allclose(got, z["esjd/values"], rtol=2e-5)         # vs the reference's esjd()
+    got_t = eng.esjd(chains.permute(1, 0, 2).contiguous(), abi.TRACE_TIME_MAJOR).cpu().numpy()
+    assert np.allclose(got_t, z["esjd/values"], rtol=2e-5)
+    assert np.allclose(oracle.esjd(z["esjd/chains"], abi.TRACE_CHAIN_MAJOR), z["esjd/values"], rtol=2e-5)
+
+
+def test_public_api_single_chain(eng, tmp_path, capsys):
+    """the reference-shaped call: one chain, CPU tensor [num_ite, d] back, CSV written, summary printed"""
+    import glabc_b200 as g
+    torch.manual_seed(0)
+    model = g.Mixture_set(epsilon=0.05)
+    lp = g.DiagGaussian(2, loc=torch.zeros(1, 2), log_scale=torch.log(torch.tensor([0.35, 0.35])))
+    gp = g.DiagGaussian(2, torch.tensor([0.0, 0.0]), torch.tensor([0.0, 0.0]))
+    theta0 = torch.tensor([0.0, 0.0])
+    y0 = model.generate_samples(theta0)
+    runner = g.MCMCRunner(model, output_dir=str(tmp_path))
+    chain = runner.run_global_mcmc(2000, theta0, y0, 0.5, lp, gp, output_file="global.csv")
+    assert chain.shape == (2000, 2) and chain.dtype == torch.float32 and not chain.is_cuda
+    assert torch.equal(chain[0], theta0)
+    assert "Theta_Re 1:" in capsys.readouterr().out
+    rows = np.loadtxt(tmp_path / "global.csv", delimiter=",", dtype=np.float32)
+    assert rows.shape == (2000, 2) and np.array_equal(rows, chain.numpy())
+    e = g.esjd(chain)
+    assert isinstance(e, np.ndarray) and e.shape == () and e.dtype == np.float32
+    # many chains: device tensor [C, num_ite, d] + stats; esjd from stats == esjd of the trace
+    out, st = runner.run_global_mcmc(500, theta0, None, 0.5, lp, gp, output_file=None, num_chains=256, seed=1, return_stats=True)
+    assert out.shape == (256, 500, 2) and out.is_cuda
+    assert np.allclose(g.esjd(out), st.esjd().cpu().numpy(), rtol=1e-4, atol=1e-7)
