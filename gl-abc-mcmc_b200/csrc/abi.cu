@@ -196,12 +196,12 @@ static ModelConsts make_model(const glabc_model_t& m)
     return k;
 }
 
-static uint32_t gf_threshold(float gf)
+// native branch coin: U_b = k * 2^-16 (k < 2^16);  U_b < gf  <=>  k < ceil(gf * 2^16)  
+static uint32_t gf_threshold16(float gf)
 {
-    // u = k * 2^-24 (k < 2^24);  u < gf  <=>  k < ceil(gf * 2^24)   (float32 compare)
     if (!(gf > 0.0f)) return 0u;
-    if (gf >= 1.0f) return 1u << 24;
-    return static_cast<uint32_t>(std::ceil(static_cast<double>(gf) * 16777216.0));
+    if (gf >= 1.0f) return 1u << 16;
+    return static_cast<uint32_t>(std::ceil(static_cast<double>(gf) * 65536.0));
 }
 
 static int make_run_params(glabc_ctx* ctx, const glabc_run_t* run, int dim, int tape_slots, RunParams* out, int* block)
@@ -210,6 +210,9 @@ static int make_run_params(glabc_ctx* ctx, const glabc_run_t* run, int dim, int 
     if (run->n_chains < 0 || run->n_chains > INT32_MAX) return fail(ctx, GLABC_ERR_INVALID, "n_chains out of range");
     if (run->n_steps < 0 || run->step_base < 0 || run->step_base + run->n_steps >= 0xFFFFFFF0ll)
         return fail(ctx, GLABC_ERR_INVALID, "step_base + n_steps must stay below 2^32 (Philox block counter)");
+    if (run->n_steps >= (1 << 24))
+        return fail(ctx, GLABC_ERR_INVALID, "at most 16,777,215 transitions per launch (float32 step counters): chunk the run "
+                                            "with step_base, the chain continues bit-identically");
     if (!run->theta || !run->y) return fail(ctx, GLABC_ERR_INVALID, "theta / y state pointers are required");
     if (run->trace_layout < GLABC_TRACE_NONE || run->trace_layout > GLABC_TRACE_CHAIN_MAJOR)
         return fail(ctx, GLABC_ERR_INVALID, "bad trace_layout %d", run->trace_layout);
@@ -242,7 +245,9 @@ static int make_run_params(glabc_ctx* ctx, const glabc_run_t* run, int dim, int 
     r.chain_hi0 = static_cast<uint32_t>(static_cast<uint64_t>(run->chain_id_base) >> 32);
     r.rk = expand_key(make_uint2(static_cast<uint32_t>(run->seed), static_cast<uint32_t>(run->seed >> 32)));
     r.gf = run->global_frequency;
-    r.gf_threshold = gf_threshold(run->global_frequency);
+    const uint32_t thr16 = gf_threshold16(run->global_frequency);
+    r.gf_all_global = thr16 >= (1u << 16);
+    r.gf_thr_hi = r.gf_all_global ? 0xFFFFFFFFu : (thr16 << 16);
     r.write_row0 = run->write_row0 && run->trace_layout != GLABC_TRACE_NONE;
     r.trace_rows = run->trace_rows;
     r.trace_chains = run->trace_chains;

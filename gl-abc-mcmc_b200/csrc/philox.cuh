@@ -4,8 +4,15 @@
 // GLMCMC.py:17); a kernel over 65,536+ independent chains needs a stateless generator keyed by the
 // GLOBAL chain id so a chain's trace does not depend on how chains are sharded over GPUs.
 //   counter = (chain_lo, chain_hi, block, slot), key = (seed_lo, seed_hi)
-//   slot 0          : uniforms; block j serves steps 2j and 2j+1 (U_b, U_a each)
-//   slot 1 + g      : normals of step `block`, group g of 4 words = 2 Box-Muller pairs
+//   slot 1      : the "step block" of step `block`: ONE Philox call carries everything a
+//                 d<=2 GlobalMCMC / local step draws (32x32->64 multiplies are quarter-rate on
+//                 sm_100, so the bit budget is spent carefully):
+//                   w.x[31:8]  24 bits  Box-Muller radius uniform, pair a     w.x[7:0]  \  16-bit branch
+//                   w.z[31:8]  24 bits  Box-Muller radius uniform, pair b     w.z[7:0]  /  uniform U_b
+//                   w.y[31:12] 20 bits  Box-Muller angle, pair a              w.y[11:0] \  24-bit accept
+//                   w.w[31:12] 20 bits  Box-Muller angle, pair b              w.w[11:0] /  uniform U_a
+//                 (disjoint bit fields of one block are independent uniform bits)
+//   slot 2 + g  : extra normal blocks (4 normals each) for d > 2 and for iSIR candidates
 //   slot 0x80000000 : float64 resampling uniform of step `block` (iSIR)
 #pragma once
 #include <cstdint>
@@ -18,8 +25,8 @@ constexpr uint32_t kPhiloxM1 = 0xCD9E8D57u;
 constexpr uint32_t kPhiloxW0 = 0x9E3779B9u;
 constexpr uint32_t kPhiloxW1 = 0xBB67AE85u;
 
-constexpr uint32_t kSlotUniform = 0u;
-constexpr uint32_t kSlotNormal = 1u;
+constexpr uint32_t kSlotStep = 1u;
+constexpr uint32_t kSlotNormal = 2u;
 constexpr uint32_t kSlotU64 = 0x80000000u;
 
 // The ten round keys are launch-uniform: the host expands them once (RoundKeys) and the kernel
@@ -73,16 +80,23 @@ __device__ __forceinline__ float lg2_approx(float x)
 __device__ __forceinline__ float log_approx(float x) { return 0.69314718055994531f * lg2_approx(x); }
 
 // Box-Muller pair from two words, MUFU path (lg2, sqrt, sin, cos): 4 MUFU + ~8 FP per pair.
-// u1 = (w0 + 0.5) * 2^-32 in (0, 1]; angle = 2*pi * w1 * 2^-32.
+// radius uniform u1 = (k + 0.5) * 2^-24 with k = w0[31:8]; angle = 2*pi * j * 2^-20 with j = w1[31:12].
+// The masked words have <= 24 significant bits, so the int->float conversions are exact and the
+// low bits (used for U_b / U_a) cannot leak into the normals.
 __device__ __forceinline__ void box_muller(uint32_t w0, uint32_t w1, float& n0, float& n1)
 {
-    const float u1 = fmaf(__uint2float_rn(w0), 0x1p-32f, 0x1p-33f);
+    const float u1 = fmaf(__uint2float_rn(w0 & 0xFFFFFF00u), 0x1p-32f, 0x1p-25f);
     const float r2 = -1.3862943611198906f * lg2_approx(u1);  // -2 ln2 * lg2(u1) = -2 ln(u1)
     float r;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(r2));
-    const float a = __uint2float_rn(w1) * (6.28318530717958647692f * 0x1p-32f);
+    const float a = __uint2float_rn(w1 & 0xFFFFF000u) * (6.28318530717958647692f * 0x1p-32f);
     n0 = r * __cosf(a);
     n1 = r * __sinf(a);
 }
+
+// U_b of a step block in the top 16 bits (low 16 bits are don't-care): global iff ub_hi < thr << 16
+__device__ __forceinline__ uint32_t step_block_ub(const uint4& w) { return __byte_perm(w.x, w.z, 0x0400); }
+// U_a of a step block: 24 bits
+__device__ __forceinline__ uint32_t step_block_ua(const uint4& w) { return (w.y & 0xFFFu) | ((w.w << 12) & 0xFFF000u); }
 
 }  // namespace glabc

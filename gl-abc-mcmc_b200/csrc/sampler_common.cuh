@@ -18,7 +18,9 @@ struct RunParams {
     uint32_t chain_lo0, chain_hi0;  // global id of chain 0 (low/high words)
     RoundKeys rk;          // Philox round keys of the run's seed
     float gf;
-    uint32_t gf_threshold;  // native mode: global iff (w >> 8) < gf_threshold   (B-15/B-16)
+    uint32_t gf_thr_hi;     // native mode: global iff (U_b16 << 16 | junk) < gf_thr_hi, U_b16 the 16-bit
+                            // branch uniform and gf_thr_hi = ceil(gf * 2^16) << 16   (cf. B-15/B-16)
+    int32_t gf_all_global;  // gf >= 1: every step is global (the threshold would not fit 32 bits)
     int32_t write_row0;
     int64_t trace_rows, trace_chains, trace_chain_off, trace_row_base;
     float* theta;
@@ -78,6 +80,7 @@ struct TimeMajorWriter {
         if (active) store_row<D>(next, v);
         next += r.trace_chains * D;
     }
+    __device__ __forceinline__ void maybe_flush(const RunParams&, uint32_t) {}
     __device__ __forceinline__ void finish(const RunParams&) {}
     static constexpr int smem_floats_per_warp = 0;
 };
@@ -99,10 +102,11 @@ struct ChainMajorWriter {
     int32_t lane;
     int32_t chains_in_warp;  // valid chains of this warp (tail warp may have < 32)
 
-    __device__ __forceinline__ ChainMajorWriter(const RunParams& r, int32_t chain, bool, float* smem_warp)
+    __device__ __forceinline__ ChainMajorWriter(const RunParams& r, int32_t, bool, float* smem_warp)
         : tile(smem_warp), chain_stride(r.trace_rows * D), row0(0), count(0), lane(threadIdx.x & 31)
     {
-        const int32_t chain0 = chain - lane;
+        // warp-uniform geometry (tail lanes shadow another chain's state but must agree on the tile)
+        const int32_t chain0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u);
         out = r.trace + (r.trace_chain_off + chain0) * chain_stride;
         chains_in_warp = min(32, r.n_chains - chain0);
     }
@@ -113,8 +117,13 @@ struct ChainMajorWriter {
 #pragma unroll
         for (int k = 0; k < D; ++k) tile[k * kPlane + count * kPitch + lane] = v[k];
         ++count;
-        // flush on a 32-row boundary of the absolute row index so runs are 128B-aligned
-        if (((row + 1u) & 31u) == 0u || count == 32) flush(r);
+    }
+
+    // call after put(row): flushes on a 32-row boundary of the absolute row index, so every run a
+    // chain receives is 32 rows long and 128B-aligned (the tile never holds more than 32 rows)
+    __device__ __forceinline__ void maybe_flush(const RunParams& r, uint32_t row)
+    {
+        if (((row + 1u) & 31u) == 0u) flush(r);
     }
 
     __device__ __forceinline__ void flush(const RunParams& r)
@@ -143,6 +152,7 @@ struct NoTraceWriter {
     __device__ __forceinline__ NoTraceWriter(const RunParams&, int32_t, bool, float*) {}
     template <int D>
     __device__ __forceinline__ void put(const RunParams&, uint32_t, const float (&)[D]) {}
+    __device__ __forceinline__ void maybe_flush(const RunParams&, uint32_t) {}
     __device__ __forceinline__ void finish(const RunParams&) {}
     static constexpr int smem_floats_per_warp = 0;
 };
@@ -159,9 +169,12 @@ template <int D>
 struct ChainStats {
     static constexpr int kTri = D * (D + 1) / 2;
     uint32_t n_global, acc_local, acc_global;
+    float f_global, f_acc, f_acc_global;  // FAST path: the same counts kept as floats on the FMA pipe
+                                          // (exact below 2^24 transitions per launch — host-enforced)
     float sum[D], sumsq[D], gram[kTri];
 
-    __device__ __forceinline__ ChainStats() : n_global(0), acc_local(0), acc_global(0)
+    __device__ __forceinline__ ChainStats()
+        : n_global(0), acc_local(0), acc_global(0), f_global(0.0f), f_acc(0.0f), f_acc_global(0.0f)
     {
 #pragma unroll
         for (int i = 0; i < D; ++i) sum[i] = sumsq[i] = 0.0f;
@@ -190,12 +203,33 @@ struct ChainStats {
             for (int j = i; j < D; ++j, ++t) gram[t] = fmaf(dl[i], dl[j], gram[t]);
     }
 
+    // glob, moved: 0/1 masks
+    __device__ __forceinline__ void update_masked(float glob, float moved, const float (&theta_new)[D],
+                                                  const float (&theta_prev)[D])
+    {
+        f_global += glob;
+        f_acc += moved;
+        f_acc_global = fmaf(moved, glob, f_acc_global);
+        float dl[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            sum[i] += theta_new[i];
+            sumsq[i] = fmaf(theta_new[i], theta_new[i], sumsq[i]);
+            dl[i] = theta_new[i] - theta_prev[i];
+        }
+        int t = 0;
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = i; j < D; ++j, ++t) gram[t] = fmaf(dl[i], dl[j], gram[t]);
+    }
+
     __device__ __forceinline__ void store(float* st, uint32_t n_steps) const
     {
         st[GLABC_STAT_STEPS] += static_cast<float>(n_steps);
-        st[GLABC_STAT_GLOBAL_STEPS] += static_cast<float>(n_global);
-        st[GLABC_STAT_ACC_LOCAL] += static_cast<float>(acc_local);
-        st[GLABC_STAT_ACC_GLOBAL] += static_cast<float>(acc_global);
+        st[GLABC_STAT_GLOBAL_STEPS] += static_cast<float>(n_global) + f_global;
+        st[GLABC_STAT_ACC_LOCAL] += static_cast<float>(acc_local) + (f_acc - f_acc_global);
+        st[GLABC_STAT_ACC_GLOBAL] += static_cast<float>(acc_global) + f_acc_global;
 #pragma unroll
         for (int i = 0; i < D; ++i) {
             st[GLABC_STAT_SUM + i] += sum[i];

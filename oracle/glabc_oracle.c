@@ -91,8 +91,10 @@ ORACLE_EXPORT void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t ke
     out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
 }
 
-/* native-mode stream layout (DESIGN.md "RNG streams"): counter = (chain_lo, chain_hi, block, slot) */
-enum { SLOT_UNIFORM = 0, SLOT_NORMAL = 1 /* + group index */ };
+/* native-mode stream layout (DESIGN.md "RNG streams"): counter = (chain_lo, chain_hi, block, slot).
+ * slot 1 = the step block: one Philox call carries the 4 normals, U_b (16 bits) and U_a (24 bits) of a
+ * step; slot 2+g = extra normal blocks; slot 0x80000000 = the float64 resampling uniform.           */
+enum { SLOT_STEP = 1, SLOT_NORMAL = 2 /* + group index */ };
 
 static inline void philox_block(uint64_t seed, uint64_t chain, uint32_t block, uint32_t slot, uint32_t out[4])
 {
@@ -101,21 +103,38 @@ static inline void philox_block(uint64_t seed, uint64_t chain, uint32_t block, u
     oracle_philox4x32_10(ctr, key, out);
 }
 
-/* 24-bit uniform on the grid torch.rand uses for float32 */
-static inline float u24(uint32_t w) { return (float)(w >> 8) * 0x1p-24f; }
-
-/* Box-Muller pair from two words */
+/* Box-Muller pair from two words: radius uniform from w0[31:8] (24 bits), angle from w1[31:12] (20) */
 static inline void box_muller(uint32_t w0, uint32_t w1, float* n0, float* n1)
 {
-    const float u1 = fmaf((float)w0, 0x1p-32f, 0x1p-33f);
-    const float u2 = (float)w1 * 0x1p-32f;
+    const float u1 = fmaf((float)(w0 & 0xFFFFFF00u), 0x1p-32f, 0x1p-25f);
     const float r = sqrtf(-2.0f * logf(u1));
-    const float a = 6.28318530717958647692f * u2;
+    const float a = (float)(w1 & 0xFFFFF000u) * (6.28318530717958647692f * 0x1p-32f);
     *n0 = r * cosf(a);
     *n1 = r * sinf(a);
 }
 
-/* n normals for (chain, step): groups of 4 words -> 2 Box-Muller pairs */
+/* the draws of step i: n normals (first four from the step block), U_b on a 16-bit grid, U_a on
+ * torch.rand's 24-bit grid (B-16) */
+static void native_step_draws(uint64_t seed, uint64_t chain, uint32_t step, int n, float* normals, float* u_b, float* u_a)
+{
+    uint32_t w[4];
+    float z[4];
+    philox_block(seed, chain, step, SLOT_STEP, w);
+    box_muller(w[0], w[1], &z[0], &z[1]);
+    box_muller(w[2], w[3], &z[2], &z[3]);
+    for (int j = 0; j < 4 && j < n; ++j) normals[j] = z[j];
+    *u_b = (float)(((w[0] & 0xFFu) << 8) | (w[2] & 0xFFu)) * 0x1p-16f;
+    *u_a = (float)((w[1] & 0xFFFu) | ((w[3] << 12) & 0xFFF000u)) * 0x1p-24f;
+    for (int g = 1; g * 4 < n; ++g) {
+        uint32_t v[4];
+        philox_block(seed, chain, step, SLOT_NORMAL + (uint32_t)(g - 1), v);
+        box_muller(v[0], v[1], &z[0], &z[1]);
+        box_muller(v[2], v[3], &z[2], &z[3]);
+        for (int j = 0; j < 4 && g * 4 + j < n; ++j) normals[g * 4 + j] = z[j];
+    }
+}
+
+/* n normals from the extra blocks slot0, slot0+1, ... of (chain, step) */
 static void native_normals(uint64_t seed, uint64_t chain, uint32_t step, uint32_t slot0, int n, float* out)
 {
     for (int g = 0; g * 4 < n; ++g) {
@@ -126,16 +145,6 @@ static void native_normals(uint64_t seed, uint64_t chain, uint32_t step, uint32_
         box_muller(w[2], w[3], &z[2], &z[3]);
         for (int j = 0; j < 4 && g * 4 + j < n; ++j) out[g * 4 + j] = z[j];
     }
-}
-
-/* the two uniforms of step i: block i>>1 of the uniform slot serves steps 2j and 2j+1 */
-static void native_uniforms(uint64_t seed, uint64_t chain, uint32_t step, float* u_b, float* u_a)
-{
-    uint32_t w[4];
-    philox_block(seed, chain, step >> 1, SLOT_UNIFORM, w);
-    const int h = (int)(step & 1u);
-    *u_b = u24(w[2 * h]);
-    *u_a = u24(w[2 * h + 1]);
 }
 
 /* -------------------------------------------------------------------------------------------
@@ -307,9 +316,8 @@ static void run_global_range(void* vctx, int64_t c_begin, int64_t c_end)
                 for (int k = 0; k < yd; ++k) eps_s[k] = t[(size_t)(1 + d + k) * C];
                 u_a = t[(size_t)(1 + d + yd) * C];
             } else {
-                float z[2 * GLABC_MAX_DIM];
-                native_uniforms(r->seed, (uint64_t)(r->chain_id_base + c), (uint32_t)i, &u_b, &u_a);
-                native_normals(r->seed, (uint64_t)(r->chain_id_base + c), (uint32_t)i, SLOT_NORMAL, d + yd, z);
+                float z[2 * GLABC_MAX_DIM + 4];
+                native_step_draws(r->seed, (uint64_t)(r->chain_id_base + c), (uint32_t)i, d + yd, z, &u_b, &u_a);
                 memcpy(eps_p, z, sizeof(float) * d);
                 memcpy(eps_s, z + d, sizeof(float) * yd);
             }
@@ -436,16 +444,22 @@ static void run_isir_range(void* vctx, int64_t c_begin, int64_t c_end)
                 u_a = t[(size_t)(1 + K * d + K * yd) * C];
                 u64 = r->tape64[(size_t)s * C + c];
             } else {
-                /* native streams: uniforms as GlobalMCMC; candidate j uses normal slot group
-                 * SLOT_NORMAL + j*G.. (G = groups per candidate); the float64 resampling uniform
-                 * is built from 53 bits of uniform-slot block 2^31 + i.                          */
+                /* native streams: the step block gives U_b, U_a and the normals of a local move
+                 * (as GlobalMCMC); candidate j of a global move uses normal blocks SLOT_NORMAL + 8 +
+                 * j*G .. (G = blocks per candidate); the float64 resampling uniform is built from 53
+                 * bits of block (i, slot 2^31).                                                     */
                 const int G = (d + yd + 3) / 4;
-                native_uniforms(r->seed, gid, (uint32_t)i, &u_b, &u_a);
+                float zl[2 * GLABC_MAX_DIM + 4];
+                native_step_draws(r->seed, gid, (uint32_t)i, d + yd, zl, &u_b, &u_a);
                 for (int j = 0; j < K; ++j) {
                     float z[2 * GLABC_MAX_DIM + 4];
-                    native_normals(r->seed, gid, (uint32_t)i, SLOT_NORMAL + (uint32_t)(j * G), d + yd, z);
+                    native_normals(r->seed, gid, (uint32_t)i, SLOT_NORMAL + 8u + (uint32_t)(j * G), d + yd, z);
                     memcpy(eps_p + j * d, z, sizeof(float) * d);
                     memcpy(eps_s + j * yd, z + d, sizeof(float) * yd);
+                }
+                if (!(u_b < gf)) { /* local move: its proposal / simulator normals come from the step block */
+                    memcpy(eps_p, zl, sizeof(float) * d);
+                    memcpy(eps_s, zl + d, sizeof(float) * yd);
                 }
                 uint32_t w[4];
                 philox_block(r->seed, gid, (uint32_t)i, 0x80000000u, w);
