@@ -27,8 +27,8 @@ ALG_BYTES_PER_STEP = 8       # one float32 trace row of d=2
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=10)
-    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--steps", type=int, default=200)
+    p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="native", choices=["native", "reference"])
     p.add_argument("--chains", type=int, default=65536, help="chains per GPU (weak scaling)")
     p.add_argument("--iters", type=int, default=10000, help="num_ite per chain (trace rows)")
@@ -111,10 +111,13 @@ def cpu_port_rate(chains, iters, seconds, threads=0):
                    trace_layout=abi.TRACE_CHAIN_MAJOR, threads=threads)
         return time.perf_counter() - t0
 
-    c = max(cores * 8, 64)
-    dt = run(c, 2000)                       # calibration
-    rate = c * 2000 / dt
     t = min(iters - 1, 9999)
+    c = max(cores * 4, 64)
+    dt = run(c, t)                          # calibration passes (thread start-up dominates tiny runs)
+    while dt < min(1.0, seconds / 4) and c < chains:
+        c = min(chains, c * 4)
+        dt = run(c, t)
+    rate = c * t / dt
     c = int(max(cores, min(chains, rate * seconds / t)))
     dt = run(c, t)
     return c * t / dt, cores, f"{c} chains x {t} transitions of the same workload, full trace in host memory, {dt:.1f} s"
@@ -203,14 +206,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for w in range(a.warmup):
         one_step(w)
     # kernel-only duration of the dominant kernel, CUDA events on the launching stream
-    barrier()
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ms = []
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    barrier()
+    n_idle = len(sampler.rows)   # samples taken before the timed region are dropped
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -218,6 +222,7 @@ def main():
         one_step(a.warmup + s)
     e1.record()
     barrier()
+    sampler.rows = sampler.rows[max(0, n_idle - 1):]
     clocks = sampler.stop()
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
     if world > 1:
@@ -227,7 +232,7 @@ def main():
     value = steps_per_pass * a.steps / (total_ms * 1e-3)
 
     # the step kernel alone (no state reset / summary kernels around it)
-    for s in range(a.steps):
+    for s in range(min(a.steps, 20)):
         theta.copy_(theta0)
         y.copy_(y0)
         k0.record()

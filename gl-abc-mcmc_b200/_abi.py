@@ -81,7 +81,7 @@ def fill(arr, values):
 
 LIB_NAME = "libglabc.so"
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", LIB_NAME)
+LIB_PATH = os.environ.get("GLABC_LIB") or os.path.join(_HERE, "csrc", LIB_NAME)  # GLABC_LIB: kernel-experiment builds
 
 # every symbol include/glabc.h declares (tests/test_abi_symbols.py parses the header and checks)
 _SIGNATURES = {

@@ -32,16 +32,20 @@ def _deps():
            [os.path.join(ROOT, "include", "glabc.h")]
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, variant=None, extra_flags=()):
+    """`variant` builds csrc/libglabc.<variant>.so with `extra_flags` (kernel experiments; select it
+    at run time with GLABC_LIB=<path>)."""
+    lib_path = LIB if variant is None else os.path.join(CSRC, f"libglabc.{variant}.so")
     newest = max(os.path.getmtime(p) for p in _deps())
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest:
-        return LIB
+    if not force and os.path.exists(lib_path) and os.path.getmtime(lib_path) >= newest:
+        return lib_path
     nvcc = _nvcc()
     logs = {}
+    tag = "" if variant is None else "." + variant
 
     def compile_one(src):
-        obj = os.path.join(CSRC, src[:-3] + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(CSRC, src[:-3] + tag + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-c", os.path.join(CSRC, src), "-o", obj]
         p = subprocess.run(cmd, capture_output=True, text=True)
         logs[src] = p.stderr + p.stdout
         if p.returncode != 0:
@@ -51,16 +55,16 @@ def build(force=False, verbose=False):
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     # -cudart static (nvcc default): the library loads on a box without a GPU or libcudart.so
-    p = subprocess.run([nvcc, "-shared", "-o", LIB, *objs, "-Xcompiler", "-fvisibility=hidden"], capture_output=True, text=True)
+    p = subprocess.run([nvcc, "-shared", "-o", lib_path, *objs, "-Xcompiler", "-fvisibility=hidden"], capture_output=True, text=True)
     if p.returncode != 0:
         raise RuntimeError("link failed:\n" + p.stderr)
-    with open(os.path.join(CSRC, "ptxas.log"), "w") as f:
+    with open(os.path.join(CSRC, f"ptxas{tag}.log"), "w") as f:
         for src in SOURCES:
             f.write(f"==== {src}\n{logs[src]}\n")
     if verbose:
         for src in SOURCES:
             sys.stderr.write(logs[src])
-    return LIB
+    return lib_path
 
 
 if __name__ == "__main__":

@@ -148,6 +148,67 @@ struct ChainMajorWriter {
     }
 };
 
+// D in {1, 2, 4}: a row is one 4/8/16-byte vector, so the tile is [32 rows][33] vectors — a lane
+// stores its chain's row with one STS (consecutive lanes, conflict-free), and a flush reads column c
+// with one LDS per lane (lane = row; pitch 33 keeps the 64/128-bit phases conflict-free) and writes
+// chain c's 32 rows as ONE coalesced store instruction of 32 vectors (128/256/512 contiguous bytes).
+template <int D>
+struct ChainMajorVecWriter {
+    using V = typename VecOf<D>::type;
+    static constexpr int kPitch = 33;
+    static constexpr int smem_floats_per_warp = 32 * kPitch * D;
+    V* tile;
+    V* out;            // &trace[chain0_of_warp][0] in vector units
+    int64_t chain_stride;  // vectors per chain
+    uint32_t row0;
+    int32_t count, lane, chains_in_warp;
+
+    __device__ __forceinline__ ChainMajorVecWriter(const RunParams& r, int32_t, bool, float* smem_warp)
+        : tile(reinterpret_cast<V*>(smem_warp)), chain_stride(r.trace_rows), row0(0), count(0), lane(threadIdx.x & 31)
+    {
+        const int32_t chain0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u);
+        out = reinterpret_cast<V*>(r.trace) + (r.trace_chain_off + chain0) * chain_stride;
+        chains_in_warp = min(32, r.n_chains - chain0);
+    }
+
+    __device__ __forceinline__ void put(const RunParams&, uint32_t row, const float (&v)[D])
+    {
+        if (count == 0) row0 = row;
+        V x;
+        if constexpr (D == 1) x = v[0];
+        else if constexpr (D == 2) x = make_float2(v[0], v[1]);
+        else x = make_float4(v[0], v[1], v[2], v[3]);
+        tile[count * kPitch + lane] = x;
+        ++count;
+    }
+
+    __device__ __forceinline__ void maybe_flush(const RunParams& r, uint32_t row)
+    {
+        if (((row + 1u) & 31u) == 0u) flush(r);
+    }
+
+    __device__ __forceinline__ void flush(const RunParams& r)
+    {
+        __syncwarp();
+        V* dst = out + (static_cast<int64_t>(row0) - r.trace_row_base) + lane;
+        const V* src = tile + lane * kPitch;
+        if (count == 32 && chains_in_warp == 32) {
+#pragma unroll 8
+            for (int32_t c = 0; c < 32; ++c) dst[c * chain_stride] = src[c];
+        } else {
+            for (int32_t c = 0; c < chains_in_warp; ++c)
+                if (lane < count) dst[c * chain_stride] = src[c];
+        }
+        __syncwarp();
+        count = 0;
+    }
+
+    __device__ __forceinline__ void finish(const RunParams& r)
+    {
+        if (count > 0) flush(r);
+    }
+};
+
 struct NoTraceWriter {
     __device__ __forceinline__ NoTraceWriter(const RunParams&, int32_t, bool, float*) {}
     template <int D>
@@ -160,7 +221,8 @@ struct NoTraceWriter {
 template <int D, int LAYOUT> struct WriterFor;
 template <int D> struct WriterFor<D, GLABC_TRACE_NONE> { using type = NoTraceWriter; };
 template <int D> struct WriterFor<D, GLABC_TRACE_TIME_MAJOR> { using type = TimeMajorWriter<D>; };
-template <int D> struct WriterFor<D, GLABC_TRACE_CHAIN_MAJOR> { using type = ChainMajorWriter<D>; };
+template <int D> struct WriterFor<D, GLABC_TRACE_CHAIN_MAJOR> { using type = ChainMajorVecWriter<D>; };
+template <> struct WriterFor<3, GLABC_TRACE_CHAIN_MAJOR> { using type = ChainMajorWriter<3>; };
 
 // ---------------------------------------------------------------------------------------------
 // Per-chain statistics (layout: GLABC_STAT_* in glabc.h)

