@@ -90,55 +90,71 @@ def workload_objects():
     return model, lp, gp
 
 
-def cpu_port_rate(chains, iters, seconds, threads=0):
-    """The oracle (C restatement of GlobalMCMC.py:37-68, native Philox mode) on the host cores, on a
-    bounded sample of the workload sized to ~`seconds` of wall time.  Returns (steps/s, cores, sample)."""
-    import numpy as np
-    from glabc_b200 import _abi as abi
-    from glabc_b200.models import lower_model, lower_proposal
-    from oracle import oracle
-    model, lp, gp = workload_objects()
-    mp, lpp, gpp = lower_model(model), lower_proposal(lp), lower_proposal(gp)
-    oracle.lib().oracle_set_num_threads(threads)
-    cores = oracle.lib().oracle_num_threads()
+class CpuPort:
+    """The oracle (C restatement of GlobalMCMC.py:37-68, native Philox mode) on the host cores, run on
+    bounded samples of the workload (the full 65,536 x 1e4 job would take ~10 s per pass per 100 M
+    steps/s of host throughput)."""
 
-    def run(c, t):
+    def __init__(self, threads=0):
+        from glabc_b200.models import lower_model, lower_proposal
+        from oracle import oracle
+        self.oracle = oracle
+        model, lp, gp = workload_objects()
+        self.pods = (lower_model(model), lower_proposal(lp), lower_proposal(gp))
+        self.threads = threads
+        oracle.lib().oracle_set_num_threads(threads)
+        self.cores = oracle.lib().oracle_num_threads()
+
+    def run(self, c, t):
+        import numpy as np
+        from glabc_b200 import _abi as abi
         theta = np.zeros((c, 2), np.float32)
         y = (np.random.default_rng(0).standard_normal((c, 2)) * 0.2236).astype(np.float32)
         trace = np.zeros((c, t + 1, 2), np.float32)
         t0 = time.perf_counter()
-        oracle.run("global", mp, lpp, gpp, theta=theta, y=y, n_steps=t, gf=0.5, seed=0, trace=trace,
-                   trace_layout=abi.TRACE_CHAIN_MAJOR, threads=threads)
+        self.oracle.run("global", *self.pods, theta=theta, y=y, n_steps=t, gf=0.5, seed=0, trace=trace,
+                        trace_layout=abi.TRACE_CHAIN_MAJOR, threads=self.threads)
         return time.perf_counter() - t0
 
-    t = min(iters - 1, 9999)
-    c = max(cores * 4, 64)
-    dt = run(c, t)                          # calibration passes (thread start-up dominates tiny runs)
-    while dt < min(1.0, seconds / 4) and c < chains:
-        c = min(chains, c * 4)
-        dt = run(c, t)
-    rate = c * t / dt
-    c = int(max(cores, min(chains, rate * seconds / t)))
-    dt = run(c, t)
-    return c * t / dt, cores, f"{c} chains x {t} transitions of the same workload, full trace in host memory, {dt:.1f} s"
+    def size_sample(self, chains, iters, seconds):
+        """chains x transitions of the workload that take about `seconds` on this host"""
+        t = min(iters - 1, 9999)
+        c = max(self.cores * 4, 64)
+        dt = self.run(c, t)                     # calibration (thread start-up dominates tiny runs)
+        while dt < min(1.0, seconds / 4) and c < chains:
+            c = min(chains, c * 4)
+            dt = self.run(c, t)
+        c = int(max(self.cores, min(chains, c * seconds / dt)))
+        return c, t
+
+
+def cpu_port_rate(chains, iters, seconds, threads=0):
+    port = CpuPort(threads)
+    c, t = port.size_sample(chains, iters, seconds)
+    dt = port.run(c, t)
+    return c * t / dt, port.cores, f"{c} chains x {t} transitions of the same workload, full trace in host memory, {dt:.1f} s"
 
 
 def bench_reference(a, rank):
+    """--impl reference: the reference's CPU path (its C port, all host threads), one bounded sample per step,
+    sized so the whole run ends within ~2 minutes."""
     if rank != 0:
         return
-    rates = []
-    sample = ""
-    per_step = max(2.0, min(a.cpu_seconds, 120.0 / max(1, a.steps + a.warmup)))
+    port = CpuPort()
+    per_step = max(0.2, min(a.cpu_seconds, 100.0 / max(1, a.steps + a.warmup)))
+    c, t = port.size_sample(a.chains, a.iters, per_step)
+    times = []
     for i in range(a.warmup + a.steps):
-        r, cores, sample = cpu_port_rate(a.chains, a.iters, per_step)
+        dt = port.run(c, t)
         if i >= a.warmup:
-            rates.append(r)
-    value = sum(rates) / len(rates)
+            times.append(dt)
+    value = c * t * len(times) / sum(times)
+    sample = f"{c} chains x {t} transitions of the same workload per step, full trace in host memory, {sum(times) / len(times):.2f} s per step"
     line = {"impl": "reference", "metric": "abc_mcmc_chain_steps_per_sec", "value": value, "unit": "chain-steps/s",
-            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": None, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(a),
-            "cpu_baseline": {"value": value, "unit": "chain-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "chain-steps/s", "cores": port.cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
