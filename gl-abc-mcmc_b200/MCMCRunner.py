@@ -20,3 +20,12 @@ class MCMCRunner:
         return GlobalMCMC(ABCset=self.abc_set, num_ite=num_iterations, Initial_theta=initial_theta,
                           Initial_y=initial_y, Global_Proposal=global_proposal, filelocation=self._path(output_file),
                           global_frequency=global_frequency, Local_Proposal=local_proposal, **kw)
+
+    def run_glmcmc(self, num_iterations, initial_theta, initial_y, global_frequency, local_proposal,
+                   importance_proposal, batch_size, output_file="glmcmc_results.csv", **kw):
+        """reference MCMCRunner.py:35-53"""
+        from .GLMCMC import GLMCMC
+        return GLMCMC(ABCset=self.abc_set, num_ite=num_iterations, Initial_theta=initial_theta, Initial_y=initial_y,
+                      Local_Proposal=local_proposal, filelocation=self._path(output_file),
+                      global_frequency=global_frequency, Importance_Proposal=importance_proposal,
+                      batch_size=batch_size, **kw)

@@ -68,7 +68,7 @@ class RunPOD(C.Structure):
                 ("trace_row_base", C.c_int64),
                 ("theta", C.c_void_p), ("y", C.c_void_p), ("aux", C.c_void_p), ("trace", C.c_void_p),
                 ("stats", C.c_void_p), ("tape32", C.c_void_p), ("tape64", C.c_void_p), ("debug", C.c_void_p),
-                ("tape_dump", C.c_void_p), ("stream", C.c_void_p)]
+                ("tape_dump", C.c_void_p), ("tape64_dump", C.c_void_p), ("stream", C.c_void_p)]
 
 
 def fill(arr, values):
@@ -95,6 +95,8 @@ _SIGNATURES = {
     "glabc_dist_set": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(DistPOD), C.c_size_t]),
     "glabc_run_global": (C.c_int, [C.c_void_p, C.POINTER(RunPOD)]),
     "glabc_run_global_host": (C.c_int, [C.c_void_p, C.POINTER(RunPOD), C.c_int64]),
+    "glabc_run_isir": (C.c_int, [C.c_void_p, C.POINTER(RunPOD)]),
+    "glabc_run_isir_host": (C.c_int, [C.c_void_p, C.POINTER(RunPOD), C.c_int64]),
     "glabc_esjd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "glabc_philox_kat": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
 }

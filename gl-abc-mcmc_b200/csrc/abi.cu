@@ -262,6 +262,7 @@ static int make_run_params(glabc_ctx* ctx, const glabc_run_t* run, int dim, int 
     r.tape64 = run->tape64;
     r.debug = run->debug;
     r.tape_dump = run->tape_dump;
+    r.tape64_dump = run->tape64_dump;
     r.n_candidates = run->n_candidates;
     (void)dim;
     *out = r;
@@ -271,7 +272,7 @@ static int make_run_params(glabc_ctx* ctx, const glabc_run_t* run, int dim, int 
 // ---------------------------------------------------------------------------------------------
 // sampler dispatch (device buffers)
 // ---------------------------------------------------------------------------------------------
-enum SamplerKind { SAMPLER_GLOBAL = 0 };
+enum SamplerKind { SAMPLER_GLOBAL = 0, SAMPLER_ISIR = 1 };
 
 static int run_device(glabc_ctx* ctx, SamplerKind kind, const glabc_run_t* run)
 {
@@ -294,6 +295,26 @@ static int run_device(glabc_ctx* ctx, SamplerKind kind, const glabc_run_t* run)
         CUDA_TRY(ctx, launch_global_mcmc(make_model(ctx->model), make_gauss(lp.a, lp.b, lp.c, d), make_gauss(gp.a, gp.b, gp.c, d),
                                          d, R, run->arith_mode == GLABC_ARITH_STRICT, run->rng_mode == GLABC_RNG_REPLAY,
                                          run->trace_layout, block, static_cast<cudaStream_t>(run->stream)));
+        return GLABC_OK;
+    }
+    case SAMPLER_ISIR: {
+        if (!ctx->has_dist[GLABC_SLOT_LOCAL] || !ctx->has_dist[GLABC_SLOT_IMPORTANCE])
+            return fail(ctx, GLABC_ERR_INVALID, "run_isir needs the LOCAL and IMPORTANCE proposal slots bound");
+        const glabc_dist_t& lp = ctx->dist[GLABC_SLOT_LOCAL];
+        const glabc_dist_t& ip = ctx->dist[GLABC_SLOT_IMPORTANCE];
+        if (lp.dim != d || ip.dim != d) return fail(ctx, GLABC_ERR_INVALID, "proposal dim does not match theta_dim %d", d);
+        if (!run) return fail(ctx, GLABC_ERR_INVALID, "null run description");
+        if (run->n_candidates < 1 || run->n_candidates > GLABC_MAX_K)
+            return fail(ctx, GLABC_ERR_INVALID, "n_candidates (batch_size) must be in 1..%d", GLABC_MAX_K);
+        if (!run->aux) return fail(ctx, GLABC_ERR_INVALID, "run_isir needs the aux state [C][%d] (log-weight, local flag)", GLABC_AUX_SLOTS);
+        int st = make_run_params(ctx, run, d, GLABC_TAPE_ISIR_SLOTS(d, d, run->n_candidates), &R, &block);
+        if (st) return st;
+        if (run->rng_mode == GLABC_RNG_REPLAY && !run->tape64)
+            return fail(ctx, GLABC_ERR_INVALID, "replay of run_isir needs tape64 (the float64 resampling uniforms)");
+        if (R.n_chains == 0) return GLABC_OK;
+        CUDA_TRY(ctx, launch_isir(make_model(ctx->model), make_gauss(lp.a, lp.b, lp.c, d), make_gauss(ip.a, ip.b, ip.c, d), d, R,
+                                  run->arith_mode == GLABC_ARITH_STRICT, run->rng_mode == GLABC_RNG_REPLAY,
+                                  run->trace_layout, block, static_cast<cudaStream_t>(run->stream)));
         return GLABC_OK;
     }
     }
@@ -439,6 +460,13 @@ int glabc_run_global(glabc_ctx* ctx, const glabc_run_t* run) { return run_device
 int glabc_run_global_host(glabc_ctx* ctx, const glabc_run_t* run, int64_t chunk_steps)
 {
     return run_host(ctx, SAMPLER_GLOBAL, run, chunk_steps);
+}
+
+int glabc_run_isir(glabc_ctx* ctx, const glabc_run_t* run) { return run_device(ctx, SAMPLER_ISIR, run); }
+
+int glabc_run_isir_host(glabc_ctx* ctx, const glabc_run_t* run, int64_t chunk_steps)
+{
+    return run_host(ctx, SAMPLER_ISIR, run, chunk_steps);
 }
 
 int glabc_esjd(glabc_ctx* ctx, const float* trace, int32_t layout, int64_t rows, int64_t chains, int32_t dim, float* out,

@@ -32,6 +32,7 @@ struct RunParams {
     const double* tape64;
     float* debug;
     float* tape_dump;
+    double* tape64_dump;
     int32_t n_candidates;
 };
 

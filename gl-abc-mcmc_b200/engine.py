@@ -102,11 +102,12 @@ class Engine:
     def run(self, sampler, *, theta, y, n_steps, gf, step_base=0, chain_id_base=0, seed=0,
             rng_mode=_abi.RNG_NATIVE, arith=_abi.ARITH_FAST, trace_layout=_abi.TRACE_CHAIN_MAJOR, trace=None,
             trace_rows=None, trace_chains=None, trace_chain_off=0, trace_row_base=0, write_row0=True,
-            stats=None, aux=None, tape32=None, tape64=None, debug=None, tape_dump=None, K=0, block_threads=0):
+            stats=None, aux=None, tape32=None, tape64=None, debug=None, tape_dump=None, tape64_dump=None, K=0,
+            block_threads=0):
         """Enqueue `n_steps` transitions of every chain on the current stream (device tensors,
         state updated in place).  Returns the trace tensor (allocated here unless given)."""
         cn, d = theta.shape
-        for t in (theta, y, stats, aux, tape32, tape64, debug, tape_dump, trace):
+        for t in (theta, y, stats, aux, tape32, tape64, debug, tape_dump, tape64_dump, trace):
             if t is not None and (not t.is_cuda or not t.is_contiguous()):
                 raise ValueError("device entry point takes contiguous CUDA tensors")
         rows = trace_rows if trace_rows is not None else step_base + n_steps + 1 - trace_row_base
@@ -121,7 +122,7 @@ class Engine:
                         trace_chain_off=trace_chain_off, trace_row_base=trace_row_base,
                         theta=self._ptr(theta), y=self._ptr(y), aux=self._ptr(aux), trace=self._ptr(trace),
                         stats=self._ptr(stats), tape32=self._ptr(tape32), tape64=self._ptr(tape64),
-                        debug=self._ptr(debug), tape_dump=self._ptr(tape_dump),
+                        debug=self._ptr(debug), tape_dump=self._ptr(tape_dump), tape64_dump=self._ptr(tape64_dump),
                         stream=C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
         fn = getattr(self.lib, "glabc_run_" + sampler)
         self.ctx.check(fn(self.ctx.handle, C.byref(r)))

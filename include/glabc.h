@@ -166,6 +166,7 @@ typedef struct {
     /* native mode only */
     float* tape_dump;         /* [n_steps][tape_slots][n_chains]: the draws the kernel used, in tape
                                  layout, so a replay (or the CPU oracle) can re-run the same chain */
+    double* tape64_dump;      /* [n_steps][n_chains]: the float64 resampling uniforms used (iSIR)   */
     void* stream;
 } glabc_run_t;
 
@@ -211,10 +212,16 @@ GLABC_API int glabc_dist_set(glabc_ctx* ctx, int slot, const glabc_dist_t* dist,
 /* GlobalMCMC loop body, GlobalMCMC.py:37-68 (local RW-MH / global independence-MH mixture)       */
 GLABC_API int glabc_run_global(glabc_ctx* ctx, const glabc_run_t* run);
 
+/* GLMCMC loop body, GLMCMC.py:58-104, incl. weight_sampling GLMCMC.py:7-22: iSIR global move with
+ * `n_candidates` fresh draws from the IMPORTANCE slot, local RW-MH from the LOCAL slot.  `aux` carries
+ * the cached log-weight and the `local` flag (init {0, 1}, GLMCMC.py:49-55).                        */
+GLABC_API int glabc_run_isir(glabc_ctx* ctx, const glabc_run_t* run);
+
 /* ---- samplers: host buffers (the reference-facing call: H2D state, run, D2H trace + stats) --- */
 /* `run->theta`, `y`, `trace`, `stats` are HOST pointers here; the trace is copied back in
  * `chunk_steps`-row chunks overlapped with the next chunk's kernel (0 = library default).        */
 GLABC_API int glabc_run_global_host(glabc_ctx* ctx, const glabc_run_t* run, int64_t chunk_steps);
+GLABC_API int glabc_run_isir_host(glabc_ctx* ctx, const glabc_run_t* run, int64_t chunk_steps);
 
 /* ---- diagnostics --------------------------------------------------------------------------- */
 /* esjd(), ESJD.py:2-25, for every chain of a device trace: out[c] = det(D^T D/(N-1))^(1/d).

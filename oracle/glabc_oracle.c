@@ -461,9 +461,14 @@ static void run_isir_range(void* vctx, int64_t c_begin, int64_t c_end)
                     memcpy(eps_p, zl, sizeof(float) * d);
                     memcpy(eps_s, zl + d, sizeof(float) * yd);
                 }
-                uint32_t w[4];
-                philox_block(r->seed, gid, (uint32_t)i, 0x80000000u, w);
-                u64 = (double)((((uint64_t)w[0] << 32) | w[1]) >> 11) * 0x1p-53;
+                /* 53-bit resampling uniform: the step block's 24-bit U_a field on top of the spare
+                 * U_a (24) / U_b (top 5) fields of candidate 0's first normal block */
+                uint32_t w0[4], c0[4];
+                philox_block(r->seed, gid, (uint32_t)i, SLOT_STEP, w0);
+                philox_block(r->seed, gid, (uint32_t)i, SLOT_NORMAL + 8u, c0);
+                const uint64_t ua_step = (w0[1] & 0xFFFu) | ((w0[3] << 12) & 0xFFF000u);
+                const uint64_t ua_c0 = (c0[1] & 0xFFFu) | ((c0[3] << 12) & 0xFFF000u);
+                u64 = (double)((ua_step << 29) | (ua_c0 << 5) | ((c0[0] & 0xFFu) >> 3)) * 0x1p-53;
             }
 
             const int is_global = u_b < gf; /* GLMCMC.py:59 */
