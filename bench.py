@@ -20,8 +20,15 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-ALG_INST_PER_STEP = 186      # thread-instructions per chain-step (Philox4x32-10 + Box-Muller floor)
 ALG_BYTES_PER_STEP = 8       # one float32 trace row of d=2
+# algorithmic thread-instructions per chain-step (Philox4x32-10 + Box-Muller floor)
+#   global: GlobalMCMC.py:37-68 = 186;  glmcmc: GLMCMC.py:58-104, K=5, gf=0.9 = 0.9*760 + 0.1*186 = 703
+SAMPLERS = {
+    "global": dict(entry="global", gf=0.5, K=0, alg_inst=186,
+                   workload="README Mixture_set GlobalMCMC (BASELINE configs[1])"),
+    "glmcmc": dict(entry="isir", gf=0.9, K=5, alg_inst=703,
+                   workload="README Mixture_set GLMCMC iSIR K=5, gf=0.9 (BASELINE configs[2], run_glmcmc)"),
+}
 
 
 def parse():
@@ -30,6 +37,7 @@ def parse():
     p.add_argument("--steps", type=int, default=200)
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="native", choices=["native", "reference"])
+    p.add_argument("--sampler", default="global", choices=sorted(SAMPLERS), help="which fused step kernel to time")
     p.add_argument("--chains", type=int, default=65536, help="chains per GPU (weak scaling)")
     p.add_argument("--iters", type=int, default=10000, help="num_ite per chain (trace rows)")
     p.add_argument("--layout", default="chain", choices=["chain", "time", "none"])
@@ -95,7 +103,8 @@ class CpuPort:
     bounded samples of the workload (the full 65,536 x 1e4 job would take ~10 s per pass per 100 M
     steps/s of host throughput)."""
 
-    def __init__(self, threads=0):
+    def __init__(self, threads=0, sampler="global"):
+        self.spec = SAMPLERS[sampler]
         from glabc_b200.models import lower_model, lower_proposal
         from oracle import oracle
         self.oracle = oracle
@@ -111,9 +120,13 @@ class CpuPort:
         theta = np.zeros((c, 2), np.float32)
         y = (np.random.default_rng(0).standard_normal((c, 2)) * 0.2236).astype(np.float32)
         trace = np.zeros((c, t + 1, 2), np.float32)
+        aux = None
+        if self.spec["K"]:
+            aux = np.zeros((c, abi.AUX_SLOTS), np.float32)
+            aux[:, abi.AUX_LOCAL] = 1.0
         t0 = time.perf_counter()
-        self.oracle.run("global", *self.pods, theta=theta, y=y, n_steps=t, gf=0.5, seed=0, trace=trace,
-                        trace_layout=abi.TRACE_CHAIN_MAJOR, threads=self.threads)
+        self.oracle.run(self.spec["entry"], *self.pods, theta=theta, y=y, n_steps=t, gf=self.spec["gf"], seed=0,
+                        trace=trace, trace_layout=abi.TRACE_CHAIN_MAJOR, threads=self.threads, K=self.spec["K"], aux=aux)
         return time.perf_counter() - t0
 
     def size_sample(self, chains, iters, seconds):
@@ -128,8 +141,8 @@ class CpuPort:
         return c, t
 
 
-def cpu_port_rate(chains, iters, seconds, threads=0):
-    port = CpuPort(threads)
+def cpu_port_rate(chains, iters, seconds, threads=0, sampler="global"):
+    port = CpuPort(threads, sampler)
     c, t = port.size_sample(chains, iters, seconds)
     dt = port.run(c, t)
     return c * t / dt, port.cores, f"{c} chains x {t} transitions of the same workload, full trace in host memory, {dt:.1f} s"
@@ -140,7 +153,7 @@ def bench_reference(a, rank):
     sized so the whole run ends within ~2 minutes."""
     if rank != 0:
         return
-    port = CpuPort()
+    port = CpuPort(sampler=a.sampler)
     per_step = max(0.2, min(a.cpu_seconds, 100.0 / max(1, a.steps + a.warmup)))
     c, t = port.size_sample(a.chains, a.iters, per_step)
     times = []
@@ -160,9 +173,10 @@ def bench_reference(a, rank):
 
 
 def workload_config(a):
-    return {"workload": "README Mixture_set GlobalMCMC (BASELINE configs[1])", "chains_per_gpu": a.chains,
-            "iterations": a.iters, "theta_dim": 2, "epsilon": 0.05, "global_frequency": 0.5,
-            "local_sigma": 0.35, "global_proposal": "N(0,I)", "trace": {"chain": "full float32 [C,T,2]",
+    spec = SAMPLERS[a.sampler]
+    return {"workload": spec["workload"], "chains_per_gpu": a.chains,
+            "iterations": a.iters, "theta_dim": 2, "epsilon": 0.05, "global_frequency": spec["gf"],
+            "local_sigma": 0.35, "global_proposal": "N(0,I)", "isir_candidates": spec["K"], "trace": {"chain": "full float32 [C,T,2]",
             "time": "full float32 [T,C,2]", "none": "statistics only"}[a.layout], "rng": "philox4x32-10 native",
             "arith": "fast", "l2": "no re-read inputs; 5.2 GB trace written per step >> 126 MB L2",
             "parallelism": f"chains sharded over {a.gpus} GPU(s), no data-path collective"}
@@ -192,6 +206,9 @@ def main():
     eng.bind_model(model)
     eng.bind_proposal(abi.SLOT_LOCAL, lp)
     eng.bind_proposal(abi.SLOT_GLOBAL, gp)
+    eng.bind_proposal(abi.SLOT_IMPORTANCE, gp)   # README.md:125: the iSIR importance proposal is the same N(0,I)
+    spec = SAMPLERS[a.sampler]
+    entry, gf, K = spec["entry"], spec["gf"], spec["K"]
     info = eng.ctx.device_info()
 
     C, T, d = a.chains, a.iters, 2
@@ -205,15 +222,25 @@ def main():
         trace = torch.empty((C, T, d) if layout == abi.TRACE_CHAIN_MAJOR else (T, C, d), device="cuda")
     theta, y = theta0.clone(), y0.clone()
     stats = torch.zeros(C, abi.nstats(d), device="cuda")
+    aux0 = aux = None
+    if K:
+        aux0 = torch.zeros(C, abi.AUX_SLOTS, device="cuda")
+        aux0[:, abi.AUX_LOCAL] = 1.0
+        aux = aux0.clone()
     summary = None
+
+    def reset_state():
+        theta.copy_(theta0)
+        y.copy_(y0)
+        if K:
+            aux.copy_(aux0)
 
     def one_step(step_idx):
         nonlocal summary
-        theta.copy_(theta0)
-        y.copy_(y0)
+        reset_state()
         stats.zero_()
-        eng.run("global", theta=theta, y=y, n_steps=T - 1, gf=0.5, seed=step_idx, chain_id_base=chain_base,
-                trace_layout=layout, trace=trace, trace_rows=T, stats=stats, block_threads=a.block)
+        eng.run(entry, theta=theta, y=y, n_steps=T - 1, gf=gf, seed=step_idx, chain_id_base=chain_base,
+                trace_layout=layout, trace=trace, trace_rows=T, stats=stats, block_threads=a.block, K=K, aux=aux)
         rs = RunStats(stats, d)
         summary = sharding.allreduce_summary(sharding.summarize(rs))   # NCCL only for N > 1
 
@@ -249,11 +276,10 @@ def main():
 
     # the step kernel alone (no state reset / summary kernels around it)
     for s in range(min(a.steps, 20)):
-        theta.copy_(theta0)
-        y.copy_(y0)
+        reset_state()
         k0.record()
-        eng.run("global", theta=theta, y=y, n_steps=T - 1, gf=0.5, seed=s, chain_id_base=chain_base,
-                trace_layout=layout, trace=trace, trace_rows=T, stats=stats, block_threads=a.block)
+        eng.run(entry, theta=theta, y=y, n_steps=T - 1, gf=gf, seed=s, chain_id_base=chain_base,
+                trace_layout=layout, trace=trace, trace_rows=T, stats=stats, block_threads=a.block, K=K, aux=aux)
         k1.record()
         torch.cuda.synchronize()
         kernel_ms.append(k0.elapsed_time(k1))
@@ -269,11 +295,11 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     sm_max_mhz = float(peaks.get("sm_max_mhz", clocks.get("sm_max_mhz") or 1965.0))
     inst_peak = info["sm_count"] * 128 * sm_max_mhz * 1e6 / 1e9            # G thread-inst/s at max clock
-    inst_ach = kernel_rate * ALG_INST_PER_STEP / 1e9
+    inst_ach = kernel_rate * spec["alg_inst"] / 1e9
     hbm_ach = kernel_rate * ALG_BYTES_PER_STEP / 1e9 if layout != abi.TRACE_NONE else 0.0
     roofline = {"bound": "alu-issue", "achieved": inst_ach, "peak": inst_peak, "unit": "Gthread-inst/s",
                 "frac": inst_ach / inst_peak, "traffic": None,
-                "note": f"{ALG_INST_PER_STEP} algorithmic thread-instructions per chain-step (SURVEY.md 8(d)); peak = "
+                "note": f"{spec['alg_inst']} algorithmic thread-instructions per chain-step (SURVEY.md 8(d)); peak = "
                         f"{info['sm_count']} SMs x 128 lanes x {sm_max_mhz:.0f} MHz; kernel {kms:.3f} ms per launch",
                 "hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
@@ -295,6 +321,8 @@ def main():
         h_theta0, h_y0 = theta0.cpu().pin_memory(), y0.cpu().pin_memory()
         h_theta, h_y = torch.empty_like(h_theta0).pin_memory(), torch.empty_like(h_y0).pin_memory()
         h_stats = torch.zeros(C, abi.nstats(d)).pin_memory()
+        h_aux0 = aux0.cpu().pin_memory() if K else None
+        h_aux = torch.empty_like(h_aux0).pin_memory() if K else None
         h_layout = abi.TRACE_TIME_MAJOR if layout != abi.TRACE_NONE else abi.TRACE_NONE
         del trace
         torch.cuda.empty_cache()
@@ -304,8 +332,10 @@ def main():
             h_theta.copy_(h_theta0)
             h_y.copy_(h_y0)
             h_stats.zero_()
-            eng.run_host("global", theta=h_theta, y=h_y, n_steps=T - 1, gf=0.5, seed=i, chain_id_base=chain_base,
-                         trace=h_trace, trace_layout=h_layout, stats=h_stats, block_threads=a.block)
+            if K:
+                h_aux.copy_(h_aux0)
+            eng.run_host(entry, theta=h_theta, y=h_y, n_steps=T - 1, gf=gf, seed=i, chain_id_base=chain_base,
+                         trace=h_trace, trace_layout=h_layout, stats=h_stats, block_threads=a.block, K=K, aux=h_aux)
         e2e_step(0)
         barrier()
         t0 = time.perf_counter()
@@ -319,11 +349,11 @@ def main():
         d2h = h2d + (h_trace.numel() * 4 if h_trace is not None else 0)
         line["e2e"] = {"value": steps_per_pass * e_steps / float(dt.item()), "unit": "chain-steps/s",
                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e_steps,
-                       "note": "glabc_run_global_host: pinned host buffers, full trace copied back in time chunks "
+                       "note": f"glabc_run_{entry}_host: pinned host buffers, full trace copied back in time chunks "
                                "overlapped with the kernels; host view [T,C,2] (chain c = trace[:, c])"}
 
     if rank == 0 and not a.no_cpu:
-        r, cores, sample = cpu_port_rate(C, T, a.cpu_seconds)
+        r, cores, sample = cpu_port_rate(C, T, a.cpu_seconds, sampler=a.sampler)
         line["cpu_baseline"] = {"value": r, "unit": "chain-steps/s", "cores": cores, "kind": "port", "sample": sample}
     if world > 1:
         dist.barrier()
