@@ -11,8 +11,11 @@ MAX_DIM = 8
 MAX_MODES = 8
 MAX_K = 16
 AUX_SLOTS = 8
-AUX_LOGW, AUX_LOCAL = 0, 1
+AUX_LOGW, AUX_LOCAL, AUX_WIDE, AUX_LW_WIDE, AUX_HAVE_GRAD = 0, 1, 2, 3, 4
 DEBUG_SLOTS = 4 + MAX_K
+STATE64_SLOTS, S64_THETA, S64_Y, S64_GRAD, S64_LOGW = 16, 0, 4, 8, 12
+DEBUG64_SLOTS = 20
+MAX_NUM_GRAD = 4096
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = range(5)
 
@@ -38,6 +41,10 @@ def tape_isir_slots(d, yd, k):
     return 2 + k * (d + yd)
 
 
+def tape_mala_slots(d, yd, k, num):
+    return 2 + k * (d + yd) + d * num * yd
+
+
 _F8 = C.c_float * MAX_DIM
 
 
@@ -46,7 +53,7 @@ class ModelPOD(C.Structure):
     _fields_ = [("family", C.c_int32), ("theta_dim", C.c_int32), ("y_dim", C.c_int32), ("reserved", C.c_int32),
                 ("y_obs", _F8), ("noise_loc", _F8), ("noise_scale", _F8), ("prior_loc", _F8),
                 ("prior_log_scale", _F8), ("prior_scale", _F8),
-                ("eps_log_scale", C.c_float), ("eps_scale", C.c_float)]
+                ("eps_log_scale", C.c_float), ("eps_scale", C.c_float), ("epsilon", C.c_double)]
 
 
 class DistPOD(C.Structure):
@@ -68,7 +75,9 @@ class RunPOD(C.Structure):
                 ("trace_row_base", C.c_int64),
                 ("theta", C.c_void_p), ("y", C.c_void_p), ("aux", C.c_void_p), ("trace", C.c_void_p),
                 ("stats", C.c_void_p), ("tape32", C.c_void_p), ("tape64", C.c_void_p), ("debug", C.c_void_p),
-                ("tape_dump", C.c_void_p), ("tape64_dump", C.c_void_p), ("stream", C.c_void_p)]
+                ("tape_dump", C.c_void_p), ("tape64_dump", C.c_void_p),
+                ("state64", C.c_void_p), ("tape_grad0", C.c_void_p), ("tape_grad0_dump", C.c_void_p),
+                ("debug64", C.c_void_p), ("tau64", C.c_double), ("stream", C.c_void_p)]
 
 
 def fill(arr, values):
@@ -97,6 +106,7 @@ _SIGNATURES = {
     "glabc_run_global_host": (C.c_int, [C.c_void_p, C.POINTER(RunPOD), C.c_int64]),
     "glabc_run_isir": (C.c_int, [C.c_void_p, C.POINTER(RunPOD)]),
     "glabc_run_isir_host": (C.c_int, [C.c_void_p, C.POINTER(RunPOD), C.c_int64]),
+    "glabc_run_mala": (C.c_int, [C.c_void_p, C.POINTER(RunPOD)]),
     "glabc_esjd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "glabc_philox_kat": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
 }

@@ -87,6 +87,7 @@ class AbsNormalModel:
         eps_t = torch.tensor([float(self.epsilon)], dtype=torch.float32)
         pod.eps_log_scale = float(torch.log(eps_t))            # Mixture.py:43
         pod.eps_scale = float(torch.exp(torch.log(eps_t)))     # distribution.py:178 (0.05 -> 0.049999997)
+        pod.epsilon = float(self.epsilon)                      # GLMALA.py:90 squares the Python float
         return pod
 
 

@@ -62,6 +62,8 @@ typedef struct {
     float prior_scale[GLABC_MAX_DIM];      /* exp(prior_log_scale) in float32                   */
     float eps_log_scale;                   /* log(epsilon) in float32, Mixture.py:43            */
     float eps_scale;                       /* exp(log(epsilon)) in float32 (0.05 -> 0.049999997)*/
+    double epsilon;                        /* the Python float `ABCset.epsilon` itself (GLMALA.py:90
+                                              uses epsilon**2 in float64)                       */
 } glabc_model_t;
 
 /* ---- proposal / prior distributions (reference: distribution.py:50,90,143,206) ------------- */
@@ -126,7 +128,20 @@ typedef enum {
 
 #define GLABC_AUX_SLOTS 8
 #define GLABC_AUX_LOGW 0            /* iSIR: cached log-weight of the current state               */
-#define GLABC_AUX_LOCAL 1           /* iSIR: 1.0 if a local move was accepted since (init 1.0)    */
+#define GLABC_AUX_LOCAL 1           /* iSIR: 1.0 if a local move was accepted since (init 1.0);
+                                       GLMALA never sets it again after the first global move
+                                       (GLMALA.py:152-157 vs :195-199), reproduced                */
+#define GLABC_AUX_WIDE 2            /* GLMALA: theta / y are float64 tensors (a local move was accepted:
+                                       GLMALA.py:43 adds a float64 gradient)       */
+#define GLABC_AUX_LW_WIDE 3         /* GLMALA: the cached log-weight (hence the iSIR weights) is float64 */
+#define GLABC_AUX_HAVE_GRAD 4       /* GLMALA: grad_logABC_Theta_old is not None (GLMALA.py:183)  */
+
+/* GLMALA carried float64 state, state64[C][GLABC_STATE64_SLOTS]                                  */
+#define GLABC_STATE64_SLOTS 16
+#define GLABC_S64_THETA 0           /* + i, i < d  (used when AUX_WIDE)                           */
+#define GLABC_S64_Y 4               /* + i                                                        */
+#define GLABC_S64_GRAD 8            /* + i: grad_logABC_Theta_old                                 */
+#define GLABC_S64_LOGW 12           /* cached log-weight                                          */
 
 /* Common fields of every sampler launch.  One launch advances `n_chains` independent chains by
  * `n_steps` transitions (loop iterations i = step_base+1 .. step_base+n_steps of the reference's
@@ -167,6 +182,14 @@ typedef struct {
     float* tape_dump;         /* [n_steps][tape_slots][n_chains]: the draws the kernel used, in tape
                                  layout, so a replay (or the CPU oracle) can re-run the same chain */
     double* tape64_dump;      /* [n_steps][n_chains]: the float64 resampling uniforms used (iSIR)   */
+    /* GLMALA (run_mala) only */
+    double* state64;          /* [C][GLABC_STATE64_SLOTS] carried float64 state, updated in place  */
+    const float* tape_grad0;  /* replay: [d*num_grad*y_dim][n_chains] draws of the first gradient
+                                 (grad_logABC_Theta_old is None, GLMALA.py:183-184)                */
+    float* tape_grad0_dump;   /* native: the same, written by the kernel                           */
+    double* debug64;          /* [n_steps][GLABC_DEBUG64_SLOTS][n_chains] per-step quantities/NULL */
+    double tau64;             /* the Python float `tau` (GLMALA.py:43 uses tau**2/2 in float64 while z*tau
+                                 is a float32 product); 0 = use (double)tau                          */
     void* stream;
 } glabc_run_t;
 
@@ -182,6 +205,17 @@ typedef struct {
  *                             3 normalised weight of the current state, 4+j log-weight of
  *                             candidate j (j < K)                                                 */
 #define GLABC_DEBUG_SLOTS (4 + GLABC_MAX_K)
+/* replay tape slots for run_mala: the iSIR layout (a local step keeps z[d] in the first proposal slots,
+ * eps_sim[y_dim] in the first simulator slots, U_a last) followed by the gradient normals
+ * [d][num_grad][y_dim] of theta' (one copy: + and - share them, GLMALA.py:76-83)    */
+#define GLABC_TAPE_MALA_SLOTS(d, yd, K, num) (2 + (K) * ((d) + (yd)) + (d) * (num) * (yd))
+/* run_mala debug64 slots (float64): 0 flags (bit0 global, bit1 state changed, bits 8.. resample index + 1,
+ *   bit16 float64 weights); MALA local move: 1 log_acc, 2+i theta'[i], 6+i y'[i], 10+i grad'[i] (i < 4),
+ *   14 log prior', 15 log kernel', 16 log q(theta|theta'), 17 log q(theta'|theta);
+ *   iSIR global move: 1 log-weight of the current state, 2 sum of weights, 3 normalised weight of the
+ *   current state, 4+j log-weight of candidate j                                                   */
+#define GLABC_DEBUG64_SLOTS 20
+#define GLABC_MAX_NUM_GRAD 4096
 
 typedef struct glabc_ctx glabc_ctx;
 
@@ -216,6 +250,12 @@ GLABC_API int glabc_run_global(glabc_ctx* ctx, const glabc_run_t* run);
  * `n_candidates` fresh draws from the IMPORTANCE slot, local RW-MH from the LOCAL slot.  `aux` carries
  * the cached log-weight and the `local` flag (init {0, 1}, GLMCMC.py:49-55).                        */
 GLABC_API int glabc_run_isir(glabc_ctx* ctx, const glabc_run_t* run);
+
+/* GLMALA loop body, GLMALA.py:150-200: the iSIR global move of run_isir (GLMALA.py:151-180) and a MALA
+ * local move (Local_proposal_forward :25-44, log_proposal :97-116) whose drift is the finite-difference
+ * synthetic-likelihood gradient numberical_gradient_logABC (:46-95) from 2*d*num_grad simulator draws with
+ * common random numbers.  run->tau, run->num_grad, run->n_candidates; needs aux and state64.          */
+GLABC_API int glabc_run_mala(glabc_ctx* ctx, const glabc_run_t* run);
 
 /* ---- samplers: host buffers (the reference-facing call: H2D state, run, D2H trace + stats) --- */
 /* `run->theta`, `y`, `trace`, `stats` are HOST pointers here; the trace is copied back in

@@ -569,6 +569,358 @@ ORACLE_EXPORT int oracle_run_isir(const glabc_model_t* m, const glabc_dist_t* lp
 }
 
 /* -------------------------------------------------------------------------------------------
+ * GLMALA — GLMALA.py:150-200
+ *
+ * dtype bookkeeping the reference does by accident and which defines its behaviour:
+ *   - the MALA proposal adds a float64 gradient (GLMALA.py:43), so theta', y', their log-densities
+ *     and log_acc are float64; once a local move is accepted Theta_old / y_old ARE float64 tensors
+ *     ("wide"), and torch.cat keeps them float64 through later global switches;
+ *   - log_weight_old is computed once, at the first global move (`local` is never set again,
+ *     GLMALA.py:152-157 vs :195-199): if the state was already wide then, the iSIR weights are
+ *     exponentiated / normalised in float64 for the rest of the run ("lw_wide"), otherwise float32.
+ * Draw order (local): U_b, [first gradient: N[num,y] per k, + and - share them], N[1,d] (z),
+ * gradient at theta' (N[num,y] per k), N[1,y] (simulator), U_a.
+ * ------------------------------------------------------------------------------------------- */
+static double torch_sum_f64(const double* v, int n)
+{
+    double p[4] = {0.0, 0.0, 0.0, 0.0};
+    const int rows = n / 4;
+    for (int r = 0; r < rows; ++r)
+        for (int k = 0; k < 4; ++k) p[k] += v[r * 4 + k];
+    for (int i = rows * 4; i < n; ++i) p[0] += v[i];
+    for (int k = 1; k < 4; ++k) p[0] += p[k];
+    return p[0];
+}
+
+static inline double half_log_2pi_f64(int d) { return -0.5 * (double)d * log(2.0 * M_PI); }
+
+/* DiagGaussian.log_prob on a float64 tensor with float32 parameters (type promotion) */
+static double diag_gauss_log_prob64(const double* z, const float* loc, const float* log_scale, const float* scale, int d)
+{
+    double t[GLABC_MAX_DIM];
+    for (int i = 0; i < d; ++i) {
+        const double r = (z[i] - (double)loc[i]) / (double)scale[i];
+        t[i] = (double)log_scale[i] + 0.5 * (r * r);
+    }
+    return half_log_2pi_f64(d) - torch_sum_f64(t, d);
+}
+
+static double model_prior64(const glabc_model_t* m, const double* theta)
+{
+    return diag_gauss_log_prob64(theta, m->prior_loc, m->prior_log_scale, m->prior_scale, m->theta_dim);
+}
+
+static double model_log_kernel64(const glabc_model_t* m, const double* y)
+{
+    double t[GLABC_MAX_DIM];
+    for (int i = 0; i < m->y_dim; ++i) {
+        const double dy = y[i] - (double)m->y_obs[i];
+        t[i] = dy * dy;
+    }
+    const double dis = sqrt(torch_sum_f64(t, m->y_dim));
+    const double r = (dis - 0.0) / (double)m->eps_scale;
+    return half_log_2pi_f64(1) - ((double)m->eps_log_scale + 0.5 * (r * r));
+}
+
+/* native-mode layout of the gradient normals: draw j of dimension k takes y_dim normals of block
+ * slot0 + k*nblk + j/dpb, dpb = draws per Philox block (4 / y_dim; 1 for y_dim 3)               */
+enum { SLOT_GRAD = 0x10000, SLOT_GRAD0 = 0x20000 };
+static inline int grad_dpb(int yd) { return yd == 3 ? 1 : 4 / yd; }
+
+static void native_grad_normals(uint64_t seed, uint64_t chain, uint32_t step, uint32_t slot0, int d, int yd, int num, float* eps)
+{
+    const int dpb = grad_dpb(yd), nblk = (num + dpb - 1) / dpb;
+    for (int k = 0; k < d; ++k)
+        for (int g = 0; g < nblk; ++g) {
+            uint32_t w[4];
+            float z[4];
+            philox_block(seed, chain, step, slot0 + (uint32_t)(k * nblk + g), w);
+            box_muller(w[0], w[1], &z[0], &z[1]);
+            box_muller(w[2], w[3], &z[2], &z[3]);
+            for (int t = 0; t < dpb && g * dpb + t < num; ++t)
+                for (int q = 0; q < yd; ++q) eps[((size_t)k * num + g * dpb + t) * yd + q] = z[t * yd + q];
+        }
+}
+
+/* numberical_gradient_logABC, GLMALA.py:46-95.  eps[d][num][y_dim]: the simulator normals (the same
+ * for theta + 0.1 e_k and theta - 0.1 e_k: both calls follow the same manual_seed, :76-83).
+ * Mean / unbiased variance of the discrepancies in float64 (:70-72,86-89) — accumulated in one pass
+ * around the noise-free discrepancy (the kernels use the same formulation; torch's reduction order
+ * differs at the 1e-16 level).                                                                     */
+static void mala_gradient(const glabc_model_t* m, const double* theta_in, int num, const float* eps, double* grad)
+{
+    const int d = m->theta_dim, yd = m->y_dim;
+    float th[GLABC_MAX_DIM], zero[GLABC_MAX_DIM] = {0};
+    for (int i = 0; i < d; ++i) th[i] = (float)theta_in[i]; /* theta.float(), :60 */
+    const float h = (float)1e-1;                             /* d * torch.eye in float32, :63 */
+    const double eps2 = m->epsilon * m->epsilon;             /* ABCset.epsilon ** 2 */
+    for (int k = 0; k < d; ++k) {
+        double logp[2];
+        for (int sgn = 0; sgn < 2; ++sgn) {
+            float tp[GLABC_MAX_DIM], y[GLABC_MAX_DIM];
+            memcpy(tp, th, sizeof(float) * d);
+            tp[k] = sgn == 0 ? th[k] + h : th[k] - h;        /* :66-67 */
+            model_simulate(m, tp, zero, y);
+            const double c = (double)model_discrepancy(m, y);
+            double s1 = 0.0, s2 = 0.0;
+            for (int j = 0; j < num; ++j) {
+                model_simulate(m, tp, eps + ((size_t)k * num + j) * yd, y);
+                const double dx = (double)model_discrepancy(m, y) - c; /* :78-83 */
+                s1 += dx;
+                s2 = fma(dx, dx, s2);
+            }
+            const double n = (double)num;
+            const double mu = c + s1 / n;
+            const double var = (s2 - s1 * s1 / n) / (n - 1.0);
+            logp[sgn] = -0.5 * log(var + eps2) - 0.5 * (mu * mu) / (var + eps2); /* :90-93 */
+        }
+        float ta[GLABC_MAX_DIM], tb[GLABC_MAX_DIM];
+        memcpy(ta, th, sizeof(float) * d);
+        memcpy(tb, th, sizeof(float) * d);
+        const float fd = (float)0.00001;                     /* eye[k,:] * 0.00001 in float32, :84-85 */
+        ta[k] = th[k] + fd;
+        tb[k] = th[k] - fd;
+        const float gprior = (model_prior(m, ta) - model_prior(m, tb)) / (float)(2 * 0.00001);
+        grad[k] = (logp[0] - logp[1]) / (2 * 1e-1) + (double)gprior; /* :94-95 */
+    }
+}
+
+/* the gradient alone (unit-tested against the reference's recorded gradients) */
+ORACLE_EXPORT void oracle_mala_gradient(const glabc_model_t* m, const double* theta, int num, const float* eps, double* grad)
+{
+    mala_gradient(m, theta, num, eps, grad);
+}
+
+typedef struct { const glabc_model_t* m; const glabc_dist_t* ip; const glabc_run_t* r; } mala_job;
+
+static void run_mala_range(void* vctx, int64_t c_begin, int64_t c_end)
+{
+    const mala_job* job = (const mala_job*)vctx;
+    const glabc_model_t* m = job->m;
+    const glabc_dist_t* ip = job->ip;
+    const glabc_run_t* r = job->r;
+    const int K = r->n_candidates, num = r->num_grad;
+    const int d = m->theta_dim, yd = m->y_dim;
+    const int slots = GLABC_TAPE_MALA_SLOTS(d, yd, K, num);
+    const int gslot0 = 2 + K * (d + yd);
+    const int ns = GLABC_NSTATS(d);
+    const float gf = r->global_frequency;
+    const float tau_f = r->tau;              /* z * tau: float32 tensor times Python scalar */
+    const double tau = r->tau64 != 0.0 ? r->tau64 : (double)r->tau; /* the Python float itself */
+    const int64_t C = r->n_chains;
+    const size_t ng = (size_t)d * num * yd;
+    float* geps = (float*)malloc(sizeof(float) * ng);
+    const float zeros[GLABC_MAX_DIM] = {0}, ones[GLABC_MAX_DIM] = {1, 1, 1, 1, 1, 1, 1, 1};
+
+    for (int64_t c = c_begin; c < c_end; ++c) {
+        double theta[GLABC_MAX_DIM], y[GLABC_MAX_DIM], grad[GLABC_MAX_DIM] = {0}, lw_old;
+        float st[GLABC_NSTATS(GLABC_MAX_DIM)];
+        memset(st, 0, sizeof(st));
+        float* aux = r->aux + c * GLABC_AUX_SLOTS;
+        double* s64 = r->state64 + c * GLABC_STATE64_SLOTS;
+        int local = aux[GLABC_AUX_LOCAL] != 0.0f, wide = aux[GLABC_AUX_WIDE] != 0.0f;
+        int lw_wide = aux[GLABC_AUX_LW_WIDE] != 0.0f, have_grad = aux[GLABC_AUX_HAVE_GRAD] != 0.0f;
+        for (int k = 0; k < d; ++k) theta[k] = wide ? s64[GLABC_S64_THETA + k] : (double)r->theta[c * d + k];
+        for (int k = 0; k < yd; ++k) y[k] = wide ? s64[GLABC_S64_Y + k] : (double)r->y[c * yd + k];
+        for (int k = 0; k < d; ++k) grad[k] = s64[GLABC_S64_GRAD + k];
+        lw_old = s64[GLABC_S64_LOGW];
+        if (r->write_row0 && r->trace_layout != GLABC_TRACE_NONE)
+            for (int k = 0; k < d; ++k) r->trace[trace_index(r, c, r->step_base, d) + k] = (float)theta[k];
+
+        for (int64_t s = 0; s < r->n_steps; ++s) {
+            const int64_t i = r->step_base + 1 + s;
+            const uint64_t gid = (uint64_t)(r->chain_id_base + c);
+            const float* t = r->rng_mode == GLABC_RNG_REPLAY ? r->tape32 + (size_t)s * slots * C + c : NULL;
+            float u_b, u_a = 0.0f, zl[2 * GLABC_MAX_DIM + 4];
+            if (t) u_b = t[0];
+            else native_step_draws(r->seed, gid, (uint32_t)i, d + yd, zl, &u_b, &u_a);
+            const int is_global = u_b < gf; /* GLMALA.py:151 */
+            int changed = 0, ind = -1;
+            double dbg[GLABC_DEBUG64_SLOTS];
+            memset(dbg, 0, sizeof(dbg));
+            float prev[GLABC_MAX_DIM], now[GLABC_MAX_DIM];
+            for (int k = 0; k < d; ++k) prev[k] = (float)theta[k];
+
+            if (is_global) { /* GLMALA.py:151-180: the iSIR move of GLMCMC.py:60-89 */
+                float eps_p[GLABC_MAX_K * GLABC_MAX_DIM], eps_s[GLABC_MAX_K * GLABC_MAX_DIM];
+                double u64;
+                if (t) {
+                    for (int k = 0; k < K * d; ++k) eps_p[k] = t[(size_t)(1 + k) * C];
+                    for (int k = 0; k < K * yd; ++k) eps_s[k] = t[(size_t)(1 + K * d + k) * C];
+                    u64 = r->tape64[(size_t)s * C + c];
+                } else {
+                    const int G = (d + yd + 3) / 4;
+                    for (int j = 0; j < K; ++j) {
+                        float z[2 * GLABC_MAX_DIM + 4];
+                        native_normals(r->seed, gid, (uint32_t)i, SLOT_NORMAL + 8u + (uint32_t)(j * G), d + yd, z);
+                        memcpy(eps_p + j * d, z, sizeof(float) * d);
+                        memcpy(eps_s + j * yd, z + d, sizeof(float) * yd);
+                    }
+                    uint32_t w0[4], c0[4];
+                    philox_block(r->seed, gid, (uint32_t)i, SLOT_STEP, w0);
+                    philox_block(r->seed, gid, (uint32_t)i, SLOT_NORMAL + 8u, c0);
+                    const uint64_t ua_step = (w0[1] & 0xFFFu) | ((w0[3] << 12) & 0xFFF000u);
+                    const uint64_t ua_c0 = (c0[1] & 0xFFFu) | ((c0[3] << 12) & 0xFFF000u);
+                    u64 = (double)((ua_step << 29) | (ua_c0 << 5) | ((c0[0] & 0xFFu) >> 3)) * 0x1p-53;
+                }
+                if (local) { /* GLMALA.py:152-156 — the only place log_weight_old is computed from the state */
+                    if (wide) {
+                        lw_old = (model_prior64(m, theta) + model_log_kernel64(m, y)) -
+                                 diag_gauss_log_prob64(theta, ip->a, ip->b, ip->c, d);
+                    } else {
+                        float tf[GLABC_MAX_DIM], yf[GLABC_MAX_DIM];
+                        for (int k = 0; k < d; ++k) tf[k] = (float)theta[k];
+                        for (int k = 0; k < yd; ++k) yf[k] = (float)y[k];
+                        lw_old = (double)((model_prior(m, tf) + model_log_kernel(m, yf)) - diag_gauss_log_prob(tf, ip->a, ip->b, ip->c, d));
+                    }
+                    lw_wide = wide;
+                }
+                local = 0;
+                float th[(GLABC_MAX_K + 1) * GLABC_MAX_DIM], x[(GLABC_MAX_K + 1) * GLABC_MAX_DIM], lw[GLABC_MAX_K + 1];
+                for (int j = 0; j < K; ++j) { /* GLMALA.py:158-165 */
+                    float* tj = th + (j + 1) * d;
+                    float* xj = x + (j + 1) * yd;
+                    const float lq = diag_gauss_forward(eps_p + j * d, ip->a, ip->b, ip->c, d, tj);
+                    model_simulate(m, tj, eps_s + j * yd, xj);
+                    lw[j + 1] = (model_prior(m, tj) + model_log_kernel(m, xj)) - lq;
+                }
+                double S, w0n;
+                if (lw_wide) { /* float64 weights: exp does not underflow near -104 (contrast B-1) */
+                    double w[GLABC_MAX_K + 1];
+                    w[0] = exp(lw_old);
+                    for (int j = 1; j <= K; ++j) w[j] = exp((double)lw[j]);
+                    for (int j = 0; j <= K; ++j) if (isnan(w[j])) w[j] = 0.0;
+                    S = torch_sum_f64(w, K + 1);
+                    double run = 0.0;
+                    for (int j = 0; j <= K; ++j) {
+                        w[j] = w[j] / S;
+                        run += w[j];
+                        if (ind < 0 && u64 < run) ind = j;
+                    }
+                    w0n = w[0];
+                } else {
+                    float w[GLABC_MAX_K + 1];
+                    w[0] = expf((float)lw_old);
+                    for (int j = 1; j <= K; ++j) w[j] = expf(lw[j]);
+                    for (int j = 0; j <= K; ++j) if (isnan(w[j])) w[j] = 0.0f;
+                    const float Sf = torch_sum_f32(w, K + 1);
+                    for (int j = 0; j <= K; ++j) w[j] = w[j] / Sf;
+                    ind = weight_sampling(w, K + 1, u64);
+                    S = (double)Sf;
+                    w0n = (double)w[0];
+                }
+                dbg[1] = lw_old;
+                dbg[2] = S;
+                dbg[3] = w0n;
+                for (int j = 0; j < K; ++j) dbg[4 + j] = (double)lw[j + 1];
+                if (ind > 0) { /* GLMALA.py:175-179: grad_logABC_Theta_old is NOT refreshed (B-6) */
+                    for (int k = 0; k < d; ++k) theta[k] = (double)th[ind * d + k];
+                    for (int k = 0; k < yd; ++k) y[k] = (double)x[ind * yd + k];
+                    lw_old = (double)lw[ind];
+                }
+                for (int k = 0; k < d; ++k) changed |= ((float)theta[k] != prev[k]);
+            } else { /* GLMALA.py:182-200 */
+                float z[GLABC_MAX_DIM], eps_s[GLABC_MAX_DIM];
+                if (!have_grad) { /* :183-184 */
+                    if (t) for (size_t q = 0; q < ng; ++q) geps[q] = r->tape_grad0[q * C + c];
+                    else native_grad_normals(r->seed, gid, (uint32_t)i, SLOT_GRAD0, d, yd, num, geps);
+                    mala_gradient(m, theta, num, geps, grad);
+                    have_grad = 1;
+                }
+                if (t) {
+                    for (int k = 0; k < d; ++k) z[k] = t[(size_t)(1 + k) * C];
+                    for (int k = 0; k < yd; ++k) eps_s[k] = t[(size_t)(1 + K * d + k) * C];
+                    u_a = t[(size_t)(1 + K * (d + yd)) * C];
+                    for (size_t q = 0; q < ng; ++q) geps[q] = t[(gslot0 + q) * C];
+                } else {
+                    memcpy(z, zl, sizeof(float) * d);
+                    memcpy(eps_s, zl + d, sizeof(float) * yd);
+                    native_grad_normals(r->seed, gid, (uint32_t)i, SLOT_GRAD, d, yd, num, geps);
+                }
+                /* Local_proposal_forward, GLMALA.py:25-44: DiagGaussian(d, [0], [0]).forward(1) */
+                float zz[GLABC_MAX_DIM];
+                const float lq_fwd = diag_gauss_forward(z, zeros, zeros, ones, d, zz);
+                double theta_p[GLABC_MAX_DIM], y_p[GLABC_MAX_DIM], grad_p[GLABC_MAX_DIM];
+                for (int k = 0; k < d; ++k) {
+                    const float zt = zz[k] * tau_f;
+                    const double a = wide ? (double)zt + theta[k] : (double)(zt + (float)theta[k]);
+                    theta_p[k] = a + grad[k] * (tau * tau) / 2.0; /* :43 */
+                }
+                mala_gradient(m, theta_p, num, geps, grad_p); /* :187 */
+                for (int k = 0; k < yd; ++k) { /* :188-189: |theta'| (float64) + likelihood.sample (float32) */
+                    const float noise = m->noise_loc[k] + m->noise_scale[k] * eps_s[k];
+                    const double mean = m->family == GLABC_MODEL_ABS_NORMAL ? fabs(theta_p[k]) : theta_p[k];
+                    y_p[k] = mean + (double)noise;
+                }
+                const double prior_p = model_prior64(m, theta_p), kern_p = model_log_kernel64(m, y_p);
+                double rr[GLABC_MAX_DIM]; /* log_proposal(Theta_prop, grad_prop, Theta_old, tau), :97-116 */
+                for (int k = 0; k < d; ++k) rr[k] = (theta[k] - theta_p[k] - grad_p[k] * (tau * tau) / 2.0) / tau;
+                const double lq_rev = diag_gauss_log_prob64(rr, zeros, zeros, ones, d);
+                double prior_o, kern_o;
+                if (wide) {
+                    prior_o = model_prior64(m, theta);
+                    kern_o = model_log_kernel64(m, y);
+                } else {
+                    float tf[GLABC_MAX_DIM], yf[GLABC_MAX_DIM];
+                    for (int k = 0; k < d; ++k) tf[k] = (float)theta[k];
+                    for (int k = 0; k < yd; ++k) yf[k] = (float)y[k];
+                    prior_o = (double)model_prior(m, tf);
+                    kern_o = (double)model_log_kernel(m, yf);
+                }
+                const double log_acc = prior_p + kern_p + lq_rev - prior_o - kern_o - (double)lq_fwd; /* :190-193 */
+                const int accept = (double)logf(u_a) < log_acc;
+                dbg[1] = log_acc;
+                for (int k = 0; k < d && k < 4; ++k) { dbg[2 + k] = theta_p[k]; dbg[10 + k] = grad_p[k]; }
+                for (int k = 0; k < yd && k < 4; ++k) dbg[6 + k] = y_p[k];
+                dbg[14] = prior_p; dbg[15] = kern_p; dbg[16] = lq_rev; dbg[17] = (double)lq_fwd;
+                if (accept) { /* :195-199 */
+                    memcpy(theta, theta_p, sizeof(double) * d);
+                    memcpy(y, y_p, sizeof(double) * yd);
+                    memcpy(grad, grad_p, sizeof(double) * d);
+                    wide = 1;
+                    changed = 1;
+                }
+            }
+            dbg[0] = (double)(is_global | (changed << 1) | ((is_global ? ind + 1 : 0) << 8) | ((is_global && lw_wide) << 16));
+            for (int k = 0; k < d; ++k) now[k] = (float)theta[k]; /* Theta_Re[i,:] = Theta_old (float32 buffer) */
+            stats_update(st, d, now, prev);
+            st[GLABC_STAT_GLOBAL_STEPS] += (float)is_global;
+            st[is_global ? GLABC_STAT_ACC_GLOBAL : GLABC_STAT_ACC_LOCAL] += (float)changed;
+            if (r->trace_layout != GLABC_TRACE_NONE)
+                memcpy(r->trace + trace_index(r, c, i, d), now, sizeof(float) * d);
+            if (r->debug64) {
+                double* g = r->debug64 + (size_t)s * GLABC_DEBUG64_SLOTS * C + c;
+                for (int k = 0; k < GLABC_DEBUG64_SLOTS; ++k) g[(size_t)k * C] = dbg[k];
+            }
+        }
+        for (int k = 0; k < d; ++k) { r->theta[c * d + k] = (float)theta[k]; s64[GLABC_S64_THETA + k] = theta[k]; s64[GLABC_S64_GRAD + k] = grad[k]; }
+        for (int k = 0; k < yd; ++k) { r->y[c * yd + k] = (float)y[k]; s64[GLABC_S64_Y + k] = y[k]; }
+        s64[GLABC_S64_LOGW] = lw_old;
+        aux[GLABC_AUX_LOCAL] = (float)local; aux[GLABC_AUX_WIDE] = (float)wide;
+        aux[GLABC_AUX_LW_WIDE] = (float)lw_wide; aux[GLABC_AUX_HAVE_GRAD] = (float)have_grad;
+        if (r->stats)
+            for (int k = 0; k < ns; ++k) r->stats[c * ns + k] += st[k];
+    }
+    free(geps);
+}
+
+ORACLE_EXPORT int oracle_run_mala(const glabc_model_t* m, const glabc_dist_t* unused, const glabc_dist_t* ip,
+                                  const glabc_run_t* r)
+{
+    (void)unused;
+    int rc = check_common(m, r);
+    if (rc) return rc;
+    if (!ip || ip->kind != GLABC_DIST_DIAG_GAUSSIAN) return GLABC_ERR_UNSUPPORTED;
+    if (m->theta_dim > 4) return GLABC_ERR_UNSUPPORTED;
+    if (r->n_candidates < 1 || r->n_candidates > GLABC_MAX_K || !r->aux || !r->state64) return GLABC_ERR_INVALID;
+    if (r->num_grad < 2 || r->num_grad > GLABC_MAX_NUM_GRAD || !(r->tau > 0.0f)) return GLABC_ERR_INVALID;
+    if (r->rng_mode == GLABC_RNG_REPLAY && (!r->tape64 || !r->tape_grad0)) return GLABC_ERR_INVALID;
+    mala_job job = {m, ip, r};
+    parallel_chains(run_mala_range, &job, r->n_chains);
+    return GLABC_OK;
+}
+
+/* -------------------------------------------------------------------------------------------
  * esjd — ESJD.py:17-24: det(D^T D / (N-1))^(1/d) in float32 (d <= 3 closed-form determinant;
  * torch.det goes through an LU factorisation, so agreement is to rounding, not bit-exact).
  * ------------------------------------------------------------------------------------------- */

@@ -32,7 +32,7 @@ def lib():
         if not os.path.exists(LIB):
             build()
         _lib = C.CDLL(LIB)
-        for name in ("oracle_run_global", "oracle_run_isir"):
+        for name in ("oracle_run_global", "oracle_run_isir", "oracle_run_mala"):
             fn = getattr(_lib, name)
             fn.restype = C.c_int
             fn.argtypes = [C.POINTER(abi.ModelPOD), C.POINTER(abi.DistPOD), C.POINTER(abi.DistPOD), C.POINTER(abi.RunPOD)]
@@ -60,14 +60,14 @@ def _ptr(a):
 def run(sampler, model, d1, d2, *, theta, y, n_steps, gf, step_base=0, chain_id_base=0, seed=0,
         rng_mode=abi.RNG_NATIVE, trace_layout=abi.TRACE_TIME_MAJOR, trace=None, trace_rows=None,
         trace_chains=None, trace_chain_off=0, write_row0=True, stats=None, aux=None, tape32=None,
-        tape64=None, debug=None, K=0, threads=0):
-    """Run `sampler` ('global' | 'isir') on numpy buffers; theta/y/aux/stats are updated in place.
+        tape64=None, debug=None, K=0, threads=0, num_grad=0, tau=0.0, state64=None, tape_grad0=None, debug64=None):
+    """Run `sampler` ('global' | 'isir' | 'mala') on numpy buffers; theta/y/aux/stats are updated in place.
 
     Returns the trace ([rows, C, d] time-major or [C, rows, d] chain-major) or None."""
     L = lib()
     L.oracle_set_num_threads(int(threads))
     Cn, d = theta.shape
-    for a in (theta, y, aux, stats, tape32, tape64, debug, trace):
+    for a in (theta, y, aux, stats, tape32, tape64, debug, trace, state64, tape_grad0, debug64):
         assert a is None or a.flags["C_CONTIGUOUS"]
     rows = trace_rows if trace_rows is not None else step_base + n_steps + 1
     tchains = trace_chains if trace_chains is not None else Cn
@@ -77,10 +77,14 @@ def run(sampler, model, d1, d2, *, theta, y, n_steps, gf, step_base=0, chain_id_
     r = abi.RunPOD(n_chains=Cn, n_steps=n_steps, step_base=step_base, chain_id_base=chain_id_base, seed=seed,
                    global_frequency=float(gf), rng_mode=rng_mode, arith_mode=abi.ARITH_STRICT,
                    trace_layout=trace_layout, write_row0=int(write_row0), n_candidates=K,
+                   num_grad=int(num_grad), tau=float(tau), tau64=float(tau), state64=_ptr(state64), tape_grad0=_ptr(tape_grad0),
+                   debug64=_ptr(debug64),
                    trace_rows=rows, trace_chains=tchains, trace_chain_off=trace_chain_off,
                    theta=_ptr(theta), y=_ptr(y), aux=_ptr(aux), trace=_ptr(trace), stats=_ptr(stats),
                    tape32=_ptr(tape32), tape64=_ptr(tape64), debug=_ptr(debug))
-    fn = {"global": L.oracle_run_global, "isir": L.oracle_run_isir}[sampler]
+    fn = {"global": L.oracle_run_global, "isir": L.oracle_run_isir, "mala": L.oracle_run_mala}[sampler]
+    if sampler == "mala" and d1 is None:
+        d1 = d2
     st = fn(C.byref(model), C.byref(d1), C.byref(d2), C.byref(r))
     if st != 0:
         raise RuntimeError(f"oracle_{sampler} failed with status {st}")

@@ -355,6 +355,197 @@ def golden_isir(cases, T, out_path):
 
 
 # ----------------------------------------------------------------------------------------------
+# GLMALA (GLMALA.py:150-200): iSIR global move + MALA local move with the CRN finite-difference
+# synthetic-likelihood gradient (GLMALA.py:46-95).  float64 records: the local path runs in float64
+#  and, once a local move was accepted, so does everything that touches theta / y.
+# ----------------------------------------------------------------------------------------------
+def golden_mala(cases, out_path):
+    import glabcmcmc.distribution as distribution
+    from Mixture import Mixture_set
+    mod = sys.modules["glabcmcmc.GLMALA"]
+    blobs = {}
+    for ci, case in enumerate(cases):
+        C, K, T, num, tau, gf = case["chains"], case["K"], case["T"], case["num_grad"], case["tau"], case["gf"]
+        model = Mixture_set(case["epsilon"])
+        ip = distribution.DiagGaussian(2, torch.tensor(case["ip_loc"]), torch.tensor(case["ip_log_scale"]))
+        d = yd = 2
+        slots = 2 + K * (d + yd) + d * num * yd
+        tape32 = np.zeros((T - 1, slots, C), np.float32)
+        tape64 = np.zeros((T - 1, C), np.float64)
+        tape_grad0 = np.zeros((d * num * yd, C), np.float32)
+        trace = np.zeros((T, C, 2), np.float32)
+        theta0s, y0s = np.zeros((C, 2), np.float32), np.zeros((C, 2), np.float32)
+        # per step (float64): 0 flags, 1 log_acc | lw_old, 2..3 theta' , 4..5 y', 6..7 grad', 8 prior', 9 kernel',
+        # 10 lq_rev, 11 lq_fwd | (global) 2 S, 3 w0, 4.. lw_j
+        rec = np.zeros((T - 1, 12 + K, C), np.float64)
+        grad0 = np.zeros((2, C), np.float64)
+        wide_at = np.full(C, -1, np.int64)
+        # the chain's full carried state BEFORE step s (row s) / after the last step (row T-1), float64:
+        # theta[2], y[2], grad[2], lw_old, flag bits (local | wide<<1 | lw_wide<<2 | have_grad<<3)
+        state = np.zeros((T, 8, C), np.float64)
+        for c in range(C):
+            torch.manual_seed(9000 + 1000 * ci + c)
+            np.random.seed(9000 + 1000 * ci + c)
+            theta0 = torch.tensor(case["theta0"])
+            y0 = model.generate_samples(theta0)
+            log = []
+            pm = CallLog(model, "model", ("generate_samples", "prior_log_prob", "calculate_log_kernel", "discrepancy"), log)
+            pip = CallLog(ip, "ip", ("forward", "log_prob"), log)
+            orig = dict(g=mod.numberical_gradient_logABC, f=mod.Local_proposal_forward, l=mod.log_proposal)
+
+            def grad_fn(*a, **k):
+                n0 = len(log)
+                out = orig["g"](*a, **k)
+                del log[n0:]          # the 2*d*num plugin calls inside the gradient are summarised by its output
+                log.append(("fn", "grad", out.detach().numpy().copy()))
+                return out
+
+            def fwd_fn(*a, **k):
+                out = orig["f"](*a, **k)
+                log.append(("fn", "fwd", (out[0].detach().numpy().copy(), out[1].detach().numpy().copy())))
+                return out
+
+            def lp_fn(*a, **k):
+                out = orig["l"](*a, **k)
+                log.append(("fn", "logprop", out.detach().numpy().copy()))
+                return out
+
+            mod.numberical_gradient_logABC, mod.Local_proposal_forward, mod.log_proposal = grad_fn, fwd_fn, lp_fn
+            try:
+                with Tape() as tape, quiet():
+                    chain = mod.GLMALA(pm, T, theta0, y0, tau, num, None, gf, pip, K)
+            finally:
+                mod.numberical_gradient_logABC, mod.Local_proposal_forward, mod.log_proposal = orig["g"], orig["f"], orig["l"]
+            ev = tape.events
+            theta0s[c], y0s[c] = theta0.numpy(), y0.view(-1).numpy()
+            trace[:, c] = chain.numpy()
+            ei, li = 0, 0
+            have_grad, local, wide, lw_wide = False, True, False, False
+            cur_th, cur_y = theta0.numpy().astype(np.float64), y0.view(-1).numpy().astype(np.float64)
+            cur_g, lw_old = np.zeros(2), np.float32(0.0)
+
+            def snapshot(row):
+                state[row, 0:2, c], state[row, 2:4, c], state[row, 4:6, c] = cur_th, cur_y, cur_g
+                state[row, 6, c] = float(lw_old)
+                state[row, 7, c] = int(local) | (int(wide) << 1) | (int(lw_wide) << 2) | (int(have_grad) << 3)
+
+            def take_grad_draws(ei):
+                """2 seeds, then per k: N[num,2] (plus), the same N[num,2] again (minus) — GLMALA.py:74-83"""
+                out = np.zeros((d, num, yd), np.float32)
+                for k in range(d):
+                    assert ev[ei][0] == "SEED", ev[ei][0]
+                    ei += 1
+                for k in range(d):
+                    a, b = ev[ei], ev[ei + 1]
+                    assert a[0] == "N32" and b[0] == "N32" and a[1].shape == (num, yd)
+                    assert np.array_equal(a[1], b[1])       # common random numbers
+                    out[k] = a[1]
+                    ei += 2
+                return out.reshape(-1), ei
+
+            for s in range(T - 1):
+                snapshot(s)
+                assert ev[ei][0] == "U32"
+                u_b = np.float32(ev[ei][1][0])
+                ei += 1
+                tape32[s, 0, c] = u_b
+                is_global = bool(u_b < np.float32(gf))
+                changed = bool(np.any(trace[s + 1, c] != trace[s, c]))
+                if is_global:
+                    e1, e2, e3 = ev[ei:ei + 3]
+                    ei += 3
+                    assert e1[0] == "N32" and e2[0] == "N32" and e3[0] == "U64" and e1[1].shape == (K, 2)
+                    tape32[s, 1:1 + 2 * K, c] = e1[1].reshape(-1)
+                    tape32[s, 1 + 2 * K:1 + 4 * K, c] = e2[1].reshape(-1)
+                    tape64[s, c] = e3[1]
+                    if local:
+                        names = [x[:2] for x in log[li:li + 3]]
+                        assert names == [("model", "calculate_log_kernel"), ("model", "prior_log_prob"), ("ip", "log_prob")], names
+                        lw_old = (log[li + 1][2][0] + log[li][2][0]) - log[li + 2][2][0]
+                        assert lw_old.dtype == (np.float64 if wide else np.float32)
+                        li += 3
+                    local = False
+                    names = [x[:2] for x in log[li:li + 4]]
+                    assert names == [("ip", "forward"), ("model", "generate_samples"),
+                                     ("model", "calculate_log_kernel"), ("model", "prior_log_prob")], names
+                    (th, lq), x, kern, prior = [v[2] for v in log[li:li + 4]]
+                    li += 4
+                    lw = (prior.astype(np.float32) + kern.astype(np.float32)) - lq.astype(np.float32)
+                    allw = torch.cat((torch.as_tensor(lw_old).view(-1), torch.from_numpy(lw)))
+                    w = torch.exp(allw)
+                    w[torch.isnan(w)] = 0.0
+                    S = torch.sum(w)
+                    wn = (w / S).tolist()
+                    ind, sw = None, 0
+                    for j in range(K + 1):
+                        sw += wn[j]
+                        if float(e3[1]) < sw:
+                            ind = j
+                            break
+                    rec[s, 1, c], rec[s, 2, c], rec[s, 3, c] = float(lw_old), S.item(), wn[0]
+                    rec[s, 4:4 + K, c] = lw
+                    lw_wide = allw.dtype == torch.float64
+                    if ind is not None and ind != 0:
+                        assert np.all(th[ind - 1] == trace[s + 1, c])
+                        lw_old = allw[ind].clone().numpy()[()]
+                        cur_th, cur_y = th[ind - 1].astype(np.float64), x[ind - 1].astype(np.float64)
+                    rec[s, 0, c] = 1 | (int(changed) << 1) | ((0 if ind is None else ind + 1) << 8) | (int(lw_wide) << 16)
+                else:
+                    if not have_grad:
+                        g0, ei = take_grad_draws(ei)
+                        tape_grad0[:, c] = g0
+                        assert log[li][:2] == ("fn", "grad")
+                        grad0[:, c] = log[li][2].reshape(-1)
+                        cur_g = grad0[:, c].copy()
+                        li += 1
+                        have_grad = True
+                    assert ev[ei][0] == "N32" and ev[ei][1].shape == (1, 2)
+                    tape32[s, 1:3, c] = ev[ei][1].reshape(-1)
+                    ei += 1
+                    gd, ei = take_grad_draws(ei)
+                    tape32[s, 2 + 4 * K:, c] = gd
+                    assert ev[ei][0] == "N32" and ev[ei][1].shape == (1, 2) and ev[ei + 1][0] == "U32"
+                    tape32[s, 1 + 2 * K:3 + 2 * K, c] = ev[ei][1].reshape(-1)
+                    tape32[s, 1 + 4 * K, c] = ev[ei + 1][1][0]
+                    ei += 2
+                    names = [x[:2] for x in log[li:li + 8]]
+                    assert names == [("fn", "fwd"), ("fn", "grad"), ("model", "generate_samples"), ("model", "prior_log_prob"),
+                                     ("model", "calculate_log_kernel"), ("fn", "logprop"),
+                                     ("model", "prior_log_prob"), ("model", "calculate_log_kernel")], names
+                    (th_p, lq_fwd), g_p, y_p, pr_p, k_p, lq_rev, pr_o, k_o = [v[2] for v in log[li:li + 8]]
+                    li += 8
+                    assert th_p.dtype == np.float64 and y_p.dtype == np.float64 and g_p.dtype == np.float64
+                    log_acc = pr_p[0] + k_p[0] + lq_rev[0] - pr_o[0] - k_o[0] - lq_fwd[0]
+                    u_a = tape32[s, 1 + 4 * K, c]
+                    acc = bool(np.log(np.float32(u_a)) < log_acc) if u_a > 0 else bool(np.isfinite(log_acc))
+                    assert acc == changed or (acc and np.all(np.float32(th_p) == trace[s, c])), (s, c, acc, changed)
+                    if acc and not wide:
+                        wide, wide_at[c] = True, s
+                    if acc:
+                        cur_th, cur_y, cur_g = th_p.reshape(-1).copy(), y_p.reshape(-1).copy(), g_p.reshape(-1).copy()
+                    rec[s, 0, c] = (int(acc) << 1)
+                    rec[s, 1, c] = log_acc
+                    rec[s, 2:4, c], rec[s, 4:6, c], rec[s, 6:8, c] = th_p.reshape(-1), y_p.reshape(-1), g_p.reshape(-1)
+                    rec[s, 8, c], rec[s, 9, c], rec[s, 10, c], rec[s, 11, c] = pr_p[0], k_p[0], lq_rev[0], lq_fwd[0]
+            snapshot(T - 1)
+            assert np.array_equal(state[:, 0:2, c].astype(np.float32), trace[:, c])
+            assert ei == len(ev) and li == len(log), (ei, len(ev), li, len(log))
+        blob = dict(tape32=tape32, tape64=tape64, tape_grad0=tape_grad0, trace=trace, theta0=theta0s, y0=y0s, rec=rec,
+                    state=state, grad0=grad0, wide_at=wide_at, gf=np.float64(gf), T=np.int64(T), K=np.int64(K), num_grad=np.int64(num),
+                    tau=np.float64(tau))
+        blob.update(model_params(model))
+        blob.update(dist_params(ip, "ip"))
+        for k, v in blob.items():
+            blobs[f"case{ci}/{k}"] = v
+        fl = rec[:, 0].astype(np.int64)
+        print(f"mala case {ci}: gf={gf} K={K} num_grad={num} tau={tau} move rate {np.mean((fl >> 1) & 1):.4f} "
+              f"local accept rate {np.mean(((fl >> 1) & 1)[(fl & 1) == 0]):.4f} wide_at {wide_at.tolist()} "
+              f"f64-weight steps {np.mean((fl >> 16) & 1):.3f}")
+    blobs["n_cases"] = np.int64(len(cases))
+    np.savez_compressed(out_path, **blobs)
+
+
+# ----------------------------------------------------------------------------------------------
 # esjd (ESJD.py) and the distribution classes (distribution.py) — small deterministic fixtures
 # ----------------------------------------------------------------------------------------------
 def golden_misc(out_path):
@@ -392,6 +583,19 @@ def golden_misc(out_path):
 
 def main():
     import_reference()
+    only = sys.argv[1:]
+    mbase = dict(chains=4, epsilon=0.05, theta0=[0.0, 0.0], ip_loc=[0.0, 0.0], ip_log_scale=[0.0, 0.0])
+    mcases = [
+        dict(mbase, chains=6, gf=0.8, K=5, tau=0.3, num_grad=100, T=400),       # README.md:128 / config 3
+        dict(mbase, gf=0.3, K=3, tau=0.2, num_grad=33, T=500),                  # local-heavy: float64 state early
+        dict(mbase, gf=0.0, K=2, tau=0.25, num_grad=8, T=400),                  # never global
+        dict(mbase, gf=0.6, K=8, tau=0.4, num_grad=64, T=400, epsilon=0.2, theta0=[1.2, -1.4], ip_loc=[0.5, -0.25],
+             ip_log_scale=[0.4, 0.2]),
+    ]
+    if not only or "mala" in only:
+        golden_mala(mcases, os.path.join(HERE, "glmala.npz"))
+    if only:
+        return
     base = dict(chains=4, epsilon=0.05, theta0=[0.0, 0.0], lp_loc=[0.0, 0.0], lp_sigma=[0.35, 0.35],
                 gp_loc=[0.0, 0.0], gp_log_scale=[0.0, 0.0])
     cases = [

@@ -30,6 +30,7 @@ def model_pod(case, family=abi.MODEL_ABS_NORMAL):
     abi.fill(m.prior_scale, case["prior_scale"])
     m.eps_log_scale = float(case["eps_log_scale"])
     m.eps_scale = float(case["eps_scale"])
+    m.epsilon = float(case["epsilon"])
     return m
 
 
@@ -46,3 +47,92 @@ def rel_err(a, b):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     return np.abs(a - b) / np.maximum(np.abs(b), 1e-30)
+
+
+def fresh_mala_state(c):
+    aux = np.zeros((c, abi.AUX_SLOTS), np.float32)
+    aux[:, abi.AUX_LOCAL] = 1.0
+    return aux, np.zeros((c, abi.STATE64_SLOTS), np.float64)
+
+
+def mala_teacher_forced(case):
+    """Every (step, chain) of a GLMALA golden case as an independent one-step pseudo-chain started from the
+    reference's own recorded state before that step.  The reference's float32 finite-difference prior
+    gradient (GLMALA.py:84-85, h = 1e-5) turns 1e-8 differences in theta into 1e-2 differences in the
+    gradient, so free-running chains agree on decisions but not to 1e-5 on values; one-step restarts do."""
+    T, Cn, K, num = int(case["T"]), case["theta0"].shape[0], int(case["K"]), int(case["num_grad"])
+    S = T - 1
+    n = S * Cn
+    st = case["state"][:S]                                       # [S, 8, C] state before step s
+    flat = lambda a: np.ascontiguousarray(a.reshape(a.shape[0] * a.shape[1], *a.shape[2:]))  # noqa: E731
+    theta64 = flat(np.moveaxis(st[:, 0:2], 1, 2))                # [S*C, 2]
+    y64 = flat(np.moveaxis(st[:, 2:4], 1, 2))
+    grad = flat(np.moveaxis(st[:, 4:6], 1, 2))
+    lw = st[:, 6].reshape(-1)
+    bits = st[:, 7].reshape(-1).astype(np.int64)
+    aux = np.zeros((n, abi.AUX_SLOTS), np.float32)
+    aux[:, abi.AUX_LOCAL] = bits & 1
+    aux[:, abi.AUX_WIDE] = (bits >> 1) & 1
+    aux[:, abi.AUX_LW_WIDE] = (bits >> 2) & 1
+    aux[:, abi.AUX_HAVE_GRAD] = (bits >> 3) & 1
+    s64 = np.zeros((n, abi.STATE64_SLOTS), np.float64)
+    s64[:, abi.S64_THETA:abi.S64_THETA + 2] = theta64
+    s64[:, abi.S64_Y:abi.S64_Y + 2] = y64
+    s64[:, abi.S64_GRAD:abi.S64_GRAD + 2] = grad
+    s64[:, abi.S64_LOGW] = lw
+    slots = case["tape32"].shape[1]
+    tape32 = np.ascontiguousarray(np.moveaxis(case["tape32"], 1, 0).reshape(1, slots, n))   # [1, slots, S*C]
+    tape64 = np.ascontiguousarray(case["tape64"].reshape(1, n))
+    grad0 = np.ascontiguousarray(np.broadcast_to(case["tape_grad0"][:, None, :], (case["tape_grad0"].shape[0], S, Cn)).reshape(-1, n))
+    rec = np.ascontiguousarray(np.moveaxis(case["rec"], 1, 0).reshape(case["rec"].shape[1], n))  # [slots, S*C]
+    return dict(n=n, theta=theta64.astype(np.float32), y=y64.astype(np.float32), aux=aux, state64=s64, tape32=tape32,
+                tape64=tape64, tape_grad0=grad0, rec=rec, K=K, num_grad=num, tau=float(case["tau"]), gf=float(case["gf"]))
+
+
+def check_mala_debug(dbg, rec, K, tol=1e-5):
+    """dbg [DEBUG64_SLOTS, n] (kernel / oracle) vs rec [12+K, n] (reference): flags exact, values to `tol`."""
+    fl_o, fl_r = dbg[0].astype(np.int64), rec[0].astype(np.int64)
+    assert np.array_equal(fl_o, fl_r), f"{(fl_o != fl_r).sum()} decisions differ"
+    loc = (fl_r & 1) == 0
+    worst = {}
+
+    def cmp(name, a, b, m, atol=0.0):
+        a, b = a[m], b[m]
+        if a.size:
+            err = np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+            err = np.where(np.abs(a - b) <= atol, 0.0, err)
+            worst[name] = float(err.max())
+            assert err.max() <= tol, (name, float(err.max()))
+
+    cmp("log_acc", dbg[1], rec[1], loc)
+    for k in range(2):
+        cmp(f"theta'{k}", dbg[2 + k], rec[2 + k], loc)
+        cmp(f"y'{k}", dbg[6 + k], rec[4 + k], loc)
+        cmp(f"grad'{k}", dbg[10 + k], rec[6 + k], loc, atol=2e-5)   # differences of O(100) log-likelihoods / 0.2
+    cmp("prior'", dbg[14], rec[8], loc)
+    cmp("kern'", dbg[15], rec[9], loc)
+    cmp("lq_rev", dbg[16], rec[10], loc)
+    cmp("lq_fwd", dbg[17], rec[11], loc)
+    g = ~loc
+    cmp("lw_old", dbg[1], rec[1], g & np.isfinite(rec[1]), atol=3e-6)
+    pos = g & (rec[2] > 1e-300)
+    cmp("S", dbg[2], rec[2], pos, atol=1e-44)
+    cmp("w0", dbg[3], rec[3], pos, atol=1e-44)
+    for j in range(K):
+        cmp(f"lw{j}", dbg[4 + j], rec[4 + j], g & np.isfinite(rec[4 + j]), atol=3e-6)
+    return worst
+
+
+def check_mala_free_running(flags, trace, case, strict_all=False):
+    """free-running GLMALA replay vs the reference: decisions are bit-exact until float32 finite-difference
+    noise (see mala_teacher_forced) flips one — rare; traces of the chains without a flip agree to 2e-2."""
+    ref_fl = case["rec"][:, 0].astype(np.int64)
+    ne = flags.astype(np.int64) != ref_fl                       # [S, C]
+    first = np.where(ne.any(0), ne.argmax(0), ne.shape[0])       # first mismatching step per chain
+    clean = first == ne.shape[0]
+    assert clean.mean() >= 0.75, f"decisions diverged in {(~clean).sum()} of {clean.size} chains"
+    if strict_all:
+        assert clean.all()
+    for c in np.flatnonzero(clean):
+        assert np.allclose(trace[:, c], case["trace"][:, c], rtol=0, atol=2e-2), c
+    return clean

@@ -65,3 +65,31 @@ def test_golden_has_the_edge_cases():
     fl = np.concatenate([c["rec"][:, 0].astype(int).ravel() for c in i])
     assert (((fl & 1) == 1) & ((fl >> 8) == 0)).sum() > 0
     assert len({int(c["K"]) for c in i}) == 4
+
+
+@pytest.mark.parametrize("ci", range(4))
+def test_glmala_replay(ci):
+    """GLMALA.py:150-200 on the reference's own draws.  Free-running: every branch / accept / resample
+    decision bit-exact, traces equal up to the amplification of float32 finite-difference noise
+    (helpers.mala_teacher_forced).  Restarted from the reference's recorded state before each step:
+    theta', y', gradient, log-densities and log_acc within 1e-5 relative."""
+    from helpers import check_mala_debug, check_mala_free_running, fresh_mala_state, mala_teacher_forced
+    case = load_cases("glmala.npz")[ci]
+    T, Cn, K, num = int(case["T"]), case["theta0"].shape[0], int(case["K"]), int(case["num_grad"])
+    theta, y = case["theta0"].copy(), case["y0"].copy()
+    aux, s64 = fresh_mala_state(Cn)
+    dbg = np.zeros((T - 1, abi.DEBUG64_SLOTS, Cn))
+    tr = oracle.run("mala", model_pod(case), None, gauss_pod(case, "ip"), theta=theta, y=y, n_steps=T - 1,
+                    gf=float(case["gf"]), rng_mode=abi.RNG_REPLAY, tape32=case["tape32"], tape64=case["tape64"],
+                    tape_grad0=case["tape_grad0"], aux=aux, state64=s64, debug64=dbg, K=K, num_grad=num,
+                    tau=float(case["tau"]))
+    clean = check_mala_free_running(dbg[:, 0], tr, case, strict_all=(ci == 0))
+    final = case["state"][-1]
+    assert np.array_equal(aux[clean, abi.AUX_WIDE], ((final[7].astype(np.int64) >> 1) & 1).astype(np.float32)[clean])
+
+    tf = mala_teacher_forced(case)
+    dbg1 = np.zeros((1, abi.DEBUG64_SLOTS, tf["n"]))
+    oracle.run("mala", model_pod(case), None, gauss_pod(case, "ip"), theta=tf["theta"], y=tf["y"], n_steps=1, gf=tf["gf"],
+               rng_mode=abi.RNG_REPLAY, tape32=tf["tape32"], tape64=tf["tape64"], tape_grad0=tf["tape_grad0"], aux=tf["aux"],
+               state64=tf["state64"], debug64=dbg1, K=K, num_grad=num, tau=tf["tau"], trace_layout=abi.TRACE_NONE)
+    check_mala_debug(dbg1[0], tf["rec"], K)
