@@ -28,6 +28,9 @@ SAMPLERS = {
                    workload="README Mixture_set GlobalMCMC (BASELINE configs[1])"),
     "glmcmc": dict(entry="isir", gf=0.9, K=5, alg_inst=703,
                    workload="README Mixture_set GLMCMC iSIR K=5, gf=0.9 (BASELINE configs[2], run_glmcmc)"),
+    # GLMALA.py:150-200, gf=0.8, K=5, tau=0.3, num_grad=100: 0.2 * ~22,000 (400 CRN simulator draws) + 0.8 * 760
+    "glmala": dict(entry="mala", gf=0.8, K=5, alg_inst=5000, num_grad=100, tau=0.3,
+                   workload="README Mixture_set GLMALA K=5, gf=0.8, tau=0.3, num_grad=100 (BASELINE configs[2], run_glmala)"),
 }
 
 
@@ -120,13 +123,16 @@ class CpuPort:
         theta = np.zeros((c, 2), np.float32)
         y = (np.random.default_rng(0).standard_normal((c, 2)) * 0.2236).astype(np.float32)
         trace = np.zeros((c, t + 1, 2), np.float32)
-        aux = None
+        aux, extra = None, {}
         if self.spec["K"]:
             aux = np.zeros((c, abi.AUX_SLOTS), np.float32)
             aux[:, abi.AUX_LOCAL] = 1.0
+        if self.spec["entry"] == "mala":
+            extra = dict(num_grad=self.spec["num_grad"], tau=self.spec["tau"], state64=np.zeros((c, abi.STATE64_SLOTS)))
         t0 = time.perf_counter()
         self.oracle.run(self.spec["entry"], *self.pods, theta=theta, y=y, n_steps=t, gf=self.spec["gf"], seed=0,
-                        trace=trace, trace_layout=abi.TRACE_CHAIN_MAJOR, threads=self.threads, K=self.spec["K"], aux=aux)
+                        trace=trace, trace_layout=abi.TRACE_CHAIN_MAJOR, threads=self.threads, K=self.spec["K"], aux=aux,
+                        **extra)
         return time.perf_counter() - t0
 
     def size_sample(self, chains, iters, seconds):
@@ -228,19 +234,25 @@ def main():
         aux0[:, abi.AUX_LOCAL] = 1.0
         aux = aux0.clone()
     summary = None
+    extra, s64 = {}, None
+    if entry == "mala":
+        s64 = torch.zeros(C, abi.STATE64_SLOTS, device="cuda", dtype=torch.float64)
+        extra = dict(num_grad=spec["num_grad"], tau=spec["tau"], state64=s64)
 
     def reset_state():
         theta.copy_(theta0)
         y.copy_(y0)
         if K:
             aux.copy_(aux0)
+        if s64 is not None:
+            s64.zero_()
 
     def one_step(step_idx):
         nonlocal summary
         reset_state()
         stats.zero_()
         eng.run(entry, theta=theta, y=y, n_steps=T - 1, gf=gf, seed=step_idx, chain_id_base=chain_base,
-                trace_layout=layout, trace=trace, trace_rows=T, stats=stats, block_threads=a.block, K=K, aux=aux)
+                trace_layout=layout, trace=trace, trace_rows=T, stats=stats, block_threads=a.block, K=K, aux=aux, **extra)
         rs = RunStats(stats, d)
         summary = sharding.allreduce_summary(sharding.summarize(rs))   # NCCL only for N > 1
 
@@ -279,7 +291,7 @@ def main():
         reset_state()
         k0.record()
         eng.run(entry, theta=theta, y=y, n_steps=T - 1, gf=gf, seed=s, chain_id_base=chain_base,
-                trace_layout=layout, trace=trace, trace_rows=T, stats=stats, block_threads=a.block, K=K, aux=aux)
+                trace_layout=layout, trace=trace, trace_rows=T, stats=stats, block_threads=a.block, K=K, aux=aux, **extra)
         k1.record()
         torch.cuda.synchronize()
         kernel_ms.append(k0.elapsed_time(k1))
@@ -323,6 +335,9 @@ def main():
         h_stats = torch.zeros(C, abi.nstats(d)).pin_memory()
         h_aux0 = aux0.cpu().pin_memory() if K else None
         h_aux = torch.empty_like(h_aux0).pin_memory() if K else None
+        h_extra = dict(extra)
+        if s64 is not None:
+            h_extra["state64"] = torch.zeros(C, abi.STATE64_SLOTS, dtype=torch.float64).pin_memory()
         h_layout = abi.TRACE_TIME_MAJOR if layout != abi.TRACE_NONE else abi.TRACE_NONE
         del trace
         torch.cuda.empty_cache()
@@ -334,8 +349,11 @@ def main():
             h_stats.zero_()
             if K:
                 h_aux.copy_(h_aux0)
+            if s64 is not None:
+                h_extra["state64"].zero_()
             eng.run_host(entry, theta=h_theta, y=h_y, n_steps=T - 1, gf=gf, seed=i, chain_id_base=chain_base,
-                         trace=h_trace, trace_layout=h_layout, stats=h_stats, block_threads=a.block, K=K, aux=h_aux)
+                         trace=h_trace, trace_layout=h_layout, stats=h_stats, block_threads=a.block, K=K, aux=h_aux,
+                         **h_extra)
         e2e_step(0)
         barrier()
         t0 = time.perf_counter()

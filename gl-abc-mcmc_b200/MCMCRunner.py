@@ -29,3 +29,12 @@ class MCMCRunner:
                       Local_Proposal=local_proposal, filelocation=self._path(output_file),
                       global_frequency=global_frequency, Importance_Proposal=importance_proposal,
                       batch_size=batch_size, **kw)
+
+    def run_glmala(self, num_iterations, initial_theta, initial_y, global_frequency, importance_proposal,
+                   batch_size, tau, num_grad, output_file="glmala_results.csv", **kw):
+        """reference MCMCRunner.py:78-98"""
+        from .GLMALA import GLMALA
+        return GLMALA(ABCset=self.abc_set, num_ite=num_iterations, Initial_theta=initial_theta, Initial_y=initial_y,
+                      tau=tau, num_grad=num_grad, filelocation=self._path(output_file),
+                      global_frequency=global_frequency, Importance_Proposal=importance_proposal,
+                      batch_size=batch_size, **kw)

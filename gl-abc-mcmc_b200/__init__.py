@@ -7,6 +7,7 @@ Export list mirrors the reference's `glabcmcmc/__init__.py:1-14`.
 from . import _abi  # noqa: F401
 from .distribution import DiagGaussian, Gamma, GaussianMixture, Uniform  # noqa: F401
 from .ESJD import esjd  # noqa: F401
+from .GLMALA import GLMALA  # noqa: F401
 from .GLMCMC import GLMCMC  # noqa: F401
 from .GlobalMCMC import GlobalMCMC  # noqa: F401
 from .MCMCRunner import MCMCRunner  # noqa: F401

@@ -107,6 +107,7 @@ _SIGNATURES = {
     "glabc_run_isir": (C.c_int, [C.c_void_p, C.POINTER(RunPOD)]),
     "glabc_run_isir_host": (C.c_int, [C.c_void_p, C.POINTER(RunPOD), C.c_int64]),
     "glabc_run_mala": (C.c_int, [C.c_void_p, C.POINTER(RunPOD)]),
+    "glabc_run_mala_host": (C.c_int, [C.c_void_p, C.POINTER(RunPOD), C.c_int64]),
     "glabc_esjd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "glabc_philox_kat": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
 }

@@ -8,6 +8,7 @@
 #include <string>
 
 #include "launch.cuh"
+#include "step_mala.cuh"
 
 using namespace glabc;
 
@@ -22,6 +23,8 @@ struct glabc_ctx {
     // scratch of the host-buffer entry points
     float* d_state = nullptr;  // theta | y | aux | stats
     size_t state_cap = 0;
+    double* d_state64 = nullptr;  // GLMALA carried float64 state
+    size_t state64_cap = 0;
     float* d_trace[2] = {nullptr, nullptr};
     size_t trace_cap = 0;
     cudaStream_t s_compute = nullptr, s_copy = nullptr;
@@ -96,6 +99,7 @@ int glabc_ctx_destroy(glabc_ctx* ctx)
     if (!ctx) return GLABC_OK;
     cudaSetDevice(ctx->device);
     if (ctx->d_state) cudaFree(ctx->d_state);
+    if (ctx->d_state64) cudaFree(ctx->d_state64);
     for (int b = 0; b < 2; ++b) {
         if (ctx->d_trace[b]) cudaFree(ctx->d_trace[b]);
         if (ctx->ev_done[b]) cudaEventDestroy(ctx->ev_done[b]);
@@ -264,6 +268,11 @@ static int make_run_params(glabc_ctx* ctx, const glabc_run_t* run, int dim, int 
     r.tape_dump = run->tape_dump;
     r.tape64_dump = run->tape64_dump;
     r.n_candidates = run->n_candidates;
+    r.trace_layout = run->trace_layout;
+    r.state64 = run->state64;
+    r.tape_grad0 = run->tape_grad0;
+    r.tape_grad0_dump = run->tape_grad0_dump;
+    r.debug64 = run->debug64;
     (void)dim;
     *out = r;
     return GLABC_OK;
@@ -272,7 +281,7 @@ static int make_run_params(glabc_ctx* ctx, const glabc_run_t* run, int dim, int 
 // ---------------------------------------------------------------------------------------------
 // sampler dispatch (device buffers)
 // ---------------------------------------------------------------------------------------------
-enum SamplerKind { SAMPLER_GLOBAL = 0, SAMPLER_ISIR = 1 };
+enum SamplerKind { SAMPLER_GLOBAL = 0, SAMPLER_ISIR = 1, SAMPLER_MALA = 2 };
 
 static int run_device(glabc_ctx* ctx, SamplerKind kind, const glabc_run_t* run)
 {
@@ -315,6 +324,41 @@ static int run_device(glabc_ctx* ctx, SamplerKind kind, const glabc_run_t* run)
         CUDA_TRY(ctx, launch_isir(make_model(ctx->model), make_gauss(lp.a, lp.b, lp.c, d), make_gauss(ip.a, ip.b, ip.c, d), d, R,
                                   run->arith_mode == GLABC_ARITH_STRICT, run->rng_mode == GLABC_RNG_REPLAY,
                                   run->trace_layout, block, static_cast<cudaStream_t>(run->stream)));
+        return GLABC_OK;
+    }
+    case SAMPLER_MALA: {
+        if (!ctx->has_dist[GLABC_SLOT_IMPORTANCE])
+            return fail(ctx, GLABC_ERR_INVALID, "run_mala needs the IMPORTANCE proposal slot bound");
+        const glabc_dist_t& ip = ctx->dist[GLABC_SLOT_IMPORTANCE];
+        if (ip.dim != d) return fail(ctx, GLABC_ERR_INVALID, "proposal dim does not match theta_dim %d", d);
+        if (!run) return fail(ctx, GLABC_ERR_INVALID, "null run description");
+        if (run->n_candidates < 1 || run->n_candidates > GLABC_MAX_K)
+            return fail(ctx, GLABC_ERR_INVALID, "n_candidates (batch_size) must be in 1..%d", GLABC_MAX_K);
+        if (run->num_grad < 2 || run->num_grad > GLABC_MAX_NUM_GRAD)
+            return fail(ctx, GLABC_ERR_INVALID, "num_grad must be in 2..%d (the variance is unbiased, GLMALA.py:88)", GLABC_MAX_NUM_GRAD);
+        if (!(run->tau > 0.0f)) return fail(ctx, GLABC_ERR_INVALID, "tau must be positive");
+        if (!run->aux || !run->state64)
+            return fail(ctx, GLABC_ERR_INVALID, "run_mala needs aux [C][%d] and state64 [C][%d]", GLABC_AUX_SLOTS, GLABC_STATE64_SLOTS);
+        int st = make_run_params(ctx, run, d, GLABC_TAPE_MALA_SLOTS(d, d, run->n_candidates, run->num_grad), &R, &block);
+        if (st) return st;
+        if (run->rng_mode == GLABC_RNG_REPLAY && (!run->tape64 || !run->tape_grad0))
+            return fail(ctx, GLABC_ERR_INVALID, "replay of run_mala needs tape64 and tape_grad0");
+        if (run->tape_dump && !run->tape_grad0_dump)
+            return fail(ctx, GLABC_ERR_INVALID, "tape_dump of run_mala also needs tape_grad0_dump");
+        if (R.n_chains == 0) return GLABC_OK;
+        if (run->block_threads == 0) block = 128;  // 4 chains (warps) per block
+        MalaConsts K{};
+        K.model = make_model(ctx->model);
+        K.ip = make_gauss(ip.a, ip.b, ip.c, d);
+        const float zeros[GLABC_MAX_DIM] = {0}, ones[GLABC_MAX_DIM] = {1, 1, 1, 1, 1, 1, 1, 1};
+        K.unit = make_gauss(zeros, zeros, ones, d);
+        const double eps = ctx->model.epsilon > 0.0 ? ctx->model.epsilon : static_cast<double>(ctx->model.eps_scale);
+        K.eps2 = eps * eps;
+        K.tau = run->tau64 != 0.0 ? run->tau64 : static_cast<double>(run->tau);
+        K.tau_f = run->tau;
+        K.num_grad = run->num_grad;
+        CUDA_TRY(ctx, launch_mala(K, d, R, run->arith_mode == GLABC_ARITH_STRICT, run->rng_mode == GLABC_RNG_REPLAY, block,
+                                  static_cast<cudaStream_t>(run->stream)));
         return GLABC_OK;
     }
     }
@@ -379,6 +423,14 @@ static int run_host(glabc_ctx* ctx, SamplerKind kind, const glabc_run_t* run, in
                  n_stats = run->stats ? size_t(C) * ns : 0;
     int st = ensure_host_scratch(ctx, n_theta + n_y + n_aux + n_stats, traced ? size_t(buf_rows) * C * d : 0);
     if (st) return st;
+    const size_t n_s64 = run->state64 ? size_t(C) * GLABC_STATE64_SLOTS : 0;
+    if (n_s64 > ctx->state64_cap) {
+        if (ctx->d_state64) cudaFree(ctx->d_state64);
+        ctx->d_state64 = nullptr;
+        ctx->state64_cap = 0;
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_state64, n_s64 * sizeof(double)));
+        ctx->state64_cap = n_s64;
+    }
     float* d_theta = ctx->d_state;
     float* d_y = d_theta + n_theta;
     float* d_aux = n_aux ? d_y + n_y : nullptr;
@@ -389,6 +441,7 @@ static int run_host(glabc_ctx* ctx, SamplerKind kind, const glabc_run_t* run, in
     CUDA_TRY(ctx, cudaMemcpyAsync(d_y, run->y, n_y * sizeof(float), cudaMemcpyHostToDevice, sc));
     if (d_aux) CUDA_TRY(ctx, cudaMemcpyAsync(d_aux, run->aux, n_aux * sizeof(float), cudaMemcpyHostToDevice, sc));
     if (d_stats) CUDA_TRY(ctx, cudaMemcpyAsync(d_stats, run->stats, n_stats * sizeof(float), cudaMemcpyHostToDevice, sc));
+    if (n_s64) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_state64, run->state64, n_s64 * sizeof(double), cudaMemcpyHostToDevice, sc));
 
     int64_t done = 0;
     int b = 0;
@@ -404,9 +457,13 @@ static int run_host(glabc_ctx* ctx, SamplerKind kind, const glabc_run_t* run, in
         dev.y = d_y;
         dev.aux = d_aux;
         dev.stats = d_stats;
+        dev.state64 = n_s64 ? ctx->d_state64 : nullptr;
         dev.stream = sc;
         dev.tape_dump = nullptr;
+        dev.tape_grad0_dump = nullptr;
+        dev.tape64_dump = nullptr;
         dev.debug = nullptr;
+        dev.debug64 = nullptr;
         const int64_t row_lo = dev.step_base + (dev.write_row0 ? 0 : 1);  // first absolute row this chunk writes
         const int64_t n_rows = n + (dev.write_row0 ? 1 : 0);
         if (traced) {
@@ -448,6 +505,7 @@ static int run_host(glabc_ctx* ctx, SamplerKind kind, const glabc_run_t* run, in
     CUDA_TRY(ctx, cudaMemcpyAsync(run->y, d_y, n_y * sizeof(float), cudaMemcpyDeviceToHost, sc));
     if (d_aux) CUDA_TRY(ctx, cudaMemcpyAsync(run->aux, d_aux, n_aux * sizeof(float), cudaMemcpyDeviceToHost, sc));
     if (d_stats) CUDA_TRY(ctx, cudaMemcpyAsync(run->stats, d_stats, n_stats * sizeof(float), cudaMemcpyDeviceToHost, sc));
+    if (n_s64) CUDA_TRY(ctx, cudaMemcpyAsync(run->state64, ctx->d_state64, n_s64 * sizeof(double), cudaMemcpyDeviceToHost, sc));
     CUDA_TRY(ctx, cudaStreamSynchronize(sc));
     CUDA_TRY(ctx, cudaStreamSynchronize(sx));
     return GLABC_OK;
@@ -467,6 +525,13 @@ int glabc_run_isir(glabc_ctx* ctx, const glabc_run_t* run) { return run_device(c
 int glabc_run_isir_host(glabc_ctx* ctx, const glabc_run_t* run, int64_t chunk_steps)
 {
     return run_host(ctx, SAMPLER_ISIR, run, chunk_steps);
+}
+
+int glabc_run_mala(glabc_ctx* ctx, const glabc_run_t* run) { return run_device(ctx, SAMPLER_MALA, run); }
+
+int glabc_run_mala_host(glabc_ctx* ctx, const glabc_run_t* run, int64_t chunk_steps)
+{
+    return run_host(ctx, SAMPLER_MALA, run, chunk_steps);
 }
 
 int glabc_esjd(glabc_ctx* ctx, const float* trace, int32_t layout, int64_t rows, int64_t chains, int32_t dim, float* out,

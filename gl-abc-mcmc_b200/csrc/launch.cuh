@@ -12,6 +12,9 @@ cudaError_t launch_global_mcmc(const ModelConsts& model, const GaussConsts& lp, 
 cudaError_t launch_isir(const ModelConsts& model, const GaussConsts& lp, const GaussConsts& ip, int dim, const RunParams& R,
                         bool strict, bool replay, int layout, int block, cudaStream_t st);
 
+struct MalaConsts;
+cudaError_t launch_mala(const MalaConsts& K, int dim, const RunParams& R, bool strict, bool replay, int block, cudaStream_t st);
+
 cudaError_t launch_esjd(const float* trace, int layout, int64_t rows, int64_t chains, int dim, float* out,
                         cudaStream_t st);
 

@@ -34,6 +34,12 @@ struct RunParams {
     float* tape_dump;
     double* tape64_dump;
     int32_t n_candidates;
+    // GLMALA (K3)
+    int32_t trace_layout;
+    double* state64;
+    const float* tape_grad0;
+    float* tape_grad0_dump;
+    double* debug64;
 };
 
 __device__ __forceinline__ Stream chain_stream(const RunParams& r, int32_t chain)

@@ -103,11 +103,12 @@ class Engine:
             rng_mode=_abi.RNG_NATIVE, arith=_abi.ARITH_FAST, trace_layout=_abi.TRACE_CHAIN_MAJOR, trace=None,
             trace_rows=None, trace_chains=None, trace_chain_off=0, trace_row_base=0, write_row0=True,
             stats=None, aux=None, tape32=None, tape64=None, debug=None, tape_dump=None, tape64_dump=None, K=0,
-            block_threads=0):
+            block_threads=0, num_grad=0, tau=0.0, state64=None, tape_grad0=None, tape_grad0_dump=None, debug64=None):
         """Enqueue `n_steps` transitions of every chain on the current stream (device tensors,
         state updated in place).  Returns the trace tensor (allocated here unless given)."""
         cn, d = theta.shape
-        for t in (theta, y, stats, aux, tape32, tape64, debug, tape_dump, tape64_dump, trace):
+        for t in (theta, y, stats, aux, tape32, tape64, debug, tape_dump, tape64_dump, trace, state64, tape_grad0,
+                  tape_grad0_dump, debug64):
             if t is not None and (not t.is_cuda or not t.is_contiguous()):
                 raise ValueError("device entry point takes contiguous CUDA tensors")
         rows = trace_rows if trace_rows is not None else step_base + n_steps + 1 - trace_row_base
@@ -123,6 +124,9 @@ class Engine:
                         theta=self._ptr(theta), y=self._ptr(y), aux=self._ptr(aux), trace=self._ptr(trace),
                         stats=self._ptr(stats), tape32=self._ptr(tape32), tape64=self._ptr(tape64),
                         debug=self._ptr(debug), tape_dump=self._ptr(tape_dump), tape64_dump=self._ptr(tape64_dump),
+                        num_grad=int(num_grad), tau=float(tau), tau64=float(tau), state64=self._ptr(state64),
+                        tape_grad0=self._ptr(tape_grad0), tape_grad0_dump=self._ptr(tape_grad0_dump),
+                        debug64=self._ptr(debug64),
                         stream=C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
         fn = getattr(self.lib, "glabc_run_" + sampler)
         self.ctx.check(fn(self.ctx.handle, C.byref(r)))
@@ -130,7 +134,7 @@ class Engine:
 
     def run_host(self, sampler, *, theta, y, n_steps, gf, trace, step_base=0, chain_id_base=0, seed=0,
                  arith=_abi.ARITH_FAST, trace_layout=_abi.TRACE_TIME_MAJOR, write_row0=True, stats=None,
-                 aux=None, K=0, chunk_steps=0, block_threads=0):
+                 aux=None, K=0, chunk_steps=0, block_threads=0, num_grad=0, tau=0.0, state64=None):
         """The reference-facing call on HOST buffers (numpy-compatible CPU tensors, ideally pinned):
         H2D of the state, kernels, D2H of trace/state/stats — returns when the host buffers hold the
         result."""
@@ -138,6 +142,8 @@ class Engine:
         for t in (theta, y, stats, aux, trace):
             if t is not None and (t.is_cuda or not t.is_contiguous() or t.dtype != torch.float32):
                 raise ValueError("host entry point takes contiguous float32 CPU tensors")
+        if state64 is not None and (state64.is_cuda or not state64.is_contiguous() or state64.dtype != torch.float64):
+            raise ValueError("state64 must be a contiguous float64 CPU tensor")
         if trace_layout == _abi.TRACE_NONE:
             rows, tchains = 0, cn
         elif trace_layout == _abi.TRACE_TIME_MAJOR:
@@ -149,7 +155,8 @@ class Engine:
                         arith_mode=arith, trace_layout=trace_layout, write_row0=int(write_row0),
                         block_threads=block_threads, n_candidates=K, trace_rows=rows, trace_chains=tchains,
                         trace_chain_off=0, trace_row_base=0, theta=self._ptr(theta), y=self._ptr(y),
-                        aux=self._ptr(aux), trace=self._ptr(trace), stats=self._ptr(stats))
+                        aux=self._ptr(aux), trace=self._ptr(trace), stats=self._ptr(stats), num_grad=int(num_grad),
+                        tau=float(tau), tau64=float(tau), state64=self._ptr(state64))
         fn = getattr(self.lib, f"glabc_run_{sampler}_host")
         self.ctx.check(fn(self.ctx.handle, C.byref(r), int(chunk_steps)))
         return trace

@@ -74,7 +74,7 @@ def print_summary(chain):
 
 def run_chains(sampler, eng, model_pod, *, num_ite, Initial_theta, Initial_y, global_frequency, filelocation,
                num_chains, seed, chain_id_base, arith, trace, return_stats, verbose, K=0, aux_init=None,
-               block_threads=0):
+               block_threads=0, **sampler_kw):
     if num_ite < 1:
         raise ValueError("num_ite must be at least 1")
     seed = default_seed() if seed is None else int(seed)
@@ -90,7 +90,7 @@ def run_chains(sampler, eng, model_pod, *, num_ite, Initial_theta, Initial_y, gl
             aux[:, slot] = val
     out = eng.run(sampler, theta=theta, y=y, n_steps=num_ite - 1, gf=global_frequency, seed=seed,
                   chain_id_base=chain_id_base, arith=_ARITH[arith], trace_layout=layout, stats=stats, aux=aux, K=K,
-                  block_threads=block_threads)
+                  block_threads=block_threads, **sampler_kw)
     rs = RunStats(stats, d)
     if single:
         chain = (out[0] if layout == _abi.TRACE_CHAIN_MAJOR else out[:, 0]).cpu() if out is not None else None

@@ -258,10 +258,11 @@ GLABC_API int glabc_run_isir(glabc_ctx* ctx, const glabc_run_t* run);
 GLABC_API int glabc_run_mala(glabc_ctx* ctx, const glabc_run_t* run);
 
 /* ---- samplers: host buffers (the reference-facing call: H2D state, run, D2H trace + stats) --- */
-/* `run->theta`, `y`, `trace`, `stats` are HOST pointers here; the trace is copied back in
+/* `run->theta`, `y`, `aux`, `state64`, `trace`, `stats` are HOST pointers here; the trace is copied back in
  * `chunk_steps`-row chunks overlapped with the next chunk's kernel (0 = library default).        */
 GLABC_API int glabc_run_global_host(glabc_ctx* ctx, const glabc_run_t* run, int64_t chunk_steps);
 GLABC_API int glabc_run_isir_host(glabc_ctx* ctx, const glabc_run_t* run, int64_t chunk_steps);
+GLABC_API int glabc_run_mala_host(glabc_ctx* ctx, const glabc_run_t* run, int64_t chunk_steps);
 
 /* ---- diagnostics --------------------------------------------------------------------------- */
 /* esjd(), ESJD.py:2-25, for every chain of a device trace: out[c] = det(D^T D/(N-1))^(1/d).

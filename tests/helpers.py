@@ -30,7 +30,7 @@ def model_pod(case, family=abi.MODEL_ABS_NORMAL):
     abi.fill(m.prior_scale, case["prior_scale"])
     m.eps_log_scale = float(case["eps_log_scale"])
     m.eps_scale = float(case["eps_scale"])
-    m.epsilon = float(case["epsilon"])
+    m.epsilon = float(case["epsilon"]) if "epsilon" in case else float(case["eps_scale"])
     return m
 
 
