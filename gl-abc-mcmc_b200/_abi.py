@@ -80,6 +80,20 @@ class RunPOD(C.Structure):
                 ("debug64", C.c_void_p), ("tau64", C.c_double), ("stream", C.c_void_p)]
 
 
+class AglmcmcPOD(C.Structure):
+    """glabc_aglmcmc_t"""
+    _fields_ = [("step_size", C.c_int32), ("init", C.c_int32), ("alpha", C.c_float), ("hat_eps_T", C.c_float),
+                ("kde_rule", C.c_int32), ("tape_rounds", C.c_int32),
+                ("init_p", C.c_void_p), ("init_s", C.c_void_p), ("ad_idx", C.c_void_p), ("ad_noise", C.c_void_p),
+                ("ad_sim", C.c_void_p), ("ad_rec", C.c_void_p), ("ad_blk", C.c_void_p), ("init_w", C.c_void_p),
+                ("dump_rounds", C.c_int32), ("reserved", C.c_int32)]
+
+
+BW_SILVERMAN, BW_SCOTT = 0, 1
+AG_REC_SLOTS = 8
+AG_MAX_BLOCK = 4096
+
+
 def fill(arr, values):
     values = [float(v) for v in values]
     if len(values) > len(arr):
@@ -108,6 +122,13 @@ _SIGNATURES = {
     "glabc_run_isir_host": (C.c_int, [C.c_void_p, C.POINTER(RunPOD), C.c_int64]),
     "glabc_run_mala": (C.c_int, [C.c_void_p, C.POINTER(RunPOD)]),
     "glabc_run_mala_host": (C.c_int, [C.c_void_p, C.POINTER(RunPOD), C.c_int64]),
+    "glabc_run_aglmcmc": (C.c_int, [C.c_void_p, C.POINTER(RunPOD), C.POINTER(AglmcmcPOD)]),
+    "glabc_kde_fit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
+                                C.c_void_p, C.c_void_p, C.c_void_p]),
+    "glabc_kde_log_prob": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                     C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
+    "glabc_kde_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                   C.c_int32, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "glabc_esjd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "glabc_philox_kat": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
 }

@@ -217,6 +217,39 @@ typedef struct {
 #define GLABC_DEBUG64_SLOTS 20
 #define GLABC_MAX_NUM_GRAD 4096
 
+/* ---- AGLMCMC (AGLMCMC.py:44-288) -------------------------------------------------------------
+ * Every chain owns a block of B = batch_size * step_size pre-generated importance candidates
+ * (theta0, x0, w0, log q0, dis0; AGLMCMC.py:84-112); a global move runs iSIR against the next
+ * batch_size of them (:127-162); after step_size global moves the chain adapts (:170-249): eps-hat
+ * quantile update, weighted KernelDensity refit on the block, a new block sampled from the KDE.
+ * The block / KDE workspace lives inside the context (sized n_chains * B).                          */
+typedef enum { GLABC_BW_SILVERMAN = 0, GLABC_BW_SCOTT = 1 } glabc_bw_rule;
+
+#define GLABC_AG_REC_SLOTS 8     /* per adaptation: 0 eps-hat, 1 KDE training points, 2+i bandwidth[i] (i < 4) */
+#define GLABC_AG_MAX_BLOCK 4096  /* batch_size * step_size                                                    */
+
+typedef struct {
+    int32_t step_size;        /* adaptation period S in global moves (AGLMCMC.py:167)                  */
+    int32_t init;             /* 1: start of a run — draw the initial block from the IMPORTANCE slot
+                                 (AGLMCMC.py:84-119); 0: continue from the context's workspace          */
+    float alpha;              /* AGLMCMC.py:186                                                         */
+    float hat_eps_T;          /* AGLMCMC.py:174,196                                                     */
+    int32_t kde_rule;         /* glabc_bw_rule; the reference uses 'silverman' (AGLMCMC.py:214)         */
+    int32_t tape_rounds;      /* replay: adaptations the tapes hold per chain                           */
+    /* replay tapes (the reference's draws), chain-minor like tape32 */
+    const float* init_p;      /* [B*d][C]   normals of Initial_ISIR_prop.forward(B)   (AGLMCMC.py:84)  */
+    const float* init_s;      /* [B*y][C]   simulator normals of the initial block     (:94)            */
+    const int32_t* ad_idx;    /* [R][4B][C] torch.multinomial indices of KDE.sample    (:220)           */
+    const float* ad_noise;    /* [R][4B*d][C] KDE.sample normals                                        */
+    const float* ad_sim;      /* [R][B*y][C] simulator normals of the new block        (:232)           */
+    /* optional dumps for parity tests (any rng mode) */
+    float* ad_rec;            /* [R][GLABC_AG_REC_SLOTS][C]                                             */
+    float* ad_blk;            /* [R][B][d + 3][C]: theta0[d], log q0, w0, dis0 of the block after adaptation r */
+    float* init_w;            /* [B][C] weights of the initial block                                    */
+    int32_t dump_rounds;      /* R of ad_rec / ad_blk                                                   */
+    int32_t reserved;
+} glabc_aglmcmc_t;
+
 typedef struct glabc_ctx glabc_ctx;
 
 #if defined(__GNUC__)
@@ -256,6 +289,30 @@ GLABC_API int glabc_run_isir(glabc_ctx* ctx, const glabc_run_t* run);
  * synthetic-likelihood gradient numberical_gradient_logABC (:46-95) from 2*d*num_grad simulator draws with
  * common random numbers.  run->tau, run->num_grad, run->n_candidates; needs aux and state64.          */
 GLABC_API int glabc_run_mala(glabc_ctx* ctx, const glabc_run_t* run);
+
+/* AGLMCMC loop body, AGLMCMC.py:124-272.  LOCAL slot = Local_Proposal, IMPORTANCE slot = Initial_ISIR_prop;
+ * run->n_candidates = batch_size.  Chains pause individually when they reach an adaptation; the call runs
+ * step / adapt rounds until every chain has performed run->n_steps iterations.  Debug slots (float32, `debug`):
+ * 0 flags as run_isir; global move: 1 proposal log-density of the current state, 2 its weight, 3 sum of the
+ * K+1 weights; local move: as run_global.                                                                    */
+GLABC_API int glabc_run_aglmcmc(glabc_ctx* ctx, const glabc_run_t* run, const glabc_aglmcmc_t* ag);
+
+/* ---- KernelDensity (kernel_density.py:4-177), batched over `sets` independent point sets ------------------
+ * Set s holds n[s] points X[s][cap][dim] (n == NULL: every set holds `cap` points).                          */
+/* fit, kernel_density.py:22-94: weights_out[s][j] = w / sum(w) (uniform when w == NULL),
+ * bw_out[s][i] = h(n, dim, rule) * weighted unbiased std of coordinate i                                    */
+GLABC_API int glabc_kde_fit(glabc_ctx* ctx, const float* X, const float* w, const int32_t* n, int64_t sets, int64_t cap,
+                            int32_t dim, int32_t rule, float* weights_out, float* bw_out, void* stream);
+/* log_prob, kernel_density.py:96-128: out[s][q] = logsumexp_j(log N(x[s][q]; X[s][j], diag(bw[s]^2)) + log(w[s][j] + 1e-10))
+ * for m queries per set, x[s][m][dim].  arith: glabc_arith_mode.                                             */
+GLABC_API int glabc_kde_log_prob(glabc_ctx* ctx, const float* X, const float* weights, const float* bw, const int32_t* n,
+                                 int64_t sets, int64_t cap, int32_t dim, const float* x, int64_t m, float* out,
+                                 int32_t arith, void* stream);
+/* sample, kernel_density.py:130-156: out[s][q] = X[s][idx] + bw[s] * normal, idx ~ Categorical(weights[s]).
+ * idx_tape / noise_tape ([s][m] / [s][m][dim], or NULL): replay the reference's torch.multinomial / randn draws. */
+GLABC_API int glabc_kde_sample(glabc_ctx* ctx, const float* X, const float* weights, const float* bw, const int32_t* n,
+                               int64_t sets, int64_t cap, int32_t dim, int64_t m, uint64_t seed, const int32_t* idx_tape,
+                               const float* noise_tape, float* out, void* stream);
 
 /* ---- samplers: host buffers (the reference-facing call: H2D state, run, D2H trace + stats) --- */
 /* `run->theta`, `y`, `aux`, `state64`, `trace`, `stats` are HOST pointers here; the trace is copied back in

@@ -921,6 +921,364 @@ ORACLE_EXPORT int oracle_run_mala(const glabc_model_t* m, const glabc_dist_t* un
 }
 
 /* -------------------------------------------------------------------------------------------
+ * KernelDensity — kernel_density.py:22-177
+ * ------------------------------------------------------------------------------------------- */
+/* fit, :70-94 + _compute_bandwidth :22-37 + weighted_std :39-68.  Sums in float64 (torch reduces the
+ * float32 tensors with a vectorised cascade; the two agree to float32 rounding).                     */
+ORACLE_EXPORT int oracle_kde_fit(const float* X, const float* w, int64_t n, int32_t d, int32_t rule, float* weights, float* bw)
+{
+    if (!X || !weights || !bw || n < 1 || d < 1 || d > GLABC_MAX_DIM) return GLABC_ERR_INVALID;
+    if (w) {
+        double sw = 0.0;
+        for (int64_t j = 0; j < n; ++j) sw += (double)w[j];
+        const float swf = (float)sw;
+        for (int64_t j = 0; j < n; ++j) weights[j] = w[j] / swf; /* :83 */
+    } else {
+        const float u = 1.0f / (float)n; /* :80 */
+        for (int64_t j = 0; j < n; ++j) weights[j] = u;
+    }
+    const double h = rule == GLABC_BW_SILVERMAN ? pow((double)n * (d + 2) / 4., -1. / (d + 4)) : pow((double)n, -1. / (d + 4));
+    double s2 = 0.0, sw2 = 0.0; /* weighted_std: w = weights / weights.sum() once more, :53 */
+    for (int64_t j = 0; j < n; ++j) s2 += (double)weights[j];
+    const float s2f = (float)s2;
+    for (int64_t j = 0; j < n; ++j) { const float wj = weights[j] / s2f; sw2 += (double)(wj * wj); }
+    float corr = 1.0f - (float)sw2; /* :64 */
+    if (corr < 1e-10f) corr = 1e-10f;
+    for (int i = 0; i < d; ++i) {
+        double mean = 0.0, var = 0.0;
+        for (int64_t j = 0; j < n; ++j) mean += (double)((weights[j] / s2f) * X[j * d + i]); /* :56 */
+        const float mf = (float)mean;
+        for (int64_t j = 0; j < n; ++j) {
+            const float df = X[j * d + i] - mf;
+            var += (double)((weights[j] / s2f) * (df * df)); /* :59-61 */
+        }
+        bw[i] = (float)h * sqrtf((float)var / corr); /* :36,65-68 */
+    }
+    return GLABC_OK;
+}
+
+/* log_prob, :96-128: max-shifted logsumexp over the n training points */
+static float kde_log_prob_one(const float* X, const float* weights, const float* bw, int64_t n, int d, const float* x)
+{
+    float slog = 0.0f; /* torch.log(bandwidth).sum() */
+    {
+        float t[GLABC_MAX_DIM];
+        for (int i = 0; i < d; ++i) t[i] = logf(bw[i]);
+        slog = torch_sum_f32(t, d);
+    }
+    const float c = 0.5f * (float)d * logf((float)(2 * M_PI)); /* 0.5*dim*log(tensor(2*pi)), float32 */
+    float mx = -INFINITY;
+    for (int pass = 0; pass < 2; ++pass) {
+        double acc = 0.0;
+        for (int64_t j = 0; j < n; ++j) {
+            float t[GLABC_MAX_DIM];
+            for (int i = 0; i < d; ++i) {
+                const float df = (x[i] - X[j * d + i]) / bw[i];
+                t[i] = df * df;
+            }
+            float lk = -0.5f * torch_sum_f32(t, d);
+            lk = lk - c;
+            lk = lk - slog;
+            const float v = lk + logf(weights[j] + 1e-10f);
+            if (pass == 0) { if (v > mx) mx = v; }
+            else acc += (double)expf(v - mx);
+        }
+        if (pass == 1) return mx + logf((float)acc);
+        if (isinf(mx)) mx = 0.0f; /* torch.logsumexp: infinite max is replaced by 0 */
+    }
+    return 0.0f;
+}
+
+ORACLE_EXPORT int oracle_kde_log_prob(const float* X, const float* weights, const float* bw, int64_t n, int32_t d,
+                                      const float* x, int64_t m, float* out)
+{
+    if (!X || !weights || !bw || !x || !out || n < 1 || d < 1 || d > GLABC_MAX_DIM) return GLABC_ERR_INVALID;
+    for (int64_t q = 0; q < m; ++q) out[q] = kde_log_prob_one(X, weights, bw, n, d, x + q * d);
+    return GLABC_OK;
+}
+
+/* -------------------------------------------------------------------------------------------
+ * AGLMCMC — AGLMCMC.py:84-272.  Draw order: init N[B,d], N[B,y]; per
+ * iteration U_b; global: U64 (+ at an adaptation: multinomial[4B], N[4B,d], N[B,y]); local: N[1,d],
+ * N[1,y], U_a.  Deviations from the reference, both on purpose: the chain is returned
+ * for any num_ite and row 0 holds the initial theta.
+ * ------------------------------------------------------------------------------------------- */
+enum { SLOT_INIT = 0x30000, SLOT_AD_SAMPLE = 0x40000000, SLOT_AD_SIM = 0x48000000 };
+
+typedef struct {
+    const glabc_model_t* m; const glabc_dist_t* lp; const glabc_dist_t* ip; const glabc_run_t* r; const glabc_aglmcmc_t* ag;
+} ag_job;
+
+static int cmp_float(const void* a, const void* b)
+{
+    const float x = *(const float*)a, y = *(const float*)b;
+    return (x > y) - (x < y);
+}
+
+/* log N(dis; 0, eps) with eps given as a float32 value: DiagGaussian(1, 0, log(tensor([eps]))).log_prob, Mixture.py:47-53 */
+static float log_kernel_dis_eps(float dis, float eps)
+{
+    const float ls = logf(eps);
+    const float r = (dis - 0.0f) / expf(ls);
+    return half_log_2pi_f32(1) - (ls + 0.5f * (r * r));
+}
+
+/* the block of one chain after its proposals theta0 / lq0 are known: simulate, discrepancy, weights */
+static void ag_finish_block(const glabc_model_t* m, int B, const float* th0, const float* lq0, const float* eps_s,
+                            float* x0, float* dis0, float* w0, int nan_to_zero)
+{
+    const int d = m->theta_dim, yd = m->y_dim;
+    int all_nan = 1;
+    for (int b = 0; b < B; ++b) {
+        model_simulate(m, th0 + b * d, eps_s + b * yd, x0 + b * yd);
+        dis0[b] = model_discrepancy(m, x0 + b * yd);
+        if (!isnan(dis0[b])) all_nan = 0;
+    }
+    if (all_nan) for (int b = 0; b < B; ++b) dis0[b] = 1000000 - 5; /* AGLMCMC.py:100-101 (scalar torch.all) */
+    for (int b = 0; b < B; ++b) {
+        const float lw = (model_prior(m, th0 + b * d) + model_log_kernel_dis(m, dis0[b])) - lq0[b];
+        float w = expf(lw);
+        if ((nan_to_zero && isnan(w)) || all_nan) w = 0.0f; /* :110-112 (initial block) / :248-249 */
+        w0[b] = w;
+    }
+}
+
+static void run_aglmcmc_range(void* vctx, int64_t c_begin, int64_t c_end)
+{
+    const ag_job* job = (const ag_job*)vctx;
+    const glabc_model_t* m = job->m;
+    const glabc_dist_t* lp = job->lp;
+    const glabc_dist_t* ip = job->ip;
+    const glabc_run_t* r = job->r;
+    const glabc_aglmcmc_t* ag = job->ag;
+    const int K = r->n_candidates, S = ag->step_size, B = K * S;
+    const int d = m->theta_dim, yd = m->y_dim;
+    const int slots = GLABC_TAPE_GLOBAL_SLOTS(d, yd);
+    const int ns = GLABC_NSTATS(d);
+    const float gf = r->global_frequency;
+    const int64_t C = r->n_chains;
+    const int replay = r->rng_mode == GLABC_RNG_REPLAY;
+    float* th0 = (float*)malloc(sizeof(float) * B * d);
+    float* x0 = (float*)malloc(sizeof(float) * B * yd);
+    float* lq0 = (float*)malloc(sizeof(float) * B);
+    float* w0 = (float*)malloc(sizeof(float) * B);
+    float* dis0 = (float*)malloc(sizeof(float) * B);
+    float* eps_s = (float*)malloc(sizeof(float) * B * yd);
+    float* kX = (float*)malloc(sizeof(float) * B * d);
+    float* kw = (float*)malloc(sizeof(float) * B);
+    float* kwn = (float*)malloc(sizeof(float) * B);
+    float* smp = (float*)malloc(sizeof(float) * 4 * B * d);
+    float* sorted = (float*)malloc(sizeof(float) * B);
+    double* cdf = (double*)malloc(sizeof(double) * B);
+
+    for (int64_t c = c_begin; c < c_end; ++c) {
+        const uint64_t gid = (uint64_t)(r->chain_id_base + c);
+        float theta[GLABC_MAX_DIM], y[GLABC_MAX_DIM], st[GLABC_NSTATS(GLABC_MAX_DIM)], kbw[GLABC_MAX_DIM] = {0};
+        memcpy(theta, r->theta + c * d, sizeof(float) * d);
+        memcpy(y, r->y + c * yd, sizeof(float) * yd);
+        memset(st, 0, sizeof(st));
+        if (r->write_row0 && r->trace_layout != GLABC_TRACE_NONE)
+            memcpy(r->trace + trace_index(r, c, r->step_base, d), theta, sizeof(float) * d);
+
+        /* ---- initial block, AGLMCMC.py:84-112 ---- */
+        for (int b = 0; b < B; ++b) {
+            float eps_p[GLABC_MAX_DIM];
+            if (replay) {
+                for (int k = 0; k < d; ++k) eps_p[k] = ag->init_p[(size_t)(b * d + k) * C + c];
+                for (int k = 0; k < yd; ++k) eps_s[b * yd + k] = ag->init_s[(size_t)(b * yd + k) * C + c];
+            } else {
+                const int G = (d + yd + 3) / 4;
+                float z[2 * GLABC_MAX_DIM + 4];
+                native_normals(r->seed, gid, 0u, SLOT_INIT + (uint32_t)(b * G), d + yd, z);
+                memcpy(eps_p, z, sizeof(float) * d);
+                memcpy(eps_s + b * yd, z + d, sizeof(float) * yd);
+            }
+            lq0[b] = diag_gauss_forward(eps_p, ip->a, ip->b, ip->c, d, th0 + b * d);
+        }
+        ag_finish_block(m, B, th0, lq0, eps_s, x0, dis0, w0, 1);
+        if (ag->init_w) for (int b = 0; b < B; ++b) ag->init_w[(size_t)b * C + c] = w0[b];
+        int kk = 0, num_train = 0, kn = 0;
+        float hat_eps = 1000000.0f;
+
+        for (int64_t s = 0; s < r->n_steps; ++s) {
+            const int64_t i = r->step_base + 1 + s;
+            const float* t = replay ? r->tape32 + (size_t)s * slots * C + c : NULL;
+            float u_b, u_a = 0.0f, zl[2 * GLABC_MAX_DIM + 4];
+            double u64 = 0.0;
+            if (t) {
+                u_b = t[0];
+                u64 = r->tape64[(size_t)s * C + c];
+            } else {
+                native_step_draws(r->seed, gid, (uint32_t)i, d + yd, zl, &u_b, &u_a);
+                uint32_t w[4]; /* a global move does not use the step block's normals: their bits give the 53-bit uniform */
+                philox_block(r->seed, gid, (uint32_t)i, SLOT_STEP, w);
+                u64 = (double)(((uint64_t)(w[0] >> 8) << 29) | ((uint64_t)(w[2] >> 8) << 5) | (uint64_t)(w[1] >> 27)) * 0x1p-53;
+            }
+            const int is_global = u_b < gf; /* AGLMCMC.py:125-126 */
+            int changed = 0, ind = -1;
+            float dbg[4] = {0, 0, 0, 0}, prev[GLABC_MAX_DIM];
+            memcpy(prev, theta, sizeof(float) * d);
+            if (is_global) {
+                /* :137-149 */
+                const float lq_old = num_train == 0 ? diag_gauss_log_prob(theta, ip->a, ip->b, ip->c, d)
+                                                    : kde_log_prob_one(kX, kwn, kbw, kn, d, theta);
+                const float w_old = expf((model_prior(m, theta) + model_log_kernel(m, y)) - lq_old);
+                float w[GLABC_MAX_K + 1];
+                w[0] = w_old;
+                for (int j = 0; j < K; ++j) w[j + 1] = w0[kk * K + j];
+                const float Ssum = torch_sum_f32(w, K + 1); /* :155 */
+                for (int j = 0; j <= K; ++j) w[j] = w[j] / Ssum;
+                ind = weight_sampling(w, K + 1, u64); /* :158 */
+                if (ind > 0) { /* :161-163 */
+                    memcpy(theta, th0 + (kk * K + ind - 1) * d, sizeof(float) * d);
+                    memcpy(y, x0 + (kk * K + ind - 1) * yd, sizeof(float) * yd);
+                }
+                for (int k = 0; k < d; ++k) changed |= theta[k] != prev[k];
+                dbg[1] = lq_old; dbg[2] = w_old; dbg[3] = Ssum;
+                kk += 1;
+                if (kk == S) { /* ---- adaptation, :170-249 ---- */
+                    kk = 0;
+                    if (hat_eps > ag->hat_eps_T) { /* :174-196 */
+                        int num_a = 0, nv = 0;
+                        for (int b = 0; b < B; ++b) {
+                            if (dis0[b] < hat_eps) ++num_a;
+                            if (!isnan(dis0[b])) sorted[nv++] = dis0[b];
+                        }
+                        if (nv > 0) {
+                            float q = (ag->alpha * (float)num_a) / (float)nv;
+                            q = q < 0.0f ? 0.0f : (q > 1.0f ? 1.0f : q);
+                            qsort(sorted, (size_t)nv, sizeof(float), cmp_float);
+                            /* torch.quantile, linear interpolation: rank = q*(n-1); lerp(below, above, frac) */
+                            const float rank = q * (float)(nv - 1);
+                            const float lo = floorf(rank);
+                            const float fr = rank - lo;
+                            const float a = sorted[(int)lo], bq = sorted[(int)ceilf(rank)];
+                            hat_eps = fr < 0.5f ? a + fr * (bq - a) : bq - (bq - a) * (1.0f - fr);
+                        }
+                        if (!(hat_eps > ag->hat_eps_T)) hat_eps = ag->hat_eps_T; /* torch.max, :196 */
+                    }
+                    kn = 0;
+                    for (int b = 0; b < B; ++b) { /* :199-208 */
+                        const float tw = expf((model_prior(m, th0 + b * d) + log_kernel_dis_eps(dis0[b], hat_eps)) - lq0[b]);
+                        if (tw > 0.0f) {
+                            memcpy(kX + kn * d, th0 + b * d, sizeof(float) * d);
+                            kw[kn++] = tw;
+                        }
+                    }
+                    {   /* :211 Train_weight / torch.sum(Train_weight) */
+                        double sw = 0.0;
+                        for (int j = 0; j < kn; ++j) sw += (double)kw[j];
+                        for (int j = 0; j < kn; ++j) kw[j] = kw[j] / (float)sw;
+                    }
+                    oracle_kde_fit(kX, kw, kn, d, ag->kde_rule, kwn, kbw); /* :214-215 */
+                    const int rr = num_train;
+                    num_train += 1;
+                    /* KDE.sample(4B), kernel_density.py:130-152; keep the first B with prior > log(1e-10), :220-226 */
+                    if (!replay) {
+                        double run = 0.0;
+                        for (int j = 0; j < kn; ++j) { run += (double)kwn[j]; cdf[j] = run; }
+                    }
+                    int nb = 0;
+                    for (int q = 0; q < 4 * B && nb < B; ++q) {
+                        int idx;
+                        float nz[GLABC_MAX_DIM + 4];
+                        if (replay) {
+                            idx = ag->ad_idx[((size_t)rr * 4 * B + q) * C + c];
+                            for (int k = 0; k < d; ++k) nz[k] = ag->ad_noise[((size_t)rr * 4 * B * d + (size_t)q * d + k) * C + c];
+                        } else {
+                            uint32_t w[4];
+                            philox_block(r->seed, gid, (uint32_t)rr, SLOT_AD_SAMPLE + 2u * (uint32_t)q, w);
+                            const double u = (double)w[0] * 0x1p-32;
+                            idx = kn - 1;
+                            for (int j = 0; j < kn; ++j) if (u < cdf[j]) { idx = j; break; }
+                            native_normals(r->seed, gid, (uint32_t)rr, SLOT_AD_SAMPLE + 2u * (uint32_t)q + 1u, d, nz);
+                        }
+                        float cand[GLABC_MAX_DIM];
+                        for (int k = 0; k < d; ++k) cand[k] = kX[idx * d + k] + nz[k] * kbw[k];
+                        if (model_prior(m, cand) > (float)log(1e-10)) memcpy(th0 + (nb++) * d, cand, sizeof(float) * d);
+                    }
+                    /* fewer than B valid samples: the reference raises IndexError; the remaining rows keep their old
+                     * candidates here (cannot happen for the fused Gaussian priors short of |theta| > 6 sigma x 4B) */
+                    oracle_kde_log_prob(kX, kwn, kbw, kn, d, th0, B, lq0); /* :229 */
+                    for (int b = 0; b < B; ++b)
+                        for (int k = 0; k < yd; ++k) {
+                            if (replay) eps_s[b * yd + k] = ag->ad_sim[((size_t)rr * B * yd + (size_t)b * yd + k) * C + c];
+                        }
+                    if (!replay)
+                        for (int b = 0; b < B; ++b) native_normals(r->seed, gid, (uint32_t)rr, SLOT_AD_SIM + (uint32_t)b, yd, eps_s + b * yd);
+                    ag_finish_block(m, B, th0, lq0, eps_s, x0, dis0, w0, 0); /* :232-249 */
+                    if (ag->ad_rec && rr < ag->dump_rounds) {
+                        float* g = ag->ad_rec + (size_t)rr * GLABC_AG_REC_SLOTS * C + c;
+                        g[0] = hat_eps; g[(size_t)1 * C] = (float)kn;
+                        for (int k = 0; k < d && k < 4; ++k) g[(size_t)(2 + k) * C] = kbw[k];
+                    }
+                    if (ag->ad_blk && rr < ag->dump_rounds)
+                        for (int b = 0; b < B; ++b) {
+                            float* g = ag->ad_blk + ((size_t)rr * B + b) * (d + 3) * C + c;
+                            for (int k = 0; k < d; ++k) g[(size_t)k * C] = th0[b * d + k];
+                            g[(size_t)d * C] = lq0[b]; g[(size_t)(d + 1) * C] = w0[b]; g[(size_t)(d + 2) * C] = dis0[b];
+                        }
+                }
+            } else { /* local RW-MH, :251-271 */
+                float eps_p[GLABC_MAX_DIM], eps_l[GLABC_MAX_DIM], z[GLABC_MAX_DIM], theta_p[GLABC_MAX_DIM], y_p[GLABC_MAX_DIM];
+                if (t) {
+                    for (int k = 0; k < d; ++k) eps_p[k] = t[(size_t)(1 + k) * C];
+                    for (int k = 0; k < yd; ++k) eps_l[k] = t[(size_t)(1 + d + k) * C];
+                    u_a = t[(size_t)(1 + d + yd) * C];
+                } else {
+                    memcpy(eps_p, zl, sizeof(float) * d);
+                    memcpy(eps_l, zl + d, sizeof(float) * yd);
+                }
+                (void)diag_gauss_forward(eps_p, lp->a, lp->b, lp->c, d, z);
+                for (int k = 0; k < d; ++k) theta_p[k] = z[k] + theta[k];
+                model_simulate(m, theta_p, eps_l, y_p);
+                const float prior_p = model_prior(m, theta_p), kern_p = model_log_kernel(m, y_p);
+                float log_acc = prior_p + kern_p;
+                log_acc = log_acc - model_prior(m, theta);
+                log_acc = log_acc - model_log_kernel(m, y);
+                if (logf(u_a) < log_acc) {
+                    memcpy(theta, theta_p, sizeof(float) * d);
+                    memcpy(y, y_p, sizeof(float) * yd);
+                    changed = 1;
+                }
+                dbg[1] = prior_p; dbg[2] = kern_p; dbg[3] = log_acc;
+            }
+            dbg[0] = (float)(is_global | (changed << 1) | ((is_global ? ind + 1 : 0) << 8));
+            stats_update(st, d, theta, prev);
+            st[GLABC_STAT_GLOBAL_STEPS] += (float)is_global;
+            st[is_global ? GLABC_STAT_ACC_GLOBAL : GLABC_STAT_ACC_LOCAL] += (float)changed;
+            if (r->trace_layout != GLABC_TRACE_NONE)
+                memcpy(r->trace + trace_index(r, c, i, d), theta, sizeof(float) * d);
+            if (r->debug) {
+                float* g = r->debug + (size_t)s * GLABC_DEBUG_SLOTS * C + c;
+                for (int k = 0; k < 4; ++k) g[(size_t)k * C] = dbg[k];
+            }
+        }
+        memcpy(r->theta + c * d, theta, sizeof(float) * d);
+        memcpy(r->y + c * yd, y, sizeof(float) * yd);
+        if (r->stats)
+            for (int k = 0; k < ns; ++k) r->stats[c * ns + k] += st[k];
+    }
+    free(th0); free(x0); free(lq0); free(w0); free(dis0); free(eps_s); free(kX); free(kw); free(kwn); free(smp);
+    free(sorted); free(cdf);
+}
+
+ORACLE_EXPORT int oracle_run_aglmcmc(const glabc_model_t* m, const glabc_dist_t* lp, const glabc_dist_t* ip,
+                                     const glabc_run_t* r, const glabc_aglmcmc_t* ag)
+{
+    int rc = check_common(m, r);
+    if (rc) return rc;
+    if (!ag || !lp || !ip || lp->kind != GLABC_DIST_DIAG_GAUSSIAN || ip->kind != GLABC_DIST_DIAG_GAUSSIAN) return GLABC_ERR_UNSUPPORTED;
+    const int K = r->n_candidates;
+    if (K < 1 || K > GLABC_MAX_K || ag->step_size < 1 || K * ag->step_size > GLABC_AG_MAX_BLOCK) return GLABC_ERR_INVALID;
+    if (r->rng_mode == GLABC_RNG_REPLAY && (!r->tape64 || !ag->init_p || !ag->init_s || !ag->ad_idx || !ag->ad_noise || !ag->ad_sim))
+        return GLABC_ERR_INVALID;
+    ag_job job = {m, lp, ip, r, ag};
+    parallel_chains(run_aglmcmc_range, &job, r->n_chains);
+    return GLABC_OK;
+}
+
+/* -------------------------------------------------------------------------------------------
  * esjd — ESJD.py:17-24: det(D^T D / (N-1))^(1/d) in float32 (d <= 3 closed-form determinant;
  * torch.det goes through an LU factorisation, so agreement is to rounding, not bit-exact).
  * ------------------------------------------------------------------------------------------- */

@@ -546,6 +546,214 @@ def golden_mala(cases, out_path):
 
 
 # ----------------------------------------------------------------------------------------------
+# AGLMCMC (AGLMCMC.py:84-272) + KernelDensity (kernel_density.py): block of K*S pre-generated
+# candidates, iSIR against the block, every S global moves: eps-hat quantile update, weighted KDE
+# refit, new block sampled from the KDE.
+# ----------------------------------------------------------------------------------------------
+def golden_aglmcmc(cases, out_path):
+    import csv
+    import tempfile
+    import glabcmcmc.distribution as distribution
+    import glabcmcmc.kernel_density as kdmod
+    from Mixture import Mixture_set
+    mod = sys.modules["glabcmcmc.AGLMCMC"]
+    blobs = {}
+    for ci, case in enumerate(cases):
+        C, K, S, T, gf = case["chains"], case["K"], case["S"], case["T"], case["gf"]
+        alpha, eps_T = case["alpha"], case["hat_eps_T"]
+        B, d = K * S, 2
+        model = Mixture_set(case["epsilon"])
+        lp = distribution.DiagGaussian(2, loc=torch.tensor(case["lp_loc"]).view(1, 2),
+                                       log_scale=torch.log(torch.tensor(case["lp_sigma"])))
+        ip = distribution.DiagGaussian(2, torch.tensor(case["ip_loc"]), torch.tensor(case["ip_log_scale"]))
+        R = (T - 1) // S + 1
+        tape32 = np.zeros((T - 1, 2 + 2 * d, C), np.float32)      # U_b, N_p[d], N_s[d], U_a (local moves)
+        tape64 = np.zeros((T - 1, C), np.float64)                 # resampling uniform (global moves)
+        init_p, init_s = np.zeros((B * d, C), np.float32), np.zeros((B * d, C), np.float32)
+        ad_idx = np.zeros((R, 4 * B, C), np.int32)
+        ad_noise = np.zeros((R, 4 * B * d, C), np.float32)
+        ad_sim = np.zeros((R, B * d, C), np.float32)
+        n_adapt = np.zeros(C, np.int64)
+        # per adaptation: hat_eps, n_train, bw[2], then the new block: theta0 [B,2], lq0 [B], w0 [B], dis0 [B]
+        ad_rec = np.zeros((R, 4, C), np.float64)
+        ad_theta = np.zeros((R, B, d, C), np.float32)
+        ad_lq, ad_w, ad_dis = (np.zeros((R, B, C), np.float32) for _ in range(3))
+        init_w = np.zeros((B, C), np.float32)
+        trace = np.zeros((T, C, 2), np.float32)
+        theta0s, y0s = np.zeros((C, 2), np.float32), np.zeros((C, 2), np.float32)
+        # flags, (lq_old | prior'), (w_old | kernel'), (S | log_acc)
+        rec = np.zeros((T - 1, 4, C), np.float64)
+        for c in range(C):
+            torch.manual_seed(7000 + 1000 * ci + c)
+            np.random.seed(7000 + 1000 * ci + c)
+            theta0 = torch.tensor(case["theta0"])
+            y0 = model.generate_samples(theta0)
+            log = []
+            pm = CallLog(model, "model", ("generate_samples", "prior_log_prob", "calculate_log_kernel"), log)
+            plp = CallLog(lp, "lp", ("sample",), log)
+            pip = CallLog(ip, "ip", ("forward", "log_prob"), log)
+            orig_dis = model.calculate_log_kernel_dis
+
+            def logged_dis(dis, epsilon=None, _o=orig_dis):
+                out = _o(dis, epsilon)
+                log.append(("model", "kernel_dis", (dis.detach().numpy().copy(), None if epsilon is None else float(epsilon),
+                                                    out.detach().numpy().copy())))
+                return out
+
+            model.calculate_log_kernel_dis = logged_dis
+
+            class LoggedKDE(kdmod.KernelDensity):
+                def fit(self, X, weights=None):
+                    r = super().fit(X, weights)
+                    log.append(("kde", "fit", (self.X.numpy().copy(), self.weights.numpy().copy(), self.bandwidth.numpy().copy())))
+                    return r
+
+                def log_prob(self, x):
+                    out = super().log_prob(x)
+                    log.append(("kde", "log_prob", out.numpy().copy()))
+                    return out
+
+                def sample(self, n_samples=1, return_log_prob=False):
+                    out = super().sample(n_samples, return_log_prob)
+                    log.append(("kde", "sample", out.numpy().copy()))
+                    return out
+
+            orig_kde = mod.KernelDensity
+            mod.KernelDensity = LoggedKDE
+            fd, path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            try:
+                with Tape() as tape, quiet():
+                    mod.AGLMCMC(pm, T, theta0, y0, plp, pip, path, gf, S, K, alpha, eps_T, device="cpu")
+            finally:
+                mod.KernelDensity = orig_kde
+                del model.calculate_log_kernel_dis
+            with open(path) as f:
+                rows = [[np.float32(v) for v in r] for r in csv.reader(f)]
+            os.unlink(path)
+            chain = np.asarray(rows, np.float32)
+            assert chain.shape == (T, 2), chain.shape
+            ev = tape.events
+            theta0s[c], y0s[c] = theta0.numpy(), y0.view(-1).numpy()
+            trace[:, c] = chain
+            # ---- initial block (AGLMCMC.py:84-112)
+            assert ev[0][0] == "N32" and ev[0][1].shape == (B, 2) and ev[1][0] == "N32" and ev[1][1].shape == (B, 2)
+            init_p[:, c], init_s[:, c] = ev[0][1].reshape(-1), ev[1][1].reshape(-1)
+            names = [x[:2] for x in log[:4]]
+            assert names == [("ip", "forward"), ("model", "generate_samples"), ("model", "kernel_dis"), ("model", "prior_log_prob")], names
+            lw0 = (log[3][2] + log[2][2][2]) - log[0][2][1]
+            w0 = torch.exp(torch.from_numpy(lw0))
+            w0[torch.isnan(w0)] = 0.0
+            init_w[:, c] = w0.numpy()
+            ei, li, kk, r, trained = 2, 4, 0, 0, False
+            for s in range(T - 1):
+                assert ev[ei][0] == "U32"
+                u_b = np.float32(ev[ei][1][0])
+                ei += 1
+                tape32[s, 0, c] = u_b
+                is_global = bool(u_b < np.float32(gf))
+                changed = bool(np.any(trace[s + 1, c] != trace[s, c])) if s > 0 else bool(np.any(trace[1, c] != theta0s[c]))
+                if is_global:
+                    names = [x[:2] for x in log[li:li + 3]]
+                    want = [("kde", "log_prob") if trained else ("ip", "log_prob"), ("model", "calculate_log_kernel"), ("model", "prior_log_prob")]
+                    assert names == want, (names, want)
+                    lq_old, k_old, p_old = [v[2] for v in log[li:li + 3]]
+                    li += 3
+                    w_old = torch.exp(torch.from_numpy((p_old + k_old) - lq_old))
+                    wt = torch.cat((w_old, w0[kk * K:(kk + 1) * K]))
+                    Ssum = torch.sum(wt)
+                    wn = (wt / Ssum).tolist()
+                    assert ev[ei][0] == "U64"
+                    u64 = float(ev[ei][1])
+                    tape64[s, c] = u64
+                    ei += 1
+                    ind, sw = None, 0
+                    for j in range(K + 1):
+                        sw += wn[j]
+                        if u64 < sw:
+                            ind = j
+                            break
+                    rec[s, 0, c] = 1 | (int(changed) << 1) | ((0 if ind is None else ind + 1) << 8)
+                    rec[s, 1, c], rec[s, 2, c], rec[s, 3, c] = lq_old[0], w_old[0].item(), Ssum.item()
+                    kk += 1
+                    if kk == S:
+                        kk = 0
+                        names = [x[:2] for x in log[li:li + 10]]
+                        assert names == [("model", "kernel_dis"), ("model", "prior_log_prob"), ("kde", "fit"), ("kde", "sample"),
+                                         ("model", "prior_log_prob"), ("kde", "log_prob"), ("model", "generate_samples"),
+                                         ("model", "kernel_dis"), ("model", "prior_log_prob")] + names[9:], names
+                        (_, hat_eps, _), _, (kX, kw, kbw), smp, prior4, lq_new, _, (dis_new, _, like_new), prior_new = [v[2] for v in log[li:li + 9]]
+                        li += 9
+                        assert ev[ei][0] == "MULTI" and ev[ei + 1][0] == "N32" and ev[ei + 2][0] == "N32"
+                        ad_idx[r, :, c] = ev[ei][1].reshape(-1)
+                        ad_noise[r, :, c] = ev[ei + 1][1].reshape(-1)
+                        ad_sim[r, :, c] = ev[ei + 2][1].reshape(-1)
+                        ei += 3
+                        ad_rec[r, 0, c], ad_rec[r, 1, c], ad_rec[r, 2:4, c] = hat_eps, kX.shape[0], kbw
+                        # the new block: theta0 = the first B prior-valid KDE samples (AGLMCMC.py:220-226)
+                        w0 = torch.exp(torch.from_numpy((prior_new + like_new) - lq_new))
+                        ad_lq[r, :, c], ad_w[r, :, c], ad_dis[r, :, c] = lq_new, w0.numpy(), dis_new
+                        ad_theta[r, :, :, c] = smp[prior4 > np.log(10 ** (-10))][:B]
+                        trained = True
+                        r += 1
+                else:
+                    e1, e2, e3 = ev[ei:ei + 3]
+                    ei += 3
+                    assert e1[0] == "N32" and e2[0] == "N32" and e3[0] == "U32" and e1[1].shape == (1, 2)
+                    tape32[s, 1:3, c], tape32[s, 3:5, c], tape32[s, 5, c] = e1[1].reshape(-1), e2[1].reshape(-1), e3[1][0]
+                    names = [x[:2] for x in log[li:li + 6]]
+                    assert names == [("lp", "sample"), ("model", "generate_samples"), ("model", "prior_log_prob"),
+                                     ("model", "calculate_log_kernel"), ("model", "prior_log_prob"),
+                                     ("model", "calculate_log_kernel")], names
+                    _, _, pr_p, k_p, pr_o, k_o = [v[2] for v in log[li:li + 6]]
+                    li += 6
+                    acc = np.float32(pr_p[0]) + np.float32(k_p[0])
+                    acc = acc - np.float32(pr_o[0])
+                    acc = acc - np.float32(k_o[0])
+                    rec[s, 0, c] = int(changed) << 1
+                    rec[s, 1, c], rec[s, 2, c], rec[s, 3, c] = pr_p[0], k_p[0], acc
+            n_adapt[c] = r
+            assert ei == len(ev) and li == len(log), (ei, len(ev), li, len(log))
+        blob = dict(tape32=tape32, tape64=tape64, init_p=init_p, init_s=init_s, init_w=init_w, ad_idx=ad_idx, ad_noise=ad_noise,
+                    ad_sim=ad_sim, ad_rec=ad_rec, ad_theta=ad_theta, ad_lq=ad_lq, ad_w=ad_w, ad_dis=ad_dis, n_adapt=n_adapt, trace=trace,
+                    theta0=theta0s, y0=y0s, rec=rec, gf=np.float64(gf), T=np.int64(T), K=np.int64(K), S=np.int64(S),
+                    alpha=np.float64(alpha), hat_eps_T=np.float64(eps_T))
+        blob.update(model_params(model))
+        blob.update(dist_params(lp, "lp"))
+        blob.update(dist_params(ip, "ip"))
+        for k, v in blob.items():
+            blobs[f"case{ci}/{k}"] = v
+        fl = rec[:, 0].astype(np.int64)
+        print(f"aglmcmc case {ci}: gf={gf} K={K} S={S} move rate {np.mean((fl >> 1) & 1):.4f} adaptations {n_adapt.tolist()} "
+              f"hat_eps path {ad_rec[:4, 0, 0].round(4).tolist()} .. {ad_rec[max(0, n_adapt[0] - 1), 0, 0]:.4f}")
+    blobs["n_cases"] = np.int64(len(cases))
+    np.savez_compressed(out_path, **blobs)
+
+
+def golden_kde(out_path):
+    """KernelDensity on its own (kernel_density.py:22-177): fit / log_prob for weighted and unweighted sets"""
+    import glabcmcmc.kernel_density as kdmod
+    g = torch.Generator().manual_seed(11)
+    blobs = {}
+    for i, (n, m, dd, weighted, rule) in enumerate([(300, 64, 2, True, "silverman"), (1000, 200, 2, False, "scott"),
+                                                    (57, 33, 3, True, "silverman"), (5, 8, 1, True, "scott"),
+                                                    (400, 50, 2, True, "silverman")]):
+        X = torch.randn(n, dd, generator=g) * torch.tensor([1.0, 0.3, 2.0][:dd]) + torch.tensor([0.5, -1.0, 0.0][:dd])
+        w = torch.rand(n, generator=g) ** 3 if weighted else None
+        x = torch.randn(m, dd, generator=g) * 2.5
+        if i == 4:
+            x[:10] += 40.0         # far queries: every kernel underflows without the max shift
+        kde = kdmod.KernelDensity(bandwidth=rule, device="cpu").fit(X, w)
+        blobs[f"kde{i}/X"], blobs[f"kde{i}/x"] = X.numpy(), x.numpy()
+        blobs[f"kde{i}/w"] = w.numpy() if weighted else np.zeros(0, np.float32)
+        blobs[f"kde{i}/weights"], blobs[f"kde{i}/bw"] = kde.weights.numpy(), kde.bandwidth.numpy()
+        blobs[f"kde{i}/log_prob"] = kde.log_prob(x).numpy()
+        blobs[f"kde{i}/rule"] = np.int64(0 if rule == "silverman" else 1)
+    blobs["n_cases"] = np.int64(5)
+    np.savez_compressed(out_path, **blobs)
+
+
+# ----------------------------------------------------------------------------------------------
 # esjd (ESJD.py) and the distribution classes (distribution.py) — small deterministic fixtures
 # ----------------------------------------------------------------------------------------------
 def golden_misc(out_path):
@@ -594,6 +802,18 @@ def main():
     ]
     if not only or "mala" in only:
         golden_mala(mcases, os.path.join(HERE, "glmala.npz"))
+    abase = dict(chains=4, epsilon=0.05, theta0=[0.0, 0.0], lp_loc=[0.0, 0.0], lp_sigma=[0.35, 0.35],
+                 ip_loc=[0.0, 0.0], ip_log_scale=[0.0, 0.0], alpha=0.8, hat_eps_T=0.2)
+    acases = [
+        dict(abase, chains=6, gf=1.0, K=5, S=40, T=700),                        # Mixture.py:74-75 with a shorter period
+        dict(abase, gf=0.7, K=3, S=25, T=600),                                  # local moves between global ones
+        dict(abase, gf=1.0, K=8, S=16, T=300, alpha=0.5, hat_eps_T=0.5, epsilon=0.2, theta0=[1.2, -1.4],
+             ip_loc=[0.5, -0.25], ip_log_scale=[0.4, 0.2]),
+    ]
+    if not only or "aglmcmc" in only:
+        golden_aglmcmc(acases, os.path.join(HERE, "aglmcmc.npz"))
+    if not only or "kde" in only:
+        golden_kde(os.path.join(HERE, "kde.npz"))
     if only:
         return
     base = dict(chains=4, epsilon=0.05, theta0=[0.0, 0.0], lp_loc=[0.0, 0.0], lp_sigma=[0.35, 0.35],

@@ -136,3 +136,40 @@ def check_mala_free_running(flags, trace, case, strict_all=False):
     for c in np.flatnonzero(clean):
         assert np.allclose(trace[:, c], case["trace"][:, c], rtol=0, atol=2e-2), c
     return clean
+
+
+def rel_max(a, b, floor=1e-30):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float((np.abs(a - b) / np.maximum(np.abs(b), floor)).max()) if a.size else 0.0
+
+
+def check_aglmcmc(case, trace, dbg, ad_rec, ad_blk, init_w, tol=1e-5):
+    """AGLMCMC replay outputs (oracle or kernel) vs the reference's records: decisions and resample indices
+    bit-exact; eps-hat, bandwidths, block log-densities / log-weights, per-step densities within `tol` relative;
+    traces to float32 rounding (the KDE bandwidth carries ~1e-7 relative summation-order noise into theta0)."""
+    rec = case["rec"]
+    fl_o, fl_r = dbg[:, 0].astype(np.int64), rec[:, 0].astype(np.int64)
+    assert np.array_equal(fl_o, fl_r), f"{(fl_o != fl_r).sum()} decisions differ"
+    assert np.allclose(trace[1:], case["trace"][1:], rtol=2e-6, atol=2e-6)   # row 0: the reference leaves zeros (B-10)
+    assert np.array_equal(trace[0], case["theta0"])
+    assert rel_max(init_w, case["init_w"], 1e-30) < 20 * tol                   # exp of O(100) log-weights
+    n = int(case["n_adapt"].min())
+    d = case["theta0"].shape[1]
+    assert rel_max(ad_rec[:n, 0], case["ad_rec"][:n, 0]) < tol                 # eps-hat (torch.quantile)
+    assert np.array_equal(ad_rec[:n, 1], case["ad_rec"][:n, 1].astype(np.float32))  # KDE training points kept
+    assert rel_max(ad_rec[:n, 2:2 + d], case["ad_rec"][:n, 2:2 + d]) < tol     # bandwidth
+    assert np.allclose(ad_blk[:n, :, 0:d], case["ad_theta"][:n], rtol=2e-6, atol=2e-6)
+    assert rel_max(ad_blk[:n, :, d], case["ad_lq"][:n], 1.0) < tol             # KDE.log_prob of the block
+    assert np.allclose(ad_blk[:n, :, d + 2], case["ad_dis"][:n], rtol=1e-5, atol=2e-6)
+    wr, wo = case["ad_w"][:n], ad_blk[:n, :, d + 1]
+    pos = wr > 1e-30
+    assert np.array_equal(wo > 0, wr > 0)
+    lw_err = np.abs(np.log(wo[pos].astype(np.float64)) - np.log(wr[pos].astype(np.float64)))
+    assert lw_err.max() < 3e-4, lw_err.max()                                    # log-weights are O(10..100): 1e-5 relative
+    g = (fl_r & 1) == 1
+    assert rel_max(dbg[:, 1][g], rec[:, 1][g], 1.0) < tol                      # proposal log-density of the current state
+    m = g & (rec[:, 2] > 1e-30)
+    assert np.abs(np.log(dbg[:, 2][m].astype(np.float64)) - np.log(rec[:, 2][m])).max() < 3e-4
+    loc = ~g
+    for k in (1, 2, 3):
+        assert rel_max(dbg[:, k][loc], rec[:, k][loc], 1e-2) < 20 * tol

@@ -93,3 +93,43 @@ def test_glmala_replay(ci):
                rng_mode=abi.RNG_REPLAY, tape32=tf["tape32"], tape64=tf["tape64"], tape_grad0=tf["tape_grad0"], aux=tf["aux"],
                state64=tf["state64"], debug64=dbg1, K=K, num_grad=num, tau=tf["tau"], trace_layout=abi.TRACE_NONE)
     check_mala_debug(dbg1[0], tf["rec"], K)
+
+
+def test_kde_golden():
+    """kernel_density.py:22-128 — fit (weights, Silverman / Scott bandwidth from the weighted std) and log_prob,
+    weighted and unweighted, d = 1..3, including queries so far out that every kernel underflows without the shift"""
+    import os
+    from helpers import GOLDEN, rel_max
+    z = np.load(os.path.join(GOLDEN, "kde.npz"))
+    for i in range(int(z["n_cases"])):
+        X, x, w = z[f"kde{i}/X"], z[f"kde{i}/x"], z[f"kde{i}/w"]
+        weights, bw = oracle.kde_fit(X, w if w.size else None, int(z[f"kde{i}/rule"]))
+        assert rel_max(weights, z[f"kde{i}/weights"]) < 1e-6 and rel_max(bw, z[f"kde{i}/bw"]) < 1e-6
+        lp = oracle.kde_log_prob(X, weights, bw, x)
+        assert np.isfinite(lp).all() and rel_max(lp, z[f"kde{i}/log_prob"], 1.0) < 1e-5
+
+
+def run_aglmcmc_oracle(case, **over):
+    T, Cn, K, S = int(case["T"]), case["theta0"].shape[0], int(case["K"]), int(case["S"])
+    B, R = K * S, case["ad_idx"].shape[0]
+    theta, y = case["theta0"].copy(), case["y0"].copy()
+    out = dict(dbg=np.zeros((T - 1, abi.DEBUG_SLOTS, Cn), np.float32), ad_rec=np.zeros((R, abi.AG_REC_SLOTS, Cn), np.float32),
+               ad_blk=np.zeros((R, B, case["theta0"].shape[1] + 3, Cn), np.float32), init_w=np.zeros((B, Cn), np.float32))
+    ag = oracle.aglmcmc_params(S=S, alpha=float(case["alpha"]), hat_eps_T=float(case["hat_eps_T"]), init_p=case["init_p"],
+                               init_s=case["init_s"], ad_idx=case["ad_idx"], ad_noise=case["ad_noise"], ad_sim=case["ad_sim"],
+                               ad_rec=out["ad_rec"], ad_blk=out["ad_blk"], init_w=out["init_w"])
+    out["trace"] = oracle.run("aglmcmc", model_pod(case), gauss_pod(case, "lp"), gauss_pod(case, "ip"), theta=theta, y=y,
+                              n_steps=T - 1, gf=float(case["gf"]), rng_mode=abi.RNG_REPLAY, tape32=case["tape32"],
+                              tape64=case["tape64"], debug=out["dbg"], K=K, ag=ag, **over)
+    return out
+
+
+@pytest.mark.parametrize("ci", range(3))
+def test_aglmcmc_replay(ci):
+    """AGLMCMC.py:84-272 on the reference's own draws (incl. its torch.multinomial indices): every branch / move /
+    resample index bit-exact through 16-18 adaptations per chain; eps-hat, KDE bandwidths, block log-densities and
+    weights to 1e-5"""
+    from helpers import check_aglmcmc
+    case = load_cases("aglmcmc.npz")[ci]
+    o = run_aglmcmc_oracle(case)
+    check_aglmcmc(case, o["trace"], o["dbg"], o["ad_rec"], o["ad_blk"], o["init_w"])
