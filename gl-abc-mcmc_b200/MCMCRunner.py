@@ -38,3 +38,12 @@ class MCMCRunner:
                       tau=tau, num_grad=num_grad, filelocation=self._path(output_file),
                       global_frequency=global_frequency, Importance_Proposal=importance_proposal,
                       batch_size=batch_size, **kw)
+
+    def run_aglmcmc(self, num_iterations, initial_theta, initial_y, global_frequency, local_proposal, Initial_ISIR_prop,
+                    batch_size, step_size, alpha, hat_eps_T, output_file="glmcmc_results.csv", **kw):
+        """reference MCMCRunner.py:55-76"""
+        from .AGLMCMC import AGLMCMC
+        return AGLMCMC(ABCset=self.abc_set, num_ite=num_iterations, Initial_theta=initial_theta, Initial_y=initial_y,
+                       Local_Proposal=local_proposal, Initial_ISIR_prop=Initial_ISIR_prop, filelocation=self._path(output_file),
+                       global_frequency=global_frequency, step_size=step_size, batch_size=batch_size, alpha=alpha,
+                       hat_eps_T=hat_eps_T, **kw)

@@ -5,10 +5,12 @@ the repo root: `import glabc_b200` (or `importlib.import_module("gl-abc-mcmc_b20
 Export list mirrors the reference's `glabcmcmc/__init__.py:1-14`.
 """
 from . import _abi  # noqa: F401
+from .AGLMCMC import AGLMCMC  # noqa: F401
 from .distribution import DiagGaussian, Gamma, GaussianMixture, Uniform  # noqa: F401
 from .ESJD import esjd  # noqa: F401
 from .GLMALA import GLMALA  # noqa: F401
 from .GLMCMC import GLMCMC  # noqa: F401
 from .GlobalMCMC import GlobalMCMC  # noqa: F401
+from .kernel_density import KernelDensity  # noqa: F401
 from .MCMCRunner import MCMCRunner  # noqa: F401
 from .models import AbsNormalModel, Mixture_set  # noqa: F401

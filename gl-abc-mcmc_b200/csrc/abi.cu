@@ -8,6 +8,7 @@
 #include <string>
 
 #include "launch.cuh"
+#include "step_aglmcmc.cuh"
 #include "step_mala.cuh"
 
 using namespace glabc;
@@ -25,6 +26,13 @@ struct glabc_ctx {
     size_t state_cap = 0;
     double* d_state64 = nullptr;  // GLMALA carried float64 state
     size_t state64_cap = 0;
+    // AGLMCMC block / KDE workspace (one allocation), KDE sampling scratch of the public entry points
+    void* ag_mem = nullptr;
+    size_t ag_bytes = 0;
+    AgWorkspace ag{};
+    int ag_dim = 0;
+    double* kde_cdf = nullptr;
+    size_t kde_cdf_cap = 0;
     float* d_trace[2] = {nullptr, nullptr};
     size_t trace_cap = 0;
     cudaStream_t s_compute = nullptr, s_copy = nullptr;
@@ -100,6 +108,8 @@ int glabc_ctx_destroy(glabc_ctx* ctx)
     cudaSetDevice(ctx->device);
     if (ctx->d_state) cudaFree(ctx->d_state);
     if (ctx->d_state64) cudaFree(ctx->d_state64);
+    if (ctx->ag_mem) cudaFree(ctx->ag_mem);
+    if (ctx->kde_cdf) cudaFree(ctx->kde_cdf);
     for (int b = 0; b < 2; ++b) {
         if (ctx->d_trace[b]) cudaFree(ctx->d_trace[b]);
         if (ctx->ev_done[b]) cudaEventDestroy(ctx->ev_done[b]);
@@ -508,6 +518,166 @@ static int run_host(glabc_ctx* ctx, SamplerKind kind, const glabc_run_t* run, in
     if (n_s64) CUDA_TRY(ctx, cudaMemcpyAsync(run->state64, ctx->d_state64, n_s64 * sizeof(double), cudaMemcpyDeviceToHost, sc));
     CUDA_TRY(ctx, cudaStreamSynchronize(sc));
     CUDA_TRY(ctx, cudaStreamSynchronize(sx));
+    return GLABC_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// AGLMCMC: workspace + entry point
+// ---------------------------------------------------------------------------------------------
+static int ensure_ag_workspace(glabc_ctx* ctx, int64_t C, int32_t B, int d, bool keep)
+{
+    if (keep) {
+        if (!ctx->ag_mem || ctx->ag.C != C || ctx->ag.B != B || ctx->ag_dim != d)
+            return fail(ctx, GLABC_ERR_INVALID, "glabc_run_aglmcmc: init = 0 but the context holds no workspace for %lld chains x block %d "
+                                                "(start the run with init = 1)", (long long)C, B);
+        return GLABC_OK;
+    }
+    const size_t cb = size_t(C) * size_t(B);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
+    const size_t o_bt = take(cb * d * 4), o_bx = take(cb * d * 4), o_bw = take(cb * 4), o_bl = take(cb * 4), o_bd = take(cb * 4);
+    const size_t o_kx = take(cb * d * 4), o_kw = take(cb * 4), o_kn = take(cb * 4), o_kl = take(cb * 4), o_kb = take(size_t(C) * d * 4);
+    const size_t o_smp = take(cb * 4 * d * 4), o_cdf = take(cb * 8);
+    const size_t o_i0 = take(size_t(C) * 4), o_i1 = take(size_t(C) * 4), o_i2 = take(size_t(C) * 4), o_i3 = take(size_t(C) * 4),
+                 o_i4 = take(size_t(C) * 4), o_i5 = take(size_t(C) * 4), o_f0 = take(size_t(C) * 4), o_f1 = take(size_t(C) * 4);
+    if (off > ctx->ag_bytes) {
+        if (ctx->ag_mem) cudaFree(ctx->ag_mem);
+        ctx->ag_mem = nullptr;
+        ctx->ag_bytes = 0;
+        CUDA_TRY(ctx, cudaMalloc(&ctx->ag_mem, off));
+        ctx->ag_bytes = off;
+    }
+    char* m = static_cast<char*>(ctx->ag_mem);
+    AgWorkspace& W = ctx->ag;
+    W.blk_theta = reinterpret_cast<float*>(m + o_bt); W.blk_x = reinterpret_cast<float*>(m + o_bx);
+    W.blk_w = reinterpret_cast<float*>(m + o_bw); W.blk_lq = reinterpret_cast<float*>(m + o_bl);
+    W.blk_dis = reinterpret_cast<float*>(m + o_bd);
+    W.kde_X = reinterpret_cast<float*>(m + o_kx); W.kde_w = reinterpret_cast<float*>(m + o_kw);
+    W.kde_wn = reinterpret_cast<float*>(m + o_kn); W.kde_lw = reinterpret_cast<float*>(m + o_kl);
+    W.kde_bw = reinterpret_cast<float*>(m + o_kb); W.smp = reinterpret_cast<float*>(m + o_smp);
+    W.cdf = reinterpret_cast<double*>(m + o_cdf);
+    W.kde_n = reinterpret_cast<int32_t*>(m + o_i0); W.kk = reinterpret_cast<int32_t*>(m + o_i1);
+    W.n_adapt = reinterpret_cast<int32_t*>(m + o_i2); W.pending = reinterpret_cast<int32_t*>(m + o_i3);
+    W.lq_valid = reinterpret_cast<int32_t*>(m + o_i4); W.next_step = reinterpret_cast<uint32_t*>(m + o_i5);
+    W.hat_eps = reinterpret_cast<float*>(m + o_f0); W.lq_cur = reinterpret_cast<float*>(m + o_f1);
+    W.C = C;
+    W.B = B;
+    ctx->ag_dim = d;
+    return GLABC_OK;
+}
+
+extern "C" int glabc_run_aglmcmc(glabc_ctx* ctx, const glabc_run_t* run, const glabc_aglmcmc_t* ag)
+{
+    if (!ctx) return GLABC_ERR_INVALID;
+    if (!ctx->has_model) return fail(ctx, GLABC_ERR_INVALID, "no model bound: call glabc_model_set first");
+    if (!run || !ag) return fail(ctx, GLABC_ERR_INVALID, "null run / aglmcmc description");
+    if (!ctx->has_dist[GLABC_SLOT_LOCAL] || !ctx->has_dist[GLABC_SLOT_IMPORTANCE])
+        return fail(ctx, GLABC_ERR_INVALID, "run_aglmcmc needs the LOCAL and IMPORTANCE (Initial_ISIR_prop) proposal slots bound");
+    const int d = ctx->model.theta_dim;
+    const glabc_dist_t& lp = ctx->dist[GLABC_SLOT_LOCAL];
+    const glabc_dist_t& ip = ctx->dist[GLABC_SLOT_IMPORTANCE];
+    if (lp.dim != d || ip.dim != d) return fail(ctx, GLABC_ERR_INVALID, "proposal dim does not match theta_dim %d", d);
+    if (run->n_candidates < 1 || run->n_candidates > GLABC_MAX_K)
+        return fail(ctx, GLABC_ERR_INVALID, "n_candidates (batch_size) must be in 1..%d", GLABC_MAX_K);
+    if (ag->step_size < 1 || int64_t(ag->step_size) * run->n_candidates > GLABC_AG_MAX_BLOCK)
+        return fail(ctx, GLABC_ERR_INVALID, "batch_size * step_size must be in 1..%d", GLABC_AG_MAX_BLOCK);
+    if (ag->kde_rule != GLABC_BW_SILVERMAN && ag->kde_rule != GLABC_BW_SCOTT) return fail(ctx, GLABC_ERR_INVALID, "bad kde_rule");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    RunParams R;
+    int block = 0;
+    int st = make_run_params(ctx, run, d, GLABC_TAPE_GLOBAL_SLOTS(d, d), &R, &block);
+    if (st) return st;
+    if (run->block_threads == 0) block = 128;
+    if (block > 128) return fail(ctx, GLABC_ERR_INVALID, "run_aglmcmc: block_threads at most 128");
+    const bool replay = run->rng_mode == GLABC_RNG_REPLAY;
+    if (replay && (!run->tape64 || !ag->ad_idx || !ag->ad_noise || !ag->ad_sim || ag->tape_rounds < 1 ||
+                   (ag->init && (!ag->init_p || !ag->init_s))))
+        return fail(ctx, GLABC_ERR_INVALID, "replay of run_aglmcmc needs tape64, init_p/init_s and the adaptation tapes");
+    if (R.n_chains == 0) return GLABC_OK;
+    const int32_t B = ag->step_size * run->n_candidates;
+    st = ensure_ag_workspace(ctx, R.n_chains, B, d, !ag->init);
+    if (st) return st;
+    AgConsts K{};
+    K.model = make_model(ctx->model);
+    K.lp = make_gauss(lp.a, lp.b, lp.c, d);
+    K.ip = make_gauss(ip.a, ip.b, ip.c, d);
+    K.S = ag->step_size;
+    K.alpha = ag->alpha;
+    K.hat_eps_T = ag->hat_eps_T;
+    K.log_prior_floor = static_cast<float>(std::log(1e-10));
+    AgTapes T{ag->init_p, ag->init_s, ag->ad_noise, ag->ad_sim, ag->ad_idx, ag->ad_rec, ag->ad_blk, ag->init_w, ag->tape_rounds,
+              ag->dump_rounds};
+    CUDA_TRY(ctx, launch_aglmcmc(K, ctx->ag, T, R, d, ag->init, ag->kde_rule, run->arith_mode == GLABC_ARITH_STRICT, replay,
+                                 run->trace_layout, block, static_cast<cudaStream_t>(run->stream)));
+    return GLABC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// KernelDensity entry points
+// ---------------------------------------------------------------------------------------------
+static int check_kde(glabc_ctx* ctx, const char* who, const void* X, int64_t sets, int64_t cap, int32_t dim)
+{
+    if (!X) return fail(ctx, GLABC_ERR_INVALID, "%s: null X", who);
+    if (sets < 0 || cap < 1 || cap > INT32_MAX) return fail(ctx, GLABC_ERR_INVALID, "%s: bad sets / cap", who);
+    if (dim < 1 || dim > 4) return fail(ctx, GLABC_ERR_UNSUPPORTED, "%s: dim %d outside 1..4", who, dim);
+    return GLABC_OK;
+}
+
+extern "C" int glabc_kde_fit(glabc_ctx* ctx, const float* X, const float* w, const int32_t* n, int64_t sets, int64_t cap,
+                             int32_t dim, int32_t rule, float* weights_out, float* bw_out, void* stream)
+{
+    if (!ctx) return GLABC_ERR_INVALID;
+    int st = check_kde(ctx, "glabc_kde_fit", X, sets, cap, dim);
+    if (st) return st;
+    if (!weights_out || !bw_out) return fail(ctx, GLABC_ERR_INVALID, "glabc_kde_fit: null output");
+    if (rule != GLABC_BW_SILVERMAN && rule != GLABC_BW_SCOTT) return fail(ctx, GLABC_ERR_INVALID, "glabc_kde_fit: bad rule %d", rule);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, launch_kde_fit(X, w, n, nullptr, sets, cap, dim, rule, weights_out, nullptr, bw_out, static_cast<cudaStream_t>(stream)));
+    return GLABC_OK;
+}
+
+extern "C" int glabc_kde_log_prob(glabc_ctx* ctx, const float* X, const float* weights, const float* bw, const int32_t* n,
+                                  int64_t sets, int64_t cap, int32_t dim, const float* x, int64_t m, float* out, int32_t arith,
+                                  void* stream)
+{
+    if (!ctx) return GLABC_ERR_INVALID;
+    int st = check_kde(ctx, "glabc_kde_log_prob", X, sets, cap, dim);
+    if (st) return st;
+    if (!weights || !bw || !x || !out || m < 0) return fail(ctx, GLABC_ERR_INVALID, "glabc_kde_log_prob: null pointer / bad m");
+    if (arith != GLABC_ARITH_FAST && arith != GLABC_ARITH_STRICT) return fail(ctx, GLABC_ERR_INVALID, "bad arith_mode %d", arith);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    KdeSets S{X, weights, bw, n, nullptr, sets, cap};
+    CUDA_TRY(ctx, launch_kde_logprob(S, nullptr, dim, x, m, out, arith == GLABC_ARITH_STRICT, static_cast<cudaStream_t>(stream)));
+    return GLABC_OK;
+}
+
+extern "C" int glabc_kde_sample(glabc_ctx* ctx, const float* X, const float* weights, const float* bw, const int32_t* n,
+                                int64_t sets, int64_t cap, int32_t dim, int64_t m, uint64_t seed, const int32_t* idx_tape,
+                                const float* noise_tape, float* out, void* stream)
+{
+    if (!ctx) return GLABC_ERR_INVALID;
+    int st = check_kde(ctx, "glabc_kde_sample", X, sets, cap, dim);
+    if (st) return st;
+    if (!weights || !bw || !out || m < 0) return fail(ctx, GLABC_ERR_INVALID, "glabc_kde_sample: null pointer / bad m");
+    if ((idx_tape == nullptr) != (noise_tape == nullptr))
+        return fail(ctx, GLABC_ERR_INVALID, "glabc_kde_sample: idx_tape and noise_tape go together");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t cs = static_cast<cudaStream_t>(stream);
+    KdeSets S{X, weights, bw, n, nullptr, sets, cap};
+    if (!idx_tape) {
+        const size_t need = size_t(sets) * size_t(cap);
+        if (need > ctx->kde_cdf_cap) {
+            if (ctx->kde_cdf) cudaFree(ctx->kde_cdf);
+            ctx->kde_cdf = nullptr;
+            ctx->kde_cdf_cap = 0;
+            CUDA_TRY(ctx, cudaMalloc(&ctx->kde_cdf, need * sizeof(double)));
+            ctx->kde_cdf_cap = need;
+        }
+        CUDA_TRY(ctx, launch_kde_cdf(weights, n, nullptr, sets, cap, ctx->kde_cdf, cs));
+    }
+    const RoundKeys rk = expand_key(make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+    CUDA_TRY(ctx, launch_kde_sample(S, dim, ctx->kde_cdf, m, rk, 0, nullptr, idx_tape, noise_tape, m, m * dim, 1, 0, 0, 0, out, cs));
     return GLABC_OK;
 }
 

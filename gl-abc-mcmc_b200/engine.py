@@ -103,7 +103,8 @@ class Engine:
             rng_mode=_abi.RNG_NATIVE, arith=_abi.ARITH_FAST, trace_layout=_abi.TRACE_CHAIN_MAJOR, trace=None,
             trace_rows=None, trace_chains=None, trace_chain_off=0, trace_row_base=0, write_row0=True,
             stats=None, aux=None, tape32=None, tape64=None, debug=None, tape_dump=None, tape64_dump=None, K=0,
-            block_threads=0, num_grad=0, tau=0.0, state64=None, tape_grad0=None, tape_grad0_dump=None, debug64=None):
+            block_threads=0, num_grad=0, tau=0.0, state64=None, tape_grad0=None, tape_grad0_dump=None, debug64=None,
+            ag=None):
         """Enqueue `n_steps` transitions of every chain on the current stream (device tensors,
         state updated in place).  Returns the trace tensor (allocated here unless given)."""
         cn, d = theta.shape
@@ -128,9 +129,69 @@ class Engine:
                         tape_grad0=self._ptr(tape_grad0), tape_grad0_dump=self._ptr(tape_grad0_dump),
                         debug64=self._ptr(debug64),
                         stream=C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        if sampler == "aglmcmc":
+            if ag is None:
+                raise ValueError("run('aglmcmc') needs the glabc_aglmcmc_t description (Engine.aglmcmc_params)")
+            self.ctx.check(self.lib.glabc_run_aglmcmc(self.ctx.handle, C.byref(r), C.byref(ag)))
+            return trace
         fn = getattr(self.lib, "glabc_run_" + sampler)
         self.ctx.check(fn(self.ctx.handle, C.byref(r)))
         return trace
+
+    def aglmcmc_params(self, *, step_size, alpha, hat_eps_T, rule=_abi.BW_SILVERMAN, init=True, init_p=None, init_s=None,
+                       ad_idx=None, ad_noise=None, ad_sim=None, ad_rec=None, ad_blk=None, init_w=None):
+        """glabc_aglmcmc_t; the tensors (replay tapes / parity dumps) must stay alive until the run is enqueued"""
+        for t in (init_p, init_s, ad_idx, ad_noise, ad_sim, ad_rec, ad_blk, init_w):
+            if t is not None and (not t.is_cuda or not t.is_contiguous()):
+                raise ValueError("aglmcmc tapes / dumps must be contiguous CUDA tensors")
+        rounds = 0 if ad_idx is None else ad_idx.shape[0]
+        dump = min([t.shape[0] for t in (ad_rec, ad_blk) if t is not None], default=0)
+        return _abi.AglmcmcPOD(step_size=int(step_size), init=int(bool(init)), alpha=float(alpha), hat_eps_T=float(hat_eps_T),
+                               kde_rule=int(rule), tape_rounds=rounds, init_p=self._ptr(init_p), init_s=self._ptr(init_s),
+                               ad_idx=self._ptr(ad_idx), ad_noise=self._ptr(ad_noise), ad_sim=self._ptr(ad_sim),
+                               ad_rec=self._ptr(ad_rec), ad_blk=self._ptr(ad_blk), init_w=self._ptr(init_w), dump_rounds=dump)
+
+    # -- KernelDensity (kernel_density.py) ------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def kde_fit(self, X, w=None, n=None, rule=_abi.BW_SILVERMAN):
+        """X [sets, cap, d] (or [n, d]), w [sets, cap] or None, n [sets] int32 or None -> (weights, bandwidth)"""
+        single = X.dim() == 2
+        X3 = X.unsqueeze(0) if single else X
+        sets, cap, d = X3.shape
+        X3 = self._f32(X3)
+        w2 = None if w is None else self._f32(w).reshape(sets, cap)
+        weights = torch.empty(sets, cap, dtype=torch.float32, device=self.device)
+        bw = torch.empty(sets, d, dtype=torch.float32, device=self.device)
+        self.ctx.check(self.lib.glabc_kde_fit(self.ctx.handle, self._ptr(X3), self._ptr(w2), self._ptr(n), sets, cap, d, int(rule),
+                                              self._ptr(weights), self._ptr(bw), self._stream()))
+        return (weights[0], bw[0]) if single else (weights, bw)
+
+    def kde_log_prob(self, X, weights, bw, x, n=None, arith=_abi.ARITH_FAST):
+        single = X.dim() == 2
+        X3, w2, b2, x3 = (X.unsqueeze(0), weights.unsqueeze(0), bw.reshape(1, -1), x.unsqueeze(0)) if single else (X, weights, bw, x)
+        sets, cap, d = X3.shape
+        X3, w2, b2, x3 = self._f32(X3), self._f32(w2), self._f32(b2), self._f32(x3)
+        m = x3.shape[1]
+        out = torch.empty(sets, m, dtype=torch.float32, device=self.device)
+        self.ctx.check(self.lib.glabc_kde_log_prob(self.ctx.handle, self._ptr(X3), self._ptr(w2), self._ptr(b2), self._ptr(n), sets,
+                                                   cap, d, self._ptr(x3), m, self._ptr(out), int(arith), self._stream()))
+        return out[0] if single else out
+
+    def kde_sample(self, X, weights, bw, m, n=None, seed=0, idx_tape=None, noise_tape=None):
+        single = X.dim() == 2
+        X3, w2, b2 = (X.unsqueeze(0), weights.unsqueeze(0), bw.reshape(1, -1)) if single else (X, weights, bw)
+        sets, cap, d = X3.shape
+        X3, w2, b2 = self._f32(X3), self._f32(w2), self._f32(b2)
+        if idx_tape is not None:
+            idx_tape = idx_tape.to(self.device, torch.int32).reshape(sets, m).contiguous()
+            noise_tape = self._f32(noise_tape).reshape(sets, m, d)
+        out = torch.empty(sets, m, d, dtype=torch.float32, device=self.device)
+        self.ctx.check(self.lib.glabc_kde_sample(self.ctx.handle, self._ptr(X3), self._ptr(w2), self._ptr(b2), self._ptr(n), sets, cap,
+                                                 d, int(m), int(seed) & 0xFFFFFFFFFFFFFFFF, self._ptr(idx_tape),
+                                                 self._ptr(noise_tape), self._ptr(out), self._stream()))
+        return out[0] if single else out
 
     def run_host(self, sampler, *, theta, y, n_steps, gf, trace, step_base=0, chain_id_base=0, seed=0,
                  arith=_abi.ARITH_FAST, trace_layout=_abi.TRACE_TIME_MAJOR, write_row0=True, stats=None,
