@@ -29,6 +29,11 @@ SAMPLERS = {
     "glmcmc": dict(entry="isir", gf=0.9, K=5, alg_inst=703,
                    workload="README Mixture_set GLMCMC iSIR K=5, gf=0.9 (BASELINE configs[2], run_glmcmc)"),
     # GLMALA.py:150-200, gf=0.8, K=5, tau=0.3, num_grad=100: 0.2 * ~22,000 (400 CRN simulator draws) + 0.8 * 760
+    # AGLMCMC.py:124-272 with the example's settings (Mixture.py:74): gf=1, K=5, step 200, alpha 0.8, eps-hat_T 0.2.
+    # Dominant work: KDE.log_prob of each new block, B x n pairs per chain per adaptation = K * n ~ 5,000 pairs per
+    # chain-step at 7 thread-instructions per pair (kde.cuh) + ~100 for the step itself
+    "aglmcmc": dict(entry="aglmcmc", gf=1.0, K=5, alg_inst=35100, step_size=200, alpha=0.8, hat_eps_T=0.2,
+                    workload="README Mixture_set AGLMCMC K=5, gf=1, step 200, alpha 0.8, eps_hat_T 0.2 (BASELINE configs[4], run_aglmcmc)"),
     "glmala": dict(entry="mala", gf=0.8, K=5, alg_inst=5000, num_grad=100, tau=0.3,
                    workload="README Mixture_set GLMALA K=5, gf=0.8, tau=0.3, num_grad=100 (BASELINE configs[2], run_glmala)"),
 }
@@ -40,7 +45,8 @@ def parse():
     p.add_argument("--steps", type=int, default=200)
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="native", choices=["native", "reference"])
-    p.add_argument("--sampler", default="global", choices=sorted(SAMPLERS), help="which fused step kernel to time")
+    p.add_argument("--sampler", default="global", choices=sorted(SAMPLERS) + ["kde"], help="which fused step kernel to time")
+    p.add_argument("--kde-points", type=int, default=100000)
     p.add_argument("--chains", type=int, default=65536, help="chains per GPU (weak scaling)")
     p.add_argument("--iters", type=int, default=10000, help="num_ite per chain (trace rows)")
     p.add_argument("--layout", default="chain", choices=["chain", "time", "none"])
@@ -129,6 +135,10 @@ class CpuPort:
             aux[:, abi.AUX_LOCAL] = 1.0
         if self.spec["entry"] == "mala":
             extra = dict(num_grad=self.spec["num_grad"], tau=self.spec["tau"], state64=np.zeros((c, abi.STATE64_SLOTS)))
+        if self.spec["entry"] == "aglmcmc":
+            aux = None
+            extra = dict(ag=self.oracle.aglmcmc_params(S=self.spec["step_size"], alpha=self.spec["alpha"],
+                                                       hat_eps_T=self.spec["hat_eps_T"]))
         t0 = time.perf_counter()
         self.oracle.run(self.spec["entry"], *self.pods, theta=theta, y=y, n_steps=t, gf=self.spec["gf"], seed=0,
                         trace=trace, trace_layout=abi.TRACE_CHAIN_MAJOR, threads=self.threads, K=self.spec["K"], aux=aux,
@@ -178,6 +188,126 @@ def bench_reference(a, rank):
     print(json.dumps(line), flush=True)
 
 
+def bench_kde(a, rank, world, local_rank):
+    """--sampler kde: KernelDensity.fit + log_prob of 1e5 queries against 1e5 weighted training draws, d = 2
+    (BASELINE configs[4]: the pairwise Gaussian KDE of AGLMCMC at pooled size).  One step = fit + log_prob."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from glabc_b200 import _abi as abi
+    from glabc_b200.engine import get_engine
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    eng = get_engine()
+    info = eng.ctx.device_info()
+    n = m = a.kde_points
+    g = torch.Generator(device="cuda").manual_seed(77 + rank)
+    signs = torch.randint(0, 2, (n, 2), device="cuda", generator=g) * 2 - 1
+    X = (signs * (1.42518 + 0.2233 * torch.randn(n, 2, device="cuda", generator=g))).contiguous()   # SURVEY.md App. D posterior
+    w = torch.rand(n, device="cuda", generator=g) ** 2
+    x = (X[torch.randperm(n, device="cuda", generator=g)[:m]] + 0.1 * torch.randn(m, 2, device="cuda", generator=g)).contiguous()
+
+    def one_step():
+        weights, bw = eng.kde_fit(X, w)
+        return eng.kde_log_prob(X, weights, bw, x)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for _ in range(a.warmup):
+        one_step()
+    barrier()
+    n_idle = len(sampler.rows)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        out = one_step()
+    e1.record()
+    barrier()
+    sampler.rows = sampler.rows[max(0, n_idle - 1):]
+    clocks = sampler.stop()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    pairs = float(n) * m * world
+    value = pairs * a.steps / (total_ms * 1e-3)
+    weights, bw = eng.kde_fit(X, w)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kms = []
+    for _ in range(min(a.steps, 20)):
+        k0.record()
+        eng.kde_log_prob(X, weights, bw, x)
+        k1.record()
+        torch.cuda.synchronize()
+        kms.append(k0.elapsed_time(k1))
+    kms = sum(kms) / len(kms)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    sm_max_mhz = float(peaks.get("sm_max_mhz", clocks.get("sm_max_mhz") or 1965.0))
+    inst_peak = info["sm_count"] * 128 * sm_max_mhz * 1e6 / 1e9
+    rate = float(n) * m / (kms * 1e-3)
+    inst_ach = rate * 7 / 1e9
+    mufu_peak = info["sm_count"] * 16 * sm_max_mhz * 1e6 / 1e9
+    roofline = {"bound": "alu-issue", "achieved": inst_ach, "peak": inst_peak, "unit": "Gthread-inst/s", "frac": inst_ach / inst_peak,
+                "traffic": None, "kernel_ms": kms, "kernel_pairs_per_sec": rate,
+                "note": "7 algorithmic thread-instructions per (query, point) pair at d = 2: 2 sub, 2 fma, 1 fma, 1 ex2, 1 add",
+                "mufu": {"achieved": rate / 1e9, "peak": mufu_peak, "unit": "Gex2/s", "frac": rate / 1e9 / mufu_peak}}
+    line = {"metric": "kde_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": "KernelDensity.fit + log_prob, weighted Silverman KDE (BASELINE configs[4] / SURVEY 6)",
+                                            "train_points": n, "queries": m, "dim": 2, "arith": "fast",
+                                            "l2": "inputs 2.4 MB, L2-resident by design; compute-bound pair loop"},
+            "clocks": clocks, "gpu_launches": 2 * a.steps, "roofline": roofline}
+    if not a.no_e2e:
+        hX, hw, hx = X.cpu().pin_memory(), w.cpu().pin_memory(), x.cpu().pin_memory()
+        hout = torch.empty(m).pin_memory()
+
+        def e2e():
+            dX, dw, dx = hX.cuda(non_blocking=True), hw.cuda(non_blocking=True), hx.cuda(non_blocking=True)
+            ww, bb = eng.kde_fit(dX, dw)
+            hout.copy_(eng.kde_log_prob(dX, ww, bb, dx), non_blocking=True)
+            torch.cuda.synchronize()
+        e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(max(1, min(a.steps, 5))):
+            e2e()
+        barrier()
+        dt = (time.perf_counter() - t0) / max(1, min(a.steps, 5))
+        line["e2e"] = {"value": pairs / dt, "unit": "pairs/s", "h2d_bytes_per_step": (hX.numel() + hw.numel() + hx.numel()) * 4,
+                       "d2h_bytes_per_step": m * 4}
+    if rank == 0 and not a.no_cpu:
+        from oracle import oracle
+        Xn, wn = X.cpu().numpy(), w.cpu().numpy()
+        wo, bo = oracle.kde_fit(Xn, wn)
+        q = 64
+        t0 = time.perf_counter()
+        oracle.kde_log_prob(Xn, wo, bo, x[:q].cpu().numpy())
+        dt = time.perf_counter() - t0
+        q = int(max(64, min(m, q * a.cpu_seconds / max(dt, 1e-3))))
+        t0 = time.perf_counter()
+        ref = oracle.kde_log_prob(Xn, wo, bo, x[:q].cpu().numpy())
+        dt = time.perf_counter() - t0
+        err = float(np.abs(out[:q].cpu().numpy() - ref).max())
+        line["cpu_baseline"] = {"value": q * n / dt, "unit": "pairs/s", "cores": 1, "kind": "port",
+                                "sample": f"{q} queries x {n} training points, {dt:.1f} s; max |gpu - cpu| = {err:.2e}"}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
 def workload_config(a):
     spec = SAMPLERS[a.sampler]
     return {"workload": spec["workload"], "chains_per_gpu": a.chains,
@@ -193,6 +323,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.sampler == "kde":
+        if a.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "--sampler kde has no reference arm; see cpu_baseline of the native line"}))
+            return
+        bench_kde(a, rank, world, local_rank)
+        return
     if a.impl == "reference":
         bench_reference(a, rank)
         return
@@ -229,7 +365,7 @@ def main():
     theta, y = theta0.clone(), y0.clone()
     stats = torch.zeros(C, abi.nstats(d), device="cuda")
     aux0 = aux = None
-    if K:
+    if K and entry != "aglmcmc":
         aux0 = torch.zeros(C, abi.AUX_SLOTS, device="cuda")
         aux0[:, abi.AUX_LOCAL] = 1.0
         aux = aux0.clone()
@@ -239,10 +375,13 @@ def main():
         s64 = torch.zeros(C, abi.STATE64_SLOTS, device="cuda", dtype=torch.float64)
         extra = dict(num_grad=spec["num_grad"], tau=spec["tau"], state64=s64)
 
+    if entry == "aglmcmc":
+        extra = dict(ag=eng.aglmcmc_params(step_size=spec["step_size"], alpha=spec["alpha"], hat_eps_T=spec["hat_eps_T"]))
+
     def reset_state():
         theta.copy_(theta0)
         y.copy_(y0)
-        if K:
+        if aux is not None:
             aux.copy_(aux0)
         if s64 is not None:
             s64.zero_()
@@ -298,6 +437,8 @@ def main():
     kms = sum(kernel_ms) / len(kernel_ms)
     kernel_rate = C * (T - 1) / (kms * 1e-3)
 
+    # kernels of ours per pass: one fused step kernel, or for AGLMCMC the init pair + per round (step + 8 adaptation kernels)
+    launches_per_pass = 1 if entry != "aglmcmc" else 3 + ((T - 1) // spec["step_size"] + 2) * 9
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -320,7 +461,7 @@ def main():
     line = {"metric": "abc_mcmc_chain_steps_per_sec", "value": value, "unit": "chain-steps/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": total_ms / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a),
-            "clocks": clocks, "gpu_launches": a.steps, "roofline": roofline}
+            "clocks": clocks, "gpu_launches": a.steps * launches_per_pass, "roofline": roofline}
     if summary is not None:
         desc = sharding.describe(summary.cpu(), d)
         line["esjd"] = {"mean_per_chain": desc["mean_esjd"], "aggregate_esjd_per_sec": desc["mean_esjd"] * value,
@@ -328,7 +469,32 @@ def main():
 
     # end-to-end through the reference-facing call with HOST buffers (pinned): H2D state, kernels in time
     # chunks, D2H of the full trace overlapped, D2H state + stats — every step.
-    if not a.no_e2e:
+    if not a.no_e2e and entry == "aglmcmc":
+        # no host-buffer C entry for AGLMCMC yet: e2e through the public Python call with host tensors in and the
+        # chains copied back (run_chains: H2D of theta / y, device run, D2H of the full trace)
+        import glabc_b200 as g
+        e_steps = max(1, min(a.steps, 3))
+        del trace
+        torch.cuda.empty_cache()
+        h_theta0, h_y0 = theta0.cpu(), y0.cpu()
+
+        def e2e_step(i):
+            out = g.AGLMCMC(model, T, h_theta0, h_y0, lp, gp, None, gf, spec["step_size"], K, spec["alpha"], spec["hat_eps_T"],
+                            num_chains=C, seed=i, chain_id_base=chain_base, trace="time", verbose=False)
+            return out.cpu()
+        e2e_step(0)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e_steps):
+            res = e2e_step(1 + i)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        line["e2e"] = {"value": steps_per_pass * e_steps / float(dt.item()), "unit": "chain-steps/s",
+                       "h2d_bytes_per_step": (h_theta0.numel() + h_y0.numel()) * 4, "d2h_bytes_per_step": res.numel() * 4,
+                       "steps": e_steps, "note": "glabc_b200.AGLMCMC(...) with host tensors in, full [T,C,2] trace copied to the host"}
+    elif not a.no_e2e:
         e_steps = max(1, min(a.steps, 3))
         h_theta0, h_y0 = theta0.cpu().pin_memory(), y0.cpu().pin_memory()
         h_theta, h_y = torch.empty_like(h_theta0).pin_memory(), torch.empty_like(h_y0).pin_memory()
