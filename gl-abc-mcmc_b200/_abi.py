@@ -89,6 +89,13 @@ class AglmcmcPOD(C.Structure):
                 ("dump_rounds", C.c_int32), ("reserved", C.c_int32)]
 
 
+class FlowPOD(C.Structure):
+    """glabc_flow_t"""
+    _fields_ = [("n_blocks", C.c_int32), ("hidden", C.c_int32), ("dim", C.c_int32), ("reserved", C.c_int32),
+                ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p), ("w3", C.c_void_p),
+                ("b3", C.c_void_p), ("base_loc", C.c_float * 2), ("base_log_scale", C.c_float * 2)]
+
+
 BW_SILVERMAN, BW_SCOTT = 0, 1
 AG_REC_SLOTS = 8
 AG_MAX_BLOCK = 4096
@@ -129,6 +136,9 @@ _SIGNATURES = {
                                      C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     "glabc_kde_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                    C.c_int32, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "glabc_flow_set": (C.c_int, [C.c_void_p, C.POINTER(FlowPOD), C.c_size_t, C.c_void_p]),
+    "glabc_flow_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "glabc_flow_log_prob": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "glabc_esjd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "glabc_philox_kat": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
 }

@@ -8,6 +8,7 @@
 #include <string>
 
 #include "launch.cuh"
+#include "flow.cuh"
 #include "step_aglmcmc.cuh"
 #include "step_mala.cuh"
 
@@ -33,6 +34,11 @@ struct glabc_ctx {
     int ag_dim = 0;
     double* kde_cdf = nullptr;
     size_t kde_cdf_cap = 0;
+    // RealNVP flow weights (device copies owned by the context)
+    float* flow_mem = nullptr;
+    size_t flow_floats = 0;
+    FlowDev flow{};
+    bool has_flow = false;
     float* d_trace[2] = {nullptr, nullptr};
     size_t trace_cap = 0;
     cudaStream_t s_compute = nullptr, s_copy = nullptr;
@@ -110,6 +116,7 @@ int glabc_ctx_destroy(glabc_ctx* ctx)
     if (ctx->d_state64) cudaFree(ctx->d_state64);
     if (ctx->ag_mem) cudaFree(ctx->ag_mem);
     if (ctx->kde_cdf) cudaFree(ctx->kde_cdf);
+    if (ctx->flow_mem) cudaFree(ctx->flow_mem);
     for (int b = 0; b < 2; ++b) {
         if (ctx->d_trace[b]) cudaFree(ctx->d_trace[b]);
         if (ctx->ev_done[b]) cudaEventDestroy(ctx->ev_done[b]);
@@ -679,6 +686,76 @@ extern "C" int glabc_kde_sample(glabc_ctx* ctx, const float* X, const float* wei
     const RoundKeys rk = expand_key(make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
     CUDA_TRY(ctx, launch_kde_sample(S, dim, ctx->kde_cdf, m, rk, 0, nullptr, idx_tape, noise_tape, m, m * dim, 1, 0, 0, 0, out, cs));
     return GLABC_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// RealNVP flow (GLMCMC-NFs importance proposal)
+// ---------------------------------------------------------------------------------------------
+extern "C" int glabc_flow_set(glabc_ctx* ctx, const glabc_flow_t* f, size_t nbytes, void* stream)
+{
+    if (!ctx) return GLABC_ERR_INVALID;
+    if (!f || nbytes != sizeof(glabc_flow_t))
+        return fail(ctx, GLABC_ERR_INVALID, "glabc_flow_set: struct size %zu, expected %zu (ABI mismatch)", nbytes, sizeof(glabc_flow_t));
+    if (f->hidden != kFlowHidden || f->dim != 2)
+        return fail(ctx, GLABC_ERR_UNSUPPORTED, "the fused flow is MLP([1,128,128,2]) couplings on a 2-d theta (GLMCMC_NFs.py:56)");
+    if (f->n_blocks < 1 || f->n_blocks > 1024) return fail(ctx, GLABC_ERR_INVALID, "glabc_flow_set: n_blocks out of range");
+    if (!f->w1 || !f->b1 || !f->w2 || !f->b2 || !f->w3 || !f->b3) return fail(ctx, GLABC_ERR_INVALID, "glabc_flow_set: null weights");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t cs = static_cast<cudaStream_t>(stream);
+    const size_t L = size_t(f->n_blocks), H = kFlowHidden;
+    const size_t need = L * (H + H + H * H + H + 2 * H + 4);
+    if (need > ctx->flow_floats) {
+        if (ctx->flow_mem) cudaFree(ctx->flow_mem);
+        ctx->flow_mem = nullptr;
+        ctx->flow_floats = 0;
+        CUDA_TRY(ctx, cudaMalloc(&ctx->flow_mem, need * sizeof(float)));
+        ctx->flow_floats = need;
+    }
+    float* p = ctx->flow_mem;
+    float* w2p = p;              p += L * H * H;   // first: 16-byte (in fact 256-byte) aligned for cp.async.bulk
+    float* w1 = p;               p += L * H;
+    float* b1 = p;               p += L * H;
+    float* b2 = p;               p += L * H;
+    float* w3 = p;               p += L * 2 * H;
+    float* b3 = p;
+    CUDA_TRY(ctx, cudaMemcpyAsync(w1, f->w1, L * H * 4, cudaMemcpyDeviceToDevice, cs));
+    CUDA_TRY(ctx, cudaMemcpyAsync(b1, f->b1, L * H * 4, cudaMemcpyDeviceToDevice, cs));
+    CUDA_TRY(ctx, cudaMemcpyAsync(b2, f->b2, L * H * 4, cudaMemcpyDeviceToDevice, cs));
+    CUDA_TRY(ctx, cudaMemcpyAsync(w3, f->w3, L * 2 * H * 4, cudaMemcpyDeviceToDevice, cs));
+    CUDA_TRY(ctx, cudaMemcpyAsync(b3, f->b3, L * 2 * 4, cudaMemcpyDeviceToDevice, cs));
+    CUDA_TRY(ctx, launch_flow_pack(f->w2, w2p, f->n_blocks, cs));
+    FlowDev d{};
+    d.w1 = w1; d.b1 = b1; d.w2p = w2p; d.b2 = b2; d.w3 = w3; d.b3 = b3;
+    for (int i = 0; i < 2; ++i) {
+        d.base_loc[i] = f->base_loc[i];
+        d.base_log_scale[i] = f->base_log_scale[i];
+    }
+    d.n_blocks = f->n_blocks;
+    ctx->flow = d;
+    ctx->has_flow = true;
+    return GLABC_OK;
+}
+
+static int run_flow(glabc_ctx* ctx, bool sample, const float* in, int64_t n, float* theta, float* log_q, void* stream)
+{
+    if (!ctx) return GLABC_ERR_INVALID;
+    if (!ctx->has_flow) return fail(ctx, GLABC_ERR_INVALID, "no flow bound: call glabc_flow_set first");
+    if (ctx->cc < 100) return fail(ctx, GLABC_ERR_UNSUPPORTED, "the flow kernels need tcgen05 tensor cores (sm_100a); this device is sm_%d", ctx->cc);
+    if (!in || !log_q || (sample && !theta) || n < 0) return fail(ctx, GLABC_ERR_INVALID, "glabc_flow_%s: null pointer / bad n", sample ? "sample" : "log_prob");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, launch_flow(ctx->flow, sample, in, n, theta, log_q, ctx->sm_count, static_cast<cudaStream_t>(stream)));
+    return GLABC_OK;
+}
+
+extern "C" int glabc_flow_sample(glabc_ctx* ctx, const float* eps, int64_t n, float* theta, float* log_q, void* stream)
+{
+    return run_flow(ctx, true, eps, n, theta, log_q, stream);
+}
+
+extern "C" int glabc_flow_log_prob(glabc_ctx* ctx, const float* theta, int64_t n, float* log_q, void* stream)
+{
+    return run_flow(ctx, false, theta, n, nullptr, log_q, stream);
 }
 
 extern "C" {

@@ -250,6 +250,24 @@ typedef struct {
     int32_t reserved;
 } glabc_aglmcmc_t;
 
+/* ---- RealNVP importance proposal of GLMCMC-NFs (GLMCMC_NFs.py:51-61; normflows 1.7 pieces) ----
+ * n_blocks x [AffineCouplingBlock(MLP([1, hidden, hidden, 2])), Permute(2, 'swap')] over DiagGaussian(2).
+ * Weight pointers are DEVICE pointers in torch's nn.Linear layout ([out][in]); glabc_flow_set copies them.   */
+typedef struct {
+    int32_t n_blocks;            /* 32, GLMCMC_NFs.py:51                                                   */
+    int32_t hidden;              /* 128, GLMCMC_NFs.py:56                                                  */
+    int32_t dim;                 /* 2                                                                      */
+    int32_t reserved;
+    const float* w1;             /* [n_blocks][hidden]          Linear(1, hidden).weight                    */
+    const float* b1;             /* [n_blocks][hidden]                                                      */
+    const float* w2;             /* [n_blocks][hidden][hidden]  Linear(hidden, hidden).weight               */
+    const float* b2;             /* [n_blocks][hidden]                                                      */
+    const float* w3;             /* [n_blocks][2][hidden]       Linear(hidden, 2).weight (row 0 shift, 1 log-scale) */
+    const float* b3;             /* [n_blocks][2]                                                           */
+    float base_loc[2];           /* nf.distributions.base.DiagGaussian(2).loc                               */
+    float base_log_scale[2];
+} glabc_flow_t;
+
 typedef struct glabc_ctx glabc_ctx;
 
 #if defined(__GNUC__)
@@ -313,6 +331,13 @@ GLABC_API int glabc_kde_log_prob(glabc_ctx* ctx, const float* X, const float* we
 GLABC_API int glabc_kde_sample(glabc_ctx* ctx, const float* X, const float* weights, const float* bw, const int32_t* n,
                                int64_t sets, int64_t cap, int32_t dim, int64_t m, uint64_t seed, const int32_t* idx_tape,
                                const float* noise_tape, float* out, void* stream);
+
+/* ---- RealNVP flow on the tensor cores (tcgen05, TF32 operands, FP32 accumulate) ----------------------------
+ * NormalizingFlow.sample(n) (GLMCMC_NFs.py:72,127): eps[n][2] standard normals in -> theta[n][2], log_q[n];
+ * NormalizingFlow.log_prob(x) (GLMCMC_NFs.py:98): theta[n][2] -> log_q[n].  Device pointers.                    */
+GLABC_API int glabc_flow_set(glabc_ctx* ctx, const glabc_flow_t* flow, size_t nbytes, void* stream);
+GLABC_API int glabc_flow_sample(glabc_ctx* ctx, const float* eps, int64_t n, float* theta, float* log_q, void* stream);
+GLABC_API int glabc_flow_log_prob(glabc_ctx* ctx, const float* theta, int64_t n, float* log_q, void* stream);
 
 /* ---- samplers: host buffers (the reference-facing call: H2D state, run, D2H trace + stats) --- */
 /* `run->theta`, `y`, `aux`, `state64`, `trace`, `stats` are HOST pointers here; the trace is copied back in
