@@ -47,3 +47,11 @@ class MCMCRunner:
                        Local_Proposal=local_proposal, Initial_ISIR_prop=Initial_ISIR_prop, filelocation=self._path(output_file),
                        global_frequency=global_frequency, step_size=step_size, batch_size=batch_size, alpha=alpha,
                        hat_eps_T=hat_eps_T, **kw)
+
+    def run_glmcmc_nf(self, num_iterations, initial_theta, initial_y, global_frequency, local_proposal,
+                      importance_proposal_base, batch_size, step_size, train_steps, output_file="glmcmc_nf_results.csv", **kw):
+        """reference MCMCRunner.py:100-121"""
+        from .GLMCMC_NFs import GLMCMC_NF
+        return GLMCMC_NF(ABCset=self.abc_set, num_ite=num_iterations, Initial_theta=initial_theta, Initial_y=initial_y,
+                         Local_Proposal=local_proposal, filelocation=self._path(output_file), global_frequency=global_frequency,
+                         step_size=step_size, batch_size=batch_size, base=importance_proposal_base, Train_step=train_steps, **kw)

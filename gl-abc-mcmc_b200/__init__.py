@@ -10,6 +10,7 @@ from .distribution import DiagGaussian, Gamma, GaussianMixture, Uniform  # noqa:
 from .ESJD import esjd  # noqa: F401
 from .GLMALA import GLMALA  # noqa: F401
 from .GLMCMC import GLMCMC  # noqa: F401
+from .GLMCMC_NFs import GLMCMC_NF  # noqa: F401
 from .GlobalMCMC import GlobalMCMC  # noqa: F401
 from .kernel_density import KernelDensity  # noqa: F401
 from .MCMCRunner import MCMCRunner  # noqa: F401

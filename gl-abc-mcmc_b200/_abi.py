@@ -96,6 +96,13 @@ class FlowPOD(C.Structure):
                 ("b3", C.c_void_p), ("base_loc", C.c_float * 2), ("base_log_scale", C.c_float * 2)]
 
 
+class BlockIsirPOD(C.Structure):
+    """glabc_block_isir_t"""
+    _fields_ = [("step_size", C.c_int32), ("block", C.c_int32), ("blk_theta", C.c_void_p), ("blk_x", C.c_void_p),
+                ("blk_w", C.c_void_p), ("blk_lq", C.c_void_p), ("kk", C.c_void_p), ("pending", C.c_void_p),
+                ("next_step", C.c_void_p), ("lq_cur", C.c_void_p), ("lq_valid", C.c_void_p)]
+
+
 BW_SILVERMAN, BW_SCOTT = 0, 1
 AG_REC_SLOTS = 8
 AG_MAX_BLOCK = 4096
@@ -136,6 +143,8 @@ _SIGNATURES = {
                                      C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     "glabc_kde_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                    C.c_int32, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "glabc_run_block_isir": (C.c_int, [C.c_void_p, C.POINTER(RunPOD), C.POINTER(BlockIsirPOD)]),
+    "glabc_block_weights": (C.c_int, [C.c_void_p, C.POINTER(RunPOD), C.POINTER(BlockIsirPOD), C.c_uint32]),
     "glabc_flow_set": (C.c_int, [C.c_void_p, C.POINTER(FlowPOD), C.c_size_t, C.c_void_p]),
     "glabc_flow_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "glabc_flow_log_prob": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),

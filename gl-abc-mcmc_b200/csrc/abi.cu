@@ -758,6 +758,73 @@ extern "C" int glabc_flow_log_prob(glabc_ctx* ctx, const float* theta, int64_t n
     return run_flow(ctx, false, theta, n, nullptr, log_q, stream);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// block iSIR with an external importance proposal (GLMCMC-NFs)
+// ---------------------------------------------------------------------------------------------
+static int block_isir_setup(glabc_ctx* ctx, const char* who, const glabc_run_t* run, const glabc_block_isir_t* b, bool need_local,
+                            AgConsts* K, AgWorkspace* W, RunParams* R, int* block)
+{
+    if (!ctx) return GLABC_ERR_INVALID;
+    if (!ctx->has_model) return fail(ctx, GLABC_ERR_INVALID, "no model bound: call glabc_model_set first");
+    if (!run || !b) return fail(ctx, GLABC_ERR_INVALID, "%s: null run / block description", who);
+    if (need_local && !ctx->has_dist[GLABC_SLOT_LOCAL]) return fail(ctx, GLABC_ERR_INVALID, "%s needs the LOCAL proposal slot bound", who);
+    const int d = ctx->model.theta_dim;
+    if (run->n_candidates < 1 || run->n_candidates > GLABC_MAX_K) return fail(ctx, GLABC_ERR_INVALID, "n_candidates must be in 1..%d", GLABC_MAX_K);
+    if (b->step_size < 1 || int64_t(b->step_size) * run->n_candidates != b->block || b->block > GLABC_AG_MAX_BLOCK)
+        return fail(ctx, GLABC_ERR_INVALID, "%s: block must equal batch_size * step_size and be at most %d", who, GLABC_AG_MAX_BLOCK);
+    if (!b->blk_theta || !b->blk_x || !b->blk_w || !b->blk_lq || !b->kk || !b->pending || !b->next_step || !b->lq_cur || !b->lq_valid)
+        return fail(ctx, GLABC_ERR_INVALID, "%s: null block / state buffer", who);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int st = make_run_params(ctx, run, d, GLABC_TAPE_GLOBAL_SLOTS(d, d), R, block);
+    if (st) return st;
+    if (run->rng_mode != GLABC_RNG_NATIVE) return fail(ctx, GLABC_ERR_UNSUPPORTED, "%s runs the native RNG only", who);
+    if (run->block_threads == 0) *block = 128;
+    if (*block > 128) return fail(ctx, GLABC_ERR_INVALID, "%s: block_threads at most 128", who);
+    *K = AgConsts{};
+    K->model = make_model(ctx->model);
+    if (need_local) {
+        const glabc_dist_t& lp = ctx->dist[GLABC_SLOT_LOCAL];
+        if (lp.dim != d) return fail(ctx, GLABC_ERR_INVALID, "proposal dim does not match theta_dim %d", d);
+        K->lp = make_gauss(lp.a, lp.b, lp.c, d);
+        K->ip = K->lp;  // unused: the importance proposal is external
+    }
+    K->S = b->step_size;
+    *W = AgWorkspace{};
+    W->blk_theta = b->blk_theta; W->blk_x = b->blk_x; W->blk_w = b->blk_w; W->blk_lq = b->blk_lq;
+    W->kk = b->kk; W->pending = b->pending; W->next_step = b->next_step; W->lq_cur = b->lq_cur; W->lq_valid = b->lq_valid;
+    W->C = R->n_chains;
+    W->B = b->block;
+    return GLABC_OK;
+}
+
+extern "C" int glabc_run_block_isir(glabc_ctx* ctx, const glabc_run_t* run, const glabc_block_isir_t* b)
+{
+    AgConsts K;
+    AgWorkspace W;
+    RunParams R;
+    int block = 0;
+    int st = block_isir_setup(ctx, "glabc_run_block_isir", run, b, true, &K, &W, &R, &block);
+    if (st) return st;
+    if (R.n_chains == 0) return GLABC_OK;
+    CUDA_TRY(ctx, launch_block_isir(K, W, R, ctx->model.theta_dim, run->arith_mode == GLABC_ARITH_STRICT, run->trace_layout, block,
+                                    static_cast<cudaStream_t>(run->stream)));
+    return GLABC_OK;
+}
+
+extern "C" int glabc_block_weights(glabc_ctx* ctx, const glabc_run_t* run, const glabc_block_isir_t* b, uint32_t round)
+{
+    AgConsts K;
+    AgWorkspace W;
+    RunParams R;
+    int block = 0;
+    int st = block_isir_setup(ctx, "glabc_block_weights", run, b, false, &K, &W, &R, &block);
+    if (st) return st;
+    if (R.n_chains == 0) return GLABC_OK;
+    CUDA_TRY(ctx, launch_block_weights(K, W, R, ctx->model.theta_dim, round, static_cast<cudaStream_t>(run->stream)));
+    return GLABC_OK;
+}
+
 extern "C" {
 
 int glabc_run_global(glabc_ctx* ctx, const glabc_run_t* run) { return run_device(ctx, SAMPLER_GLOBAL, run); }

@@ -62,6 +62,54 @@ static cudaError_t run_dim(const AgConsts& K, const AgWorkspace& W, const AgTape
     return run_family<D, GLABC_MODEL_ID_NORMAL>(K, W, T, R, init, kde_rule, strict, replay, layout, block, st);
 }
 
+template <int D, int FAMILY>
+static cudaError_t block_isir_family(const AgConsts& K, const AgWorkspace& W, const RunParams& R, bool strict, int layout, int block,
+                                     cudaStream_t st)
+{
+    const unsigned g_step = static_cast<unsigned>((W.C + block - 1) / block);
+    if (R.write_row0 && layout != GLABC_TRACE_NONE) k_ag_row0<D><<<static_cast<unsigned>((W.C + 255) / 256), 256, 0, st>>>(R, W.C, layout);
+    if (strict) k_ag_step<D, FAMILY, true, false, true><<<g_step, block, 0, st>>>(K, R, W, layout);
+    else k_ag_step<D, FAMILY, false, false, true><<<g_step, block, 0, st>>>(K, R, W, layout);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_block_isir(const AgConsts& K, const AgWorkspace& W, const RunParams& R, int dim, bool strict, int layout,
+                              int block, cudaStream_t st)
+{
+    const bool ab = K.model.family == GLABC_MODEL_ABS_NORMAL;
+    switch (dim) {
+    case 1: return ab ? block_isir_family<1, GLABC_MODEL_ABS_NORMAL>(K, W, R, strict, layout, block, st)
+                      : block_isir_family<1, GLABC_MODEL_ID_NORMAL>(K, W, R, strict, layout, block, st);
+    case 2: return ab ? block_isir_family<2, GLABC_MODEL_ABS_NORMAL>(K, W, R, strict, layout, block, st)
+                      : block_isir_family<2, GLABC_MODEL_ID_NORMAL>(K, W, R, strict, layout, block, st);
+    case 3: return ab ? block_isir_family<3, GLABC_MODEL_ABS_NORMAL>(K, W, R, strict, layout, block, st)
+                      : block_isir_family<3, GLABC_MODEL_ID_NORMAL>(K, W, R, strict, layout, block, st);
+    case 4: return ab ? block_isir_family<4, GLABC_MODEL_ABS_NORMAL>(K, W, R, strict, layout, block, st)
+                      : block_isir_family<4, GLABC_MODEL_ID_NORMAL>(K, W, R, strict, layout, block, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_block_weights(const AgConsts& K, const AgWorkspace& W, const RunParams& R, int dim, uint32_t round, cudaStream_t st)
+{
+    const int64_t cb = (W.C * W.B + 255) / 256;
+    if (cb > 0x7fffffffll) return cudaErrorInvalidValue;
+    const unsigned g = static_cast<unsigned>(cb);
+    const bool ab = K.model.family == GLABC_MODEL_ABS_NORMAL;
+#define GLABC_BW(DD)                                                                                          \
+    if (ab) k_blk_weights<DD, GLABC_MODEL_ABS_NORMAL><<<g, 256, 0, st>>>(K, R, W, round);                     \
+    else k_blk_weights<DD, GLABC_MODEL_ID_NORMAL><<<g, 256, 0, st>>>(K, R, W, round)
+    switch (dim) {
+    case 1: GLABC_BW(1); break;
+    case 2: GLABC_BW(2); break;
+    case 3: GLABC_BW(3); break;
+    case 4: GLABC_BW(4); break;
+    default: return cudaErrorInvalidValue;
+    }
+#undef GLABC_BW
+    return cudaGetLastError();
+}
+
 cudaError_t launch_aglmcmc(const AgConsts& K, const AgWorkspace& W, const AgTapes& T, const RunParams& R, int dim, int init,
                            int kde_rule, bool strict, bool replay, int layout, int block, cudaStream_t st)
 {

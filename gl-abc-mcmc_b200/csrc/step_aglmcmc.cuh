@@ -330,7 +330,10 @@ __global__ void __launch_bounds__(256) k_ag_filter(const __grid_constant__ AgCon
 // ---------------------------------------------------------------------------------------------
 // the chain step, AGLMCMC.py:124-168 (global) / :251-271 (local)
 // ---------------------------------------------------------------------------------------------
-template <int D, int FAMILY, bool STRICT, bool REPLAY>
+// EXT = the importance proposal lives outside this kernel (GLMCMC-NFs: the shared RealNVP flow): the cached
+// proposal log-density of a state that changed is not recomputed here — the chain pauses (pending bit 1) and the
+// host refreshes it in one batched tensor-core log_prob launch (flow.cuh) before relaunching.
+template <int D, int FAMILY, bool STRICT, bool REPLAY, bool EXT = false>
 __global__ void __launch_bounds__(128) k_ag_step(const __grid_constant__ AgConsts K, const __grid_constant__ RunParams R,
                                                  AgWorkspace W, int layout)
 {
@@ -350,11 +353,12 @@ __global__ void __launch_bounds__(128) k_ag_step(const __grid_constant__ AgConst
         y[k] = R.y[c * D + k];
     }
     int kk = W.kk[c];
-    const int n_adapt = W.n_adapt[c];
+    const int n_adapt = EXT ? 1 : W.n_adapt[c];
     uint32_t i = W.next_step[c];
     float lq_cur = W.lq_cur[c];
     bool lq_valid = W.lq_valid[c] != 0;
-    const int kn = W.kde_n[c];
+    const int kn = EXT ? 0 : W.kde_n[c];
+    bool pend_lq = false;
     bool running = in_range && i <= R.last_step && R.last_step >= R.first_step && kk < K.S;
     ChainStats<D> stats;
     uint32_t done = 0;
@@ -402,8 +406,14 @@ __global__ void __launch_bounds__(128) k_ag_step(const __grid_constant__ AgConst
                 u64 = static_cast<double>(m53) * 0x1p-53;
             }
         }
+        if constexpr (EXT) {
+            if (running && is_global && !lq_valid) {  // pause before the move: its draws are counter-based, so it replays
+                running = false;
+                pend_lq = true;
+            }
+        }
         // ---- refresh stale KDE log-densities of current states, one chain at a time, 32 lanes per chain ----
-        unsigned need = __ballot_sync(0xffffffffu, running && is_global && n_adapt > 0 && !lq_valid);
+        unsigned need = EXT ? 0u : __ballot_sync(0xffffffffu, running && is_global && n_adapt > 0 && !lq_valid);
         while (need) {
             const int src = __ffs(need) - 1;
             need &= need - 1;
@@ -551,7 +561,7 @@ __global__ void __launch_bounds__(128) k_ag_step(const __grid_constant__ AgConst
         W.next_step[c] = i;
         W.lq_cur[c] = lq_cur;
         W.lq_valid[c] = lq_valid ? 1 : 0;
-        W.pending[c] = kk >= K.S ? 1 : 0;  // :169: adapt before the next iteration
+        W.pending[c] = (kk >= K.S ? 1 : 0) | (pend_lq ? 2 : 0);  // :169: adapt before the next iteration
         if (R.stats != nullptr && done > 0) stats.store(R.stats + c * GLABC_NSTATS(D), done);
     }
 }
@@ -570,6 +580,40 @@ __global__ void __launch_bounds__(256) k_ag_row0(RunParams R, int64_t C, int lay
                                                    : R.trace + (row * R.trace_chains + R.trace_chain_off + c) * D;
     store_row<D>(dst, v);
 }
+
+// GLMCMC-NFs block refresh (GLMCMC_NFs.py:73-85,129-140): theta0 / log q0 come from the flow; simulate, log-kernel,
+// weights exp(prior + log K - log q0) with NaN -> 0.  One thread per (chain, b); `round` keys the simulator normals.
+template <int D, int FAMILY>
+__global__ void __launch_bounds__(256) k_blk_weights(const __grid_constant__ AgConsts K, const __grid_constant__ RunParams R,
+                                                     AgWorkspace W, uint32_t round)
+{
+    const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (g >= W.C * W.B) return;
+    const int64_t c = g / W.B;
+    const int b = static_cast<int>(g - c * W.B);
+    const uint64_t gid = (static_cast<uint64_t>(R.chain_hi0) << 32 | R.chain_lo0) + static_cast<uint64_t>(c);
+    const Stream st{static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32)};
+    float th[D], eps_s[D], x[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) th[k] = W.blk_theta[(c * W.B + b) * D + k];
+    const uint4 w = st.block(R.rk, round, kSlotAdSim + static_cast<uint32_t>(b));
+    float z[4];
+    box_muller(w.x, w.y, z[0], z[1]);
+    box_muller(w.z, w.w, z[2], z[3]);
+#pragma unroll
+    for (int k = 0; k < D; ++k) eps_s[k] = z[k];
+    model_simulate<D, true>(K.model, th, eps_s, x);
+    const float like = model_log_kernel<D, true>(K.model, x);
+    float wgt = expf(__fsub_rn(__fadd_rn(model_prior<D, true>(K.model, th), like), W.blk_lq[c * W.B + b]));
+    if (wgt != wgt) wgt = 0.0f;  // GLMCMC_NFs.py:84-85 (rows with NaN proposals get weight 0 as well, :83)
+#pragma unroll
+    for (int k = 0; k < D; ++k) W.blk_x[(c * W.B + b) * D + k] = x[k];
+    W.blk_w[c * W.B + b] = wgt;
+}
+
+cudaError_t launch_block_isir(const AgConsts& K, const AgWorkspace& W, const RunParams& R, int dim, bool strict, int layout,
+                              int block, cudaStream_t st);
+cudaError_t launch_block_weights(const AgConsts& K, const AgWorkspace& W, const RunParams& R, int dim, uint32_t round, cudaStream_t st);
 
 cudaError_t launch_aglmcmc(const AgConsts& K, const AgWorkspace& W, const AgTapes& T, const RunParams& R, int dim, int init,
                            int kde_rule, bool strict, bool replay, int layout, int block, cudaStream_t st);

@@ -104,7 +104,7 @@ class Engine:
             trace_rows=None, trace_chains=None, trace_chain_off=0, trace_row_base=0, write_row0=True,
             stats=None, aux=None, tape32=None, tape64=None, debug=None, tape_dump=None, tape64_dump=None, K=0,
             block_threads=0, num_grad=0, tau=0.0, state64=None, tape_grad0=None, tape_grad0_dump=None, debug64=None,
-            ag=None):
+            ag=None, blk=None):
         """Enqueue `n_steps` transitions of every chain on the current stream (device tensors,
         state updated in place).  Returns the trace tensor (allocated here unless given)."""
         cn, d = theta.shape
@@ -129,6 +129,12 @@ class Engine:
                         tape_grad0=self._ptr(tape_grad0), tape_grad0_dump=self._ptr(tape_grad0_dump),
                         debug64=self._ptr(debug64),
                         stream=C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        if sampler == "block_isir":
+            self.ctx.check(self.lib.glabc_run_block_isir(self.ctx.handle, C.byref(r), C.byref(blk)))
+            return trace
+        if sampler == "block_weights":
+            self.ctx.check(self.lib.glabc_block_weights(self.ctx.handle, C.byref(r), C.byref(blk), int(step_base) & 0xFFFFFFFF))
+            return None
         if sampler == "aglmcmc":
             if ag is None:
                 raise ValueError("run('aglmcmc') needs the glabc_aglmcmc_t description (Engine.aglmcmc_params)")

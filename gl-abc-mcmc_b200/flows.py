@@ -105,12 +105,13 @@ class RealNVP(nn.Module):
         torch.cuda.current_stream(eng.device).synchronize()   # the staging tensors in `t` may be freed now
         return eng
 
-    def fused_sample_from(self, eps, eng=None):
+    def fused_sample_from(self, eps, eng=None, theta=None, log_q=None):
         eng = eng or get_engine(self.loc.device)
         eps = eps.to(eng.device, torch.float32).contiguous()
         n = eps.shape[0]
-        theta = torch.empty(n, 2, device=eng.device)
-        log_q = torch.empty(n, device=eng.device)
+        theta = torch.empty(n, 2, device=eng.device) if theta is None else theta
+        log_q = torch.empty(n, device=eng.device) if log_q is None else log_q
+        assert theta.is_contiguous() and log_q.is_contiguous() and theta.numel() == 2 * n and log_q.numel() == n
         eng.ctx.check(eng.lib.glabc_flow_sample(eng.ctx.handle, eng._ptr(eps), n, eng._ptr(theta), eng._ptr(log_q), eng._stream()))
         return theta, log_q
 

@@ -268,6 +268,22 @@ typedef struct {
     float base_log_scale[2];
 } glabc_flow_t;
 
+/* ---- block iSIR with an external importance proposal (GLMCMC-NFs, GLMCMC_NFs.py:90-152) --------------------
+ * Caller-owned DEVICE buffers: every chain's block of `block` = batch_size * step_size candidates and its counters. */
+typedef struct {
+    int32_t step_size;        /* S: global moves per block (GLMCMC_NFs.py:111)                              */
+    int32_t block;            /* B = batch_size * step_size                                                 */
+    float* blk_theta;         /* [C][B][d]  candidates from the proposal (NF_model.sample, :72,127)         */
+    float* blk_x;             /* [C][B][y]  their simulations (:80,136)                                     */
+    float* blk_w;             /* [C][B]     importance weights (:82-85)                                     */
+    float* blk_lq;            /* [C][B]     proposal log-densities                                          */
+    int32_t* kk;              /* [C] global moves done in the current block                                 */
+    int32_t* pending;         /* [C] out: bit 0 = block consumed (kk == S), bit 1 = needs lq_cur refreshed  */
+    uint32_t* next_step;      /* [C] loop index of the next iteration to perform (init step_base + 1)       */
+    float* lq_cur;            /* [C] proposal log-density of the current state (NF_model.log_prob, :98)     */
+    int32_t* lq_valid;        /* [C] lq_cur is up to date                                                   */
+} glabc_block_isir_t;
+
 typedef struct glabc_ctx glabc_ctx;
 
 #if defined(__GNUC__)
@@ -331,6 +347,15 @@ GLABC_API int glabc_kde_log_prob(glabc_ctx* ctx, const float* X, const float* we
 GLABC_API int glabc_kde_sample(glabc_ctx* ctx, const float* X, const float* weights, const float* bw, const int32_t* n,
                                int64_t sets, int64_t cap, int32_t dim, int64_t m, uint64_t seed, const int32_t* idx_tape,
                                const float* noise_tape, float* out, void* stream);
+
+/* GLMCMC-NFs loop body, GLMCMC_NFs.py:90-152, ONE pass: every chain advances until it has done run->n_steps
+ * iterations, consumed its block (pending bit 0: GLMCMC_NFs.py:111 — train / regenerate) or needs the proposal
+ * log-density of a changed state (pending bit 1).  The caller refreshes lq_cur with glabc_flow_log_prob, refills the
+ * block with glabc_flow_sample + glabc_block_weights, and calls again.  LOCAL slot = Local_Proposal.             */
+GLABC_API int glabc_run_block_isir(glabc_ctx* ctx, const glabc_run_t* run, const glabc_block_isir_t* blk);
+/* GLMCMC_NFs.py:73-85,129-140: blk_x = simulate(blk_theta), blk_w = exp(prior + log K - blk_lq), NaN -> 0;
+ * `round` keys the simulator's Philox normals (run->seed, run->chain_id_base as usual)                           */
+GLABC_API int glabc_block_weights(glabc_ctx* ctx, const glabc_run_t* run, const glabc_block_isir_t* blk, uint32_t round);
 
 /* ---- RealNVP flow on the tensor cores (tcgen05, TF32 operands, FP32 accumulate) ----------------------------
  * NormalizingFlow.sample(n) (GLMCMC_NFs.py:72,127): eps[n][2] standard normals in -> theta[n][2], log_q[n];

@@ -730,6 +730,24 @@ def golden_aglmcmc(cases, out_path):
     np.savez_compressed(out_path, **blobs)
 
 
+def golden_resample(out_path):
+    """systematic `resample` of GLMCMC_NFs.py:29-40 (same code at AGLMCMC.py:30-41) on seeded inputs"""
+    mod = sys.modules["glabcmcmc.GLMCMC_NFs"]
+    g = torch.Generator().manual_seed(5)
+    blobs = {}
+    cases = [(1000, 1000, 3.0), (50, 200, 1.0), (300, 40, 8.0), (7, 7, 0.5), (1000, 1000, 0.0)]
+    for i, (n, N, power) in enumerate(cases):
+        W = torch.rand(n, generator=g) ** power if power > 0 else torch.ones(n)
+        W = W / W.sum()
+        if i == 2:
+            W = W * 0.9            # cumulative sum tops out below 1: fewer than N indices come back
+        torch.manual_seed(100 + i)
+        idx = mod.resample(W, N)
+        blobs[f"rs{i}/W"], blobs[f"rs{i}/N"], blobs[f"rs{i}/idx"], blobs[f"rs{i}/seed"] = W.numpy(), np.int64(N), idx.numpy(), np.int64(100 + i)
+    blobs["n_cases"] = np.int64(len(cases))
+    np.savez_compressed(out_path, **blobs)
+
+
 def golden_kde(out_path):
     """KernelDensity on its own (kernel_density.py:22-177): fit / log_prob for weighted and unweighted sets"""
     import glabcmcmc.kernel_density as kdmod
@@ -814,6 +832,8 @@ def main():
         golden_aglmcmc(acases, os.path.join(HERE, "aglmcmc.npz"))
     if not only or "kde" in only:
         golden_kde(os.path.join(HERE, "kde.npz"))
+    if not only or "resample" in only:
+        golden_resample(os.path.join(HERE, "resample.npz"))
     if only:
         return
     base = dict(chains=4, epsilon=0.05, theta0=[0.0, 0.0], lp_loc=[0.0, 0.0], lp_sigma=[0.35, 0.35],

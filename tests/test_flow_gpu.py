@@ -77,3 +77,64 @@ def test_density_integrates_to_one(flow):
     mass = float(torch.exp(torch.nan_to_num(lp.double(), nan=-1e30, posinf=-1e30)).sum() * cell)
     mass_r = float(torch.exp(torch.nan_to_num(lp_r.double(), nan=-1e30, posinf=-1e30)).sum() * cell)
     assert abs(mass - mass_r) < 5e-3 and abs(mass - 1.0) < 3e-2, (mass, mass_r)
+
+
+# ---------------------------------------------------------------------------------------------
+# GLMCMC_NF sampler (block iSIR against the shared flow)
+# ---------------------------------------------------------------------------------------------
+def readme_objects():
+    import glabc_b200 as g
+    model = g.Mixture_set(epsilon=0.05)
+    lp = g.DiagGaussian(2, loc=torch.zeros(1, 2), log_scale=torch.log(torch.tensor([0.35, 0.35])))
+    return g, model, lp
+
+
+def test_block_isir_equals_glmcmc_semantics():
+    """With the untrained flow (identity map, proposal = N(0, I) exactly) and no training, GLMCMC_NF is iSIR with an
+    N(0, I) importance proposal whose candidates are pre-generated: its chains must follow the same law as run_glmcmc
+    with ip = N(0, I) — same closed-form posterior, same move rate and ESJD bands (reference: 0.92 %, 0.0295)."""
+    from scipy import stats as sst
+    g, model, lp = readme_objects()
+    out, st = g.GLMCMC_NF(model, 3001, torch.zeros(2), None, lp, None, 0.9, 50, 5, None, 0, num_chains=8192, seed=3,
+                          trace="none", return_stats=True)
+    assert out is None
+    move, e = float(st.move_rate.mean()), float(st.esjd().mean())
+    assert 0.0075 < move < 0.0110, move
+    assert 0.024 < e < 0.035, e
+    out2 = g.GLMCMC_NF(model, 2001, torch.zeros(2), None, lp, None, 0.9, 50, 5, None, 0, num_chains=8192, seed=4, trace="time")
+    a = out2[-1].abs().cpu().numpy().astype(np.float64)
+    for i in range(2):
+        assert sst.kstest(a[:, i], sst.norm(1.42518, np.sqrt(0.049881)).cdf).statistic < 0.03
+    # chains pause / resume individually (lq refresh after local accepts): every row of every chain was written
+    assert torch.isfinite(out2).all() and torch.equal(out2[0], torch.zeros(8192, 2, device=out2.device))
+
+
+def test_glmcmc_nf_training_improves_the_proposal():
+    """Mixture.py:78-79 structure (gf 0.5, K 5, 50 training steps; a shorter block and a larger Adam step so that the 50
+    steps fit a short test), many chains sharing one flow: the forward-KL loss falls, the trained flow moves its mass
+    onto the four posterior modes, and the chains still target the posterior"""
+    from scipy import stats as sst
+    g, model, lp = readme_objects()
+    res, st, flow, losses = g.GLMCMC_NF(model, 4001, torch.zeros(2), None, lp, None, 0.5, 25, 5, None, 50, num_chains=2048,
+                                        seed=1, trace="time", return_stats=True, return_flow=True, lr=3e-3)
+    assert len(losses) == 50 and np.mean(losses[-5:]) < np.mean(losses[:3]) - 0.5, losses
+    th, _ = flow.fused_sample_from(torch.randn(50000, 2, device="cuda"))
+    near_mode = ((th.abs() - 1.425).abs() < 0.7).all(1).float().mean()
+    assert float(near_mode) > 0.3, float(near_mode)            # N(0, I) puts ~9 % there
+    a = res[-1].abs().cpu().numpy().astype(np.float64)
+    for i in range(2):
+        assert sst.kstest(a[:, i], sst.norm(1.42518, np.sqrt(0.049881)).cdf).statistic < 0.05
+    assert float(st.move_rate.mean()) > 0.012                   # the untrained proposal moves 0.9 % of the time
+
+
+def test_public_api_glmcmc_nf(tmp_path):
+    """examples/Mixture.py:78-79: run_glmcmc_nf(num_ite, theta0, y0, 0.5, lp, gp_base, 5, 200, 50)"""
+    g, model, lp = readme_objects()
+    torch.manual_seed(0)
+    theta0 = torch.tensor([0.0, 0.0])
+    y0 = model.generate_samples(theta0)
+    base = g.DiagGaussian(2, torch.zeros(1, 2), torch.zeros(1, 2))      # stands in for nf.distributions.base.DiagGaussian(2)
+    runner = g.MCMCRunner(model, output_dir=str(tmp_path))
+    chain = runner.run_glmcmc_nf(1500, theta0, y0, 0.5, lp, base, 5, 200, 50, output_file="glmcmc_nf_results.csv", verbose=False)
+    assert chain.shape == (1500, 2) and chain.dtype == torch.float32 and torch.equal(chain[0], theta0)
+    assert (tmp_path / "glmcmc_nf_results.csv").exists()

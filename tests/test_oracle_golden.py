@@ -133,3 +133,18 @@ def test_aglmcmc_replay(ci):
     case = load_cases("aglmcmc.npz")[ci]
     o = run_aglmcmc_oracle(case)
     check_aglmcmc(case, o["trace"], o["dbg"], o["ad_rec"], o["ad_blk"], o["init_w"])
+
+
+def test_resample_golden():
+    """systematic resampling GLMCMC_NFs.py:29-40 (host logic of the flow training step): the vectorised searchsorted
+    form returns the reference's exact index lists, including the short return when the cumulative sum tops out below 1"""
+    import os
+    import torch
+    from helpers import GOLDEN
+    from glabc_b200.GLMCMC_NFs import resample
+    z = np.load(os.path.join(GOLDEN, "resample.npz"))
+    for i in range(int(z["n_cases"])):
+        torch.manual_seed(int(z[f"rs{i}/seed"]))
+        got = resample(torch.from_numpy(z[f"rs{i}/W"]), int(z[f"rs{i}/N"]))
+        assert np.array_equal(got.numpy(), z[f"rs{i}/idx"]), i
+    assert len(z["rs2/idx"]) < int(z["rs2/N"])
