@@ -25,8 +25,8 @@ cudaError_t launch_flow(const FlowDev& W, bool sample, const float* in, int64_t 
     }
     const int64_t chunks = (n + kFlowTilesPerCta * kFlowTile - 1) / (kFlowTilesPerCta * kFlowTile);
     const unsigned grid = static_cast<unsigned>(chunks < sm_count ? chunks : sm_count);  // persistent: one CTA per SM
-    if (sample) k_flow<true><<<grid, kFlowTile, kFlowSmemBytes, st>>>(W, in, n, out_theta, out_lq);
-    else k_flow<false><<<grid, kFlowTile, kFlowSmemBytes, st>>>(W, in, n, out_theta, out_lq);
+    if (sample) k_flow<true><<<grid, kFlowThreads, kFlowSmemBytes, st>>>(W, in, n, out_theta, out_lq);
+    else k_flow<false><<<grid, kFlowThreads, kFlowSmemBytes, st>>>(W, in, n, out_theta, out_lq);
     return cudaGetLastError();
 }
 

@@ -3,7 +3,9 @@
 // trainable DiagGaussian(2) base.  sample(n) and log_prob(x) for large batches.
 //
 // The dense piece — the 128x128 hidden layer of every coupling MLP — runs on the 5th-generation tensor cores:
-//   * one CTA (128 threads) owns tiles of 128 samples = the 128 TMEM lanes of an M=128 accumulator;
+//   * a CTA holds two groups of 128 threads; a group owns tiles of 128 samples = the 128 TMEM lanes of an M=128
+//     accumulator (each group has its own A buffer, accumulator columns and mbarrier, so one group's MMA overlaps the
+//     other's CUDA-core phases);
 //   * per coupling block: thread r computes row r of A = relu(w1 * z1[r] + b1) (the 1->128 layer is a K=1 outer
 //     product: CUDA cores) straight into shared memory in the UMMA K-major core-matrix layout, one elected thread
 //     issues 16 x tcgen05.mma.kind::tf32 (M128 N128 K8, FP32 accumulate in TMEM) against W2 (pre-packed in the
@@ -26,7 +28,9 @@ constexpr int kFlowTile = 128;
 constexpr int kFlowTilesPerCta = 8;
 constexpr int kFlowW2Bytes = kFlowHidden * kFlowHidden * 4;           // 64 KB per block
 constexpr int kFlowVecFloats = 768;                                  // w1, b1, b2 [128], w3 [2][128], b3 [2] (+pad)
-constexpr int kFlowSmemBytes = 2 * kFlowW2Bytes + kFlowVecFloats * 4 + 3 * kFlowTilesPerCta * kFlowTile * 4 + 64;
+constexpr int kFlowGroups = 2;                                        // two 128-thread groups, one tile in flight each
+constexpr int kFlowThreads = kFlowGroups * kFlowTile;
+constexpr int kFlowSmemBytes = (1 + kFlowGroups) * kFlowW2Bytes + kFlowVecFloats * 4 + 3 * kFlowTilesPerCta * kFlowTile * 4 + 64;
 
 struct FlowDev {
     const float* w1;   // [L][128]
@@ -119,6 +123,10 @@ __device__ __forceinline__ float to_tf32(float x)
     return __uint_as_float(r);
 }
 
+// round-to-nearest TF32 of a non-negative float in ONE integer add: the tensor core ignores the low 13 mantissa bits
+// (truncation), so adding half a TF32 ulp first rounds to nearest (cvt.rna.tf32 is a multi-instruction sequence)
+__device__ __forceinline__ float round_tf32_nonneg(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
+
 // pack W2 [L][out=128][in=128] (torch Linear.weight) into the UMMA layout, rounded to TF32
 static __global__ void __launch_bounds__(256) k_flow_pack(const float* __restrict__ w2, float* __restrict__ w2p, int64_t total)
 {
@@ -130,36 +138,46 @@ static __global__ void __launch_bounds__(256) k_flow_pack(const float* __restric
     w2p[l * kFlowHidden * kFlowHidden + flow_pack_offset(r, k) / 4] = to_tf32(w2[g]);
 }
 
+__device__ __forceinline__ void group_sync(int group)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(kFlowTile) : "memory");
+}
+
 // SAMPLE: in = eps [n][2] standard normals -> theta [n][2], log q [n]       (NormalizingFlow.sample)
 // !SAMPLE: in = theta [n][2] -> log q [n]                                     (NormalizingFlow.log_prob)
+// 256 threads = two groups of 128; each group owns its own A buffer, TMEM accumulator (128 columns) and mbarrier and
+// walks its tiles independently, so the MMA of one group's tile overlaps the CUDA-core phases (layer 1, epilogue) of the
+// other's, and every scheduler holds two warps.
 template <bool SAMPLE>
-__global__ void __launch_bounds__(kFlowTile, 1) k_flow(const __grid_constant__ FlowDev W, const float* __restrict__ in, int64_t n,
-                                                       float* __restrict__ out_theta, float* __restrict__ out_lq)
+__global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant__ FlowDev W, const float* __restrict__ in,
+                                                          int64_t n, float* __restrict__ out_theta, float* __restrict__ out_lq)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     float* sB = reinterpret_cast<float*>(smem);
-    float* sA = reinterpret_cast<float*>(smem + kFlowW2Bytes);
-    float* sVec = reinterpret_cast<float*>(smem + 2 * kFlowW2Bytes);
+    float* sVec = reinterpret_cast<float*>(smem + (1 + kFlowGroups) * kFlowW2Bytes);
     float* sState = sVec + kFlowVecFloats;  // [3][tiles][128]: z1, z2, log q
     uint64_t* bars = reinterpret_cast<uint64_t*>(sState + 3 * kFlowTilesPerCta * kFlowTile);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + kFlowGroups);
     const int tid = threadIdx.x, warp = tid >> 5;
-    const uint32_t bar_w = smem_u32(&bars[0]), bar_m = smem_u32(&bars[1]);
+    const int group = tid >> 7, gtid = tid & (kFlowTile - 1), gwarp = gtid >> 5;
+    float* sA = reinterpret_cast<float*>(smem + (1 + group) * kFlowW2Bytes);
+    const uint32_t bar_w = smem_u32(&bars[0]), bar_m = smem_u32(&bars[1 + group]);
     constexpr int TS = kFlowTilesPerCta * kFlowTile;
 
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(static_cast<uint32_t>(kFlowGroups * 128))
+                     : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        mbar_init(bar_w, 1);
-        mbar_init(bar_m, 1);
+        for (int i = 0; i < 1 + kFlowGroups; ++i) mbar_init(smem_u32(&bars[i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = *tmem_slot + static_cast<uint32_t>(group * 128);  // this group's accumulator columns
     // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128 (cute::UMMA::InstrDescriptor bit layout)
     constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
@@ -171,8 +189,9 @@ __global__ void __launch_bounds__(kFlowTile, 1) k_flow(const __grid_constant__ F
     for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
         int tiles = 0;
         for (int t = 0; t < kFlowTilesPerCta; ++t) {
-            const int64_t idx = (chunk * kFlowTilesPerCta + t) * kFlowTile + tid;
             if ((chunk * kFlowTilesPerCta + t) * kFlowTile < n) tiles = t + 1;
+            if ((t & 1) != group) continue;  // a tile's state is only ever touched by its own group
+            const int64_t idx = (chunk * kFlowTilesPerCta + t) * kFlowTile + gtid;
             float a = 0.0f, b = 0.0f, lq = 0.0f;
             if (idx < n) {
                 a = in[idx * 2];
@@ -183,13 +202,13 @@ __global__ void __launch_bounds__(kFlowTile, 1) k_flow(const __grid_constant__ F
                     b = W.base_loc[1] + expf(W.base_log_scale[1]) * b;
                 }
             }
-            sState[0 * TS + t * kFlowTile + tid] = a;
-            sState[1 * TS + t * kFlowTile + tid] = b;
-            sState[2 * TS + t * kFlowTile + tid] = lq;
+            sState[0 * TS + t * kFlowTile + gtid] = a;
+            sState[1 * TS + t * kFlowTile + gtid] = b;
+            sState[2 * TS + t * kFlowTile + gtid] = lq;
         }
         for (int li = 0; li < L; ++li) {
             const int l = SAMPLE ? li : L - 1 - li;
-            __syncthreads();  // every thread is done with the previous block's vectors; its MMAs were waited for
+            __syncthreads();  // both groups are done with the previous block's W2 / vectors (their MMAs were waited for)
             if (tid == 0) {
                 mbar_expect_tx(bar_w, kFlowW2Bytes);
 #pragma unroll
@@ -197,41 +216,45 @@ __global__ void __launch_bounds__(kFlowTile, 1) k_flow(const __grid_constant__ F
                     bulk_g2s(sB_addr + q * (kFlowW2Bytes / 4), reinterpret_cast<const uint8_t*>(W.w2p) +
                              static_cast<int64_t>(l) * kFlowW2Bytes + q * (kFlowW2Bytes / 4), kFlowW2Bytes / 4, bar_w);
             }
-            sVec[tid] = W.w1[l * kFlowHidden + tid];
-            sVec[128 + tid] = W.b1[l * kFlowHidden + tid];
-            sVec[256 + tid] = W.b2[l * kFlowHidden + tid];
-            sVec[384 + tid] = W.w3[(l * 2 + 0) * kFlowHidden + tid];
-            sVec[512 + tid] = W.w3[(l * 2 + 1) * kFlowHidden + tid];
-            if (tid < 2) sVec[640 + tid] = W.b3[l * 2 + tid];
+            if (tid < kFlowHidden) {
+                sVec[tid] = W.w1[l * kFlowHidden + tid];
+                sVec[128 + tid] = W.b1[l * kFlowHidden + tid];
+                sVec[256 + tid] = W.b2[l * kFlowHidden + tid];
+            } else {
+                const int u = tid - kFlowHidden;
+                sVec[384 + u] = W.w3[(l * 2 + 0) * kFlowHidden + u];
+                sVec[512 + u] = W.w3[(l * 2 + 1) * kFlowHidden + u];
+                if (u < 2) sVec[640 + u] = W.b3[l * 2 + u];
+            }
             __syncthreads();
             mbar_wait(bar_w, ph_w);
             ph_w ^= 1u;
 
-            for (int t = 0; t < tiles; ++t) {
-                float z1 = sState[0 * TS + t * kFlowTile + tid], z2 = sState[1 * TS + t * kFlowTile + tid];
+            for (int t = group; t < tiles; t += kFlowGroups) {
+                float z1 = sState[0 * TS + t * kFlowTile + gtid], z2 = sState[1 * TS + t * kFlowTile + gtid];
                 if (!SAMPLE) {  // Permute(swap)^-1 precedes the coupling's inverse
                     const float tmp = z1;
                     z1 = z2;
                     z2 = tmp;
                 }
                 // ---- layer 1 (K = 1) on CUDA cores, written as the A operand ----
-                uint8_t* rowp = reinterpret_cast<uint8_t*>(sA) + (tid >> 3) * 4096 + (tid & 7) * 16;
+                uint8_t* rowp = reinterpret_cast<uint8_t*>(sA) + (gtid >> 3) * 4096 + (gtid & 7) * 16;
 #pragma unroll 8
                 for (int kc = 0; kc < kFlowHidden / 4; ++kc) {
                     const float4 w = *reinterpret_cast<const float4*>(&sVec[kc * 4]);
                     const float4 bb = *reinterpret_cast<const float4*>(&sVec[128 + kc * 4]);
                     float4 h;
-                    h.x = to_tf32(fmaxf(fmaf(w.x, z1, bb.x), 0.0f));
-                    h.y = to_tf32(fmaxf(fmaf(w.y, z1, bb.y), 0.0f));
-                    h.z = to_tf32(fmaxf(fmaf(w.z, z1, bb.z), 0.0f));
-                    h.w = to_tf32(fmaxf(fmaf(w.w, z1, bb.w), 0.0f));
+                    h.x = round_tf32_nonneg(fmaxf(fmaf(w.x, z1, bb.x), 0.0f));
+                    h.y = round_tf32_nonneg(fmaxf(fmaf(w.y, z1, bb.y), 0.0f));
+                    h.z = round_tf32_nonneg(fmaxf(fmaf(w.z, z1, bb.z), 0.0f));
+                    h.w = round_tf32_nonneg(fmaxf(fmaf(w.w, z1, bb.w), 0.0f));
                     *reinterpret_cast<float4*>(rowp + kc * 128) = h;
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
                 tc_fence_before();
-                __syncthreads();
+                group_sync(group);
                 // ---- layer 2 (128 x 128 x 128) on the tensor cores ----
-                if (tid == 0) {
+                if (gtid == 0) {
                     tc_fence_after();
 #pragma unroll
                     for (int k = 0; k < kFlowHidden / 8; ++k) {
@@ -244,12 +267,12 @@ __global__ void __launch_bounds__(kFlowTile, 1) k_flow(const __grid_constant__ F
                 mbar_wait(bar_m, ph_m);
                 ph_m ^= 1u;
                 tc_fence_after();
-                // ---- bias + ReLU + layer 3 (N = 2) from TMEM ----
-                float p0 = 0.0f, p1 = 0.0f;
+                // ---- bias + ReLU + layer 3 (N = 2) from TMEM; four independent partial sums per output ----
+                float p0[4] = {0.0f, 0.0f, 0.0f, 0.0f}, p1[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
                 for (int cb = 0; cb < 4; ++cb) {
                     uint32_t v[32];
-                    tmem_ld32(tmem + (static_cast<uint32_t>(warp * 32) << 16) + cb * 32, v);
+                    tmem_ld32(tmem + (static_cast<uint32_t>(gwarp * 32) << 16) + cb * 32, v);
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {  // broadcast LDS.128 of b2 / W3 rows: 3 loads per 4 columns
                         const float4 b2v = *reinterpret_cast<const float4*>(&sVec[256 + cb * 32 + j]);
@@ -257,36 +280,36 @@ __global__ void __launch_bounds__(kFlowTile, 1) k_flow(const __grid_constant__ F
                         const float4 wb = *reinterpret_cast<const float4*>(&sVec[512 + cb * 32 + j]);
                         const float h0 = fmaxf(__uint_as_float(v[j]) + b2v.x, 0.0f), h1 = fmaxf(__uint_as_float(v[j + 1]) + b2v.y, 0.0f);
                         const float h2 = fmaxf(__uint_as_float(v[j + 2]) + b2v.z, 0.0f), h3 = fmaxf(__uint_as_float(v[j + 3]) + b2v.w, 0.0f);
-                        p0 = fmaf(wa.x, h0, p0); p1 = fmaf(wb.x, h0, p1);
-                        p0 = fmaf(wa.y, h1, p0); p1 = fmaf(wb.y, h1, p1);
-                        p0 = fmaf(wa.z, h2, p0); p1 = fmaf(wb.z, h2, p1);
-                        p0 = fmaf(wa.w, h3, p0); p1 = fmaf(wb.w, h3, p1);
+                        p0[0] = fmaf(wa.x, h0, p0[0]); p1[0] = fmaf(wb.x, h0, p1[0]);
+                        p0[1] = fmaf(wa.y, h1, p0[1]); p1[1] = fmaf(wb.y, h1, p1[1]);
+                        p0[2] = fmaf(wa.z, h2, p0[2]); p1[2] = fmaf(wb.z, h2, p1[2]);
+                        p0[3] = fmaf(wa.w, h3, p0[3]); p1[3] = fmaf(wb.w, h3, p1[3]);
                     }
                 }
-                p0 += sVec[640];  // shift     = param[:, 0::2]
-                p1 += sVec[641];  // log-scale = param[:, 1::2]
-                float lq = sState[2 * TS + t * kFlowTile + tid];
+                const float sh = ((p0[0] + p0[1]) + (p0[2] + p0[3])) + sVec[640];  // shift     = param[:, 0::2]
+                const float sc = ((p1[0] + p1[1]) + (p1[2] + p1[3])) + sVec[641];  // log-scale = param[:, 1::2]
+                float lq = sState[2 * TS + t * kFlowTile + gtid];
                 if (SAMPLE) {
-                    const float z2n = fmaf(z2, expf(p1), p0);  // z2 * exp(s) + shift; log q -= log det
-                    lq -= p1;
-                    sState[0 * TS + t * kFlowTile + tid] = z2n;  // Permute(swap)
-                    sState[1 * TS + t * kFlowTile + tid] = z1;
+                    const float z2n = fmaf(z2, expf(sc), sh);  // z2 * exp(s) + shift; log q -= log det
+                    lq -= sc;
+                    sState[0 * TS + t * kFlowTile + gtid] = z2n;  // Permute(swap)
+                    sState[1 * TS + t * kFlowTile + gtid] = z1;
                 } else {
-                    const float z2n = (z2 - p0) * expf(-p1);     // inverse; log det = -s
-                    lq -= p1;
-                    sState[0 * TS + t * kFlowTile + tid] = z1;
-                    sState[1 * TS + t * kFlowTile + tid] = z2n;
+                    const float z2n = (z2 - sh) * expf(-sc);     // inverse; log det = -s
+                    lq -= sc;
+                    sState[0 * TS + t * kFlowTile + gtid] = z1;
+                    sState[1 * TS + t * kFlowTile + gtid] = z2n;
                 }
-                sState[2 * TS + t * kFlowTile + tid] = lq;
+                sState[2 * TS + t * kFlowTile + gtid] = lq;
                 tc_fence_before();
-                __syncthreads();  // TMEM and the A buffer are free for the next tile
+                group_sync(group);  // this group's TMEM columns and A buffer are free for its next tile
             }
         }
-        for (int t = 0; t < tiles; ++t) {
-            const int64_t idx = (chunk * kFlowTilesPerCta + t) * kFlowTile + tid;
+        for (int t = group; t < tiles; t += kFlowGroups) {
+            const int64_t idx = (chunk * kFlowTilesPerCta + t) * kFlowTile + gtid;
             if (idx >= n) continue;
-            const float a = sState[0 * TS + t * kFlowTile + tid], b = sState[1 * TS + t * kFlowTile + tid];
-            float lq = sState[2 * TS + t * kFlowTile + tid];
+            const float a = sState[0 * TS + t * kFlowTile + gtid], b = sState[1 * TS + t * kFlowTile + gtid];
+            float lq = sState[2 * TS + t * kFlowTile + gtid];
             if (SAMPLE) {
                 out_theta[idx * 2] = a;
                 out_theta[idx * 2 + 1] = b;
@@ -298,8 +321,11 @@ __global__ void __launch_bounds__(kFlowTile, 1) k_flow(const __grid_constant__ F
             out_lq[idx] = lq;
         }
     }
+    tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"(static_cast<uint32_t>(kFlowGroups * 128))
+                     : "memory");
 }
 
 cudaError_t launch_flow_pack(const float* w2, float* w2p, int n_blocks, cudaStream_t st);
