@@ -450,8 +450,15 @@ def main():
     inst_peak = info["sm_count"] * 128 * sm_max_mhz * 1e6 / 1e9            # G thread-inst/s at max clock
     inst_ach = kernel_rate * spec["alg_inst"] / 1e9
     hbm_ach = kernel_rate * ALG_BYTES_PER_STEP / 1e9 if layout != abi.TRACE_NONE else 0.0
+    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of the step kernel, one ncu --set full capture per workload
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            tr = json.load(f).get(f"{a.sampler}:{C}x{T}:{a.layout}")
+            traffic = tr["bytes"] if tr else None
+    except (OSError, ValueError, KeyError):
+        pass
     roofline = {"bound": "alu-issue", "achieved": inst_ach, "peak": inst_peak, "unit": "Gthread-inst/s",
-                "frac": inst_ach / inst_peak, "traffic": None,
+                "frac": inst_ach / inst_peak, "traffic": traffic,
                 "note": f"{spec['alg_inst']} algorithmic thread-instructions per chain-step (SURVEY.md 8(d)); peak = "
                         f"{info['sm_count']} SMs x 128 lanes x {sm_max_mhz:.0f} MHz; kernel {kms:.3f} ms per launch",
                 "hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,

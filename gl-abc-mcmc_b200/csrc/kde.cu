@@ -23,7 +23,8 @@ static cudaError_t logprob_dim(const KdeSets& S, const float* lw, const float* x
 {
     // two queries per thread amortise the shared-memory broadcast of a training point; small batches keep one
     // query per thread so the grid still fills the machine
-    const bool two = m >= 2 * kKdeThreads * 4;
+    // (one query per thread until the grid would exceed ~8 CTAs per SM: occupancy beats the amortised LDS)
+    const bool two = S.sets * ((m + kKdeThreads - 1) / kKdeThreads) >= 8 * 148 * 2;
     const int64_t per_cta = static_cast<int64_t>(kKdeThreads) * (two ? 2 : 1);
     const int64_t qtiles = (m + per_cta - 1) / per_cta;
     const int64_t grid = S.sets * qtiles;

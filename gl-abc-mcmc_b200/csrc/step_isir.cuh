@@ -103,7 +103,9 @@ __device__ __forceinline__ void make_candidate(const IsirConsts& K, const float 
     }
 }
 
-template <int D, int FAMILY, bool STRICT, bool REPLAY, int LAYOUT, bool DUMP>
+// NKT > 0: K is a compile-time constant — the candidate loops unroll, so the K independent Philox / Box-Muller /
+// log-weight chains of a global move interleave (ILP K) instead of running one after the other.
+template <int D, int FAMILY, bool STRICT, bool REPLAY, int LAYOUT, bool DUMP, int NKT = 0>
 __global__ void __launch_bounds__(256) k_isir(const __grid_constant__ IsirConsts K, const __grid_constant__ RunParams R)
 {
     using Writer = typename WriterFor<D, LAYOUT>::type;
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(256) k_isir(const __grid_constant__ IsirConsts
     const int32_t chain = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = chain < R.n_chains;
     const int32_t cidx = active ? chain : R.n_chains - 1;
-    const int NK = R.n_candidates;
+    const int NK = NKT > 0 ? NKT : R.n_candidates;
 
     // shared memory: [trace staging of every warp][candidate table of the block]
     float* stage = smem + (threadIdx.x >> 5) * Writer::smem_floats_per_warp;
@@ -182,6 +184,7 @@ __global__ void __launch_bounds__(256) k_isir(const __grid_constant__ IsirConsts
         }
 
         // ---------------- iSIR arm: K candidates into the table (state-independent) ----------------
+#pragma unroll
         for (int j = 0; j < NK; ++j) {
             float eps_p[D], eps_s[D];
             if constexpr (REPLAY) {
@@ -235,10 +238,12 @@ __global__ void __launch_bounds__(256) k_isir(const __grid_constant__ IsirConsts
             }
         } else {
             S = 0.0f;
+#pragma unroll
             for (int j = 0; j <= NK; ++j) S += tab.at(j, 0);
             // u < sum_{i<=j} w_i / S  <=>  u * S < sum_{i<=j} w_i, evaluated in float64
             const double thr = u64 * static_cast<double>(S);
             double run = 0.0;
+#pragma unroll
             for (int j = 0; j <= NK; ++j) {
                 run += static_cast<double>(tab.at(j, 0));
                 if (ind < 0 && thr < run) ind = j;
@@ -353,14 +358,14 @@ __global__ void __launch_bounds__(256) k_isir(const __grid_constant__ IsirConsts
     }
 }
 
-template <int D, int FAMILY, bool STRICT, bool REPLAY, int LAYOUT, bool DUMP>
+template <int D, int FAMILY, bool STRICT, bool REPLAY, int LAYOUT, bool DUMP, int NKT = 0>
 static cudaError_t launch_isir_one(const IsirConsts& K, const RunParams& R, int block, cudaStream_t st)
 {
     using Writer = typename WriterFor<D, LAYOUT>::type;
     const int grid = (R.n_chains + block - 1) / block;
     const size_t smem = sizeof(float) * (static_cast<size_t>(Writer::smem_floats_per_warp) * (block / 32) +
                                          static_cast<size_t>(R.n_candidates + 1) * CandTable<D>::kFields * block);
-    auto kern = k_isir<D, FAMILY, STRICT, REPLAY, LAYOUT, DUMP>;
+    auto kern = k_isir<D, FAMILY, STRICT, REPLAY, LAYOUT, DUMP, NKT>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
@@ -383,6 +388,15 @@ static cudaError_t launch_isir_mode(const IsirConsts& K, const RunParams& R, boo
     if (R.tape_dump != nullptr) {
         if (layout != GLABC_TRACE_TIME_MAJOR) return cudaErrorInvalidValue;
         return launch_isir_one<D, FAMILY, STRICT, false, GLABC_TRACE_TIME_MAJOR, true>(K, R, block, st);
+    }
+    if constexpr (!STRICT && D == 2) {  // the README / BASELINE configuration: batch_size = 5 (Mixture.py:73, README.md:125)
+        if (R.n_candidates == 5) {
+            switch (layout) {
+            case GLABC_TRACE_NONE: return launch_isir_one<D, FAMILY, STRICT, false, GLABC_TRACE_NONE, false, 5>(K, R, block, st);
+            case GLABC_TRACE_TIME_MAJOR: return launch_isir_one<D, FAMILY, STRICT, false, GLABC_TRACE_TIME_MAJOR, false, 5>(K, R, block, st);
+            case GLABC_TRACE_CHAIN_MAJOR: return launch_isir_one<D, FAMILY, STRICT, false, GLABC_TRACE_CHAIN_MAJOR, false, 5>(K, R, block, st);
+            }
+        }
     }
     switch (layout) {
     case GLABC_TRACE_NONE: return launch_isir_one<D, FAMILY, STRICT, false, GLABC_TRACE_NONE, false>(K, R, block, st);
