@@ -4,12 +4,14 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <initializer_list>
 #include <new>
 #include <string>
 
 #include "launch.cuh"
 #include "flow.cuh"
 #include "step_aglmcmc.cuh"
+#include "step_generic.cuh"
 #include "step_mala.cuh"
 
 using namespace glabc;
@@ -165,11 +167,29 @@ int glabc_dist_set(glabc_ctx* ctx, int slot, const glabc_dist_t* dist, size_t nb
     if (!dist || nbytes != sizeof(glabc_dist_t))
         return fail(ctx, GLABC_ERR_INVALID, "glabc_dist_set: struct size %zu, expected %zu (ABI mismatch)", nbytes,
                     sizeof(glabc_dist_t));
-    if (dist->kind != GLABC_DIST_DIAG_GAUSSIAN)
-        return fail(ctx, GLABC_ERR_UNSUPPORTED, "distribution kind %d is not fused as a proposal (DiagGaussian is)", dist->kind);
     if (dist->dim < 1 || dist->dim > 4) return fail(ctx, GLABC_ERR_UNSUPPORTED, "proposal dim %d outside 1..4", dist->dim);
-    for (int i = 0; i < dist->dim; ++i)
-        if (!(dist->c[i] > 0.0f)) return fail(ctx, GLABC_ERR_INVALID, "proposal scale must be positive");
+    switch (dist->kind) {
+    case GLABC_DIST_DIAG_GAUSSIAN:
+        for (int i = 0; i < dist->dim; ++i)
+            if (!(dist->c[i] > 0.0f)) return fail(ctx, GLABC_ERR_INVALID, "proposal scale must be positive");
+        break;
+    case GLABC_DIST_UNIFORM:
+        for (int i = 0; i < dist->dim; ++i)
+            if (!(dist->b[i] > dist->a[i])) return fail(ctx, GLABC_ERR_INVALID, "Uniform needs high > low");
+        break;
+    case GLABC_DIST_GAMMA:
+        for (int i = 0; i < dist->dim; ++i)
+            if (!(dist->a[i] > 0.0f) || !(dist->b[i] > 0.0f)) return fail(ctx, GLABC_ERR_INVALID, "Gamma needs shape, rate > 0");
+        break;
+    case GLABC_DIST_GAUSSIAN_MIXTURE:
+        if (dist->n_modes < 1 || dist->n_modes > GLABC_MAX_MODES) return fail(ctx, GLABC_ERR_INVALID, "GaussianMixture: 1..%d modes", GLABC_MAX_MODES);
+        for (int m = 0; m < dist->n_modes; ++m)
+            for (int i = 0; i < dist->dim; ++i)
+                if (!(dist->mix_scale[m][i] > 0.0f)) return fail(ctx, GLABC_ERR_INVALID, "GaussianMixture scale must be positive");
+        break;
+    default:
+        return fail(ctx, GLABC_ERR_UNSUPPORTED, "unknown distribution kind %d", dist->kind);
+    }
     ctx->dist[slot] = *dist;
     ctx->has_dist[slot] = true;
     return GLABC_OK;
@@ -197,6 +217,46 @@ static GaussConsts make_gauss(const float* loc, const float* log_scale, const fl
     g.c = half_log_2pi(d);
     g.c_fast = static_cast<float>(static_cast<double>(g.c) - sum_ls);
     return g;
+}
+
+// glabc_dist_t -> constants of the general-proposal kernel (step_generic.cuh)
+static DistConsts make_dist(const glabc_dist_t& p)
+{
+    DistConsts q{};
+    q.kind = p.kind;
+    q.dim = p.dim;
+    q.n_modes = p.n_modes;
+    q.half_log_2pi = half_log_2pi(p.dim);
+    for (int i = 0; i < p.dim && i < kGenMaxDim; ++i) {
+        q.a[i] = p.a[i];
+        q.b[i] = p.b[i];
+        q.c[i] = p.c[i];
+        if (p.kind == GLABC_DIST_GAMMA)
+            q.c[i] = static_cast<float>(static_cast<double>(p.a[i]) * std::log(static_cast<double>(p.b[i])) - std::lgamma(static_cast<double>(p.a[i])));
+    }
+    if (p.kind == GLABC_DIST_GAUSSIAN_MIXTURE) {
+        double run = 0.0;
+        for (int m = 0; m < p.n_modes; ++m) {
+            double sls = 0.0;
+            for (int i = 0; i < p.dim && i < kGenMaxDim; ++i) {
+                q.mix_loc[m][i] = p.mix_loc[m][i];
+                q.mix_scale[m][i] = p.mix_scale[m][i];
+                q.mix_inv_scale[m][i] = 1.0f / p.mix_scale[m][i];
+                sls += p.mix_log_scale[m][i];
+            }
+            q.mix_c[m] = static_cast<float>(-0.5 * p.dim * std::log(2.0 * M_PI) + static_cast<double>(p.mix_log_w[m]) - sls);
+            run += p.mix_w[m];
+            q.mix_cdf[m] = static_cast<float>(run);
+        }
+    }
+    return q;
+}
+
+static bool all_gaussian(const glabc_ctx* ctx, std::initializer_list<int> slots)
+{
+    for (int s : slots)
+        if (ctx->dist[s].kind != GLABC_DIST_DIAG_GAUSSIAN) return false;
+    return true;
 }
 
 static ModelConsts make_model(const glabc_model_t& m)
@@ -318,6 +378,17 @@ static int run_device(glabc_ctx* ctx, SamplerKind kind, const glabc_run_t* run)
         int st = make_run_params(ctx, run, d, GLABC_TAPE_GLOBAL_SLOTS(d, d), &R, &block);
         if (st) return st;
         if (R.n_chains == 0) return GLABC_OK;
+        if (!all_gaussian(ctx, {GLABC_SLOT_LOCAL, GLABC_SLOT_GLOBAL})) {
+            // Uniform / Gamma / GaussianMixture proposals: the general kernel (native RNG, float32)
+            if (run->rng_mode != GLABC_RNG_NATIVE || run->tape_dump)
+                return fail(ctx, GLABC_ERR_UNSUPPORTED, "replay / tape dump exist for DiagGaussian proposals only");
+            GenericConsts G{};
+            G.model = make_model(ctx->model);
+            G.lp = make_dist(lp);
+            G.gp = make_dist(gp);
+            CUDA_TRY(ctx, launch_global_generic(G, d, R, run->trace_layout, block, static_cast<cudaStream_t>(run->stream)));
+            return GLABC_OK;
+        }
         CUDA_TRY(ctx, launch_global_mcmc(make_model(ctx->model), make_gauss(lp.a, lp.b, lp.c, d), make_gauss(gp.a, gp.b, gp.c, d),
                                          d, R, run->arith_mode == GLABC_ARITH_STRICT, run->rng_mode == GLABC_RNG_REPLAY,
                                          run->trace_layout, block, static_cast<cudaStream_t>(run->stream)));
@@ -329,6 +400,8 @@ static int run_device(glabc_ctx* ctx, SamplerKind kind, const glabc_run_t* run)
         const glabc_dist_t& lp = ctx->dist[GLABC_SLOT_LOCAL];
         const glabc_dist_t& ip = ctx->dist[GLABC_SLOT_IMPORTANCE];
         if (lp.dim != d || ip.dim != d) return fail(ctx, GLABC_ERR_INVALID, "proposal dim does not match theta_dim %d", d);
+        if (!all_gaussian(ctx, {GLABC_SLOT_LOCAL, GLABC_SLOT_IMPORTANCE}))
+            return fail(ctx, GLABC_ERR_UNSUPPORTED, "run_isir is fused for DiagGaussian proposals (other kinds: run_global)");
         if (!run) return fail(ctx, GLABC_ERR_INVALID, "null run description");
         if (run->n_candidates < 1 || run->n_candidates > GLABC_MAX_K)
             return fail(ctx, GLABC_ERR_INVALID, "n_candidates (batch_size) must be in 1..%d", GLABC_MAX_K);
@@ -348,6 +421,8 @@ static int run_device(glabc_ctx* ctx, SamplerKind kind, const glabc_run_t* run)
             return fail(ctx, GLABC_ERR_INVALID, "run_mala needs the IMPORTANCE proposal slot bound");
         const glabc_dist_t& ip = ctx->dist[GLABC_SLOT_IMPORTANCE];
         if (ip.dim != d) return fail(ctx, GLABC_ERR_INVALID, "proposal dim does not match theta_dim %d", d);
+        if (!all_gaussian(ctx, {GLABC_SLOT_IMPORTANCE}))
+            return fail(ctx, GLABC_ERR_UNSUPPORTED, "run_mala is fused for a DiagGaussian importance proposal");
         if (!run) return fail(ctx, GLABC_ERR_INVALID, "null run description");
         if (run->n_candidates < 1 || run->n_candidates > GLABC_MAX_K)
             return fail(ctx, GLABC_ERR_INVALID, "n_candidates (batch_size) must be in 1..%d", GLABC_MAX_K);
@@ -585,6 +660,8 @@ extern "C" int glabc_run_aglmcmc(glabc_ctx* ctx, const glabc_run_t* run, const g
     const glabc_dist_t& lp = ctx->dist[GLABC_SLOT_LOCAL];
     const glabc_dist_t& ip = ctx->dist[GLABC_SLOT_IMPORTANCE];
     if (lp.dim != d || ip.dim != d) return fail(ctx, GLABC_ERR_INVALID, "proposal dim does not match theta_dim %d", d);
+    if (!all_gaussian(ctx, {GLABC_SLOT_LOCAL, GLABC_SLOT_IMPORTANCE}))
+        return fail(ctx, GLABC_ERR_UNSUPPORTED, "run_aglmcmc is fused for DiagGaussian Local_Proposal / Initial_ISIR_prop");
     if (run->n_candidates < 1 || run->n_candidates > GLABC_MAX_K)
         return fail(ctx, GLABC_ERR_INVALID, "n_candidates (batch_size) must be in 1..%d", GLABC_MAX_K);
     if (ag->step_size < 1 || int64_t(ag->step_size) * run->n_candidates > GLABC_AG_MAX_BLOCK)
@@ -786,6 +863,7 @@ static int block_isir_setup(glabc_ctx* ctx, const char* who, const glabc_run_t* 
     if (need_local) {
         const glabc_dist_t& lp = ctx->dist[GLABC_SLOT_LOCAL];
         if (lp.dim != d) return fail(ctx, GLABC_ERR_INVALID, "proposal dim does not match theta_dim %d", d);
+        if (lp.kind != GLABC_DIST_DIAG_GAUSSIAN) return fail(ctx, GLABC_ERR_UNSUPPORTED, "%s is fused for a DiagGaussian Local_Proposal", who);
         K->lp = make_gauss(lp.a, lp.b, lp.c, d);
         K->ip = K->lp;  // unused: the importance proposal is external
     }
@@ -822,6 +900,32 @@ extern "C" int glabc_block_weights(glabc_ctx* ctx, const glabc_run_t* run, const
     if (st) return st;
     if (R.n_chains == 0) return GLABC_OK;
     CUDA_TRY(ctx, launch_block_weights(K, W, R, ctx->model.theta_dim, round, static_cast<cudaStream_t>(run->stream)));
+    return GLABC_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// device-side forward() / log_prob() of a bound proposal distribution
+// ---------------------------------------------------------------------------------------------
+extern "C" int glabc_dist_log_prob(glabc_ctx* ctx, int slot, const float* z, int64_t n, float* log_p, void* stream)
+{
+    if (!ctx) return GLABC_ERR_INVALID;
+    if (slot < 0 || slot >= GLABC_SLOT_COUNT || !ctx->has_dist[slot]) return fail(ctx, GLABC_ERR_INVALID, "glabc_dist_log_prob: slot %d is not bound", slot);
+    if (!z || !log_p || n < 0) return fail(ctx, GLABC_ERR_INVALID, "glabc_dist_log_prob: null pointer / bad n");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const RoundKeys rk = expand_key(make_uint2(0u, 0u));
+    CUDA_TRY(ctx, launch_dist_eval(make_dist(ctx->dist[slot]), ctx->dist[slot].dim, rk, n, z, nullptr, log_p, static_cast<cudaStream_t>(stream)));
+    return GLABC_OK;
+}
+
+extern "C" int glabc_dist_sample(glabc_ctx* ctx, int slot, int64_t n, uint64_t seed, float* z, float* log_p, void* stream)
+{
+    if (!ctx) return GLABC_ERR_INVALID;
+    if (slot < 0 || slot >= GLABC_SLOT_COUNT || !ctx->has_dist[slot]) return fail(ctx, GLABC_ERR_INVALID, "glabc_dist_sample: slot %d is not bound", slot);
+    if (!z || n < 0) return fail(ctx, GLABC_ERR_INVALID, "glabc_dist_sample: null pointer / bad n");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const RoundKeys rk = expand_key(make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+    CUDA_TRY(ctx, launch_dist_eval(make_dist(ctx->dist[slot]), ctx->dist[slot].dim, rk, n, nullptr, z, log_p, static_cast<cudaStream_t>(stream)));
     return GLABC_OK;
 }
 

@@ -1,0 +1,278 @@
+// Device versions of the reference's proposal distributions (distribution.py: Uniform :50-86, Gamma :90-137,
+// DiagGaussian :143-181, GaussianMixture :206-293) and the GlobalMCMC step (GlobalMCMC.py:37-68) for ANY of them in the
+// Local_Proposal / Global_Proposal slots.  K1 (step_global.cuh) is the tuned kernel for the all-Gaussian case; this is
+// the general one: one thread = one chain, native Philox RNG, float32 (the reference evaluates Gamma / GaussianMixture
+// in float64 — agreement is to float32 rounding, checked against the reference's recorded log-densities).
+//   Uniform          z = low + (high - low) * U                         log p = -log prod(high - low), -inf outside
+//   Gamma            Marsaglia-Tsang squeeze per coordinate (+ the U^(1/a) boost for shape < 1)
+//                                                                        log p = sum a log b - lgamma(a) + (a-1) log z - b z
+//   GaussianMixture  mode by inverse CDF of the soft-maxed weights, then a diagonal Gaussian; log p = logsumexp over modes
+#pragma once
+#include "launch.cuh"
+#include "sampler_common.cuh"
+
+namespace glabc {
+
+constexpr int kGenMaxDim = 4;
+
+struct DistConsts {
+    int32_t kind, dim, n_modes;
+    float a[kGenMaxDim], b[kGenMaxDim], c[kGenMaxDim];  // Gauss: loc, log_scale, scale; Uniform: low, high, c[0] = log p;
+                                                        // Gamma: shape, rate, c = a log b - lgamma(a)
+    float half_log_2pi;                                 // float32(-0.5 d log 2 pi)
+    float mix_loc[GLABC_MAX_MODES][kGenMaxDim], mix_inv_scale[GLABC_MAX_MODES][kGenMaxDim], mix_scale[GLABC_MAX_MODES][kGenMaxDim];
+    float mix_c[GLABC_MAX_MODES];    // -0.5 d log 2 pi + log w_m - sum log_scale_m
+    float mix_cdf[GLABC_MAX_MODES];  // inclusive prefix sums of the weights
+};
+
+struct GenericConsts {
+    ModelConsts model;
+    DistConsts lp, gp;
+};
+
+constexpr uint32_t kSlotGeneric = 0x50000000u;  // word stream of the generic proposals: blocks kSlotGeneric + 0, 1, ...
+
+// sequential 32-bit words / uniforms / normals of one (chain, step): successive Philox blocks of a dedicated slot range
+struct WordStream {
+    const RoundKeys& rk;
+    Stream st;
+    uint32_t step, slot;
+    uint4 cur;
+    int used;
+    float spare;
+    bool has_spare;
+    __device__ __forceinline__ WordStream(const RoundKeys& k, const Stream& s, uint32_t stp, uint32_t slot0)
+        : rk(k), st(s), step(stp), slot(slot0), cur(make_uint4(0, 0, 0, 0)), used(4), spare(0.0f), has_spare(false) {}
+    __device__ __forceinline__ uint32_t next()
+    {
+        if (used == 4) {
+            cur = st.block(rk, step, slot++);
+            used = 0;
+        }
+        const uint32_t w = used == 0 ? cur.x : used == 1 ? cur.y : used == 2 ? cur.z : cur.w;
+        ++used;
+        return w;
+    }
+    __device__ __forceinline__ float uniform() { return u24(next()); }                       // [0, 1) on the 2^-24 grid
+    __device__ __forceinline__ float uniform_open() { return fmaf(__uint2float_rn(next() >> 8), 0x1p-24f, 0x1p-25f); }  // (0, 1)
+    __device__ __forceinline__ float normal()
+    {
+        if (has_spare) {
+            has_spare = false;
+            return spare;
+        }
+        const uint32_t w0 = next(), w1 = next();
+        float n0, n1;
+        box_muller(w0, w1, n0, n1);
+        spare = n1;
+        has_spare = true;
+        return n0;
+    }
+};
+
+template <int D>
+__device__ __forceinline__ float dist_log_prob(const DistConsts& q, const float (&z)[D])
+{
+    switch (q.kind) {
+    case GLABC_DIST_DIAG_GAUSSIAN: {
+        float s = 0.0f;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            const float r = (z[i] - q.a[i]) / q.c[i];
+            s += q.b[i] + 0.5f * (r * r);
+        }
+        return q.half_log_2pi - s;
+    }
+    case GLABC_DIST_UNIFORM: {
+        bool out = false;
+#pragma unroll
+        for (int i = 0; i < D; ++i) out |= (z[i] < q.a[i]) || (z[i] > q.b[i]);  // distribution.py:82-85
+        return out ? -INFINITY : q.c[0];
+    }
+    case GLABC_DIST_GAMMA: {
+        float s = 0.0f;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            float lp;
+            if (z[i] > 0.0f) lp = q.c[i] + (q.a[i] - 1.0f) * logf(z[i]) - q.b[i] * z[i];
+            else if (z[i] == 0.0f && q.a[i] == 1.0f) lp = q.c[i];   // pdf(0) = b for shape 1
+            else lp = -INFINITY;                                     // pdf == 0 -> -inf, distribution.py:133-136
+            s += lp;
+        }
+        return s;
+    }
+    case GLABC_DIST_GAUSSIAN_MIXTURE: {
+        float t[GLABC_MAX_MODES], mx = -INFINITY;
+        for (int m = 0; m < q.n_modes; ++m) {
+            float s = 0.0f;
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                const float r = (z[i] - q.mix_loc[m][i]) * q.mix_inv_scale[m][i];
+                s = fmaf(r, r, s);
+            }
+            t[m] = fmaf(-0.5f, s, q.mix_c[m]);  // distribution.py:283-288
+            mx = fmaxf(mx, t[m]);
+        }
+        if (mx == -INFINITY) return -INFINITY;
+        float acc = 0.0f;
+        for (int m = 0; m < q.n_modes; ++m) acc += expf(t[m] - mx);
+        return mx + logf(acc);
+    }
+    }
+    return NAN;
+}
+
+// forward(): one draw and its log-density
+template <int D>
+__device__ __forceinline__ float dist_forward(const DistConsts& q, WordStream& ws, float (&z)[D])
+{
+    switch (q.kind) {
+    case GLABC_DIST_DIAG_GAUSSIAN: {
+        float s = 0.0f;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            const float e = ws.normal();
+            z[i] = fmaf(q.c[i], e, q.a[i]);
+            s += q.b[i] + 0.5f * (e * e);  // log p from eps, distribution.py:171-173
+        }
+        return q.half_log_2pi - s;
+    }
+    case GLABC_DIST_UNIFORM: {
+#pragma unroll
+        for (int i = 0; i < D; ++i) z[i] = fmaf(q.b[i] - q.a[i], ws.uniform(), q.a[i]);  // distribution.py:73-77
+        return q.c[0];
+    }
+    case GLABC_DIST_GAMMA: {
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            // Marsaglia & Tsang (2000): Gamma(a >= 1) by squeeze-rejection from a cubed normal; shape < 1 via Gamma(a + 1) * U^(1/a)
+            const float a0 = q.a[i];
+            const float a = a0 < 1.0f ? a0 + 1.0f : a0;
+            const float dd = a - (1.0f / 3.0f), cc = rsqrtf(9.0f * dd);
+            float g = dd;
+            for (int it = 0; it < 64; ++it) {
+                const float x = ws.normal();
+                const float t = fmaf(cc, x, 1.0f);
+                if (t <= 0.0f) continue;
+                const float v = t * t * t;
+                const float u = ws.uniform_open();
+                if (logf(u) < 0.5f * x * x + dd - dd * v + dd * logf(v)) {
+                    g = dd * v;
+                    break;
+                }
+            }
+            if (a0 < 1.0f) g *= powf(ws.uniform_open(), 1.0f / a0);
+            z[i] = g / q.b[i];  // scale = 1 / rate, distribution.py:118
+        }
+        return dist_log_prob<D>(q, z);
+    }
+    case GLABC_DIST_GAUSSIAN_MIXTURE: {
+        const float u = ws.uniform();
+        int m = q.n_modes - 1;
+        for (int j = q.n_modes - 2; j >= 0; --j)
+            if (u < q.mix_cdf[j]) m = j;  // torch.multinomial(weights, 1): first mode whose cumulative weight exceeds u
+#pragma unroll
+        for (int i = 0; i < D; ++i) z[i] = fmaf(ws.normal(), q.mix_scale[m][i], q.mix_loc[m][i]);  // distribution.py:258-260
+        return dist_log_prob<D>(q, z);
+    }
+    }
+    return NAN;
+}
+
+// GlobalMCMC.py:37-68 with arbitrary proposal kinds
+template <int D, int FAMILY>
+__global__ void __launch_bounds__(128) k_global_generic(const __grid_constant__ GenericConsts K, const __grid_constant__ RunParams R,
+                                                        int layout)
+{
+    const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (c >= R.n_chains) return;
+    float theta[D], y[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        theta[k] = R.theta[c * D + k];
+        y[k] = R.y[c * D + k];
+    }
+    auto put = [&](uint32_t row_abs) {
+        if (layout == GLABC_TRACE_NONE) return;
+        const int64_t row = static_cast<int64_t>(row_abs) - R.trace_row_base;
+        float* dst = layout == GLABC_TRACE_CHAIN_MAJOR ? R.trace + ((R.trace_chain_off + c) * R.trace_rows + row) * D
+                                                       : R.trace + (row * R.trace_chains + R.trace_chain_off + c) * D;
+        store_row<D>(dst, theta);
+    };
+    if (R.write_row0) put(R.first_step - 1u);
+    ChainStats<D> stats;
+    const Stream stream = chain_stream(R, static_cast<int32_t>(c));
+    float prior_old = model_prior<D, false>(K.model, theta), kern_old = model_log_kernel<D, false>(K.model, y);
+
+    for (uint32_t i = R.first_step; i <= R.last_step && R.last_step >= R.first_step; ++i) {
+        const uint4 w0 = stream.block(R.rk, i, kSlotStep);
+        const bool is_global = (step_block_ub(w0) < R.gf_thr_hi) || R.gf_all_global;  // GlobalMCMC.py:39
+        const float log_w = log_approx(__uint2float_rn(step_block_ua(w0)) * 0x1p-24f);  // :47,62
+        WordStream ws(R.rk, stream, i, kSlotGeneric);
+        float th_p[D], y_p[D], eps_s[D], corr = 0.0f;
+        if (is_global) {
+            const float lq_p = dist_forward<D>(K.gp, ws, th_p);       // :40
+            corr = dist_log_prob<D>(K.gp, theta) - lq_p;              // :45-46
+        } else {
+            float z[D];
+            (void)dist_forward<D>(K.lp, ws, z);                       // Local_Proposal.sample(1), :56
+#pragma unroll
+            for (int k = 0; k < D; ++k) th_p[k] = z[k] + theta[k];
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) eps_s[k] = ws.normal();
+        model_simulate<D, false>(K.model, th_p, eps_s, y_p);           // :41,57
+        const float prior_p = model_prior<D, false>(K.model, th_p), kern_p = model_log_kernel<D, false>(K.model, y_p);
+        const float log_acc = (prior_p + kern_p) + corr - (prior_old + kern_old);   // :44-46 / :60-61
+        const bool accept = log_w < log_acc;                                        // :49,64 (NaN rejects)
+        float prev[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) prev[k] = theta[k];
+        if (accept) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                theta[k] = th_p[k];
+                y[k] = y_p[k];
+            }
+            prior_old = prior_p;
+            kern_old = kern_p;
+        }
+        stats.update(is_global, accept, theta, prev);
+        put(i);
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        R.theta[c * D + k] = theta[k];
+        R.y[c * D + k] = y[k];
+    }
+    if (R.stats != nullptr) stats.store(R.stats + c * GLABC_NSTATS(D), R.last_step + 1u - R.first_step);
+}
+
+// device-side forward() / log_prob() of a bound distribution (glabc_dist_sample / glabc_dist_log_prob)
+template <int D>
+__global__ void __launch_bounds__(256) k_dist_eval(const __grid_constant__ DistConsts q, RoundKeys rk, int64_t n, const float* __restrict__ z_in,
+                                                   float* __restrict__ z_out, float* __restrict__ logp)
+{
+    const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    float z[D];
+    float lp;
+    if (z_in != nullptr) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) z[k] = z_in[g * D + k];
+        lp = dist_log_prob<D>(q, z);
+    } else {
+        const Stream st{static_cast<uint32_t>(g), static_cast<uint32_t>(g >> 32)};
+        WordStream ws(rk, st, 0u, kSlotGeneric);
+        lp = dist_forward<D>(q, ws, z);
+#pragma unroll
+        for (int k = 0; k < D; ++k) z_out[g * D + k] = z[k];
+    }
+    if (logp != nullptr) logp[g] = lp;
+}
+
+cudaError_t launch_global_generic(const GenericConsts& K, int dim, const RunParams& R, int layout, int block, cudaStream_t st);
+cudaError_t launch_dist_eval(const DistConsts& q, int dim, const RoundKeys& rk, int64_t n, const float* z_in, float* z_out, float* logp,
+                             cudaStream_t st);
+
+}  // namespace glabc

@@ -157,6 +157,21 @@ class Engine:
                                ad_idx=self._ptr(ad_idx), ad_noise=self._ptr(ad_noise), ad_sim=self._ptr(ad_sim),
                                ad_rec=self._ptr(ad_rec), ad_blk=self._ptr(ad_blk), init_w=self._ptr(init_w), dump_rounds=dump)
 
+    def dist_log_prob(self, slot, z):
+        """log_prob of the distribution bound to `slot`, evaluated on the device"""
+        z = self._f32(z)
+        out = torch.empty(z.shape[0], dtype=torch.float32, device=self.device)
+        self.ctx.check(self.lib.glabc_dist_log_prob(self.ctx.handle, int(slot), self._ptr(z), z.shape[0], self._ptr(out), self._stream()))
+        return out
+
+    def dist_sample(self, slot, n, dim, seed=0):
+        """forward(n) of the distribution bound to `slot`: (z [n, dim], log_p [n])"""
+        z = torch.empty(n, dim, dtype=torch.float32, device=self.device)
+        lp = torch.empty(n, dtype=torch.float32, device=self.device)
+        self.ctx.check(self.lib.glabc_dist_sample(self.ctx.handle, int(slot), int(n), int(seed) & 0xFFFFFFFFFFFFFFFF, self._ptr(z),
+                                                  self._ptr(lp), self._stream()))
+        return z, lp
+
     # -- KernelDensity (kernel_density.py) ------------------------------------------------------
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)

@@ -309,8 +309,15 @@ GLABC_API int glabc_model_set(glabc_ctx* ctx, const glabc_model_t* model, size_t
  * GLMCMC.py:24-25)                                                                               */
 GLABC_API int glabc_dist_set(glabc_ctx* ctx, int slot, const glabc_dist_t* dist, size_t nbytes);
 
+/* device-side forward() / log_prob() of the distribution bound to `slot` (distribution.py:73-86, 106-137, 166-181,
+ * 242-293): z[n][dim] -> log_p[n], and n fresh draws z[n][dim] (+ their log-densities, log_p may be NULL)            */
+GLABC_API int glabc_dist_log_prob(glabc_ctx* ctx, int slot, const float* z, int64_t n, float* log_p, void* stream);
+GLABC_API int glabc_dist_sample(glabc_ctx* ctx, int slot, int64_t n, uint64_t seed, float* z, float* log_p, void* stream);
+
 /* ---- samplers: device buffers, asynchronous on `stream` ------------------------------------- */
-/* GlobalMCMC loop body, GlobalMCMC.py:37-68 (local RW-MH / global independence-MH mixture)       */
+/* GlobalMCMC loop body, GlobalMCMC.py:37-68 (local RW-MH / global independence-MH mixture).  DiagGaussian proposals
+ * in both slots run the tuned kernel (replay + strict arithmetic available); any Uniform / Gamma / GaussianMixture
+ * proposal selects the general kernel (native RNG, float32).                                                       */
 GLABC_API int glabc_run_global(glabc_ctx* ctx, const glabc_run_t* run);
 
 /* GLMCMC loop body, GLMCMC.py:58-104, incl. weight_sampling GLMCMC.py:7-22: iSIR global move with

@@ -1,0 +1,125 @@
+"""GPU tests of the device versions of the reference's distribution classes (distribution.py: Uniform, Gamma,
+DiagGaussian, GaussianMixture) and of GlobalMCMC with them as proposals (the general kernel, csrc/step_generic.cuh)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+from scipy import stats as sst
+
+from helpers import GOLDEN, abi
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from glabc_b200.engine import Engine
+    return Engine()
+
+
+@pytest.fixture(scope="module")
+def dists():
+    import glabc_b200 as g
+    z = np.load(os.path.join(GOLDEN, "misc.npz"))
+    t = torch.from_numpy
+    return z, dict(
+        diag=g.DiagGaussian(2, t(z["diag/loc"]), t(z["diag/log_scale"])),
+        uniform=g.Uniform(2, t(z["uniform/low"]), t(z["uniform/high"])),
+        gamma=g.Gamma(t(np.asarray(z["gamma/shape"])), t(np.asarray(z["gamma/rate"]))),
+        mix=g.GaussianMixture(3, 2, loc=z["mix/loc"], scale=np.exp(z["mix/log_scale"]), weights=np.exp(z["mix/weight_scores"])))
+
+
+@pytest.mark.parametrize("name", ["diag", "uniform", "gamma", "mix"])
+def test_log_prob_matches_the_reference(eng, dists, name):
+    """device log_prob against the values the reference's own classes produced (tests/golden/misc.npz), incl. -inf
+    outside the Uniform box / Gamma support; float32 vs the reference's float64 for Gamma and GaussianMixture"""
+    z, d = dists
+    eng.bind_proposal(abi.SLOT_GLOBAL, d[name])
+    got = eng.dist_log_prob(abi.SLOT_GLOBAL, torch.from_numpy(z[f"{name}/z"]).float()).cpu().numpy().astype(np.float64)
+    want = z[f"{name}/log_prob"].astype(np.float64)
+    assert np.array_equal(np.isneginf(got), np.isneginf(want))
+    fin = np.isfinite(want)
+    assert fin.any() and np.allclose(got[fin], want[fin], rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("name", ["diag", "uniform", "gamma", "mix"])
+def test_forward_draws_follow_the_law(eng, dists, name):
+    """device forward(): the returned log-density is log_prob of the returned draw, and the draws follow the distribution"""
+    _, d = dists
+    dist = d[name]
+    eng.bind_proposal(abi.SLOT_LOCAL, dist)
+    n = 200000
+    zs, lp = eng.dist_sample(abi.SLOT_LOCAL, n, 2, seed=7)
+    assert torch.allclose(lp, eng.dist_log_prob(abi.SLOT_LOCAL, zs), rtol=2e-5, atol=2e-5)
+    x = zs.cpu().numpy().astype(np.float64)
+    if name == "uniform":
+        lo, hi = dist.low.numpy(), dist.high.numpy()
+        for i in range(2):
+            assert sst.kstest(x[:, i], sst.uniform(lo[i], hi[i] - lo[i]).cdf).statistic < 0.005
+    elif name == "gamma":
+        a, b = dist.Shape.numpy(), dist.Rate.numpy()
+        for i in range(2):
+            assert sst.kstest(x[:, i], sst.gamma(a[i], scale=1 / b[i]).cdf).statistic < 0.005
+    elif name == "diag":
+        loc, sc = dist.loc.reshape(-1).numpy(), np.exp(dist.log_scale.reshape(-1).numpy())
+        for i in range(2):
+            assert sst.kstest(x[:, i], sst.norm(loc[i], sc[i]).cdf).statistic < 0.005
+    else:
+        w = torch.softmax(dist.weight_scores, 1)[0].numpy()
+        loc, sc = dist.loc[0].numpy(), np.exp(dist.log_scale[0].numpy())
+        cdf0 = lambda v: sum(w[m] * sst.norm(loc[m, 0], sc[m, 0]).cdf(v) for m in range(3))  # noqa: E731
+        assert sst.kstest(x[:, 0], cdf0).statistic < 0.005
+        # importance-sampling identity E_q[p/q] = 1 with p = a narrow Gaussian inside mode 0 (bounded ratio): the
+        # returned density is the normalised density of the draws
+        logp = (sst.norm(loc[0, 0], 0.5 * sc[0, 0]).logpdf(x[:, 0]) + sst.norm(loc[0, 1], 0.5 * sc[0, 1]).logpdf(x[:, 1]))
+        assert abs(np.exp(logp - lp.cpu().numpy().astype(np.float64)).mean() - 1.0) < 0.03
+    small = eng.dist_sample(abi.SLOT_LOCAL, 5, 2, seed=8)[0]
+    assert not torch.equal(small, zs[:5])
+    if name == "gamma":   # shape < 1 takes the U^(1/a) boost
+        import glabc_b200 as g
+        eng.bind_proposal(abi.SLOT_LOCAL, g.Gamma(torch.tensor([0.4, 0.9]), torch.tensor([2.0, 1.0])))
+        xs = eng.dist_sample(abi.SLOT_LOCAL, n, 2, seed=9)[0].cpu().numpy().astype(np.float64)
+        assert sst.kstest(xs[:, 0], sst.gamma(0.4, scale=0.5).cdf).statistic < 0.006
+
+
+def readme():
+    import glabc_b200 as g
+    model = g.Mixture_set(epsilon=0.05)
+    lp = g.DiagGaussian(2, loc=torch.zeros(1, 2), log_scale=torch.log(torch.tensor([0.35, 0.35])))
+    return g, model, lp
+
+
+def check_posterior(theta, tol=0.04):
+    a = theta.abs().cpu().numpy().astype(np.float64)
+    for i in range(2):
+        assert sst.kstest(a[:, i], sst.norm(1.42518, np.sqrt(0.049881)).cdf).statistic < tol
+    quad = ((theta[:, 0] > 0).long() * 2 + (theta[:, 1] > 0).long()).bincount(minlength=4).cpu().numpy() / theta.shape[0]
+    assert np.abs(quad - 0.25).max() < tol
+
+
+def test_global_mcmc_with_mixture_and_uniform_proposals(eng):
+    """GlobalMCMC.py:37-68 with non-Gaussian proposals: a 4-mode GaussianMixture independence proposal (accepts several times
+    more often than N(0, I); the ABC kernel of the fresh simulation caps the rate), a Uniform box independence proposal, and a Uniform random-walk local proposal —
+    each must leave the closed-form ABC posterior invariant"""
+    g, model, lp = readme()
+    modes = [[1.425, 1.425], [1.425, -1.425], [-1.425, 1.425], [-1.425, -1.425]]
+    gm = g.GaussianMixture(4, 2, loc=modes, scale=[[0.3, 0.3]] * 4, weights=[1, 1, 1, 1])
+    _, st = g.GlobalMCMC(model, 1501, torch.zeros(2), None, gm, None, 0.5, lp, num_chains=8192, seed=2, trace="none", return_stats=True)
+    acc_g = float((st.accepted_global / st.global_steps.clamp(min=1)).mean())
+    assert acc_g > 0.02, acc_g                      # N(0, I) proposal: ~0.5 %
+    out = g.GlobalMCMC(model, 1501, torch.zeros(2), None, gm, None, 0.5, lp, num_chains=8192, seed=3, trace="time")
+    check_posterior(out[-1])
+    box = g.Uniform(2, torch.tensor([-3.0, -3.0]), torch.tensor([3.0, 3.0]))
+    out = g.GlobalMCMC(model, 6001, torch.zeros(2), None, box, None, 0.5, lp, num_chains=8192, seed=4, trace="time")
+    check_posterior(out[-1], tol=0.05)
+    rw = g.Uniform(2, torch.tensor([-0.6, -0.6]), torch.tensor([0.6, 0.6]))      # symmetric box random walk
+    out = g.GlobalMCMC(model, 1501, torch.zeros(2), None, gm, None, 0.3, rw, num_chains=8192, seed=5, trace="time")
+    check_posterior(out[-1])
+
+
+def test_non_gaussian_proposals_are_refused_where_not_fused(eng):
+    g, model, lp = readme()
+    box = g.Uniform(2, torch.tensor([-3.0, -3.0]), torch.tensor([3.0, 3.0]))
+    with pytest.raises(abi.GlabcError, match="DiagGaussian"):
+        g.GLMCMC(model, 100, torch.zeros(2), None, lp, None, 0.9, box, 5, num_chains=64)
