@@ -53,6 +53,7 @@ def parse():
     p.add_argument("--block", type=int, default=0)
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
+    p.add_argument("--no-extra", action="store_true", help="skip the short device-resident timings of the other kernels")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
     return p.parse_args()
 
@@ -308,6 +309,49 @@ def bench_kde(a, rank, world, local_rank):
         print(json.dumps(line), flush=True)
 
 
+def other_kernels(eng, model, lp, gp):
+    """Short device-resident timings of the other hot-path kernels (the headline line stays GlobalMCMC, BASELINE configs[1]);
+    full lines with e2e / cpu_baseline: `bench.py --sampler glmcmc|glmala|aglmcmc|kde`.  CUDA events, 3 warm-up + 5 timed."""
+    import torch
+    import glabc_b200 as g
+    from glabc_b200.flows import RealNVP
+
+    def timed(fn, units):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        return {"ms": ms, "per_sec": units / (ms * 1e-3)}
+
+    z = torch.zeros(2)
+    out = {}
+    out["glmcmc_isir_K5"] = dict(timed(lambda: g.GLMCMC(model, 10000, z, None, lp, None, 0.9, gp, 5, num_chains=65536, seed=1, trace="none"),
+                                       65536 * 9999), unit="chain-steps/s", workload="65,536 chains x 1e4, gf 0.9, statistics only")
+    out["glmala"] = dict(timed(lambda: g.GLMALA(model, 1001, z, None, 0.3, 100, None, 0.8, gp, 5, num_chains=32768, seed=1, trace="none"),
+                               32768 * 1000), unit="chain-steps/s", workload="32,768 chains x 1e3, gf 0.8, tau 0.3, num_grad 100")
+    out["aglmcmc"] = dict(timed(lambda: g.AGLMCMC(model, 2001, z, None, lp, gp, None, 1.0, 200, 5, 0.8, 0.2, num_chains=16384, seed=1,
+                                                  trace="none"), 16384 * 2000), unit="chain-steps/s",
+                          workload="16,384 chains x 2e3, gf 1, K 5, step 200")
+    X = torch.randn(100000, 2, device="cuda")
+    w, bw = eng.kde_fit(X, None)
+    out["kde_log_prob"] = dict(timed(lambda: eng.kde_log_prob(X, w, bw, X), 1e10), unit="pairs/s", workload="1e5 queries x 1e5 points, d = 2")
+    flow = RealNVP(device="cuda")
+    with torch.no_grad():
+        flow.w3.copy_(0.05 * torch.randn_like(flow.w3))
+    flow.bind(eng)
+    eps = torch.randn(1 << 21, 2, device="cuda")
+    r = timed(lambda: flow.fused_sample_from(eps, eng), float(1 << 21))
+    out["realnvp_sample_tcgen05"] = dict(r, unit="samples/s", tflops_tf32=r["per_sec"] * 1.049e6 / 1e12,
+                                         workload="2,097,152 samples through 32 coupling blocks (128x128 hidden layer on tensor cores)")
+    return out
+
+
 def workload_config(a):
     spec = SAMPLERS[a.sampler]
     return {"workload": spec["workload"], "chains_per_gpu": a.chains,
@@ -543,6 +587,8 @@ def main():
                        "note": f"glabc_run_{entry}_host: pinned host buffers, full trace copied back in time chunks "
                                "overlapped with the kernels; host view [T,C,2] (chain c = trace[:, c])"}
 
+    if rank == 0 and world == 1 and a.sampler == "global" and not a.no_extra:
+        line["other_kernels"] = other_kernels(eng, model, lp, gp)
     if rank == 0 and not a.no_cpu:
         r, cores, sample = cpu_port_rate(C, T, a.cpu_seconds, sampler=a.sampler)
         line["cpu_baseline"] = {"value": r, "unit": "chain-steps/s", "cores": cores, "kind": "port", "sample": sample}
