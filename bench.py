@@ -140,11 +140,17 @@ class CpuPort:
             aux = None
             extra = dict(ag=self.oracle.aglmcmc_params(S=self.spec["step_size"], alpha=self.spec["alpha"],
                                                        hat_eps_T=self.spec["hat_eps_T"]))
+        stats = np.zeros((c, abi.nstats(2)), np.float32)
         t0 = time.perf_counter()
         self.oracle.run(self.spec["entry"], *self.pods, theta=theta, y=y, n_steps=t, gf=self.spec["gf"], seed=0,
                         trace=trace, trace_layout=abi.TRACE_CHAIN_MAJOR, threads=self.threads, K=self.spec["K"], aux=aux,
-                        **extra)
-        return time.perf_counter() - t0
+                        stats=stats, **extra)
+        dt = time.perf_counter() - t0
+        # ESJD.py:17-24 from the Gram accumulators: det(sum dd^T / n)^(1/2) per chain, averaged
+        n = np.maximum(stats[:, abi.STAT_STEPS].astype(np.float64), 1.0)
+        g00, g01, g11 = (stats[:, abi.STAT_SUM + 4 + k].astype(np.float64) / n for k in range(3))
+        self.mean_esjd = float(np.sqrt(np.maximum(g00 * g11 - g01 * g01, 0.0)).mean())
+        return dt
 
     def size_sample(self, chains, iters, seconds):
         """chains x transitions of the workload that take about `seconds` on this host"""
@@ -162,7 +168,8 @@ def cpu_port_rate(chains, iters, seconds, threads=0, sampler="global"):
     port = CpuPort(threads, sampler)
     c, t = port.size_sample(chains, iters, seconds)
     dt = port.run(c, t)
-    return c * t / dt, port.cores, f"{c} chains x {t} transitions of the same workload, full trace in host memory, {dt:.1f} s"
+    return (c * t / dt, port.cores, f"{c} chains x {t} transitions of the same workload, full trace in host memory, {dt:.1f} s",
+            port.mean_esjd)
 
 
 def bench_reference(a, rank):
@@ -184,7 +191,8 @@ def bench_reference(a, rank):
             "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(a),
-            "cpu_baseline": {"value": value, "unit": "chain-steps/s", "cores": port.cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "chain-steps/s", "cores": port.cores, "kind": "port", "sample": sample,
+                             "esjd": {"mean_per_chain": port.mean_esjd, "aggregate_esjd_per_sec": port.mean_esjd * value}},
             "e2e": {"value": value, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -582,6 +590,29 @@ def main():
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         h2d = (h_theta.numel() + h_y.numel() + h_stats.numel()) * 4
         d2h = h2d + (h_trace.numel() * 4 if h_trace is not None else 0)
+        # the same call when the caller wants the in-kernel statistics (ESJD Gram, moments, acceptance) instead of the chain
+        def e2e_stats_step(i):
+            h_theta.copy_(h_theta0)
+            h_y.copy_(h_y0)
+            h_stats.zero_()
+            if K:
+                h_aux.copy_(h_aux0)
+            if s64 is not None:
+                h_extra["state64"].zero_()
+            eng.run_host(entry, theta=h_theta, y=h_y, n_steps=T - 1, gf=gf, seed=i, chain_id_base=chain_base, trace=None,
+                         trace_layout=abi.TRACE_NONE, stats=h_stats, block_threads=a.block, K=K, aux=h_aux, **h_extra)
+        e2e_stats_step(0)
+        barrier()
+        t1 = time.perf_counter()
+        for i in range(e_steps):
+            e2e_stats_step(1 + i)
+        barrier()
+        dt_s = torch.tensor([time.perf_counter() - t1], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt_s, op=dist.ReduceOp.MAX)
+        line["e2e_stats_only"] = {"value": steps_per_pass * e_steps / float(dt_s.item()), "unit": "chain-steps/s",
+                                  "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d,
+                                  "note": "same host-buffer call with trace_layout NONE: state + statistics copied back, no chain"}
         line["e2e"] = {"value": steps_per_pass * e_steps / float(dt.item()), "unit": "chain-steps/s",
                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e_steps,
                        "note": f"glabc_run_{entry}_host: pinned host buffers, full trace copied back in time chunks "
@@ -590,8 +621,9 @@ def main():
     if rank == 0 and world == 1 and a.sampler == "global" and not a.no_extra:
         line["other_kernels"] = other_kernels(eng, model, lp, gp)
     if rank == 0 and not a.no_cpu:
-        r, cores, sample = cpu_port_rate(C, T, a.cpu_seconds, sampler=a.sampler)
-        line["cpu_baseline"] = {"value": r, "unit": "chain-steps/s", "cores": cores, "kind": "port", "sample": sample}
+        r, cores, sample, cpu_esjd = cpu_port_rate(C, T, a.cpu_seconds, sampler=a.sampler)
+        line["cpu_baseline"] = {"value": r, "unit": "chain-steps/s", "cores": cores, "kind": "port", "sample": sample,
+                                "esjd": {"mean_per_chain": cpu_esjd, "aggregate_esjd_per_sec": cpu_esjd * r}}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
