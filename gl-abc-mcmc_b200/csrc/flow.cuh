@@ -12,8 +12,11 @@
 //     same layout, fetched per block with one cp.async.bulk into shared memory), tcgen05.commit -> mbarrier;
 //   * epilogue: each warp pulls its 32 lanes x 128 columns back with tcgen05.ld, adds b2, ReLU, and contracts
 //     with the two rows of W3 (N=2: CUDA cores) -> (shift, log-scale) -> affine update of z2, log-det, swap.
-//   * W2 of a block is reused for kFlowTilesPerCta tiles (1,024 samples) before the next block's weights are
-//     fetched, so weight traffic is 2 KB per sample from L2, nothing from HBM (the whole flow is 2.1 MB).
+//   * W2 of a block is reused for kFlowTilesPerCta tiles (2,048 samples) before the next block's weights are
+//     fetched, so weight traffic is 1 KB per sample from L2, nothing from HBM (the whole flow is 2.1 MB).
+//   * the A operand goes registers -> TMEM (tcgen05.st) and is consumed by the TS form of tcgen05.mma: at 4 bytes per
+//     TF32 element, writing and re-reading a 64 KB A tile through shared memory costs as many smem cycles as the MMA
+//     takes tensor cycles.
 // TF32 operands: sample() and log_prob() evaluate the SAME deterministic network (same kernel, same rounding), so
 // the log-density returned for a sample is the exact density of the map that produced it — importance weights stay
 // exact whatever the operand precision; only the agreement with an fp32 evaluation of the weights is ~1e-3.
@@ -25,12 +28,19 @@ namespace glabc {
 
 constexpr int kFlowHidden = 128;
 constexpr int kFlowTile = 128;
-constexpr int kFlowTilesPerCta = 8;
+// experiment switches (profiles/r1_k4_flow_ncu.md): -DGLABC_FLOW_TILES=n, -DGLABC_FLOW_SKIP_{L1,MMA,EPI} time the phases
+#ifndef GLABC_FLOW_TILES
+#define GLABC_FLOW_TILES 16
+#endif
+constexpr int kFlowTilesPerCta = GLABC_FLOW_TILES;
 constexpr int kFlowW2Bytes = kFlowHidden * kFlowHidden * 4;           // 64 KB per block
 constexpr int kFlowVecFloats = 768;                                  // w1, b1, b2 [128], w3 [2][128], b3 [2] (+pad)
-constexpr int kFlowGroups = 2;                                        // two 128-thread groups, one tile in flight each
-constexpr int kFlowThreads = kFlowGroups * kFlowTile;
-constexpr int kFlowSmemBytes = (1 + kFlowGroups) * kFlowW2Bytes + kFlowVecFloats * 4 + 3 * kFlowTilesPerCta * kFlowTile * 4 + 64;
+constexpr int kFlowGroups = 2;                                        // two groups, one tile in flight each
+constexpr int kFlowGroupThreads = 2 * kFlowTile;                      // two threads per sample row (half the hidden units each)
+constexpr int kFlowThreads = kFlowGroups * kFlowGroupThreads;         // 512: four warps per scheduler
+constexpr int kFlowSmemBytes = kFlowW2Bytes + kFlowVecFloats * 4 + 3 * kFlowTilesPerCta * kFlowTile * 4 +
+                               kFlowGroups * kFlowTile * 8 + 64;   // W2 of the block, vectors, states, partial sums, barriers
+constexpr uint32_t kFlowTmemCols = 512;                                // per group: 128 accumulator + 128 A-operand columns
 
 struct FlowDev {
     const float* w1;   // [L][128]
@@ -116,6 +126,33 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        :
+        : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+          "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]),
+          "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
+          "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+
+// D[tmem] (+)= A[tmem] * B[smem]^T: the A operand (row i = TMEM lane i, 8 TF32 values = 8 columns per MMA) never touches
+// shared memory — at 4 bytes per element the smem pipe (A write + A read + B read) would otherwise bound the kernel
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 __device__ __forceinline__ float to_tf32(float x)
 {
     uint32_t r;
@@ -140,33 +177,38 @@ static __global__ void __launch_bounds__(256) k_flow_pack(const float* __restric
 
 __device__ __forceinline__ void group_sync(int group)
 {
-    asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(kFlowTile) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(kFlowGroupThreads) : "memory");
 }
 
 // SAMPLE: in = eps [n][2] standard normals -> theta [n][2], log q [n]       (NormalizingFlow.sample)
 // !SAMPLE: in = theta [n][2] -> log q [n]                                     (NormalizingFlow.log_prob)
-// 256 threads = two groups of 128; each group owns its own A buffer, TMEM accumulator (128 columns) and mbarrier and
-// walks its tiles independently, so the MMA of one group's tile overlaps the CUDA-core phases (layer 1, epilogue) of the
-// other's, and every scheduler holds two warps.
+// 512 threads = two groups of 256.  A group owns one tile of 128 samples at a time with its own A buffer, TMEM
+// accumulator (128 columns) and mbarrier, so the MMA of one group's tile overlaps the CUDA-core phases of the other's.
+// Inside a group TWO threads serve each sample row — warps w and w+4 may both read TMEM lanes 32(w%4).., so thread
+// (row, half) computes hidden units [64 half, 64 half + 64) of layer 1 and reduces the same 64 accumulator columns in
+// the epilogue; the two partial (shift, log-scale) sums meet in shared memory.  Four warps per scheduler instead of two.
 template <bool SAMPLE>
 __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant__ FlowDev W, const float* __restrict__ in,
                                                           int64_t n, float* __restrict__ out_theta, float* __restrict__ out_lq)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     float* sB = reinterpret_cast<float*>(smem);
-    float* sVec = reinterpret_cast<float*>(smem + (1 + kFlowGroups) * kFlowW2Bytes);
+    float* sVec = reinterpret_cast<float*>(smem + kFlowW2Bytes);
     float* sState = sVec + kFlowVecFloats;  // [3][tiles][128]: z1, z2, log q
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sState + 3 * kFlowTilesPerCta * kFlowTile);
+    float2* sPart = reinterpret_cast<float2*>(sState + 3 * kFlowTilesPerCta * kFlowTile);  // [groups][128] partial sums of half 1
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sPart + kFlowGroups * kFlowTile);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + kFlowGroups);
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int group = tid >> 7, gtid = tid & (kFlowTile - 1), gwarp = gtid >> 5;
-    float* sA = reinterpret_cast<float*>(smem + (1 + group) * kFlowW2Bytes);
+    const int group = tid / kFlowGroupThreads, gtid = tid % kFlowGroupThreads;
+    const int half = gtid >> 7, row = gtid & (kFlowTile - 1), quad = (gtid >> 5) & 3;
+    float2* part = sPart + group * kFlowTile;
     const uint32_t bar_w = smem_u32(&bars[0]), bar_m = smem_u32(&bars[1 + group]);
     constexpr int TS = kFlowTilesPerCta * kFlowTile;
+    constexpr int HK = kFlowHidden / 2;  // hidden units per thread
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"(static_cast<uint32_t>(kFlowGroups * 128))
+                     "r"(kFlowTmemCols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -177,10 +219,11 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot + static_cast<uint32_t>(group * 128);  // this group's accumulator columns
+    const uint32_t tmem = *tmem_slot + static_cast<uint32_t>(group * 256);  // this group's accumulator columns
+    const uint32_t tmem_a = tmem + 128u;                                    // and its A-operand columns
     // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128 (cute::UMMA::InstrDescriptor bit layout)
     constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-    const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+    const uint32_t sB_addr = smem_u32(sB);
     uint32_t ph_w = 0, ph_m = 0;
     const float c2 = -1.8378770664093453f;  // -0.5 * 2 * log(2 pi)
     const int L = W.n_blocks;
@@ -190,8 +233,8 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
         int tiles = 0;
         for (int t = 0; t < kFlowTilesPerCta; ++t) {
             if ((chunk * kFlowTilesPerCta + t) * kFlowTile < n) tiles = t + 1;
-            if ((t & 1) != group) continue;  // a tile's state is only ever touched by its own group
-            const int64_t idx = (chunk * kFlowTilesPerCta + t) * kFlowTile + gtid;
+            if ((t & 1) != group || half != 0) continue;  // a tile's state is written by half 0 of its own group only
+            const int64_t idx = (chunk * kFlowTilesPerCta + t) * kFlowTile + row;
             float a = 0.0f, b = 0.0f, lq = 0.0f;
             if (idx < n) {
                 a = in[idx * 2];
@@ -202,13 +245,13 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
                     b = W.base_loc[1] + expf(W.base_log_scale[1]) * b;
                 }
             }
-            sState[0 * TS + t * kFlowTile + gtid] = a;
-            sState[1 * TS + t * kFlowTile + gtid] = b;
-            sState[2 * TS + t * kFlowTile + gtid] = lq;
+            sState[0 * TS + t * kFlowTile + row] = a;
+            sState[1 * TS + t * kFlowTile + row] = b;
+            sState[2 * TS + t * kFlowTile + row] = lq;
         }
         for (int li = 0; li < L; ++li) {
             const int l = SAMPLE ? li : L - 1 - li;
-            __syncthreads();  // both groups are done with the previous block's W2 / vectors (their MMAs were waited for)
+            __syncthreads();  // both groups are done with the previous block's W2 / vectors / state updates
             if (tid == 0) {
                 mbar_expect_tx(bar_w, kFlowW2Bytes);
 #pragma unroll
@@ -216,68 +259,78 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
                     bulk_g2s(sB_addr + q * (kFlowW2Bytes / 4), reinterpret_cast<const uint8_t*>(W.w2p) +
                              static_cast<int64_t>(l) * kFlowW2Bytes + q * (kFlowW2Bytes / 4), kFlowW2Bytes / 4, bar_w);
             }
-            if (tid < kFlowHidden) {
-                sVec[tid] = W.w1[l * kFlowHidden + tid];
-                sVec[128 + tid] = W.b1[l * kFlowHidden + tid];
-                sVec[256 + tid] = W.b2[l * kFlowHidden + tid];
-            } else {
-                const int u = tid - kFlowHidden;
-                sVec[384 + u] = W.w3[(l * 2 + 0) * kFlowHidden + u];
-                sVec[512 + u] = W.w3[(l * 2 + 1) * kFlowHidden + u];
-                if (u < 2) sVec[640 + u] = W.b3[l * 2 + u];
-            }
+            if (tid < 128) sVec[tid] = W.w1[l * kFlowHidden + tid];
+            else if (tid < 256) sVec[tid] = W.b1[l * kFlowHidden + tid - 128];
+            else if (tid < 384) sVec[tid] = W.b2[l * kFlowHidden + tid - 256];
+            else sVec[tid] = W.w3[(l * 2) * kFlowHidden + tid - 384];  // w3 rows 0 and 1 are contiguous: [384, 640)
+            if (tid < 128) sVec[512 + tid] = W.w3[(l * 2 + 1) * kFlowHidden + tid];
+            if (tid < 2) sVec[640 + tid] = W.b3[l * 2 + tid];
             __syncthreads();
             mbar_wait(bar_w, ph_w);
             ph_w ^= 1u;
 
             for (int t = group; t < tiles; t += kFlowGroups) {
-                float z1 = sState[0 * TS + t * kFlowTile + gtid], z2 = sState[1 * TS + t * kFlowTile + gtid];
+                float z1 = sState[0 * TS + t * kFlowTile + row], z2 = sState[1 * TS + t * kFlowTile + row];
                 if (!SAMPLE) {  // Permute(swap)^-1 precedes the coupling's inverse
                     const float tmp = z1;
                     z1 = z2;
                     z2 = tmp;
                 }
-                // ---- layer 1 (K = 1) on CUDA cores, written as the A operand ----
-                uint8_t* rowp = reinterpret_cast<uint8_t*>(sA) + (gtid >> 3) * 4096 + (gtid & 7) * 16;
-#pragma unroll 8
-                for (int kc = 0; kc < kFlowHidden / 4; ++kc) {
-                    const float4 w = *reinterpret_cast<const float4*>(&sVec[kc * 4]);
-                    const float4 bb = *reinterpret_cast<const float4*>(&sVec[128 + kc * 4]);
-                    float4 h;
-                    h.x = round_tf32_nonneg(fmaxf(fmaf(w.x, z1, bb.x), 0.0f));
-                    h.y = round_tf32_nonneg(fmaxf(fmaf(w.y, z1, bb.y), 0.0f));
-                    h.z = round_tf32_nonneg(fmaxf(fmaf(w.z, z1, bb.z), 0.0f));
-                    h.w = round_tf32_nonneg(fmaxf(fmaf(w.w, z1, bb.w), 0.0f));
-                    *reinterpret_cast<float4*>(rowp + kc * 128) = h;
+                // ---- layer 1 (K = 1) on CUDA cores, written as the A operand into TMEM: this thread's 64 hidden units ----
+#ifdef GLABC_FLOW_SKIP_L1
+                if (z1 == 123.456f)
+#endif
+#pragma unroll
+                for (int cb = 0; cb < HK / 32; ++cb) {
+                    uint32_t hv[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 w = *reinterpret_cast<const float4*>(&sVec[half * HK + cb * 32 + j]);
+                        const float4 bb = *reinterpret_cast<const float4*>(&sVec[128 + half * HK + cb * 32 + j]);
+                        hv[j] = __float_as_uint(round_tf32_nonneg(fmaxf(fmaf(w.x, z1, bb.x), 0.0f)));
+                        hv[j + 1] = __float_as_uint(round_tf32_nonneg(fmaxf(fmaf(w.y, z1, bb.y), 0.0f)));
+                        hv[j + 2] = __float_as_uint(round_tf32_nonneg(fmaxf(fmaf(w.z, z1, bb.z), 0.0f)));
+                        hv[j + 3] = __float_as_uint(round_tf32_nonneg(fmaxf(fmaf(w.w, z1, bb.w), 0.0f)));
+                    }
+                    tmem_st32(tmem_a + (static_cast<uint32_t>(quad * 32) << 16) + half * HK + cb * 32, hv);
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
-                group_sync(group);
+                group_sync(group);  // (also: half 0 has consumed the previous tile's partial sums)
                 // ---- layer 2 (128 x 128 x 128) on the tensor cores ----
+#ifdef GLABC_FLOW_SKIP_MMA
+                if (gtid == 0 && z1 == 123.456f) {
+#else
                 if (gtid == 0) {
+#endif
                     tc_fence_after();
 #pragma unroll
                     for (int k = 0; k < kFlowHidden / 8; ++k) {
-                        const uint64_t ad = umma_desc(sA_addr + k * 256, 128, 4096);
                         const uint64_t bd = umma_desc(sB_addr + k * 256, 128, 4096);
-                        umma_tf32(tmem, ad, bd, idesc, k > 0 ? 1u : 0u);
+                        umma_tf32_ts(tmem, tmem_a + k * 8, bd, idesc, k > 0 ? 1u : 0u);
                     }
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_m) : "memory");
                 }
+#ifndef GLABC_FLOW_SKIP_MMA
                 mbar_wait(bar_m, ph_m);
                 ph_m ^= 1u;
+#endif
                 tc_fence_after();
-                // ---- bias + ReLU + layer 3 (N = 2) from TMEM; four independent partial sums per output ----
+                // ---- bias + ReLU + layer 3 (N = 2) from TMEM: this thread's 64 columns, four independent partial sums ----
                 float p0[4] = {0.0f, 0.0f, 0.0f, 0.0f}, p1[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#ifdef GLABC_FLOW_SKIP_EPI
+                if (z1 == 123.456f)
+#endif
 #pragma unroll
-                for (int cb = 0; cb < 4; ++cb) {
+                for (int cb = 0; cb < 2; ++cb) {
                     uint32_t v[32];
-                    tmem_ld32(tmem + (static_cast<uint32_t>(gwarp * 32) << 16) + cb * 32, v);
+                    const int col0 = half * HK + cb * 32;
+                    tmem_ld32(tmem + (static_cast<uint32_t>(quad * 32) << 16) + col0, v);
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {  // broadcast LDS.128 of b2 / W3 rows: 3 loads per 4 columns
-                        const float4 b2v = *reinterpret_cast<const float4*>(&sVec[256 + cb * 32 + j]);
-                        const float4 wa = *reinterpret_cast<const float4*>(&sVec[384 + cb * 32 + j]);
-                        const float4 wb = *reinterpret_cast<const float4*>(&sVec[512 + cb * 32 + j]);
+                        const float4 b2v = *reinterpret_cast<const float4*>(&sVec[256 + col0 + j]);
+                        const float4 wa = *reinterpret_cast<const float4*>(&sVec[384 + col0 + j]);
+                        const float4 wb = *reinterpret_cast<const float4*>(&sVec[512 + col0 + j]);
                         const float h0 = fmaxf(__uint_as_float(v[j]) + b2v.x, 0.0f), h1 = fmaxf(__uint_as_float(v[j + 1]) + b2v.y, 0.0f);
                         const float h2 = fmaxf(__uint_as_float(v[j + 2]) + b2v.z, 0.0f), h3 = fmaxf(__uint_as_float(v[j + 3]) + b2v.w, 0.0f);
                         p0[0] = fmaf(wa.x, h0, p0[0]); p1[0] = fmaf(wb.x, h0, p1[0]);
@@ -286,30 +339,37 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
                         p0[3] = fmaf(wa.w, h3, p0[3]); p1[3] = fmaf(wb.w, h3, p1[3]);
                     }
                 }
-                const float sh = ((p0[0] + p0[1]) + (p0[2] + p0[3])) + sVec[640];  // shift     = param[:, 0::2]
-                const float sc = ((p1[0] + p1[1]) + (p1[2] + p1[3])) + sVec[641];  // log-scale = param[:, 1::2]
-                float lq = sState[2 * TS + t * kFlowTile + gtid];
-                if (SAMPLE) {
-                    const float z2n = fmaf(z2, expf(sc), sh);  // z2 * exp(s) + shift; log q -= log det
-                    lq -= sc;
-                    sState[0 * TS + t * kFlowTile + gtid] = z2n;  // Permute(swap)
-                    sState[1 * TS + t * kFlowTile + gtid] = z1;
-                } else {
-                    const float z2n = (z2 - sh) * expf(-sc);     // inverse; log det = -s
-                    lq -= sc;
-                    sState[0 * TS + t * kFlowTile + gtid] = z1;
-                    sState[1 * TS + t * kFlowTile + gtid] = z2n;
-                }
-                sState[2 * TS + t * kFlowTile + gtid] = lq;
+                const float s0 = (p0[0] + p0[1]) + (p0[2] + p0[3]), s1 = (p1[0] + p1[1]) + (p1[2] + p1[3]);
+                if (half == 1) part[row] = make_float2(s0, s1);
                 tc_fence_before();
-                group_sync(group);  // this group's TMEM columns and A buffer are free for its next tile
+                group_sync(group);  // TMEM columns and the A buffer are free for the group's next tile; partial sums visible
+                if (half == 0) {
+                    const float2 o = part[row];
+                    const float sh = (s0 + o.x) + sVec[640];  // shift     = param[:, 0::2]
+                    const float sc = (s1 + o.y) + sVec[641];  // log-scale = param[:, 1::2]
+                    float lq = sState[2 * TS + t * kFlowTile + row];
+                    if (SAMPLE) {
+                        const float z2n = fmaf(z2, expf(sc), sh);  // z2 * exp(s) + shift; log q -= log det
+                        lq -= sc;
+                        sState[0 * TS + t * kFlowTile + row] = z2n;  // Permute(swap)
+                        sState[1 * TS + t * kFlowTile + row] = z1;
+                    } else {
+                        const float z2n = (z2 - sh) * expf(-sc);     // inverse; log det = -s
+                        lq -= sc;
+                        sState[0 * TS + t * kFlowTile + row] = z1;
+                        sState[1 * TS + t * kFlowTile + row] = z2n;
+                    }
+                    sState[2 * TS + t * kFlowTile + row] = lq;
+                }
             }
         }
+        __syncthreads();
         for (int t = group; t < tiles; t += kFlowGroups) {
-            const int64_t idx = (chunk * kFlowTilesPerCta + t) * kFlowTile + gtid;
+            if (half != 0) continue;
+            const int64_t idx = (chunk * kFlowTilesPerCta + t) * kFlowTile + row;
             if (idx >= n) continue;
-            const float a = sState[0 * TS + t * kFlowTile + gtid], b = sState[1 * TS + t * kFlowTile + gtid];
-            float lq = sState[2 * TS + t * kFlowTile + gtid];
+            const float a = sState[0 * TS + t * kFlowTile + row], b = sState[1 * TS + t * kFlowTile + row];
+            float lq = sState[2 * TS + t * kFlowTile + row];
             if (SAMPLE) {
                 out_theta[idx * 2] = a;
                 out_theta[idx * 2 + 1] = b;
@@ -324,7 +384,7 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
     tc_fence_before();
     __syncthreads();
     if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"(static_cast<uint32_t>(kFlowGroups * 128))
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"(kFlowTmemCols)
                      : "memory");
 }
 
