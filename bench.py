@@ -194,7 +194,7 @@ def bench_reference(a, rank):
             "cpu_baseline": {"value": value, "unit": "chain-steps/s", "cores": port.cores, "kind": "port", "sample": sample,
                              "esjd": {"mean_per_chain": port.mean_esjd, "aggregate_esjd_per_sec": port.mean_esjd * value}},
             "e2e": {"value": value, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def bench_kde(a, rank, world, local_rank):
@@ -314,7 +314,7 @@ def bench_kde(a, rank, world, local_rank):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
 
 
 def other_kernels(eng, model, lp, gp):
@@ -371,13 +371,36 @@ def workload_config(a):
 
 
 def main():
+    # stdout carries exactly ONE JSON line: libraries that chat on fd 1 (NCCL's version banner, ...) are sent to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        _main()
+    finally:
+        sys.stdout.flush()
+        os.dup2(json_fd, 1)
+        os.close(json_fd)
+        if _RESULT:
+            print(_RESULT[-1], flush=True)
+
+
+_RESULT = []
+
+
+def emit(line):
+    _RESULT.append(json.dumps(line))
+
+
+def _main():
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if a.sampler == "kde":
         if a.impl == "reference":
-            print(json.dumps({"impl": "reference", "unavailable": "--sampler kde has no reference arm; see cpu_baseline of the native line"}))
+            if rank == 0:
+                emit({"impl": "reference", "unavailable": "--sampler kde has no reference arm; see cpu_baseline of the native line"})
             return
         bench_kde(a, rank, world, local_rank)
         return
@@ -628,7 +651,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
 
 
 if __name__ == "__main__":
