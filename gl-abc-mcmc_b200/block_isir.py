@@ -1,0 +1,110 @@
+"""Host driver of the block-iSIR samplers whose importance proposal is SHARED by all chains: GLMCMC-NFs (one RealNVP,
+GLMCMC_NFs.py:90-152) and pooled AGLMCMC (one KernelDensity over the pooled training draws, AGLMCMC.py:124-272).
+
+The chain step is the fused kernel `k_ag_step<EXT>` (csrc/step_aglmcmc.cuh) behind `glabc_run_block_isir`: a chain pauses
+when its block of batch_size * step_size candidates is consumed or when the proposal log-density of a changed state is
+needed.  This loop refreshes those log-densities in one batched launch of the proposal's kernel and, when every chain of
+the rank has consumed its block, lets the proposal adapt (train / refit — the only place ranks exchange data) and refills.
+
+A proposal object provides
+    fill(blk_theta [C,B,d], blk_lq [C,B], round)   fresh candidates and their log-densities (kernels)
+    log_prob(theta [n,d]) -> [n]                    proposal log-density of the given states (kernel)
+    adapt(block) -> None                            end-of-block training; may run collectives, every rank calls it
+"""
+import torch
+
+from . import _abi
+from .engine import RunStats
+from .pooled import RoundSync, _world
+from .samplers import _ARITH, _LAYOUT, print_summary, write_csv
+
+
+class Block:
+    """a rank's candidate blocks and per-chain counters (glabc_block_isir_t, include/glabc.h)"""
+
+    def __init__(self, c, K, S, d, yd, dev):
+        B = K * S
+        self.c, self.K, self.S, self.B, self.d = c, K, S, B, d
+        self.theta = torch.empty(c, B, d, device=dev)
+        self.x = torch.empty(c, B, yd, device=dev)
+        self.w = torch.empty(c, B, device=dev)
+        self.lq = torch.empty(c, B, device=dev)
+        self.kk = torch.zeros(c, dtype=torch.int32, device=dev)
+        self.pending = torch.zeros_like(self.kk)
+        self.lq_valid = torch.zeros_like(self.kk)
+        self.next_step = torch.ones(c, dtype=torch.int32, device=dev)
+        self.lq_cur = torch.zeros(c, device=dev)
+        self.pod = _abi.BlockIsirPOD(step_size=S, block=B, blk_theta=self.theta.data_ptr(), blk_x=self.x.data_ptr(),
+                                     blk_w=self.w.data_ptr(), blk_lq=self.lq.data_ptr(), kk=self.kk.data_ptr(),
+                                     pending=self.pending.data_ptr(), next_step=self.next_step.data_ptr(),
+                                     lq_cur=self.lq_cur.data_ptr(), lq_valid=self.lq_valid.data_ptr())
+
+
+def run_block_isir(eng, pod, proposal, *, num_ite, theta, y, K, S, gf, seed, chain_id_base, arith, trace, single,
+                   filelocation, verbose, max_adapt=None):
+    """Advance every chain by num_ite - 1 iterations.  Returns (result, RunStats, rounds)."""
+    c, d = theta.shape
+    dev = eng.device
+    blk = Block(c, K, S, d, pod.y_dim, dev)
+    common = dict(theta=theta, y=y, gf=gf, seed=seed, chain_id_base=chain_id_base, K=K, blk=blk.pod)
+
+    def refill(rnd):    # GLMCMC_NFs.py:70-85,125-140 / AGLMCMC.py:84-112,219-249
+        proposal.fill(blk.theta, blk.lq, rnd)
+        eng.run("block_weights", n_steps=0, step_base=rnd, trace_layout=_abi.TRACE_NONE, **common)
+
+    def refresh_lq(idx=None):   # proposal.log_prob(Theta_old), GLMCMC_NFs.py:96-98 / AGLMCMC.py:137-140, where the state changed
+        if idx is None:
+            blk.lq_cur.copy_(proposal.log_prob(theta))
+            blk.lq_valid.fill_(1)
+        else:
+            blk.lq_cur[idx] = proposal.log_prob(theta[idx])
+            blk.lq_valid[idx] = 1
+
+    refill(0)
+    refresh_lq()
+    layout = _LAYOUT[trace]
+    n_steps = num_ite - 1
+    out = None
+    if layout != _abi.TRACE_NONE:
+        out = torch.empty((num_ite, c, d) if layout == _abi.TRACE_TIME_MAJOR else (c, num_ite, d), device=dev)
+    stats = torch.zeros(c, _abi.nstats(d), device=dev)
+    world = _world()[1]
+    sync = RoundSync(dev)
+    rnd, first, n_adapt = 0, True, 0
+    while True:
+        eng.run("block_isir", n_steps=n_steps, arith=_ARITH[arith], trace_layout=layout, trace=out, trace_rows=num_ite,
+                write_row0=first, stats=stats, **common)
+        first = False
+        need = (blk.pending & 2) != 0
+        settled = (blk.next_step > n_steps) | ((blk.pending & 1) != 0)
+        n_need, n_done, n_settled = torch.stack([need.sum(), (blk.next_step > n_steps).sum(), settled.sum()]).tolist()
+        if n_need:
+            refresh_lq(need.nonzero().squeeze(1))
+        if world == 1 and n_done == c:
+            break
+        if n_need == 0 and n_settled == c:      # every chain of this rank consumed its block (GLMCMC_NFs.py:111)
+            if world > 1 and sync.round_end(n_done == c):
+                break
+            if max_adapt is None or n_adapt < max_adapt:
+                proposal.adapt(blk)
+                n_adapt += 1
+            if n_done < c:
+                rnd += 1
+                refill(rnd)
+                refresh_lq()
+                blk.kk.zero_()
+                blk.pending.zero_()
+    rs = RunStats(stats, d)
+    if single:
+        chain = (out[0] if layout == _abi.TRACE_CHAIN_MAJOR else out[:, 0]).cpu() if out is not None else None
+        if filelocation is not None and chain is not None:
+            write_csv(filelocation, chain)
+        if verbose is not False and chain is not None:
+            print_summary(chain)
+        result = chain
+    else:
+        if filelocation is not None and out is not None:
+            import numpy as np
+            np.save(filelocation if str(filelocation).endswith(".npy") else str(filelocation) + ".npy", out.cpu().numpy())
+        result = out
+    return result, rs, rnd

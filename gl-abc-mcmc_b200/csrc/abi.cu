@@ -36,6 +36,8 @@ struct glabc_ctx {
     int ag_dim = 0;
     double* kde_cdf = nullptr;
     size_t kde_cdf_cap = 0;
+    float* kde_part = nullptr;   // partial sums of the point-split log_prob
+    size_t kde_part_cap = 0;
     // RealNVP flow weights (device copies owned by the context)
     float* flow_mem = nullptr;
     size_t flow_floats = 0;
@@ -118,6 +120,7 @@ int glabc_ctx_destroy(glabc_ctx* ctx)
     if (ctx->d_state64) cudaFree(ctx->d_state64);
     if (ctx->ag_mem) cudaFree(ctx->ag_mem);
     if (ctx->kde_cdf) cudaFree(ctx->kde_cdf);
+    if (ctx->kde_part) cudaFree(ctx->kde_part);
     if (ctx->flow_mem) cudaFree(ctx->flow_mem);
     for (int b = 0; b < 2; ++b) {
         if (ctx->d_trace[b]) cudaFree(ctx->d_trace[b]);
@@ -732,7 +735,19 @@ extern "C" int glabc_kde_log_prob(glabc_ctx* ctx, const float* X, const float* w
     if (arith != GLABC_ARITH_FAST && arith != GLABC_ARITH_STRICT) return fail(ctx, GLABC_ERR_INVALID, "bad arith_mode %d", arith);
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     KdeSets S{X, weights, bw, n, nullptr, sets, cap};
-    CUDA_TRY(ctx, launch_kde_logprob(S, nullptr, dim, x, m, out, arith == GLABC_ARITH_STRICT, static_cast<cudaStream_t>(stream)));
+    const int ksplit = arith == GLABC_ARITH_STRICT ? 1 : kde_logprob_split(sets, m, cap);
+    if (ksplit > 1) {
+        const size_t need = size_t(ksplit) * size_t(sets) * size_t(m);
+        if (need > ctx->kde_part_cap) {
+            if (ctx->kde_part) cudaFree(ctx->kde_part);
+            ctx->kde_part = nullptr;
+            ctx->kde_part_cap = 0;
+            CUDA_TRY(ctx, cudaMalloc(&ctx->kde_part, need * sizeof(float)));
+            ctx->kde_part_cap = need;
+        }
+    }
+    CUDA_TRY(ctx, launch_kde_logprob(S, nullptr, dim, x, m, out, arith == GLABC_ARITH_STRICT, static_cast<cudaStream_t>(stream), ksplit,
+                                     ctx->kde_part));
     return GLABC_OK;
 }
 

@@ -191,6 +191,40 @@ __device__ __forceinline__ float warp_logsumexp(float v)
     return m + logf(e);
 }
 
+// packed FP32 pairs (PTX f32x2, sm_100+): one FADD2 / FMUL2 / FFMA2 issue slot does two lanes' worth of work
+using f32x2 = unsigned long long;
+__device__ __forceinline__ f32x2 pack2(float a, float b)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
 constexpr int kKdeTile = 1024;     // training points per shared-memory tile
 constexpr int kKdeThreads = 128;
 
@@ -198,13 +232,22 @@ constexpr int kKdeThreads = 128;
 template <int D, int Q, bool STRICT>
 __global__ void __launch_bounds__(kKdeThreads) k_kde_logprob(KdeSets S, const float* __restrict__ lw_in,
                                                              const float* __restrict__ x, int64_t m, int64_t qtiles,
-                                                             float* __restrict__ out)
+                                                             float* __restrict__ out, int ksplit = 1,
+                                                             float* __restrict__ partial = nullptr)
 {
+    // ksplit > 1 (FAST only): grid.x = sets * qtiles * ksplit, CTA (.., ks) sums the point tiles ks, ks + ksplit, ... and
+    // stores its partial sum to partial[ks][set][q]; k_kde_logprob_finish adds them in a fixed order (a small query
+    // batch then still fills every SM)
     // tile: FAST [kKdeTile][D + 1] = scaled coordinates + log2-weight; STRICT [kKdeTile][D + 1] = raw + log-weight
-    __shared__ __align__(16) float tile[kKdeTile * (D + 1 + ((D + 1) & 1))];
-    constexpr int P = D + 1 + ((D + 1) & 1);  // padded row: 4 floats for d = 2,3; 2 for d = 1; 6 for d = 4 (8-byte aligned)
-    const int64_t set = blockIdx.x / qtiles;
-    const int64_t qt = blockIdx.x - set * qtiles;
+    //       FAST rows hold a PAIR of points, component-interleaved: (x0_a, x0_b, x1_a, x1_b, ..., lw_a, lw_b), pitch PP
+    constexpr int P = D + 1 + ((D + 1) & 1);  // STRICT row: 4 floats for d = 2,3; 2 for d = 1; 6 for d = 4 (8-byte aligned)
+    constexpr int PP = (2 * (D + 1) + 3) & ~3;  // FAST pair row, 16-byte aligned: 4 / 8 / 8 / 12 floats for d = 1..4
+    constexpr int kTileFloats = (kKdeTile * P > (kKdeTile / 2) * PP) ? kKdeTile * P : (kKdeTile / 2) * PP;
+    __shared__ __align__(16) float tile[kTileFloats];
+    const int ks = STRICT ? 0 : static_cast<int>(blockIdx.x % ksplit);
+    const int64_t bq = STRICT ? blockIdx.x : blockIdx.x / ksplit;
+    const int64_t set = bq / qtiles;
+    const int64_t qt = bq - set * qtiles;
     if (S.active != nullptr && S.active[set] == 0) return;
     const int n = S.n != nullptr ? S.n[set] : static_cast<int>(S.cap);
     const float* Xs = S.X + set * S.cap * D;
@@ -229,24 +272,31 @@ __global__ void __launch_bounds__(kKdeThreads) k_kde_logprob(KdeSets S, const fl
     }
 
     float acc[Q], mx[Q];
+    f32x2 acc2[Q];   // FAST: partial sums over even / odd points
 #pragma unroll
     for (int u = 0; u < Q; ++u) {
         acc[u] = 0.0f;
         mx[u] = -INFINITY;
+        acc2[u] = pack2(0.0f, 0.0f);
     }
     const int passes = STRICT ? 2 : 1;
+    const int tstep = STRICT ? kKdeTile : kKdeTile * ksplit;
     for (int pass = 0; pass < passes; ++pass) {
-        for (int t0 = 0; t0 < n; t0 += kKdeTile) {
+        for (int t0 = ks * kKdeTile; t0 < n; t0 += tstep) {
             const int tn = min(kKdeTile, n - t0);
             __syncthreads();
-            for (int j = threadIdx.x; j < tn; j += kKdeThreads) {
-                const float lwj = lws != nullptr ? lws[t0 + j] : logf(__fadd_rn(ws[t0 + j], 1e-10f));  // :124
+            for (int j = threadIdx.x; j < ((tn + 1) & ~1); j += kKdeThreads) {
+                const bool real = j < tn;   // FAST pads an odd tile with a point of weight exp2(-inf) = 0
+                const float lwj = !real ? -INFINITY : lws != nullptr ? lws[t0 + j] : logf(__fadd_rn(ws[t0 + j], 1e-10f));  // :124
+                if (STRICT && !real) continue;
 #pragma unroll
                 for (int i = 0; i < D; ++i) {
-                    const float v = Xs[static_cast<int64_t>(t0 + j) * D + i];
-                    tile[j * P + i] = STRICT ? v : v * kc.inv_bw[i];
+                    const float v = real ? Xs[static_cast<int64_t>(t0 + j) * D + i] : 0.0f;
+                    if constexpr (STRICT) tile[j * P + i] = v;
+                    else tile[(j >> 1) * PP + 2 * i + (j & 1)] = v * kc.inv_bw[i];
                 }
-                tile[j * P + D] = STRICT ? lwj : lwj * kLog2e;
+                if constexpr (STRICT) tile[j * P + D] = lwj;
+                else tile[(j >> 1) * PP + 2 * D + (j & 1)] = lwj * kLog2e;
             }
             __syncthreads();
             if constexpr (STRICT) {
@@ -261,30 +311,42 @@ __global__ void __launch_bounds__(kKdeThreads) k_kde_logprob(KdeSets S, const fl
             } else {
                 // exp2(lw2_j - 0.5*log2e*|xs - Xs_j|^2): every term <= 1 because the weights are normalised,
                 // so the fixed shift M0 = -c - slog needs no running maximum
+                // two training points per 64-bit register pair: FADD2 / FMUL2 / FFMA2 (sm_100 packed FP32) halve the issue
+                // slots of the distance + exponent arithmetic, leaving MUFU.EX2 (16 / clk / SM) as the bound
+                const f32x2 kk = pack2(-0.5f * kLog2e, -0.5f * kLog2e);
+                const int np = (tn + 1) >> 1;
 #pragma unroll 4
-                for (int j = 0; j < tn; ++j) {
-                    float p[P];
-                    if constexpr (P == 4) {
-                        const float4 v = *reinterpret_cast<const float4*>(&tile[j * P]);
-                        p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w;
+                for (int j = 0; j < np; ++j) {
+                    f32x2 p[D + 1];
+                    const float* row = &tile[j * PP];
+                    if constexpr (D == 1) {
+                        const float4 v = *reinterpret_cast<const float4*>(row);
+                        p[0] = pack2(v.x, v.y); p[1] = pack2(v.z, v.w);
                     } else {
 #pragma unroll
-                        for (int i = 0; i < P; i += 2) {
-                            const float2 v = *reinterpret_cast<const float2*>(&tile[j * P + i]);
-                            p[i] = v.x; p[i + 1] = v.y;
+                        for (int i = 0; i + 1 < D + 1; i += 2) {
+                            const float4 v = *reinterpret_cast<const float4*>(row + 2 * i);
+                            p[i] = pack2(v.x, v.y); p[i + 1] = pack2(v.z, v.w);
+                        }
+                        if constexpr ((D + 1) & 1) {
+                            const float2 v = *reinterpret_cast<const float2*>(row + 2 * D);
+                            p[D] = pack2(v.x, v.y);
                         }
                     }
 #pragma unroll
                     for (int u = 0; u < Q; ++u) {
-                        float s2 = 0.0f;
+                        f32x2 df = sub2(pack2(xq[u][0], xq[u][0]), p[0]);
+                        f32x2 s2 = mul2(df, df);
 #pragma unroll
-                        for (int i = 0; i < D; ++i) {
-                            const float df = xq[u][i] - p[i];
-                            s2 = fmaf(df, df, s2);
+                        for (int i = 1; i < D; ++i) {
+                            df = sub2(pack2(xq[u][i], xq[u][i]), p[i]);
+                            s2 = fma2(df, df, s2);
                         }
-                        float e;
-                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(-0.5f * kLog2e, s2, p[D])));
-                        acc[u] += e;
+                        float t0, t1, e0, e1;
+                        unpack2(fma2(s2, kk, p[D]), t0, t1);
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(t0));
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(t1));
+                        acc2[u] = add2(acc2[u], pack2(e0, e1));
                     }
                 }
             }
@@ -293,6 +355,20 @@ __global__ void __launch_bounds__(kKdeThreads) k_kde_logprob(KdeSets S, const fl
 #pragma unroll
             for (int u = 0; u < Q; ++u)
                 if (mx[u] == -INFINITY || mx[u] == INFINITY) mx[u] = 0.0f;  // torch.logsumexp's handling of an infinite max
+        }
+    }
+    if constexpr (!STRICT) {
+#pragma unroll
+        for (int u = 0; u < Q; ++u) {
+            float a, b;
+            unpack2(acc2[u], a, b);
+            acc[u] = a + b;
+        }
+        if (ksplit > 1) {
+#pragma unroll
+            for (int u = 0; u < Q; ++u)
+                if (valid[u]) partial[(static_cast<int64_t>(ks) * S.sets + set) * m + qi[u]] = acc[u];
+            return;
         }
     }
 #pragma unroll
@@ -325,6 +401,47 @@ __global__ void __launch_bounds__(kKdeThreads) k_kde_logprob(KdeSets S, const fl
         }
         out[set * m + qi[u]] = r;
     }
+}
+
+// second half of the point-split log_prob: out[set][q] = log(sum_ks partial[ks][set][q]) - c - slog, with the same
+// max-shifted redo for a query whose terms all underflowed
+template <int D>
+__global__ void __launch_bounds__(256) k_kde_logprob_finish(KdeSets S, const float* __restrict__ lw_in, const float* __restrict__ x,
+                                                            int64_t m, int ksplit, const float* __restrict__ partial,
+                                                            float* __restrict__ out)
+{
+    const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (g >= S.sets * m) return;
+    const int64_t set = g / m;
+    if (S.active != nullptr && S.active[set] == 0) return;
+    float acc = 0.0f;
+    for (int k = 0; k < ksplit; ++k) acc += partial[static_cast<int64_t>(k) * S.sets * m + g];
+    const KdeConst<D> kc = kde_const<D>(S.bw + set * D);
+    float r;
+    if (acc > 1e-30f) {
+        r = fmaf(0.6931471805599453f, lg2_approx(acc), -(kc.c + kc.slog));
+    } else {
+        const int n = S.n != nullptr ? S.n[set] : static_cast<int>(S.cap);
+        const float* Xs = S.X + set * S.cap * D;
+        const float* ws = S.weights + set * S.cap;
+        const float* lws = lw_in != nullptr ? lw_in + set * S.cap : nullptr;
+        float xr[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) xr[i] = x[g * D + i];
+        float mxs = -INFINITY, sum = 0.0f;
+        for (int j = 0; j < n; ++j) {
+            const float lwj = lws != nullptr ? lws[j] : logf(__fadd_rn(ws[j], 1e-10f));
+            const float v = kde_term_strict<D>(kc, xr, Xs + static_cast<int64_t>(j) * D, lwj);
+            if (v > mxs) {
+                sum = sum * expf(mxs - v) + 1.0f;
+                mxs = v;
+            } else {
+                sum += expf(v - mxs);
+            }
+        }
+        r = mxs + logf(sum);
+    }
+    out[g] = r;
 }
 
 // inclusive float64 prefix sums of the normalised weights of every set (native-mode sampling)
@@ -399,8 +516,10 @@ __global__ void __launch_bounds__(256) k_kde_sample(KdeSets S, const double* __r
 // host launchers (kde.cu)
 cudaError_t launch_kde_fit(const float* X, const float* w, const int32_t* n, const int32_t* active, int64_t sets, int64_t cap,
                            int dim, int rule, float* weights_out, float* lw_out, float* bw_out, cudaStream_t st);
+// point-split factor the public entry should use for (sets, m) queries against <= cap points, and the scratch floats it needs
+int kde_logprob_split(int64_t sets, int64_t m, int64_t cap);
 cudaError_t launch_kde_logprob(const KdeSets& S, const float* lw, int dim, const float* x, int64_t m, float* out, bool strict,
-                               cudaStream_t st);
+                               cudaStream_t st, int ksplit = 1, float* partial = nullptr);
 cudaError_t launch_kde_cdf(const float* weights, const int32_t* n, const int32_t* active, int64_t sets, int64_t cap, double* cdf,
                            cudaStream_t st);
 cudaError_t launch_kde_sample(const KdeSets& S, int dim, const double* cdf, int64_t m, const RoundKeys& rk, uint64_t chain_id_base,

@@ -242,3 +242,43 @@ def test_public_api_aglmcmc(eng, tmp_path):
     assert (tmp_path / "aglmcmc_results.csv").exists()
     out = runner.run_aglmcmc(12000, theta0, None, 1, lp, ip, 5, 200, 0.8, 0.2, output_file=None, num_chains=32, seed=4)
     assert out.shape == (32, 12000, 2)   # the reference stops at 10,000 rows
+
+
+def test_aglmcmc_pooled_kde_posterior(eng):
+    """pooled=True: ONE KernelDensity over the pooled weighted draws of all chains (BASELINE config 5) — the sampler must
+    still target the ABC posterior (closed form) and the tolerance must anneal down to eps-hat_T"""
+    from scipy import stats as sst
+    import glabc_b200 as g
+    model = g.Mixture_set(epsilon=0.05)
+    lp = g.DiagGaussian(2, loc=torch.zeros(1, 2), log_scale=torch.log(torch.tensor([0.35, 0.35])))
+    ip = g.DiagGaussian(2, torch.tensor([0.0, 0.0]), torch.tensor([0.0, 0.0]))
+    Cn = 2048
+    out, st, prop = g.AGLMCMC(model, 1501, torch.zeros(2), None, lp, ip, None, 0.9, 50, 5, 0.8, 0.2, num_chains=Cn, seed=3,
+                              trace="none", return_stats=True, pooled=True, kde_train=20000, return_proposal=True)
+    assert out is None and len(prop.history) >= 10
+    eps_hist = [h[0] for h in prop.history]
+    assert all(a >= b for a, b in zip(eps_hist, eps_hist[1:])) and eps_hist[-1] == pytest.approx(0.2)
+    assert prop.history[-1][1] > 15000                    # the pooled training set is (almost) kde_train draws
+    # the adapted proposal concentrates on the four posterior modes: the global acceptance beats the N(0, I) start
+    assert float(st.accepted_global.sum() / st.global_steps.sum()) > 0.03
+    out2 = g.AGLMCMC(model, 1001, torch.zeros(2), None, lp, ip, None, 0.9, 50, 5, 0.8, 0.2, num_chains=Cn, seed=5, trace="time",
+                     pooled=True, kde_train=20000)
+    th = out2[-1].abs().cpu().numpy().astype(np.float64)
+    for i in range(2):
+        assert sst.kstest(th[:, i], sst.norm(1.42518, np.sqrt(0.049881)).cdf).statistic < 0.05
+    quad = ((out2[-1][:, 0] > 0).long() * 2 + (out2[-1][:, 1] > 0).long()).bincount(minlength=4).cpu().numpy() / Cn
+    assert np.abs(quad - 0.25).max() < 0.05
+
+
+def test_kde_logprob_large_batch_paths(eng):
+    """the 1-, 2- and 4-queries-per-thread instantiations of the packed (FFMA2) pair loop agree with the strict kernel,
+    odd point counts included"""
+    g = torch.Generator(device="cuda").manual_seed(2)
+    for n, m in ((999, 700), (1025, 128 * 8 * 148 * 2 + 5), (513, 128 * 8 * 148 * 4 + 3)):
+        X = torch.randn(n, 2, device="cuda", generator=g)
+        w = torch.rand(n, device="cuda", generator=g)
+        wn, bw = eng.kde_fit(X, w)
+        x = torch.randn(m, 2, device="cuda", generator=g) * 1.5
+        fast = eng.kde_log_prob(X, wn, bw, x, arith=abi.ARITH_FAST)
+        strict = eng.kde_log_prob(X, wn, bw, x, arith=abi.ARITH_STRICT)
+        assert float((fast - strict).abs().max()) < 2e-4
