@@ -103,10 +103,184 @@ __device__ __forceinline__ void make_candidate(const IsirConsts& K, const float 
     }
 }
 
+
+// ---- software-pipelined form of the native FAST loop (NKT > 0) --------------------------------------------------
+// Everything of step i + 1 that does not depend on the chain state — the step's Philox blocks, the K candidates, the
+// local proposal's increment and simulator noise, log U — is computed IN REGISTERS in the same straight-line block as
+// the short dependent part of step i (weight of the current state, resample, local MH test, state update), so the
+// scheduler fills the dependent chain's latency holes at 3-4 warps per scheduler.  The candidates' weights stay in
+// registers; the fields a switch needs (theta, x, log-weight, prior + kernel) are parked in a single-buffered
+// shared-memory table AFTER step i has read its own row, which keeps "take candidate ind" one indexed load and the
+// table small enough (7.5 KB per 64 chains) for every CTA of a 65,536-chain launch to be resident at once.
+template <int D, int NK>
+struct IsirStepIn {
+    bool is_global;
+    float log_w;      // log U_a of the local MH test
+    float z_l[D];     // Local_Proposal increment (state-independent)
+    float n_l[D];     // simulator noise of the local candidate
+    double u64;       // resampling uniform
+    float w[NK];      // importance weights of the K candidates
+};
+
+template <int D, int NK>
+struct IsirCands {    // what a switch to candidate j needs
+    float lw[NK], pk[NK], th[NK][D], x[NK][D];
+};
+
+// pipelined table: slot j in [0, K), fields 0 log-weight, 1 prior + kernel, 2.. theta[D], 2+D.. x[D]
+template <int D>
+struct TakeTable {
+    static constexpr int kFields = 2 + 2 * D;
+    float* base;      // + threadIdx.x already applied
+    uint32_t stride;  // blockDim.x
+    __device__ __forceinline__ float& at(int slot, int field) const { return base[(slot * kFields + field) * stride]; }
+};
+
+template <int D, int FAMILY, int NK>
+__device__ __forceinline__ void isir_prepare(const IsirConsts& K, const RunParams& R, const Stream& stream, uint32_t i,
+                                             IsirStepIn<D, NK>& in, IsirCands<D, NK>& c)
+{
+    constexpr int kGroups = (2 * D + 3) / 4;
+    const uint4 w0 = stream.block(R.rk, i, kSlotStep);
+    float z[kGroups * 4];
+    box_muller(w0.x, w0.y, z[0], z[1]);
+    box_muller(w0.z, w0.w, z[2], z[3]);
+#pragma unroll
+    for (int g = 1; g < kGroups; ++g) {
+        const uint4 w = stream.block(R.rk, i, kSlotNormal + g - 1);
+        box_muller(w.x, w.y, z[4 * g], z[4 * g + 1]);
+        box_muller(w.z, w.w, z[4 * g + 2], z[4 * g + 3]);
+    }
+    float eps_lp[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        eps_lp[k] = z[k];
+        in.n_l[k] = fmaf(K.model.noise_scale[k], z[D + k], K.model.noise_loc[k]);
+    }
+    (void)gauss_forward<D, false>(K.lp, eps_lp, in.z_l);
+    in.is_global = (step_block_ub(w0) < R.gf_thr_hi) || R.gf_all_global;
+    const uint32_t ua24 = step_block_ua(w0);
+    in.log_w = log_approx(__uint2float_rn(ua24) * 0x1p-24f);
+#pragma unroll
+    for (int j = 0; j < NK; ++j) {
+        float zz[kGroups * 4], eps_p[D];
+        uint4 wj[kGroups];
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) {
+            wj[g] = stream.block(R.rk, i, kSlotNormal + 8u + j * kGroups + g);
+            box_muller(wj[g].x, wj[g].y, zz[4 * g], zz[4 * g + 1]);
+            box_muller(wj[g].z, wj[g].w, zz[4 * g + 2], zz[4 * g + 3]);
+        }
+        if (j == 0) {  // 53-bit resampling uniform: see the plain loop
+            const uint64_t m53 = (static_cast<uint64_t>(ua24) << 29) | (static_cast<uint64_t>(step_block_ua(wj[0])) << 5) |
+                                 static_cast<uint64_t>(step_block_ub(wj[0]) >> 27);
+            in.u64 = static_cast<double>(m53) * 0x1p-53;
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) eps_p[k] = zz[k];
+        const float lq = gauss_forward<D, false>(K.ip, eps_p, c.th[j]);  // GLMCMC.py:66
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const float mean = FAMILY == GLABC_MODEL_ABS_NORMAL ? fabsf(c.th[j][k]) : c.th[j][k];
+            c.x[j][k] = mean + fmaf(K.model.noise_scale[k], zz[D + k], K.model.noise_loc[k]);  // GLMCMC.py:71
+        }
+        c.pk[j] = model_prior<D, false>(K.model, c.th[j]) + model_log_kernel<D, false>(K.model, c.x[j]);
+        c.lw[j] = c.pk[j] - lq;                                          // GLMCMC.py:72-74
+        in.w[j] = weight_exp<false>(c.lw[j]);
+    }
+}
+
+template <int D, int NK>
+__device__ __forceinline__ void isir_park(const IsirCands<D, NK>& c, const TakeTable<D>& tab)
+{
+#pragma unroll
+    for (int j = 0; j < NK; ++j) {
+        tab.at(j, 0) = c.lw[j];
+        tab.at(j, 1) = c.pk[j];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            tab.at(j, 2 + k) = c.th[j][k];
+            tab.at(j, 2 + D + k) = c.x[j][k];
+        }
+    }
+}
+
+template <int D>
+struct IsirState {
+    float theta[D], y[D];
+    float pk_old, lw_old;   // prior + kernel of the current state, its cached log-weight
+    bool local;
+};
+
+template <int D, int FAMILY, int NK, class Writer>
+__device__ __forceinline__ void isir_advance(const IsirConsts& K, const RunParams& R, uint32_t i, const IsirStepIn<D, NK>& in,
+                                             const TakeTable<D>& tab, IsirState<D>& s, ChainStats<D>& stats, Writer& writer)
+{
+    // iSIR arm: weight of the current state, resample (GLMCMC.py:60-64,78-84)
+    float lw_cur = s.lw_old;
+    if (s.local) lw_cur = s.pk_old - gauss_log_prob<D, false>(K.ip, s.theta);
+    const float w0 = weight_exp<false>(lw_cur);
+    float S = w0;
+#pragma unroll
+    for (int j = 0; j < NK; ++j) S += in.w[j];
+    const double thr = in.u64 * static_cast<double>(S);   // u < cumsum(w) / S  <=>  u * S < cumsum(w), in float64
+    double run = static_cast<double>(w0);
+    int ind = thr < run ? 0 : -1;
+#pragma unroll
+    for (int j = 0; j < NK; ++j) {
+        run += static_cast<double>(in.w[j]);
+        if (ind < 0 && thr < run) ind = j + 1;
+    }
+    const bool switch_g = in.is_global && ind > 0;
+    const int take = switch_g ? ind - 1 : 0;   // always a valid row: the loads are unconditional, their use predicated
+    float tk[TakeTable<D>::kFields];
+#pragma unroll
+    for (int f = 0; f < TakeTable<D>::kFields; ++f) tk[f] = tab.at(take, f);
+
+    // local arm (GLMCMC.py:90-104)
+    float th_l[D], y_l[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        th_l[k] = in.z_l[k] + s.theta[k];
+        y_l[k] = (FAMILY == GLABC_MODEL_ABS_NORMAL ? fabsf(th_l[k]) : th_l[k]) + in.n_l[k];
+    }
+    const float pk_l = model_prior<D, false>(K.model, th_l) + model_log_kernel<D, false>(K.model, y_l);
+    const bool accept_l = !in.is_global && (in.log_w < pk_l - s.pk_old);
+
+    float prev[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) prev[k] = s.theta[k];
+    if (switch_g) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            s.theta[k] = tk[2 + k];
+            s.y[k] = tk[2 + D + k];
+        }
+        lw_cur = tk[0];      // GLMCMC.py:86: cached log-weight of the taken candidate
+        s.pk_old = tk[1];
+    }
+    if (accept_l) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            s.theta[k] = th_l[k];
+            s.y[k] = y_l[k];
+        }
+        s.pk_old = pk_l;
+    }
+    if (in.is_global) {
+        s.lw_old = lw_cur;
+        s.local = false;     // GLMCMC.py:65
+    }
+    s.local = s.local || accept_l;  // GLMCMC.py:100
+    stats.update(in.is_global, switch_g || accept_l, s.theta, prev);
+    writer.put(R, i, s.theta);
+    writer.maybe_flush(R, i);
+}
+
 // NKT > 0: K is a compile-time constant — the candidate loops unroll, so the K independent Philox / Box-Muller /
 // log-weight chains of a global move interleave (ILP K) instead of running one after the other.
 template <int D, int FAMILY, bool STRICT, bool REPLAY, int LAYOUT, bool DUMP, int NKT = 0>
-__global__ void __launch_bounds__(256) k_isir(const __grid_constant__ IsirConsts K, const __grid_constant__ RunParams R)
+__global__ void __launch_bounds__(256, 2) k_isir(const __grid_constant__ IsirConsts K, const __grid_constant__ RunParams R)
 {
     using Writer = typename WriterFor<D, LAYOUT>::type;
     extern __shared__ float smem[];
@@ -140,6 +314,37 @@ __global__ void __launch_bounds__(256) k_isir(const __grid_constant__ IsirConsts
     const int tape_slots = 2 + NK * 2 * D;
     constexpr int kGroups = (2 * D + 3) / 4;  // Philox blocks per candidate
 
+    constexpr bool PIPE = !STRICT && !REPLAY && !DUMP && NKT > 0;
+    if constexpr (PIPE) {
+        constexpr int NKC = NKT > 0 ? NKT : 1;
+        const TakeTable<D> take{tab.base, blockDim.x};
+        IsirState<D> s;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            s.theta[k] = theta[k];
+            s.y[k] = y[k];
+        }
+        s.pk_old = prior_old + kern_old; s.lw_old = lw_old; s.local = local;
+        if (R.last_step >= R.first_step) {
+            IsirStepIn<D, NKC> cur, nxt;
+            IsirCands<D, NKC> cands;
+            isir_prepare<D, FAMILY, NKC>(K, R, stream, R.first_step, cur, cands);
+            isir_park<D, NKC>(cands, take);
+            for (uint32_t i = R.first_step; i <= R.last_step; ++i) {
+                // (the prepare past the last step is wasted work; its rows are never read)
+                isir_prepare<D, FAMILY, NKC>(K, R, stream, i + 1u, nxt, cands);
+                isir_advance<D, FAMILY, NKC>(K, R, i, cur, take, s, stats, writer);
+                isir_park<D, NKC>(cands, take);
+                cur = nxt;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            theta[k] = s.theta[k];
+            y[k] = s.y[k];
+        }
+        lw_old = s.lw_old; local = s.local;
+    } else
     for (uint32_t i = R.first_step; i <= R.last_step && R.last_step >= R.first_step; ++i) {
         // ---------------- draws ----------------
         bool is_global;
@@ -363,8 +568,10 @@ static cudaError_t launch_isir_one(const IsirConsts& K, const RunParams& R, int 
 {
     using Writer = typename WriterFor<D, LAYOUT>::type;
     const int grid = (R.n_chains + block - 1) / block;
-    const size_t smem = sizeof(float) * (static_cast<size_t>(Writer::smem_floats_per_warp) * (block / 32) +
-                                         static_cast<size_t>(R.n_candidates + 1) * CandTable<D>::kFields * block);
+    constexpr bool PIPE = !STRICT && !REPLAY && !DUMP && NKT > 0;   // pipelined loop: the smaller take-table
+    const size_t table = PIPE ? static_cast<size_t>(R.n_candidates) * TakeTable<D>::kFields
+                              : static_cast<size_t>(R.n_candidates + 1) * CandTable<D>::kFields;
+    const size_t smem = sizeof(float) * (static_cast<size_t>(Writer::smem_floats_per_warp) * (block / 32) + table * block);
     auto kern = k_isir<D, FAMILY, STRICT, REPLAY, LAYOUT, DUMP, NKT>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));

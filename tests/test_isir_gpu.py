@@ -239,3 +239,26 @@ def test_esjd_sweep(eng):
                              grid=[0.0, 0.5, 0.9, 1.0], num_chains=4096)
     assert table.shape == (4, 4) and best >= 0.5
     assert table[0, 1] < table[2, 1]          # esjd(gf = 0) < esjd(gf = 0.9): 0.0007 vs 0.03 in the reference
+
+
+def test_pipelined_fast_loop_equals_plain_loop(eng):
+    """K = 5 in FAST native mode runs the software-pipelined loop (candidates of step i+1 generated while step i
+    resolves); with a tape dump attached the plain loop runs.  Same Philox streams, same arithmetic: same chains."""
+    case, m, lp, ip = readme_pods()
+    Cn, d, K = 777, 2, 5
+    bind(eng, m, lp, ip)
+    y0 = (torch.randn(Cn, d, generator=torch.Generator().manual_seed(9)) * 0.2236).cuda()
+    for T in (1, 2, 97, 400):
+        th, yy, ax = torch.zeros(Cn, d, device="cuda"), y0.clone(), fresh_aux(Cn, "cuda")
+        st = torch.zeros(Cn, abi.nstats(d), device="cuda")
+        piped = eng.run("isir", theta=th, y=yy, aux=ax, n_steps=T, gf=0.9, seed=5, K=K, trace_layout=abi.TRACE_TIME_MAJOR, stats=st)
+        th2, yy2, ax2 = torch.zeros(Cn, d, device="cuda"), y0.clone(), fresh_aux(Cn, "cuda")
+        st2 = torch.zeros(Cn, abi.nstats(d), device="cuda")
+        dump = torch.zeros(T, abi.tape_isir_slots(d, d, K), Cn, device="cuda")
+        plain = eng.run("isir", theta=th2, y=yy2, aux=ax2, n_steps=T, gf=0.9, seed=5, K=K, trace_layout=abi.TRACE_TIME_MAJOR,
+                        stats=st2, tape_dump=dump)
+        torch.cuda.synchronize()
+        same = (piped == plain).all(-1).all(0)                       # per chain
+        assert float(same.float().mean()) > 0.995                    # an FMA contracted differently may flip a rare decision
+        assert torch.equal(st[:, abi.STAT_GLOBAL_STEPS], st2[:, abi.STAT_GLOBAL_STEPS])
+        assert torch.allclose(ax[same][:, :2], ax2[same][:, :2], rtol=1e-5, atol=1e-6)
