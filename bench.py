@@ -45,7 +45,9 @@ def parse():
     p.add_argument("--steps", type=int, default=200)
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="native", choices=["native", "reference"])
-    p.add_argument("--sampler", default="global", choices=sorted(SAMPLERS) + ["kde"], help="which fused step kernel to time")
+    p.add_argument("--sampler", default="global", choices=sorted(SAMPLERS) + ["kde", "glmcmc_nf", "aglmcmc_pooled"],
+                   help="which fused step kernel to time")
+    p.add_argument("--kde-train", type=int, default=100000, help="aglmcmc_pooled: pooled KDE training draws (all ranks together)")
     p.add_argument("--kde-points", type=int, default=100000)
     p.add_argument("--chains", type=int, default=65536, help="chains per GPU (weak scaling)")
     p.add_argument("--iters", type=int, default=10000, help="num_ite per chain (trace rows)")
@@ -317,6 +319,179 @@ def bench_kde(a, rank, world, local_rank):
         emit(line)
 
 
+# samplers whose importance proposal is SHARED by all chains of all ranks (the two places the path exchanges data):
+#   glmcmc_nf      BASELINE configs[3]: one RealNVP, flow sample / log_prob on tcgen05, gradients all-reduced per Adam step
+#   aglmcmc_pooled BASELINE configs[4]: one KernelDensity over `--kde-train` pooled draws, all-gathered before every fit
+SHARED = {
+    "glmcmc_nf": dict(gf=0.5, K=5, step_size=200, train_steps=50, chains=131072, iters=1001,
+                      workload="README Mixture_set GLMCMC-NFs: shared RealNVP(32 blocks), gf 0.5, K 5, step 200, 50 train steps "
+                               "(BASELINE configs[3], run_glmcmc_nf)"),
+    "aglmcmc_pooled": dict(gf=1.0, K=5, step_size=200, alpha=0.8, hat_eps_T=0.2, chains=16384, iters=1001,
+                           workload="README Mixture_set AGLMCMC with ONE pooled KernelDensity (BASELINE configs[4]), gf 1, K 5, "
+                                    "step 200, alpha 0.8, eps_hat_T 0.2"),
+}
+
+
+def bench_shared(a, rank, world, local_rank):
+    """One step = one whole sampler call through the public entry point (C chains x (T - 1) iterations per GPU, statistics
+    only), device-resident inputs; e2e = the same call with host tensors in and the statistics copied back."""
+    import torch
+    import torch.distributed as dist
+    import glabc_b200 as g
+    from glabc_b200 import _abi as abi
+    from glabc_b200.engine import get_engine
+    from glabc_b200.flows import RealNVP
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    spec = SHARED[a.sampler]
+    C = a.chains if a.chains != 65536 else spec["chains"]
+    T = a.iters if a.iters != 10000 else spec["iters"]
+    eng = get_engine()
+    info = eng.ctx.device_info()
+    model, lp, gp = workload_objects()
+    K, S, gf = spec["K"], spec["step_size"], spec["gf"]
+    base = rank * C
+    z_dev = torch.zeros(2, device="cuda")
+    z_host = torch.zeros(2)
+
+    def call(theta0, seed):
+        if a.sampler == "glmcmc_nf":
+            return g.GLMCMC_NF(model, T, theta0, None, lp, None, gf, S, K, None, spec["train_steps"], num_chains=C, seed=seed,
+                               chain_id_base=base, trace="none", return_stats=True, verbose=False)
+        return g.AGLMCMC(model, T, theta0, None, lp, gp, None, gf, S, K, spec["alpha"], spec["hat_eps_T"], num_chains=C, seed=seed,
+                         chain_id_base=base, trace="none", return_stats=True, verbose=False, pooled=True, kde_train=a.kde_train)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for w in range(a.warmup):
+        call(z_dev, w)
+    barrier()
+    n_idle = len(sampler.rows)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    calls0 = eng.ctx.n_calls
+    e0.record()
+    for s in range(a.steps):
+        _, st = call(z_dev, a.warmup + s)
+    e1.record()
+    barrier()
+    n_launch_calls = eng.ctx.n_calls - calls0    # every one launches at least one kernel of libglabc.so (3 binds per call aside)
+    sampler.rows = sampler.rows[max(0, n_idle - 1):]
+    clocks = sampler.stop()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    steps_per_pass = float(C) * (T - 1) * world
+    value = steps_per_pass * a.steps / (total_ms * 1e-3)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    sm_max_mhz = float(peaks.get("sm_max_mhz", clocks.get("sm_max_mhz") or 1965.0))
+
+    # the dominant kernel, timed alone at the size one block refill launches it (CUDA events on the launching stream)
+    def timed(fn, reps=5):
+        fn()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        k0.record()
+        for _ in range(reps):
+            fn()
+        k1.record()
+        torch.cuda.synchronize()
+        return k0.elapsed_time(k1) / reps
+    n_cand = C * K * S
+    if a.sampler == "glmcmc_nf":
+        flow = RealNVP(device="cuda")
+        with torch.no_grad():
+            flow.w3.copy_(0.05 * torch.randn_like(flow.w3))
+        flow.bind(eng)
+        eps = torch.randn(n_cand, 2, device="cuda")
+        th, lq = torch.empty(n_cand, 2, device="cuda"), torch.empty(n_cand, device="cuda")
+        kms = timed(lambda: flow.fused_sample_from(eps, eng, theta=th, log_q=lq))
+        tf = n_cand * 1.049e6 / (kms * 1e-3) / 1e12
+        peak = float(peaks.get("bf16_tflops", 1654.4)) / 2
+        roofline = {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "traffic": None,
+                    "kernel_ms": kms, "note": f"k_flow sample of one block refill ({n_cand} candidates x 32 coupling blocks, 1.049 MFLOP "
+                    "dense per sample, TF32 operands on tcgen05); peak = measured bf16 dense / 2 (MEASURED_PEAKS.json)"}
+        del eps, th, lq
+    else:
+        n = a.kde_train
+        X = torch.randn(n, 2, device="cuda")
+        wn, bw = eng.kde_fit(X, torch.rand(n, device="cuda"))
+        q = torch.randn(n_cand, 2, device="cuda")
+        kms = timed(lambda: eng.kde_log_prob(X, wn, bw, q), reps=2)
+        rate = float(n_cand) * n / (kms * 1e-3)
+        mufu_peak = info["sm_count"] * 16 * sm_max_mhz * 1e6
+        roofline = {"bound": "mufu", "achieved": rate / 1e9, "peak": mufu_peak / 1e9, "unit": "Gex2/s", "frac": rate / mufu_peak,
+                    "traffic": None, "kernel_ms": kms, "note": f"k_kde_logprob of one block refill: {n_cand} candidates x {n} pooled "
+                    "training draws, one MUFU.EX2 per pair (16 / clk / SM)"}
+        del X, q
+    torch.cuda.empty_cache()
+    cfg = {"workload": spec["workload"], "chains_per_gpu": C, "iterations": T, "theta_dim": 2, "epsilon": 0.05, "global_frequency": gf,
+           "isir_candidates": K, "step_size": S, "trace": "statistics only", "rng": "philox4x32-10 native", "arith": "fast",
+           "l2": "candidate blocks (C x 1000 x 24 B) stream through HBM once per refill, >> 126 MB L2",
+           "parallelism": f"chains sharded over {world} GPU(s); shared proposal: " +
+                          ("gradients all-reduced per Adam step" if a.sampler == "glmcmc_nf" else
+                           f"{a.kde_train} training draws all-gathered per fit")}
+    line = {"metric": "abc_mcmc_chain_steps_per_sec", "value": value, "unit": "chain-steps/s", "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32/f32" if a.sampler == "glmcmc_nf" else "f32", "data": "synthetic", "config": cfg, "clocks": clocks,
+            "gpu_launches": n_launch_calls - 4 * a.steps, "roofline": roofline,
+            "esjd": {"mean_per_chain": float(st.esjd().mean()), "move_rate": float(st.move_rate.mean())}}
+    line["esjd"]["aggregate_esjd_per_sec"] = line["esjd"]["mean_per_chain"] * value
+    if not a.no_e2e:
+        call(z_host, 1000)
+        barrier()
+        t0 = time.perf_counter()
+        e_steps = max(1, min(a.steps, 2))
+        for i in range(e_steps):
+            _, st = call(z_host, 1001 + i)
+            h = st.raw.cpu()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        line["e2e"] = {"value": steps_per_pass * e_steps / float(dt.item()), "unit": "chain-steps/s", "h2d_bytes_per_step": 8,
+                       "d2h_bytes_per_step": h.numel() * 4, "steps": e_steps,
+                       "note": "public entry point with host tensors in (theta0 broadcast to the chains on the device), per-chain statistics out"}
+    if rank == 0 and not a.no_cpu:
+        if a.sampler == "aglmcmc_pooled":
+            r, cores, sample, cpu_esjd = cpu_port_rate(C, T, a.cpu_seconds, sampler="aglmcmc")
+            line["cpu_baseline"] = {"value": r, "unit": "chain-steps/s", "cores": cores, "kind": "port",
+                                    "sample": sample + " (the reference's own per-chain KDE: it has no pooled mode)"}
+        else:
+            cf = RealNVP()
+            n_eval = 4096
+            torch.set_num_threads(os.cpu_count() or 1)
+            with torch.no_grad():
+                t0 = time.perf_counter()
+                reps = 0
+                while time.perf_counter() - t0 < a.cpu_seconds:
+                    xs, _ = cf.sample(n_eval)
+                    cf.log_prob(xs[: n_eval // K])
+                    reps += 1
+                dt = time.perf_counter() - t0
+            moves = reps * (n_eval // K)                 # a global move = K fresh samples + 1 log_prob (GLMCMC_NFs.py:98,127)
+            line["cpu_baseline"] = {"value": moves / dt / gf, "unit": "chain-steps/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"fp32 torch RealNVP (flows.py restatement of the normflows model) on the host: {reps} x "
+                                              f"({n_eval} samples + {n_eval // K} log_probs) in {dt:.1f} s; flow evaluations only "
+                                              "(the step arithmetic is negligible beside them), batched — the reference evaluates log_prob on a batch of one"}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        emit(line)
+
+
 def other_kernels(eng, model, lp, gp):
     """Short device-resident timings of the other hot-path kernels (the headline line stays GlobalMCMC, BASELINE configs[1]);
     full lines with e2e / cpu_baseline: `bench.py --sampler glmcmc|glmala|aglmcmc|kde`.  CUDA events, 3 warm-up + 5 timed."""
@@ -403,6 +578,13 @@ def _main():
                 emit({"impl": "reference", "unavailable": "--sampler kde has no reference arm; see cpu_baseline of the native line"})
             return
         bench_kde(a, rank, world, local_rank)
+        return
+    if a.sampler in SHARED:
+        if a.impl == "reference":
+            if rank == 0:
+                emit({"impl": "reference", "unavailable": f"--sampler {a.sampler}: see cpu_baseline of the native line"})
+            return
+        bench_shared(a, rank, world, local_rank)
         return
     if a.impl == "reference":
         bench_reference(a, rank)

@@ -194,8 +194,10 @@ class Context:
             raise GlabcError(st, self.lib.glabc_status_string(st).decode() +
                              " — glabc needs a CUDA device (sm_100a); there is no CPU fallback")
         self.handle = h
+        self.n_calls = 0          # status-checked C-ABI calls so far (bench.py reports kernel-launching calls from it)
 
     def check(self, st):
+        self.n_calls += 1
         if st != OK:
             raise GlabcError(st, self.lib.glabc_last_error(self.handle).decode())
 
