@@ -59,7 +59,7 @@ class FlowProposal:
             loss.backward()
         average_gradients(list(flow.parameters()))
         self.opt.step()                          # runs even when backward was skipped
-        self.losses.append(float(loss))
+        self.losses.append(float(loss.detach()))
         flow.bind(self.eng)
 
 

@@ -3,9 +3,12 @@
 random-walk move from `Local_Proposal`; the ABC likelihood is a Gaussian kernel on the discrepancy
 of one simulator draw.  The loop body (GlobalMCMC.py:37-68) runs in the fused kernel
 `k_global_mcmc` (csrc/step_global.cu) for all chains at once."""
+import torch
+
 from . import _abi
-from .engine import get_engine
-from .samplers import run_chains
+from .engine import RunStats, get_engine
+from .models import UserModel
+from .samplers import _LAYOUT, default_seed, print_summary, run_chains, write_csv
 
 
 def GlobalMCMC(ABCset, num_ite, Initial_theta, Initial_y, Global_Proposal, filelocation, global_frequency,
@@ -24,6 +27,9 @@ def GlobalMCMC(ABCset, num_ite, Initial_theta, Initial_y, Global_Proposal, filel
     if Local_Proposal is None:
         raise ValueError("Local_Proposal is required (the reference dereferences it on every local move, GlobalMCMC.py:56)")
     eng = get_engine(device)
+    if isinstance(ABCset, UserModel):
+        return _global_user(eng, ABCset, num_ite, Initial_theta, Initial_y, Global_Proposal, Local_Proposal, filelocation,
+                            global_frequency, num_chains, seed, chain_id_base, trace, return_stats, verbose, block_threads)
     pod = eng.bind_model(ABCset)
     eng.bind_proposal(_abi.SLOT_LOCAL, Local_Proposal)
     eng.bind_proposal(_abi.SLOT_GLOBAL, Global_Proposal)
@@ -31,3 +37,38 @@ def GlobalMCMC(ABCset, num_ite, Initial_theta, Initial_y, Global_Proposal, filel
                       global_frequency=global_frequency, filelocation=filelocation, num_chains=num_chains, seed=seed,
                       chain_id_base=chain_id_base, arith=arith, trace=trace, return_stats=return_stats, verbose=verbose,
                       block_threads=block_threads)
+
+
+def _global_user(eng, model, num_ite, Initial_theta, Initial_y, Global_Proposal, Local_Proposal, filelocation, gf, num_chains,
+                 seed, chain_id_base, trace, return_stats, verbose, block_threads):
+    """GlobalMCMC for a run-time compiled `UserModel` (glabc_run_global_user)."""
+    if num_ite < 1:
+        raise ValueError("num_ite must be at least 1")
+    if Initial_y is None:
+        raise ValueError("a UserModel run needs Initial_y (the library cannot call the simulator outside the kernel)")
+    eng.bind_proposal(_abi.SLOT_LOCAL, Local_Proposal)
+    eng.bind_proposal(_abi.SLOT_GLOBAL, Global_Proposal)
+    d, yd = model.theta_dim, model.y_dim
+    seed = default_seed() if seed is None else int(seed)
+    theta = torch.as_tensor(Initial_theta, dtype=torch.float32).reshape(-1, d)
+    c = num_chains if num_chains is not None else theta.shape[0]
+    y = torch.as_tensor(Initial_y, dtype=torch.float32).reshape(-1, yd)
+    if theta.shape[0] not in (1, c) or y.shape[0] not in (1, c):
+        raise ValueError(f"Initial_theta / Initial_y must have 1 or {c} rows")
+    theta = theta.to(eng.device).expand(c, d).contiguous().clone()
+    y = y.to(eng.device).expand(c, yd).contiguous().clone()
+    single = num_chains is None and c == 1
+    layout = _LAYOUT[trace]
+    stats = torch.zeros(c, _abi.nstats(d), dtype=torch.float32, device=eng.device)
+    out = eng.run_user(model, theta=theta, y=y, n_steps=num_ite - 1, gf=gf, seed=seed, chain_id_base=chain_id_base,
+                       trace_layout=layout, stats=stats, block_threads=block_threads)
+    rs = RunStats(stats, d)
+    if single:
+        result = (out[0] if layout == _abi.TRACE_CHAIN_MAJOR else out[:, 0]).cpu() if out is not None else None
+        if filelocation is not None and result is not None:
+            write_csv(filelocation, result)
+        if verbose is not False and result is not None:
+            print_summary(result)
+    else:
+        result = out
+    return (result, rs) if return_stats else result

@@ -14,4 +14,4 @@ from .GLMCMC_NFs import GLMCMC_NF  # noqa: F401
 from .GlobalMCMC import GlobalMCMC  # noqa: F401
 from .kernel_density import KernelDensity  # noqa: F401
 from .MCMCRunner import MCMCRunner  # noqa: F401
-from .models import AbsNormalModel, Mixture_set  # noqa: F401
+from .models import AbsNormalModel, Mixture_set, UserModel  # noqa: F401

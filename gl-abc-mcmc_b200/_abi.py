@@ -103,6 +103,15 @@ class BlockIsirPOD(C.Structure):
                 ("next_step", C.c_void_p), ("lq_cur", C.c_void_p), ("lq_valid", C.c_void_p)]
 
 
+USER_MAX_PARAMS, USER_MAX_NOISE = 64, 32
+
+
+class UserModelPOD(C.Structure):
+    """glabc_user_model_t"""
+    _fields_ = [("theta_dim", C.c_int32), ("y_dim", C.c_int32), ("n_noise", C.c_int32), ("n_params", C.c_int32),
+                ("source", C.c_char_p), ("params", C.c_float * USER_MAX_PARAMS), ("epsilon", C.c_double)]
+
+
 BW_SILVERMAN, BW_SCOTT = 0, 1
 AG_REC_SLOTS = 8
 AG_MAX_BLOCK = 4096
@@ -133,6 +142,8 @@ _SIGNATURES = {
     "glabc_dist_log_prob": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "glabc_dist_sample": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "glabc_run_global": (C.c_int, [C.c_void_p, C.POINTER(RunPOD)]),
+    "glabc_run_global_user": (C.c_int, [C.c_void_p, C.POINTER(RunPOD), C.POINTER(UserModelPOD)]),
+    "glabc_user_model_check": (C.c_int, [C.POINTER(UserModelPOD), C.c_int32, C.c_char_p, C.c_size_t]),
     "glabc_run_global_host": (C.c_int, [C.c_void_p, C.POINTER(RunPOD), C.c_int64]),
     "glabc_run_isir": (C.c_int, [C.c_void_p, C.POINTER(RunPOD)]),
     "glabc_run_isir_host": (C.c_int, [C.c_void_p, C.POINTER(RunPOD), C.c_int64]),

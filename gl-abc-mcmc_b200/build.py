@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 SOURCES = ["abi.cu", "diag.cu", "step_global.cu", "step_global_d1.cu", "step_global_d2.cu", "step_global_d3.cu",
            "step_global_d4.cu", "step_isir.cu", "step_isir_d1.cu", "step_isir_d2.cu", "step_isir_d3.cu", "step_isir_d4.cu",
            "step_mala.cu", "step_mala_d1.cu", "step_mala_d2.cu", "step_mala_d3.cu", "step_mala_d4.cu",
-           "kde.cu", "step_aglmcmc.cu", "flow.cu", "step_generic.cu"]
+           "kde.cu", "step_aglmcmc.cu", "flow.cu", "step_generic.cu", "user_model.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xptxas", "-v",
               "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "include")]
@@ -57,7 +57,7 @@ def build(force=False, verbose=False, variant=None, extra_flags=()):
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     # -cudart static (nvcc default): the library loads on a box without a GPU or libcudart.so
-    p = subprocess.run([nvcc, "-shared", "-o", lib_path, *objs, "-Xcompiler", "-fvisibility=hidden"], capture_output=True, text=True)
+    p = subprocess.run([nvcc, "-shared", "-o", lib_path, *objs, "-Xcompiler", "-fvisibility=hidden", "-ldl"], capture_output=True, text=True)
     if p.returncode != 0:
         raise RuntimeError("link failed:\n" + p.stderr)
     with open(os.path.join(CSRC, f"ptxas{tag}.log"), "w") as f:

@@ -13,6 +13,7 @@
 #include "step_aglmcmc.cuh"
 #include "step_generic.cuh"
 #include "step_mala.cuh"
+#include "user_model.cuh"
 
 using namespace glabc;
 
@@ -941,6 +942,91 @@ extern "C" int glabc_dist_sample(glabc_ctx* ctx, int slot, int64_t n, uint64_t s
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const RoundKeys rk = expand_key(make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
     CUDA_TRY(ctx, launch_dist_eval(make_dist(ctx->dist[slot]), ctx->dist[slot].dim, rk, n, nullptr, z, log_p, static_cast<cudaStream_t>(stream)));
+    return GLABC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// GlobalMCMC with a user-supplied model compiled at run time (user_model.cu)
+// ---------------------------------------------------------------------------------------------
+extern "C" int glabc_user_model_check(const glabc_user_model_t* um, int32_t cc, char* log, size_t log_cap)
+{
+    if (log && log_cap) log[0] = '\0';
+    if (!um || !um->source) return GLABC_ERR_INVALID;
+    if (um->theta_dim < 1 || um->theta_dim > GLABC_MAX_DIM || um->y_dim < 1 || um->y_dim > 2 * GLABC_MAX_DIM || um->n_noise < 0 ||
+        um->n_noise > GLABC_USER_MAX_NOISE)
+        return GLABC_ERR_INVALID;
+    std::string err;
+    const int st = user_model_check(cc, *um, err);
+    if (log && log_cap) {
+        strncpy(log, err.c_str(), log_cap - 1);
+        log[log_cap - 1] = '\0';
+    }
+    return st;
+}
+
+extern "C" int glabc_run_global_user(glabc_ctx* ctx, const glabc_run_t* run, const glabc_user_model_t* um)
+{
+    if (!ctx) return GLABC_ERR_INVALID;
+    if (!um || !um->source) return fail(ctx, GLABC_ERR_INVALID, "glabc_run_global_user: null model / source");
+    if (um->theta_dim < 1 || um->theta_dim > GLABC_MAX_DIM || um->y_dim < 1 || um->y_dim > 2 * GLABC_MAX_DIM)
+        return fail(ctx, GLABC_ERR_INVALID, "user model: theta_dim in 1..%d, y_dim in 1..%d", GLABC_MAX_DIM, 2 * GLABC_MAX_DIM);
+    if (um->n_noise < 0 || um->n_noise > GLABC_USER_MAX_NOISE || um->n_params < 0 || um->n_params > GLABC_USER_MAX_PARAMS)
+        return fail(ctx, GLABC_ERR_INVALID, "user model: n_noise in 0..%d, n_params in 0..%d", GLABC_USER_MAX_NOISE, GLABC_USER_MAX_PARAMS);
+    if (!(um->epsilon > 0.0)) return fail(ctx, GLABC_ERR_INVALID, "user model: epsilon must be positive");
+    const int d = um->theta_dim;
+    for (int slot : {GLABC_SLOT_LOCAL, GLABC_SLOT_GLOBAL}) {
+        if (!ctx->has_dist[slot]) return fail(ctx, GLABC_ERR_INVALID, "glabc_run_global_user needs the LOCAL and GLOBAL proposal slots bound");
+        if (ctx->dist[slot].kind != GLABC_DIST_DIAG_GAUSSIAN)
+            return fail(ctx, GLABC_ERR_UNSUPPORTED, "glabc_run_global_user is fused for DiagGaussian proposals");
+        if (ctx->dist[slot].dim != d) return fail(ctx, GLABC_ERR_INVALID, "proposal dim does not match the user model's theta_dim %d", d);
+    }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    RunParams R;
+    int block = 0;
+    int st = make_run_params(ctx, run, d, 0, &R, &block);
+    if (st) return st;
+    if (run->rng_mode != GLABC_RNG_NATIVE) return fail(ctx, GLABC_ERR_UNSUPPORTED, "glabc_run_global_user runs the native RNG only");
+    CUDA_TRY(ctx, cudaFree(nullptr));   // make sure the primary context exists and is current for the driver calls
+    void* fn = nullptr;
+    std::string err;
+    st = user_model_compile(ctx->device, ctx->cc, *um, &fn, err);
+    if (st) return fail(ctx, st, "%s", err.c_str());
+    UserRun U{};
+    U.n_chains = R.n_chains;
+    U.first_step = R.first_step;
+    U.last_step = R.last_step;
+    U.chain_lo0 = R.chain_lo0;
+    U.chain_hi0 = R.chain_hi0;
+    U.key0 = static_cast<uint32_t>(run->seed);
+    U.key1 = static_cast<uint32_t>(run->seed >> 32);
+    const double gf = static_cast<double>(run->global_frequency);
+    U.gf_all_global = gf >= 1.0;
+    U.gf_thr = gf <= 0.0 ? 0u : (gf >= 1.0 ? 0xFFFFFFFFu : static_cast<uint32_t>(gf * 4294967296.0));
+    U.write_row0 = R.write_row0;
+    U.trace_layout = run->trace_layout;
+    U.trace_rows = R.trace_rows;
+    U.trace_chains = R.trace_chains;
+    U.trace_chain_off = R.trace_chain_off;
+    U.trace_row_base = R.trace_row_base;
+    U.theta = R.theta;
+    U.y = R.y;
+    U.trace = R.trace;
+    U.stats = R.stats;
+    const glabc_dist_t& lp = ctx->dist[GLABC_SLOT_LOCAL];
+    const glabc_dist_t& gp = ctx->dist[GLABC_SLOT_GLOBAL];
+    for (int k = 0; k < d; ++k) {   // glabc_dist_t DiagGaussian: a = loc, b = log_scale, c = exp(log_scale) in float32
+        U.lp_loc[k] = lp.a[k];
+        U.lp_scale[k] = lp.c[k];
+        U.gp_loc[k] = gp.a[k];
+        U.gp_scale[k] = gp.c[k];
+        U.gp_inv_scale[k] = 1.0f / gp.c[k];
+    }
+    const float eps = static_cast<float>(um->epsilon);
+    U.kern_c = static_cast<float>(-0.5 * std::log(2.0 * M_PI)) - std::log(eps);
+    U.kern_m = -0.5f / (eps * eps);
+    for (int k = 0; k < um->n_params; ++k) U.params[k] = um->params[k];
+    st = user_model_launch(fn, U, block > 128 ? 128 : block, static_cast<cudaStream_t>(run->stream), err);
+    if (st) return fail(ctx, st, "%s", err.c_str());
     return GLABC_OK;
 }
 

@@ -1,0 +1,374 @@
+// User-supplied ABC models compiled at run time into the fused GlobalMCMC step kernel.
+//
+// The reference's plugin surface is a duck-typed Python object (generate_samples / prior_log_prob / discrepancy,
+// examples/Mixture.py:13-36, README.md:66-104); an arbitrary Python simulator cannot run inside a kernel.  Here the
+// three model functions arrive as CUDA C++ device-function source, are concatenated between a prelude (Philox4x32-10,
+// Box-Muller) and the step kernel below, and compiled with NVRTC for the device's architecture — the simulator is
+// inlined into the same single kernel as the proposal, the Gaussian ABC kernel and the MH test (GlobalMCMC.py:37-68).
+//
+// libnvrtc / libcuda are dlopen'ed on first use: libglabc.so itself keeps no link-time dependency on them, so it
+// still loads (and exports every symbol) on a machine without a driver.
+#include <dlfcn.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <nvrtc.h>
+
+#include "user_model.cuh"
+
+namespace glabc {
+
+namespace {
+
+// ---- the kernel's source: prelude + (user source) + step kernel.  D, YD, NN arrive as -D macros. ----
+const char* kPrelude = R"GLABC(
+typedef unsigned int u32;
+typedef unsigned long long u64;
+// NVRTC compiles without the host's <cmath>: the usual constants a model may want
+#ifndef INFINITY
+#define INFINITY __int_as_float(0x7f800000)
+#endif
+#ifndef NAN
+#define NAN __int_as_float(0x7fffffff)
+#endif
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+struct UserRun {
+    int n_chains;
+    u32 first_step, last_step, chain_lo0, chain_hi0, key0, key1, gf_thr;
+    int gf_all_global, write_row0, trace_layout, pad;
+    long long trace_rows, trace_chains, trace_chain_off, trace_row_base;
+    float *theta, *y, *trace, *stats;
+    float lp_loc[8], lp_scale[8], gp_loc[8], gp_scale[8], gp_inv_scale[8];
+    float kern_c, kern_m;     // log K(dis) = kern_c + kern_m * dis^2   (Mixture.py:38-53)
+    float params[64];
+};
+__device__ __forceinline__ uint4 glabc_philox(u32 c0, u32 c1, u32 c2, u32 c3, u32 k0, u32 k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const u64 p0 = (u64)0xD2511F53u * c0;
+        const u64 p1 = (u64)0xCD9E8D57u * c2;
+        const u32 n0 = (u32)(p1 >> 32) ^ c1 ^ k0, n2 = (u32)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (u32)p1; c3 = (u32)p0; c0 = n0; c2 = n2;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ void glabc_box_muller(u32 w0, u32 w1, float& n0, float& n1)
+{
+    const float u1 = fmaf(__uint2float_rn(w0 >> 8), 0x1p-24f, 0x1p-25f);
+    const float r = sqrtf(-2.0f * __logf(u1));
+    const float a = __uint2float_rn(w1 >> 8) * (6.28318530717958647692f * 0x1p-24f);
+    float s, c;
+    __sincosf(a, &s, &c);
+    n0 = r * c;
+    n1 = r * s;
+}
+)GLABC";
+
+const char* kKernel = R"GLABC(
+__device__ __forceinline__ float glabc_target(const UserRun& R, const float* th, const float* y)
+{
+    const float dis = glabc_user_discrepancy(y, R.params);
+    return glabc_user_prior_log_prob(th, R.params) + fmaf(R.kern_m, dis * dis, R.kern_c);
+}
+extern "C" __global__ void __launch_bounds__(128) glabc_k_global_user(const __grid_constant__ UserRun R)
+{
+    const int chain = blockIdx.x * blockDim.x + threadIdx.x;
+    if (chain >= R.n_chains) return;
+    const u64 gid = ((u64)R.chain_hi0 << 32 | R.chain_lo0) + (u64)chain;
+    const u32 g0 = (u32)gid, g1 = (u32)(gid >> 32);
+    float th[D], y[YD];
+#pragma unroll
+    for (int k = 0; k < D; ++k) th[k] = R.theta[(long long)chain * D + k];
+#pragma unroll
+    for (int k = 0; k < YD; ++k) y[k] = R.y[(long long)chain * YD + k];
+    float tgt = glabc_target(R, th, y);
+    float n_glob = 0.f, acc_l = 0.f, acc_g = 0.f, sum[D], sumsq[D], gram[D * (D + 1) / 2];
+#pragma unroll
+    for (int k = 0; k < D; ++k) sum[k] = sumsq[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < D * (D + 1) / 2; ++k) gram[k] = 0.f;
+    // trace rows: row index = loop index i, row 0 = initial theta (GlobalMCMC.py:34-35)
+    const long long cstride = R.trace_layout == 2 ? (long long)D : R.trace_chains * D;   // per ROW
+    float* row = nullptr;
+    if (R.trace_layout != 0) {
+        const long long r0 = (long long)R.first_step - (R.write_row0 ? 1 : 0) - R.trace_row_base;
+        row = R.trace_layout == 2 ? R.trace + ((R.trace_chain_off + chain) * R.trace_rows + r0) * D
+                                  : R.trace + (r0 * R.trace_chains + R.trace_chain_off + chain) * D;
+        if (R.write_row0) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) row[k] = th[k];
+            row += cstride;
+        }
+    }
+    constexpr int NZ = D + NN;                 // normals per step
+    constexpr int NB = (NZ + 3) / 4;           // extra Philox blocks carrying them
+    for (u32 i = R.first_step; i <= R.last_step && R.last_step >= R.first_step; ++i) {
+        const uint4 w0 = glabc_philox(g0, g1, i, 1u, R.key0, R.key1);
+        const bool is_global = R.gf_all_global || (w0.x < R.gf_thr);              // GlobalMCMC.py:38-39
+        const float log_u = __logf(__uint2float_rn(w0.y >> 8) * 0x1p-24f);         // :47,61 (log 0 = -inf accepts, as torch's)
+        float z[NB * 4 + 4];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const uint4 w = glabc_philox(g0, g1, i, 2u + b, R.key0, R.key1);
+            glabc_box_muller(w.x, w.y, z[4 * b], z[4 * b + 1]);
+            glabc_box_muller(w.z, w.w, z[4 * b + 2], z[4 * b + 3]);
+        }
+        float thp[D], yp[YD], corr = 0.f;
+        if (is_global) {                       // independence proposal q = Global_Proposal, :40-46
+            float qn = 0.f, qo = 0.f;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                thp[k] = fmaf(R.gp_scale[k], z[k], R.gp_loc[k]);
+                const float r = (th[k] - R.gp_loc[k]) * R.gp_inv_scale[k];
+                qn = fmaf(z[k], z[k], qn);
+                qo = fmaf(r, r, qo);
+            }
+            corr = 0.5f * (qn - qo);           // log q(theta) - log q(theta'): the constants cancel
+        } else {                               // symmetric random walk, :56-60
+#pragma unroll
+            for (int k = 0; k < D; ++k) thp[k] = th[k] + fmaf(R.lp_scale[k], z[k], R.lp_loc[k]);
+        }
+        glabc_user_simulate(thp, z + D, R.params, yp);
+        const float tgt_p = glabc_target(R, thp, yp);
+        const bool acc = log_u < (tgt_p - tgt) + corr;
+        float dl[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            dl[k] = acc ? thp[k] - th[k] : 0.f;
+            th[k] = acc ? thp[k] : th[k];
+            sum[k] += th[k];
+            sumsq[k] = fmaf(th[k], th[k], sumsq[k]);
+        }
+        if (acc) {
+#pragma unroll
+            for (int k = 0; k < YD; ++k) y[k] = yp[k];
+            tgt = tgt_p;
+        }
+        int t = 0;
+#pragma unroll
+        for (int a = 0; a < D; ++a)
+#pragma unroll
+            for (int b = a; b < D; ++b, ++t) gram[t] = fmaf(dl[a], dl[b], gram[t]);
+        n_glob += is_global ? 1.f : 0.f;
+        acc_g += (acc && is_global) ? 1.f : 0.f;
+        acc_l += (acc && !is_global) ? 1.f : 0.f;
+        if (row != nullptr) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) row[k] = th[k];
+            row += cstride;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) R.theta[(long long)chain * D + k] = th[k];
+#pragma unroll
+    for (int k = 0; k < YD; ++k) R.y[(long long)chain * YD + k] = y[k];
+    if (R.stats != nullptr) {
+        float* st = R.stats + (long long)chain * (4 + 2 * D + D * (D + 1) / 2);
+        st[0] += R.last_step >= R.first_step ? (float)(R.last_step + 1u - R.first_step) : 0.f;
+        st[1] += n_glob;
+        st[2] += acc_l;
+        st[3] += acc_g;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            st[4 + k] += sum[k];
+            st[4 + D + k] += sumsq[k];
+        }
+#pragma unroll
+        for (int k = 0; k < D * (D + 1) / 2; ++k) st[4 + 2 * D + k] += gram[k];
+    }
+}
+)GLABC";
+
+// ---- lazily bound NVRTC / driver entry points --------------------------------------------------------------------
+struct Dyn {
+    bool tried = false, rt_ok = false, ok = false;   // rt_ok: NVRTC usable (compile checks need no driver); ok: + driver
+    std::string why;
+    decltype(&nvrtcCreateProgram) createProgram = nullptr;
+    decltype(&nvrtcCompileProgram) compileProgram = nullptr;
+    decltype(&nvrtcGetProgramLogSize) getLogSize = nullptr;
+    decltype(&nvrtcGetProgramLog) getLog = nullptr;
+    decltype(&nvrtcGetCUBINSize) getCubinSize = nullptr;
+    decltype(&nvrtcGetCUBIN) getCubin = nullptr;
+    decltype(&nvrtcDestroyProgram) destroyProgram = nullptr;
+    decltype(&nvrtcGetErrorString) errString = nullptr;
+    CUresult (*moduleLoadData)(CUmodule*, const void*) = nullptr;
+    CUresult (*moduleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+    CUresult (*launchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**,
+                             void**) = nullptr;
+    CUresult (*getErrorString)(CUresult, const char**) = nullptr;
+};
+
+Dyn& dyn()
+{
+    static Dyn d;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (d.tried) return d;
+    d.tried = true;
+    void* rt = nullptr;
+    for (const char* name : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"}) {
+        rt = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+        if (rt) break;
+    }
+    if (!rt) {
+        d.why = "libnvrtc.so.12 could not be loaded (needed to compile a user model)";
+        return d;
+    }
+#define GLABC_SYM(lib, field, sym)                                             \
+    d.field = reinterpret_cast<decltype(d.field)>(dlsym(lib, sym));           \
+    if (!d.field) {                                                           \
+        d.why = std::string("symbol ") + sym + " not found";                  \
+        return d;                                                             \
+    }
+    GLABC_SYM(rt, createProgram, "nvrtcCreateProgram")
+    GLABC_SYM(rt, compileProgram, "nvrtcCompileProgram")
+    GLABC_SYM(rt, getLogSize, "nvrtcGetProgramLogSize")
+    GLABC_SYM(rt, getLog, "nvrtcGetProgramLog")
+    GLABC_SYM(rt, getCubinSize, "nvrtcGetCUBINSize")
+    GLABC_SYM(rt, getCubin, "nvrtcGetCUBIN")
+    GLABC_SYM(rt, destroyProgram, "nvrtcDestroyProgram")
+    GLABC_SYM(rt, errString, "nvrtcGetErrorString")
+    d.rt_ok = true;
+    void* cu = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!cu) {
+        d.why = "libcuda.so.1 could not be loaded";
+        return d;
+    }
+    GLABC_SYM(cu, moduleLoadData, "cuModuleLoadData")
+    GLABC_SYM(cu, moduleGetFunction, "cuModuleGetFunction")
+    GLABC_SYM(cu, launchKernel, "cuLaunchKernel")
+    GLABC_SYM(cu, getErrorString, "cuGetErrorString")
+#undef GLABC_SYM
+    d.ok = true;
+    return d;
+}
+
+struct Compiled {
+    CUmodule mod = nullptr;
+    CUfunction fn = nullptr;
+};
+std::mutex g_cache_mu;
+std::map<std::string, Compiled> g_cache;   // key: device | arch | dims | source
+
+std::string cu_err(Dyn& d, CUresult r)
+{
+    const char* s = nullptr;
+    d.getErrorString(r, &s);
+    return s ? s : "unknown driver error";
+}
+
+}  // namespace
+
+// NVRTC: prelude + user source + step kernel -> cubin for sm_<cc>
+static int compile_to_cubin(Dyn& d, int cc, const glabc_user_model_t& um, std::vector<char>& cubin, std::string& err)
+{
+    const std::string src = std::string(kPrelude) + "\n// ---- user model ----\n" + um.source + "\n// ---- step kernel ----\n" + kKernel;
+    nvrtcProgram prog = nullptr;
+    nvrtcResult r = d.createProgram(&prog, src.c_str(), "glabc_user_model.cu", 0, nullptr, nullptr);
+    if (r != NVRTC_SUCCESS) {
+        err = std::string("nvrtcCreateProgram: ") + d.errString(r);
+        return GLABC_ERR_CUDA;
+    }
+    char arch[48], dD[24], dY[24], dN[24];
+    snprintf(arch, sizeof(arch), "--gpu-architecture=sm_%d%s", cc, cc >= 90 ? "a" : "");
+    snprintf(dD, sizeof(dD), "-DD=%d", um.theta_dim);
+    snprintf(dY, sizeof(dY), "-DYD=%d", um.y_dim);
+    snprintf(dN, sizeof(dN), "-DNN=%d", um.n_noise);
+    const char* opts[] = {arch, dD, dY, dN, "--std=c++17", "--use_fast_math", "-lineinfo"};
+    r = d.compileProgram(prog, static_cast<int>(sizeof(opts) / sizeof(opts[0])), opts);
+    if (r != NVRTC_SUCCESS) {
+        size_t n = 0;
+        d.getLogSize(prog, &n);
+        std::string log(n, '\0');
+        if (n) d.getLog(prog, &log[0]);
+        d.destroyProgram(&prog);
+        err = std::string("user model does not compile: ") + log.c_str();
+        return GLABC_ERR_INVALID;
+    }
+    size_t nb = 0;
+    d.getCubinSize(prog, &nb);
+    cubin.resize(nb);
+    d.getCubin(prog, cubin.data());
+    d.destroyProgram(&prog);
+    return GLABC_OK;
+}
+
+int user_model_check(int cc, const glabc_user_model_t& um, std::string& err)
+{
+    Dyn& d = dyn();
+    if (!d.rt_ok) {
+        err = d.why;
+        return GLABC_ERR_UNSUPPORTED;
+    }
+    std::vector<char> cubin;
+    return compile_to_cubin(d, cc, um, cubin, err);
+}
+
+int user_model_compile(int device, int cc, const glabc_user_model_t& um, void** fn_out, std::string& err)
+{
+    Dyn& d = dyn();
+    if (!d.ok) {
+        err = d.why;
+        return GLABC_ERR_UNSUPPORTED;
+    }
+    char head[160];
+    snprintf(head, sizeof(head), "%d|%d|%d|%d|%d|", device, cc, um.theta_dim, um.y_dim, um.n_noise);
+    const std::string key = std::string(head) + um.source;
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    auto it = g_cache.find(key);
+    if (it != g_cache.end()) {
+        *fn_out = it->second.fn;
+        return GLABC_OK;
+    }
+    std::vector<char> cubin;
+    int st = compile_to_cubin(d, cc, um, cubin, err);
+    if (st) return st;
+    Compiled c;
+    CUresult cr = d.moduleLoadData(&c.mod, cubin.data());
+    if (cr != CUDA_SUCCESS) {
+        err = "cuModuleLoadData: " + cu_err(d, cr);
+        return GLABC_ERR_CUDA;
+    }
+    cr = d.moduleGetFunction(&c.fn, c.mod, "glabc_k_global_user");
+    if (cr != CUDA_SUCCESS) {
+        err = "cuModuleGetFunction: " + cu_err(d, cr);
+        return GLABC_ERR_CUDA;
+    }
+    g_cache[key] = c;
+    *fn_out = c.fn;
+    return GLABC_OK;
+}
+
+int user_model_launch(void* fn, const UserRun& R, int block, cudaStream_t st, std::string& err)
+{
+    Dyn& d = dyn();
+    if (!d.ok) {
+        err = d.why;
+        return GLABC_ERR_UNSUPPORTED;
+    }
+    if (R.n_chains <= 0) return GLABC_OK;
+    UserRun copy = R;
+    void* args[] = {&copy};
+    const unsigned grid = static_cast<unsigned>((R.n_chains + block - 1) / block);
+    const CUresult cr = d.launchKernel(static_cast<CUfunction>(fn), grid, 1, 1, static_cast<unsigned>(block), 1, 1, 0,
+                                       reinterpret_cast<CUstream>(st), args, nullptr);
+    if (cr != CUDA_SUCCESS) {
+        err = "cuLaunchKernel: " + cu_err(d, cr);
+        return GLABC_ERR_CUDA;
+    }
+    return GLABC_OK;
+}
+
+}  // namespace glabc

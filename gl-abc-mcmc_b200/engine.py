@@ -144,6 +144,23 @@ class Engine:
         self.ctx.check(fn(self.ctx.handle, C.byref(r)))
         return trace
 
+    def run_user(self, model, *, theta, y, n_steps, gf, step_base=0, chain_id_base=0, seed=0, trace_layout=_abi.TRACE_CHAIN_MAJOR,
+                 trace=None, trace_rows=None, write_row0=True, stats=None, block_threads=0):
+        """GlobalMCMC transitions for a `models.UserModel` (compiled on first use); LOCAL / GLOBAL slots must be bound"""
+        cn, d = theta.shape
+        rows = trace_rows if trace_rows is not None else step_base + n_steps + 1
+        if trace is None and trace_layout != _abi.TRACE_NONE:
+            shape = (rows, cn, d) if trace_layout == _abi.TRACE_TIME_MAJOR else (cn, rows, d)
+            trace = torch.empty(shape, dtype=torch.float32, device=self.device)
+        r = _abi.RunPOD(n_chains=cn, n_steps=n_steps, step_base=step_base, chain_id_base=chain_id_base,
+                        seed=int(seed) & 0xFFFFFFFFFFFFFFFF, global_frequency=float(gf), rng_mode=_abi.RNG_NATIVE,
+                        arith_mode=_abi.ARITH_FAST, trace_layout=trace_layout, write_row0=int(write_row0),
+                        block_threads=block_threads, trace_rows=rows, trace_chains=cn, theta=self._ptr(theta), y=self._ptr(y),
+                        trace=self._ptr(trace), stats=self._ptr(stats), stream=self._stream())
+        pod = model.user_pod()
+        self.ctx.check(self.lib.glabc_run_global_user(self.ctx.handle, C.byref(r), C.byref(pod)))
+        return trace
+
     def aglmcmc_params(self, *, step_size, alpha, hat_eps_T, rule=_abi.BW_SILVERMAN, init=True, init_p=None, init_s=None,
                        ad_idx=None, ad_noise=None, ad_sim=None, ad_rec=None, ad_blk=None, init_w=None):
         """glabc_aglmcmc_t; the tensors (replay tapes / parity dumps) must stay alive until the run is enqueued"""

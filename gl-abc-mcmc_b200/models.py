@@ -99,6 +99,42 @@ class Mixture_set(AbsNormalModel):
         super().__init__(epsilon, y_obs=(1.5, 1.5), noise_var=0.05, device=device)
 
 
+class UserModel:
+    """An ABC model given as CUDA C++ source: the three plugin methods every sampler calls —
+    `generate_samples`, `prior_log_prob`, `discrepancy` (examples/Mixture.py:13-36, README.md:66-104) — written as device
+    functions, compiled at run time INTO the fused GlobalMCMC step kernel (csrc/user_model.cu):
+
+        __device__ void  glabc_user_simulate(const float* theta, const float* noise, const float* params, float* y);
+        __device__ float glabc_user_prior_log_prob(const float* theta, const float* params);
+        __device__ float glabc_user_discrepancy(const float* y, const float* params);
+
+    `noise` holds `n_noise` independent N(0,1) draws per simulator call, `params` the model's constants.  The Gaussian
+    ABC kernel of width `epsilon` (Mixture.py:38-53) stays the library's.  `check()` compiles the source without a GPU."""
+
+    def __init__(self, source, theta_dim, y_dim, n_noise, epsilon, params=()):
+        self.source, self.theta_dim, self.y_dim, self.n_noise = str(source), int(theta_dim), int(y_dim), int(n_noise)
+        self.epsilon = float(epsilon)
+        self.params = [float(p) for p in params]
+        if len(self.params) > _abi.USER_MAX_PARAMS:
+            raise ValueError(f"at most {_abi.USER_MAX_PARAMS} params")
+
+    def user_pod(self):
+        pod = _abi.UserModelPOD(theta_dim=self.theta_dim, y_dim=self.y_dim, n_noise=self.n_noise, n_params=len(self.params),
+                                source=self.source.encode(), epsilon=self.epsilon)
+        _abi.fill(pod.params, self.params)
+        return pod
+
+    def check(self, cc=100):
+        """compile-only validation (NVRTC, no GPU needed); raises ValueError with the compiler log"""
+        import ctypes as C
+        log = C.create_string_buffer(8192)
+        pod = self.user_pod()
+        st = _abi.load().glabc_user_model_check(C.byref(pod), int(cc), log, len(log))
+        if st != _abi.OK:
+            raise ValueError(f"user model rejected (status {st}): {log.value.decode(errors='replace')}")
+        return True
+
+
 def lower_model(abc_set):
     """POD for `abc_set`: our own model classes lower themselves; a foreign object is accepted only
     if it behaves exactly like the AbsNormal family on a deterministic probe (so a reference

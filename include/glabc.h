@@ -284,6 +284,32 @@ typedef struct {
     int32_t* lq_valid;        /* [C] lq_cur is up to date                                                   */
 } glabc_block_isir_t;
 
+/* ---- user-supplied model, compiled at run time ------------------------------------------
+ * The plugin surface of the reference is duck-typed Python (`generate_samples / prior_log_prob / discrepancy`,
+ * examples/Mixture.py:13-36, README.md:66-104).  A model outside the built-in family is given as CUDA C++ source
+ * defining three device functions; the library compiles them (NVRTC, sm_100a) INTO the fused GlobalMCMC step kernel,
+ * so the simulator, prior and discrepancy are inlined into the same single kernel as the proposal, the Gaussian ABC
+ * kernel (Mixture.py:38-53) and the Metropolis-Hastings test:
+ *
+ *   __device__ void  glabc_user_simulate(const float* theta, const float* noise, const float* params, float* y);
+ *       y[y_dim] <- one simulator draw at theta[theta_dim]; noise[n_noise] are independent N(0,1) draws
+ *       (generate_samples, Mixture.py:13-26)
+ *   __device__ float glabc_user_prior_log_prob(const float* theta, const float* params);      (Mixture.py:28-31)
+ *   __device__ float glabc_user_discrepancy(const float* y, const float* params);             (Mixture.py:33-36)
+ *
+ * `params` (<= GLABC_USER_MAX_PARAMS floats) carries the model's constants (y_obs, noise scales, ...).            */
+#define GLABC_USER_MAX_PARAMS 64
+#define GLABC_USER_MAX_NOISE 32
+typedef struct {
+    int32_t theta_dim;        /* 1..GLABC_MAX_DIM                                                            */
+    int32_t y_dim;            /* 1..2*GLABC_MAX_DIM                                                          */
+    int32_t n_noise;          /* N(0,1) draws one simulator call consumes, 0..GLABC_USER_MAX_NOISE           */
+    int32_t n_params;
+    const char* source;       /* NUL-terminated CUDA C++ defining the three functions above                  */
+    float params[GLABC_USER_MAX_PARAMS];
+    double epsilon;           /* width of the Gaussian ABC kernel (Mixture.py:7,43)                          */
+} glabc_user_model_t;
+
 typedef struct glabc_ctx glabc_ctx;
 
 #if defined(__GNUC__)
@@ -337,6 +363,15 @@ GLABC_API int glabc_run_mala(glabc_ctx* ctx, const glabc_run_t* run);
  * 0 flags as run_isir; global move: 1 proposal log-density of the current state, 2 its weight, 3 sum of the
  * K+1 weights; local move: as run_global.                                                                    */
 GLABC_API int glabc_run_aglmcmc(glabc_ctx* ctx, const glabc_run_t* run, const glabc_aglmcmc_t* ag);
+
+/* GlobalMCMC loop body (GlobalMCMC.py:37-68) for a user-supplied model: LOCAL / GLOBAL slots must hold DiagGaussian
+ * proposals of the model's theta_dim; native RNG; run->theta [C][theta_dim], run->y [C][y_dim]; trace / stats as
+ * glabc_run_global.  The first call for a given source compiles it (about a second); the module is cached for the
+ * life of the process.  A compile error is returned as GLABC_ERR_INVALID with the NVRTC log in glabc_last_error.     */
+GLABC_API int glabc_run_global_user(glabc_ctx* ctx, const glabc_run_t* run, const glabc_user_model_t* model);
+/* Compile-only check of a user model for compute capability `cc` (100 = sm_100a): needs NVRTC but neither a GPU nor a
+ * context.  The NVRTC log (or "" on success) is copied to log[log_cap].                                              */
+GLABC_API int glabc_user_model_check(const glabc_user_model_t* model, int32_t cc, char* log, size_t log_cap);
 
 /* ---- KernelDensity (kernel_density.py:4-177), batched over `sets` independent point sets ------------------
  * Set s holds n[s] points X[s][cap][dim] (n == NULL: every set holds `cap` points).                          */
