@@ -521,6 +521,12 @@ def other_kernels(eng, model, lp, gp):
     out["aglmcmc"] = dict(timed(lambda: g.AGLMCMC(model, 2001, z, None, lp, gp, None, 1.0, 200, 5, 0.8, 0.2, num_chains=16384, seed=1,
                                                   trace="none"), 16384 * 2000), unit="chain-steps/s",
                           workload="16,384 chains x 2e3, gf 1, K 5, step 200")
+    from glabc_b200.models import mixture_user_model
+    um, y0 = mixture_user_model(0.05), torch.randn(65536, 2, device="cuda") * 0.2236
+    out["global_user_model_nvrtc"] = dict(timed(lambda: g.GlobalMCMC(um, 10000, z, y0, gp, None, 0.5, lp, num_chains=65536, seed=1,
+                                                                     trace="none"), 65536 * 9999), unit="chain-steps/s",
+                                          workload="65,536 chains x 1e4, the README model given as CUDA source and compiled by NVRTC "
+                                                   "into the step kernel, statistics only")
     X = torch.randn(100000, 2, device="cuda")
     w, bw = eng.kde_fit(X, None)
     out["kde_log_prob"] = dict(timed(lambda: eng.kde_log_prob(X, w, bw, X), 1e10), unit="pairs/s", workload="1e5 queries x 1e5 points, d = 2")

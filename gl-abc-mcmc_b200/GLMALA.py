@@ -12,7 +12,7 @@ from .samplers import run_chains
 
 def GLMALA(ABCset, num_ite, Initial_theta, Initial_y, tau, num_grad, filelocation, global_frequency=0,
            Importance_Proposal=None, batch_size=None, *, num_chains=None, seed=None, chain_id_base=0, arith="fast",
-           trace="chain", return_stats=False, verbose=None, device=None, block_threads=0):
+           trace="chain", return_stats=False, verbose=None, device=None, block_threads=0, checkpoint=None, resume=None):
     """Same positional signature and return value as the reference for one chain; keyword extensions as in
     `GlobalMCMC` (num_chains, seed, chain_id_base, arith, trace, return_stats)."""
     if Importance_Proposal is None or batch_size is None:
@@ -30,4 +30,4 @@ def GLMALA(ABCset, num_ite, Initial_theta, Initial_y, tau, num_grad, filelocatio
                       global_frequency=global_frequency, filelocation=filelocation, num_chains=num_chains, seed=seed,
                       chain_id_base=chain_id_base, arith=arith, trace=trace, return_stats=return_stats, verbose=verbose,
                       K=int(batch_size), aux_init={_abi.AUX_LOCAL: 1.0}, block_threads=block_threads,
-                      num_grad=int(num_grad), tau=float(tau), state64=state64)
+                      num_grad=int(num_grad), tau=float(tau), state64=state64, checkpoint=checkpoint, resume=resume)

@@ -13,7 +13,7 @@ from .samplers import _LAYOUT, default_seed, print_summary, run_chains, write_cs
 
 def GlobalMCMC(ABCset, num_ite, Initial_theta, Initial_y, Global_Proposal, filelocation, global_frequency,
                Local_Proposal=None, *, num_chains=None, seed=None, chain_id_base=0, arith="fast", trace="chain",
-               return_stats=False, verbose=None, device=None, block_threads=0):
+               return_stats=False, verbose=None, device=None, block_threads=0, checkpoint=None, resume=None):
     """Same positional signature and return value as the reference (a float32 CPU tensor
     `[num_ite, theta_dim]`, row 0 = `Initial_theta`) when called for one chain.
 
@@ -36,7 +36,7 @@ def GlobalMCMC(ABCset, num_ite, Initial_theta, Initial_y, Global_Proposal, filel
     return run_chains("global", eng, pod, num_ite=num_ite, Initial_theta=Initial_theta, Initial_y=Initial_y,
                       global_frequency=global_frequency, filelocation=filelocation, num_chains=num_chains, seed=seed,
                       chain_id_base=chain_id_base, arith=arith, trace=trace, return_stats=return_stats, verbose=verbose,
-                      block_threads=block_threads)
+                      block_threads=block_threads, checkpoint=checkpoint, resume=resume)
 
 
 def _global_user(eng, model, num_ite, Initial_theta, Initial_y, Global_Proposal, Local_Proposal, filelocation, gf, num_chains,

@@ -135,6 +135,30 @@ class UserModel:
         return True
 
 
+# examples/Mixture.py:13-36 written as a user model (params = {y_obs0, y_obs1, noise_sd}): the worked example of the
+# run-time compiled path, and what bench.py times beside the built-in family
+MIXTURE_USER_SOURCE = r"""
+__device__ void glabc_user_simulate(const float* theta, const float* noise, const float* params, float* y)
+{
+    y[0] = fabsf(theta[0]) + params[2] * noise[0];
+    y[1] = fabsf(theta[1]) + params[2] * noise[1];
+}
+__device__ float glabc_user_prior_log_prob(const float* theta, const float* params)
+{
+    return -1.8378770664093453f - 0.5f * (theta[0] * theta[0] + theta[1] * theta[1]);
+}
+__device__ float glabc_user_discrepancy(const float* y, const float* params)
+{
+    const float a = y[0] - params[0], b = y[1] - params[1];
+    return sqrtf(a * a + b * b);
+}
+"""
+
+
+def mixture_user_model(epsilon=0.05):
+    return UserModel(MIXTURE_USER_SOURCE, theta_dim=2, y_dim=2, n_noise=2, epsilon=epsilon, params=[1.5, 1.5, 0.05 ** 0.5])
+
+
 def lower_model(abc_set):
     """POD for `abc_set`: our own model classes lower themselves; a foreign object is accepted only
     if it behaves exactly like the AbsNormal family on a deterministic probe (so a reference

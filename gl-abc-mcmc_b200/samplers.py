@@ -72,25 +72,74 @@ def print_summary(chain):
         print(f"  95% Confidence Interval: {(m - 1.96 * std, m + 1.96 * std)}")
 
 
+CHECKPOINT_VERSION = 1
+
+
+def save_checkpoint(path, *, sampler, step_base, seed, chain_id_base, theta, y, stats, aux=None, state64=None):
+    """Everything a run needs to continue bit-identically: the chain state, the carried iSIR / MALA
+    state, the statistics accumulators and the Philox coordinates (seed, global chain id base, next step index) — the
+    generator itself is stateless, so no RNG state exists beyond these three integers."""
+    cpu = lambda t: None if t is None else t.detach().cpu()  # noqa: E731
+    torch.save(dict(version=CHECKPOINT_VERSION, sampler=sampler, step_base=int(step_base), seed=int(seed),
+                    chain_id_base=int(chain_id_base), theta=cpu(theta), y=cpu(y), stats=cpu(stats), aux=cpu(aux),
+                    state64=cpu(state64)), path)
+
+
+def load_checkpoint(path_or_dict, sampler, device):
+    ck = path_or_dict if isinstance(path_or_dict, dict) else torch.load(path_or_dict, map_location="cpu", weights_only=True)
+    if ck.get("version") != CHECKPOINT_VERSION:
+        raise ValueError(f"checkpoint version {ck.get('version')} (this build reads {CHECKPOINT_VERSION})")
+    if ck["sampler"] != sampler:
+        raise ValueError(f"checkpoint was written by the {ck['sampler']!r} sampler, not {sampler!r}")
+    dev = lambda t: None if t is None else t.to(device).contiguous()  # noqa: E731
+    return dict(ck, theta=dev(ck["theta"]), y=dev(ck["y"]), stats=dev(ck["stats"]), aux=dev(ck["aux"]), state64=dev(ck["state64"]))
+
+
 def run_chains(sampler, eng, model_pod, *, num_ite, Initial_theta, Initial_y, global_frequency, filelocation,
                num_chains, seed, chain_id_base, arith, trace, return_stats, verbose, K=0, aux_init=None,
-               block_threads=0, **sampler_kw):
+               block_threads=0, checkpoint=None, resume=None, **sampler_kw):
+    """`checkpoint=path` writes the end-of-run state; `resume=path` continues a run from such a file up to iteration
+    num_ite - 1 (same sampler, model and proposals): the chains continue bit-identically — the returned trace then holds
+    only the NEW rows (iterations step_base + 1 .. num_ite - 1)."""
     if num_ite < 1:
         raise ValueError("num_ite must be at least 1")
-    seed = default_seed() if seed is None else int(seed)
-    theta, y, c = initial_state(eng, model_pod, Initial_theta, Initial_y, num_chains, seed)
     d = model_pod.theta_dim
+    step_base = 0
+    if resume is not None:
+        if sampler == "aglmcmc":
+            raise NotImplementedError("AGLMCMC keeps its candidate block and KDE inside the context: not checkpointed yet")
+        ck = load_checkpoint(resume, sampler, eng.device)
+        theta, y, stats, aux, step_base = ck["theta"], ck["y"], ck["stats"], ck["aux"], ck["step_base"]
+        seed, chain_id_base, c = ck["seed"], ck["chain_id_base"], ck["theta"].shape[0]
+        if theta.shape[1] != d:
+            raise ValueError("checkpoint theta_dim does not match the model")
+        if num_ite - 1 < step_base:
+            raise ValueError(f"the checkpoint is already at iteration {step_base}")
+        if "state64" in sampler_kw:
+            sampler_kw["state64"] = ck["state64"]
+    else:
+        seed = default_seed() if seed is None else int(seed)
+        theta, y, c = initial_state(eng, model_pod, Initial_theta, Initial_y, num_chains, seed)
+        stats = torch.zeros(c, _abi.nstats(d), dtype=torch.float32, device=eng.device)
+        aux = None
+        if aux_init is not None:
+            aux = torch.zeros(c, _abi.AUX_SLOTS, dtype=torch.float32, device=eng.device)
+            for slot, val in aux_init.items():
+                aux[:, slot] = val
     single = num_chains is None and c == 1
     layout = _LAYOUT[trace]
-    stats = torch.zeros(c, _abi.nstats(d), dtype=torch.float32, device=eng.device)
-    aux = None
-    if aux_init is not None:
-        aux = torch.zeros(c, _abi.AUX_SLOTS, dtype=torch.float32, device=eng.device)
-        for slot, val in aux_init.items():
-            aux[:, slot] = val
-    out = eng.run(sampler, theta=theta, y=y, n_steps=num_ite - 1, gf=global_frequency, seed=seed,
+    resumed = dict(step_base=step_base, trace_row_base=step_base + 1, write_row0=False,
+                   trace_rows=num_ite - 1 - step_base) if resume is not None else {}
+    if resume is not None and num_ite - 1 == step_base:
+        layout = _abi.TRACE_NONE
+    out = eng.run(sampler, theta=theta, y=y, n_steps=num_ite - 1 - step_base, gf=global_frequency, seed=seed,
                   chain_id_base=chain_id_base, arith=_ARITH[arith], trace_layout=layout, stats=stats, aux=aux, K=K,
-                  block_threads=block_threads, **sampler_kw)
+                  block_threads=block_threads, **resumed, **sampler_kw)
+    if checkpoint is not None:
+        if sampler == "aglmcmc":
+            raise NotImplementedError("AGLMCMC keeps its candidate block and KDE inside the context: not checkpointed yet")
+        save_checkpoint(checkpoint, sampler=sampler, step_base=num_ite - 1, seed=seed, chain_id_base=chain_id_base, theta=theta,
+                        y=y, stats=stats, aux=aux, state64=sampler_kw.get("state64"))
     rs = RunStats(stats, d)
     if single:
         chain = (out[0] if layout == _abi.TRACE_CHAIN_MAJOR else out[:, 0]).cpu() if out is not None else None
