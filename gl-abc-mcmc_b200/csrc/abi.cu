@@ -383,14 +383,17 @@ static int run_device(glabc_ctx* ctx, SamplerKind kind, const glabc_run_t* run)
         if (st) return st;
         if (R.n_chains == 0) return GLABC_OK;
         if (!all_gaussian(ctx, {GLABC_SLOT_LOCAL, GLABC_SLOT_GLOBAL})) {
-            // Uniform / Gamma / GaussianMixture proposals: the general kernel (native RNG, float32)
-            if (run->rng_mode != GLABC_RNG_NATIVE || run->tape_dump)
-                return fail(ctx, GLABC_ERR_UNSUPPORTED, "replay / tape dump exist for DiagGaussian proposals only");
+            // Uniform / Gamma / GaussianMixture proposals: the general kernel (float32; replay takes the proposal draws
+            // themselves: tape32 [steps][2 + d][C] = U_b, eps_sim, U_a and tape64 [steps][d][C] = the draw in float64)
+            if (run->tape_dump) return fail(ctx, GLABC_ERR_UNSUPPORTED, "tape dump exists for DiagGaussian proposals only");
+            if (run->rng_mode == GLABC_RNG_REPLAY && !run->tape64)
+                return fail(ctx, GLABC_ERR_INVALID, "replay with non-Gaussian proposals needs tape64 [n_steps][%d][n_chains] (the proposal draws)", d);
             GenericConsts G{};
             G.model = make_model(ctx->model);
             G.lp = make_dist(lp);
             G.gp = make_dist(gp);
-            CUDA_TRY(ctx, launch_global_generic(G, d, R, run->trace_layout, block, static_cast<cudaStream_t>(run->stream)));
+            CUDA_TRY(ctx, launch_global_generic(G, d, R, run->trace_layout, block, run->rng_mode == GLABC_RNG_REPLAY,
+                                                static_cast<cudaStream_t>(run->stream)));
             return GLABC_OK;
         }
         CUDA_TRY(ctx, launch_global_mcmc(make_model(ctx->model), make_gauss(lp.a, lp.b, lp.c, d), make_gauss(gp.a, gp.b, gp.c, d),

@@ -4,22 +4,27 @@
 namespace glabc {
 
 template <int D>
-static cudaError_t generic_dim(const GenericConsts& K, const RunParams& R, int layout, int block, cudaStream_t st)
+static cudaError_t generic_dim(const GenericConsts& K, const RunParams& R, int layout, int block, bool replay, cudaStream_t st)
 {
     const unsigned grid = static_cast<unsigned>((R.n_chains + block - 1) / block);
-    if (K.model.family == GLABC_MODEL_ABS_NORMAL) k_global_generic<D, GLABC_MODEL_ABS_NORMAL><<<grid, block, 0, st>>>(K, R, layout);
-    else k_global_generic<D, GLABC_MODEL_ID_NORMAL><<<grid, block, 0, st>>>(K, R, layout);
+    if (replay) {
+        if (K.model.family == GLABC_MODEL_ABS_NORMAL) k_global_generic<D, GLABC_MODEL_ABS_NORMAL, true><<<grid, block, 0, st>>>(K, R, layout);
+        else k_global_generic<D, GLABC_MODEL_ID_NORMAL, true><<<grid, block, 0, st>>>(K, R, layout);
+    } else {
+        if (K.model.family == GLABC_MODEL_ABS_NORMAL) k_global_generic<D, GLABC_MODEL_ABS_NORMAL, false><<<grid, block, 0, st>>>(K, R, layout);
+        else k_global_generic<D, GLABC_MODEL_ID_NORMAL, false><<<grid, block, 0, st>>>(K, R, layout);
+    }
     return cudaGetLastError();
 }
 
-cudaError_t launch_global_generic(const GenericConsts& K, int dim, const RunParams& R, int layout, int block, cudaStream_t st)
+cudaError_t launch_global_generic(const GenericConsts& K, int dim, const RunParams& R, int layout, int block, bool replay, cudaStream_t st)
 {
     if (block > 128) block = 128;
     switch (dim) {
-    case 1: return generic_dim<1>(K, R, layout, block, st);
-    case 2: return generic_dim<2>(K, R, layout, block, st);
-    case 3: return generic_dim<3>(K, R, layout, block, st);
-    case 4: return generic_dim<4>(K, R, layout, block, st);
+    case 1: return generic_dim<1>(K, R, layout, block, replay, st);
+    case 2: return generic_dim<2>(K, R, layout, block, replay, st);
+    case 3: return generic_dim<3>(K, R, layout, block, replay, st);
+    case 4: return generic_dim<4>(K, R, layout, block, replay, st);
     default: return cudaErrorInvalidValue;
     }
 }

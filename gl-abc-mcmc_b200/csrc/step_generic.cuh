@@ -179,18 +179,27 @@ __device__ __forceinline__ float dist_forward(const DistConsts& q, WordStream& w
     return NAN;
 }
 
-// GlobalMCMC.py:37-68 with arbitrary proposal kinds
-template <int D, int FAMILY>
+// GlobalMCMC.py:37-68 with arbitrary proposal kinds.
+// REPLAY (parity mode): the reference's own draws drive the step — tape32 [steps][2 + D][C] = U_b, eps_sim[D], U_a and
+// tape64 [steps][D][C] = the proposal's draw in float64 (theta' of a global move, the increment z of a local one; Gamma and
+// GaussianMixture draw in float64, distribution.py:118,238-240).  The state is carried in float64 with the reference's dtype
+// promotion: theta becomes a float64 tensor after the first accepted float64 candidate, and `z + theta` is then a float64
+// add (GlobalMCMC.py:56) — so the float32 trace rows (Theta_Re[i] = Theta_old, :52,67) match bit for bit.  Densities are
+// evaluated in float32 from the rounded state (the reference's are float64 after promotion: agreement to 1e-6).
+template <int D, int FAMILY, bool REPLAY>
 __global__ void __launch_bounds__(128) k_global_generic(const __grid_constant__ GenericConsts K, const __grid_constant__ RunParams R,
                                                         int layout)
 {
     const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (c >= R.n_chains) return;
     float theta[D], y[D];
+    double th64[D];
+    bool wide = false;
 #pragma unroll
     for (int k = 0; k < D; ++k) {
         theta[k] = R.theta[c * D + k];
         y[k] = R.y[c * D + k];
+        th64[k] = static_cast<double>(theta[k]);
     }
     auto put = [&](uint32_t row_abs) {
         if (layout == GLABC_TRACE_NONE) return;
@@ -203,24 +212,58 @@ __global__ void __launch_bounds__(128) k_global_generic(const __grid_constant__ 
     ChainStats<D> stats;
     const Stream stream = chain_stream(R, static_cast<int32_t>(c));
     float prior_old = model_prior<D, false>(K.model, theta), kern_old = model_log_kernel<D, false>(K.model, y);
+    const bool lp64 = K.lp.kind == GLABC_DIST_GAMMA || K.lp.kind == GLABC_DIST_GAUSSIAN_MIXTURE;
+    const bool gp64 = K.gp.kind == GLABC_DIST_GAMMA || K.gp.kind == GLABC_DIST_GAUSSIAN_MIXTURE;
 
     for (uint32_t i = R.first_step; i <= R.last_step && R.last_step >= R.first_step; ++i) {
-        const uint4 w0 = stream.block(R.rk, i, kSlotStep);
-        const bool is_global = (step_block_ub(w0) < R.gf_thr_hi) || R.gf_all_global;  // GlobalMCMC.py:39
-        const float log_w = log_approx(__uint2float_rn(step_block_ua(w0)) * 0x1p-24f);  // :47,62
-        WordStream ws(R.rk, stream, i, kSlotGeneric);
-        float th_p[D], y_p[D], eps_s[D], corr = 0.0f;
-        if (is_global) {
-            const float lq_p = dist_forward<D>(K.gp, ws, th_p);       // :40
-            corr = dist_log_prob<D>(K.gp, theta) - lq_p;              // :45-46
+        bool is_global, p_wide = false;
+        float log_w, th_p[D], y_p[D], eps_s[D], corr = 0.0f;
+        double th_p64[D];
+        if constexpr (REPLAY) {
+            const int64_t srow = static_cast<int64_t>(i - R.first_step), C = R.n_chains;
+            const float* tp = R.tape32 + srow * (2 + D) * C + c;
+            is_global = __ldg(tp) < R.gf;                                            // GlobalMCMC.py:39
+            log_w = logf(__ldg(tp + static_cast<int64_t>(1 + D) * C));                // :47,62
+            double draw[D];
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                eps_s[k] = __ldg(tp + static_cast<int64_t>(1 + k) * C);
+                draw[k] = R.tape64[(srow * D + k) * C + c];
+            }
+            if (is_global) {
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    th_p64[k] = draw[k];
+                    th_p[k] = static_cast<float>(draw[k]);
+                }
+                corr = dist_log_prob<D>(K.gp, theta) - dist_log_prob<D>(K.gp, th_p);   // :45-46 (forward's log_p == log_prob(theta'))
+                p_wide = gp64;
+            } else {
+                p_wide = wide || lp64;                                                // dtype of z + Theta_old, :56
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    th_p64[k] = p_wide ? draw[k] + th64[k]
+                                       : static_cast<double>(__fadd_rn(static_cast<float>(draw[k]), static_cast<float>(th64[k])));
+                    th_p[k] = static_cast<float>(th_p64[k]);
+                }
+            }
         } else {
-            float z[D];
-            (void)dist_forward<D>(K.lp, ws, z);                       // Local_Proposal.sample(1), :56
+            const uint4 w0 = stream.block(R.rk, i, kSlotStep);
+            is_global = (step_block_ub(w0) < R.gf_thr_hi) || R.gf_all_global;  // GlobalMCMC.py:39
+            log_w = log_approx(__uint2float_rn(step_block_ua(w0)) * 0x1p-24f);  // :47,62
+            WordStream ws(R.rk, stream, i, kSlotGeneric);
+            if (is_global) {
+                const float lq_p = dist_forward<D>(K.gp, ws, th_p);       // :40
+                corr = dist_log_prob<D>(K.gp, theta) - lq_p;              // :45-46
+            } else {
+                float z[D];
+                (void)dist_forward<D>(K.lp, ws, z);                       // Local_Proposal.sample(1), :56
 #pragma unroll
-            for (int k = 0; k < D; ++k) th_p[k] = z[k] + theta[k];
+                for (int k = 0; k < D; ++k) th_p[k] = z[k] + theta[k];
+            }
+#pragma unroll
+            for (int k = 0; k < D; ++k) eps_s[k] = ws.normal();
         }
-#pragma unroll
-        for (int k = 0; k < D; ++k) eps_s[k] = ws.normal();
         model_simulate<D, false>(K.model, th_p, eps_s, y_p);           // :41,57
         const float prior_p = model_prior<D, false>(K.model, th_p), kern_p = model_log_kernel<D, false>(K.model, y_p);
         const float log_acc = (prior_p + kern_p) + corr - (prior_old + kern_old);   // :44-46 / :60-61
@@ -233,12 +276,23 @@ __global__ void __launch_bounds__(128) k_global_generic(const __grid_constant__ 
             for (int k = 0; k < D; ++k) {
                 theta[k] = th_p[k];
                 y[k] = y_p[k];
+                if constexpr (REPLAY) th64[k] = th_p64[k];
             }
             prior_old = prior_p;
             kern_old = kern_p;
+            if constexpr (REPLAY) wide = p_wide;
         }
         stats.update(is_global, accept, theta, prev);
         put(i);
+        if constexpr (REPLAY) {
+            if (R.debug != nullptr) {
+                float* g = R.debug + static_cast<int64_t>(i - R.first_step) * GLABC_DEBUG_SLOTS * R.n_chains + c;
+                g[0] = static_cast<float>(static_cast<int>(is_global) | (static_cast<int>(accept) << 1));
+                g[R.n_chains] = prior_p;
+                g[2 * static_cast<int64_t>(R.n_chains)] = kern_p;
+                g[3 * static_cast<int64_t>(R.n_chains)] = log_acc;
+            }
+        }
     }
 #pragma unroll
     for (int k = 0; k < D; ++k) {
@@ -271,7 +325,7 @@ __global__ void __launch_bounds__(256) k_dist_eval(const __grid_constant__ DistC
     if (logp != nullptr) logp[g] = lp;
 }
 
-cudaError_t launch_global_generic(const GenericConsts& K, int dim, const RunParams& R, int layout, int block, cudaStream_t st);
+cudaError_t launch_global_generic(const GenericConsts& K, int dim, const RunParams& R, int layout, int block, bool replay, cudaStream_t st);
 cudaError_t launch_dist_eval(const DistConsts& q, int dim, const RoundKeys& rk, int64_t n, const float* z_in, float* z_out, float* logp,
                              cudaStream_t st);
 

@@ -343,7 +343,9 @@ GLABC_API int glabc_dist_sample(glabc_ctx* ctx, int slot, int64_t n, uint64_t se
 /* ---- samplers: device buffers, asynchronous on `stream` ------------------------------------- */
 /* GlobalMCMC loop body, GlobalMCMC.py:37-68 (local RW-MH / global independence-MH mixture).  DiagGaussian proposals
  * in both slots run the tuned kernel (replay + strict arithmetic available); any Uniform / Gamma / GaussianMixture
- * proposal selects the general kernel (native RNG, float32).                                                       */
+ * proposal selects the general kernel (float32).  Its replay mode takes the reference's proposal draws themselves:
+ * tape32 [n_steps][2 + d][C] = U_b, eps_sim[d], U_a and tape64 [n_steps][d][C] = the draw in float64 (theta' of a global
+ * move, the increment of a local one); debug slots 0..3 as for the tuned kernel.                                    */
 GLABC_API int glabc_run_global(glabc_ctx* ctx, const glabc_run_t* run);
 
 /* GLMCMC loop body, GLMCMC.py:58-104, incl. weight_sampling GLMCMC.py:7-22: iSIR global move with

@@ -1,0 +1,85 @@
+"""TEST INFRASTRUCTURE — not part of the product (only tests/ may import this).
+
+numpy (float64) restatement of the reference's GlobalMCMC loop body (GlobalMCMC.py:37-68) for ANY of its proposal classes
+in the Local / Global slots — Uniform (distribution.py:50-86), Gamma (:90-137), DiagGaussian (:143-203), GaussianMixture
+(:206-293) — driven by recorded draws (replay).  Pinned by tests/golden/global_generic.npz, which was recorded from the
+reference itself (tests/golden/make_golden.py `golden_global_generic`); the CUDA kernel `k_global_generic<REPLAY>` is
+checked against the same recordings.  Pure-Python loop: small cases only."""
+import math
+
+import numpy as np
+from scipy.special import gammaln, logsumexp
+
+HALF_LOG_2PI = 0.5 * math.log(2 * math.pi)
+
+
+def log_prob(spec, z):
+    """log density of one point z[d] under `spec` (dict: kind + parameters as in the golden file)"""
+    kind = spec["kind"]
+    z = np.asarray(z, np.float64)
+    if kind == "gauss":       # distribution.py:176-181
+        ls = np.log(np.asarray(spec["sigma"], np.float64))
+        r = (z - spec["loc"]) / np.exp(ls)
+        return -len(z) * HALF_LOG_2PI - np.sum(ls + 0.5 * r * r)
+    if kind == "uniform":     # :79-85
+        if np.any(z < spec["low"]) or np.any(z > spec["high"]):
+            return -np.inf
+        return -math.log(np.prod(np.asarray(spec["high"]) - np.asarray(spec["low"])))
+    if kind == "gamma":       # :122-137: log pdf, -inf where the pdf is 0
+        a, b = np.asarray(spec["shape"], np.float64), np.asarray(spec["rate"], np.float64)
+        if np.any(z < 0) or np.any((z == 0) & (a != 1)):
+            return -np.inf
+        with np.errstate(divide="ignore"):
+            return float(np.sum(a * np.log(b) - gammaln(a) + (a - 1) * np.log(z) - b * z))
+    if kind == "mixture":     # :270-291
+        loc, sc = np.asarray(spec["loc"], np.float64), np.asarray(spec["scale"], np.float64)
+        w = np.asarray(spec["weights"], np.float64)
+        w = w / w.sum()
+        eps = (z[None, :] - loc) / sc
+        return float(logsumexp(-len(z) * HALF_LOG_2PI + np.log(w) - 0.5 * np.sum(eps * eps, 1) - np.sum(np.log(sc), 1)))
+    raise ValueError(kind)
+
+
+def is_float64_kind(spec):
+    return spec["kind"] in ("gamma", "mixture")   # scipy / nn.Parameter(float64): distribution.py:118,238-240
+
+
+def replay_chain(model, lp, gp, theta0, y0, gf, tape32, tape64):
+    """One chain.  model: dict(y_obs, noise_scale, eps_scale, eps_log_scale); tape32 [steps][4] = U_b, eps_sim[2], U_a;
+    tape64 [steps][2] = the proposal's draw.  Returns (trace float32 [steps + 1][2], rec [steps][4] = flags, prior', kernel',
+    log_acc).  Mixture.py:13-53 for the model, prior N(0, I)."""
+    y_obs, ns = np.asarray(model["y_obs"], np.float64), np.asarray(model["noise_scale"], np.float64)
+    eps, leps = float(model["eps_scale"]), float(model["eps_log_scale"])
+
+    def prior(th):
+        return -len(th) * HALF_LOG_2PI - 0.5 * float(np.sum(th * th))
+
+    def kernel(y):
+        dis = math.sqrt(float(np.sum((y - y_obs) ** 2)))
+        return -HALF_LOG_2PI - (leps + 0.5 * (dis / eps) ** 2)
+
+    steps = tape32.shape[0]
+    theta, y, wide = np.asarray(theta0, np.float64), np.asarray(y0, np.float64), False
+    trace = np.zeros((steps + 1, len(theta)), np.float32)
+    trace[0] = theta
+    rec = np.zeros((steps, 4))
+    for s in range(steps):
+        u_b, u_a, e_s, draw = tape32[s, 0], tape32[s, 3], tape32[s, 1:3].astype(np.float64), tape64[s]
+        is_global = bool(np.float32(u_b) < np.float32(gf))            # GlobalMCMC.py:39
+        if is_global:
+            th_p, p_wide = draw.copy(), is_float64_kind(gp)
+            corr = log_prob(gp, theta) - log_prob(gp, th_p)           # :45-46
+        else:
+            p_wide = wide or is_float64_kind(lp)
+            th_p = draw + theta if p_wide else (draw.astype(np.float32) + theta.astype(np.float32)).astype(np.float64)   # :56
+            corr = 0.0
+        y_p = np.abs(th_p) + ns * e_s                                 # :41,57 (Mixture.py:13-26)
+        pr_p, k_p = prior(th_p), kernel(y_p)
+        log_acc = pr_p + k_p + corr - prior(theta) - kernel(y)        # :44-46 / :60-61
+        with np.errstate(divide="ignore"):
+            accept = bool(np.log(np.float32(u_a)) < log_acc)          # :47-49,62-64
+        if accept:
+            theta, y, wide = th_p, y_p, p_wide
+        trace[s + 1] = theta
+        rec[s] = [int(is_global) | (int(accept) << 1), pr_p, k_p, log_acc]
+    return trace, rec

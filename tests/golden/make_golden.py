@@ -235,6 +235,113 @@ def golden_global(cases, T, out_path):
 
 
 # ----------------------------------------------------------------------------------------------
+# GlobalMCMC with Uniform / Gamma / GaussianMixture proposals (distribution.py:50-137,206-293)
+# ----------------------------------------------------------------------------------------------
+def make_dist(distribution, spec):
+    kind = spec["kind"]
+    if kind == "gauss":
+        return distribution.DiagGaussian(2, torch.tensor(spec["loc"]).view(1, 2), torch.log(torch.tensor(spec["sigma"])))
+    if kind == "uniform":
+        return distribution.Uniform(2, low=torch.tensor(spec["low"]), high=torch.tensor(spec["high"]))
+    if kind == "gamma":
+        return distribution.Gamma(torch.tensor(spec["shape"]), torch.tensor(spec["rate"]))
+    if kind == "mixture":
+        return distribution.GaussianMixture(len(spec["loc"]), 2, loc=spec["loc"], scale=spec["scale"], weights=spec["weights"])
+    raise ValueError(kind)
+
+
+def dist_spec_arrays(spec, prefix):
+    """flat description of a proposal for the test side (rebuilt there with the product's own classes)"""
+    out = {prefix + "_kind": np.array(["gauss", "uniform", "gamma", "mixture"].index(spec["kind"]), np.int64)}
+    for k, v in spec.items():
+        if k != "kind":
+            out[f"{prefix}_{k}"] = np.asarray(v, np.float64)
+    return out
+
+
+N_EVENTS = {"gauss": ["N32"], "uniform": ["U32"], "gamma": [], "mixture": ["MULTI", "N32"]}   # draws one forward() makes
+
+
+def golden_global_generic(cases, T, out_path):
+    """tape32 [T-1][4][C] = U_b, eps_sim[2], U_a; tape64 [T-1][2][C] = the proposal's own draw in float64 (theta' of a
+    global move, the increment z of a local one); rec [T-1][8][C] = flags, prior', kernel', log_acc, y'[2], theta'[2]."""
+    import glabcmcmc.distribution as distribution
+    from Mixture import Mixture_set
+    GlobalMCMC = sys.modules["glabcmcmc.GlobalMCMC"].GlobalMCMC
+    blobs = {}
+    for ci, case in enumerate(cases):
+        C, gf = case["chains"], case["gf"]
+        model = Mixture_set(case["epsilon"])
+        lp, gp = make_dist(distribution, case["lp"]), make_dist(distribution, case["gp"])
+        tape32 = np.zeros((T - 1, 4, C), np.float32)
+        tape64 = np.zeros((T - 1, 2, C), np.float64)
+        trace = np.zeros((T, C, 2), np.float32)
+        theta0s, y0s = np.zeros((C, 2), np.float32), np.zeros((C, 2), np.float32)
+        rec = np.zeros((T - 1, 8, C), np.float64)
+        for c in range(C):
+            torch.manual_seed(5000 + 1000 * ci + c)
+            np.random.seed(5000 + 1000 * ci + c)
+            theta0 = torch.tensor(case["theta0"])
+            y0 = model.generate_samples(theta0)
+            log = []
+            pm = CallLog(model, "model", ("generate_samples", "prior_log_prob", "calculate_log_kernel"), log)
+            plp = CallLog(lp, "lp", ("sample",), log)
+            pgp = CallLog(gp, "gp", ("forward", "log_prob"), log)
+            with Tape() as tape, quiet():
+                chain = GlobalMCMC(pm, T, theta0, y0, pgp, None, gf, plp)
+            ev = tape.events
+            theta0s[c], y0s[c] = theta0.numpy(), y0.view(-1).numpy()
+            trace[:, c] = chain.detach().numpy()
+            li = ei = 0
+            for s in range(T - 1):
+                assert ev[ei][0] == "U32", ev[ei][0]
+                u_b = ev[ei][1][0]
+                ei += 1
+                is_global = bool(np.float32(u_b) < np.float32(gf))
+                for kind in N_EVENTS[case["gp" if is_global else "lp"]["kind"]]:
+                    assert ev[ei][0] == kind, (ev[ei][0], kind)
+                    ei += 1
+                assert ev[ei][0] == "N32" and ev[ei + 1][0] == "U32"
+                n_s, u_a = ev[ei][1], ev[ei + 1][1][0]
+                ei += 2
+                tape32[s, :, c] = [u_b, n_s[0, 0], n_s[0, 1], u_a]
+                if is_global:
+                    (th_p, lq_p), y_p, pr_p, k_p, lq_o, pr_o, k_o = [x[2] for x in log[li:li + 7]]
+                    assert [x[1] for x in log[li:li + 7]] == ["forward", "generate_samples", "prior_log_prob", "calculate_log_kernel",
+                                                              "log_prob", "prior_log_prob", "calculate_log_kernel"]
+                    li += 7
+                    draw = np.asarray(th_p, np.float64).reshape(-1)
+                    acc = float(pr_p[0]) + float(k_p[0]) + float(lq_o[0]) - float(lq_p[0]) - float(pr_o[0]) - float(k_o[0])
+                    th_new = draw
+                else:
+                    z, y_p, pr_p, k_p, pr_o, k_o = [x[2] for x in log[li:li + 6]]
+                    assert [x[1] for x in log[li:li + 6]] == ["sample", "generate_samples", "prior_log_prob", "calculate_log_kernel",
+                                                              "prior_log_prob", "calculate_log_kernel"]
+                    li += 6
+                    draw = np.asarray(z, np.float64).reshape(-1)
+                    acc = float(pr_p[0]) + float(k_p[0]) - float(pr_o[0]) - float(k_o[0])
+                    th_new = np.full(2, np.nan)
+                tape64[s, :, c] = draw
+                accepted = bool(np.any(trace[s + 1, c] != trace[s, c]))
+                rec[s, 0, c] = int(is_global) | (int(accepted) << 1)
+                rec[s, 1, c], rec[s, 2, c], rec[s, 3, c] = float(pr_p[0]), float(k_p[0]), acc
+                rec[s, 4:6, c] = np.asarray(y_p, np.float64).reshape(-1)
+                rec[s, 6:8, c] = th_new
+            assert li == len(log) and ei == len(ev), (li, len(log), ei, len(ev))
+        blob = dict(tape32=tape32, tape64=tape64, trace=trace, theta0=theta0s, y0=y0s, rec=rec, gf=np.float64(gf), T=np.int64(T))
+        blob.update(model_params(model))
+        blob.update(dist_spec_arrays(case["lp"], "lp"))
+        blob.update(dist_spec_arrays(case["gp"], "gp"))
+        for k, v in blob.items():
+            blobs[f"case{ci}/{k}"] = v
+        flags = rec[:, 0].astype(int)
+        print(f"generic case {ci}: lp={case['lp']['kind']} gp={case['gp']['kind']} gf={gf} global accept "
+              f"{np.mean(((flags >> 1) & 1)[(flags & 1) == 1]):.4f} local accept {np.mean(((flags >> 1) & 1)[(flags & 1) == 0]):.4f}")
+    blobs["n_cases"] = np.int64(len(cases))
+    np.savez_compressed(out_path, **blobs)
+
+
+# ----------------------------------------------------------------------------------------------
 # GLMCMC (GLMCMC.py:58-104)
 # ----------------------------------------------------------------------------------------------
 def golden_isir(cases, T, out_path):
@@ -834,6 +941,21 @@ def main():
         golden_kde(os.path.join(HERE, "kde.npz"))
     if not only or "resample" in only:
         golden_resample(os.path.join(HERE, "resample.npz"))
+    modes = [[1.4, 1.4], [1.4, -1.4], [-1.4, 1.4], [-1.4, -1.4]]
+    gauss = dict(kind="gauss", loc=[0.0, 0.0], sigma=[0.35, 0.35])
+    gcases = [
+        dict(chains=6, epsilon=0.2, theta0=[0.0, 0.0], gf=0.5, lp=gauss,          # float64 mixture as the global proposal
+             gp=dict(kind="mixture", loc=modes, scale=[[0.35, 0.35]] * 4, weights=[1.0, 2.0, 1.0, 1.0])),
+        dict(chains=6, epsilon=0.2, theta0=[0.0, 0.0], gf=0.4, lp=dict(kind="uniform", low=[-0.6, -0.6], high=[0.6, 0.6]),
+             gp=dict(kind="uniform", low=[-3.0, -3.0], high=[3.0, 3.0])),
+        dict(chains=6, epsilon=0.2, theta0=[1.0, 1.0], gf=0.5, lp=dict(kind="gauss", loc=[0.0, 0.0], sigma=[0.3, 0.3]),
+             gp=dict(kind="gamma", shape=[6.0, 6.0], rate=[4.0, 4.0])),           # support theta > 0 only
+        dict(chains=6, epsilon=0.2, theta0=[0.0, 0.0], gf=0.3,                     # float64 increments from a local mixture
+             lp=dict(kind="mixture", loc=[[0.3, 0.3], [-0.3, -0.3]], scale=[[0.2, 0.2]] * 2, weights=[1.0, 1.0]),
+             gp=dict(kind="gauss", loc=[0.0, 0.0], sigma=[1.0, 1.0])),
+    ]
+    if not only or "generic" in only:
+        golden_global_generic(gcases, 800, os.path.join(HERE, "global_generic.npz"))
     if only:
         return
     base = dict(chains=4, epsilon=0.05, theta0=[0.0, 0.0], lp_loc=[0.0, 0.0], lp_sigma=[0.35, 0.35],

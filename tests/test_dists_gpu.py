@@ -123,3 +123,50 @@ def test_non_gaussian_proposals_are_refused_where_not_fused(eng):
     box = g.Uniform(2, torch.tensor([-3.0, -3.0]), torch.tensor([3.0, 3.0]))
     with pytest.raises(abi.GlabcError, match="DiagGaussian"):
         g.GLMCMC(model, 100, torch.zeros(2), None, lp, None, 0.9, box, 5, num_chains=64)
+
+
+def _dist_from_golden(z, ci, prefix):
+    import glabc_b200 as g
+    kind = ["gauss", "uniform", "gamma", "mixture"][int(z[f"case{ci}/{prefix}_kind"])]
+    get = lambda k: z[f"case{ci}/{prefix}_{k}"]  # noqa: E731
+    t = lambda k: torch.from_numpy(get(k)).float()  # noqa: E731
+    if kind == "gauss":
+        return g.DiagGaussian(2, t("loc").view(1, 2), torch.log(t("sigma")))
+    if kind == "uniform":
+        return g.Uniform(2, low=t("low"), high=t("high"))
+    if kind == "gamma":
+        return g.Gamma(t("shape"), t("rate"))
+    return g.GaussianMixture(get("loc").shape[0], 2, loc=get("loc"), scale=get("scale"), weights=get("weights"))
+
+
+@pytest.mark.parametrize("ci", [0, 1, 2, 3])
+def test_global_mcmc_replay_with_reference_recordings(eng, ci):
+    """tests/golden/global_generic.npz: the REFERENCE's GlobalMCMC run with GaussianMixture / Uniform / Gamma proposals
+    (distribution.py:50-137,206-293), every draw recorded.  Fed the same draws, the general kernel must take the same
+    branch and the same accept / reject decision at every step, write the same float32 trace bit for bit (float64 state
+    promotion reproduced), and agree on log prior, log kernel and log_acc within 1e-5 relative."""
+    import glabc_b200 as g
+    z = np.load(os.path.join(GOLDEN, "global_generic.npz"))
+    p = lambda k: z[f"case{ci}/{k}"]  # noqa: E731
+    model = g.Mixture_set(float(p("epsilon")))
+    eng.bind_model(model)
+    eng.bind_proposal(abi.SLOT_LOCAL, _dist_from_golden(z, ci, "lp"))
+    eng.bind_proposal(abi.SLOT_GLOBAL, _dist_from_golden(z, ci, "gp"))
+    T, Cn = int(p("T")), p("theta0").shape[0]
+    theta, y = torch.from_numpy(p("theta0")).cuda(), torch.from_numpy(p("y0")).cuda()
+    tape32, tape64 = torch.from_numpy(p("tape32")).cuda().contiguous(), torch.from_numpy(p("tape64")).cuda().contiguous()
+    debug = torch.zeros(T - 1, abi.DEBUG_SLOTS, Cn, device="cuda")
+    got = eng.run("global", theta=theta, y=y, n_steps=T - 1, gf=float(p("gf")), rng_mode=abi.RNG_REPLAY, tape32=tape32,
+                  tape64=tape64, debug=debug, trace_layout=abi.TRACE_TIME_MAJOR).cpu().numpy()
+    dbg, rec = debug.cpu().numpy().astype(np.float64), p("rec")
+    assert np.array_equal(dbg[:, 0], rec[:, 0])                 # branch + accept decision of every step
+    assert np.array_equal(got, p("trace"))                      # the chains, bit for bit
+    for slot, name in ((1, "log prior"), (2, "log kernel"), (3, "log_acc")):
+        a, b = dbg[:, slot], rec[:, slot]
+        fin = np.isfinite(b)
+        assert np.array_equal(np.isneginf(a), np.isneginf(b)), name
+        # log_acc is a difference of O(100) terms: relative to the size of the terms, not of the result
+        scale = np.maximum(np.abs(b[fin]), 1.0) if slot != 3 else np.maximum(np.abs(rec[:, 2][fin]) + np.abs(b[fin]), 1.0)
+        assert np.max(np.abs(a[fin] - b[fin]) / scale) < 1e-5, name
+    flags = rec[:, 0].astype(int)
+    assert ((flags & 1) == 1).any() and ((flags & 1) == 0).any() and ((flags >> 1) & 1).sum() > 50

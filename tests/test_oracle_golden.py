@@ -148,3 +148,32 @@ def test_resample_golden():
         got = resample(torch.from_numpy(z[f"rs{i}/W"]), int(z[f"rs{i}/N"]))
         assert np.array_equal(got.numpy(), z[f"rs{i}/idx"]), i
     assert len(z["rs2/idx"]) < int(z["rs2/N"])
+
+
+def test_generic_proposal_oracle_reproduces_the_reference_recordings():
+    """GlobalMCMC with GaussianMixture / Uniform / Gamma proposals: the numpy restatement (oracle/generic_oracle.py), fed
+    the reference's recorded draws, reproduces its decisions and its float32 chains bit for bit (tests/golden/global_generic.npz)"""
+    import os
+    from helpers import GOLDEN
+    from oracle import generic_oracle as go
+    z = np.load(os.path.join(GOLDEN, "global_generic.npz"))
+    kinds = ["gauss", "uniform", "gamma", "mixture"]
+    for ci in range(int(z["n_cases"])):
+        p = lambda k: z[f"case{ci}/{k}"]  # noqa: E731
+
+        def spec(prefix):
+            out = {"kind": kinds[int(p(prefix + "_kind"))]}
+            for key in z.files:
+                if key.startswith(f"case{ci}/{prefix}_") and not key.endswith("_kind"):
+                    out[key.split(f"{prefix}_", 1)[1]] = z[key]
+            return out
+        lp, gp = spec("lp"), spec("gp")
+        model = dict(y_obs=p("y_obs"), noise_scale=p("noise_scale"), eps_scale=p("eps_scale"), eps_log_scale=p("eps_log_scale"))
+        for c in range(min(3, p("theta0").shape[0])):
+            trace, rec = go.replay_chain(model, lp, gp, p("theta0")[c], p("y0")[c], float(p("gf")), p("tape32")[:, :, c], p("tape64")[:, :, c])
+            assert np.array_equal(rec[:, 0], p("rec")[:, 0, c]), (ci, c)
+            assert np.array_equal(trace, p("trace")[:, c]), (ci, c)
+            want = p("rec")[:, 1:4, c]
+            fin = np.isfinite(want)
+            assert np.array_equal(np.isneginf(rec[:, 1:4]), np.isneginf(want))
+            assert np.max(np.abs(rec[:, 1:4][fin] - want[fin]) / np.maximum(np.abs(want[fin]), 1.0)) < 1e-4   # the reference is float32 before promotion
