@@ -750,8 +750,9 @@ extern "C" int glabc_kde_log_prob(glabc_ctx* ctx, const float* X, const float* w
             ctx->kde_part_cap = need;
         }
     }
+    // (a non-null scratch pointer tells the launcher the point split is available, even when this call needs ksplit = 1)
     CUDA_TRY(ctx, launch_kde_logprob(S, nullptr, dim, x, m, out, arith == GLABC_ARITH_STRICT, static_cast<cudaStream_t>(stream), ksplit,
-                                     ctx->kde_part));
+                                     ksplit > 1 ? ctx->kde_part : reinterpret_cast<float*>(out)));
     return GLABC_OK;
 }
 

@@ -18,15 +18,27 @@ cudaError_t launch_kde_fit(const float* X, const float* w, const int32_t* n, con
     return cudaGetLastError();
 }
 
+// Queries per thread for (sets, m): more queries per thread amortise the shared-memory broadcast of a point pair
+// (5 -> 4.5 -> 4.25 issue slots per pair), as long as the query tiles alone still give every SM a few CTAs.
+// Without the point split (STRICT, or no scratch: the AGLMCMC-internal launches) the query tiles alone must fill the machine.
+static int kde_queries_per_thread(int64_t sets, int64_t m, bool strict, bool can_split)
+{
+    const int64_t ctas1 = sets * ((m + kKdeThreads - 1) / kKdeThreads);
+    const int64_t need = can_split && !strict ? 148 : 8 * 148;
+    if (!strict && ctas1 >= need * 4) return 4;
+    return ctas1 >= need * 2 ? 2 : 1;
+}
+
 // A small query batch against a big point set (the stand-alone estimator: 1e5 x 1e5) gives too few CTAs to hide the
 // MUFU / shared-memory latency; the point tiles are then dealt to `ksplit` CTAs per query tile (FAST arithmetic only:
 // with the fixed shift the partial sums simply add).  Target: ~12 CTAs of 4 warps per SM.
 int kde_logprob_split(int64_t sets, int64_t m, int64_t cap)
 {
-    const int64_t ctas1 = sets * ((m + kKdeThreads - 1) / kKdeThreads);
+    const int q = kde_queries_per_thread(sets, m, false, true);
+    const int64_t ctas = sets * ((m + kKdeThreads * q - 1) / (kKdeThreads * q));
     const int64_t tiles = (cap + kKdeTile - 1) / kKdeTile;
-    if (ctas1 <= 0 || ctas1 >= 12 * 148 || tiles < 4) return 1;
-    int64_t k = (12 * 148 + ctas1 - 1) / ctas1;
+    if (ctas <= 0 || ctas >= 12 * 148 || tiles < 4) return 1;
+    int64_t k = (12 * 148 + ctas - 1) / ctas;
     if (k > tiles / 2) k = tiles / 2;
     if (k > 64) k = 64;
     return k < 1 ? 1 : static_cast<int>(k);
@@ -36,12 +48,8 @@ template <int D>
 static cudaError_t logprob_dim(const KdeSets& S, const float* lw, const float* x, int64_t m, float* out, bool strict, cudaStream_t st,
                                int ksplit, float* partial)
 {
-    // several queries per thread amortise the shared-memory broadcast of a training point; small batches keep one
-    // query per thread so the grid still fills the machine
-    // (one query per thread until the grid would exceed ~8 CTAs per SM: occupancy beats the amortised LDS)
+    const int q = kde_queries_per_thread(S.sets, m, strict, partial != nullptr && ksplit >= 1);
     if (strict || partial == nullptr || ksplit < 1) ksplit = 1;
-    const int64_t ctas1 = S.sets * ((m + kKdeThreads - 1) / kKdeThreads);
-    const int q = ksplit > 1 ? 1 : (!strict && ctas1 >= 8 * 148 * 4) ? 4 : ctas1 >= 8 * 148 * 2 ? 2 : 1;
     const int64_t per_cta = static_cast<int64_t>(kKdeThreads) * q;
     const int64_t qtiles = (m + per_cta - 1) / per_cta;
     const int64_t grid = S.sets * qtiles * ksplit;
@@ -52,8 +60,8 @@ static cudaError_t logprob_dim(const KdeSets& S, const float* lw, const float* x
         if (q == 2) k_kde_logprob<D, 2, true><<<g, kKdeThreads, 0, st>>>(S, lw, x, m, qtiles, out);
         else k_kde_logprob<D, 1, true><<<g, kKdeThreads, 0, st>>>(S, lw, x, m, qtiles, out);
     } else {
-        if (q == 4) k_kde_logprob<D, 4, false><<<g, kKdeThreads, 0, st>>>(S, lw, x, m, qtiles, out);
-        else if (q == 2) k_kde_logprob<D, 2, false><<<g, kKdeThreads, 0, st>>>(S, lw, x, m, qtiles, out);
+        if (q == 4) k_kde_logprob<D, 4, false><<<g, kKdeThreads, 0, st>>>(S, lw, x, m, qtiles, out, ksplit, partial);
+        else if (q == 2) k_kde_logprob<D, 2, false><<<g, kKdeThreads, 0, st>>>(S, lw, x, m, qtiles, out, ksplit, partial);
         else k_kde_logprob<D, 1, false><<<g, kKdeThreads, 0, st>>>(S, lw, x, m, qtiles, out, ksplit, partial);
         if (ksplit > 1) {
             const int64_t tot = S.sets * m;
