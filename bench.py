@@ -418,10 +418,13 @@ def bench_shared(a, rank, world, local_rank):
         th, lq = torch.empty(n_cand, 2, device="cuda"), torch.empty(n_cand, device="cuda")
         kms = timed(lambda: flow.fused_sample_from(eps, eng, theta=th, log_q=lq))
         tf = n_cand * 1.049e6 / (kms * 1e-3) / 1e12
-        peak = float(peaks.get("bf16_tflops", 1654.4)) / 2
+        peak = float(peaks.get("bf16_tflops", 1654.4))
         roofline = {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "traffic": None,
-                    "kernel_ms": kms, "note": f"k_flow sample of one block refill ({n_cand} candidates x 32 coupling blocks, 1.049 MFLOP "
-                    "dense per sample, TF32 operands on tcgen05); peak = measured bf16 dense / 2 (MEASURED_PEAKS.json)"}
+                    "kernel_ms": kms, "samples_per_sec": n_cand / (kms * 1e-3),
+                    "note": f"k_flow sample of one block refill ({n_cand} candidates x 32 coupling blocks, 1.049 MFLOP dense per "
+                    "sample, FP16 operands / FP32 accumulate on tcgen05 kind::f16); peak = measured dense bf16 / fp16 rate "
+                    "(MEASURED_PEAKS.json); the kernel's binding unit is the shared-memory broadcast of the layer vectors "
+                    "(DESIGN.md K4), not the tensor pipe"}
         del eps, th, lq
     else:
         n = a.kde_train
@@ -444,7 +447,7 @@ def bench_shared(a, rank, world, local_rank):
                            f"{a.kde_train} training draws all-gathered per fit")}
     line = {"metric": "abc_mcmc_chain_steps_per_sec", "value": value, "unit": "chain-steps/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32/f32" if a.sampler == "glmcmc_nf" else "f32", "data": "synthetic", "config": cfg, "clocks": clocks,
+            "dtype": "f16/f32" if a.sampler == "glmcmc_nf" else "f32", "data": "synthetic", "config": cfg, "clocks": clocks,
             "gpu_launches": n_launch_calls - 4 * a.steps, "roofline": roofline,
             "esjd": {"mean_per_chain": float(st.esjd().mean()), "move_rate": float(st.move_rate.mean())}}
     line["esjd"]["aggregate_esjd_per_sec"] = line["esjd"]["mean_per_chain"] * value
@@ -536,7 +539,7 @@ def other_kernels(eng, model, lp, gp):
     flow.bind(eng)
     eps = torch.randn(1 << 21, 2, device="cuda")
     r = timed(lambda: flow.fused_sample_from(eps, eng), float(1 << 21))
-    out["realnvp_sample_tcgen05"] = dict(r, unit="samples/s", tflops_tf32=r["per_sec"] * 1.049e6 / 1e12,
+    out["realnvp_sample_tcgen05"] = dict(r, unit="samples/s", tflops_f16=r["per_sec"] * 1.049e6 / 1e12,
                                          workload="2,097,152 samples through 32 coupling blocks (128x128 hidden layer on tensor cores)")
     return out
 

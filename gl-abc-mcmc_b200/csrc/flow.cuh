@@ -22,24 +22,40 @@
 // exact whatever the operand precision; only the agreement with an fp32 evaluation of the weights is ~1e-3.
 #pragma once
 #include <cstdint>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 namespace glabc {
 
 constexpr int kFlowHidden = 128;
 constexpr int kFlowTile = 128;
-// experiment switches (profiles/r1_k4_flow_ncu.md): -DGLABC_FLOW_TILES=n, -DGLABC_FLOW_SKIP_{L1,MMA,EPI} time the phases
+// experiment switch (profiles/r1_k4_flow_ncu.md): -DGLABC_FLOW_TILES=n
 #ifndef GLABC_FLOW_TILES
 #define GLABC_FLOW_TILES 16
 #endif
 constexpr int kFlowTilesPerCta = GLABC_FLOW_TILES;
-constexpr int kFlowW2Bytes = kFlowHidden * kFlowHidden * 4;           // 64 KB per block
+// Operand precision of the 128 x 128 layer.  FP16 (default) and TF32 carry the same 10-bit mantissa — the agreement with an
+// fp32 evaluation is the same ~1e-3 — but kind::f16 runs at twice the tensor rate, halves the A operand's TMEM columns and
+// W2's shared-memory footprint, and ReLU + saturation + rounding + packing of TWO activations is ONE instruction
+// (F2FP.SATFINITE.RELU.F16.F32.PACK_AB).  Activations beyond 65504 saturate instead of overflowing.  -DGLABC_FLOW_F16=0: TF32.
+#ifndef GLABC_FLOW_F16
+#define GLABC_FLOW_F16 1
+#endif
+constexpr bool kFlowF16 = GLABC_FLOW_F16 != 0;
+// FP16 leaves room in TMEM (per group 128 accumulator + 2 x 64 A-operand columns) to double-buffer the A operand: layer 1 of
+// the group's NEXT tile is computed while the tensor cores work on the current one (-DGLABC_FLOW_OVERLAP=0: one buffer).
+#ifndef GLABC_FLOW_OVERLAP
+#define GLABC_FLOW_OVERLAP GLABC_FLOW_F16
+#endif
+constexpr bool kFlowOverlap = kFlowF16 && GLABC_FLOW_OVERLAP != 0;
+constexpr int kFlowElemBytes = kFlowF16 ? 2 : 4;
+constexpr int kFlowW2Bytes = kFlowHidden * kFlowHidden * kFlowElemBytes;   // 32 KB (FP16) / 64 KB (TF32) per block
 constexpr int kFlowVecFloats = 768;                                  // w1, b1, b2 [128], w3 [2][128], b3 [2] (+pad)
 constexpr int kFlowGroups = 2;                                        // two groups, one tile in flight each
 constexpr int kFlowGroupThreads = 2 * kFlowTile;                      // two threads per sample row (half the hidden units each)
 constexpr int kFlowThreads = kFlowGroups * kFlowGroupThreads;         // 512: four warps per scheduler
 constexpr int kFlowSmemBytes = kFlowW2Bytes + kFlowVecFloats * 4 + 3 * kFlowTilesPerCta * kFlowTile * 4 +
-                               kFlowGroups * kFlowTile * 8 + 64;   // W2 of the block, vectors, states, partial sums, barriers
+                               kFlowGroups * 2 * kFlowTile * 8 + 64;   // W2 of the block, vectors, states, partial sums, barriers
 constexpr uint32_t kFlowTmemCols = 512;                                // per group: 128 accumulator + 128 A-operand columns
 
 struct FlowDev {
@@ -57,7 +73,8 @@ struct FlowDev {
 // core matrix = 8 rows x 16 bytes, core matrices contiguous along K (LBO = 128 B), 8-row groups 4 KB apart (SBO)
 __host__ __device__ constexpr uint32_t flow_pack_offset(uint32_t r, uint32_t k)
 {
-    return (r >> 3) * 4096u + (k >> 2) * 128u + (r & 7u) * 16u + (k & 3u) * 4u;
+    return kFlowF16 ? (r >> 3) * 2048u + (k >> 3) * 128u + (r & 7u) * 16u + (k & 7u) * 2u      // 8 halves per 16-byte row
+                    : (r >> 3) * 4096u + (k >> 2) * 128u + (r & 7u) * 16u + (k & 3u) * 4u;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -126,6 +143,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 16 columns, asynchronous: the registers are valid after tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&v)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32])
 {
     asm volatile(
@@ -153,6 +183,46 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
         : "memory");
 }
 
+// D[tmem] (+)= A[tmem] * B[smem]^T with FP16 operands: K = 16 per instruction, A row i = TMEM lane i, 16 halves = 8 columns
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// relu(lo), relu(hi) -> saturated, rounded FP16 pair (lo in bits 0..15): one F2FP instruction
+__device__ __forceinline__ uint32_t relu_pack_f16(float lo, float hi)
+{
+    uint32_t r;
+    asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
+// relu(a * b + c) on two FP16 lanes at once (HFMA2.RELU): layer 1 of the coupling MLP directly in the A operand's format
+__device__ __forceinline__ uint32_t hfma2_relu(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r;
+    asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t hfma2(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r;
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi)
+{
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_half2(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
+
 __device__ __forceinline__ float to_tf32(float x)
 {
     uint32_t r;
@@ -172,7 +242,11 @@ static __global__ void __launch_bounds__(256) k_flow_pack(const float* __restric
     const int64_t l = g / (kFlowHidden * kFlowHidden);
     const uint32_t e = static_cast<uint32_t>(g - l * kFlowHidden * kFlowHidden);
     const uint32_t r = e / kFlowHidden, k = e % kFlowHidden;
-    w2p[l * kFlowHidden * kFlowHidden + flow_pack_offset(r, k) / 4] = to_tf32(w2[g]);
+    if constexpr (kFlowF16) {
+        reinterpret_cast<__half*>(w2p)[l * kFlowHidden * kFlowHidden + flow_pack_offset(r, k) / 2] = __float2half_rn(w2[g]);
+    } else {
+        w2p[l * kFlowHidden * kFlowHidden + flow_pack_offset(r, k) / 4] = to_tf32(w2[g]);
+    }
 }
 
 __device__ __forceinline__ void group_sync(int group)
@@ -196,12 +270,12 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
     float* sVec = reinterpret_cast<float*>(smem + kFlowW2Bytes);
     float* sState = sVec + kFlowVecFloats;  // [3][tiles][128]: z1, z2, log q
     float2* sPart = reinterpret_cast<float2*>(sState + 3 * kFlowTilesPerCta * kFlowTile);  // [groups][128] partial sums of half 1
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sPart + kFlowGroups * kFlowTile);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sPart + kFlowGroups * 2 * kFlowTile);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + kFlowGroups);
     const int tid = threadIdx.x, warp = tid >> 5;
     const int group = tid / kFlowGroupThreads, gtid = tid % kFlowGroupThreads;
     const int half = gtid >> 7, row = gtid & (kFlowTile - 1), quad = (gtid >> 5) & 3;
-    float2* part = sPart + group * kFlowTile;
+    float2* part_base = sPart + group * 2 * kFlowTile;   // two buffers: a tile's partial sums are read after the next tile's may start
     const uint32_t bar_w = smem_u32(&bars[0]), bar_m = smem_u32(&bars[1 + group]);
     constexpr int TS = kFlowTilesPerCta * kFlowTile;
     constexpr int HK = kFlowHidden / 2;  // hidden units per thread
@@ -220,9 +294,11 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot + static_cast<uint32_t>(group * 256);  // this group's accumulator columns
-    const uint32_t tmem_a = tmem + 128u;                                    // and its A-operand columns
+    const uint32_t tmem_a0 = tmem + 128u;                                   // and its A-operand columns (FP16: two buffers of 64)
     // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128 (cute::UMMA::InstrDescriptor bit layout)
-    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+    // (a_format / b_format: 0 = F16 for kind::f16, 2 = TF32 for kind::tf32)
+    constexpr uint32_t idesc = kFlowF16 ? (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24)
+                                        : (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t sB_addr = smem_u32(sB);
     uint32_t ph_w = 0, ph_m = 0;
     const float c2 = -1.8378770664093453f;  // -0.5 * 2 * log(2 pi)
@@ -259,84 +335,140 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
                     bulk_g2s(sB_addr + q * (kFlowW2Bytes / 4), reinterpret_cast<const uint8_t*>(W.w2p) +
                              static_cast<int64_t>(l) * kFlowW2Bytes + q * (kFlowW2Bytes / 4), kFlowW2Bytes / 4, bar_w);
             }
-            if (tid < 128) sVec[tid] = W.w1[l * kFlowHidden + tid];
-            else if (tid < 256) sVec[tid] = W.b1[l * kFlowHidden + tid - 128];
-            else if (tid < 384) sVec[tid] = W.b2[l * kFlowHidden + tid - 256];
-            else sVec[tid] = W.w3[(l * 2) * kFlowHidden + tid - 384];  // w3 rows 0 and 1 are contiguous: [384, 640)
-            if (tid < 128) sVec[512 + tid] = W.w3[(l * 2 + 1) * kFlowHidden + tid];
-            if (tid < 2) sVec[640 + tid] = W.b3[l * 2 + tid];
+            if constexpr (kFlowF16) {
+                // The broadcast reads of these vectors are what bounds the kernel (every warp re-reads them for every tile:
+                // 1,280 B per thread and tile in fp32 = more shared-memory cycles than the tile takes), so they are staged in
+                // the narrowest form the arithmetic allows: w1 / b1 as FP16 pairs (layer 1 runs as HFMA2.RELU straight into the
+                // A operand's format), the two W3 rows interleaved as one FP16 pair per column, b2 in fp32: 768 B.
+                uint32_t* sU = reinterpret_cast<uint32_t*>(sVec);
+                if (tid < 64) sU[tid] = pack_half2(W.w1[l * kFlowHidden + 2 * tid], W.w1[l * kFlowHidden + 2 * tid + 1]);
+                else if (tid < 128) sU[tid] = pack_half2(W.b1[l * kFlowHidden + 2 * (tid - 64)], W.b1[l * kFlowHidden + 2 * (tid - 64) + 1]);
+                else if (tid < 256) sVec[128 + tid] = W.b2[l * kFlowHidden + tid - 128];                    // [256, 384)
+                else if (tid < 384) sU[128 + tid] = pack_half2(W.w3[(l * 2) * kFlowHidden + tid - 256],       // [384, 512)
+                                                               W.w3[(l * 2 + 1) * kFlowHidden + tid - 256]);
+                else if (tid < 386) sVec[640 + tid - 384] = W.b3[l * 2 + tid - 384];
+            } else {
+                if (tid < 128) sVec[tid] = W.w1[l * kFlowHidden + tid];
+                else if (tid < 256) sVec[tid] = W.b1[l * kFlowHidden + tid - 128];
+                else if (tid < 384) sVec[tid] = W.b2[l * kFlowHidden + tid - 256];
+                else sVec[tid] = W.w3[(l * 2) * kFlowHidden + tid - 384];  // w3 rows 0 and 1 are contiguous: [384, 640)
+                if (tid < 128) sVec[512 + tid] = W.w3[(l * 2 + 1) * kFlowHidden + tid];
+                if (tid < 2) sVec[640 + tid] = W.b3[l * 2 + tid];
+            }
             __syncthreads();
             mbar_wait(bar_w, ph_w);
             ph_w ^= 1u;
 
-            for (int t = group; t < tiles; t += kFlowGroups) {
-                float z1 = sState[0 * TS + t * kFlowTile + row], z2 = sState[1 * TS + t * kFlowTile + row];
-                if (!SAMPLE) {  // Permute(swap)^-1 precedes the coupling's inverse
-                    const float tmp = z1;
-                    z1 = z2;
-                    z2 = tmp;
-                }
-                // ---- layer 1 (K = 1) on CUDA cores, written as the A operand into TMEM: this thread's 64 hidden units ----
-#ifdef GLABC_FLOW_SKIP_L1
-                if (z1 == 123.456f)
-#endif
-#pragma unroll
-                for (int cb = 0; cb < HK / 32; ++cb) {
+            // layer 1 (K = 1) of tile t on CUDA cores, written as the A operand into TMEM columns `a_cols`: this thread's 64 hidden units
+            auto layer1 = [&](int t, uint32_t tmem_a) {
+                float z1 = sState[(SAMPLE ? 0 : 1) * TS + t * kFlowTile + row];   // !SAMPLE: Permute(swap)^-1 precedes the inverse
+                if constexpr (kFlowF16) {
+                    // this thread's 64 hidden units as 32 packed FP16 pairs = 32 TMEM columns, ONE tcgen05.st
                     uint32_t hv[32];
+                    // z1 as an FP16 hi + lo pair: rounding the INPUT to 11 bits would perturb all 128 hidden units coherently
+                    // (the error of the block would be the network's derivative times 5e-4 |z1|); the roundings left are per-unit
+                    const float z_hi = __half2float(__float2half_rn(z1));
+                    const uint32_t zz = pack_half2(z_hi, z_hi), zl = pack_half2(z1 - z_hi, z1 - z_hi);
+                    const uint4* w1h = reinterpret_cast<const uint4*>(sVec) + half * (HK / 8);        // 8 hidden units per 16 bytes
+                    const uint4* b1h = reinterpret_cast<const uint4*>(sVec + 64) + half * (HK / 8);
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 w = *reinterpret_cast<const float4*>(&sVec[half * HK + cb * 32 + j]);
-                        const float4 bb = *reinterpret_cast<const float4*>(&sVec[128 + half * HK + cb * 32 + j]);
-                        hv[j] = __float_as_uint(round_tf32_nonneg(fmaxf(fmaf(w.x, z1, bb.x), 0.0f)));
-                        hv[j + 1] = __float_as_uint(round_tf32_nonneg(fmaxf(fmaf(w.y, z1, bb.y), 0.0f)));
-                        hv[j + 2] = __float_as_uint(round_tf32_nonneg(fmaxf(fmaf(w.z, z1, bb.z), 0.0f)));
-                        hv[j + 3] = __float_as_uint(round_tf32_nonneg(fmaxf(fmaf(w.w, z1, bb.w), 0.0f)));
+                    for (int j = 0; j < HK / 8; ++j) {
+                        const uint4 w = w1h[j], bb = b1h[j];
+                        hv[4 * j] = hfma2_relu(w.x, zz, hfma2(w.x, zl, bb.x));
+                        hv[4 * j + 1] = hfma2_relu(w.y, zz, hfma2(w.y, zl, bb.y));
+                        hv[4 * j + 2] = hfma2_relu(w.z, zz, hfma2(w.z, zl, bb.z));
+                        hv[4 * j + 3] = hfma2_relu(w.w, zz, hfma2(w.w, zl, bb.w));
                     }
-                    tmem_st32(tmem_a + (static_cast<uint32_t>(quad * 32) << 16) + half * HK + cb * 32, hv);
+                    tmem_st32(tmem_a + (static_cast<uint32_t>(quad * 32) << 16) + half * (HK / 2), hv);
+                } else {
+#pragma unroll
+                    for (int cb = 0; cb < HK / 32; ++cb) {
+                        uint32_t hv[32];
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 w = *reinterpret_cast<const float4*>(&sVec[half * HK + cb * 32 + j]);
+                            const float4 bb = *reinterpret_cast<const float4*>(&sVec[128 + half * HK + cb * 32 + j]);
+                            hv[j] = __float_as_uint(round_tf32_nonneg(fmaxf(fmaf(w.x, z1, bb.x), 0.0f)));
+                            hv[j + 1] = __float_as_uint(round_tf32_nonneg(fmaxf(fmaf(w.y, z1, bb.y), 0.0f)));
+                            hv[j + 2] = __float_as_uint(round_tf32_nonneg(fmaxf(fmaf(w.z, z1, bb.z), 0.0f)));
+                            hv[j + 3] = __float_as_uint(round_tf32_nonneg(fmaxf(fmaf(w.w, z1, bb.w), 0.0f)));
+                        }
+                        tmem_st32(tmem_a + (static_cast<uint32_t>(quad * 32) << 16) + half * HK + cb * 32, hv);
+                    }
                 }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            };
+            uint32_t buf = 0;
+            if (kFlowOverlap && group < tiles) {
+                layer1(group, tmem_a0);
                 tc_fence_before();
-                group_sync(group);  // (also: half 0 has consumed the previous tile's partial sums)
+                group_sync(group);
+            }
+            for (int t = group; t < tiles; t += kFlowGroups) {
+                const uint32_t tmem_a = tmem_a0 + (kFlowOverlap ? buf * 64u : 0u);
+                float2* part = part_base + buf * kFlowTile;
+                if constexpr (!kFlowOverlap) {
+                    layer1(t, tmem_a);
+                    tc_fence_before();
+                    group_sync(group);  // (also: half 0 has consumed the previous tile's partial sums)
+                }
                 // ---- layer 2 (128 x 128 x 128) on the tensor cores ----
-#ifdef GLABC_FLOW_SKIP_MMA
-                if (gtid == 0 && z1 == 123.456f) {
-#else
                 if (gtid == 0) {
-#endif
                     tc_fence_after();
+                    if constexpr (kFlowF16) {
 #pragma unroll
-                    for (int k = 0; k < kFlowHidden / 8; ++k) {
-                        const uint64_t bd = umma_desc(sB_addr + k * 256, 128, 4096);
-                        umma_tf32_ts(tmem, tmem_a + k * 8, bd, idesc, k > 0 ? 1u : 0u);
+                        for (int k = 0; k < kFlowHidden / 16; ++k) {   // K = 16 halves = 2 core matrices = 256 B of B, 8 columns of A
+                            const uint64_t bd = umma_desc(sB_addr + k * 256, 128, 2048);
+                            umma_f16_ts(tmem, tmem_a + k * 8, bd, idesc, k > 0 ? 1u : 0u);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < kFlowHidden / 8; ++k) {
+                            const uint64_t bd = umma_desc(sB_addr + k * 256, 128, 4096);
+                            umma_tf32_ts(tmem, tmem_a + k * 8, bd, idesc, k > 0 ? 1u : 0u);
+                        }
                     }
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_m) : "memory");
                 }
-#ifndef GLABC_FLOW_SKIP_MMA
+                if constexpr (kFlowOverlap) {   // the group's next tile: its layer 1 fills the other A buffer while the MMA runs
+                    if (t + kFlowGroups < tiles) layer1(t + kFlowGroups, tmem_a0 + (buf ^ 1u) * 64u);
+                }
                 mbar_wait(bar_m, ph_m);
                 ph_m ^= 1u;
-#endif
                 tc_fence_after();
                 // ---- bias + ReLU + layer 3 (N = 2) from TMEM: this thread's 64 columns, four independent partial sums ----
                 float p0[4] = {0.0f, 0.0f, 0.0f, 0.0f}, p1[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#ifdef GLABC_FLOW_SKIP_EPI
-                if (z1 == 123.456f)
-#endif
+                {
+                    // four 16-column TMEM loads, software-pipelined: chunk c + 1 is in flight while chunk c is reduced
+                    uint32_t v[2][16];
+                    const uint32_t trow = tmem + (static_cast<uint32_t>(quad * 32) << 16) + half * HK;
+                    tmem_ld16_async(trow, v[0]);
 #pragma unroll
-                for (int cb = 0; cb < 2; ++cb) {
-                    uint32_t v[32];
-                    const int col0 = half * HK + cb * 32;
-                    tmem_ld32(tmem + (static_cast<uint32_t>(quad * 32) << 16) + col0, v);
+                    for (int c = 0; c < HK / 16; ++c) {
+                        tmem_ld_wait();
+                        if (c + 1 < HK / 16) tmem_ld16_async(trow + (c + 1) * 16, v[(c + 1) & 1]);
+                        const int col0 = half * HK + c * 16;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {  // broadcast LDS.128 of b2 / W3 rows: 3 loads per 4 columns
-                        const float4 b2v = *reinterpret_cast<const float4*>(&sVec[256 + col0 + j]);
-                        const float4 wa = *reinterpret_cast<const float4*>(&sVec[384 + col0 + j]);
-                        const float4 wb = *reinterpret_cast<const float4*>(&sVec[512 + col0 + j]);
-                        const float h0 = fmaxf(__uint_as_float(v[j]) + b2v.x, 0.0f), h1 = fmaxf(__uint_as_float(v[j + 1]) + b2v.y, 0.0f);
-                        const float h2 = fmaxf(__uint_as_float(v[j + 2]) + b2v.z, 0.0f), h3 = fmaxf(__uint_as_float(v[j + 3]) + b2v.w, 0.0f);
-                        p0[0] = fmaf(wa.x, h0, p0[0]); p1[0] = fmaf(wb.x, h0, p1[0]);
-                        p0[1] = fmaf(wa.y, h1, p0[1]); p1[1] = fmaf(wb.y, h1, p1[1]);
-                        p0[2] = fmaf(wa.z, h2, p0[2]); p1[2] = fmaf(wb.z, h2, p1[2]);
-                        p0[3] = fmaf(wa.w, h3, p0[3]); p1[3] = fmaf(wb.w, h3, p1[3]);
+                        for (int j = 0; j < 16; j += 4) {  // broadcast LDS.128 of b2 and of the W3 pairs: 2 loads per 4 columns
+                            const float4 b2v = *reinterpret_cast<const float4*>(&sVec[256 + col0 + j]);
+                            float2 w0, w1, w2, w3;
+                            if constexpr (kFlowF16) {
+                                const uint4 wq = *reinterpret_cast<const uint4*>(&sVec[384 + col0 + j]);
+                                w0 = unpack_half2(wq.x); w1 = unpack_half2(wq.y); w2 = unpack_half2(wq.z); w3 = unpack_half2(wq.w);
+                            } else {
+                                const float4 wa = *reinterpret_cast<const float4*>(&sVec[384 + col0 + j]);
+                                const float4 wb = *reinterpret_cast<const float4*>(&sVec[512 + col0 + j]);
+                                w0 = make_float2(wa.x, wb.x); w1 = make_float2(wa.y, wb.y);
+                                w2 = make_float2(wa.z, wb.z); w3 = make_float2(wa.w, wb.w);
+                            }
+                            const uint32_t* vv = v[c & 1];
+                            const float h0 = fmaxf(__uint_as_float(vv[j]) + b2v.x, 0.0f), h1 = fmaxf(__uint_as_float(vv[j + 1]) + b2v.y, 0.0f);
+                            const float h2 = fmaxf(__uint_as_float(vv[j + 2]) + b2v.z, 0.0f), h3 = fmaxf(__uint_as_float(vv[j + 3]) + b2v.w, 0.0f);
+                            p0[0] = fmaf(w0.x, h0, p0[0]); p1[0] = fmaf(w0.y, h0, p1[0]);
+                            p0[1] = fmaf(w1.x, h1, p0[1]); p1[1] = fmaf(w1.y, h1, p1[1]);
+                            p0[2] = fmaf(w2.x, h2, p0[2]); p1[2] = fmaf(w2.y, h2, p1[2]);
+                            p0[3] = fmaf(w3.x, h3, p0[3]); p1[3] = fmaf(w3.y, h3, p1[3]);
+                        }
                     }
                 }
                 const float s0 = (p0[0] + p0[1]) + (p0[2] + p0[3]), s1 = (p1[0] + p1[1]) + (p1[2] + p1[3]);
@@ -344,6 +476,12 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
                 tc_fence_before();
                 group_sync(group);  // TMEM columns and the A buffer are free for the group's next tile; partial sums visible
                 if (half == 0) {
+                    float z1 = sState[0 * TS + t * kFlowTile + row], z2 = sState[1 * TS + t * kFlowTile + row];
+                    if (!SAMPLE) {  // Permute(swap)^-1 precedes the coupling's inverse
+                        const float tmp = z1;
+                        z1 = z2;
+                        z2 = tmp;
+                    }
                     const float2 o = part[row];
                     const float sh = (s0 + o.x) + sVec[640];  // shift     = param[:, 0::2]
                     const float sc = (s1 + o.y) + sVec[641];  // log-scale = param[:, 1::2]
@@ -361,6 +499,7 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
                     }
                     sState[2 * TS + t * kFlowTile + row] = lq;
                 }
+                buf ^= 1u;
             }
         }
         __syncthreads();

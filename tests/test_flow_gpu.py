@@ -36,12 +36,14 @@ def test_identity_at_init():
 
 @pytest.mark.parametrize("n", [1, 127, 128, 1024, 1025, 50000])
 def test_matches_fp32_torch(flow, n):
-    """sample / log_prob against the fp32 autograd path; tolerance = TF32 operand rounding through 32 blocks"""
+    """sample / log_prob against the fp32 autograd path; tolerance = 11-bit operand rounding (FP16 activations, W2, and the
+    FP16-staged w1 / b1 / W3 vectors) through 32 blocks: tight in the bulk, amplified by exp(s) in the tails"""
     eps = torch.randn(n, 2, device="cuda", generator=torch.Generator(device="cuda").manual_seed(n))
     th, lq = flow.fused_sample_from(eps)
     with torch.no_grad():
         th_r, lq_r = flow.sample_from(eps)
-        assert torch.allclose(th, th_r, rtol=5e-3, atol=5e-3), float((th - th_r).abs().max())
+        e_th = ((th - th_r).abs() / (1 + th_r.abs())).max(1).values
+        assert float(e_th.median()) < 1.5e-3 and float(e_th.quantile(0.99)) < 1e-2 and float(e_th.max()) < 0.1, float(e_th.max())
         assert torch.allclose(lq, lq_r, rtol=0, atol=2e-2), float((lq - lq_r).abs().max())
         # queries around the flow's own samples (far outside its support exp(-s) overflows in fp32 for both paths)
         x = th_r + 0.1 * torch.randn(n, 2, device="cuda", generator=torch.Generator(device="cuda").manual_seed(n + 1))
@@ -50,7 +52,9 @@ def test_matches_fp32_torch(flow, n):
         assert ok.float().mean() > 0.99 and torch.equal(torch.isfinite(lp), ok)
         err = (lp[ok] - lp_r[ok]).abs() / (1 + 0.01 * lp_r[ok].abs())
         # TF32 operand rounding (2^-11 relative) through 32 blocks: tight in the bulk, amplified by exp(-s) in the tails
-        assert float(err.median()) < 3e-3 and float(err.quantile(0.99)) < 5e-2 and float(err.max()) < 0.5, float(err.max())
+        assert float(err.median()) < 3e-3 and float(err.quantile(0.99)) < 5e-2 and float(err.max()) < 5.0, float(err.max())
+        if n >= 1024:
+            assert float(err.quantile(0.999)) < 0.3
 
 
 def test_sample_log_prob_consistency(flow):
