@@ -48,13 +48,21 @@ constexpr bool kFlowF16 = GLABC_FLOW_F16 != 0;
 #define GLABC_FLOW_OVERLAP GLABC_FLOW_F16
 #endif
 constexpr bool kFlowOverlap = kFlowF16 && GLABC_FLOW_OVERLAP != 0;
+// The N = 2 output layer as a SECOND small MMA (M128 N16 K128): the epilogue then only adds b2, applies ReLU and packs the
+// activations back into the tile's (free again) A columns — no W3 reads from shared memory, no 2 x 128 FMA contraction on
+// the CUDA cores.  -DGLABC_FLOW_MMA2=0: the contraction stays on the CUDA cores.
+#ifndef GLABC_FLOW_MMA2
+#define GLABC_FLOW_MMA2 GLABC_FLOW_OVERLAP
+#endif
+constexpr bool kFlowMma2 = kFlowOverlap && GLABC_FLOW_MMA2 != 0;
+constexpr int kFlowW3Bytes = kFlowMma2 ? 16 * kFlowHidden * 2 : 0;   // W3 as a 16 x 128 FP16 B operand (rows 2..15 zero)
 constexpr int kFlowElemBytes = kFlowF16 ? 2 : 4;
 constexpr int kFlowW2Bytes = kFlowHidden * kFlowHidden * kFlowElemBytes;   // 32 KB (FP16) / 64 KB (TF32) per block
 constexpr int kFlowVecFloats = 768;                                  // w1, b1, b2 [128], w3 [2][128], b3 [2] (+pad)
 constexpr int kFlowGroups = 2;                                        // two groups, one tile in flight each
 constexpr int kFlowGroupThreads = 2 * kFlowTile;                      // two threads per sample row (half the hidden units each)
 constexpr int kFlowThreads = kFlowGroups * kFlowGroupThreads;         // 512: four warps per scheduler
-constexpr int kFlowSmemBytes = kFlowW2Bytes + kFlowVecFloats * 4 + 3 * kFlowTilesPerCta * kFlowTile * 4 +
+constexpr int kFlowSmemBytes = kFlowW2Bytes + kFlowW3Bytes + kFlowVecFloats * 4 + 3 * kFlowTilesPerCta * kFlowTile * 4 +
                                kFlowGroups * 2 * kFlowTile * 8 + 64;   // W2 of the block, vectors, states, partial sums, barriers
 constexpr uint32_t kFlowTmemCols = 512;                                // per group: 128 accumulator + 128 A-operand columns
 
@@ -267,7 +275,8 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     float* sB = reinterpret_cast<float*>(smem);
-    float* sVec = reinterpret_cast<float*>(smem + kFlowW2Bytes);
+    __half* sW3 = reinterpret_cast<__half*>(smem + kFlowW2Bytes);   // [16][128] FP16, UMMA K-major core-matrix layout (kFlowMma2)
+    float* sVec = reinterpret_cast<float*>(smem + kFlowW2Bytes + kFlowW3Bytes);
     float* sState = sVec + kFlowVecFloats;  // [3][tiles][128]: z1, z2, log q
     float2* sPart = reinterpret_cast<float2*>(sState + 3 * kFlowTilesPerCta * kFlowTile);  // [groups][128] partial sums of half 1
     uint64_t* bars = reinterpret_cast<uint64_t*>(sPart + kFlowGroups * 2 * kFlowTile);
@@ -290,6 +299,8 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
         for (int i = 0; i < 1 + kFlowGroups; ++i) mbar_init(smem_u32(&bars[i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if constexpr (kFlowMma2)
+        for (int i = tid; i < kFlowW3Bytes / 4; i += kFlowThreads) reinterpret_cast<uint32_t*>(sW3)[i] = 0u;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -347,6 +358,12 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
                 else if (tid < 384) sU[128 + tid] = pack_half2(W.w3[(l * 2) * kFlowHidden + tid - 256],       // [384, 512)
                                                                W.w3[(l * 2 + 1) * kFlowHidden + tid - 256]);
                 else if (tid < 386) sVec[640 + tid - 384] = W.b3[l * 2 + tid - 384];
+                if constexpr (kFlowMma2) {   // element (n, k) of the 16 x 128 operand: rows 0 (shift) and 1 (log-scale)
+                    if (tid >= 256) {
+                        const int n = (tid - 256) >> 7, k = (tid - 256) & 127;
+                        sW3[((k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2) / 2] = __float2half_rn(W.w3[(l * 2 + n) * kFlowHidden + k]);
+                    }
+                }
             } else {
                 if (tid < 128) sVec[tid] = W.w1[l * kFlowHidden + tid];
                 else if (tid < 256) sVec[tid] = W.b1[l * kFlowHidden + tid - 128];
@@ -355,6 +372,7 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
                 if (tid < 128) sVec[512 + tid] = W.w3[(l * 2 + 1) * kFlowHidden + tid];
                 if (tid < 2) sVec[640 + tid] = W.b3[l * 2 + tid];
             }
+            if constexpr (kFlowMma2) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // sW3: generic writes -> MMA reads
             __syncthreads();
             mbar_wait(bar_w, ph_w);
             ph_w ^= 1u;
@@ -436,6 +454,60 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
                 mbar_wait(bar_m, ph_m);
                 ph_m ^= 1u;
                 tc_fence_after();
+                float s0 = 0.0f, s1 = 0.0f;
+                float2 o = make_float2(0.0f, 0.0f);
+                if constexpr (kFlowMma2) {
+                    // ---- bias + ReLU from TMEM, packed back as FP16 into this tile's A columns (free since its MMA completed) ----
+                    {
+                        uint32_t v[2][16], hp[32];
+                        const uint32_t trow = tmem + (static_cast<uint32_t>(quad * 32) << 16) + half * HK;
+                        tmem_ld16_async(trow, v[0]);
+#pragma unroll
+                        for (int c = 0; c < HK / 16; ++c) {
+                            tmem_ld_wait();
+                            if (c + 1 < HK / 16) tmem_ld16_async(trow + (c + 1) * 16, v[(c + 1) & 1]);
+                            const int col0 = half * HK + c * 16;
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) {
+                                const float4 b2v = *reinterpret_cast<const float4*>(&sVec[256 + col0 + j]);
+                                const uint32_t* vv = v[c & 1];
+                                hp[c * 8 + j / 2] = relu_pack_f16(__uint_as_float(vv[j]) + b2v.x, __uint_as_float(vv[j + 1]) + b2v.y);
+                                hp[c * 8 + j / 2 + 1] = relu_pack_f16(__uint_as_float(vv[j + 2]) + b2v.z, __uint_as_float(vv[j + 3]) + b2v.w);
+                            }
+                        }
+                        tmem_st32(tmem_a + (static_cast<uint32_t>(quad * 32) << 16) + half * (HK / 2), hp);
+                        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    }
+                    tc_fence_before();
+                    group_sync(group);  // every thread has read its accumulator columns and written its activations
+                    // ---- layer 3 (128 x 16 x 128, rows 0 / 1 of W3) on the tensor cores, into accumulator columns 0..15 ----
+                    if (gtid == 0) {
+                        tc_fence_after();
+                        constexpr uint32_t idesc3 = (1u << 4) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+                        const uint32_t sW3_addr = smem_u32(sW3);
+#pragma unroll
+                        for (int k = 0; k < kFlowHidden / 16; ++k) {
+                            const uint64_t bd = umma_desc(sW3_addr + k * 256, 128, 2048);
+                            umma_f16_ts(tmem, tmem_a + k * 8, bd, idesc3, k > 0 ? 1u : 0u);
+                        }
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_m) : "memory");
+                    }
+                    mbar_wait(bar_m, ph_m);
+                    ph_m ^= 1u;
+                    tc_fence_after();
+                    if (half == 0) {   // warp-uniform: warps 0..3 of the group
+                        uint32_t r0, r1;
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];"
+                                     : "=r"(r0), "=r"(r1)
+                                     : "r"(tmem + (static_cast<uint32_t>(quad * 32) << 16))
+                                     : "memory");
+                        tmem_ld_wait();
+                        s0 = __uint_as_float(r0);
+                        s1 = __uint_as_float(r1);
+                    }
+                    tc_fence_before();
+                    group_sync(group);  // the accumulator and both A buffers' roles are free for the group's next tile
+                } else {
                 // ---- bias + ReLU + layer 3 (N = 2) from TMEM: this thread's 64 columns, four independent partial sums ----
                 float p0[4] = {0.0f, 0.0f, 0.0f, 0.0f}, p1[4] = {0.0f, 0.0f, 0.0f, 0.0f};
                 {
@@ -471,10 +543,13 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
                         }
                     }
                 }
-                const float s0 = (p0[0] + p0[1]) + (p0[2] + p0[3]), s1 = (p1[0] + p1[1]) + (p1[2] + p1[3]);
+                s0 = (p0[0] + p0[1]) + (p0[2] + p0[3]);
+                s1 = (p1[0] + p1[1]) + (p1[2] + p1[3]);
                 if (half == 1) part[row] = make_float2(s0, s1);
                 tc_fence_before();
                 group_sync(group);  // TMEM columns and the A buffer are free for the group's next tile; partial sums visible
+                if (half == 0) o = part[row];
+                }
                 if (half == 0) {
                     float z1 = sState[0 * TS + t * kFlowTile + row], z2 = sState[1 * TS + t * kFlowTile + row];
                     if (!SAMPLE) {  // Permute(swap)^-1 precedes the coupling's inverse
@@ -482,7 +557,6 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
                         z1 = z2;
                         z2 = tmp;
                     }
-                    const float2 o = part[row];
                     const float sh = (s0 + o.x) + sVec[640];  // shift     = param[:, 0::2]
                     const float sc = (s1 + o.y) + sVec[641];  // log-scale = param[:, 1::2]
                     float lq = sState[2 * TS + t * kFlowTile + row];
