@@ -5,6 +5,8 @@ random-walk Metropolis–Hastings move from `Local_Proposal`.  The loop body (GL
 the fused kernel `k_isir` (csrc/step_isir.cuh) for all chains at once."""
 from . import _abi
 from .engine import get_engine
+from .GlobalMCMC import run_user_model
+from .models import UserModel
 from .samplers import run_chains
 
 
@@ -18,6 +20,10 @@ def GLMCMC(ABCset, num_ite, Initial_theta, Initial_y, Local_Proposal, filelocati
     if not 1 <= int(batch_size) <= _abi.MAX_K:
         raise ValueError(f"batch_size must be in 1..{_abi.MAX_K}")
     eng = get_engine(device)
+    if isinstance(ABCset, UserModel):       # run-time compiled model (csrc/user_model.cu)
+        eng.bind_proposal(_abi.SLOT_IMPORTANCE, Importance_Proposal)
+        return run_user_model(eng, ABCset, "isir", num_ite, Initial_theta, Initial_y, Local_Proposal, filelocation, global_frequency,
+                              num_chains, seed, chain_id_base, trace, return_stats, verbose, block_threads, K=int(batch_size))
     pod = eng.bind_model(ABCset)
     eng.bind_proposal(_abi.SLOT_LOCAL, Local_Proposal)
     eng.bind_proposal(_abi.SLOT_IMPORTANCE, Importance_Proposal)

@@ -968,32 +968,41 @@ extern "C" int glabc_user_model_check(const glabc_user_model_t* um, int32_t cc, 
     return st;
 }
 
-extern "C" int glabc_run_global_user(glabc_ctx* ctx, const glabc_run_t* run, const glabc_user_model_t* um)
+static int run_user(glabc_ctx* ctx, const glabc_run_t* run, const glabc_user_model_t* um, bool isir)
 {
     if (!ctx) return GLABC_ERR_INVALID;
-    if (!um || !um->source) return fail(ctx, GLABC_ERR_INVALID, "glabc_run_global_user: null model / source");
+    if (!um || !um->source) return fail(ctx, GLABC_ERR_INVALID, "glabc_run_*_user: null model / source");
     if (um->theta_dim < 1 || um->theta_dim > GLABC_MAX_DIM || um->y_dim < 1 || um->y_dim > 2 * GLABC_MAX_DIM)
         return fail(ctx, GLABC_ERR_INVALID, "user model: theta_dim in 1..%d, y_dim in 1..%d", GLABC_MAX_DIM, 2 * GLABC_MAX_DIM);
     if (um->n_noise < 0 || um->n_noise > GLABC_USER_MAX_NOISE || um->n_params < 0 || um->n_params > GLABC_USER_MAX_PARAMS)
         return fail(ctx, GLABC_ERR_INVALID, "user model: n_noise in 0..%d, n_params in 0..%d", GLABC_USER_MAX_NOISE, GLABC_USER_MAX_PARAMS);
     if (!(um->epsilon > 0.0)) return fail(ctx, GLABC_ERR_INVALID, "user model: epsilon must be positive");
     const int d = um->theta_dim;
-    for (int slot : {GLABC_SLOT_LOCAL, GLABC_SLOT_GLOBAL}) {
-        if (!ctx->has_dist[slot]) return fail(ctx, GLABC_ERR_INVALID, "glabc_run_global_user needs the LOCAL and GLOBAL proposal slots bound");
+    const int far_slot = isir ? GLABC_SLOT_IMPORTANCE : GLABC_SLOT_GLOBAL;   // the state-independent proposal of the sampler
+    for (int slot : {static_cast<int>(GLABC_SLOT_LOCAL), far_slot}) {
+        if (!ctx->has_dist[slot])
+            return fail(ctx, GLABC_ERR_INVALID, "%s needs the LOCAL and %s proposal slots bound", isir ? "glabc_run_isir_user" : "glabc_run_global_user",
+                        isir ? "IMPORTANCE" : "GLOBAL");
         if (ctx->dist[slot].kind != GLABC_DIST_DIAG_GAUSSIAN)
-            return fail(ctx, GLABC_ERR_UNSUPPORTED, "glabc_run_global_user is fused for DiagGaussian proposals");
+            return fail(ctx, GLABC_ERR_UNSUPPORTED, "the user-model kernels are fused for DiagGaussian proposals");
         if (ctx->dist[slot].dim != d) return fail(ctx, GLABC_ERR_INVALID, "proposal dim does not match the user model's theta_dim %d", d);
+    }
+    if (isir) {
+        if (!run) return fail(ctx, GLABC_ERR_INVALID, "null run description");
+        if (run->n_candidates < 1 || run->n_candidates > GLABC_MAX_K)
+            return fail(ctx, GLABC_ERR_INVALID, "n_candidates (batch_size) must be in 1..%d", GLABC_MAX_K);
+        if (!run->aux) return fail(ctx, GLABC_ERR_INVALID, "glabc_run_isir_user needs the aux state [C][%d] (log-weight, local flag)", GLABC_AUX_SLOTS);
     }
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     RunParams R;
     int block = 0;
     int st = make_run_params(ctx, run, d, 0, &R, &block);
     if (st) return st;
-    if (run->rng_mode != GLABC_RNG_NATIVE) return fail(ctx, GLABC_ERR_UNSUPPORTED, "glabc_run_global_user runs the native RNG only");
+    if (run->rng_mode != GLABC_RNG_NATIVE) return fail(ctx, GLABC_ERR_UNSUPPORTED, "the user-model kernels run the native RNG only");
     CUDA_TRY(ctx, cudaFree(nullptr));   // make sure the primary context exists and is current for the driver calls
     void* fn = nullptr;
     std::string err;
-    st = user_model_compile(ctx->device, ctx->cc, *um, &fn, err);
+    st = user_model_compile(ctx->device, ctx->cc, *um, isir, &fn, err);
     if (st) return fail(ctx, st, "%s", err.c_str());
     UserRun U{};
     U.n_chains = R.n_chains;
@@ -1017,7 +1026,9 @@ extern "C" int glabc_run_global_user(glabc_ctx* ctx, const glabc_run_t* run, con
     U.trace = R.trace;
     U.stats = R.stats;
     const glabc_dist_t& lp = ctx->dist[GLABC_SLOT_LOCAL];
-    const glabc_dist_t& gp = ctx->dist[GLABC_SLOT_GLOBAL];
+    const glabc_dist_t& gp = ctx->dist[far_slot];
+    U.aux = isir ? run->aux : nullptr;
+    U.n_candidates = isir ? run->n_candidates : 0;
     for (int k = 0; k < d; ++k) {   // glabc_dist_t DiagGaussian: a = loc, b = log_scale, c = exp(log_scale) in float32
         U.lp_loc[k] = lp.a[k];
         U.lp_scale[k] = lp.c[k];
@@ -1033,6 +1044,9 @@ extern "C" int glabc_run_global_user(glabc_ctx* ctx, const glabc_run_t* run, con
     if (st) return fail(ctx, st, "%s", err.c_str());
     return GLABC_OK;
 }
+
+extern "C" int glabc_run_global_user(glabc_ctx* ctx, const glabc_run_t* run, const glabc_user_model_t* um) { return run_user(ctx, run, um, false); }
+extern "C" int glabc_run_isir_user(glabc_ctx* ctx, const glabc_run_t* run, const glabc_user_model_t* um) { return run_user(ctx, run, um, true); }
 
 extern "C" {
 

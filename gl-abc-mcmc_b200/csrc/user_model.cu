@@ -51,6 +51,8 @@ struct UserRun {
     float lp_loc[8], lp_scale[8], gp_loc[8], gp_scale[8], gp_inv_scale[8];
     float kern_c, kern_m;     // log K(dis) = kern_c + kern_m * dis^2   (Mixture.py:38-53)
     float params[64];
+    float* aux;               // iSIR: [C][8] carried state (slot 0 cached log-weight, slot 1 `local` flag)
+    int n_candidates, pad2;
 };
 __device__ __forceinline__ uint4 glabc_philox(u32 c0, u32 c1, u32 c2, u32 c3, u32 k0, u32 k1)
 {
@@ -189,6 +191,181 @@ extern "C" __global__ void __launch_bounds__(128) glabc_k_global_user(const __gr
         for (int k = 0; k < D * (D + 1) / 2; ++k) st[4 + 2 * D + k] += gram[k];
     }
 }
+
+// ---- GLMCMC (iSIR) step for a user model: GLMCMC.py:58-104 with weight_sampling :7-22 --------------------------------
+// gp_* hold the Importance_Proposal here.  Candidate j of step i is a pure function of (chain, i, j) through Philox, so
+// the K weights are computed first and only the selected candidate is rebuilt — no per-candidate storage.
+__device__ __forceinline__ float glabc_candidate(const UserRun& R, u32 g0, u32 g1, u32 i, int j, float* th, float* y, float& pk)
+{
+    constexpr int NZ = D + NN, NB = (NZ + 3) / 4;
+    float z[NB * 4];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const uint4 w = glabc_philox(g0, g1, i, 0x100u + (u32)(j * NB + b), R.key0, R.key1);
+        glabc_box_muller(w.x, w.y, z[4 * b], z[4 * b + 1]);
+        glabc_box_muller(w.z, w.w, z[4 * b + 2], z[4 * b + 3]);
+    }
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        th[k] = fmaf(R.gp_scale[k], z[k], R.gp_loc[k]);     // Importance_Proposal.forward, GLMCMC.py:66
+        q = fmaf(z[k], z[k], q);
+    }
+    glabc_user_simulate(th, z + D, R.params, y);            // :71
+    pk = glabc_target(R, th, y);                            // log prior + log kernel
+    return pk + 0.5f * q;                                   // log-weight up to the proposal's constant (it cancels in the ratio)
+}
+extern "C" __global__ void __launch_bounds__(128) glabc_k_isir_user(const __grid_constant__ UserRun R)
+{
+    const int chain = blockIdx.x * blockDim.x + threadIdx.x;
+    if (chain >= R.n_chains) return;
+    const u64 gid = ((u64)R.chain_hi0 << 32 | R.chain_lo0) + (u64)chain;
+    const u32 g0 = (u32)gid, g1 = (u32)(gid >> 32);
+    const int NK = R.n_candidates;
+    float th[D], y[YD];
+#pragma unroll
+    for (int k = 0; k < D; ++k) th[k] = R.theta[(long long)chain * D + k];
+#pragma unroll
+    for (int k = 0; k < YD; ++k) y[k] = R.y[(long long)chain * YD + k];
+    float pk = glabc_target(R, th, y);
+    float lw_old = R.aux[(long long)chain * 8 + 0];
+    bool local = R.aux[(long long)chain * 8 + 1] != 0.f;
+    float n_glob = 0.f, acc_l = 0.f, acc_g = 0.f, sum[D], sumsq[D], gram[D * (D + 1) / 2];
+#pragma unroll
+    for (int k = 0; k < D; ++k) sum[k] = sumsq[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < D * (D + 1) / 2; ++k) gram[k] = 0.f;
+    const long long cstride = R.trace_layout == 2 ? (long long)D : R.trace_chains * D;
+    float* row = nullptr;
+    if (R.trace_layout != 0) {
+        const long long r0 = (long long)R.first_step - (R.write_row0 ? 1 : 0) - R.trace_row_base;
+        row = R.trace_layout == 2 ? R.trace + ((R.trace_chain_off + chain) * R.trace_rows + r0) * D
+                                  : R.trace + (r0 * R.trace_chains + R.trace_chain_off + chain) * D;
+        if (R.write_row0) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) row[k] = th[k];
+            row += cstride;
+        }
+    }
+    for (u32 i = R.first_step; i <= R.last_step && R.last_step >= R.first_step; ++i) {
+        const uint4 w0 = glabc_philox(g0, g1, i, 1u, R.key0, R.key1);
+        const bool is_global = R.gf_all_global || (w0.x < R.gf_thr);              // GLMCMC.py:59
+        float dl[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) dl[k] = 0.f;
+        bool moved = false;
+        if (is_global) {
+            if (local) {                                                          // :60-64: log-weight of the current state
+                float qo = 0.f;
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    const float r = (th[k] - R.gp_loc[k]) * R.gp_inv_scale[k];
+                    qo = fmaf(r, r, qo);
+                }
+                lw_old = pk + 0.5f * qo;
+            }
+            local = false;
+            // shifted weights (the reference exponentiates un-shifted in float32, :78; the shift only removes underflow)
+            float lw[17], thc[D], yc[YD], pkc, mx = lw_old;
+            lw[0] = lw_old;
+            for (int j = 0; j < NK; ++j) {
+                lw[j + 1] = glabc_candidate(R, g0, g1, i, j, thc, yc, pkc);
+                if (!(lw[j + 1] == lw[j + 1])) lw[j + 1] = -INFINITY;             // :80-81 NaN weight -> 0
+                mx = fmaxf(mx, lw[j + 1]);
+            }
+            if (mx > -INFINITY) {
+                double S = 0.0;
+                for (int j = 0; j <= NK; ++j) S += (double)__expf(lw[j] - mx);
+                const uint4 wu = glabc_philox(g0, g1, i, 0x80000000u, R.key0, R.key1);
+                const double u = ((double)wu.x * 4294967296.0 + (double)wu.y) * (1.0 / 18446744073709551616.0);
+                const double thr = u * S;                                         // weight_sampling, :7-22
+                double run = 0.0;
+                int ind = -1;
+                for (int j = 0; j <= NK; ++j) {
+                    run += (double)__expf(lw[j] - mx);
+                    if (ind < 0 && thr < run) ind = j;
+                }
+                if (ind > 0) {                                                    // :84-88
+                    const float lwn = glabc_candidate(R, g0, g1, i, ind - 1, thc, yc, pkc);
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {
+                        dl[k] = thc[k] - th[k];
+                        th[k] = thc[k];
+                    }
+#pragma unroll
+                    for (int k = 0; k < YD; ++k) y[k] = yc[k];
+                    pk = pkc;
+                    lw_old = lwn;
+                    moved = true;
+                }
+            }
+        } else {                                                                  // local random walk, :90-104
+            constexpr int NZ = D + NN, NB = (NZ + 3) / 4;
+            float z[NB * 4], thp[D], yp[YD];
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                const uint4 w = glabc_philox(g0, g1, i, 2u + b, R.key0, R.key1);
+                glabc_box_muller(w.x, w.y, z[4 * b], z[4 * b + 1]);
+                glabc_box_muller(w.z, w.w, z[4 * b + 2], z[4 * b + 3]);
+            }
+#pragma unroll
+            for (int k = 0; k < D; ++k) thp[k] = th[k] + fmaf(R.lp_scale[k], z[k], R.lp_loc[k]);
+            glabc_user_simulate(thp, z + D, R.params, yp);
+            const float pkp = glabc_target(R, thp, yp);
+            const float log_u = __logf(__uint2float_rn(w0.y >> 8) * 0x1p-24f);
+            if (log_u < pkp - pk) {
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    dl[k] = thp[k] - th[k];
+                    th[k] = thp[k];
+                }
+#pragma unroll
+                for (int k = 0; k < YD; ++k) y[k] = yp[k];
+                pk = pkp;
+                local = true;                                                     // :100
+                moved = true;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            sum[k] += th[k];
+            sumsq[k] = fmaf(th[k], th[k], sumsq[k]);
+        }
+        int t = 0;
+#pragma unroll
+        for (int a = 0; a < D; ++a)
+#pragma unroll
+            for (int b = a; b < D; ++b, ++t) gram[t] = fmaf(dl[a], dl[b], gram[t]);
+        n_glob += is_global ? 1.f : 0.f;
+        acc_g += (moved && is_global) ? 1.f : 0.f;
+        acc_l += (moved && !is_global) ? 1.f : 0.f;
+        if (row != nullptr) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) row[k] = th[k];
+            row += cstride;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) R.theta[(long long)chain * D + k] = th[k];
+#pragma unroll
+    for (int k = 0; k < YD; ++k) R.y[(long long)chain * YD + k] = y[k];
+    R.aux[(long long)chain * 8 + 0] = lw_old;
+    R.aux[(long long)chain * 8 + 1] = local ? 1.f : 0.f;
+    if (R.stats != nullptr) {
+        float* st = R.stats + (long long)chain * (4 + 2 * D + D * (D + 1) / 2);
+        st[0] += R.last_step >= R.first_step ? (float)(R.last_step + 1u - R.first_step) : 0.f;
+        st[1] += n_glob;
+        st[2] += acc_l;
+        st[3] += acc_g;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            st[4 + k] += sum[k];
+            st[4 + D + k] += sumsq[k];
+        }
+#pragma unroll
+        for (int k = 0; k < D * (D + 1) / 2; ++k) st[4 + 2 * D + k] += gram[k];
+    }
+}
 )GLABC";
 
 // ---- lazily bound NVRTC / driver entry points --------------------------------------------------------------------
@@ -257,7 +434,8 @@ Dyn& dyn()
 
 struct Compiled {
     CUmodule mod = nullptr;
-    CUfunction fn = nullptr;
+    CUfunction fn = nullptr;        // glabc_k_global_user
+    CUfunction fn_isir = nullptr;   // glabc_k_isir_user
 };
 std::mutex g_cache_mu;
 std::map<std::string, Compiled> g_cache;   // key: device | arch | dims | source
@@ -316,7 +494,7 @@ int user_model_check(int cc, const glabc_user_model_t& um, std::string& err)
     return compile_to_cubin(d, cc, um, cubin, err);
 }
 
-int user_model_compile(int device, int cc, const glabc_user_model_t& um, void** fn_out, std::string& err)
+int user_model_compile(int device, int cc, const glabc_user_model_t& um, bool isir, void** fn_out, std::string& err)
 {
     Dyn& d = dyn();
     if (!d.ok) {
@@ -329,7 +507,7 @@ int user_model_compile(int device, int cc, const glabc_user_model_t& um, void** 
     std::lock_guard<std::mutex> lock(g_cache_mu);
     auto it = g_cache.find(key);
     if (it != g_cache.end()) {
-        *fn_out = it->second.fn;
+        *fn_out = isir ? it->second.fn_isir : it->second.fn;
         return GLABC_OK;
     }
     std::vector<char> cubin;
@@ -346,8 +524,13 @@ int user_model_compile(int device, int cc, const glabc_user_model_t& um, void** 
         err = "cuModuleGetFunction: " + cu_err(d, cr);
         return GLABC_ERR_CUDA;
     }
+    cr = d.moduleGetFunction(&c.fn_isir, c.mod, "glabc_k_isir_user");
+    if (cr != CUDA_SUCCESS) {
+        err = "cuModuleGetFunction: " + cu_err(d, cr);
+        return GLABC_ERR_CUDA;
+    }
     g_cache[key] = c;
-    *fn_out = c.fn;
+    *fn_out = isir ? c.fn_isir : c.fn;
     return GLABC_OK;
 }
 

@@ -145,8 +145,9 @@ class Engine:
         return trace
 
     def run_user(self, model, *, theta, y, n_steps, gf, step_base=0, chain_id_base=0, seed=0, trace_layout=_abi.TRACE_CHAIN_MAJOR,
-                 trace=None, trace_rows=None, write_row0=True, stats=None, block_threads=0):
-        """GlobalMCMC transitions for a `models.UserModel` (compiled on first use); LOCAL / GLOBAL slots must be bound"""
+                 trace=None, trace_rows=None, write_row0=True, stats=None, block_threads=0, sampler="global", K=0, aux=None):
+        """GlobalMCMC (`sampler="global"`, LOCAL / GLOBAL slots) or GLMCMC (`"isir"`, LOCAL / IMPORTANCE slots, K candidates, aux)
+        transitions for a `models.UserModel` (compiled on first use)"""
         cn, d = theta.shape
         rows = trace_rows if trace_rows is not None else step_base + n_steps + 1
         if trace is None and trace_layout != _abi.TRACE_NONE:
@@ -155,10 +156,11 @@ class Engine:
         r = _abi.RunPOD(n_chains=cn, n_steps=n_steps, step_base=step_base, chain_id_base=chain_id_base,
                         seed=int(seed) & 0xFFFFFFFFFFFFFFFF, global_frequency=float(gf), rng_mode=_abi.RNG_NATIVE,
                         arith_mode=_abi.ARITH_FAST, trace_layout=trace_layout, write_row0=int(write_row0),
-                        block_threads=block_threads, trace_rows=rows, trace_chains=cn, theta=self._ptr(theta), y=self._ptr(y),
-                        trace=self._ptr(trace), stats=self._ptr(stats), stream=self._stream())
+                        block_threads=block_threads, n_candidates=int(K), trace_rows=rows, trace_chains=cn, theta=self._ptr(theta),
+                        y=self._ptr(y), aux=self._ptr(aux), trace=self._ptr(trace), stats=self._ptr(stats), stream=self._stream())
         pod = model.user_pod()
-        self.ctx.check(self.lib.glabc_run_global_user(self.ctx.handle, C.byref(r), C.byref(pod)))
+        fn = self.lib.glabc_run_isir_user if sampler == "isir" else self.lib.glabc_run_global_user
+        self.ctx.check(fn(self.ctx.handle, C.byref(r), C.byref(pod)))
         return trace
 
     def aglmcmc_params(self, *, step_size, alpha, hat_eps_T, rule=_abi.BW_SILVERMAN, init=True, init_p=None, init_s=None,

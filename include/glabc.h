@@ -371,6 +371,11 @@ GLABC_API int glabc_run_aglmcmc(glabc_ctx* ctx, const glabc_run_t* run, const gl
  * glabc_run_global.  The first call for a given source compiles it (about a second); the module is cached for the
  * life of the process.  A compile error is returned as GLABC_ERR_INVALID with the NVRTC log in glabc_last_error.     */
 GLABC_API int glabc_run_global_user(glabc_ctx* ctx, const glabc_run_t* run, const glabc_user_model_t* model);
+/* GLMCMC loop body (GLMCMC.py:58-104, weight_sampling :7-22) for a user-supplied model: LOCAL = Local_Proposal, IMPORTANCE =
+ * Importance_Proposal (DiagGaussian), run->n_candidates = batch_size, run->aux as glabc_run_isir.  The importance weights are
+ * exponentiated max-shifted (the reference's un-shifted float32 exp can underflow a whole row to `None`; the shift removes
+ * that artefact and nothing else).                                                                                        */
+GLABC_API int glabc_run_isir_user(glabc_ctx* ctx, const glabc_run_t* run, const glabc_user_model_t* model);
 /* Compile-only check of a user model for compute capability `cc` (100 = sm_100a): needs NVRTC but neither a GPU nor a
  * context.  The NVRTC log (or "" on success) is copied to log[log_cap].                                              */
 GLABC_API int glabc_user_model_check(const glabc_user_model_t* model, int32_t cc, char* log, size_t log_cap);
