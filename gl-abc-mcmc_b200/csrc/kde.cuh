@@ -433,6 +433,32 @@ static __global__ void __launch_bounds__(256) k_kde_cdf(const float* __restrict_
     }
 }
 
+// one native-mode draw q of set `set` (kernel_density.py:142-149): categorical index by inverse CDF on the float64 prefix
+// sums, Gaussian jitter; a pure function of (chain id, round, q) through Philox, so any subset of the q's can be generated
+template <int D>
+__device__ __forceinline__ void kde_draw_native(const KdeSets& S, const double* __restrict__ cdf, int64_t set, int n, int round,
+                                                int64_t q, const RoundKeys& rk, uint64_t chain_id_base, float (&out)[D])
+{
+    const uint64_t gid = chain_id_base + static_cast<uint64_t>(set);
+    const Stream st{static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32)};
+    const uint4 wu = st.block(rk, static_cast<uint32_t>(round), kSlotAdSample + 2u * static_cast<uint32_t>(q));
+    const double u = static_cast<double>(wu.x) * 0x1p-32;
+    const double* cs = cdf + set * S.cap;
+    int lo = 0, hi = n - 1;  // first j with u < cdf[j]; n - 1 if rounding leaves none
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (u < cs[mid]) hi = mid; else lo = mid + 1;
+    }
+    const int idx = min(max(lo, 0), n - 1);
+    const uint4 wn = st.block(rk, static_cast<uint32_t>(round), kSlotAdSample + 2u * static_cast<uint32_t>(q) + 1u);
+    float z[4];
+    box_muller(wn.x, wn.y, z[0], z[1]);
+    box_muller(wn.z, wn.w, z[2], z[3]);
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+        out[i] = __fadd_rn(S.X[(set * S.cap + idx) * D + i], __fmul_rn(z[i], S.bw[set * D + i]));
+}
+
 // sample(), kernel_density.py:130-152
 template <int D>
 __global__ void __launch_bounds__(256) k_kde_sample(KdeSets S, const double* __restrict__ cdf, int64_t m, RoundKeys rk,

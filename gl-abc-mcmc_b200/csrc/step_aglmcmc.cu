@@ -40,10 +40,14 @@ static cudaError_t run_family(const AgConsts& K, const AgWorkspace& W, const AgT
             return e;
         if (!replay && (e = launch_kde_cdf(W.kde_wn, W.kde_n, W.pending, C, B, W.cdf, st)) != cudaSuccess) return e;
         const uint64_t base = (static_cast<uint64_t>(R.chain_hi0) << 32) | R.chain_lo0;
-        e = launch_kde_sample(S, D, W.cdf, 4 * B, R.rk, base, W.n_adapt, replay ? T.ad_idx : nullptr, replay ? T.ad_noise : nullptr,
-                              1, 1, C, 4 * B * C, 4 * B * D * C, replay ? T.tape_rounds - 1 : 0x7fffffff, W.smp, st);
-        if (e != cudaSuccess) return e;
-        k_ag_filter<D><<<static_cast<unsigned>(C), 256, 0, st>>>(K, W);
+        if (replay) {
+            e = launch_kde_sample(S, D, W.cdf, 4 * B, R.rk, base, W.n_adapt, T.ad_idx, T.ad_noise, 1, 1, C, 4 * B * C, 4 * B * D * C,
+                                  T.tape_rounds - 1, W.smp, st);
+            if (e != cudaSuccess) return e;
+            k_ag_filter<D><<<static_cast<unsigned>(C), 256, 0, st>>>(K, W);
+        } else {
+            k_ag_sample_filter<D><<<static_cast<unsigned>(C), 256, 0, st>>>(K, W, S, R.rk, base);
+        }
         if ((e = launch_kde_logprob(S, W.kde_lw, D, W.blk_theta, B, W.blk_lq, strict, st)) != cudaSuccess) return e;
         if (replay) k_ag_block<D, FAMILY, false, true><<<g_cb, 256, 0, st>>>(K, R, W, T);
         else k_ag_block<D, FAMILY, false, false><<<g_cb, 256, 0, st>>>(K, R, W, T);

@@ -327,6 +327,47 @@ __global__ void __launch_bounds__(256) k_ag_filter(const __grid_constant__ AgCon
     }
 }
 
+// Native RNG: KDE.sample(4B) + the prior filter fused (AGLMCMC.py:219-226).  Draw q is a pure function of (chain, round, q),
+// so the CTA generates draws in order, 256 at a time, and stops as soon as B valid ones are placed — with a prior that almost
+// never rejects that is B draws instead of 4B, and the [C][4B][D] sample buffer is never touched.  Same block as
+// k_kde_sample + k_ag_filter produce (tested through the native-mode oracle comparison).
+template <int D>
+__global__ void __launch_bounds__(256) k_ag_sample_filter(const __grid_constant__ AgConsts K, AgWorkspace W, KdeSets S, RoundKeys rk,
+                                                          uint64_t chain_id_base)
+{
+    __shared__ int wsum[8];
+    const int64_t c = blockIdx.x;
+    if (W.pending[c] == 0) return;
+    const int B = W.B, M = 4 * W.B, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = W.kde_n[c], round = W.n_adapt[c];
+    int have = 0;
+    for (int start = 0; start < M && have < B; start += 256) {
+        const int j = start + tid;
+        float th[D];
+        bool valid = false;
+        if (j < M) {
+            kde_draw_native<D>(S, W.cdf, c, n, round, j, rk, chain_id_base, th);
+            valid = model_prior<D, true>(K.model, th) > K.log_prior_floor;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, valid);
+        if (lane == 0) wsum[warp] = __popc(bal);
+        __syncthreads();
+        int before = __popc(bal & ((1u << lane) - 1u)), total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            before += w < warp ? wsum[w] : 0;
+            total += wsum[w];
+        }
+        const int pos = have + before;
+        if (valid && pos < B) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) W.blk_theta[(c * B + pos) * D + k] = th[k];
+        }
+        have += total;
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // the chain step, AGLMCMC.py:124-168 (global) / :251-271 (local)
 // ---------------------------------------------------------------------------------------------
