@@ -463,7 +463,28 @@ __global__ void __launch_bounds__(256) k_mala(const __grid_constant__ MalaConsts
             local = false;
 
             double S, w0n;
-            if (lw_wide) {  // float64 weights (no underflow near -104)
+            if (!STRICT && lw_wide) {
+                // FAST: the promoted (float64) weights only matter because float32 exp underflows near -104; exponentiating
+                // max-shifted in float32 gives the same resampling law without the double-precision exp, divide and scan
+                const float lw_f = lane == 0 ? static_cast<float>(lw_old) : lw_c;
+                float m = (lane <= NK && lw_f == lw_f) ? lw_f : -INFINITY;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+                float w;
+                asm("ex2.approx.f32 %0, %1;" : "=f"(w) : "f"((lw_f - m) * 1.4426950408889634f));
+                if (w != w || lane > NK || m == -INFINITY) w = 0.0f;
+                float Sf = w;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) Sf += __shfl_xor_sync(0xffffffffu, Sf, off);
+                const double thr = u64 * static_cast<double>(Sf);
+                double run = 0.0;
+                for (int j = 0; j <= NK; ++j) {
+                    run += static_cast<double>(__shfl_sync(0xffffffffu, w, j));
+                    if (ind < 0 && thr < run) ind = j;
+                }
+                S = static_cast<double>(Sf) * exp(static_cast<double>(m));   // un-shifted, for the debug record only (dead otherwise)
+                w0n = static_cast<double>(__fdiv_rn(__shfl_sync(0xffffffffu, w, 0), Sf));
+            } else if (lw_wide) {  // float64 weights (no underflow near -104)
                 double w = exp(lane == 0 ? lw_old : static_cast<double>(lw_c));
                 if (w != w || lane > NK) w = 0.0;
                 S = torch_sum_lanes64(w, NK + 1);
@@ -617,27 +638,50 @@ __global__ void __launch_bounds__(256) k_mala(const __grid_constant__ MalaConsts
                 const double mean = FAMILY == GLABC_MODEL_ABS_NORMAL ? fabs(theta_p[k]) : theta_p[k];
                 y_p[k] = mean + static_cast<double>(noise);
             }
-            const double prior_p = gauss_log_prob64<D>(K.model.prior, theta_p);
-            const double kern_p = model_log_kernel64<D>(K.model, y_p);
-            double rr[D];  // log_proposal(Theta_prop, grad_prop, Theta_old, tau), :97-116
+            double prior_p, kern_p, lq_rev, log_acc;
+            if constexpr (STRICT) {
+                prior_p = gauss_log_prob64<D>(K.model.prior, theta_p);
+                kern_p = model_log_kernel64<D>(K.model, y_p);
+                double rr[D];  // log_proposal(Theta_prop, grad_prop, Theta_old, tau), :97-116
 #pragma unroll
-            for (int k = 0; k < D; ++k) rr[k] = (theta[k] - theta_p[k] - grad_p[k] * (K.tau * K.tau) / 2.0) / K.tau;
-            const double lq_rev = gauss_log_prob64<D>(K.unit, rr);
-            double prior_o, kern_o;
-            if (wide) {
-                prior_o = gauss_log_prob64<D>(K.model.prior, theta);
-                kern_o = model_log_kernel64<D>(K.model, y);
+                for (int k = 0; k < D; ++k) rr[k] = (theta[k] - theta_p[k] - grad_p[k] * (K.tau * K.tau) / 2.0) / K.tau;
+                lq_rev = gauss_log_prob64<D>(K.unit, rr);
+                double prior_o, kern_o;
+                if (wide) {
+                    prior_o = gauss_log_prob64<D>(K.model.prior, theta);
+                    kern_o = model_log_kernel64<D>(K.model, y);
+                } else {
+                    float tf[D], yf[D];
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {
+                        tf[k] = __double2float_rn(theta[k]);
+                        yf[k] = __double2float_rn(y[k]);
+                    }
+                    prior_o = static_cast<double>(model_prior<D, STRICT>(K.model, tf));
+                    kern_o = static_cast<double>(model_log_kernel<D, STRICT>(K.model, yf));
+                }
+                log_acc = prior_p + kern_p + lq_rev - prior_o - kern_o - static_cast<double>(lq_fwd);  // :190-193
             } else {
-                float tf[D], yf[D];
+                // FAST: the five log-densities in float32 (the reference's are float64 only because theta was promoted); the
+                // state itself stays float64 so the chain's arithmetic on theta is unchanged
+                float tpf[D], ypf[D], tf[D], yf[D], rrf[D];
+                const float inv_tau = 1.0f / K.tau_f, half_tau2 = 0.5f * K.tau_f * K.tau_f;
 #pragma unroll
                 for (int k = 0; k < D; ++k) {
-                    tf[k] = __double2float_rn(theta[k]);
-                    yf[k] = __double2float_rn(y[k]);
+                    tpf[k] = static_cast<float>(theta_p[k]);
+                    ypf[k] = static_cast<float>(y_p[k]);
+                    tf[k] = static_cast<float>(theta[k]);
+                    yf[k] = static_cast<float>(y[k]);
+                    rrf[k] = (static_cast<float>(theta[k] - theta_p[k]) - static_cast<float>(grad_p[k]) * half_tau2) * inv_tau;
                 }
-                prior_o = static_cast<double>(model_prior<D, STRICT>(K.model, tf));
-                kern_o = static_cast<double>(model_log_kernel<D, STRICT>(K.model, yf));
+                const float pp = model_prior<D, false>(K.model, tpf), kp = model_log_kernel<D, false>(K.model, ypf);
+                const float lr = gauss_log_prob<D, false>(K.unit, rrf);
+                const float po = model_prior<D, false>(K.model, tf), ko = model_log_kernel<D, false>(K.model, yf);
+                prior_p = static_cast<double>(pp);
+                kern_p = static_cast<double>(kp);
+                lq_rev = static_cast<double>(lr);
+                log_acc = static_cast<double>(((pp + kp) - (po + ko)) + (lr - lq_fwd));
             }
-            const double log_acc = prior_p + kern_p + lq_rev - prior_o - kern_o - static_cast<double>(lq_fwd);  // :190-193
             const float log_w = STRICT ? logf(u_a) : log_approx(u_a);
             const bool accept = static_cast<double>(log_w) < log_acc;
             if constexpr (REPLAY) {

@@ -67,7 +67,10 @@ def test_replay_golden(eng, ci, arith):
         assert same.mean() > 0.999
         loc = ((tf["rec"][0].astype(np.int64) & 1) == 0) & same
         for a, b in ((1, 1), (2, 2), (3, 3), (6, 4), (7, 5), (14, 8), (15, 9), (16, 10)):
-            err = np.abs(d1[a][loc] - tf["rec"][b][loc]) / np.maximum(np.abs(tf["rec"][b][loc]), 1e-3)
+            scale = np.maximum(np.abs(tf["rec"][b][loc]), 1e-3)
+            if a == 1:   # log_acc is a difference of O(100) float32 log-densities in FAST mode: relative to the terms
+                scale = scale + np.abs(tf["rec"][8][loc]) + np.abs(tf["rec"][9][loc]) + np.abs(tf["rec"][10][loc])
+            err = np.abs(d1[a][loc] - tf["rec"][b][loc]) / scale
             assert err.max() < 5e-3, (a, float(err.max()))
 
 
