@@ -777,10 +777,13 @@ def _main():
         h_extra = dict(extra)
         if s64 is not None:
             h_extra["state64"] = torch.zeros(C, abi.STATE64_SLOTS, dtype=torch.float64).pin_memory()
-        h_layout = abi.TRACE_TIME_MAJOR if layout != abi.TRACE_NONE else abi.TRACE_NONE
+        # host view: chain-major [C, T, 2] for GlobalMCMC (out[c] is a reference-shaped chain; glabc_run_global_host brings part
+        # of the chains back as move events and expands them on the host cores), time-major for the other samplers
+        chain_host = entry in ("global", "isir") and layout != abi.TRACE_NONE
+        h_layout = abi.TRACE_NONE if layout == abi.TRACE_NONE else (abi.TRACE_CHAIN_MAJOR if chain_host else abi.TRACE_TIME_MAJOR)
         del trace
         torch.cuda.empty_cache()
-        h_trace = torch.empty((T, C, d)).pin_memory() if h_layout != abi.TRACE_NONE else None
+        h_trace = None if h_layout == abi.TRACE_NONE else torch.empty((C, T, d) if chain_host else (T, C, d)).pin_memory()
 
         def e2e_step(i):
             h_theta.copy_(h_theta0)
@@ -829,8 +832,13 @@ def _main():
                                   "note": "same host-buffer call with trace_layout NONE: state + statistics copied back, no chain"}
         line["e2e"] = {"value": steps_per_pass * e_steps / float(dt.item()), "unit": "chain-steps/s",
                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e_steps,
-                       "note": f"glabc_run_{entry}_host: pinned host buffers, full trace copied back in time chunks "
-                               "overlapped with the kernels; host view [T,C,2] (chain c = trace[:, c])"}
+                       "note": (f"glabc_run_{entry}_host: pinned host buffers, the full dense float32 trace [C,T,2] delivered to the host: "
+                                "the chains travel as run-length (move) events (a chain moves on ~1 % of its steps) and the host cores "
+                                "expand them into the dense buffer with full-line non-temporal stores, group by group while the next "
+                                "group's kernel runs; bit-identical to the dense PCIe copy (GLABC_HOST_EVENTS=0), bounded by the "
+                                "host's DRAM write rate instead of PCIe") if chain_host else
+                               (f"glabc_run_{entry}_host: pinned host buffers, full trace copied back in time chunks "
+                                "overlapped with the kernels; host view [T,C,2] (chain c = trace[:, c])")}
 
     if rank == 0 and world == 1 and a.sampler == "global" and not a.no_extra:
         line["other_kernels"] = other_kernels(eng, model, lp, gp)

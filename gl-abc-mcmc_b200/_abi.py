@@ -24,7 +24,7 @@ DIST_NONE, DIST_DIAG_GAUSSIAN, DIST_UNIFORM, DIST_GAMMA, DIST_GAUSSIAN_MIXTURE =
 SLOT_LOCAL, SLOT_GLOBAL, SLOT_IMPORTANCE = range(3)
 RNG_NATIVE, RNG_REPLAY = 0, 1
 ARITH_FAST, ARITH_STRICT = 0, 1
-TRACE_NONE, TRACE_TIME_MAJOR, TRACE_CHAIN_MAJOR = 0, 1, 2
+TRACE_NONE, TRACE_TIME_MAJOR, TRACE_CHAIN_MAJOR, TRACE_EVENTS = 0, 1, 2, 3
 
 STAT_STEPS, STAT_GLOBAL_STEPS, STAT_ACC_LOCAL, STAT_ACC_GLOBAL, STAT_SUM = 0, 1, 2, 3, 4
 

@@ -6,7 +6,14 @@
 #include <cstring>
 #include <initializer_list>
 #include <new>
+#include <immintrin.h>
+
+#include <atomic>
+#include <chrono>
+#include <cstdlib>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "launch.cuh"
 #include "flow.cuh"
@@ -47,6 +54,14 @@ struct glabc_ctx {
     float* d_trace[2] = {nullptr, nullptr};
     size_t trace_cap = 0;
     cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    // host entry, event transport (run_global_host_hybrid): device state + event buffer of the event-encoded chains, pinned staging
+    cudaStream_t s_ev = nullptr;
+    cudaEvent_t ev_events = nullptr;   // (unused: kept for ABI-neutral layout of the context)
+    cudaEvent_t ev_group[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float* d_ev = nullptr;
+    size_t d_ev_cap = 0;
+    float* h_ev = nullptr;
+    size_t h_ev_cap = 0;
     cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
 };
 
@@ -128,6 +143,12 @@ int glabc_ctx_destroy(glabc_ctx* ctx)
         if (ctx->ev_done[b]) cudaEventDestroy(ctx->ev_done[b]);
         if (ctx->ev_free[b]) cudaEventDestroy(ctx->ev_free[b]);
     }
+    if (ctx->s_ev) cudaStreamDestroy(ctx->s_ev);
+    if (ctx->ev_events) cudaEventDestroy(ctx->ev_events);
+    for (auto& e : ctx->ev_group)
+        if (e) cudaEventDestroy(e);
+    if (ctx->d_ev) cudaFree(ctx->d_ev);
+    if (ctx->h_ev) cudaFreeHost(ctx->h_ev);
     if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
     if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
     delete ctx;
@@ -289,9 +310,12 @@ static uint32_t gf_threshold16(float gf)
     return static_cast<uint32_t>(std::ceil(static_cast<double>(gf) * 65536.0));
 }
 
-static int make_run_params(glabc_ctx* ctx, const glabc_run_t* run, int dim, int tape_slots, RunParams* out, int* block)
+static int make_run_params(glabc_ctx* ctx, const glabc_run_t* run, int dim, int tape_slots, RunParams* out, int* block,
+                           bool events_ok = false)
 {
     if (!run) return fail(ctx, GLABC_ERR_INVALID, "null run description");
+    if (run->trace_layout == GLABC_TRACE_EVENTS && !events_ok)
+        return fail(ctx, GLABC_ERR_UNSUPPORTED, "GLABC_TRACE_EVENTS is written by run_global (DiagGaussian proposals) and run_isir only");
     if (run->n_chains < 0 || run->n_chains > INT32_MAX) return fail(ctx, GLABC_ERR_INVALID, "n_chains out of range");
     if (run->n_steps < 0 || run->step_base < 0 || run->step_base + run->n_steps >= 0xFFFFFFF0ll)
         return fail(ctx, GLABC_ERR_INVALID, "step_base + n_steps must stay below 2^32 (Philox block counter)");
@@ -299,9 +323,14 @@ static int make_run_params(glabc_ctx* ctx, const glabc_run_t* run, int dim, int 
         return fail(ctx, GLABC_ERR_INVALID, "at most 16,777,215 transitions per launch (float32 step counters): chunk the run "
                                             "with step_base, the chain continues bit-identically");
     if (!run->theta || !run->y) return fail(ctx, GLABC_ERR_INVALID, "theta / y state pointers are required");
-    if (run->trace_layout < GLABC_TRACE_NONE || run->trace_layout > GLABC_TRACE_CHAIN_MAJOR)
+    if (run->trace_layout < GLABC_TRACE_NONE || run->trace_layout > GLABC_TRACE_EVENTS)
         return fail(ctx, GLABC_ERR_INVALID, "bad trace_layout %d", run->trace_layout);
-    if (run->trace_layout != GLABC_TRACE_NONE) {
+    if (run->trace_layout == GLABC_TRACE_EVENTS) {
+        if (!run->trace || run->trace_rows < 2) return fail(ctx, GLABC_ERR_INVALID, "GLABC_TRACE_EVENTS needs trace [chains][trace_rows >= 2][1 + d]");
+        if (run->rng_mode != GLABC_RNG_NATIVE || run->tape_dump) return fail(ctx, GLABC_ERR_UNSUPPORTED, "GLABC_TRACE_EVENTS: native RNG, no tape dump");
+        if (run->trace_chain_off < 0 || run->trace_chain_off + run->n_chains > run->trace_chains)
+            return fail(ctx, GLABC_ERR_INVALID, "chains fall outside the event buffer");
+    } else if (run->trace_layout != GLABC_TRACE_NONE) {
         if (!run->trace) return fail(ctx, GLABC_ERR_INVALID, "trace pointer required for this trace_layout");
         const int64_t lo = run->step_base + (run->write_row0 ? 0 : 1) - run->trace_row_base;
         const int64_t hi = run->step_base + run->n_steps - run->trace_row_base;
@@ -379,10 +408,11 @@ static int run_device(glabc_ctx* ctx, SamplerKind kind, const glabc_run_t* run)
         const glabc_dist_t& lp = ctx->dist[GLABC_SLOT_LOCAL];
         const glabc_dist_t& gp = ctx->dist[GLABC_SLOT_GLOBAL];
         if (lp.dim != d || gp.dim != d) return fail(ctx, GLABC_ERR_INVALID, "proposal dim does not match theta_dim %d", d);
-        int st = make_run_params(ctx, run, d, GLABC_TAPE_GLOBAL_SLOTS(d, d), &R, &block);
+        const bool tuned = all_gaussian(ctx, {GLABC_SLOT_LOCAL, GLABC_SLOT_GLOBAL});
+        int st = make_run_params(ctx, run, d, GLABC_TAPE_GLOBAL_SLOTS(d, d), &R, &block, tuned);
         if (st) return st;
         if (R.n_chains == 0) return GLABC_OK;
-        if (!all_gaussian(ctx, {GLABC_SLOT_LOCAL, GLABC_SLOT_GLOBAL})) {
+        if (!tuned) {
             // Uniform / Gamma / GaussianMixture proposals: the general kernel (float32; replay takes the proposal draws
             // themselves: tape32 [steps][2 + d][C] = U_b, eps_sim, U_a and tape64 [steps][d][C] = the draw in float64)
             if (run->tape_dump) return fail(ctx, GLABC_ERR_UNSUPPORTED, "tape dump exists for DiagGaussian proposals only");
@@ -413,7 +443,7 @@ static int run_device(glabc_ctx* ctx, SamplerKind kind, const glabc_run_t* run)
         if (run->n_candidates < 1 || run->n_candidates > GLABC_MAX_K)
             return fail(ctx, GLABC_ERR_INVALID, "n_candidates (batch_size) must be in 1..%d", GLABC_MAX_K);
         if (!run->aux) return fail(ctx, GLABC_ERR_INVALID, "run_isir needs the aux state [C][%d] (log-weight, local flag)", GLABC_AUX_SLOTS);
-        int st = make_run_params(ctx, run, d, GLABC_TAPE_ISIR_SLOTS(d, d, run->n_candidates), &R, &block);
+        int st = make_run_params(ctx, run, d, GLABC_TAPE_ISIR_SLOTS(d, d, run->n_candidates), &R, &block, true);
         if (st) return st;
         if (run->rng_mode == GLABC_RNG_REPLAY && !run->tape64)
             return fail(ctx, GLABC_ERR_INVALID, "replay of run_isir needs tape64 (the float64 resampling uniforms)");
@@ -1048,20 +1078,384 @@ static int run_user(glabc_ctx* ctx, const glabc_run_t* run, const glabc_user_mod
 extern "C" int glabc_run_global_user(glabc_ctx* ctx, const glabc_run_t* run, const glabc_user_model_t* um) { return run_user(ctx, run, um, false); }
 extern "C" int glabc_run_isir_user(glabc_ctx* ctx, const glabc_run_t* run, const glabc_user_model_t* um) { return run_user(ctx, run, um, true); }
 
+
+// ---------------------------------------------------------------------------------------------
+// Host entry of GlobalMCMC with a chain-major host trace: part of the chains travels as EVENTS.
+// A chain is piecewise constant (the README workload moves on 1.2 % of its steps), so its dense float32 trace is 98 %
+// repetition and the 5.2 GB device -> host copy of 65,536 x 1e4 rows is what bounds the call (PCIe, ~55 GB/s).  Here the
+// last `f` of the chains are run with GLABC_TRACE_EVENTS, their moves (a few hundred KB per thousand chains) are copied
+// back, and the host cores expand them into the caller's dense buffer WHILE the DMA engine brings the other chains' dense
+// rows over PCIe (the chunked, double-buffered path above).  The caller's buffer ends up bit-identical to the all-dense path.
+// A chain with more moves than the event capacity makes the event part fall back to the dense path.
+// Tunables (environment): GLABC_HOST_EVENTS=0 disables, GLABC_HOST_EVENT_FRACTION (default 0.6), GLABC_HOST_THREADS.
+// ---------------------------------------------------------------------------------------------
+// Run-length expansion of one chain into the caller's dense rows.  With AVX-512 and a row size that divides a cache line
+// (d in {1, 2, 4}) the whole chain is written as FULL 64-byte lines with non-temporal stores — a line that straddles a move
+// is assembled in a register first — so no line is read for ownership: 137 GB/s on the 16 host cores of the B200 box against
+// 65 GB/s for ordinary stores (profiles/micro/host_fill.cu; narrower NT stores are slower than ordinary ones).
+__attribute__((target("avx512f"))) static void expand_chain_nt512(const float* ev, uint32_t m, int d, int64_t row_base, int64_t row_end,
+                                                                  float* out)
+{
+    const int per_line = 16 / d;
+    alignas(64) float buf[16], pat[16];
+    int lv = 0;                       // floats of the current (aligned) line already assembled in buf
+    float* dst = nullptr;             // next float to write
+    bool aligned = false;
+    for (uint32_t k = 1; k <= m; ++k) {
+        const float* e = ev + static_cast<int64_t>(k) * (1 + d);
+        uint32_t r0, r1;
+        memcpy(&r0, e, sizeof(r0));
+        if (k < m) memcpy(&r1, e + (1 + d), sizeof(r1));
+        else r1 = static_cast<uint32_t>(row_end + 1);
+        int64_t n = static_cast<int64_t>(r1) - r0;
+        const float* row = e + 1;
+        if (k == 1) dst = out + (static_cast<int64_t>(r0) - row_base) * d;
+        while (!aligned && n > 0) {   // head of the chain: whole rows up to the first cache-line boundary
+            if ((reinterpret_cast<uintptr_t>(dst) & 63u) == 0) {
+                aligned = true;
+                break;
+            }
+            for (int i = 0; i < d; ++i) dst[i] = row[i];
+            dst += d;
+            --n;
+        }
+        if (n == 0) continue;
+        if (lv > 0) {                 // finish the line a previous run left open
+            while (lv < 16 && n > 0) {
+                for (int i = 0; i < d; ++i) buf[lv + i] = row[i];
+                lv += d;
+                --n;
+            }
+            if (lv == 16) {
+                _mm512_stream_ps(dst, _mm512_load_ps(buf));
+                dst += 16;
+                lv = 0;
+            }
+        }
+        if (n >= per_line) {
+            for (int i = 0; i < 16; ++i) pat[i] = row[i % d];
+            const __m512 v = _mm512_load_ps(pat);
+            const int64_t lines = n / per_line;
+            for (int64_t l = 0; l < lines; ++l) _mm512_stream_ps(dst + l * 16, v);
+            dst += lines * 16;
+            n -= lines * per_line;
+        }
+        for (; n > 0; --n) {          // open the next line
+            for (int i = 0; i < d; ++i) buf[lv + i] = row[i];
+            lv += d;
+        }
+    }
+    for (int i = 0; i < lv; ++i) dst[i] = buf[i];   // tail of the chain
+}
+
+static void fill_rows_plain(float* dst, int64_t n, const float* row, int d)
+{
+    if (d == 2) {
+        float2* p = reinterpret_cast<float2*>(dst);
+        const float2 v = make_float2(row[0], row[1]);
+        for (int64_t i = 0; i < n; ++i) p[i] = v;
+    } else {
+        for (int64_t i = 0; i < n; ++i)
+            for (int k = 0; k < d; ++k) dst[i * d + k] = row[k];
+    }
+}
+
+static void expand_chain(const float* ev, int64_t cap, int d, int64_t row_base, int64_t row_end, float* out, bool nt512)
+{
+    uint32_t m;
+    memcpy(&m, ev, sizeof(m));
+    if (m > cap - 1) m = static_cast<uint32_t>(cap - 1);
+    if (nt512) {
+        expand_chain_nt512(ev, m, d, row_base, row_end, out);
+        return;
+    }
+    for (uint32_t k = 1; k <= m; ++k) {
+        const float* e = ev + static_cast<int64_t>(k) * (1 + d);
+        uint32_t r0, r1;
+        memcpy(&r0, e, sizeof(r0));
+        if (k < m) memcpy(&r1, e + (1 + d), sizeof(r1));
+        else r1 = static_cast<uint32_t>(row_end + 1);
+        fill_rows_plain(out + (static_cast<int64_t>(r0) - row_base) * d, static_cast<int64_t>(r1) - r0, e + 1, d);
+    }
+}
+
+static int run_host(glabc_ctx* ctx, SamplerKind kind, const glabc_run_t* run, int64_t chunk_steps);
+
+// Dense transport for a chain-major host trace: the chains are run in GROUPS over all their steps, and each group's
+// [chains][rows][d] block — contiguous on both sides — goes back in one full-rate copy while the next group's kernel runs
+// (time chunks of a chain-major trace would be 2-D copies of ~1 KB segments, which the DMA engine moves at half the rate).
+static int dense_chain_groups(glabc_ctx* ctx, SamplerKind kind, const glabc_run_t* run, int64_t Cd)
+{
+    const int d = ctx->model.theta_dim, yd = ctx->model.y_dim, ns = GLABC_NSTATS(d);
+    const int64_t n_rows = run->n_steps + (run->write_row0 ? 1 : 0);
+    const int64_t row_lo = run->step_base + (run->write_row0 ? 0 : 1);
+    int64_t Cg = (int64_t(320) << 20) / (n_rows * d * int64_t(sizeof(float))) / 32 * 32;
+    if (Cg < 32) Cg = 32;
+    if (Cg > Cd) Cg = Cd;
+    const size_t n_theta = size_t(Cd) * d, n_y = size_t(Cd) * yd, n_stats = run->stats ? size_t(Cd) * ns : 0;
+    const size_t n_aux = run->aux ? size_t(Cd) * GLABC_AUX_SLOTS : 0;
+    int st = ensure_host_scratch(ctx, n_theta + n_y + n_stats + n_aux, size_t(Cg) * n_rows * d);
+    if (st) return st;
+    float* d_theta = ctx->d_state;
+    float* d_y = d_theta + n_theta;
+    float* d_stats = n_stats ? d_y + n_y : nullptr;
+    float* d_aux = n_aux ? d_y + n_y + n_stats : nullptr;
+    cudaStream_t sc = ctx->s_compute, sx = ctx->s_copy;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_theta, run->theta, n_theta * sizeof(float), cudaMemcpyHostToDevice, sc));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_y, run->y, n_y * sizeof(float), cudaMemcpyHostToDevice, sc));
+    if (d_stats) CUDA_TRY(ctx, cudaMemcpyAsync(d_stats, run->stats, n_stats * sizeof(float), cudaMemcpyHostToDevice, sc));
+    if (d_aux) CUDA_TRY(ctx, cudaMemcpyAsync(d_aux, run->aux, n_aux * sizeof(float), cudaMemcpyHostToDevice, sc));
+    bool used[2] = {false, false};
+    int b = 0;
+    for (int64_t g0 = 0; g0 < Cd; g0 += Cg) {
+        const int64_t n = std::min<int64_t>(Cg, Cd - g0);
+        glabc_run_t dev = *run;
+        dev.n_chains = n;
+        dev.chain_id_base = run->chain_id_base + g0;
+        dev.theta = d_theta + g0 * d;
+        dev.y = d_y + g0 * yd;
+        dev.stats = d_stats ? d_stats + g0 * ns : nullptr;
+        dev.aux = d_aux ? d_aux + g0 * GLABC_AUX_SLOTS : nullptr;
+        dev.trace = ctx->d_trace[b];
+        dev.trace_layout = GLABC_TRACE_CHAIN_MAJOR;
+        dev.trace_rows = n_rows;
+        dev.trace_chains = n;
+        dev.trace_chain_off = 0;
+        dev.trace_row_base = row_lo;
+        dev.stream = sc;
+        dev.tape_dump = nullptr;
+        dev.debug = nullptr;
+        if (used[b]) CUDA_TRY(ctx, cudaStreamWaitEvent(sc, ctx->ev_free[b], 0));
+        st = run_device(ctx, kind, &dev);
+        if (st) return st;
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_done[b], sc));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(sx, ctx->ev_done[b], 0));
+        float* dst = run->trace + ((run->trace_chain_off + g0) * run->trace_rows + (row_lo - run->trace_row_base)) * d;
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(dst, size_t(run->trace_rows) * d * sizeof(float), ctx->d_trace[b], size_t(n_rows) * d * sizeof(float),
+                                        size_t(n_rows) * d * sizeof(float), size_t(n), cudaMemcpyDeviceToHost, sx));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_free[b], sx));
+        used[b] = true;
+        b ^= 1;
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(run->theta, d_theta, n_theta * sizeof(float), cudaMemcpyDeviceToHost, sc));
+    CUDA_TRY(ctx, cudaMemcpyAsync(run->y, d_y, n_y * sizeof(float), cudaMemcpyDeviceToHost, sc));
+    if (d_stats) CUDA_TRY(ctx, cudaMemcpyAsync(run->stats, d_stats, n_stats * sizeof(float), cudaMemcpyDeviceToHost, sc));
+    if (d_aux) CUDA_TRY(ctx, cudaMemcpyAsync(run->aux, d_aux, n_aux * sizeof(float), cudaMemcpyDeviceToHost, sc));
+    CUDA_TRY(ctx, cudaStreamSynchronize(sc));
+    CUDA_TRY(ctx, cudaStreamSynchronize(sx));
+    return GLABC_OK;
+}
+
+static int run_global_host_hybrid(glabc_ctx* ctx, SamplerKind kind, const glabc_run_t* run, int64_t chunk_steps, bool* handled)
+{
+    *handled = false;
+    const char* off = getenv("GLABC_HOST_EVENTS");
+    if (off && off[0] == '0') return GLABC_OK;
+    if (!ctx->has_model || !run || run->trace_layout != GLABC_TRACE_CHAIN_MAJOR || !run->trace || run->rng_mode != GLABC_RNG_NATIVE ||
+        run->n_steps < 512 || run->n_chains < 256 || !run->theta || !run->y)
+        return GLABC_OK;
+    const int far_slot = kind == SAMPLER_ISIR ? GLABC_SLOT_IMPORTANCE : GLABC_SLOT_GLOBAL;
+    if (kind != SAMPLER_GLOBAL && kind != SAMPLER_ISIR) return GLABC_OK;
+    if (!ctx->has_dist[GLABC_SLOT_LOCAL] || !ctx->has_dist[far_slot] || !all_gaussian(ctx, {GLABC_SLOT_LOCAL, far_slot})) return GLABC_OK;
+    if (kind == SAMPLER_ISIR && !run->aux) return GLABC_OK;
+    const int dd = ctx->model.theta_dim;
+    const bool nt512 = (dd == 1 || dd == 2 || dd == 4) && __builtin_cpu_supports("avx512f");
+    // with full-line non-temporal stores the expansion alone runs at the host's DRAM write rate, which a concurrent dense DMA
+    // would only share; with ordinary stores (65 GB/s) the PCIe copy of part of the chains adds bandwidth
+    double frac = nt512 ? 1.0 : 0.6;
+    if (const char* f = getenv("GLABC_HOST_EVENT_FRACTION")) frac = atof(f);
+    if (!(frac > 0.0)) return GLABC_OK;
+    if (frac > 1.0) frac = 1.0;
+    const int d = ctx->model.theta_dim, yd = ctx->model.y_dim, ns = GLABC_NSTATS(d);
+    const int64_t C = run->n_chains;
+    int64_t Ce = static_cast<int64_t>(C * frac) / 32 * 32;
+    if (Ce <= 0) return GLABC_OK;
+    const int64_t Cd = C - Ce;
+    const int64_t row_lo = run->step_base + (run->write_row0 ? 0 : 1), row_end = run->step_base + run->n_steps;
+    if (row_lo - run->trace_row_base < 0 || row_end - run->trace_row_base >= run->trace_rows)
+        return fail(ctx, GLABC_ERR_INVALID, "trace rows fall outside the host buffer");
+    if (run->trace_chain_off < 0 || run->trace_chain_off + C > run->trace_chains)
+        return fail(ctx, GLABC_ERR_INVALID, "chains fall outside the host trace buffer");
+    *handled = true;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->s_ev) {
+        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_ev, cudaStreamNonBlocking));
+        for (auto& e : ctx->ev_group) CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    int64_t cap = run->n_steps / 32;
+    if (cap < 64) cap = 64;
+    if (cap > run->n_steps + 2) cap = run->n_steps + 2;
+    const size_t n_theta = size_t(Ce) * d, n_y = size_t(Ce) * yd, n_stats = run->stats ? size_t(Ce) * ns : 0;
+    const size_t n_aux = kind == SAMPLER_ISIR ? size_t(Ce) * GLABC_AUX_SLOTS : 0;
+    const size_t n_state = n_theta + n_y + n_stats + n_aux, n_events = size_t(Ce) * size_t(cap) * (1 + d);
+    if (n_state + n_events > ctx->d_ev_cap) {
+        if (ctx->d_ev) cudaFree(ctx->d_ev);
+        ctx->d_ev = nullptr;
+        ctx->d_ev_cap = 0;
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_ev, (n_state + n_events) * sizeof(float)));
+        ctx->d_ev_cap = n_state + n_events;
+    }
+    if (n_state + n_events > ctx->h_ev_cap) {
+        if (ctx->h_ev) cudaFreeHost(ctx->h_ev);
+        ctx->h_ev = nullptr;
+        ctx->h_ev_cap = 0;
+        CUDA_TRY(ctx, cudaHostAlloc(&ctx->h_ev, (n_state + n_events) * sizeof(float), cudaHostAllocDefault));
+        ctx->h_ev_cap = n_state + n_events;
+    }
+    float* d_theta = ctx->d_ev;
+    float* d_y = d_theta + n_theta;
+    float* d_stats = n_stats ? d_y + n_y : nullptr;
+    float* d_aux = n_aux ? d_y + n_y + n_stats : nullptr;
+    float* d_events = ctx->d_ev + n_state;
+    float* h_state = ctx->h_ev;                 // final theta | y | stats of the event chains
+    float* h_events = ctx->h_ev + n_state;
+    cudaStream_t se = ctx->s_ev;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_theta, run->theta + Cd * d, n_theta * sizeof(float), cudaMemcpyHostToDevice, se));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_y, run->y + Cd * yd, n_y * sizeof(float), cudaMemcpyHostToDevice, se));
+    if (d_stats) CUDA_TRY(ctx, cudaMemcpyAsync(d_stats, run->stats + Cd * ns, n_stats * sizeof(float), cudaMemcpyHostToDevice, se));
+    if (d_aux) CUDA_TRY(ctx, cudaMemcpyAsync(d_aux, run->aux + Cd * GLABC_AUX_SLOTS, n_aux * sizeof(float), cudaMemcpyHostToDevice, se));
+    // the event chains in up to 8 groups: the kernel of group g + 1 and the copy of group g's events overlap the expansion of
+    // group g - 1 on the host cores
+    int n_groups = static_cast<int>(Ce / 8192);
+    if (n_groups < 1) n_groups = 1;
+    if (n_groups > 8) n_groups = 8;
+    const int64_t per_group = ((Ce + n_groups - 1) / n_groups + 31) / 32 * 32;
+    int st = GLABC_OK;
+    for (int g = 0; g < n_groups; ++g) {
+        const int64_t g0 = g * per_group, gn = std::min<int64_t>(per_group, Ce - g0);
+        if (gn <= 0) {
+            n_groups = g;
+            break;
+        }
+        glabc_run_t dev = *run;
+        dev.n_chains = gn;
+        dev.chain_id_base = run->chain_id_base + Cd + g0;
+        dev.theta = d_theta + g0 * d;
+        dev.y = d_y + g0 * yd;
+        dev.stats = d_stats ? d_stats + g0 * ns : nullptr;
+        dev.aux = d_aux ? d_aux + g0 * GLABC_AUX_SLOTS : nullptr;
+        dev.trace = d_events + g0 * cap * (1 + d);
+        dev.trace_layout = GLABC_TRACE_EVENTS;
+        dev.trace_rows = cap;
+        dev.trace_chains = gn;
+        dev.trace_chain_off = 0;
+        dev.trace_row_base = 0;
+        dev.stream = se;
+        dev.tape_dump = nullptr;
+        dev.debug = nullptr;
+        st = run_device(ctx, kind, &dev);
+        if (st) return st;
+        CUDA_TRY(ctx, cudaMemcpyAsync(h_events + g0 * cap * (1 + d), d_events + g0 * cap * (1 + d), size_t(gn) * cap * (1 + d) * sizeof(float),
+                                      cudaMemcpyDeviceToHost, se));
+        if (g == n_groups - 1) CUDA_TRY(ctx, cudaMemcpyAsync(h_state, ctx->d_ev, n_state * sizeof(float), cudaMemcpyDeviceToHost, se));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_group[g], se));
+    }
+
+    // the host cores expand the events while the dense part (below) streams over PCIe
+    std::atomic<int> overflow{0};
+    int n_threads = static_cast<int>(std::thread::hardware_concurrency());
+    if (const char* t = getenv("GLABC_HOST_THREADS")) n_threads = atoi(t);
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 64) n_threads = 64;
+    const int device = ctx->device;
+    cudaEvent_t evg[8];
+    for (int g = 0; g < 8; ++g) evg[g] = ctx->ev_group[g];
+    float* host_trace = run->trace;
+    const int64_t trace_rows = run->trace_rows, chain_off = run->trace_chain_off + Cd, row_base = run->trace_row_base;
+    const bool timing = getenv("GLABC_HOST_TIMING") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto ms_since = [t_start]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
+    std::thread expander([=, &overflow]() {
+        cudaSetDevice(device);
+        double t_first = 0.0;
+        for (int g = 0; g < n_groups; ++g) {
+            if (cudaEventSynchronize(evg[g]) != cudaSuccess) {
+                overflow.store(2);
+                return;
+            }
+            if (g == 0) t_first = ms_since();
+            const int64_t g0 = g * per_group, g1 = std::min<int64_t>(g0 + per_group, Ce);
+            for (int64_t j = g0; j < g1; ++j) {   // a chain with more moves than the capacity: the event part is redone densely
+                uint32_t m;
+                memcpy(&m, h_events + j * cap * (1 + d), sizeof(m));
+                if (m > static_cast<uint32_t>(cap - 1)) {
+                    overflow.store(1);
+                    return;
+                }
+            }
+            std::vector<std::thread> workers;
+            for (int t = 0; t < n_threads; ++t)
+                workers.emplace_back([=]() {
+                    for (int64_t j = g0 + t; j < g1; j += n_threads)
+                        expand_chain(h_events + j * cap * (1 + d), cap, d, row_base, row_end, host_trace + (chain_off + j) * trace_rows * d,
+                                     nt512);
+                    _mm_sfence();   // the non-temporal stores are globally visible before the thread is joined
+                });
+            for (auto& w : workers) w.join();
+        }
+        if (timing) fprintf(stderr, "[glabc host] first events at %.1f ms, all expanded at %.1f ms (%lld chains, %d groups, %d threads, nt512 %d)\n",
+                            t_first, ms_since(), static_cast<long long>(Ce), n_groups, n_threads, static_cast<int>(nt512));
+    });
+
+    if (Cd > 0) st = dense_chain_groups(ctx, kind, run, Cd);   // the dense part: chains [0, Cd), group by group over PCIe
+    if (timing) fprintf(stderr, "[glabc host] dense part (%lld chains) done at %.1f ms\n", static_cast<long long>(Cd), ms_since());
+    expander.join();
+    if (timing) fprintf(stderr, "[glabc host] joined at %.1f ms\n", ms_since());
+    if (st) return st;
+    if (overflow.load() == 2) return fail(ctx, GLABC_ERR_CUDA, "event transport: waiting for the event copy failed");
+    if (overflow.load() == 1) {   // redo the event chains densely from their (untouched) initial host state
+        glabc_run_t redo = *run;
+        redo.n_chains = Ce;
+        redo.chain_id_base = run->chain_id_base + Cd;
+        redo.theta = run->theta + Cd * d;
+        redo.y = run->y + Cd * yd;
+        redo.stats = run->stats ? run->stats + Cd * ns : nullptr;
+        redo.aux = run->aux ? run->aux + Cd * GLABC_AUX_SLOTS : nullptr;
+        redo.trace_chain_off = run->trace_chain_off + Cd;
+        return run_host(ctx, kind, &redo, chunk_steps);
+    }
+    memcpy(run->theta + Cd * d, h_state, n_theta * sizeof(float));
+    memcpy(run->y + Cd * yd, h_state + n_theta, n_y * sizeof(float));
+    if (n_stats) memcpy(run->stats + Cd * ns, h_state + n_theta + n_y, n_stats * sizeof(float));
+    if (n_aux) memcpy(run->aux + Cd * GLABC_AUX_SLOTS, h_state + n_theta + n_y + n_stats, n_aux * sizeof(float));
+    return GLABC_OK;
+}
+
 extern "C" {
 
 int glabc_run_global(glabc_ctx* ctx, const glabc_run_t* run) { return run_device(ctx, SAMPLER_GLOBAL, run); }
 
+// host entry of a sampler whose trace can travel as events (GlobalMCMC, GLMCMC)
+static int run_host_chain_major(glabc_ctx* ctx, SamplerKind kind, const glabc_run_t* run, int64_t chunk_steps)
+{
+    if (!ctx) return GLABC_ERR_INVALID;
+    bool handled = false;
+    const int st = run_global_host_hybrid(ctx, kind, run, chunk_steps, &handled);
+    if (handled || st) return st;
+    if (ctx->has_model && run && run->trace_layout == GLABC_TRACE_CHAIN_MAJOR && run->trace && run->theta && run->y && run->n_chains > 0 &&
+        run->n_steps > 0 && run->rng_mode == GLABC_RNG_NATIVE && chunk_steps == 0 && (kind == SAMPLER_GLOBAL || run->aux)) {
+        // chain-major host trace without the event transport: whole chains, group by group (contiguous copies)
+        const int64_t row_lo = run->step_base + (run->write_row0 ? 0 : 1), row_end = run->step_base + run->n_steps;
+        if (row_lo - run->trace_row_base < 0 || row_end - run->trace_row_base >= run->trace_rows)
+            return fail(ctx, GLABC_ERR_INVALID, "trace rows fall outside the host buffer");
+        if (run->trace_chain_off < 0 || run->trace_chain_off + run->n_chains > run->trace_chains)
+            return fail(ctx, GLABC_ERR_INVALID, "chains fall outside the host trace buffer");
+        CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+        return dense_chain_groups(ctx, kind, run, run->n_chains);
+    }
+    return run_host(ctx, kind, run, chunk_steps);
+}
+
 int glabc_run_global_host(glabc_ctx* ctx, const glabc_run_t* run, int64_t chunk_steps)
 {
-    return run_host(ctx, SAMPLER_GLOBAL, run, chunk_steps);
+    return run_host_chain_major(ctx, SAMPLER_GLOBAL, run, chunk_steps);
 }
 
 int glabc_run_isir(glabc_ctx* ctx, const glabc_run_t* run) { return run_device(ctx, SAMPLER_ISIR, run); }
 
 int glabc_run_isir_host(glabc_ctx* ctx, const glabc_run_t* run, int64_t chunk_steps)
 {
-    return run_host(ctx, SAMPLER_ISIR, run, chunk_steps);
+    return run_host_chain_major(ctx, SAMPLER_ISIR, run, chunk_steps);
 }
 
 int glabc_run_mala(glabc_ctx* ctx, const glabc_run_t* run) { return run_device(ctx, SAMPLER_MALA, run); }

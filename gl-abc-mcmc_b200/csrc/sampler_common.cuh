@@ -216,6 +216,45 @@ struct ChainMajorVecWriter {
     }
 };
 
+// EVENTS: the chain as its moves (glabc.h GLABC_TRACE_EVENTS).  One scattered store per move instead of one row per step.
+template <int D>
+struct EventWriter {
+    float* ev;        // &events[chain][0][0], entries of 1 + D floats
+    uint32_t n;       // entries used so far + 1 (entry 0 is the header)
+    uint32_t cap;     // trace_rows
+    float last[D];
+    bool active;
+    static constexpr int smem_floats_per_warp = 0;
+    __device__ __forceinline__ EventWriter(const RunParams& r, int32_t chain, bool act, float*)
+        : ev(r.trace + (r.trace_chain_off + chain) * r.trace_rows * (1 + D)), n(1u), cap(static_cast<uint32_t>(r.trace_rows)), active(act)
+    {
+#pragma unroll
+        for (int k = 0; k < D; ++k) last[k] = __int_as_float(0x7fc00000);   // NaN: the first row always differs
+    }
+    __device__ __forceinline__ void put(const RunParams&, uint32_t row, const float (&v)[D])
+    {
+        bool moved = false;
+#pragma unroll
+        for (int k = 0; k < D; ++k) moved |= !(v[k] == last[k]);
+        if (moved) {
+            if (active && n < cap) {
+                float* e = ev + static_cast<int64_t>(n) * (1 + D);
+                e[0] = __uint_as_float(row);
+#pragma unroll
+                for (int k = 0; k < D; ++k) e[1 + k] = v[k];
+            }
+            ++n;
+#pragma unroll
+            for (int k = 0; k < D; ++k) last[k] = v[k];
+        }
+    }
+    __device__ __forceinline__ void maybe_flush(const RunParams&, uint32_t) {}
+    __device__ __forceinline__ void finish(const RunParams&)
+    {
+        if (active) ev[0] = __uint_as_float(n - 1u);
+    }
+};
+
 struct NoTraceWriter {
     __device__ __forceinline__ NoTraceWriter(const RunParams&, int32_t, bool, float*) {}
     template <int D>
@@ -230,6 +269,7 @@ template <int D> struct WriterFor<D, GLABC_TRACE_NONE> { using type = NoTraceWri
 template <int D> struct WriterFor<D, GLABC_TRACE_TIME_MAJOR> { using type = TimeMajorWriter<D>; };
 template <int D> struct WriterFor<D, GLABC_TRACE_CHAIN_MAJOR> { using type = ChainMajorVecWriter<D>; };
 template <> struct WriterFor<3, GLABC_TRACE_CHAIN_MAJOR> { using type = ChainMajorWriter<3>; };
+template <int D> struct WriterFor<D, GLABC_TRACE_EVENTS> { using type = EventWriter<D>; };
 
 // ---------------------------------------------------------------------------------------------
 // Per-chain statistics (layout: GLABC_STAT_* in glabc.h)

@@ -365,6 +365,7 @@ static cudaError_t launch_mode(const GlobalConsts& K, const RunParams& R, bool r
     case GLABC_TRACE_NONE: return launch_one<D, FAMILY, STRICT, false, GLABC_TRACE_NONE, false>(K, R, block, st);
     case GLABC_TRACE_TIME_MAJOR: return launch_one<D, FAMILY, STRICT, false, GLABC_TRACE_TIME_MAJOR, false>(K, R, block, st);
     case GLABC_TRACE_CHAIN_MAJOR: return launch_one<D, FAMILY, STRICT, false, GLABC_TRACE_CHAIN_MAJOR, false>(K, R, block, st);
+    case GLABC_TRACE_EVENTS: return launch_one<D, FAMILY, STRICT, false, GLABC_TRACE_EVENTS, false>(K, R, block, st);
     }
     return cudaErrorInvalidValue;
 }

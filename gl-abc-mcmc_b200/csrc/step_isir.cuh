@@ -602,6 +602,7 @@ static cudaError_t launch_isir_mode(const IsirConsts& K, const RunParams& R, boo
             case GLABC_TRACE_NONE: return launch_isir_one<D, FAMILY, STRICT, false, GLABC_TRACE_NONE, false, 5>(K, R, block, st);
             case GLABC_TRACE_TIME_MAJOR: return launch_isir_one<D, FAMILY, STRICT, false, GLABC_TRACE_TIME_MAJOR, false, 5>(K, R, block, st);
             case GLABC_TRACE_CHAIN_MAJOR: return launch_isir_one<D, FAMILY, STRICT, false, GLABC_TRACE_CHAIN_MAJOR, false, 5>(K, R, block, st);
+            case GLABC_TRACE_EVENTS: return launch_isir_one<D, FAMILY, STRICT, false, GLABC_TRACE_EVENTS, false, 5>(K, R, block, st);
             }
         }
     }
@@ -609,6 +610,7 @@ static cudaError_t launch_isir_mode(const IsirConsts& K, const RunParams& R, boo
     case GLABC_TRACE_NONE: return launch_isir_one<D, FAMILY, STRICT, false, GLABC_TRACE_NONE, false>(K, R, block, st);
     case GLABC_TRACE_TIME_MAJOR: return launch_isir_one<D, FAMILY, STRICT, false, GLABC_TRACE_TIME_MAJOR, false>(K, R, block, st);
     case GLABC_TRACE_CHAIN_MAJOR: return launch_isir_one<D, FAMILY, STRICT, false, GLABC_TRACE_CHAIN_MAJOR, false>(K, R, block, st);
+    case GLABC_TRACE_EVENTS: return launch_isir_one<D, FAMILY, STRICT, false, GLABC_TRACE_EVENTS, false>(K, R, block, st);
     }
     return cudaErrorInvalidValue;
 }

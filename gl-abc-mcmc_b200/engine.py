@@ -114,6 +114,8 @@ class Engine:
                 raise ValueError("device entry point takes contiguous CUDA tensors")
         rows = trace_rows if trace_rows is not None else step_base + n_steps + 1 - trace_row_base
         tchains = trace_chains if trace_chains is not None else cn
+        if trace is None and trace_layout == _abi.TRACE_EVENTS:
+            raise ValueError("TRACE_EVENTS needs a caller-allocated trace [chains, trace_rows, 1 + d]")
         if trace is None and trace_layout != _abi.TRACE_NONE:
             shape = (rows, tchains, d) if trace_layout == _abi.TRACE_TIME_MAJOR else (tchains, rows, d)
             trace = torch.empty(shape, dtype=torch.float32, device=self.device)

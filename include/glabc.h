@@ -111,8 +111,15 @@ typedef enum {
 typedef enum {
     GLABC_TRACE_NONE = 0,        /* statistics only                                               */
     GLABC_TRACE_TIME_MAJOR = 1,  /* trace[row][chain][d]                                          */
-    GLABC_TRACE_CHAIN_MAJOR = 2  /* trace[chain][row][d] — out[c] is a reference-shaped chain,
+    GLABC_TRACE_CHAIN_MAJOR = 2, /* trace[chain][row][d] — out[c] is a reference-shaped chain,
                                     rows staged through shared memory (GlobalMCMC.py:34,98)       */
+    GLABC_TRACE_EVENTS = 3       /* run_global / device buffers only: the chain as its MOVES.  trace[chain][trace_rows][1 + d]:
+                                    entry 0 = {number of moves (uint32 bits), -}, entry k >= 1 = {row index (uint32 bits),
+                                    theta[d]} of the k-th row whose theta differs from the previous row's (the first row
+                                    written always counts).  A chain is piecewise constant — the README workload moves on
+                                    1.2 % of its steps — so this is the trace losslessly run-length encoded; moves beyond
+                                    trace_rows - 1 are counted but not stored.  The host-buffer entry point uses it to bring
+                                    part of the chains back as events and expands them with the host cores.              */
 } glabc_trace_layout;
 
 /* Per-chain statistics accumulated in-kernel (replaces the reference's unused `num_acc`,

@@ -361,3 +361,48 @@ def test_checkpoint_resume_continues_bit_identically(tmp_path, which):
     with pytest.raises(ValueError, match="sampler"):
         g.GLMCMC(model, 400, torch.zeros(2), y0, lp, None, 0.9, gp, 5, resume=ck) if which != "glmcmc" else \
             g.GlobalMCMC(model, 400, torch.zeros(2), y0, gp, None, 0.5, lp, resume=ck)
+
+
+def test_host_entry_event_transport(monkeypatch):
+    """glabc_run_global_host with a chain-major host trace: part of the chains travels as move events and is expanded by
+    the host cores while the rest comes densely over PCIe — the host buffer must equal the device-resident dense trace
+    bit for bit, for every split, and a chain with more moves than the event capacity must fall back to the dense path."""
+    import glabc_b200 as g
+    from glabc_b200.engine import get_engine
+    eng = get_engine()
+    lp = g.DiagGaussian(2, torch.zeros(1, 2), torch.log(torch.tensor([0.35, 0.35])))
+    gp = g.DiagGaussian(2, torch.tensor([0.0, 0.0]), torch.tensor([0.0, 0.0]))
+    Cn, T, d = 1000, 1500, 2
+    y0 = torch.randn(Cn, d, generator=torch.Generator().manual_seed(4)) * 0.2236
+    for eps, frac in ((0.05, "0.6"), (0.05, "1.0"), (0.05, "0.13"), (3.0, "0.6")):   # eps = 3: most proposals accepted -> overflow
+        monkeypatch.setenv("GLABC_HOST_EVENT_FRACTION", frac)
+        eng.bind_model(g.Mixture_set(eps))
+        eng.bind_proposal(abi.SLOT_LOCAL, lp)
+        eng.bind_proposal(abi.SLOT_GLOBAL, gp)
+        th, yy = torch.zeros(Cn, d, device="cuda"), y0.cuda()
+        st = torch.zeros(Cn, abi.nstats(d), device="cuda")
+        want = eng.run("global", theta=th, y=yy, n_steps=T - 1, gf=0.5, seed=31, chain_id_base=7, stats=st,
+                       trace_layout=abi.TRACE_CHAIN_MAJOR)
+        torch.cuda.synchronize()
+        host = torch.full((Cn, T, d), float("nan")).pin_memory()
+        hth, hy, hst = torch.zeros(Cn, d), y0.clone(), torch.zeros(Cn, abi.nstats(d))
+        eng.run_host("global", theta=hth, y=hy, n_steps=T - 1, gf=0.5, seed=31, chain_id_base=7, trace=host, stats=hst,
+                     trace_layout=abi.TRACE_CHAIN_MAJOR)
+        assert torch.equal(host, want.cpu()), (eps, frac)
+        assert torch.equal(hth, th.cpu()) and torch.equal(hy, yy.cpu()) and torch.equal(hst, st.cpu())
+        if eps > 1:
+            assert float(st[:, abi.STAT_ACC_LOCAL].mean() + st[:, abi.STAT_ACC_GLOBAL].mean()) > (T - 1) / 32   # really overflowed
+    # the events layout itself, device buffers: entry 0 = count, entries = (row, theta) of every move
+    monkeypatch.delenv("GLABC_HOST_EVENT_FRACTION")
+    eng.bind_model(g.Mixture_set(0.05))
+    th, yy = torch.zeros(64, d, device="cuda"), y0[:64].cuda()
+    dense = eng.run("global", theta=th, y=yy, n_steps=600, gf=0.5, seed=5, trace_layout=abi.TRACE_CHAIN_MAJOR).cpu()
+    th, yy = torch.zeros(64, d, device="cuda"), y0[:64].cuda()
+    ev = torch.zeros(64, 128, 3, device="cuda")
+    eng.run("global", theta=th, y=yy, n_steps=600, gf=0.5, seed=5, trace_layout=abi.TRACE_EVENTS, trace=ev, trace_rows=128)
+    ev = ev.cpu()
+    for c in (0, 17, 63):
+        m = int(ev[c, 0, 0].view(torch.int32))
+        rows = ev[c, 1:m + 1, 0].contiguous().view(torch.int32).tolist()
+        moved = [0] + [i for i in range(1, 601) if not torch.equal(dense[c, i], dense[c, i - 1])]
+        assert rows == moved and torch.equal(ev[c, 1:m + 1, 1:], dense[c, moved])

@@ -262,3 +262,20 @@ def test_pipelined_fast_loop_equals_plain_loop(eng):
         assert float(same.float().mean()) > 0.995                    # an FMA contracted differently may flip a rare decision
         assert torch.equal(st[:, abi.STAT_GLOBAL_STEPS], st2[:, abi.STAT_GLOBAL_STEPS])
         assert torch.allclose(ax[same][:, :2], ax2[same][:, :2], rtol=1e-5, atol=1e-6)
+
+
+def test_host_entry_event_transport_isir(eng, monkeypatch):
+    """glabc_run_isir_host with a chain-major host trace (event transport, tests/test_global_gpu.py): equals the device trace"""
+    case, m, lp, ip = readme_pods()
+    Cn, T, d, K = 700, 1200, 2, 5
+    bind(eng, m, lp, ip)
+    y0 = (torch.randn(Cn, d, generator=torch.Generator().manual_seed(3)) * 0.2236)
+    for frac in ("1.0", "0.5"):
+        monkeypatch.setenv("GLABC_HOST_EVENT_FRACTION", frac)
+        th, yy, ax = torch.zeros(Cn, d, device="cuda"), y0.cuda(), fresh_aux(Cn, "cuda")
+        want = eng.run("isir", theta=th, y=yy, aux=ax, n_steps=T - 1, gf=0.9, seed=7, K=K, trace_layout=abi.TRACE_CHAIN_MAJOR)
+        torch.cuda.synchronize()
+        host = torch.full((Cn, T, d), float("nan")).pin_memory()
+        hth, hy, hax = torch.zeros(Cn, d), y0.clone(), torch.from_numpy(fresh_aux(Cn))
+        eng.run_host("isir", theta=hth, y=hy, aux=hax, n_steps=T - 1, gf=0.9, seed=7, K=K, trace=host, trace_layout=abi.TRACE_CHAIN_MAJOR)
+        assert torch.equal(host, want.cpu()) and torch.equal(hth, th.cpu()) and torch.equal(hax[:, :2], ax.cpu()[:, :2])
