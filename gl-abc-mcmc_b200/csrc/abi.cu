@@ -1353,7 +1353,12 @@ static int run_global_host_hybrid(glabc_ctx* ctx, SamplerKind kind, const glabc_
 
     // the host cores expand the events while the dense part (below) streams over PCIe
     std::atomic<int> overflow{0};
+    // one process per GPU shares the host's cores: LOCAL_WORLD_SIZE (torchrun) divides them between the ranks
     int n_threads = static_cast<int>(std::thread::hardware_concurrency());
+    if (const char* lws = getenv("LOCAL_WORLD_SIZE")) {
+        const int r = atoi(lws);
+        if (r > 1) n_threads = (n_threads + r - 1) / r;
+    }
     if (const char* t = getenv("GLABC_HOST_THREADS")) n_threads = atoi(t);
     if (n_threads < 1) n_threads = 1;
     if (n_threads > 64) n_threads = 64;
