@@ -1316,9 +1316,12 @@ static int run_global_host_hybrid(glabc_ctx* ctx, SamplerKind kind, const glabc_
     if (d_aux) CUDA_TRY(ctx, cudaMemcpyAsync(d_aux, run->aux + Cd * GLABC_AUX_SLOTS, n_aux * sizeof(float), cudaMemcpyHostToDevice, se));
     // the event chains in up to 8 groups: the kernel of group g + 1 and the copy of group g's events overlap the expansion of
     // group g - 1 on the host cores
+    // (a group's kernel is latency-bound — a chain's steps are sequential — so it takes about as long as a full launch's warp:
+    // many small groups are free for the 2 ms GlobalMCMC kernel, while the 24 ms iSIR kernel is cut in three at most)
     int n_groups = static_cast<int>(Ce / 8192);
+    const int max_groups = kind == SAMPLER_ISIR ? 3 : 8;
     if (n_groups < 1) n_groups = 1;
-    if (n_groups > 8) n_groups = 8;
+    if (n_groups > max_groups) n_groups = max_groups;
     const int64_t per_group = ((Ce + n_groups - 1) / n_groups + 31) / 32 * 32;
     int st = GLABC_OK;
     for (int g = 0; g < n_groups; ++g) {
