@@ -830,8 +830,13 @@ def _main():
         line["e2e_stats_only"] = {"value": steps_per_pass * e_steps / float(dt_s.item()), "unit": "chain-steps/s",
                                   "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d,
                                   "note": "same host-buffer call with trace_layout NONE: state + statistics copied back, no chain"}
+        wire = None
+        if chain_host and os.environ.get("GLABC_HOST_EVENTS", "1") != "0":
+            cap = min(T + 1, max(64, (T - 1) // 32))            # event capacity per chain (csrc/abi.cu run_global_host_hybrid)
+            wire = h2d + C * cap * (1 + d) * 4
         line["e2e"] = {"value": steps_per_pass * e_steps / float(dt.item()), "unit": "chain-steps/s",
                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e_steps,
+                       "pcie_d2h_bytes_per_step": wire if wire is not None else d2h,
                        "note": (f"glabc_run_{entry}_host: pinned host buffers, the full dense float32 trace [C,T,2] delivered to the host: "
                                 "the chains travel as run-length (move) events (a chain moves on ~1 % of its steps) and the host cores "
                                 "expand them into the dense buffer with full-line non-temporal stores, group by group while the next "
