@@ -361,7 +361,126 @@ __global__ void __launch_bounds__(256) k_mala(const __grid_constant__ MalaConsts
     ChainStats<D> stats;
     const Stream stream = chain_stream(R, chain);
 
+    // FAST native mode: a run of consecutive GLOBAL moves is resolved in one batch.  The branch coins and the K candidates of
+    // a step are state-independent (Philox), so lane (s, j) = s * (K + 1) + j builds candidate j - 1 of step i + s for up to five
+    // steps at once (30 of 32 lanes busy instead of 6); only the short dependent part — the weight of the current state, the
+    // max-shifted float32 weights, the scan against the 53-bit uniform, the switch — then runs step by step.
+    const int G1 = NK + 1;
+    const int slots = 32 / G1 < 5 ? 32 / G1 : 5;
+    constexpr bool kBatch = !STRICT && !REPLAY && !DUMP;
+
     for (uint32_t i = R.first_step; i <= R.last_step && R.last_step >= R.first_step; ++i) {
+        if constexpr (kBatch) {
+            if (slots >= 2) {
+                const int s_mine = lane / G1, j_mine = lane - s_mine * G1;
+                const uint32_t step_mine = i + static_cast<uint32_t>(s_mine);
+                const bool in_use = s_mine < slots && step_mine <= R.last_step && step_mine >= i;
+                const uint4 w0s = stream.block(R.rk, in_use ? step_mine : i, kSlotStep);
+                const bool glob_mine = in_use && ((step_block_ub(w0s) < R.gf_thr_hi) || R.gf_all_global);
+                const unsigned bal = __ballot_sync(0xffffffffu, glob_mine && j_mine == 0);
+                int L = 0;
+                while (L < slots && ((bal >> (L * G1)) & 1u)) ++L;
+                if (L >= 1) {
+                    // ---- state-independent part, all slots at once: candidate cj of step `step_mine` (GLMALA.py:158-165) ----
+                    const int cj = j_mine > 0 ? j_mine - 1 : 0;   // lane (s, 0) shadows candidate 0: it needs that block's spare bits
+                    float zc[kGroups * 4];
+                    uint4 wfirst = make_uint4(0, 0, 0, 0);
+#pragma unroll
+                    for (int g = 0; g < kGroups; ++g) {
+                        const uint4 w = stream.block(R.rk, in_use ? step_mine : i, kSlotNormal + 8u + cj * kGroups + g);
+                        if (g == 0) wfirst = w;
+                        box_muller(w.x, w.y, zc[4 * g], zc[4 * g + 1]);
+                        box_muller(w.z, w.w, zc[4 * g + 2], zc[4 * g + 3]);
+                    }
+                    float eps_p[D], eps_s[D], th_c[D], x_c[D];
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {
+                        eps_p[k] = zc[k];
+                        eps_s[k] = zc[D + k];
+                    }
+                    const float lq = gauss_forward<D, false>(K.ip, eps_p, th_c);
+                    model_simulate<D, false>(K.model, th_c, eps_s, x_c);
+                    const float lw_c = (model_prior<D, false>(K.model, th_c) + model_log_kernel<D, false>(K.model, x_c)) - lq;
+                    const uint64_t m53 = (static_cast<uint64_t>(step_block_ua(w0s)) << 29) |
+                                         (static_cast<uint64_t>(step_block_ua(wfirst)) << 5) |
+                                         static_cast<uint64_t>(step_block_ub(wfirst) >> 27);
+                    const double u64_mine = static_cast<double>(m53) * 0x1p-53;   // valid in lane (s, 0)
+                    // ---- the dependent part, step by step ----
+                    for (int sidx = 0; sidx < L; ++sidx) {
+                        const uint32_t step = i + static_cast<uint32_t>(sidx);
+                        const int base = sidx * G1;
+                        float prev[D];
+#pragma unroll
+                        for (int k = 0; k < D; ++k) prev[k] = __double2float_rn(theta[k]);
+                        if (local) {  // GLMALA.py:152-156
+                            if (wide) {
+                                lw_old = (gauss_log_prob64<D>(K.model.prior, theta) + model_log_kernel64<D>(K.model, y)) -
+                                         gauss_log_prob64<D>(K.ip, theta);
+                            } else {
+                                float tf[D], yf[D];
+#pragma unroll
+                                for (int k = 0; k < D; ++k) {
+                                    tf[k] = __double2float_rn(theta[k]);
+                                    yf[k] = __double2float_rn(y[k]);
+                                }
+                                lw_old = static_cast<double>((model_prior<D, false>(K.model, tf) + model_log_kernel<D, false>(K.model, yf)) -
+                                                             gauss_log_prob<D, false>(K.ip, tf));
+                            }
+                            lw_wide = wide;
+                        }
+                        local = false;
+                        const bool in_grp = lane >= base && lane < base + G1;
+                        const float lw_f = lane == base ? static_cast<float>(lw_old) : lw_c;
+                        float m = (in_grp && lw_f == lw_f) ? lw_f : -INFINITY;
+#pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+                        float w;
+                        asm("ex2.approx.f32 %0, %1;" : "=f"(w) : "f"((lw_f - m) * 1.4426950408889634f));
+                        if (w != w || !in_grp || m == -INFINITY) w = 0.0f;
+                        double S = 0.0;   // summed in candidate order: the result does not depend on which slot the step sits in
+                        for (int j = 0; j <= NK; ++j) S += static_cast<double>(__shfl_sync(0xffffffffu, w, base + j));
+                        const double thr = shfl_f64(u64_mine, base) * S;
+                        double run = 0.0;
+                        int ind = -1;
+                        for (int j = 0; j <= NK; ++j) {
+                            run += static_cast<double>(__shfl_sync(0xffffffffu, w, base + j));
+                            if (ind < 0 && thr < run) ind = j;
+                        }
+                        const int src = base + (ind > 0 ? ind : 1);
+                        float th_t[D], x_t[D];
+#pragma unroll
+                        for (int k = 0; k < D; ++k) {
+                            th_t[k] = __shfl_sync(0xffffffffu, th_c[k], src);
+                            x_t[k] = __shfl_sync(0xffffffffu, x_c[k], src);
+                        }
+                        const float lw_t = __shfl_sync(0xffffffffu, lw_c, src);
+                        if (ind > 0) {  // GLMALA.py:175-179: the cached gradient is NOT refreshed (B-6)
+#pragma unroll
+                            for (int k = 0; k < D; ++k) {
+                                theta[k] = static_cast<double>(th_t[k]);
+                                y[k] = static_cast<double>(x_t[k]);
+                            }
+                            lw_old = static_cast<double>(lw_t);
+                        }
+                        bool changed = false;
+                        float now[D];
+#pragma unroll
+                        for (int k = 0; k < D; ++k) {
+                            now[k] = __double2float_rn(theta[k]);
+                            changed |= now[k] != prev[k];
+                        }
+                        stats.update(true, changed, now, prev);
+                        if (lane == static_cast<int>(step & 31u)) {
+#pragma unroll
+                            for (int k = 0; k < D; ++k) keep[k] = now[k];
+                        }
+                        if (((step + 1u) & 31u) == 0u || step == R.last_step) flush(step);
+                    }
+                    i += static_cast<uint32_t>(L - 1);
+                    continue;
+                }
+            }
+        }
         const int64_t srow = static_cast<int64_t>(i - R.first_step);
         const float* tp = nullptr;
         uint4 w0 = make_uint4(0, 0, 0, 0);
