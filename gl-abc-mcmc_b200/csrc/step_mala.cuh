@@ -309,7 +309,7 @@ __device__ __forceinline__ double warp_scan_f64(double v, int lane)
 }
 
 template <int D, int FAMILY, bool STRICT, bool REPLAY, bool DUMP>
-__global__ void __launch_bounds__(256) k_mala(const __grid_constant__ MalaConsts K, const __grid_constant__ RunParams R)
+__global__ void __launch_bounds__(128, 6) k_mala(const __grid_constant__ MalaConsts K, const __grid_constant__ RunParams R)
 {
     const int lane = threadIdx.x & 31;
     const int32_t chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -873,6 +873,7 @@ __global__ void __launch_bounds__(256) k_mala(const __grid_constant__ MalaConsts
 template <int D, int FAMILY, bool STRICT, bool REPLAY, bool DUMP>
 static cudaError_t launch_mala_one(const MalaConsts& K, const RunParams& R, int block, cudaStream_t st)
 {
+    if (block > 128) block = 128;   // __launch_bounds__(128, 6): 80 registers, six CTAs (24 chains) per SM
     const int warps_per_block = block / 32;
     const int grid = (R.n_chains + warps_per_block - 1) / warps_per_block;
     k_mala<D, FAMILY, STRICT, REPLAY, DUMP><<<grid, block, 0, st>>>(K, R);
