@@ -56,7 +56,6 @@ struct glabc_ctx {
     cudaStream_t s_compute = nullptr, s_copy = nullptr;
     // host entry, event transport (run_global_host_hybrid): device state + event buffer of the event-encoded chains, pinned staging
     cudaStream_t s_ev = nullptr;
-    cudaEvent_t ev_events = nullptr;   // (unused: kept for ABI-neutral layout of the context)
     cudaEvent_t ev_group[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float* d_ev = nullptr;
     size_t d_ev_cap = 0;
@@ -144,7 +143,6 @@ int glabc_ctx_destroy(glabc_ctx* ctx)
         if (ctx->ev_free[b]) cudaEventDestroy(ctx->ev_free[b]);
     }
     if (ctx->s_ev) cudaStreamDestroy(ctx->s_ev);
-    if (ctx->ev_events) cudaEventDestroy(ctx->ev_events);
     for (auto& e : ctx->ev_group)
         if (e) cudaEventDestroy(e);
     if (ctx->d_ev) cudaFree(ctx->d_ev);
@@ -1178,8 +1176,6 @@ static void expand_chain(const float* ev, int64_t cap, int d, int64_t row_base, 
         fill_rows_plain(out + (static_cast<int64_t>(r0) - row_base) * d, static_cast<int64_t>(r1) - r0, e + 1, d);
     }
 }
-
-static int run_host(glabc_ctx* ctx, SamplerKind kind, const glabc_run_t* run, int64_t chunk_steps);
 
 // Dense transport for a chain-major host trace: the chains are run in GROUPS over all their steps, and each group's
 // [chains][rows][d] block — contiguous on both sides — goes back in one full-rate copy while the next group's kernel runs
