@@ -320,9 +320,15 @@ static int make_run_params(glabc_ctx* ctx, const glabc_run_t* run, int dim, int 
     if (run->n_steps >= (1 << 24))
         return fail(ctx, GLABC_ERR_INVALID, "at most 16,777,215 transitions per launch (float32 step counters): chunk the run "
                                             "with step_base, the chain continues bit-identically");
-    if (!run->theta || !run->y) return fail(ctx, GLABC_ERR_INVALID, "theta / y state pointers are required");
     if (run->trace_layout < GLABC_TRACE_NONE || run->trace_layout > GLABC_TRACE_EVENTS)
         return fail(ctx, GLABC_ERR_INVALID, "bad trace_layout %d", run->trace_layout);
+    if (run->n_chains == 0) {   // nothing to do: empty buffers may be null pointers
+        RunParams r{};
+        *out = r;
+        *block = 64;
+        return GLABC_OK;
+    }
+    if (!run->theta || !run->y) return fail(ctx, GLABC_ERR_INVALID, "theta / y state pointers are required");
     if (run->trace_layout == GLABC_TRACE_EVENTS) {
         if (!run->trace || run->trace_rows < 2) return fail(ctx, GLABC_ERR_INVALID, "GLABC_TRACE_EVENTS needs trace [chains][trace_rows >= 2][1 + d]");
         if (run->rng_mode != GLABC_RNG_NATIVE || run->tape_dump) return fail(ctx, GLABC_ERR_UNSUPPORTED, "GLABC_TRACE_EVENTS: native RNG, no tape dump");
@@ -531,8 +537,8 @@ static int run_host(glabc_ctx* ctx, SamplerKind kind, const glabc_run_t* run, in
     if (!ctx->has_model) return fail(ctx, GLABC_ERR_INVALID, "no model bound: call glabc_model_set first");
     if (!run) return fail(ctx, GLABC_ERR_INVALID, "null run description");
     if (run->rng_mode != GLABC_RNG_NATIVE) return fail(ctx, GLABC_ERR_INVALID, "host entry points run the native RNG only");
-    if (!run->theta || !run->y) return fail(ctx, GLABC_ERR_INVALID, "theta / y state pointers are required");
     if (run->n_chains <= 0 || run->n_steps < 0) return run->n_chains == 0 ? GLABC_OK : fail(ctx, GLABC_ERR_INVALID, "bad sizes");
+    if (!run->theta || !run->y) return fail(ctx, GLABC_ERR_INVALID, "theta / y state pointers are required");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const int d = ctx->model.theta_dim, yd = ctx->model.y_dim;
     const int64_t C = run->n_chains;
