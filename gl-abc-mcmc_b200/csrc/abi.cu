@@ -1490,6 +1490,16 @@ int glabc_esjd(glabc_ctx* ctx, const float* trace, int32_t layout, int64_t rows,
     return GLABC_OK;
 }
 
+int glabc_summarize(glabc_ctx* ctx, const float* stats, int64_t chains, int32_t dim, double* out, void* stream)
+{
+    if (!ctx) return GLABC_ERR_INVALID;
+    if (!out || (chains > 0 && !stats)) return fail(ctx, GLABC_ERR_INVALID, "glabc_summarize: null pointer");
+    if (dim < 1 || dim > 4) return fail(ctx, GLABC_ERR_UNSUPPORTED, "glabc_summarize: dim %d outside 1..4", dim);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, launch_summarize(stats, chains, dim, out, static_cast<cudaStream_t>(stream)));
+    return GLABC_OK;
+}
+
 int glabc_philox_kat(glabc_ctx* ctx, const uint32_t* ctr, const uint32_t* key, int64_t n, uint32_t* out, void* stream)
 {
     if (!ctx) return GLABC_ERR_INVALID;

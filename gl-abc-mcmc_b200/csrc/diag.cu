@@ -95,6 +95,85 @@ cudaError_t launch_esjd(const float* trace, int layout, int64_t rows, int64_t ch
     }
 }
 
+// Summary of a shard's per-chain statistics in ONE launch (sharding.summarize): out[6 + 2d] float64 +=
+// {chains, steps, global steps, accepted local, accepted global, sum of per-chain ESJD (ESJD.py:21-24 from the Gram
+// accumulators), sum theta[d], sum theta^2[d]} — the additive vector the ranks all-reduce.
+template <int D>
+__global__ void __launch_bounds__(256) k_summarize(const float* __restrict__ stats, int64_t chains, double* __restrict__ out)
+{
+    constexpr int NS = 4 + 2 * D + D * (D + 1) / 2, NO = 6 + 2 * D;
+    double acc[NO];
+#pragma unroll
+    for (int k = 0; k < NO; ++k) acc[k] = 0.0;
+    for (int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; c < chains; c += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const float* st = stats + c * NS;
+        const double n = fmax(static_cast<double>(st[GLABC_STAT_STEPS]), 1.0);
+        acc[0] += 1.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[1 + k] += static_cast<double>(st[k]);
+        // det(G / n)^(1/D), G the symmetric Gram matrix (upper triangle, row-major), by elimination in float64
+        double g[D][D];
+        int q = 0;
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = i; j < D; ++j, ++q) g[i][j] = g[j][i] = static_cast<double>(st[GLABC_STAT_SUM + 2 * D + q]) / n;
+        double det = 1.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            const double piv = g[i][i];
+            det *= piv;
+            if (piv != 0.0) {
+#pragma unroll
+                for (int r = i + 1; r < D; ++r) {
+                    const double f = g[r][i] / piv;
+#pragma unroll
+                    for (int cc = i + 1; cc < D; ++cc) g[r][cc] -= f * g[i][cc];
+                }
+            }
+        }
+        acc[5] += det > 0.0 ? pow(det, 1.0 / D) : 0.0;
+#pragma unroll
+        for (int k = 0; k < 2 * D; ++k) acc[6 + k] += static_cast<double>(st[GLABC_STAT_SUM + k]);
+    }
+    __shared__ double red[8][NO];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NO; ++k) {
+        double v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            int lo = __double2loint(v), hi = __double2hiint(v);
+            lo = __shfl_xor_sync(0xffffffffu, lo, o);
+            hi = __shfl_xor_sync(0xffffffffu, hi, o);
+            v += __hiloint2double(hi, lo);
+        }
+        if (lane == 0) red[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NO) {
+        double v = 0.0;
+        for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+        atomicAdd(out + threadIdx.x, v);
+    }
+}
+
+cudaError_t launch_summarize(const float* stats, int64_t chains, int dim, double* out, cudaStream_t st)
+{
+    if (chains <= 0) return cudaSuccess;
+    int64_t blocks = (chains + 255) / 256;
+    if (blocks > 296) blocks = 296;
+    const unsigned g = static_cast<unsigned>(blocks);
+    switch (dim) {
+    case 1: k_summarize<1><<<g, 256, 0, st>>>(stats, chains, out); break;
+    case 2: k_summarize<2><<<g, 256, 0, st>>>(stats, chains, out); break;
+    case 3: k_summarize<3><<<g, 256, 0, st>>>(stats, chains, out); break;
+    case 4: k_summarize<4><<<g, 256, 0, st>>>(stats, chains, out); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
 __global__ void k_philox_kat(const uint32_t* __restrict__ ctr, const uint32_t* __restrict__ key, int64_t n,
                              uint32_t* __restrict__ out)
 {

@@ -18,6 +18,8 @@ cudaError_t launch_mala(const MalaConsts& K, int dim, const RunParams& R, bool s
 cudaError_t launch_esjd(const float* trace, int layout, int64_t rows, int64_t chains, int dim, float* out,
                         cudaStream_t st);
 
+cudaError_t launch_summarize(const float* stats, int64_t chains, int dim, double* out, cudaStream_t st);
+
 cudaError_t launch_philox_kat(const uint32_t* ctr, const uint32_t* key, int64_t n, uint32_t* out, cudaStream_t st);
 
 }  // namespace glabc

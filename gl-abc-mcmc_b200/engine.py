@@ -264,6 +264,14 @@ class Engine:
         self.ctx.check(fn(self.ctx.handle, C.byref(r), int(chunk_steps)))
         return trace
 
+    def summarize(self, stats_raw, dim):
+        """[chains, steps, global steps, acc local, acc global, sum esjd, sum theta (d), sum theta^2 (d)] of a shard, float64,
+        one kernel (glabc_summarize)"""
+        out = torch.zeros(6 + 2 * dim, dtype=torch.float64, device=self.device)
+        self.ctx.check(self.lib.glabc_summarize(self.ctx.handle, self._ptr(stats_raw), stats_raw.shape[0], int(dim), self._ptr(out),
+                                                self._stream()))
+        return out
+
     def esjd(self, trace, layout):
         """per-chain esjd of a device trace ([rows, C, d] time-major / [C, rows, d] chain-major)."""
         if layout == _abi.TRACE_TIME_MAJOR:

@@ -33,8 +33,11 @@ def allreduce_summary(local_sums):
 def summarize(stats, esjd_per_chain=None):
     """Additive summary vector of a shard's RunStats: [chains, steps, global_steps, acc_local,
     acc_global, sum esjd, sum theta (d), sum theta^2 (d)] — ready for `allreduce_summary`."""
-    raw = stats.raw.double()
     d = stats.dim
+    if stats.raw.is_cuda and esjd_per_chain is None and stats.raw.is_contiguous() and d <= 4:
+        from .engine import get_engine              # one fused kernel instead of ~25 small torch launches
+        return get_engine(stats.raw.device).summarize(stats.raw, d)
+    raw = stats.raw.double()
     e = stats.esjd() if esjd_per_chain is None else esjd_per_chain.double()
     head = torch.stack([torch.tensor(float(raw.shape[0]), dtype=torch.float64, device=raw.device),
                         raw[:, 0].sum(), raw[:, 1].sum(), raw[:, 2].sum(), raw[:, 3].sum(), e.sum()])

@@ -433,6 +433,12 @@ GLABC_API int glabc_run_mala_host(glabc_ctx* ctx, const glabc_run_t* run, int64_
 GLABC_API int glabc_esjd(glabc_ctx* ctx, const float* trace, int32_t layout, int64_t rows, int64_t chains,
                int32_t dim, float* out, void* stream);
 
+/* Additive summary of a shard's per-chain statistics (stats [chains][GLABC_NSTATS(dim)], as the samplers fill them) in one
+ * launch: out[6 + 2 dim] float64 += {chains, steps, global steps, accepted local, accepted global, sum over chains of
+ * esjd (ESJD.py:21-24 from the Gram accumulators), sum theta[dim], sum theta^2[dim]} — the vector the ranks all-reduce.
+ * The caller zeroes `out`.                                                                                              */
+GLABC_API int glabc_summarize(glabc_ctx* ctx, const float* stats, int64_t chains, int32_t dim, double* out, void* stream);
+
 /* raw Philox4x32-10 blocks for known-answer tests: out[n][4] = philox(ctr[n][4], key[n][2])       */
 GLABC_API int glabc_philox_kat(glabc_ctx* ctx, const uint32_t* ctr, const uint32_t* key, int64_t n,
                      uint32_t* out, void* stream);

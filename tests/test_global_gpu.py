@@ -406,3 +406,29 @@ def test_host_entry_event_transport(monkeypatch):
         rows = ev[c, 1:m + 1, 0].contiguous().view(torch.int32).tolist()
         moved = [0] + [i for i in range(1, 601) if not torch.equal(dense[c, i], dense[c, i - 1])]
         assert rows == moved and torch.equal(ev[c, 1:m + 1, 1:], dense[c, moved])
+
+
+def test_summarize_kernel_matches_torch(eng):
+    """glabc_summarize (one launch) == the torch restatement in sharding.summarize, d = 1..4"""
+    from glabc_b200 import sharding
+    from glabc_b200.engine import RunStats
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for d in (1, 2, 3, 4):
+        Cn = 1000 + d
+        raw = torch.zeros(Cn, abi.nstats(d), device="cuda")
+        raw[:, 0] = 500.0
+        raw[:, 1:4] = torch.randint(0, 200, (Cn, 3), device="cuda", generator=g).float()
+        th = torch.randn(Cn, 500, d, device="cuda", generator=g) * 0.1
+        raw[:, 4:4 + d] = th.sum(1)
+        raw[:, 4 + d:4 + 2 * d] = (th * th).sum(1)
+        dl = th[:, 1:] - th[:, :-1]
+        t = 0
+        for i in range(d):
+            for j in range(i, d):
+                raw[:, 4 + 2 * d + t] = (dl[:, :, i] * dl[:, :, j]).sum(1)
+                t += 1
+        rs = RunStats(raw, d)
+        got = sharding.summarize(rs)
+        want = sharding.summarize(rs, esjd_per_chain=rs.esjd())       # the torch path
+        assert got.shape == want.shape == (6 + 2 * d,)
+        assert torch.allclose(got, want, rtol=1e-9, atol=1e-9), (d, got, want)
