@@ -704,7 +704,8 @@ def _main():
     kernel_rate = C * (T - 1) / (kms * 1e-3)
 
     # kernels of ours per pass: one fused step kernel, or for AGLMCMC the init pair + per round (step + 8 adaptation kernels)
-    launches_per_pass = 1 if entry != "aglmcmc" else 3 + ((T - 1) // spec["step_size"] + 2) * 9
+    # (+ 1: the fused summary kernel glabc_summarize that closes every pass)
+    launches_per_pass = 1 + (1 if entry != "aglmcmc" else 3 + ((T - 1) // spec["step_size"] + 2) * 9)
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
