@@ -23,10 +23,18 @@ cudaError_t launch_flow(const FlowDev& W, bool sample, const float* in, int64_t 
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    const int64_t chunks = (n + kFlowTilesPerCta * kFlowTile - 1) / (kFlowTilesPerCta * kFlowTile);
+    // tiles per chunk: at most what the shared-memory state holds, sized so that the chunks divide evenly over the SMs (an
+    // even number: one tile per group at least)
+    const int64_t tiles = (n + kFlowTile - 1) / kFlowTile;
+    const int64_t waves = (tiles + int64_t(sm_count) * kFlowTilesPerCta - 1) / (int64_t(sm_count) * kFlowTilesPerCta);
+    int64_t tpc = (tiles + sm_count * waves - 1) / (sm_count * waves);   // every SM gets `waves` chunks of (almost) equal size
+    tpc = (tpc + 1) / 2 * 2;
+    if (tpc < 2) tpc = 2;
+    if (tpc > kFlowTilesPerCta) tpc = kFlowTilesPerCta;
+    const int64_t chunks = (tiles + tpc - 1) / tpc;
     const unsigned grid = static_cast<unsigned>(chunks < sm_count ? chunks : sm_count);  // persistent: one CTA per SM
-    if (sample) k_flow<true><<<grid, kFlowThreads, kFlowSmemBytes, st>>>(W, in, n, out_theta, out_lq);
-    else k_flow<false><<<grid, kFlowThreads, kFlowSmemBytes, st>>>(W, in, n, out_theta, out_lq);
+    if (sample) k_flow<true><<<grid, kFlowThreads, kFlowSmemBytes, st>>>(W, in, n, out_theta, out_lq, static_cast<int>(tpc));
+    else k_flow<false><<<grid, kFlowThreads, kFlowSmemBytes, st>>>(W, in, n, out_theta, out_lq, static_cast<int>(tpc));
     return cudaGetLastError();
 }
 
