@@ -1490,6 +1490,39 @@ int glabc_esjd(glabc_ctx* ctx, const float* trace, int32_t layout, int64_t rows,
     return GLABC_OK;
 }
 
+int glabc_expand_events(const float* events, int64_t chains, int64_t cap, int32_t dim, int64_t row_base, int64_t row_end, float* trace,
+                        int64_t trace_rows, int32_t n_threads)
+{
+    if (!events || !trace || chains < 0 || cap < 2 || dim < 1 || dim > GLABC_MAX_DIM || row_end < row_base || row_end - row_base >= trace_rows)
+        return GLABC_ERR_INVALID;
+    for (int64_t c = 0; c < chains; ++c) {   // validate before writing anything: counts within capacity, rows ascending and in range
+        const float* ev = events + c * cap * (1 + dim);
+        uint32_t m;
+        memcpy(&m, ev, sizeof(m));
+        if (m > static_cast<uint32_t>(cap - 1)) return GLABC_ERR_INVALID;
+        int64_t prev = row_base - 1;
+        for (uint32_t k = 1; k <= m; ++k) {
+            uint32_t r;
+            memcpy(&r, ev + static_cast<int64_t>(k) * (1 + dim), sizeof(r));
+            if (static_cast<int64_t>(r) <= prev || static_cast<int64_t>(r) > row_end) return GLABC_ERR_INVALID;
+            prev = r;
+        }
+    }
+    const bool nt512 = (dim == 1 || dim == 2 || dim == 4) && __builtin_cpu_supports("avx512f");
+    int nt = n_threads > 0 ? n_threads : static_cast<int>(std::thread::hardware_concurrency());
+    if (nt < 1) nt = 1;
+    if (nt > 64) nt = 64;
+    if (nt > chains) nt = chains > 0 ? static_cast<int>(chains) : 1;
+    std::vector<std::thread> workers;
+    for (int t = 0; t < nt; ++t)
+        workers.emplace_back([=]() {
+            for (int64_t c = t; c < chains; c += nt) expand_chain(events + c * cap * (1 + dim), cap, dim, row_base, row_end, trace + c * trace_rows * dim, nt512);
+            _mm_sfence();
+        });
+    for (auto& w : workers) w.join();
+    return GLABC_OK;
+}
+
 int glabc_summarize(glabc_ctx* ctx, const float* stats, int64_t chains, int32_t dim, double* out, void* stream)
 {
     if (!ctx) return GLABC_ERR_INVALID;

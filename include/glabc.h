@@ -433,6 +433,14 @@ GLABC_API int glabc_run_mala_host(glabc_ctx* ctx, const glabc_run_t* run, int64_
 GLABC_API int glabc_esjd(glabc_ctx* ctx, const float* trace, int32_t layout, int64_t rows, int64_t chains,
                int32_t dim, float* out, void* stream);
 
+/* HOST-side expansion of a GLABC_TRACE_EVENTS buffer (already copied to host memory) into dense chain-major rows:
+ * trace[c][r - row_base][dim] for r = first recorded row .. row_end, chain c's events at events[c][cap][1 + dim].  What the
+ * host-buffer entry points do internally (full-line non-temporal stores with AVX-512, n_threads workers, 0 = all cores); a
+ * caller that keeps GLABC_TRACE_EVENTS traces on the device can expand them later with this.  No GPU needed.
+ * GLABC_ERR_INVALID (nothing written) if a count exceeds cap - 1 or rows are not ascending within [row_base, row_end].   */
+GLABC_API int glabc_expand_events(const float* events, int64_t chains, int64_t cap, int32_t dim, int64_t row_base, int64_t row_end,
+                                  float* trace, int64_t trace_rows, int32_t n_threads);
+
 /* Additive summary of a shard's per-chain statistics (stats [chains][GLABC_NSTATS(dim)], as the samplers fill them) in one
  * launch: out[6 + 2 dim] float64 += {chains, steps, global steps, accepted local, accepted global, sum over chains of
  * esjd (ESJD.py:21-24 from the Gram accumulators), sum theta[dim], sum theta^2[dim]} — the vector the ranks all-reduce.

@@ -79,3 +79,35 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"import\s+oracle|from\s+oracle|liboracle|oracle[/.]\w", text), f"{f} uses the oracle"
+
+
+def test_expand_events_on_the_host():
+    """glabc_expand_events (no GPU): a GLABC_TRACE_EVENTS buffer expanded into dense chain-major rows equals the numpy expansion,
+    for every row width, ragged run lengths (runs shorter than a cache line included), and bad buffers are refused untouched"""
+    import numpy as np
+    lib = abi.load()
+    rng = np.random.default_rng(5)
+    for d in (1, 2, 3, 4):
+        chains, cap, T = 37, 64, 777
+        ev = np.zeros((chains, cap, 1 + d), np.float32)
+        want = np.zeros((chains, T, d), np.float32)
+        for c in range(chains):
+            m = int(rng.integers(1, cap - 1))
+            rows = np.sort(rng.choice(np.arange(1, T), size=m - 1, replace=False)) if m > 1 else np.zeros(0, np.int64)
+            rows = np.concatenate([[0], rows]).astype(np.uint32)
+            vals = rng.standard_normal((m, d)).astype(np.float32)
+            ev[c, 0, 0] = np.array([m], np.uint32).view(np.float32)[0]
+            ev[c, 1:m + 1, 0] = rows.view(np.float32)
+            ev[c, 1:m + 1, 1:] = vals
+            ends = np.concatenate([rows[1:], [T]])
+            for k in range(m):
+                want[c, rows[k]:ends[k]] = vals[k]
+        for threads in (1, 5):
+            got = np.full((chains, T, d), np.nan, np.float32)
+            st = lib.glabc_expand_events(ev.ctypes.data, chains, cap, d, 0, T - 1, got.ctypes.data, T, threads)
+            assert st == abi.OK and np.array_equal(got, want), (d, threads)
+        bad = ev.copy()
+        bad[3, 0, 0] = np.array([cap], np.uint32).view(np.float32)[0]          # more moves than the capacity
+        got = np.full((chains, T, d), np.nan, np.float32)
+        assert lib.glabc_expand_events(bad.ctypes.data, chains, cap, d, 0, T - 1, got.ctypes.data, T, 2) == abi.ERR_INVALID
+        assert np.isnan(got).all()
