@@ -14,7 +14,7 @@ AUX_SLOTS = 8
 AUX_LOGW, AUX_LOCAL, AUX_WIDE, AUX_LW_WIDE, AUX_HAVE_GRAD = 0, 1, 2, 3, 4
 DEBUG_SLOTS = 4 + MAX_K
 STATE64_SLOTS, S64_THETA, S64_Y, S64_GRAD, S64_LOGW = 16, 0, 4, 8, 12
-DEBUG64_SLOTS = 20
+DEBUG64_SLOTS = 36
 MAX_NUM_GRAD = 4096
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = range(5)

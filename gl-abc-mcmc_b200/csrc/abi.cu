@@ -537,6 +537,12 @@ static int run_host(glabc_ctx* ctx, SamplerKind kind, const glabc_run_t* run, in
     if (!ctx->has_model) return fail(ctx, GLABC_ERR_INVALID, "no model bound: call glabc_model_set first");
     if (!run) return fail(ctx, GLABC_ERR_INVALID, "null run description");
     if (run->rng_mode != GLABC_RNG_NATIVE) return fail(ctx, GLABC_ERR_INVALID, "host entry points run the native RNG only");
+    // GLABC_TRACE_EVENTS is a device-buffer layout (glabc.h): the scratch below is sized for dense rows, an event writer
+    // would run past it.  The event TRANSPORT of the host entries is chosen internally (run_host_hybrid), never by the caller.
+    if (run->trace_layout != GLABC_TRACE_NONE && run->trace_layout != GLABC_TRACE_TIME_MAJOR &&
+        run->trace_layout != GLABC_TRACE_CHAIN_MAJOR)
+        return fail(ctx, GLABC_ERR_UNSUPPORTED, "host entry points deliver GLABC_TRACE_NONE / TIME_MAJOR / CHAIN_MAJOR traces "
+                                                "(trace_layout %d is a device-buffer layout)", run->trace_layout);
     if (run->n_chains <= 0 || run->n_steps < 0) return run->n_chains == 0 ? GLABC_OK : fail(ctx, GLABC_ERR_INVALID, "bad sizes");
     if (!run->theta || !run->y) return fail(ctx, GLABC_ERR_INVALID, "theta / y state pointers are required");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));

@@ -146,7 +146,7 @@ struct GradSource {
 template <int D, int FAMILY, bool STRICT, bool REPLAY>
 __device__ __forceinline__ void mala_gradient(const MalaConsts& K, const RoundKeys& rk, const Stream& stream,
                                               const GradSource& src, const double (&theta_in)[D], int lane,
-                                              double (&grad)[D])
+                                              double (&grad)[D], double* gstat)
 {
     constexpr int kDpb = D == 3 ? 1 : 4 / D;  // draws per Philox block
     const int num = K.num_grad;
@@ -225,8 +225,14 @@ __device__ __forceinline__ void mala_gradient(const MalaConsts& K, const RoundKe
             s2m = warp_sum_f64(s2m);
             const double n = static_cast<double>(num);
             const double mup = static_cast<double>(cpf) + s1p / n, mum = static_cast<double>(cmf) + s1m / n;  // :86-87
-            const double vp = (s2p - s1p * s1p / n) / (n - 1.0) + K.eps2;                                    // :88-89 (+ eps^2)
-            const double vm = (s2m - s1m * s1m / n) / (n - 1.0) + K.eps2;
+            const double sp = (s2p - s1p * s1p / n) / (n - 1.0), sm = (s2m - s1m * s1m / n) / (n - 1.0);     // :88-89
+            if (gstat != nullptr && k < 4) {   // replay debug record (glabc.h: debug64 slots 20..35)
+                gstat[k] = mup;
+                gstat[4 + k] = mum;
+                gstat[8 + k] = sp;
+                gstat[12 + k] = sm;
+            }
+            const double vp = sp + K.eps2, vm = sm + K.eps2;
             const double lpp = -0.5 * log(vp) - 0.5 * (mup * mup) / vp;  // :90-93
             const double lpm = -0.5 * log(vm) - 0.5 * (mum * mum) / vm;
             gk = (lpp - lpm) / (2 * 1e-1) + static_cast<double>(gprior);  // :94-95
@@ -743,7 +749,9 @@ __global__ void __launch_bounds__(128, 6) k_mala(const __grid_constant__ MalaCon
                 double gout[D];
 #pragma unroll
                 for (int k = 0; k < D; ++k) gout[k] = 0.0;
-                mala_gradient<D, FAMILY, STRICT, REPLAY>(K, R.rk, stream, gs, tgt, lane, gout);
+                double* gstat = nullptr;
+                if constexpr (REPLAY) gstat = pass == 1 ? dbg + 20 : nullptr;
+                mala_gradient<D, FAMILY, STRICT, REPLAY>(K, R.rk, stream, gs, tgt, lane, gout, gstat);
 #pragma unroll
                 for (int k = 0; k < D; ++k) {
                     if (pass == 0) grad[k] = gout[k];

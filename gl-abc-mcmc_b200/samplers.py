@@ -19,8 +19,10 @@ _LAYOUT = {"chain": _abi.TRACE_CHAIN_MAJOR, "time": _abi.TRACE_TIME_MAJOR, "none
 
 
 def default_seed():
-    """torch.manual_seed(s) in the user script makes runs reproducible, as it does for the reference."""
-    return int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+    """One draw from torch's global CPU generator: reproducible under torch.manual_seed(s) in the user script, as the
+    reference is, and ADVANCING between calls, as the reference's draws from the global generator do — two successive
+    sampler calls without seed= are independent runs, not replays of the same Philox streams."""
+    return int(torch.randint(0, 2 ** 62, (1,)).item())
 
 
 def initial_state(eng, model_pod, Initial_theta, Initial_y, num_chains, seed):

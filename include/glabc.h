@@ -218,10 +218,11 @@ typedef struct {
 #define GLABC_TAPE_MALA_SLOTS(d, yd, K, num) (2 + (K) * ((d) + (yd)) + (d) * (num) * (yd))
 /* run_mala debug64 slots (float64): 0 flags (bit0 global, bit1 state changed, bits 8.. resample index + 1,
  *   bit16 float64 weights); MALA local move: 1 log_acc, 2+i theta'[i], 6+i y'[i], 10+i grad'[i] (i < 4),
- *   14 log prior', 15 log kernel', 16 log q(theta|theta'), 17 log q(theta'|theta);
+ *   14 log prior', 15 log kernel', 16 log q(theta|theta'), 17 log q(theta'|theta); the float64 statistics inside the
+ *   gradient at theta' (GLMALA.py:86-89): 20+i mu_plus[i], 24+i mu_minus[i], 28+i Sigma_plus[i], 32+i Sigma_minus[i];
  *   iSIR global move: 1 log-weight of the current state, 2 sum of weights, 3 normalised weight of the
  *   current state, 4+j log-weight of candidate j                                                   */
-#define GLABC_DEBUG64_SLOTS 20
+#define GLABC_DEBUG64_SLOTS 36
 #define GLABC_MAX_NUM_GRAD 4096
 
 /* ---- AGLMCMC (AGLMCMC.py:44-288) -------------------------------------------------------------

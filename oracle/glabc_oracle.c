@@ -647,8 +647,8 @@ static void native_grad_normals(uint64_t seed, uint64_t chain, uint32_t step, ui
  * Mean / unbiased variance of the discrepancies in float64 (:70-72,86-89) — accumulated in one pass
  * around the noise-free discrepancy (the kernels use the same formulation; torch's reduction order
  * differs at the 1e-16 level).                                                                     */
-static void mala_gradient(const glabc_model_t* m, const double* theta_in, int num, const float* eps, double* grad)
-{
+static void mala_gradient(const glabc_model_t* m, const double* theta_in, int num, const float* eps, double* grad, double* gstat)
+{   /* gstat (optional): mu_plus[4], mu_minus[4], Sigma_plus[4], Sigma_minus[4] — torch.mean / torch.var of :86-89 */
     const int d = m->theta_dim, yd = m->y_dim;
     float th[GLABC_MAX_DIM], zero[GLABC_MAX_DIM] = {0};
     for (int i = 0; i < d; ++i) th[i] = (float)theta_in[i]; /* theta.float(), :60 */
@@ -672,6 +672,7 @@ static void mala_gradient(const glabc_model_t* m, const double* theta_in, int nu
             const double n = (double)num;
             const double mu = c + s1 / n;
             const double var = (s2 - s1 * s1 / n) / (n - 1.0);
+            if (gstat && k < 4) { gstat[sgn * 4 + k] = mu; gstat[8 + sgn * 4 + k] = var; }
             logp[sgn] = -0.5 * log(var + eps2) - 0.5 * (mu * mu) / (var + eps2); /* :90-93 */
         }
         float ta[GLABC_MAX_DIM], tb[GLABC_MAX_DIM];
@@ -688,7 +689,7 @@ static void mala_gradient(const glabc_model_t* m, const double* theta_in, int nu
 /* the gradient alone (unit-tested against the reference's recorded gradients) */
 ORACLE_EXPORT void oracle_mala_gradient(const glabc_model_t* m, const double* theta, int num, const float* eps, double* grad)
 {
-    mala_gradient(m, theta, num, eps, grad);
+    mala_gradient(m, theta, num, eps, grad, NULL);
 }
 
 typedef struct { const glabc_model_t* m; const glabc_dist_t* ip; const glabc_run_t* r; } mala_job;
@@ -824,7 +825,7 @@ static void run_mala_range(void* vctx, int64_t c_begin, int64_t c_end)
                 if (!have_grad) { /* :183-184 */
                     if (t) for (size_t q = 0; q < ng; ++q) geps[q] = r->tape_grad0[q * C + c];
                     else native_grad_normals(r->seed, gid, (uint32_t)i, SLOT_GRAD0, d, yd, num, geps);
-                    mala_gradient(m, theta, num, geps, grad);
+                    mala_gradient(m, theta, num, geps, grad, NULL);
                     have_grad = 1;
                 }
                 if (t) {
@@ -846,7 +847,7 @@ static void run_mala_range(void* vctx, int64_t c_begin, int64_t c_end)
                     const double a = wide ? (double)zt + theta[k] : (double)(zt + (float)theta[k]);
                     theta_p[k] = a + grad[k] * (tau * tau) / 2.0; /* :43 */
                 }
-                mala_gradient(m, theta_p, num, geps, grad_p); /* :187 */
+                mala_gradient(m, theta_p, num, geps, grad_p, dbg + 20); /* :187 */
                 for (int k = 0; k < yd; ++k) { /* :188-189: |theta'| (float64) + likelihood.sample (float32) */
                     const float noise = m->noise_loc[k] + m->noise_scale[k] * eps_s[k];
                     const double mean = m->family == GLABC_MODEL_ABS_NORMAL ? fabs(theta_p[k]) : theta_p[k];

@@ -19,6 +19,7 @@ Nothing here is imported by the test-suite at run time; the .npz files are commi
 import contextlib
 import io
 import os
+import random
 import sys
 import types
 
@@ -43,9 +44,12 @@ def import_reference():
 class Tape:
     """Records every draw of the global RNG entry points, in call order."""
 
-    def __init__(self):
+    def __init__(self, secret_seed=0):
         self.events = []  # (kind, np.ndarray)
         self._orig = {}
+        # secrets.randbelow reads OS entropy (GLMALA.py:74): replaced by a private seeded generator so that a
+        # recording regenerates bit-identically; it does not touch the torch / numpy global generators
+        self._secret = random.Random(secret_seed)
 
     def __enter__(self):
         import secrets
@@ -69,7 +73,7 @@ class Tape:
             return out
 
         def randbelow(n):
-            out = tape._orig["randbelow"](n)
+            out = tape._secret.randrange(n)
             tape.events.append(("SEED", np.asarray(out, dtype=np.int64)))
             return out
 
@@ -485,14 +489,17 @@ def golden_mala(cases, out_path):
         # per step (float64): 0 flags, 1 log_acc | lw_old, 2..3 theta' , 4..5 y', 6..7 grad', 8 prior', 9 kernel',
         # 10 lq_rev, 11 lq_fwd | (global) 2 S, 3 w0, 4.. lw_j
         rec = np.zeros((T - 1, 12 + K, C), np.float64)
+        # the float64 statistics inside the gradient at theta' (GLMALA.py:86-89), per local step:
+        # mu_plus[d], mu_minus[d], Sigma_plus[d], Sigma_minus[d] — the conditioning of grad' is stated from these
+        grec = np.zeros((T - 1, 4 * d, C), np.float64)
         grad0 = np.zeros((2, C), np.float64)
         wide_at = np.full(C, -1, np.int64)
         # the chain's full carried state BEFORE step s (row s) / after the last step (row T-1), float64:
         # theta[2], y[2], grad[2], lw_old, flag bits (local | wide<<1 | lw_wide<<2 | have_grad<<3)
         state = np.zeros((T, 8, C), np.float64)
         for c in range(C):
-            torch.manual_seed(9000 + 1000 * ci + c)
-            np.random.seed(9000 + 1000 * ci + c)
+            torch.manual_seed(case.get("seed_base", 9000) + 1000 * case.get("case_id", ci) + c)
+            np.random.seed(case.get("seed_base", 9000) + 1000 * case.get("case_id", ci) + c)
             theta0 = torch.tensor(case["theta0"])
             y0 = model.generate_samples(theta0)
             log = []
@@ -502,9 +509,27 @@ def golden_mala(cases, out_path):
 
             def grad_fn(*a, **k):
                 n0 = len(log)
-                out = orig["g"](*a, **k)
+                stats = []
+                t_mean, t_var = torch.mean, torch.var
+
+                def mean(*aa, **kk):
+                    out = t_mean(*aa, **kk)
+                    stats.append(out.detach().numpy().reshape(-1).copy())
+                    return out
+
+                def var(*aa, **kk):
+                    out = t_var(*aa, **kk)
+                    stats.append(out.detach().numpy().reshape(-1).copy())
+                    return out
+
+                torch.mean, torch.var = mean, var
+                try:
+                    out = orig["g"](*a, **k)
+                finally:
+                    torch.mean, torch.var = t_mean, t_var
                 del log[n0:]          # the 2*d*num plugin calls inside the gradient are summarised by its output
-                log.append(("fn", "grad", out.detach().numpy().copy()))
+                assert len(stats) == 4 and all(v.dtype == np.float64 for v in stats)
+                log.append(("fn", "grad", out.detach().numpy().copy(), np.concatenate(stats)))
                 return out
 
             def fwd_fn(*a, **k):
@@ -519,7 +544,7 @@ def golden_mala(cases, out_path):
 
             mod.numberical_gradient_logABC, mod.Local_proposal_forward, mod.log_proposal = grad_fn, fwd_fn, lp_fn
             try:
-                with Tape() as tape, quiet():
+                with Tape(secret_seed=case.get("seed_base", 9000) + 1000 * case.get("case_id", ci) + c) as tape, quiet():
                     chain = mod.GLMALA(pm, T, theta0, y0, tau, num, None, gf, pip, K)
             finally:
                 mod.numberical_gradient_logABC, mod.Local_proposal_forward, mod.log_proposal = orig["g"], orig["f"], orig["l"]
@@ -620,6 +645,7 @@ def golden_mala(cases, out_path):
                                      ("model", "calculate_log_kernel"), ("fn", "logprop"),
                                      ("model", "prior_log_prob"), ("model", "calculate_log_kernel")], names
                     (th_p, lq_fwd), g_p, y_p, pr_p, k_p, lq_rev, pr_o, k_o = [v[2] for v in log[li:li + 8]]
+                    grec[s, :, c] = log[li + 1][3]
                     li += 8
                     assert th_p.dtype == np.float64 and y_p.dtype == np.float64 and g_p.dtype == np.float64
                     log_acc = pr_p[0] + k_p[0] + lq_rev[0] - pr_o[0] - k_o[0] - lq_fwd[0]
@@ -638,7 +664,7 @@ def golden_mala(cases, out_path):
             assert np.array_equal(state[:, 0:2, c].astype(np.float32), trace[:, c])
             assert ei == len(ev) and li == len(log), (ei, len(ev), li, len(log))
         blob = dict(tape32=tape32, tape64=tape64, tape_grad0=tape_grad0, trace=trace, theta0=theta0s, y0=y0s, rec=rec,
-                    state=state, grad0=grad0, wide_at=wide_at, gf=np.float64(gf), T=np.int64(T), K=np.int64(K), num_grad=np.int64(num),
+                    grec=grec, state=state, grad0=grad0, wide_at=wide_at, gf=np.float64(gf), T=np.int64(T), K=np.int64(K), num_grad=np.int64(num),
                     tau=np.float64(tau))
         blob.update(model_params(model))
         blob.update(dist_params(ip, "ip"))
@@ -919,12 +945,14 @@ def main():
     only = sys.argv[1:]
     mbase = dict(chains=4, epsilon=0.05, theta0=[0.0, 0.0], ip_loc=[0.0, 0.0], ip_log_scale=[0.0, 0.0])
     mcases = [
-        dict(mbase, chains=6, gf=0.8, K=5, tau=0.3, num_grad=100, T=400),       # README.md:128 / config 3
+        dict(mbase, chains=4, gf=0.8, K=5, tau=0.3, num_grad=100, T=400),       # README.md:128 / config 3
         dict(mbase, gf=0.3, K=3, tau=0.2, num_grad=33, T=500),                  # local-heavy: float64 state early
         dict(mbase, gf=0.0, K=2, tau=0.25, num_grad=8, T=400),                  # never global
         dict(mbase, gf=0.6, K=8, tau=0.4, num_grad=64, T=400, epsilon=0.2, theta0=[1.2, -1.4], ip_loc=[0.5, -0.25],
              ip_log_scale=[0.4, 0.2]),
     ]
+    # three independent recordings of every case (own torch / numpy / secrets seeds): cases 0-3, 4-7, 8-11
+    mcases = [dict(case, case_id=i, seed_base=base) for base in (9000, 19000, 29000) for i, case in enumerate(mcases)]
     if not only or "mala" in only:
         golden_mala(mcases, os.path.join(HERE, "glmala.npz"))
     abase = dict(chains=4, epsilon=0.05, theta0=[0.0, 0.0], lp_loc=[0.0, 0.0], lp_sigma=[0.35, 0.35],

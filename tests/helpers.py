@@ -85,41 +85,94 @@ def mala_teacher_forced(case):
     tape64 = np.ascontiguousarray(case["tape64"].reshape(1, n))
     grad0 = np.ascontiguousarray(np.broadcast_to(case["tape_grad0"][:, None, :], (case["tape_grad0"].shape[0], S, Cn)).reshape(-1, n))
     rec = np.ascontiguousarray(np.moveaxis(case["rec"], 1, 0).reshape(case["rec"].shape[1], n))  # [slots, S*C]
-    return dict(n=n, theta=theta64.astype(np.float32), y=y64.astype(np.float32), aux=aux, state64=s64, tape32=tape32,
+    grec = np.ascontiguousarray(np.moveaxis(case["grec"], 1, 0).reshape(case["grec"].shape[1], n))
+    eps2 = float(case["epsilon"]) ** 2 if "epsilon" in case else float(case["eps_scale"]) ** 2
+    kern_c = -0.5 * np.log(2 * np.pi) - float(case["eps_log_scale"])
+    return dict(n=n, grec=grec, eps2=eps2, kern_c=kern_c, theta=theta64.astype(np.float32), y=y64.astype(np.float32), aux=aux, state64=s64, tape32=tape32,
                 tape64=tape64, tape_grad0=grad0, rec=rec, K=K, num_grad=num, tau=float(case["tau"]), gf=float(case["gf"]))
 
 
-def check_mala_debug(dbg, rec, K, tol=1e-5):
-    """dbg [DEBUG64_SLOTS, n] (kernel / oracle) vs rec [12+K, n] (reference): flags exact, values to `tol`."""
+def mala_grad_parts(mu_p, mu_m, s_p, s_m, eps2):
+    """the likelihood part of numberical_gradient_logABC from its float64 statistics (GLMALA.py:90-94)"""
+    lp = -0.5 * np.log(s_p + eps2) - 0.5 * mu_p ** 2 / (s_p + eps2)
+    lm = -0.5 * np.log(s_m + eps2) - 0.5 * mu_m ** 2 / (s_m + eps2)
+    return (lp - lm) / (2 * 1e-1)
+
+
+def mala_grad_bound(mu, sig, eps2, n, u=2.0 ** -23):
+    """First-order bound on |d logp| (GLMALA.py:90-93) when each of the n float32 discrepancies d_j moves by at most one
+    unit in the last place, |delta_j| <= u d_j.  Why one ulp: the reference takes torch.sqrt, which on the CPU build that
+    made the fixtures (MKL VML) returns the float32 BELOW the correctly rounded root for 0.64 % of its inputs
+    (tests/golden/README in DESIGN.md section 2); IEEE sqrt (oracle, kernels) differs from it by exactly that ulp.
+      |d mu| <= u mu,   |d Sigma| <= 2/(n-1) sum |d_j - mu| |delta_j| <= 2 u sqrt(Sigma) sqrt(Sigma + n mu^2 / (n-1))
+      d logp = -(mu / V) d mu + (-1/(2V) + mu^2 / (2 V^2)) d Sigma,   V = Sigma + eps^2"""
+    v = sig + eps2
+    d_mu = u * np.abs(mu)
+    d_sig = 2.0 * u * np.sqrt(sig) * np.sqrt(sig + n * mu ** 2 / (n - 1.0))
+    return np.abs(mu / v) * d_mu + np.abs(-0.5 / v + 0.5 * mu ** 2 / v ** 2) * d_sig
+
+
+def check_mala_debug(dbg, rec, K, tol=1e-5, grec=None, eps2=None, num_grad=None, kern_c=2.08):
+    """dbg [DEBUG64_SLOTS, n] (kernel / oracle) vs rec [12+K, n] (reference): flags exact, values within `tol`
+    RELATIVE with no absolute slack.  Two quantities are not judged by a bare relative error, with the reason:
+      * log K(y') crosses zero (log K(0) = +2.08, decreasing in the distance), so its error is taken relative to the
+        larger of its two terms, |c| and (dis/eps)^2 / 2, not to their difference;
+      * grad' is a finite difference of synthetic log-likelihoods divided by 0.2 (GLMALA.py:94): it is pinned through
+        its ingredients — mu+-, Sigma+- (the reference's own torch.mean / torch.var outputs, `grec`) within `tol` relative,
+        the combination step by recomputing it from the implementation's own statistics, and the value itself within
+        `tol` relative plus the first-order effect of a one-ulp perturbation of the float32 discrepancies
+        (mala_grad_bound: the reference's sqrt is not correctly rounded)."""
     fl_o, fl_r = dbg[0].astype(np.int64), rec[0].astype(np.int64)
     assert np.array_equal(fl_o, fl_r), f"{(fl_o != fl_r).sum()} decisions differ"
     loc = (fl_r & 1) == 0
     worst = {}
 
-    def cmp(name, a, b, m, atol=0.0):
+    def cmp(name, a, b, m, scale=None, slack=None, rtol=tol):
         a, b = a[m], b[m]
         if a.size:
-            err = np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
-            err = np.where(np.abs(a - b) <= atol, 0.0, err)
+            den = np.maximum(np.abs(b), 1e-300) if scale is None else np.maximum(scale[m], 1e-300)
+            excess = np.abs(a - b) - (0.0 if slack is None else slack[m])
+            err = np.maximum(excess, 0.0) / den
             worst[name] = float(err.max())
-            assert err.max() <= tol, (name, float(err.max()))
+            assert err.max() <= rtol, (name, float(err.max()))
 
-    cmp("log_acc", dbg[1], rec[1], loc)
+    # log_acc = prior' + kern' + lq_rev - prior - kern - lq_fwd (GLMALA.py:190-193): relative to its largest term
+    acc_scale = np.maximum.reduce([np.abs(rec[1]), np.abs(rec[8]), np.abs(rec[9]), np.abs(rec[10]), np.abs(rec[11])])
+    cmp("log_acc", dbg[1], rec[1], loc, scale=acc_scale)
     for k in range(2):
         cmp(f"theta'{k}", dbg[2 + k], rec[2 + k], loc)
         cmp(f"y'{k}", dbg[6 + k], rec[4 + k], loc)
-        cmp(f"grad'{k}", dbg[10 + k], rec[6 + k], loc, atol=2e-5)   # differences of O(100) log-likelihoods / 0.2
     cmp("prior'", dbg[14], rec[8], loc)
-    cmp("kern'", dbg[15], rec[9], loc)
+    cmp("kern'", dbg[15], rec[9], loc, scale=np.maximum(np.abs(rec[9]), abs(kern_c)))   # kern_c = -(1/2) log 2 pi - log eps
     cmp("lq_rev", dbg[16], rec[10], loc)
     cmp("lq_fwd", dbg[17], rec[11], loc)
+    if grec is not None:
+        d = 2
+        mu_p, mu_m, s_p, s_m = grec[0:d], grec[d:2 * d], grec[2 * d:3 * d], grec[3 * d:4 * d]
+        for k in range(d):
+            cmp(f"mu+{k}", dbg[20 + k], mu_p[k], loc)
+            cmp(f"mu-{k}", dbg[24 + k], mu_m[k], loc)
+            cmp(f"Sigma+{k}", dbg[28 + k], s_p[k], loc)
+            cmp(f"Sigma-{k}", dbg[32 + k], s_m[k], loc)
+            like_ref = mala_grad_parts(mu_p[k], mu_m[k], s_p[k], s_m[k], eps2)
+            gprior = rec[6 + k] - like_ref                       # the float32 finite-difference prior gradient (GLMALA.py:84-85)
+            like_own = mala_grad_parts(dbg[20 + k], dbg[24 + k], dbg[28 + k], dbg[32 + k], eps2)
+            # the combination step, from the implementation's own statistics: exact up to float64 rounding
+            cmp(f"grad'{k} (own statistics)", dbg[10 + k], like_own + gprior, loc, rtol=1e-9,
+                scale=np.maximum(np.abs(like_own), np.abs(gprior)))
+            bound = (mala_grad_bound(mu_p[k], s_p[k], eps2, num_grad) + mala_grad_bound(mu_m[k], s_m[k], eps2, num_grad)) / 0.2
+            cmp(f"grad'{k}", dbg[10 + k], rec[6 + k], loc, slack=bound)
+            worst[f"grad'{k} abs / bound"] = float((np.abs(dbg[10 + k] - rec[6 + k])[loc] / bound[loc]).max()) if loc.any() else 0.0
+    else:
+        for k in range(2):
+            cmp(f"grad'{k}", dbg[10 + k], rec[6 + k], loc, scale=np.maximum(np.abs(rec[6 + k]), 1.0) * 100)
     g = ~loc
-    cmp("lw_old", dbg[1], rec[1], g & np.isfinite(rec[1]), atol=3e-6)
+    cmp("lw_old", dbg[1], rec[1], g & np.isfinite(rec[1]))
     pos = g & (rec[2] > 1e-300)
-    cmp("S", dbg[2], rec[2], pos, atol=1e-44)
-    cmp("w0", dbg[3], rec[3], pos, atol=1e-44)
+    cmp("S", dbg[2], rec[2], pos)
+    cmp("w0", dbg[3], rec[3], pos)
     for j in range(K):
-        cmp(f"lw{j}", dbg[4 + j], rec[4 + j], g & np.isfinite(rec[4 + j]), atol=3e-6)
+        cmp(f"lw{j}", dbg[4 + j], rec[4 + j], g & np.isfinite(rec[4 + j]))
     return worst
 
 

