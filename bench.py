@@ -57,6 +57,9 @@ def parse():
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-extra", action="store_true", help="skip the short device-resident timings of the other kernels")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
+    p.add_argument("--no-ref-python", action="store_true", help="skip timing the unmodified reference package (baseline/_ref)")
+    p.add_argument("--ref-python-its", type=int, default=10001, help="iterations per reference chain (one chain per host core)")
+    p.add_argument("--no-other-configs", action="store_true", help="skip BASELINE configs 3-5 / strong scaling (other_configs)")
     return p.parse_args()
 
 
@@ -192,10 +195,15 @@ def bench_reference(a, rank):
     line = {"impl": "reference", "metric": "abc_mcmc_chain_steps_per_sec", "value": value, "unit": "chain-steps/s",
             "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(a),
+            "config": workload_config(a, cpu=dict(chains_per_step=c, transitions=t, threads=port.cores)),
             "cpu_baseline": {"value": value, "unit": "chain-steps/s", "cores": port.cores, "kind": "port", "sample": sample,
                              "esjd": {"mean_per_chain": port.mean_esjd, "aggregate_esjd_per_sec": port.mean_esjd * value}},
             "e2e": {"value": value, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if a.sampler in ("global", "glmcmc") and not a.no_ref_python:
+        # the reference's own Python (unmodified, baseline/_ref), beside its C port: ~1e4 chain-steps/s on 8 cores
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        import ref_python
+        line["cpu_baseline"]["reference_python"] = ref_python.measure(a.ref_python_its, sampler=a.sampler)
     emit(line)
 
 
@@ -544,14 +552,209 @@ def other_kernels(eng, model, lp, gp):
     return out
 
 
-def workload_config(a):
+def other_configs(a, eng, model, lp, gp, rank, world, info, sm_max_mhz, peaks):
+    """BASELINE configs 3-5 and the strong-scaling form of config 2, at THIS world size (every rank takes part; chains are
+    sharded by rank with Philox keyed by the global chain id).  Short runs: CUDA events on the launching stream, barrier on both
+    sides, max over ranks; `value` = chain-steps of all ranks / that time; `kernel_ms` = one launch of the dominant kernel timed
+    alone on rank 0's GPU; `roofline.frac` against the same peaks as the headline line."""
+    import torch
+    import torch.distributed as dist
+    import glabc_b200 as g
+    from glabc_b200 import _abi as abi
+    from glabc_b200 import sweeps
+    from glabc_b200.flows import RealNVP
+    inst_peak = info["sm_count"] * 128 * sm_max_mhz * 1e6
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, reps, warm=1):
+        for _ in range(warm):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1) / reps], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def step_kernel(entry, C, T, gf, K, layout, alg_inst, reps, **extra):
+        """device-resident pass of a fused step kernel: C chains per rank x (T - 1) transitions"""
+        d = 2
+        theta0 = torch.zeros(C, d, device="cuda")
+        y0 = torch.randn(C, d, device="cuda", generator=torch.Generator(device="cuda").manual_seed(99 + rank)) * 0.22360679507255554
+        theta, y = theta0.clone(), y0.clone()
+        stats = torch.zeros(C, abi.nstats(d), device="cuda")
+        aux0 = None
+        if K:
+            aux0 = torch.zeros(C, abi.AUX_SLOTS, device="cuda")
+            aux0[:, abi.AUX_LOCAL] = 1.0
+        aux = None if aux0 is None else aux0.clone()
+        if entry == "mala":
+            extra = dict(extra, state64=torch.zeros(C, abi.STATE64_SLOTS, device="cuda", dtype=torch.float64))
+        trace = None if layout == abi.TRACE_NONE else torch.empty(C, T, d, device="cuda")
+
+        def fn():
+            theta.copy_(theta0)
+            y.copy_(y0)
+            stats.zero_()
+            if aux is not None:
+                aux.copy_(aux0)
+            if "state64" in extra:
+                extra["state64"].zero_()
+            eng.run(entry, theta=theta, y=y, n_steps=T - 1, gf=gf, seed=3, chain_id_base=rank * C, trace_layout=layout,
+                    trace=trace, trace_rows=T, stats=stats, K=K, aux=aux, **extra)
+        ms = timed(fn, reps)
+        rate = float(C) * (T - 1) * world / (ms * 1e-3)
+        frac = rate / world * alg_inst / inst_peak
+        return {"value": rate, "unit": "chain-steps/s", "ms_per_pass": ms, "kernel_ms": ms, "chains_total": C * world, "chains_per_gpu": C,
+                "iterations": T, "roofline": {"bound": "alu-issue", "frac": frac, "alg_inst_per_chain_step": alg_inst,
+                                              "note": "state reset + one fused step kernel per pass; frac = per-GPU rate x algorithmic "
+                                                      "thread-instructions / (SMs x 128 x max clock)"}}
+
+    out = {}
+    # (iv) BASELINE metric's own size: 65,536 chains IN TOTAL (strong scaling), full chain-major trace on the device
+    out["global_strong_65536"] = dict(step_kernel("global", 65536 // world, a.iters, 0.5, 0, abi.TRACE_CHAIN_MAJOR, 186, reps=20),
+                                      scaling="strong", workload="BASELINE configs[1]: GlobalMCMC, 65,536 chains in total, full [C,T,2] trace")
+    # (i) BASELINE configs[2]: 262,144 chains in total
+    out["glmcmc_262144"] = dict(step_kernel("isir", 262144 // world, 10000, 0.9, 5, abi.TRACE_NONE, 703, reps=3), scaling="strong",
+                                workload="BASELINE configs[2]: run_glmcmc iSIR K=5 gf=0.9, 262,144 chains in total x 1e4, statistics only")
+    out["glmala_262144"] = dict(step_kernel("mala", 262144 // world, 1001, 0.8, 5, abi.TRACE_NONE, 5000, reps=2, num_grad=100, tau=0.3),
+                                scaling="strong",
+                                workload="BASELINE configs[2]: run_glmala K=5 gf=0.8 tau=0.3 num_grad=100, 262,144 chains in total x 1e3, statistics only")
+    torch.cuda.empty_cache()
+
+    # (ii) BASELINE configs[3]: GLMCMC-NFs, 1,048,576 chains in total, one shared flow (gradients all-reduced per Adam step)
+    C_nf, T_nf = 1048576 // world, 401
+    z = torch.zeros(2, device="cuda")
+
+    def nf_call():
+        return g.GLMCMC_NF(model, T_nf, z, None, lp, None, 0.5, 200, 5, None, 50, num_chains=C_nf, seed=5, chain_id_base=rank * C_nf,
+                           trace="none", return_stats=True, verbose=False)
+    ms = timed(nf_call, reps=1, warm=1)
+    flow = RealNVP(device="cuda")
+    with torch.no_grad():
+        flow.w3.copy_(0.05 * torch.randn_like(flow.w3))
+    flow.bind(eng)
+    n_s = 1 << 21
+    eps = torch.randn(n_s, 2, device="cuda")
+    th, lq = torch.empty(n_s, 2, device="cuda"), torch.empty(n_s, device="cuda")
+    flow.fused_sample_from(eps, eng, theta=th, log_q=lq)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    k0.record()
+    for _ in range(3):
+        flow.fused_sample_from(eps, eng, theta=th, log_q=lq)
+    k1.record()
+    torch.cuda.synchronize()
+    kms = k0.elapsed_time(k1) / 3
+    tf = n_s * 1.049e6 / (kms * 1e-3) / 1e12
+    peak = float(peaks.get("bf16_tflops", 1654.4))
+    out["glmcmc_nf_1M"] = {"value": float(C_nf) * (T_nf - 1) * world / (ms * 1e-3), "unit": "chain-steps/s", "ms_per_pass": ms,
+                           "kernel_ms": kms, "chains_total": C_nf * world, "chains_per_gpu": C_nf, "iterations": T_nf, "scaling": "strong",
+                           "flow_precision": os.environ.get("GLABC_FLOW_PRECISION", "default"),
+                           "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+                                        "samples_per_sec": n_s / (kms * 1e-3),
+                                        "note": f"k_flow sample, {n_s} samples x 32 coupling blocks, 1.049 MFLOP dense-equivalent per sample"},
+                           "workload": "BASELINE configs[3]: run_glmcmc_nf gf=0.5 K=5 step 200, 50 train steps, 1,048,576 chains in total, "
+                                       "statistics only (one sampler call per pass: block refills + flow training inside)"}
+    del eps, th, lq, flow
+    torch.cuda.empty_cache()
+
+    # (iii) BASELINE configs[4]: AGLMCMC with ONE pooled KernelDensity over 1e5 draws (all-gathered before every fit) ...
+    C_ag, T_ag = 16384, 1001
+
+    def ag_call():
+        return g.AGLMCMC(model, T_ag, z, None, lp, gp, None, 1.0, 200, 5, 0.8, 0.2, num_chains=C_ag, seed=6, chain_id_base=rank * C_ag,
+                         trace="none", return_stats=True, verbose=False, pooled=True, kde_train=a.kde_train)
+    ms = timed(ag_call, reps=1, warm=1)
+    n = a.kde_train
+    X = torch.randn(n, 2, device="cuda")
+    wn, bw = eng.kde_fit(X, torch.rand(n, device="cuda"))
+    q = torch.randn(C_ag * 250, 2, device="cuda")
+    eng.kde_log_prob(X, wn, bw, q)
+    torch.cuda.synchronize()
+    k0.record()
+    eng.kde_log_prob(X, wn, bw, q)
+    k1.record()
+    torch.cuda.synchronize()
+    kms = k0.elapsed_time(k1)
+    pair_rate = float(q.shape[0]) * n / (kms * 1e-3)
+    mufu_peak = info["sm_count"] * 16 * sm_max_mhz * 1e6
+    out["aglmcmc_pooled_kde1e5"] = {"value": float(C_ag) * (T_ag - 1) * world / (ms * 1e-3), "unit": "chain-steps/s", "ms_per_pass": ms,
+                                    "kernel_ms": kms, "chains_total": C_ag * world, "chains_per_gpu": C_ag, "iterations": T_ag,
+                                    "scaling": "weak", "kde_train_total": n,
+                                    "roofline": {"bound": "mufu", "achieved": pair_rate / 1e9, "peak": mufu_peak / 1e9, "unit": "Gex2/s",
+                                                 "frac": pair_rate / mufu_peak,
+                                                 "note": f"k_kde_logprob, {q.shape[0]} queries x {n} pooled points, one ex2 per pair"},
+                                    "workload": "BASELINE configs[4]: run_aglmcmc gf=1 K=5 step 200 alpha 0.8 eps_hat_T 0.2 with one pooled "
+                                                "KernelDensity (1e5 training draws all-gathered per fit), 16,384 chains per GPU"}
+    del X, q
+    torch.cuda.empty_cache()
+    # ... plus the ESJD hyper-parameter sweep of examples/Mixture_hyper.py:23-41 (11 global_frequency values, run_glmcmc K=5),
+    # grid points dealt to the ranks, score table all-reduced
+    barrier()
+    t0 = time.perf_counter()
+    best, table = sweeps.esjd_sweep(lambda gf, **kw: g.GLMCMC(model, 1000, z, None, lp, None, gf, gp, 5, verbose=False, **kw),
+                                    num_chains=8192, seed=7, rank=rank, world=world)
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    out["esjd_sweep_mixture_hyper"] = {"best_global_frequency": best, "seconds": float(dt.item()), "grid_points": int(table.shape[0]),
+                                       "chains_per_point": 8192, "iterations": 1000,
+                                       "esjd_per_sec": [float(v) for v in table[:, 3]], "mean_esjd": [float(v) for v in table[:, 1]],
+                                       "workload": "Mixture_hyper.py:23-41: esjd / seconds-per-iteration of run_glmcmc(1000 its, K=5) over "
+                                                   "global_frequency in {0, 0.1, .., 1}; the reference's 10 seeds become 8,192 chains per point"}
+    return out
+
+
+def replay_parity_bit(eng, abi, entry, gf, T, trace_first64, theta0, y0, seed, chain_base):
+    """the first 64 chains of the TIMED configuration against the oracle.  The kernel re-runs them in
+    the reference's float32 operation order (STRICT) dumping every Philox draw it uses; the oracle replays the dump; and the rows
+    the timed FAST launch wrote for those chains are compared with that replay."""
+    import numpy as np
+    import torch
+    from glabc_b200.models import lower_model, lower_proposal
+    from oracle import oracle
+    model, lp, gp = workload_objects()
+    n = 64
+    th, yy = theta0[:n].clone(), y0[:n].clone()
+    dump = torch.zeros(T - 1, 6, n, device="cuda")
+    got = eng.run(entry, theta=th, y=yy, n_steps=T - 1, gf=gf, seed=seed, chain_id_base=chain_base, arith=abi.ARITH_STRICT,
+                  trace_layout=abi.TRACE_TIME_MAJOR, tape_dump=dump)
+    torch.cuda.synchronize()
+    th_o, y_o = theta0[:n].cpu().numpy().copy(), y0[:n].cpu().numpy().copy()
+    want = oracle.run(entry, lower_model(model), lower_proposal(lp), lower_proposal(gp), theta=th_o, y=y_o, n_steps=T - 1, gf=gf,
+                      rng_mode=abi.RNG_REPLAY, tape32=dump.cpu().numpy())
+    strict_equal = bool(np.array_equal(got.cpu().numpy(), want))
+    fast = trace_first64.cpu().numpy()                       # [64, T, 2] rows of the timed launch
+    same = float((fast.transpose(1, 0, 2) == want).all(-1).mean())
+    return {"chains": n, "transitions": T - 1, "strict_kernel_equals_oracle_bitwise": strict_equal, "timed_fast_rows_equal_oracle": same,
+            "note": "oracle = C restatement of GlobalMCMC.py:37-68 pinned by tests/golden; draws = the kernel's own Philox stream"}
+
+
+def workload_config(a, cpu=None):
     spec = SAMPLERS[a.sampler]
-    return {"workload": spec["workload"], "chains_per_gpu": a.chains,
-            "iterations": a.iters, "theta_dim": 2, "epsilon": 0.05, "global_frequency": spec["gf"],
-            "local_sigma": 0.35, "global_proposal": "N(0,I)", "isir_candidates": spec["K"], "trace": {"chain": "full float32 [C,T,2]",
-            "time": "full float32 [T,C,2]", "none": "statistics only"}[a.layout], "rng": "philox4x32-10 native",
-            "arith": "fast", "l2": "no re-read inputs; 5.2 GB trace written per step >> 126 MB L2",
-            "parallelism": f"chains sharded over {a.gpus} GPU(s), no data-path collective"}
+    cfg = {"workload": spec["workload"], "chains_per_gpu": a.chains,
+           "iterations": a.iters, "theta_dim": 2, "epsilon": 0.05, "global_frequency": spec["gf"],
+           "local_sigma": 0.35, "global_proposal": "N(0,I)", "isir_candidates": spec["K"], "trace": {"chain": "full float32 [C,T,2]",
+           "time": "full float32 [T,C,2]", "none": "statistics only"}[a.layout], "rng": "philox4x32-10 native"}
+    if cpu is None:
+        cfg.update({"arith": "fast", "l2": "no re-read inputs; 5.2 GB trace written per step >> 126 MB L2",
+                    "parallelism": f"chains sharded over {a.gpus} GPU(s), no data-path collective"})
+    else:   # the CPU arm: the oracle port in the reference's float32 operation order, a bounded sample of the workload per step
+        cfg.update({"arith": "reference float32 order (C port of GlobalMCMC.py:37-68 / GLMCMC.py:58-104)",
+                    "sample_per_step": f"{cpu['chains_per_step']} chains x {cpu['transitions']} transitions (of {a.chains} x {a.iters - 1})",
+                    "parallelism": f"{cpu['threads']} host threads, chains split over them"})
+    return cfg
 
 
 def main():
@@ -652,6 +855,8 @@ def _main():
         if s64 is not None:
             s64.zero_()
 
+    pending = []   # (summary tensor, NCCL work handle) of the passes whose all-reduce is still in flight
+
     def one_step(step_idx):
         nonlocal summary
         reset_state()
@@ -659,7 +864,16 @@ def _main():
         eng.run(entry, theta=theta, y=y, n_steps=T - 1, gf=gf, seed=step_idx, chain_id_base=chain_base,
                 trace_layout=layout, trace=trace, trace_rows=T, stats=stats, block_threads=a.block, K=K, aux=aux, **extra)
         rs = RunStats(stats, d)
-        summary = sharding.allreduce_summary(sharding.summarize(rs))   # NCCL only for N > 1
+        summary = sharding.summarize(rs).to(torch.float64)
+        if world > 1:
+            # the one collective of the path (6 + 2d float64 scalars): asynchronous, on NCCL's own stream, so the next pass's
+            # kernel does not wait for it; all of them are waited for before the timed region closes
+            pending.append((summary, dist.all_reduce(summary, op=dist.ReduceOp.SUM, async_op=True)))
+
+    def drain():
+        for _, work in pending:
+            work.wait()
+        pending.clear()
 
     def barrier():
         if world > 1:
@@ -670,6 +884,7 @@ def _main():
     sampler.start()
     for w in range(a.warmup):
         one_step(w)
+    drain()
     # kernel-only duration of the dominant kernel, CUDA events on the launching stream
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ms = []
@@ -680,6 +895,7 @@ def _main():
     e0.record()
     for s in range(a.steps):
         one_step(a.warmup + s)
+    drain()
     e1.record()
     barrier()
     sampler.rows = sampler.rows[max(0, n_idle - 1):]
@@ -689,6 +905,8 @@ def _main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
     steps_per_pass = C * (T - 1) * world
+    last_seed = a.warmup + a.steps - 1
+    first64 = trace[:64].clone() if (layout == abi.TRACE_CHAIN_MAJOR and entry == "global" and C >= 64) else None
     value = steps_per_pass * a.steps / (total_ms * 1e-3)
 
     # the step kernel alone (no state reset / summary kernels around it)
@@ -850,12 +1068,30 @@ def _main():
                                (f"glabc_run_{entry}_host: pinned host buffers, full trace copied back in time chunks "
                                 "overlapped with the kernels; host view [T,C,2] (chain c = trace[:, c])")}
 
+    if a.sampler == "global" and not a.no_extra and not a.no_other_configs:
+        torch.cuda.empty_cache()
+        oc = other_configs(a, eng, model, lp, gp, rank, world, info, sm_max_mhz, peaks)   # every rank takes part
+        if rank == 0:
+            line["other_configs"] = oc
+        eng.bind_model(model)
+        eng.bind_proposal(abi.SLOT_LOCAL, lp)
+        eng.bind_proposal(abi.SLOT_GLOBAL, gp)
+        eng.bind_proposal(abi.SLOT_IMPORTANCE, gp)
     if rank == 0 and world == 1 and a.sampler == "global" and not a.no_extra:
         line["other_kernels"] = other_kernels(eng, model, lp, gp)
     if rank == 0 and not a.no_cpu:
         r, cores, sample, cpu_esjd = cpu_port_rate(C, T, a.cpu_seconds, sampler=a.sampler)
         line["cpu_baseline"] = {"value": r, "unit": "chain-steps/s", "cores": cores, "kind": "port", "sample": sample,
                                 "esjd": {"mean_per_chain": cpu_esjd, "aggregate_esjd_per_sec": cpu_esjd * r}}
+        if first64 is not None:
+            eng.bind_model(model)
+            eng.bind_proposal(abi.SLOT_LOCAL, lp)
+            eng.bind_proposal(abi.SLOT_GLOBAL, gp)
+            line["parity"] = replay_parity_bit(eng, abi, entry, gf, T, first64, theta0, y0, last_seed, chain_base)
+        if world == 1 and a.sampler in ("global", "glmcmc") and not a.no_ref_python:
+            sys.path.insert(0, os.path.join(ROOT, "baseline"))
+            import ref_python
+            line["cpu_baseline"]["reference_python"] = ref_python.measure(a.ref_python_its, sampler=a.sampler)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

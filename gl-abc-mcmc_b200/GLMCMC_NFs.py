@@ -21,11 +21,22 @@ from .pooled import average_gradients
 from .samplers import default_seed, initial_state
 
 
-def resample(W, N):
+def resample(W, N, eng=None):
     """Systematic resampling, GLMCMC_NFs.py:29-40: u_i = (U + i) / N, index j repeated once per u_i in
-    [Psum[j-1], Psum[j]); u_i beyond the last cumulative weight are dropped (the reference returns fewer than N then)."""
+    [Psum[j-1], Psum[j]); u_i beyond the last cumulative weight are dropped (the reference returns fewer than N then).
+    Device weights go through the kernel `glabc_resample` (csrc/resample.cu); host weights (the reference's own call shape)
+    through the equivalent torch.cumsum / searchsorted form.  Both consume ONE torch.rand(1), as the reference does."""
     W = torch.as_tensor(W)
-    u = ((torch.rand(1).item() + torch.arange(N)) / N).to(W.device, W.dtype)
+    u0 = torch.rand(1).item()
+    if W.is_cuda:
+        eng = eng or get_engine(W.device)
+        W = W.to(torch.float32).contiguous()
+        idx = torch.empty(int(N), dtype=torch.int64, device=W.device)
+        count = torch.zeros(1, dtype=torch.int64, device=W.device)
+        eng.ctx.check(eng.lib.glabc_resample(eng.ctx.handle, eng._ptr(W), W.numel(), int(N), float(u0), eng._ptr(idx),
+                                             eng._ptr(count), eng._stream()))
+        return idx[: int(count.item())]
+    u = ((u0 + torch.arange(N)) / N).to(W.dtype)
     psum = torch.cumsum(W, dim=0)
     idx = torch.searchsorted(psum, u, right=True)      # first j with Psum[j] > u_i
     return idx[idx < W.shape[0]]
@@ -53,7 +64,7 @@ class FlowProposal:
         flow, d = self.flow, blk.d
         self.opt.zero_grad()
         w = torch.nan_to_num(blk.w.reshape(-1), nan=0.0)
-        idx = resample(w / torch.sum(w), min(w.numel(), self.train_batch))
+        idx = resample(w / torch.sum(w), min(w.numel(), self.train_batch), self.eng)
         loss = flow.forward_kld(blk.theta.reshape(-1, d)[idx].detach().float())
         if not (torch.isnan(loss) | torch.isinf(loss)):
             loss.backward()

@@ -44,6 +44,8 @@ struct glabc_ctx {
     int ag_dim = 0;
     double* kde_cdf = nullptr;
     size_t kde_cdf_cap = 0;
+    double* rs_scratch = nullptr;   // block prefixes of glabc_resample
+    size_t rs_cap = 0;
     float* kde_part = nullptr;   // partial sums of the point-split log_prob
     size_t kde_part_cap = 0;
     // RealNVP flow weights (device copies owned by the context)
@@ -136,6 +138,7 @@ int glabc_ctx_destroy(glabc_ctx* ctx)
     if (ctx->ag_mem) cudaFree(ctx->ag_mem);
     if (ctx->kde_cdf) cudaFree(ctx->kde_cdf);
     if (ctx->kde_part) cudaFree(ctx->kde_part);
+    if (ctx->rs_scratch) cudaFree(ctx->rs_scratch);
     if (ctx->flow_mem) cudaFree(ctx->flow_mem);
     for (int b = 0; b < 2; ++b) {
         if (ctx->d_trace[b]) cudaFree(ctx->d_trace[b]);
@@ -1479,6 +1482,24 @@ int glabc_run_mala(glabc_ctx* ctx, const glabc_run_t* run) { return run_device(c
 int glabc_run_mala_host(glabc_ctx* ctx, const glabc_run_t* run, int64_t chunk_steps)
 {
     return run_host(ctx, SAMPLER_MALA, run, chunk_steps);
+}
+
+int glabc_resample(glabc_ctx* ctx, const float* W, int64_t n, int64_t N, float u0, int64_t* idx, uint64_t* count, void* stream)
+{
+    if (!ctx) return GLABC_ERR_INVALID;
+    if (n < 0 || N < 0 || (n > 0 && !W) || (N > 0 && !idx) || !count) return fail(ctx, GLABC_ERR_INVALID, "glabc_resample: bad sizes / null pointer");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t need = static_cast<size_t>((n + 4095) / 4096) + 1;
+    if (need > ctx->rs_cap) {
+        if (ctx->rs_scratch) cudaFree(ctx->rs_scratch);
+        ctx->rs_scratch = nullptr;
+        ctx->rs_cap = 0;
+        CUDA_TRY(ctx, cudaMalloc(&ctx->rs_scratch, need * sizeof(double)));
+        ctx->rs_cap = need;
+    }
+    CUDA_TRY(ctx, launch_resample(W, n, N, u0, idx, reinterpret_cast<unsigned long long*>(count), ctx->rs_scratch,
+                                  static_cast<cudaStream_t>(stream)));
+    return GLABC_OK;
 }
 
 int glabc_esjd(glabc_ctx* ctx, const float* trace, int32_t layout, int64_t rows, int64_t chains, int32_t dim, float* out,

@@ -20,6 +20,9 @@ cudaError_t launch_esjd(const float* trace, int layout, int64_t rows, int64_t ch
 
 cudaError_t launch_summarize(const float* stats, int64_t chains, int dim, double* out, cudaStream_t st);
 
+cudaError_t launch_resample(const float* w, int64_t n, int64_t N, float u0, int64_t* idx, unsigned long long* count, double* scratch,
+                            cudaStream_t st);
+
 cudaError_t launch_philox_kat(const uint32_t* ctr, const uint32_t* key, int64_t n, uint32_t* out, cudaStream_t st);
 
 }  // namespace glabc

@@ -888,11 +888,17 @@ static cudaError_t launch_mala_one(const MalaConsts& K, const RunParams& R, int 
     return cudaGetLastError();
 }
 
+// the throughput path (step_mala_fast.cuh): FAST arithmetic, native Philox, no tape dump
+template <int D, int FAMILY>
+static cudaError_t launch_mala_fast(const MalaConsts& K, const RunParams& R, cudaStream_t st);
+
 template <int D, int FAMILY>
 static cudaError_t launch_mala_family(const MalaConsts& K, const RunParams& R, bool strict, bool replay, int block,
                                       cudaStream_t st)
 {
     const bool dump = R.tape_dump != nullptr;
+    // block_threads == 96 keeps the warp-per-chain kernel for FAST runs too (tests compare the two layouts)
+    if (!strict && !replay && !dump && block != 96) return launch_mala_fast<D, FAMILY>(K, R, st);
     if (replay)
         return strict ? launch_mala_one<D, FAMILY, true, true, false>(K, R, block, st)
                       : launch_mala_one<D, FAMILY, false, true, false>(K, R, block, st);

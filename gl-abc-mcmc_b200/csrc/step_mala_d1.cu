@@ -1,5 +1,5 @@
 // K3 instantiations for theta_dim = 1
-#include "step_mala.cuh"
+#include "step_mala_fast.cuh"
 
 namespace glabc {
 template cudaError_t launch_mala_dim<1>(const MalaConsts&, const RunParams&, bool, bool, int, cudaStream_t);

@@ -448,6 +448,13 @@ GLABC_API int glabc_expand_events(const float* events, int64_t chains, int64_t c
  * The caller zeroes `out`.                                                                                              */
 GLABC_API int glabc_summarize(glabc_ctx* ctx, const float* stats, int64_t chains, int32_t dim, double* out, void* stream);
 
+/* resample(W, N), GLMCMC_NFs.py:29-40 / AGLMCMC.py:30-41 — systematic resampling of the candidate block by its normalised
+ * weights W[n] (device, float32) with the ONE uniform u0 = torch.rand(1) the reference draws: idx[i] (device, int64, i < N) =
+ * the index emitted for u_i = (u0 + i) / N, or n when u_i lies at or beyond the last cumulative weight (the reference returns
+ * fewer than N indices then; they are always the LAST ones, so idx[0 .. *count) is the reference's list); count (device).   */
+GLABC_API int glabc_resample(glabc_ctx* ctx, const float* W, int64_t n, int64_t N, float u0, int64_t* idx, uint64_t* count,
+                             void* stream);
+
 /* raw Philox4x32-10 blocks for known-answer tests: out[n][4] = philox(ctr[n][4], key[n][2])       */
 GLABC_API int glabc_philox_kat(glabc_ctx* ctx, const uint32_t* ctr, const uint32_t* key, int64_t n,
                      uint32_t* out, void* stream);

@@ -112,6 +112,13 @@ def test_boundary_errors_carry_a_message(objs):
                 state64=torch.zeros(4, abi.STATE64_SLOTS, device="cuda", dtype=torch.float64),
                 trace_layout=abi.TRACE_EVENTS, trace=torch.zeros(4, 8, 3, device="cuda"), trace_rows=8)
     assert ei.value.status == abi.ERR_UNSUPPORTED
+    # the event layout is a device-buffer layout: the host entry points refuse it before anything is allocated or launched
+    hth, hy = torch.zeros(4, 2), torch.zeros(4, 2)
+    for sampler, kw in (("global", {}), ("isir", dict(K=5, aux=torch.zeros(4, abi.AUX_SLOTS)))):
+        ev = torch.full((4, 8, 3), 7.0)
+        with pytest.raises(abi.GlabcError, match="device-buffer layout") as ei:
+            eng.run_host(sampler, theta=hth, y=hy, n_steps=30, gf=0.5, trace=ev, trace_layout=abi.TRACE_EVENTS, **kw)
+        assert ei.value.status == abi.ERR_UNSUPPORTED and bool((ev == 7.0).all())
     # a 5-dimensional model has no fused family
     with pytest.raises(NotImplementedError):
         g.AbsNormalModel(0.05, y_obs=(1.0,) * 5).lower()

@@ -169,6 +169,39 @@ def test_native_draws_replayed_by_oracle(eng):
     assert torch.equal(again, got)
 
 
+@pytest.mark.parametrize("d,K,num", [(2, 5, 100), (1, 3, 7), (3, 4, 33), (4, 6, 50)])
+def test_thread_per_chain_kernel_equals_warp_per_chain_kernel(eng, d, K, num):
+    """FAST native mode runs k_mala_fast (a thread per chain, the gradient dealt over the warp); block_threads = 96 keeps
+    the warp-per-chain kernel.  Same Philox layout, same formulas, float32 instead of float64 state: the two take the
+    same decisions until float32 finite-difference noise flips one (as between kernel and oracle), and agree on the chain
+    values up to then."""
+    case, tape, tape64, tg0, theta0, y0 = synthetic_case(d, 333, 1, K, num, seed=7 * d + K)
+    family = abi.MODEL_ABS_NORMAL if d % 2 == 0 else abi.MODEL_ID_NORMAL
+    bind(eng, model_pod(case, family), gauss_pod(case, "ip"))
+    Cn, T = 333, 60
+    out = {}
+    for name, bt in (("thread", 0), ("warp", 96)):
+        theta, y = dev(theta0), dev(y0)
+        aux, s64 = fresh_dev(Cn)
+        st = torch.zeros(Cn, abi.nstats(d), device="cuda")
+        tr = eng.run("mala", theta=theta, y=y, aux=aux, state64=s64, n_steps=T, gf=0.6, seed=5, chain_id_base=11, K=K, num_grad=num,
+                     tau=0.25, stats=st, trace_layout=abi.TRACE_TIME_MAJOR, block_threads=bt)
+        torch.cuda.synchronize()
+        out[name] = (tr.cpu().numpy(), st.cpu().numpy(), aux.cpu().numpy(), s64.cpu().numpy())
+    a, b = out["thread"][0], out["warp"][0]
+    moved_a, moved_b = (a[1:] != a[:-1]).any(-1), (b[1:] != b[:-1]).any(-1)
+    clean = (moved_a == moved_b).all(0)
+    assert clean.mean() > 0.9, clean.mean()
+    assert moved_a.mean() > 0.02                                  # the chains do move
+    # values: identical until a chain's first accepted MALA move, then apart by the amplified float32 finite-difference noise
+    # of the prior gradient (1e-2 in the drift, helpers.check_mala_free_running uses the same 2e-2 against the reference)
+    diff = np.abs(a[:, clean] - b[:, clean])
+    assert diff.max() < 2e-2, float(diff.max())
+    assert (diff < 1e-5).mean() > 0.5, float((diff < 1e-5).mean())
+    assert np.array_equal(out["thread"][1][clean, :4], out["warp"][1][clean, :4])     # step / global / accept counters
+    assert np.array_equal(out["thread"][2][clean, :5], out["warp"][2][clean, :5])     # local / wide / have_grad flags
+
+
 def test_native_invariances(eng):
     """chunked / resumed runs (float64 state carried in state64), sharding by chain_id_base and both trace layouts
     give bit-identical chains"""
