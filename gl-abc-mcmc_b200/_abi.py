@@ -25,6 +25,7 @@ SLOT_LOCAL, SLOT_GLOBAL, SLOT_IMPORTANCE = range(3)
 RNG_NATIVE, RNG_REPLAY = 0, 1
 ARITH_FAST, ARITH_STRICT = 0, 1
 TRACE_NONE, TRACE_TIME_MAJOR, TRACE_CHAIN_MAJOR, TRACE_EVENTS = 0, 1, 2, 3
+FLOW_FAST, FLOW_PRECISE = 0, 1
 
 STAT_STEPS, STAT_GLOBAL_STEPS, STAT_ACC_LOCAL, STAT_ACC_GLOBAL, STAT_SUM = 0, 1, 2, 3, 4
 
@@ -164,6 +165,7 @@ _SIGNATURES = {
     "glabc_flow_log_prob": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "glabc_esjd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "glabc_expand_events": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int32]),
+    "glabc_flow_precision": (C.c_int, [C.c_void_p, C.c_int32]),
     "glabc_resample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "glabc_summarize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "glabc_philox_kat": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),

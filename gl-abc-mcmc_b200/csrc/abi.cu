@@ -53,6 +53,7 @@ struct glabc_ctx {
     size_t flow_floats = 0;
     FlowDev flow{};
     bool has_flow = false;
+    int32_t flow_precision = GLABC_FLOW_PRECISE;   // the mode that meets north_star's 1e-5 on log-densities is the default
     float* d_trace[2] = {nullptr, nullptr};
     size_t trace_cap = 0;
     cudaStream_t s_compute = nullptr, s_copy = nullptr;
@@ -864,9 +865,11 @@ extern "C" int glabc_flow_set(glabc_ctx* ctx, const glabc_flow_t* f, size_t nbyt
     CUDA_TRY(ctx, cudaMemcpyAsync(b2, f->b2, L * H * 4, cudaMemcpyDeviceToDevice, cs));
     CUDA_TRY(ctx, cudaMemcpyAsync(w3, f->w3, L * 2 * H * 4, cudaMemcpyDeviceToDevice, cs));
     CUDA_TRY(ctx, cudaMemcpyAsync(b3, f->b3, L * 2 * 4, cudaMemcpyDeviceToDevice, cs));
-    CUDA_TRY(ctx, launch_flow_pack(f->w2, w2p, f->n_blocks, cs));
+    // the packed FP16 W2 takes half of the L*H*H float slots; the other half holds the FP16 remainder W2 - FP16(W2) (PRECISE mode)
+    float* w2p_lo = w2p + L * H * H / 2;
+    CUDA_TRY(ctx, launch_flow_pack(f->w2, w2p, w2p_lo, f->n_blocks, cs));
     FlowDev d{};
-    d.w1 = w1; d.b1 = b1; d.w2p = w2p; d.b2 = b2; d.w3 = w3; d.b3 = b3;
+    d.w1 = w1; d.b1 = b1; d.w2p = w2p; d.w2p_lo = w2p_lo; d.b2 = b2; d.w3 = w3; d.b3 = b3;
     for (int i = 0; i < 2; ++i) {
         d.base_loc[i] = f->base_loc[i];
         d.base_log_scale[i] = f->base_log_scale[i];
@@ -884,7 +887,16 @@ static int run_flow(glabc_ctx* ctx, bool sample, const float* in, int64_t n, flo
     if (ctx->cc < 100) return fail(ctx, GLABC_ERR_UNSUPPORTED, "the flow kernels need tcgen05 tensor cores (sm_100a); this device is sm_%d", ctx->cc);
     if (!in || !log_q || (sample && !theta) || n < 0) return fail(ctx, GLABC_ERR_INVALID, "glabc_flow_%s: null pointer / bad n", sample ? "sample" : "log_prob");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    CUDA_TRY(ctx, launch_flow(ctx->flow, sample, in, n, theta, log_q, ctx->sm_count, static_cast<cudaStream_t>(stream)));
+    CUDA_TRY(ctx, launch_flow(ctx->flow, sample, ctx->flow_precision == GLABC_FLOW_PRECISE, in, n, theta, log_q, ctx->sm_count,
+                              static_cast<cudaStream_t>(stream)));
+    return GLABC_OK;
+}
+
+extern "C" int glabc_flow_precision(glabc_ctx* ctx, int32_t mode)
+{
+    if (!ctx) return GLABC_ERR_INVALID;
+    if (mode != GLABC_FLOW_FAST && mode != GLABC_FLOW_PRECISE) return fail(ctx, GLABC_ERR_INVALID, "glabc_flow_precision: bad mode %d", mode);
+    ctx->flow_precision = mode;
     return GLABC_OK;
 }
 

@@ -66,11 +66,20 @@ constexpr int kFlowThreads = kFlowGroups * kFlowGroupThreads;         // 512: fo
 constexpr int kFlowSmemBytes = kFlowW2Bytes + kFlowW3Bytes + kFlowVecFloats * 4 + 3 * kFlowTilesPerCta * kFlowTile * 4 +
                                kFlowGroups * 2 * kFlowTile * 8 + 64;   // W2 of the block, vectors, states, partial sums, barriers
 constexpr uint32_t kFlowTmemCols = 512;                                // per group: 128 accumulator + 128 A-operand columns
+// PRECISE mode (split precision): A = A_hi + A_lo and W2 = W_hi + W_lo as FP16 pairs, three MMAs per K step
+// (A_hi W_hi + A_lo W_hi + A_hi W_lo, FP32 accumulate; the dropped A_lo W_lo term is 2^-22 of the product), layers 1 and 3 and
+// every vector in FP32 on the CUDA cores.  FP16 subnormals keep the lo parts to 3e-8 absolute, so the hidden layer carries
+// ~22 significant bits and the flow's log-density agrees with a float64 evaluation to ~1e-6 (tests/test_flow_gpu.py): the
+// tolerance north_star states (1e-5) — which FP16 / TF32 operands alone miss by 20-600x.  Shared memory: W_hi and W_lo (64 KB);
+// TMEM per group: 128 accumulator + 64 A_hi + 64 A_lo columns (no double-buffered A).
+constexpr int kFlowSmemBytesPrecise = 2 * kFlowW2Bytes + kFlowVecFloats * 4 + 3 * kFlowTilesPerCta * kFlowTile * 4 +
+                                      kFlowGroups * 2 * kFlowTile * 8 + 64;
 
 struct FlowDev {
     const float* w1;   // [L][128]
     const float* b1;   // [L][128]
-    const float* w2p;  // [L][128*128] tf32 bits, UMMA K-major / no-swizzle core-matrix layout (flow_pack_offset)
+    const float* w2p;  // [L][128*128] FP16 (or TF32 bits), UMMA K-major / no-swizzle core-matrix layout (flow_pack_offset)
+    const float* w2p_lo;  // PRECISE mode: FP16(W2 - FP16(W2)) in the same layout
     const float* b2;   // [L][128]
     const float* w3;   // [L][2][128]
     const float* b3;   // [L][2]
@@ -244,7 +253,8 @@ __device__ __forceinline__ float to_tf32(float x)
 __device__ __forceinline__ float round_tf32_nonneg(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
 
 // pack W2 [L][out=128][in=128] (torch Linear.weight) into the UMMA layout, rounded to TF32
-static __global__ void __launch_bounds__(256) k_flow_pack(const float* __restrict__ w2, float* __restrict__ w2p, int64_t total)
+static __global__ void __launch_bounds__(256) k_flow_pack(const float* __restrict__ w2, float* __restrict__ w2p, float* __restrict__ w2p_lo,
+                                                          int64_t total)
 {
     const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (g >= total) return;
@@ -252,7 +262,10 @@ static __global__ void __launch_bounds__(256) k_flow_pack(const float* __restric
     const uint32_t e = static_cast<uint32_t>(g - l * kFlowHidden * kFlowHidden);
     const uint32_t r = e / kFlowHidden, k = e % kFlowHidden;
     if constexpr (kFlowF16) {
-        reinterpret_cast<__half*>(w2p)[l * kFlowHidden * kFlowHidden + flow_pack_offset(r, k) / 2] = __float2half_rn(w2[g]);
+        const __half hi = __float2half_rn(w2[g]);
+        reinterpret_cast<__half*>(w2p)[l * kFlowHidden * kFlowHidden + flow_pack_offset(r, k) / 2] = hi;
+        if (w2p_lo != nullptr)
+            reinterpret_cast<__half*>(w2p_lo)[l * kFlowHidden * kFlowHidden + flow_pack_offset(r, k) / 2] = __float2half_rn(w2[g] - __half2float(hi));
     } else {
         w2p[l * kFlowHidden * kFlowHidden + flow_pack_offset(r, k) / 4] = to_tf32(w2[g]);
     }
@@ -270,15 +283,20 @@ __device__ __forceinline__ void group_sync(int group)
 // Inside a group TWO threads serve each sample row — warps w and w+4 may both read TMEM lanes 32(w%4).., so thread
 // (row, half) computes hidden units [64 half, 64 half + 64) of layer 1 and reduces the same 64 accumulator columns in
 // the epilogue; the two partial (shift, log-scale) sums meet in shared memory.  Four warps per scheduler instead of two.
-template <bool SAMPLE>
+template <bool SAMPLE, bool PRECISE>
 __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant__ FlowDev W, const float* __restrict__ in,
                                                           int64_t n, float* __restrict__ out_theta, float* __restrict__ out_lq, int tpc)
 {
+    static_assert(!PRECISE || kFlowF16, "the split-precision mode splits into FP16 pairs");
+    // the fast configuration's switches, all off in PRECISE mode
+    constexpr bool kOverlap = !PRECISE && kFlowOverlap;      // double-buffered A operand
+    constexpr bool kMma2 = !PRECISE && kFlowMma2;            // output layer as a second small MMA
+    constexpr bool kVecF16 = !PRECISE && kFlowF16;           // layer vectors staged as FP16 pairs
     // tpc: tiles per chunk (<= kFlowTilesPerCta), chosen by the launcher
     extern __shared__ __align__(1024) uint8_t smem[];
     float* sB = reinterpret_cast<float*>(smem);
-    __half* sW3 = reinterpret_cast<__half*>(smem + kFlowW2Bytes);   // [16][128] FP16, UMMA K-major core-matrix layout (kFlowMma2)
-    float* sVec = reinterpret_cast<float*>(smem + kFlowW2Bytes + kFlowW3Bytes);
+    __half* sW3 = reinterpret_cast<__half*>(smem + kFlowW2Bytes);   // FAST: [16][128] FP16, UMMA K-major core-matrix layout (kMma2)
+    float* sVec = reinterpret_cast<float*>(smem + (PRECISE ? 2 * kFlowW2Bytes : kFlowW2Bytes + kFlowW3Bytes));   // PRECISE: W_lo follows W_hi
     float* sState = sVec + kFlowVecFloats;  // [3][tiles][128]: z1, z2, log q
     float2* sPart = reinterpret_cast<float2*>(sState + 3 * kFlowTilesPerCta * kFlowTile);  // [groups][128] partial sums of half 1
     uint64_t* bars = reinterpret_cast<uint64_t*>(sPart + kFlowGroups * 2 * kFlowTile);
@@ -301,7 +319,7 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
         for (int i = 0; i < 1 + kFlowGroups; ++i) mbar_init(smem_u32(&bars[i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if constexpr (kFlowMma2)
+    if constexpr (kMma2)
         for (int i = tid; i < kFlowW3Bytes / 4; i += kFlowThreads) reinterpret_cast<uint32_t*>(sW3)[i] = 0u;
     tc_fence_before();
     __syncthreads();
@@ -342,13 +360,19 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
             const int l = SAMPLE ? li : L - 1 - li;
             __syncthreads();  // both groups are done with the previous block's W2 / vectors / state updates
             if (tid == 0) {
-                mbar_expect_tx(bar_w, kFlowW2Bytes);
+                mbar_expect_tx(bar_w, PRECISE ? 2 * kFlowW2Bytes : kFlowW2Bytes);
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                     bulk_g2s(sB_addr + q * (kFlowW2Bytes / 4), reinterpret_cast<const uint8_t*>(W.w2p) +
                              static_cast<int64_t>(l) * kFlowW2Bytes + q * (kFlowW2Bytes / 4), kFlowW2Bytes / 4, bar_w);
+                if constexpr (PRECISE) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        bulk_g2s(sB_addr + kFlowW2Bytes + q * (kFlowW2Bytes / 4), reinterpret_cast<const uint8_t*>(W.w2p_lo) +
+                                 static_cast<int64_t>(l) * kFlowW2Bytes + q * (kFlowW2Bytes / 4), kFlowW2Bytes / 4, bar_w);
+                }
             }
-            if constexpr (kFlowF16) {
+            if constexpr (kVecF16) {
                 // The broadcast reads of these vectors are what bounds the kernel (every warp re-reads them for every tile:
                 // 1,280 B per thread and tile in fp32 = more shared-memory cycles than the tile takes), so they are staged in
                 // the narrowest form the arithmetic allows: w1 / b1 as FP16 pairs (layer 1 runs as HFMA2.RELU straight into the
@@ -360,7 +384,7 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
                 else if (tid < 384) sU[128 + tid] = pack_half2(W.w3[(l * 2) * kFlowHidden + tid - 256],       // [384, 512)
                                                                W.w3[(l * 2 + 1) * kFlowHidden + tid - 256]);
                 else if (tid < 386) sVec[640 + tid - 384] = W.b3[l * 2 + tid - 384];
-                if constexpr (kFlowMma2) {   // element (n, k) of the 16 x 128 operand: rows 0 (shift) and 1 (log-scale)
+                if constexpr (kMma2) {   // element (n, k) of the 16 x 128 operand: rows 0 (shift) and 1 (log-scale)
                     if (tid >= 256) {
                         const int n = (tid - 256) >> 7, k = (tid - 256) & 127;
                         sW3[((k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2) / 2] = __float2half_rn(W.w3[(l * 2 + n) * kFlowHidden + k]);
@@ -374,7 +398,7 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
                 if (tid < 128) sVec[512 + tid] = W.w3[(l * 2 + 1) * kFlowHidden + tid];
                 if (tid < 2) sVec[640 + tid] = W.b3[l * 2 + tid];
             }
-            if constexpr (kFlowMma2) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // sW3: generic writes -> MMA reads
+            if constexpr (kMma2) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // sW3: generic writes -> MMA reads
             __syncthreads();
             mbar_wait(bar_w, ph_w);
             ph_w ^= 1u;
@@ -382,7 +406,25 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
             // layer 1 (K = 1) of tile t on CUDA cores, written as the A operand into TMEM columns `a_cols`: this thread's 64 hidden units
             auto layer1 = [&](int t, uint32_t tmem_a) {
                 float z1 = sState[(SAMPLE ? 0 : 1) * TS + t * kFlowTile + row];   // !SAMPLE: Permute(swap)^-1 precedes the inverse
-                if constexpr (kFlowF16) {
+                if constexpr (PRECISE) {
+                    // FP32 layer 1, then the FP16 hi / lo split of every activation: 32 + 32 packed columns, two tcgen05.st
+                    uint32_t hv[32], lv[32];
+#pragma unroll
+                    for (int j = 0; j < HK / 4; ++j) {
+                        const float4 w = *reinterpret_cast<const float4*>(&sVec[half * HK + 4 * j]);
+                        const float4 bb = *reinterpret_cast<const float4*>(&sVec[128 + half * HK + 4 * j]);
+                        const float a0 = fmaxf(fmaf(w.x, z1, bb.x), 0.0f), a1 = fmaxf(fmaf(w.y, z1, bb.y), 0.0f);
+                        const float a2 = fmaxf(fmaf(w.z, z1, bb.z), 0.0f), a3 = fmaxf(fmaf(w.w, z1, bb.w), 0.0f);
+                        const uint32_t h01 = relu_pack_f16(a0, a1), h23 = relu_pack_f16(a2, a3);   // saturating round to FP16
+                        const float2 f01 = unpack_half2(h01), f23 = unpack_half2(h23);
+                        hv[2 * j] = h01;
+                        hv[2 * j + 1] = h23;
+                        lv[2 * j] = pack_half2(a0 - f01.x, a1 - f01.y);
+                        lv[2 * j + 1] = pack_half2(a2 - f23.x, a3 - f23.y);
+                    }
+                    tmem_st32(tmem_a + (static_cast<uint32_t>(quad * 32) << 16) + half * (HK / 2), hv);
+                    tmem_st32(tmem_a + 64u + (static_cast<uint32_t>(quad * 32) << 16) + half * (HK / 2), lv);
+                } else if constexpr (kFlowF16) {
                     // this thread's 64 hidden units as 32 packed FP16 pairs = 32 TMEM columns, ONE tcgen05.st
                     uint32_t hv[32];
                     // z1 as an FP16 hi + lo pair: rounding the INPUT to 11 bits would perturb all 128 hidden units coherently
@@ -419,15 +461,15 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             };
             uint32_t buf = 0;
-            if (kFlowOverlap && group < tiles) {
+            if (kOverlap && group < tiles) {
                 layer1(group, tmem_a0);
                 tc_fence_before();
                 group_sync(group);
             }
             for (int t = group; t < tiles; t += kFlowGroups) {
-                const uint32_t tmem_a = tmem_a0 + (kFlowOverlap ? buf * 64u : 0u);
+                const uint32_t tmem_a = tmem_a0 + (kOverlap ? buf * 64u : 0u);
                 float2* part = part_base + buf * kFlowTile;
-                if constexpr (!kFlowOverlap) {
+                if constexpr (!kOverlap) {
                     layer1(t, tmem_a);
                     tc_fence_before();
                     group_sync(group);  // (also: half 0 has consumed the previous tile's partial sums)
@@ -435,7 +477,18 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
                 // ---- layer 2 (128 x 128 x 128) on the tensor cores ----
                 if (gtid == 0) {
                     tc_fence_after();
-                    if constexpr (kFlowF16) {
+                    if constexpr (PRECISE) {
+                        // A_hi W_hi, then the two cross terms, all into the same FP32 accumulator
+#pragma unroll
+                        for (int k = 0; k < kFlowHidden / 16; ++k)
+                            umma_f16_ts(tmem, tmem_a + k * 8, umma_desc(sB_addr + k * 256, 128, 2048), idesc, k > 0 ? 1u : 0u);
+#pragma unroll
+                        for (int k = 0; k < kFlowHidden / 16; ++k)
+                            umma_f16_ts(tmem, tmem_a + 64u + k * 8, umma_desc(sB_addr + k * 256, 128, 2048), idesc, 1u);
+#pragma unroll
+                        for (int k = 0; k < kFlowHidden / 16; ++k)
+                            umma_f16_ts(tmem, tmem_a + k * 8, umma_desc(sB_addr + kFlowW2Bytes + k * 256, 128, 2048), idesc, 1u);
+                    } else if constexpr (kFlowF16) {
 #pragma unroll
                         for (int k = 0; k < kFlowHidden / 16; ++k) {   // K = 16 halves = 2 core matrices = 256 B of B, 8 columns of A
                             const uint64_t bd = umma_desc(sB_addr + k * 256, 128, 2048);
@@ -450,7 +503,7 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
                     }
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_m) : "memory");
                 }
-                if constexpr (kFlowOverlap) {   // the group's next tile: its layer 1 fills the other A buffer while the MMA runs
+                if constexpr (kOverlap) {   // the group's next tile: its layer 1 fills the other A buffer while the MMA runs
                     if (t + kFlowGroups < tiles) layer1(t + kFlowGroups, tmem_a0 + (buf ^ 1u) * 64u);
                 }
                 mbar_wait(bar_m, ph_m);
@@ -458,7 +511,7 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
                 tc_fence_after();
                 float s0 = 0.0f, s1 = 0.0f;
                 float2 o = make_float2(0.0f, 0.0f);
-                if constexpr (kFlowMma2) {
+                if constexpr (kMma2) {
                     // ---- bias + ReLU from TMEM, packed back as FP16 into this tile's A columns (free since its MMA completed) ----
                     {
                         uint32_t v[2][16], hp[32];
@@ -526,7 +579,7 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
                         for (int j = 0; j < 16; j += 4) {  // broadcast LDS.128 of b2 and of the W3 pairs: 2 loads per 4 columns
                             const float4 b2v = *reinterpret_cast<const float4*>(&sVec[256 + col0 + j]);
                             float2 w0, w1, w2, w3;
-                            if constexpr (kFlowF16) {
+                            if constexpr (kVecF16) {
                                 const uint4 wq = *reinterpret_cast<const uint4*>(&sVec[384 + col0 + j]);
                                 w0 = unpack_half2(wq.x); w1 = unpack_half2(wq.y); w2 = unpack_half2(wq.z); w3 = unpack_half2(wq.w);
                             } else {
@@ -603,8 +656,8 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
                      : "memory");
 }
 
-cudaError_t launch_flow_pack(const float* w2, float* w2p, int n_blocks, cudaStream_t st);
-cudaError_t launch_flow(const FlowDev& W, bool sample, const float* in, int64_t n, float* out_theta, float* out_lq, int sm_count,
-                        cudaStream_t st);
+cudaError_t launch_flow_pack(const float* w2, float* w2p, float* w2p_lo, int n_blocks, cudaStream_t st);
+cudaError_t launch_flow(const FlowDev& W, bool sample, bool precise, const float* in, int64_t n, float* out_theta, float* out_lq,
+                        int sm_count, cudaStream_t st);
 
 }  // namespace glabc

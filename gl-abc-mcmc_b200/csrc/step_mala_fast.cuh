@@ -16,6 +16,18 @@
 #pragma once
 #include "step_mala.cuh"
 
+#ifndef GLABC_MALA_UNROLL
+#define GLABC_MALA_UNROLL 1
+#endif
+#ifndef GLABC_MALA_KUNROLL
+#define GLABC_MALA_KUNROLL 5
+#endif
+#ifndef GLABC_MALA_BLOCK
+#define GLABC_MALA_BLOCK 64
+#endif
+#define GLABC_PRAGMA(x) _Pragma(#x)
+#define GLABC_UNROLL(n) GLABC_PRAGMA(unroll n)
+
 namespace glabc {
 
 // dealing of a gradient's (dimension k, Philox block g) items over the lanes
@@ -68,8 +80,7 @@ __device__ __forceinline__ void warp_gradient_sums(const MalaConsts& K, const Ro
         const float cp = sim_discrepancy_fast<D, FAMILY>(K.model, bp, zero), cm = sim_discrepancy_fast<D, FAMILY>(K.model, bm, zero);
         float f1p = 0.0f, f2p = 0.0f, f1m = 0.0f, f2m = 0.0f;
         const uint32_t slot_k = slot0 + static_cast<uint32_t>(k * nblk);
-#pragma unroll 2
-        for (int g = sub; g < nblk; g += LPD) {
+        auto block_of_draws = [&](int g, int n_live) {
             const uint4 w = src_stream.block(rk, step, slot_k + static_cast<uint32_t>(g));
             float z[4];
             box_muller(w.x, w.y, z[0], z[1]);
@@ -79,15 +90,21 @@ __device__ __forceinline__ void warp_gradient_sums(const MalaConsts& K, const Ro
                 float eps[D];
 #pragma unroll
                 for (int q = 0; q < D; ++q) eps[q] = z[t * D + q];
-                const float xp = sim_discrepancy_fast<D, FAMILY>(K.model, bp, eps) - cp;  // :78-79
-                const float xm = sim_discrepancy_fast<D, FAMILY>(K.model, bm, eps) - cm;  // :80-83 (the same draws)
-                const bool live = g * kDpb + t < num;
-                f1p += live ? xp : 0.0f;
-                f2p = fmaf(live ? xp : 0.0f, xp, f2p);
-                f1m += live ? xm : 0.0f;
-                f2m = fmaf(live ? xm : 0.0f, xm, f2m);
+                float xp = sim_discrepancy_fast<D, FAMILY>(K.model, bp, eps) - cp;  // :78-79
+                float xm = sim_discrepancy_fast<D, FAMILY>(K.model, bm, eps) - cm;  // :80-83 (the same draws)
+                if (t >= n_live) xp = xm = 0.0f;     // compile-time false in the full-block loop
+                f1p += xp;
+                f2p = fmaf(xp, xp, f2p);
+                f1m += xm;
+                f2m = fmaf(xm, xm, f2m);
             }
-        }
+        };
+        // NOT unrolled: measured at 262,144 chains, unroll 1 / 2 / 4 = 5.0e9 / 4.5e9 / 3.5e9 chain-steps/s — the loop body must
+        // stay resident in the instruction cache while the warps of an SM sit in different phases of the step
+        const int nfull = num / kDpb;                 // blocks whose kDpb draws all count; at most one partial block follows
+GLABC_UNROLL(GLABC_MALA_UNROLL)
+        for (int g = sub; g < nfull; g += LPD) block_of_draws(g, kDpb);
+        if (nfull < nblk && (nfull & (LPD - 1)) == sub) block_of_draws(nfull, num - nfull * kDpb);
 #pragma unroll
         for (int off = LPD / 2; off > 0; off >>= 1) {
             f1p += __shfl_xor_sync(0xffffffffu, f1p, off);
@@ -141,14 +158,19 @@ __device__ __forceinline__ void gradient_from_sums(const MalaConsts& K, const fl
     }
 }
 
-template <int D, int FAMILY, int LAYOUT>
-__global__ void __launch_bounds__(64) k_mala_fast(const __grid_constant__ MalaConsts K, const __grid_constant__ RunParams R)
+// CPW = chains per warp: 32, or 16 when there are too few chains to occupy the schedulers (lanes 16..31 then only help with
+// the gradients: the thread-per-chain phases cost twice the issue slots per chain, the gradients — 80 % of the work — the
+// same, and twice as many warps hide the latency of the Philox / MUFU chains).  The chain-major trace tile needs 32.
+template <int D, int FAMILY, int LAYOUT, int CPW>
+__global__ void __launch_bounds__(GLABC_MALA_BLOCK) k_mala_fast(const __grid_constant__ MalaConsts K, const __grid_constant__ RunParams R)
 {
     using Writer = typename WriterFor<D, LAYOUT>::type;
+    static_assert(CPW == 32 || LAYOUT != GLABC_TRACE_CHAIN_MAJOR, "the chain-major tile stages 32 chains per warp");
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int32_t chain = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = chain < R.n_chains;
+    const int32_t warp_chain0 = static_cast<int32_t>((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * CPW;
+    const int32_t chain = warp_chain0 + lane;
+    const bool active = lane < CPW && chain < R.n_chains;
     const int32_t cidx = active ? chain : R.n_chains - 1;   // tail lanes read a valid chain and never write
     const int NK = R.n_candidates;
     constexpr int kGroups = (2 * D + 3) / 4;
@@ -174,7 +196,6 @@ __global__ void __launch_bounds__(64) k_mala_fast(const __grid_constant__ MalaCo
 
     ChainStats<D> stats;
     const Stream stream = chain_stream(R, cidx);
-    const int32_t warp_chain0 = chain - lane;
     const float tau = K.tau_f, half_tau2 = 0.5f * K.tau_f * K.tau_f, inv_tau = 1.0f / K.tau_f;
 
     for (uint32_t i = R.first_step; i <= R.last_step && R.last_step >= R.first_step; ++i) {
@@ -195,7 +216,7 @@ __global__ void __launch_bounds__(64) k_mala_fast(const __grid_constant__ MalaCo
             local = false;
             float m = lw_old == lw_old ? lw_old : -INFINITY;
             uint4 wfirst = make_uint4(0, 0, 0, 0);
-#pragma unroll 5
+GLABC_UNROLL(GLABC_MALA_KUNROLL)
             for (int j = 0; j < NK; ++j) {   // :158-165, candidate j
                 float zc[kGroups * 4];
 #pragma unroll
@@ -372,16 +393,29 @@ __global__ void __launch_bounds__(64) k_mala_fast(const __grid_constant__ MalaCo
     }
 }
 
+template <int D, int FAMILY, int LAYOUT, int CPW>
+static cudaError_t launch_mala_fast_cpw(const MalaConsts& K, const RunParams& R, cudaStream_t st)
+{
+    using Writer = typename WriterFor<D, LAYOUT>::type;
+    constexpr int block = GLABC_MALA_BLOCK;
+    constexpr int chains_per_block = block / 32 * CPW;
+    const int grid = (R.n_chains + chains_per_block - 1) / chains_per_block;
+    const size_t smem = sizeof(float) * (static_cast<size_t>(Writer::smem_floats_per_warp) * (block / 32) +
+                                         static_cast<size_t>(R.n_candidates) * block);
+    k_mala_fast<D, FAMILY, LAYOUT, CPW><<<grid, block, smem, st>>>(K, R);
+    return cudaGetLastError();
+}
+
 template <int D, int FAMILY, int LAYOUT>
 static cudaError_t launch_mala_fast_one(const MalaConsts& K, const RunParams& R, cudaStream_t st)
 {
-    using Writer = typename WriterFor<D, LAYOUT>::type;
-    constexpr int block = 64;
-    const int grid = (R.n_chains + block - 1) / block;
-    const size_t smem = sizeof(float) * (static_cast<size_t>(Writer::smem_floats_per_warp) * (block / 32) +
-                                         static_cast<size_t>(R.n_candidates) * block);
-    k_mala_fast<D, FAMILY, LAYOUT><<<grid, block, smem, st>>>(K, R);
-    return cudaGetLastError();
+    // CPW = 16 (twice the warps for the same chains) was measured at 32,768 chains, where only 1.7 warps sit on a scheduler:
+    // issue-active rose from 47 % to 63 % but the warp-instructions per chain-step rose from 152 to 193 — the same 9.85 ms
+    // (profiles/r2_k3_mala_fast_ncu.md).  Kept behind a build flag for other shapes.
+#if defined(GLABC_MALA_FORCE_CPW) && GLABC_MALA_FORCE_CPW == 16
+    if constexpr (LAYOUT != GLABC_TRACE_CHAIN_MAJOR) return launch_mala_fast_cpw<D, FAMILY, LAYOUT, 16>(K, R, st);
+#endif
+    return launch_mala_fast_cpw<D, FAMILY, LAYOUT, 32>(K, R, st);
 }
 
 template <int D, int FAMILY>

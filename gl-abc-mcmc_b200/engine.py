@@ -264,6 +264,12 @@ class Engine:
         self.ctx.check(fn(self.ctx.handle, C.byref(r), int(chunk_steps)))
         return trace
 
+    def flow_precision(self, mode):
+        """operand precision of the flow's hidden layer for the following glabc_flow_sample / glabc_flow_log_prob calls of this
+        context: "precise" (FP16 hi + lo split, 1e-5-class log-densities; the default) or "fast" (single FP16 operands)"""
+        code = {"fast": _abi.FLOW_FAST, "precise": _abi.FLOW_PRECISE}[mode] if isinstance(mode, str) else int(mode)
+        self.ctx.check(self.lib.glabc_flow_precision(self.ctx.handle, code))
+
     def summarize(self, stats_raw, dim):
         """[chains, steps, global steps, acc local, acc global, sum esjd, sum theta (d), sum theta^2 (d)] of a shard, float64,
         one kernel (glabc_summarize)"""

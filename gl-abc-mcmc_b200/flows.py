@@ -105,8 +105,11 @@ class RealNVP(nn.Module):
         torch.cuda.current_stream(eng.device).synchronize()   # the staging tensors in `t` may be freed now
         return eng
 
-    def fused_sample_from(self, eps, eng=None, theta=None, log_q=None):
+    def fused_sample_from(self, eps, eng=None, theta=None, log_q=None, precision=None):
+        """`precision`: "precise" / "fast" sets the context's flow precision for this and the following calls (None: keep it)"""
         eng = eng or get_engine(self.loc.device)
+        if precision is not None:
+            eng.flow_precision(precision)
         eps = eps.to(eng.device, torch.float32).contiguous()
         n = eps.shape[0]
         theta = torch.empty(n, 2, device=eng.device) if theta is None else theta
@@ -115,8 +118,10 @@ class RealNVP(nn.Module):
         eng.ctx.check(eng.lib.glabc_flow_sample(eng.ctx.handle, eng._ptr(eps), n, eng._ptr(theta), eng._ptr(log_q), eng._stream()))
         return theta, log_q
 
-    def fused_log_prob(self, x, eng=None):
+    def fused_log_prob(self, x, eng=None, precision=None):
         eng = eng or get_engine(self.loc.device)
+        if precision is not None:
+            eng.flow_precision(precision)
         x = x.to(eng.device, torch.float32).reshape(-1, 2).contiguous()
         log_q = torch.empty(x.shape[0], device=eng.device)
         eng.ctx.check(eng.lib.glabc_flow_log_prob(eng.ctx.handle, eng._ptr(x), x.shape[0], eng._ptr(log_q), eng._stream()))

@@ -414,9 +414,18 @@ GLABC_API int glabc_run_block_isir(glabc_ctx* ctx, const glabc_run_t* run, const
  * `round` keys the simulator's Philox normals (run->seed, run->chain_id_base as usual)                           */
 GLABC_API int glabc_block_weights(glabc_ctx* ctx, const glabc_run_t* run, const glabc_block_isir_t* blk, uint32_t round);
 
-/* ---- RealNVP flow on the tensor cores (tcgen05, TF32 operands, FP32 accumulate) ----------------------------
+/* ---- RealNVP flow on the tensor cores (tcgen05 kind::f16, FP32 accumulate in TMEM) --------------------------
  * NormalizingFlow.sample(n) (GLMCMC_NFs.py:72,127): eps[n][2] standard normals in -> theta[n][2], log_q[n];
- * NormalizingFlow.log_prob(x) (GLMCMC_NFs.py:98): theta[n][2] -> log_q[n].  Device pointers.                    */
+ * NormalizingFlow.log_prob(x) (GLMCMC_NFs.py:98): theta[n][2] -> log_q[n].  Device pointers.
+ * Operand precision of the 128 x 128 hidden layer (glabc_flow_precision, per context):
+ *   GLABC_FLOW_PRECISE (default)  FP16 hi + lo split of activations and weights, three MMAs, layers 1 / 3 in FP32: log q and
+ *                                 log_prob agree with a float64 evaluation of the reference's float32 network within 1e-5
+ *                                 relative (the tolerance north_star states for log-densities);
+ *   GLABC_FLOW_FAST               single FP16 operands, one MMA (+ the output layer as a second small MMA): ~3x the samples/s,
+ *                                 agreement ~1e-3.  sample() still returns the exact log-density of the map it applied.     */
+#define GLABC_FLOW_FAST 0
+#define GLABC_FLOW_PRECISE 1
+GLABC_API int glabc_flow_precision(glabc_ctx* ctx, int32_t mode);
 GLABC_API int glabc_flow_set(glabc_ctx* ctx, const glabc_flow_t* flow, size_t nbytes, void* stream);
 GLABC_API int glabc_flow_sample(glabc_ctx* ctx, const float* eps, int64_t n, float* theta, float* log_q, void* stream);
 GLABC_API int glabc_flow_log_prob(glabc_ctx* ctx, const float* theta, int64_t n, float* log_q, void* stream);
