@@ -9,7 +9,10 @@ B200 mapping (many chains, ONE shared flow — the reference's single chain has 
   * the chain step against the block: fused kernel `k_ag_step<EXT>` (csrc/step_aglmcmc.cuh) — a chain pauses when its
     block is consumed or when the proposal log-density of a changed state is needed; this host loop then refreshes those
     log-densities in one batched log_prob launch, and at the end of a block trains / rebinds the flow and refills;
-  * the <= Train_step Adam steps use torch autograd on the fp32 module (flows.RealNVP) over the pooled candidates.
+  * the <= Train_step training steps (forward KL on systematically resampled candidates, backward, Adam) are kernels of the
+    extension too: `resample` -> glabc_resample, forward_kld / backward -> glabc_flow_grad (tcgen05 GEMMs, csrc/flow_train.cuh),
+    the flat gradient all-reduced over the ranks, Adam -> glabc_flow_adam_step.  flows.RealNVP keeps an fp32 torch autograd
+    restatement of the same network as the tests' checker (`flow_train="torch"`).
 Parity note: `normflows` cannot be installed here, so this path is unpinned against it."""
 import torch
 
@@ -17,7 +20,7 @@ from . import _abi
 from .block_isir import run_block_isir
 from .engine import get_engine
 from .flows import RealNVP
-from .pooled import average_gradients
+from .pooled import average_flat, average_gradients
 from .samplers import default_seed, initial_state
 
 
@@ -45,13 +48,16 @@ def resample(W, N, eng=None):
 class FlowProposal:
     """the shared RealNVP as the external proposal of `block_isir.run_block_isir`"""
 
-    def __init__(self, flow, eng, seed, chain_id_base, train_batch, lr, weight_decay, precision="precise"):
-        self.flow, self.eng, self.train_batch = flow, eng, int(train_batch)
+    def __init__(self, flow, eng, seed, chain_id_base, train_batch, lr, weight_decay, precision="precise", train="native"):
+        self.flow, self.eng, self.train_batch, self.train = flow, eng, int(train_batch), train
         eng.flow_precision(precision)
-        self.opt = torch.optim.Adam(flow.parameters(), lr=lr, weight_decay=weight_decay)     # GLMCMC_NFs.py:63
         self.gen = torch.Generator(device=eng.device).manual_seed((seed * 0x9E3779B1 + chain_id_base + 0x5F) & 0x7FFFFFFFFFFFFFFF)
         self.losses = []
-        flow.bind(eng)
+        if train == "native":
+            flow.train_init(eng, lr=lr, weight_decay=weight_decay)                                # GLMCMC_NFs.py:63, in the context
+        else:   # the fp32 torch autograd restatement (the checker of tests/test_flow_train_gpu.py)
+            self.opt = torch.optim.Adam(flow.parameters(), lr=lr, weight_decay=weight_decay)
+            flow.bind(eng)
 
     def fill(self, blk_theta, blk_lq, rnd):     # NF_model.sample, GLMCMC_NFs.py:72,127
         c, B, d = blk_theta.shape
@@ -63,14 +69,23 @@ class FlowProposal:
 
     def adapt(self, blk):                       # GLMCMC_NFs.py:113-124, pooled over the chains (and, averaged, over the ranks)
         flow, d = self.flow, blk.d
-        self.opt.zero_grad()
         w = torch.nan_to_num(blk.w.reshape(-1), nan=0.0)
         idx = resample(w / torch.sum(w), min(w.numel(), self.train_batch), self.eng)
-        loss = flow.forward_kld(blk.theta.reshape(-1, d)[idx].detach().float())
+        x = blk.theta.reshape(-1, d)[idx].detach().float()
+        if self.train == "native":
+            # forward_kld, backward and Adam as kernels of libglabc.so (tcgen05 GEMMs, csrc/flow_train.cuh); the flat gradient
+            # is the one buffer the ranks all-reduce
+            g, loss = flow.grad(x, self.eng)
+            average_flat(g, loss)
+            flow.adam_step(g, loss, self.eng)    # skipped inside when the loss is NaN / inf
+            self.losses.append(float(loss))
+            return
+        self.opt.zero_grad()
+        loss = flow.forward_kld(x)
         if not (torch.isnan(loss) | torch.isinf(loss)):
             loss.backward()
         average_gradients(list(flow.parameters()))
-        self.opt.step()                          # runs even when backward was skipped
+        self.opt.step()
         self.losses.append(float(loss.detach()))
         flow.bind(self.eng)
 
@@ -87,12 +102,13 @@ def _base_params(base):
 def GLMCMC_NF(ABCset, num_ite, Initial_theta, Initial_y, Local_Proposal, filelocation, global_frequency, step_size, batch_size,
               base, Train_step, *, num_chains=None, seed=None, chain_id_base=0, arith="fast", trace="chain", return_stats=False,
               verbose=None, device=None, n_blocks=32, train_batch=65536, lr=5e-4, weight_decay=1e-5, flow=None,
-              return_flow=False, flow_precision="precise"):
+              return_flow=False, flow_precision="precise", flow_train="native"):
     """Same positional signature and return value as the reference for one chain; keyword extensions as in `GlobalMCMC`,
     plus `flow` (continue with a given RealNVP), `train_batch` (pooled resample size), `return_flow` and `flow_precision`:
     "precise" (default — the flow's log-densities agree with the reference's float32 network to 1e-5, three tensor-core MMAs per
     hidden layer) or "fast" (single FP16 operands, ~3x the flow throughput, 1e-3-class agreement; importance weights stay exact
-    either way because sample() returns the density of the map it applied)."""
+    either way because sample() returns the density of the map it applied); `flow_train`: "native" (the training step as
+    kernels of the extension, the default) or "torch" (the fp32 autograd restatement, kept as the tests' checker)."""
     if num_ite < 1:
         raise ValueError("num_ite must be at least 1")
     K, S = int(batch_size), int(step_size)
@@ -113,7 +129,7 @@ def GLMCMC_NF(ABCset, num_ite, Initial_theta, Initial_y, Local_Proposal, fileloc
             torch.manual_seed(seed & 0x7FFFFFFF)         # (identical on every rank: the flow is shared)
             flow = RealNVP(n_blocks=n_blocks, base_loc=loc, base_log_scale=ls)
     flow.to(dev)
-    prop = FlowProposal(flow, eng, seed, chain_id_base, train_batch, lr, weight_decay, precision=flow_precision)
+    prop = FlowProposal(flow, eng, seed, chain_id_base, train_batch, lr, weight_decay, precision=flow_precision, train=flow_train)
     result, rs, _ = run_block_isir(eng, pod, prop, num_ite=num_ite, theta=theta, y=y, K=K, S=S, gf=global_frequency, seed=seed,
                                    chain_id_base=chain_id_base, arith=arith, trace=trace, single=single,
                                    filelocation=filelocation, verbose=verbose, max_adapt=int(Train_step))

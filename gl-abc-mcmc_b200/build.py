@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 SOURCES = ["abi.cu", "diag.cu", "step_global.cu", "step_global_d1.cu", "step_global_d2.cu", "step_global_d3.cu",
            "step_global_d4.cu", "step_isir.cu", "step_isir_d1.cu", "step_isir_d2.cu", "step_isir_d3.cu", "step_isir_d4.cu",
            "step_mala.cu", "step_mala_d1.cu", "step_mala_d2.cu", "step_mala_d3.cu", "step_mala_d4.cu",
-           "kde.cu", "resample.cu", "step_aglmcmc.cu", "flow.cu", "step_generic.cu", "user_model.cu"]
+           "kde.cu", "resample.cu", "step_aglmcmc.cu", "flow.cu", "flow_train.cu", "step_generic.cu", "user_model.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xptxas", "-v",
               "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "include")]

@@ -17,6 +17,7 @@
 
 #include "launch.cuh"
 #include "flow.cuh"
+#include "flow_param_layout.h"
 #include "step_aglmcmc.cuh"
 #include "step_generic.cuh"
 #include "step_mala.cuh"
@@ -53,7 +54,17 @@ struct glabc_ctx {
     size_t flow_floats = 0;
     FlowDev flow{};
     bool has_flow = false;
+    int flow_blocks = 0;
     int32_t flow_precision = GLABC_FLOW_PRECISE;   // the mode that meets north_star's 1e-5 on log-densities is the default
+    // training state of the flow (glabc_flow_train_init): Adam moments, gradient, per-CTA partial gradients, forward scratch
+    float* tr_mem = nullptr;       // m | v | grad | loss
+    float* tr_partial = nullptr;
+    int tr_slices = 0;
+    float* tr_fwd = nullptr;       // z [n][2] | log q [n]
+    int64_t tr_fwd_cap = 0;
+    int64_t tr_step = 0;
+    float tr_lr = 5e-4f, tr_beta1 = 0.9f, tr_beta2 = 0.999f, tr_eps = 1e-8f, tr_wd = 1e-5f;
+    bool tr_ready = false;
     float* d_trace[2] = {nullptr, nullptr};
     size_t trace_cap = 0;
     cudaStream_t s_compute = nullptr, s_copy = nullptr;
@@ -141,6 +152,9 @@ int glabc_ctx_destroy(glabc_ctx* ctx)
     if (ctx->kde_part) cudaFree(ctx->kde_part);
     if (ctx->rs_scratch) cudaFree(ctx->rs_scratch);
     if (ctx->flow_mem) cudaFree(ctx->flow_mem);
+    if (ctx->tr_mem) cudaFree(ctx->tr_mem);
+    if (ctx->tr_partial) cudaFree(ctx->tr_partial);
+    if (ctx->tr_fwd) cudaFree(ctx->tr_fwd);
     for (int b = 0; b < 2; ++b) {
         if (ctx->d_trace[b]) cudaFree(ctx->d_trace[b]);
         if (ctx->ev_done[b]) cudaEventDestroy(ctx->ev_done[b]);
@@ -845,7 +859,9 @@ extern "C" int glabc_flow_set(glabc_ctx* ctx, const glabc_flow_t* f, size_t nbyt
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t cs = static_cast<cudaStream_t>(stream);
     const size_t L = size_t(f->n_blocks), H = kFlowHidden;
-    const size_t need = L * (H + H + H * H + H + 2 * H + 4);
+    const FlowParamLayout P(f->n_blocks);
+    // [packed W2: FP16 hi then FP16 lo, L*H*H floats in all][the flat FP32 parameter vector, FlowParamLayout]
+    const size_t need = L * H * H + size_t(P.total);
     if (need > ctx->flow_floats) {
         if (ctx->flow_mem) cudaFree(ctx->flow_mem);
         ctx->flow_mem = nullptr;
@@ -853,23 +869,23 @@ extern "C" int glabc_flow_set(glabc_ctx* ctx, const glabc_flow_t* f, size_t nbyt
         CUDA_TRY(ctx, cudaMalloc(&ctx->flow_mem, need * sizeof(float)));
         ctx->flow_floats = need;
     }
-    float* p = ctx->flow_mem;
-    float* w2p = p;              p += L * H * H;   // first: 16-byte (in fact 256-byte) aligned for cp.async.bulk
-    float* w1 = p;               p += L * H;
-    float* b1 = p;               p += L * H;
-    float* b2 = p;               p += L * H;
-    float* w3 = p;               p += L * 2 * H;
-    float* b3 = p;
-    CUDA_TRY(ctx, cudaMemcpyAsync(w1, f->w1, L * H * 4, cudaMemcpyDeviceToDevice, cs));
-    CUDA_TRY(ctx, cudaMemcpyAsync(b1, f->b1, L * H * 4, cudaMemcpyDeviceToDevice, cs));
-    CUDA_TRY(ctx, cudaMemcpyAsync(b2, f->b2, L * H * 4, cudaMemcpyDeviceToDevice, cs));
-    CUDA_TRY(ctx, cudaMemcpyAsync(w3, f->w3, L * 2 * H * 4, cudaMemcpyDeviceToDevice, cs));
-    CUDA_TRY(ctx, cudaMemcpyAsync(b3, f->b3, L * 2 * 4, cudaMemcpyDeviceToDevice, cs));
-    // the packed FP16 W2 takes half of the L*H*H float slots; the other half holds the FP16 remainder W2 - FP16(W2) (PRECISE mode)
-    float* w2p_lo = w2p + L * H * H / 2;
-    CUDA_TRY(ctx, launch_flow_pack(f->w2, w2p, w2p_lo, f->n_blocks, cs));
+    if (ctx->flow_blocks != f->n_blocks) ctx->tr_ready = false;   // moments of another architecture
+    ctx->flow_blocks = f->n_blocks;
+    float* w2p = ctx->flow_mem;                   // first: 16-byte (in fact 256-byte) aligned for cp.async.bulk
+    float* w2p_lo = w2p + L * H * H / 2;          // the FP16 remainder W2 - FP16(W2) (PRECISE mode, training)
+    float* par = ctx->flow_mem + L * H * H;
+    CUDA_TRY(ctx, cudaMemcpyAsync(par + P.w1, f->w1, L * H * 4, cudaMemcpyDeviceToDevice, cs));
+    CUDA_TRY(ctx, cudaMemcpyAsync(par + P.b1, f->b1, L * H * 4, cudaMemcpyDeviceToDevice, cs));
+    CUDA_TRY(ctx, cudaMemcpyAsync(par + P.w2, f->w2, L * H * H * 4, cudaMemcpyDeviceToDevice, cs));
+    CUDA_TRY(ctx, cudaMemcpyAsync(par + P.b2, f->b2, L * H * 4, cudaMemcpyDeviceToDevice, cs));
+    CUDA_TRY(ctx, cudaMemcpyAsync(par + P.w3, f->w3, L * 2 * H * 4, cudaMemcpyDeviceToDevice, cs));
+    CUDA_TRY(ctx, cudaMemcpyAsync(par + P.b3, f->b3, L * 2 * 4, cudaMemcpyDeviceToDevice, cs));
+    const float base[4] = {f->base_loc[0], f->base_loc[1], f->base_log_scale[0], f->base_log_scale[1]};
+    CUDA_TRY(ctx, cudaMemcpyAsync(par + P.loc, base, sizeof(base), cudaMemcpyHostToDevice, cs));
+    CUDA_TRY(ctx, cudaStreamSynchronize(cs));     // `base` is a stack array
+    CUDA_TRY(ctx, launch_flow_pack(par + P.w2, w2p, w2p_lo, f->n_blocks, cs));
     FlowDev d{};
-    d.w1 = w1; d.b1 = b1; d.w2p = w2p; d.w2p_lo = w2p_lo; d.b2 = b2; d.w3 = w3; d.b3 = b3;
+    d.w1 = par + P.w1; d.b1 = par + P.b1; d.w2p = w2p; d.w2p_lo = w2p_lo; d.b2 = par + P.b2; d.w3 = par + P.w3; d.b3 = par + P.b3;
     for (int i = 0; i < 2; ++i) {
         d.base_loc[i] = f->base_loc[i];
         d.base_log_scale[i] = f->base_log_scale[i];
@@ -897,6 +913,128 @@ extern "C" int glabc_flow_precision(glabc_ctx* ctx, int32_t mode)
     if (!ctx) return GLABC_ERR_INVALID;
     if (mode != GLABC_FLOW_FAST && mode != GLABC_FLOW_PRECISE) return fail(ctx, GLABC_ERR_INVALID, "glabc_flow_precision: bad mode %d", mode);
     ctx->flow_precision = mode;
+    return GLABC_OK;
+}
+
+// ---- training step (GLMCMC_NFs.py:63,112-124) ----
+static float* flow_params(glabc_ctx* ctx) { return ctx->flow_mem + size_t(ctx->flow_blocks) * kFlowHidden * kFlowHidden; }
+
+extern "C" int64_t glabc_flow_param_count(int32_t n_blocks) { return n_blocks < 1 ? 0 : FlowParamLayout(n_blocks).total; }
+
+extern "C" int glabc_flow_train_init(glabc_ctx* ctx, float lr, float beta1, float beta2, float eps, float weight_decay)
+{
+    if (!ctx) return GLABC_ERR_INVALID;
+    if (!ctx->has_flow) return fail(ctx, GLABC_ERR_INVALID, "no flow bound: call glabc_flow_set first");
+    if (!(lr > 0.0f) || !(beta1 >= 0.0f && beta1 < 1.0f) || !(beta2 >= 0.0f && beta2 < 1.0f) || !(eps > 0.0f) || !(weight_decay >= 0.0f))
+        return fail(ctx, GLABC_ERR_INVALID, "glabc_flow_train_init: bad Adam hyper-parameters");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int64_t total = FlowParamLayout(ctx->flow_blocks).total;
+    if (ctx->tr_mem) cudaFree(ctx->tr_mem);
+    if (ctx->tr_partial) cudaFree(ctx->tr_partial);
+    ctx->tr_mem = ctx->tr_partial = nullptr;
+    ctx->tr_ready = false;
+    CUDA_TRY(ctx, cudaMalloc(&ctx->tr_mem, (3 * size_t(total) + 4) * sizeof(float)));
+    CUDA_TRY(ctx, cudaMemset(ctx->tr_mem, 0, (3 * size_t(total) + 4) * sizeof(float)));
+    ctx->tr_slices = ctx->sm_count > 0 ? ctx->sm_count : 1;
+    CUDA_TRY(ctx, cudaMalloc(&ctx->tr_partial, size_t(ctx->tr_slices) * size_t((total + 3) & ~int64_t(3)) * sizeof(float)));
+    ctx->tr_lr = lr; ctx->tr_beta1 = beta1; ctx->tr_beta2 = beta2; ctx->tr_eps = eps; ctx->tr_wd = weight_decay;
+    ctx->tr_step = 0;
+    ctx->tr_ready = true;
+    return GLABC_OK;
+}
+
+extern "C" int glabc_flow_grad(glabc_ctx* ctx, const float* x, int64_t n, float* grad, float* loss, void* stream)
+{
+    if (!ctx) return GLABC_ERR_INVALID;
+    if (!ctx->has_flow || !ctx->tr_ready) return fail(ctx, GLABC_ERR_INVALID, "glabc_flow_grad: call glabc_flow_set and glabc_flow_train_init first");
+    if (ctx->cc < 100) return fail(ctx, GLABC_ERR_UNSUPPORTED, "the flow kernels need tcgen05 tensor cores (sm_100a); this device is sm_%d", ctx->cc);
+    if (!x || n < 1) return fail(ctx, GLABC_ERR_INVALID, "glabc_flow_grad: null samples / n < 1");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t cs = static_cast<cudaStream_t>(stream);
+    const int64_t total = FlowParamLayout(ctx->flow_blocks).total;
+    if (n > ctx->tr_fwd_cap) {
+        if (ctx->tr_fwd) cudaFree(ctx->tr_fwd);
+        ctx->tr_fwd = nullptr;
+        ctx->tr_fwd_cap = 0;
+        CUDA_TRY(ctx, cudaMalloc(&ctx->tr_fwd, size_t(n) * 3 * sizeof(float)));
+        ctx->tr_fwd_cap = n;
+    }
+    float* z = ctx->tr_fwd;
+    float* lq = ctx->tr_fwd + 2 * n;
+    float* g = grad ? grad : ctx->tr_mem + 2 * total;
+    float* ls = loss ? loss : ctx->tr_mem + 3 * total;
+    // forward: log q(x) and the latent z = f^-1(x), split-precision mode whatever the inference mode is
+    CUDA_TRY(ctx, launch_flow(ctx->flow, false, true, x, n, z, lq, ctx->sm_count, cs));
+    CUDA_TRY(ctx, launch_flow_loss(lq, n, ls, cs));
+    const int64_t chunks = (n + flow_train_chunk_samples() - 1) / flow_train_chunk_samples();
+    const int slices = static_cast<int>(chunks < ctx->tr_slices ? chunks : ctx->tr_slices);
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->tr_partial, 0, size_t(slices) * size_t((total + 3) & ~int64_t(3)) * sizeof(float), cs));
+    CUDA_TRY(ctx, launch_flow_bwd(ctx->flow, z, n, ctx->tr_partial, slices, cs));
+    CUDA_TRY(ctx, launch_flow_grad_reduce(ctx->tr_partial, slices, total, n, g, cs));
+    return GLABC_OK;
+}
+
+extern "C" int glabc_flow_adam_step(glabc_ctx* ctx, const float* grad, const float* loss, void* stream)
+{
+    if (!ctx) return GLABC_ERR_INVALID;
+    if (!ctx->has_flow || !ctx->tr_ready) return fail(ctx, GLABC_ERR_INVALID, "glabc_flow_adam_step: call glabc_flow_set and glabc_flow_train_init first");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t cs = static_cast<cudaStream_t>(stream);
+    const FlowParamLayout P(ctx->flow_blocks);
+    const float* g = grad ? grad : ctx->tr_mem + 2 * P.total;
+    const float* ls = loss ? loss : ctx->tr_mem + 3 * P.total;
+    float host_loss = 0.0f;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&host_loss, ls, sizeof(float), cudaMemcpyDeviceToHost, cs));
+    CUDA_TRY(ctx, cudaStreamSynchronize(cs));
+    if (!std::isfinite(host_loss)) return GLABC_OK;   // GLMCMC_NFs.py:120-121: no backward, and Adam leaves gradient-less parameters alone
+    ctx->tr_step += 1;
+    float* par = flow_params(ctx);
+    CUDA_TRY(ctx, launch_flow_adam(par, ctx->tr_mem, ctx->tr_mem + P.total, g, P.total, ls, ctx->tr_lr, ctx->tr_beta1, ctx->tr_beta2,
+                                   ctx->tr_eps, ctx->tr_wd, ctx->tr_step, cs));
+    // the kernels read W2 packed and the base parameters from the launch descriptor: refresh both
+    const size_t LHH = size_t(ctx->flow_blocks) * kFlowHidden * kFlowHidden;
+    CUDA_TRY(ctx, launch_flow_pack(par + P.w2, ctx->flow_mem, ctx->flow_mem + LHH / 2, ctx->flow_blocks, cs));
+    float base[4];
+    CUDA_TRY(ctx, cudaMemcpyAsync(base, par + P.loc, sizeof(base), cudaMemcpyDeviceToHost, cs));
+    CUDA_TRY(ctx, cudaStreamSynchronize(cs));
+    ctx->flow.base_loc[0] = base[0]; ctx->flow.base_loc[1] = base[1];
+    ctx->flow.base_log_scale[0] = base[2]; ctx->flow.base_log_scale[1] = base[3];
+    return GLABC_OK;
+}
+
+extern "C" int glabc_flow_train_step(glabc_ctx* ctx, const float* x, int64_t n, float* loss, void* stream)
+{
+    int st = glabc_flow_grad(ctx, x, n, nullptr, loss, stream);
+    if (st) return st;
+    return glabc_flow_adam_step(ctx, nullptr, loss, stream);
+}
+
+extern "C" int glabc_flow_get(glabc_ctx* ctx, float* params, void* stream)
+{
+    if (!ctx) return GLABC_ERR_INVALID;
+    if (!ctx->has_flow) return fail(ctx, GLABC_ERR_INVALID, "no flow bound");
+    if (!params) return fail(ctx, GLABC_ERR_INVALID, "glabc_flow_get: null pointer");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaMemcpyAsync(params, flow_params(ctx), size_t(FlowParamLayout(ctx->flow_blocks).total) * sizeof(float), cudaMemcpyDeviceToDevice,
+                                  static_cast<cudaStream_t>(stream)));
+    return GLABC_OK;
+}
+
+/* Adam moments and step count, for checkpoints: state[2 * P] = m | v (device); *step in / out */
+extern "C" int glabc_flow_train_state(glabc_ctx* ctx, float* state, int64_t* step, int32_t restore, void* stream)
+{
+    if (!ctx) return GLABC_ERR_INVALID;
+    if (!ctx->has_flow || !ctx->tr_ready) return fail(ctx, GLABC_ERR_INVALID, "glabc_flow_train_state: no training state");
+    if (!state || !step) return fail(ctx, GLABC_ERR_INVALID, "glabc_flow_train_state: null pointer");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t bytes = 2 * size_t(FlowParamLayout(ctx->flow_blocks).total) * sizeof(float);
+    if (restore) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tr_mem, state, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+        ctx->tr_step = *step;
+    } else {
+        CUDA_TRY(ctx, cudaMemcpyAsync(state, ctx->tr_mem, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+        *step = ctx->tr_step;
+    }
     return GLABC_OK;
 }
 

@@ -642,6 +642,10 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
                 out_theta[idx * 2] = a;
                 out_theta[idx * 2 + 1] = b;
             } else {  // + base.log_prob(z)
+                if (out_theta != nullptr) {   // the latent z = f^-1(x): where the training step's backward sweep starts (flow_train.cuh)
+                    out_theta[idx * 2] = a;
+                    out_theta[idx * 2 + 1] = b;
+                }
                 const float r0 = (a - W.base_loc[0]) / expf(W.base_log_scale[0]);
                 const float r1 = (b - W.base_loc[1]) / expf(W.base_log_scale[1]);
                 lq += c2 - ((W.base_log_scale[0] + 0.5f * (r0 * r0)) + (W.base_log_scale[1] + 0.5f * (r1 * r1)));

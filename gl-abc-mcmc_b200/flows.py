@@ -105,6 +105,46 @@ class RealNVP(nn.Module):
         torch.cuda.current_stream(eng.device).synchronize()   # the staging tensors in `t` may be freed now
         return eng
 
+    # ---- native training step (csrc/flow_train.cuh) ---------------------------------------------------------
+    _FLAT = ("w1", "b1", "w2", "b2", "w3", "b3", "loc", "log_scale")      # FlowParamLayout (include/glabc.h)
+
+    def flat_params(self):
+        return torch.cat([getattr(self, k).detach().reshape(-1).float() for k in self._FLAT])
+
+    def load_flat(self, flat):
+        """copy a flat parameter vector (glabc_flow_get) back into the module's tensors"""
+        off = 0
+        with torch.no_grad():
+            for k in self._FLAT:
+                p = getattr(self, k)
+                p.copy_(flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+
+    def train_init(self, eng=None, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5):
+        """bind the current weights and (re)start Adam in the engine's context (GLMCMC_NFs.py:63)"""
+        eng = self.bind(eng)
+        eng.ctx.check(eng.lib.glabc_flow_train_init(eng.ctx.handle, float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay)))
+        return eng
+
+    def grad(self, x, eng=None):
+        """d forward_kld(x) / d parameters as one flat device tensor + the loss (device scalar): glabc_flow_grad"""
+        eng = eng or get_engine(self.loc.device)
+        x = x.to(eng.device, torch.float32).reshape(-1, 2).contiguous()
+        n_par = int(eng.lib.glabc_flow_param_count(self.n_blocks))
+        g = torch.empty(n_par, device=eng.device)
+        loss = torch.empty(1, device=eng.device)
+        eng.ctx.check(eng.lib.glabc_flow_grad(eng.ctx.handle, eng._ptr(x), x.shape[0], eng._ptr(g), eng._ptr(loss), eng._stream()))
+        return g, loss
+
+    def adam_step(self, g, loss, eng=None, sync_module=True):
+        """one Adam update of the context's master parameters from the flat gradient `g`; the module's tensors follow"""
+        eng = eng or get_engine(self.loc.device)
+        eng.ctx.check(eng.lib.glabc_flow_adam_step(eng.ctx.handle, eng._ptr(g), eng._ptr(loss), eng._stream()))
+        if sync_module:
+            flat = torch.empty_like(g)
+            eng.ctx.check(eng.lib.glabc_flow_get(eng.ctx.handle, eng._ptr(flat), eng._stream()))
+            self.load_flat(flat)
+
     def fused_sample_from(self, eps, eng=None, theta=None, log_q=None, precision=None):
         """`precision`: "precise" / "fast" sets the context's flow precision for this and the following calls (None: keep it)"""
         eng = eng or get_engine(self.loc.device)

@@ -114,6 +114,18 @@ def average_gradients(params):
         off += n
 
 
+def average_flat(grad, loss=None):
+    """mean over the ranks of a flat gradient buffer (glabc_flow_grad's output) and of the loss: one collective each"""
+    _, world = _world()
+    if world == 1:
+        return
+    dist.all_reduce(grad)
+    grad /= world
+    if loss is not None:
+        dist.all_reduce(loss)
+        loss /= world
+
+
 class RoundSync:
     """Keeps the collective sequence of a shared-proposal sampler aligned across ranks.  Every rank calls
     `round_end(local_done)` each time ALL of its chains have consumed their block (or finished); the call returns True

@@ -430,6 +430,29 @@ GLABC_API int glabc_flow_set(glabc_ctx* ctx, const glabc_flow_t* flow, size_t nb
 GLABC_API int glabc_flow_sample(glabc_ctx* ctx, const float* eps, int64_t n, float* theta, float* log_q, void* stream);
 GLABC_API int glabc_flow_log_prob(glabc_ctx* ctx, const float* theta, int64_t n, float* log_q, void* stream);
 
+/* ---- the flow's training step (GLMCMC_NFs.py:63,112-124): loss = NF_model.forward_kld(x) = -mean log q(x), backward through
+ * the coupling blocks, torch.optim.Adam(lr, weight_decay).  The context owns the FP32 master parameters (copied in by
+ * glabc_flow_set) and the Adam moments.  Flat parameter / gradient layout, P = glabc_flow_param_count(n_blocks) floats:
+ *   w1 [L][128] | b1 [L][128] | w2 [L][128][128] | b2 [L][128] | w3 [L][2][128] | b3 [L][2] | base loc [2] | base log_scale [2]
+ *   glabc_flow_train_init   (re)starts training: zero moments, step count 0, Adam hyper-parameters (GLMCMC_NFs.py:63: lr 5e-4,
+ *                           weight_decay 1e-5; betas 0.9 / 0.999 and eps 1e-8 are torch's defaults)
+ *   glabc_flow_grad         x [n][2] (device) -> grad [P] (device; NULL: the context's buffer) = d loss / d parameters, and
+ *                           loss [1] (device; NULL: the context's).  A multi-GPU caller all-reduces `grad` (mean) next.
+ *   glabc_flow_adam_step    one Adam update of the master parameters from `grad` (NULL: the context's buffer), then the
+ *                           kernels' packed weights are refreshed.  Nothing is updated when *loss is NaN / inf: the reference
+ *                           skips backward() then (:120-121) and Adam.step() leaves gradient-less parameters untouched.
+ *   glabc_flow_train_step   = glabc_flow_grad + glabc_flow_adam_step (single GPU)
+ *   glabc_flow_get          the master parameters -> params [P] (device)
+ *   glabc_flow_train_state  save (restore = 0) / load (1) the Adam moments state [2 P] = m | v (device) and *step: with
+ *                           glabc_flow_get / glabc_flow_set this checkpoints a flow in training                            */
+GLABC_API int64_t glabc_flow_param_count(int32_t n_blocks);
+GLABC_API int glabc_flow_train_init(glabc_ctx* ctx, float lr, float beta1, float beta2, float eps, float weight_decay);
+GLABC_API int glabc_flow_grad(glabc_ctx* ctx, const float* x, int64_t n, float* grad, float* loss, void* stream);
+GLABC_API int glabc_flow_adam_step(glabc_ctx* ctx, const float* grad, const float* loss, void* stream);
+GLABC_API int glabc_flow_train_step(glabc_ctx* ctx, const float* x, int64_t n, float* loss, void* stream);
+GLABC_API int glabc_flow_get(glabc_ctx* ctx, float* params, void* stream);
+GLABC_API int glabc_flow_train_state(glabc_ctx* ctx, float* state, int64_t* step, int32_t restore, void* stream);
+
 /* ---- samplers: host buffers (the reference-facing call: H2D state, run, D2H trace + stats) --- */
 /* `run->theta`, `y`, `aux`, `state64`, `trace`, `stats` are HOST pointers here; the trace is copied back in
  * `chunk_steps`-row chunks overlapped with the next chunk's kernel (0 = library default).        */
