@@ -85,10 +85,13 @@ class PooledKDEProposal:
 def AGLMCMC(ABCset, num_ite, Initial_theta, Initial_y, Local_Proposal, Initial_ISIR_prop, filelocation, global_frequency,
             step_size, batch_size, alpha, hat_eps_T, device=None, *, num_chains=None, seed=None, chain_id_base=0, arith="fast",
             trace="chain", return_stats=False, verbose=None, block_threads=0, pooled=False, kde_train=100000,
-            return_proposal=False):
+            return_proposal=False, checkpoint=None, resume=None):
     """Same positional signature as the reference; keyword extensions as in `GlobalMCMC`.  `pooled=True`: all chains (of
     all ranks of the process group) share ONE KernelDensity fitted on `kde_train` pooled weighted draws instead of one KDE
-    per chain — see `PooledKDEProposal`."""
+    per chain — see `PooledKDEProposal`.  `checkpoint=` / `resume=` (per-chain mode): the end-of-run state incl. every chain's
+    candidate block, KernelDensity and eps-hat; a resumed run continues bit-identically (samplers.run_chains)."""
+    if pooled and (checkpoint is not None or resume is not None):
+        raise NotImplementedError("checkpoint / resume: per-chain AGLMCMC (pooled=False)")
     if not 1 <= int(batch_size) <= _abi.MAX_K:
         raise ValueError(f"batch_size must be in 1..{_abi.MAX_K}")
     if int(step_size) < 1 or int(step_size) * int(batch_size) > _abi.AG_MAX_BLOCK:
@@ -110,4 +113,4 @@ def AGLMCMC(ABCset, num_ite, Initial_theta, Initial_y, Local_Proposal, Initial_I
     return run_chains("aglmcmc", eng, pod, num_ite=num_ite, Initial_theta=Initial_theta, Initial_y=Initial_y,
                       global_frequency=global_frequency, filelocation=filelocation, num_chains=num_chains, seed=seed,
                       chain_id_base=chain_id_base, arith=arith, trace=trace, return_stats=return_stats, verbose=verbose,
-                      K=int(batch_size), block_threads=block_threads, ag=ag)
+                      K=int(batch_size), block_threads=block_threads, ag=ag, checkpoint=checkpoint, resume=resume)

@@ -24,8 +24,10 @@ def GLMALA(ABCset, num_ite, Initial_theta, Initial_y, tau, num_grad, filelocatio
     eng = get_engine(device)
     pod = eng.bind_model(ABCset)
     eng.bind_proposal(_abi.SLOT_IMPORTANCE, Importance_Proposal)
-    c = num_chains if num_chains is not None else torch.as_tensor(Initial_theta).reshape(-1, pod.theta_dim).shape[0]
-    state64 = torch.zeros(c, _abi.STATE64_SLOTS, dtype=torch.float64, device=eng.device)
+    state64 = None      # resume: the carried float64 state comes from the checkpoint (Initial_theta / Initial_y are not read)
+    if resume is None:
+        c = num_chains if num_chains is not None else torch.as_tensor(Initial_theta).reshape(-1, pod.theta_dim).shape[0]
+        state64 = torch.zeros(c, _abi.STATE64_SLOTS, dtype=torch.float64, device=eng.device)
     return run_chains("mala", eng, pod, num_ite=num_ite, Initial_theta=Initial_theta, Initial_y=Initial_y,
                       global_frequency=global_frequency, filelocation=filelocation, num_chains=num_chains, seed=seed,
                       chain_id_base=chain_id_base, arith=arith, trace=trace, return_stats=return_stats, verbose=verbose,

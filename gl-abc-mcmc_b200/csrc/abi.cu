@@ -40,7 +40,7 @@ struct glabc_ctx {
     size_t state64_cap = 0;
     // AGLMCMC block / KDE workspace (one allocation), KDE sampling scratch of the public entry points
     void* ag_mem = nullptr;
-    size_t ag_bytes = 0;
+    size_t ag_bytes = 0, ag_used = 0;
     AgWorkspace ag{};
     int ag_dim = 0;
     double* kde_cdf = nullptr;
@@ -413,7 +413,7 @@ static int make_run_params(glabc_ctx* ctx, const glabc_run_t* run, int dim, int 
 // ---------------------------------------------------------------------------------------------
 // sampler dispatch (device buffers)
 // ---------------------------------------------------------------------------------------------
-enum SamplerKind { SAMPLER_GLOBAL = 0, SAMPLER_ISIR = 1, SAMPLER_MALA = 2 };
+enum SamplerKind { SAMPLER_GLOBAL = 0, SAMPLER_ISIR = 1, SAMPLER_MALA = 2, SAMPLER_AGLMCMC = 3 };
 
 static int run_device(glabc_ctx* ctx, SamplerKind kind, const glabc_run_t* run)
 {
@@ -549,7 +549,7 @@ static int ensure_host_scratch(glabc_ctx* ctx, size_t state_floats, size_t trace
     return GLABC_OK;
 }
 
-static int run_host(glabc_ctx* ctx, SamplerKind kind, const glabc_run_t* run, int64_t chunk_steps)
+static int run_host(glabc_ctx* ctx, SamplerKind kind, const glabc_run_t* run, int64_t chunk_steps, const glabc_aglmcmc_t* ag = nullptr)
 {
     if (!ctx) return GLABC_ERR_INVALID;
     if (!ctx->has_model) return fail(ctx, GLABC_ERR_INVALID, "no model bound: call glabc_model_set first");
@@ -631,7 +631,17 @@ static int run_host(glabc_ctx* ctx, SamplerKind kind, const glabc_run_t* run, in
             dev.trace_chain_off = 0;
             dev.trace_row_base = row_lo;
         }
-        st = run_device(ctx, kind, &dev);
+        if (kind == SAMPLER_AGLMCMC) {   // the first chunk starts the run (initial block), the others continue from the workspace
+            glabc_aglmcmc_t a = *ag;
+            a.init = first_chunk ? ag->init : 0;
+            a.init_p = a.init_s = a.ad_noise = a.ad_sim = nullptr;
+            a.ad_idx = nullptr;
+            a.ad_rec = a.ad_blk = a.init_w = nullptr;
+            a.tape_rounds = a.dump_rounds = 0;
+            st = glabc_run_aglmcmc(ctx, &dev, &a);
+        } else {
+            st = run_device(ctx, kind, &dev);
+        }
         if (st) return st;
         if (traced && n_rows > 0) {
             CUDA_TRY(ctx, cudaEventRecord(ctx->ev_done[b], sc));
@@ -695,6 +705,7 @@ static int ensure_ag_workspace(glabc_ctx* ctx, int64_t C, int32_t B, int d, bool
         CUDA_TRY(ctx, cudaMalloc(&ctx->ag_mem, off));
         ctx->ag_bytes = off;
     }
+    ctx->ag_used = off;
     char* m = static_cast<char*>(ctx->ag_mem);
     AgWorkspace& W = ctx->ag;
     W.blk_theta = reinterpret_cast<float*>(m + o_bt); W.blk_x = reinterpret_cast<float*>(m + o_bx);
@@ -759,6 +770,32 @@ extern "C" int glabc_run_aglmcmc(glabc_ctx* ctx, const glabc_run_t* run, const g
               ag->dump_rounds};
     CUDA_TRY(ctx, launch_aglmcmc(K, ctx->ag, T, R, d, ag->init, ag->kde_rule, run->arith_mode == GLABC_ARITH_STRICT, replay,
                                  run->trace_layout, block, static_cast<cudaStream_t>(run->stream)));
+    return GLABC_OK;
+}
+
+/* the workspace of glabc_run_aglmcmc (every chain's candidate block, per-chain KDE, counters, eps-hat) as an opaque blob */
+extern "C" int glabc_aglmcmc_state(glabc_ctx* ctx, void* blob, int64_t* bytes, int64_t n_chains, int32_t block, int32_t restore, void* stream)
+{
+    if (!ctx) return GLABC_ERR_INVALID;
+    if (!ctx->has_model) return fail(ctx, GLABC_ERR_INVALID, "no model bound: call glabc_model_set first");
+    if (!bytes) return fail(ctx, GLABC_ERR_INVALID, "glabc_aglmcmc_state: null size pointer");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int d = ctx->model.theta_dim;
+    if (!restore) {
+        if (!ctx->ag_mem || ctx->ag_used == 0) return fail(ctx, GLABC_ERR_INVALID, "glabc_aglmcmc_state: the context holds no AGLMCMC workspace");
+        if (!blob) { *bytes = static_cast<int64_t>(ctx->ag_used); return GLABC_OK; }     // size query
+        if (*bytes < static_cast<int64_t>(ctx->ag_used)) return fail(ctx, GLABC_ERR_INVALID, "glabc_aglmcmc_state: blob too small");
+        CUDA_TRY(ctx, cudaMemcpyAsync(blob, ctx->ag_mem, ctx->ag_used, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+        *bytes = static_cast<int64_t>(ctx->ag_used);
+        return GLABC_OK;
+    }
+    if (!blob || n_chains < 1 || block < 1 || block > GLABC_AG_MAX_BLOCK) return fail(ctx, GLABC_ERR_INVALID, "glabc_aglmcmc_state: bad blob / sizes");
+    int st = ensure_ag_workspace(ctx, n_chains, block, d, false);
+    if (st) return st;
+    if (*bytes != static_cast<int64_t>(ctx->ag_used))
+        return fail(ctx, GLABC_ERR_INVALID, "glabc_aglmcmc_state: blob of %lld bytes, a workspace of %lld chains x block %d takes %zu",
+                    (long long)*bytes, (long long)n_chains, block, ctx->ag_used);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ag_mem, blob, ctx->ag_used, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
     return GLABC_OK;
 }
 
@@ -1632,6 +1669,13 @@ int glabc_run_mala(glabc_ctx* ctx, const glabc_run_t* run) { return run_device(c
 int glabc_run_mala_host(glabc_ctx* ctx, const glabc_run_t* run, int64_t chunk_steps)
 {
     return run_host(ctx, SAMPLER_MALA, run, chunk_steps);
+}
+
+int glabc_run_aglmcmc_host(glabc_ctx* ctx, const glabc_run_t* run, const glabc_aglmcmc_t* ag, int64_t chunk_steps)
+{
+    if (!ctx) return GLABC_ERR_INVALID;
+    if (!ag) return fail(ctx, GLABC_ERR_INVALID, "null aglmcmc description");
+    return run_host(ctx, SAMPLER_AGLMCMC, run, chunk_steps, ag);
 }
 
 int glabc_resample(glabc_ctx* ctx, const float* W, int64_t n, int64_t N, float u0, int64_t* idx, uint64_t* count, void* stream)

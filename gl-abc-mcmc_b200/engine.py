@@ -237,7 +237,7 @@ class Engine:
 
     def run_host(self, sampler, *, theta, y, n_steps, gf, trace, step_base=0, chain_id_base=0, seed=0,
                  arith=_abi.ARITH_FAST, trace_layout=_abi.TRACE_TIME_MAJOR, write_row0=True, stats=None,
-                 aux=None, K=0, chunk_steps=0, block_threads=0, num_grad=0, tau=0.0, state64=None):
+                 aux=None, K=0, chunk_steps=0, block_threads=0, num_grad=0, tau=0.0, state64=None, ag=None):
         """The reference-facing call on HOST buffers (numpy-compatible CPU tensors, ideally pinned):
         H2D of the state, kernels, D2H of trace/state/stats — returns when the host buffers hold the
         result."""
@@ -260,9 +260,28 @@ class Engine:
                         trace_chain_off=0, trace_row_base=0, theta=self._ptr(theta), y=self._ptr(y),
                         aux=self._ptr(aux), trace=self._ptr(trace), stats=self._ptr(stats), num_grad=int(num_grad),
                         tau=float(tau), tau64=float(tau), state64=self._ptr(state64))
+        if sampler == "aglmcmc":
+            if ag is None:
+                raise ValueError("run_host('aglmcmc') needs the glabc_aglmcmc_t description (Engine.aglmcmc_params)")
+            self.ctx.check(self.lib.glabc_run_aglmcmc_host(self.ctx.handle, C.byref(r), C.byref(ag), int(chunk_steps)))
+            return trace
         fn = getattr(self.lib, f"glabc_run_{sampler}_host")
         self.ctx.check(fn(self.ctx.handle, C.byref(r), int(chunk_steps)))
         return trace
+
+    def aglmcmc_state(self):
+        """the context's AGLMCMC workspace (candidate blocks, per-chain KDEs, counters, eps-hat) as a uint8 device tensor"""
+        n = C.c_int64(0)
+        self.ctx.check(self.lib.glabc_aglmcmc_state(self.ctx.handle, None, C.byref(n), 0, 0, 0, self._stream()))
+        blob = torch.empty(n.value, dtype=torch.uint8, device=self.device)
+        self.ctx.check(self.lib.glabc_aglmcmc_state(self.ctx.handle, self._ptr(blob), C.byref(n), 0, 0, 0, self._stream()))
+        return blob
+
+    def aglmcmc_restore(self, blob, n_chains, block):
+        blob = blob.to(self.device).contiguous()
+        n = C.c_int64(blob.numel())
+        self.ctx.check(self.lib.glabc_aglmcmc_state(self.ctx.handle, self._ptr(blob), C.byref(n), int(n_chains), int(block), 1, self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()
 
     def flow_precision(self, mode):
         """operand precision of the flow's hidden layer for the following glabc_flow_sample / glabc_flow_log_prob calls of this

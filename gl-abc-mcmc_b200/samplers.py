@@ -77,14 +77,14 @@ def print_summary(chain):
 CHECKPOINT_VERSION = 1
 
 
-def save_checkpoint(path, *, sampler, step_base, seed, chain_id_base, theta, y, stats, aux=None, state64=None):
+def save_checkpoint(path, *, sampler, step_base, seed, chain_id_base, theta, y, stats, aux=None, state64=None, ag_state=None):
     """Everything a run needs to continue bit-identically: the chain state, the carried iSIR / MALA
     state, the statistics accumulators and the Philox coordinates (seed, global chain id base, next step index) — the
     generator itself is stateless, so no RNG state exists beyond these three integers."""
     cpu = lambda t: None if t is None else t.detach().cpu()  # noqa: E731
     torch.save(dict(version=CHECKPOINT_VERSION, sampler=sampler, step_base=int(step_base), seed=int(seed),
                     chain_id_base=int(chain_id_base), theta=cpu(theta), y=cpu(y), stats=cpu(stats), aux=cpu(aux),
-                    state64=cpu(state64)), path)
+                    state64=cpu(state64), ag_state=cpu(ag_state)), path)
 
 
 def load_checkpoint(path_or_dict, sampler, device):
@@ -94,7 +94,8 @@ def load_checkpoint(path_or_dict, sampler, device):
     if ck["sampler"] != sampler:
         raise ValueError(f"checkpoint was written by the {ck['sampler']!r} sampler, not {sampler!r}")
     dev = lambda t: None if t is None else t.to(device).contiguous()  # noqa: E731
-    return dict(ck, theta=dev(ck["theta"]), y=dev(ck["y"]), stats=dev(ck["stats"]), aux=dev(ck["aux"]), state64=dev(ck["state64"]))
+    return dict(ck, theta=dev(ck["theta"]), y=dev(ck["y"]), stats=dev(ck["stats"]), aux=dev(ck["aux"]), state64=dev(ck["state64"]),
+                ag_state=dev(ck.get("ag_state")))
 
 
 def run_chains(sampler, eng, model_pod, *, num_ite, Initial_theta, Initial_y, global_frequency, filelocation,
@@ -105,11 +106,11 @@ def run_chains(sampler, eng, model_pod, *, num_ite, Initial_theta, Initial_y, gl
     only the NEW rows (iterations step_base + 1 .. num_ite - 1)."""
     if num_ite < 1:
         raise ValueError("num_ite must be at least 1")
+    if trace not in _LAYOUT:
+        raise ValueError(f"trace must be one of {sorted(_LAYOUT)}")
     d = model_pod.theta_dim
     step_base = 0
     if resume is not None:
-        if sampler == "aglmcmc":
-            raise NotImplementedError("AGLMCMC keeps its candidate block and KDE inside the context: not checkpointed yet")
         ck = load_checkpoint(resume, sampler, eng.device)
         theta, y, stats, aux, step_base = ck["theta"], ck["y"], ck["stats"], ck["aux"], ck["step_base"]
         seed, chain_id_base, c = ck["seed"], ck["chain_id_base"], ck["theta"].shape[0]
@@ -119,6 +120,12 @@ def run_chains(sampler, eng, model_pod, *, num_ite, Initial_theta, Initial_y, gl
             raise ValueError(f"the checkpoint is already at iteration {step_base}")
         if "state64" in sampler_kw:
             sampler_kw["state64"] = ck["state64"]
+        if sampler == "aglmcmc":     # the chains' candidate blocks, KDEs, counters and eps-hat live in the context's workspace
+            if ck.get("ag_state") is None:
+                raise ValueError("the checkpoint holds no AGLMCMC workspace")
+            ag = sampler_kw["ag"]
+            eng.aglmcmc_restore(ck["ag_state"], c, int(K) * int(ag.step_size))
+            ag.init = 0
     else:
         seed = default_seed() if seed is None else int(seed)
         theta, y, c = initial_state(eng, model_pod, Initial_theta, Initial_y, num_chains, seed)
@@ -138,10 +145,9 @@ def run_chains(sampler, eng, model_pod, *, num_ite, Initial_theta, Initial_y, gl
                   chain_id_base=chain_id_base, arith=_ARITH[arith], trace_layout=layout, stats=stats, aux=aux, K=K,
                   block_threads=block_threads, **resumed, **sampler_kw)
     if checkpoint is not None:
-        if sampler == "aglmcmc":
-            raise NotImplementedError("AGLMCMC keeps its candidate block and KDE inside the context: not checkpointed yet")
         save_checkpoint(checkpoint, sampler=sampler, step_base=num_ite - 1, seed=seed, chain_id_base=chain_id_base, theta=theta,
-                        y=y, stats=stats, aux=aux, state64=sampler_kw.get("state64"))
+                        y=y, stats=stats, aux=aux, state64=sampler_kw.get("state64"),
+                        ag_state=eng.aglmcmc_state() if sampler == "aglmcmc" else None)
     rs = RunStats(stats, d)
     if single:
         chain = (out[0] if layout == _abi.TRACE_CHAIN_MAJOR else out[:, 0]).cpu() if out is not None else None
@@ -153,7 +159,7 @@ def run_chains(sampler, eng, model_pod, *, num_ite, Initial_theta, Initial_y, gl
     else:
         if filelocation is not None and out is not None:
             np.save(filelocation if str(filelocation).endswith(".npy") else str(filelocation) + ".npy", out.cpu().numpy())
-        if verbose:
-            print_summary(out.reshape(-1, d) if layout != _abi.TRACE_TIME_MAJOR else out.reshape(-1, d))
+        if verbose and out is not None:
+            print_summary(out.reshape(-1, d))
         result = out
     return (result, rs) if return_stats else result

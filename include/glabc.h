@@ -459,6 +459,15 @@ GLABC_API int glabc_flow_train_state(glabc_ctx* ctx, float* state, int64_t* step
 GLABC_API int glabc_run_global_host(glabc_ctx* ctx, const glabc_run_t* run, int64_t chunk_steps);
 GLABC_API int glabc_run_isir_host(glabc_ctx* ctx, const glabc_run_t* run, int64_t chunk_steps);
 GLABC_API int glabc_run_mala_host(glabc_ctx* ctx, const glabc_run_t* run, int64_t chunk_steps);
+/* AGLMCMC.py:124-272 on host buffers: the chains' candidate blocks and KDEs stay in the context's workspace; the run is cut
+ * into time chunks (ag->init applies to the first, the others continue) and each chunk's rows travel while the next one runs */
+GLABC_API int glabc_run_aglmcmc_host(glabc_ctx* ctx, const glabc_run_t* run, const glabc_aglmcmc_t* ag, int64_t chunk_steps);
+/* Checkpoint of glabc_run_aglmcmc's workspace (every chain's block of candidates, its KernelDensity, counters and eps-hat) as an
+ * opaque device blob.  restore = 0: blob == NULL returns the size in *bytes, otherwise the workspace is copied out; restore = 1:
+ * a workspace for n_chains x block (= batch_size * step_size) is set up from the blob, ready for glabc_run_aglmcmc with
+ * ag->init = 0 and run->step_base = the iterations already done (bit-identical continuation).                          */
+GLABC_API int glabc_aglmcmc_state(glabc_ctx* ctx, void* blob, int64_t* bytes, int64_t n_chains, int32_t block, int32_t restore,
+                                  void* stream);
 
 /* ---- diagnostics --------------------------------------------------------------------------- */
 /* esjd(), ESJD.py:2-25, for every chain of a device trace: out[c] = det(D^T D/(N-1))^(1/d).

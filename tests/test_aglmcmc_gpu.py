@@ -282,3 +282,39 @@ def test_kde_logprob_large_batch_paths(eng):
         fast = eng.kde_log_prob(X, wn, bw, x, arith=abi.ARITH_FAST)
         strict = eng.kde_log_prob(X, wn, bw, x, arith=abi.ARITH_STRICT)
         assert float((fast - strict).abs().max()) < 2e-4
+
+
+def test_checkpoint_resume_and_host_entry_are_bit_identical(tmp_path):
+    """SURVEY.md 8(f) n4 for AGLMCMC: the end-of-run state incl. every chain's candidate block, KernelDensity, counters and
+    eps-hat (glabc_aglmcmc_state) — a run cut in two continues bit-identically through further adaptations; and the
+    host-buffer entry glabc_run_aglmcmc_host (time chunks, the workspace carried from chunk to chunk) delivers the same chains."""
+    import glabc_b200 as g
+    from glabc_b200.engine import get_engine
+    model = g.Mixture_set(0.05)
+    lp = g.DiagGaussian(2, torch.zeros(1, 2), torch.log(torch.tensor([0.35, 0.35])))
+    ip = g.DiagGaussian(2, torch.zeros(2), torch.zeros(2))
+    C, T, T1, S, K = 300, 401, 173, 20, 5
+    run = lambda n, **kw: g.AGLMCMC(model, n, torch.zeros(2), None, lp, ip, None, 0.8, S, K, 0.8, 0.2, num_chains=C, seed=9,   # noqa: E731
+                                    trace="time", return_stats=True, **kw)
+    full, st_full = run(T)
+    ck = tmp_path / "ag.pt"
+    first, _ = run(T1, checkpoint=str(ck))
+    rest, st_rest = run(T, resume=str(ck))
+    assert torch.equal(first, full[:T1]) and torch.equal(rest, full[T1:])
+    assert torch.equal(st_rest.raw[:, :4], st_full.raw[:, :4]) and torch.allclose(st_rest.raw, st_full.raw, rtol=1e-4, atol=1e-3)
+    assert float(st_full.move_rate.mean()) > 0.01
+    # host entry: pinned host buffers, 64-row chunks
+    eng = get_engine()
+    eng.bind_model(model)
+    eng.bind_proposal(abi.SLOT_LOCAL, lp)
+    eng.bind_proposal(abi.SLOT_IMPORTANCE, ip)
+    from glabc_b200.samplers import initial_state
+    th0, y0, _ = initial_state(eng, eng.bind_model(model), torch.zeros(2), None, C, 9)
+    h_th, h_y = th0.cpu().contiguous(), y0.cpu().contiguous()
+    h_stats = torch.zeros(C, abi.nstats(2))
+    h_trace = torch.zeros(T, C, 2).pin_memory()
+    ag = eng.aglmcmc_params(step_size=S, alpha=0.8, hat_eps_T=0.2)
+    eng.run_host("aglmcmc", theta=h_th, y=h_y, n_steps=T - 1, gf=0.8, seed=9, trace=h_trace, trace_layout=abi.TRACE_TIME_MAJOR,
+                 stats=h_stats, K=K, ag=ag, chunk_steps=64)
+    assert torch.equal(h_trace, full.cpu())
+    assert torch.equal(h_stats[:, :4], st_full.raw.cpu()[:, :4]) and torch.allclose(h_stats, st_full.raw.cpu(), rtol=1e-4, atol=1e-3)
