@@ -45,6 +45,17 @@ class PooledKDEProposal:
                                                          torch.tensor(list(pod.prior_log_scale)[:d])))
         self.floor = math.log(1e-10)
 
+    def state_dict(self):
+        """the pooled KernelDensity (points, normalised weights, bandwidth), eps-hat, the generator of the training draws"""
+        kde = None if self.kde is None else tuple(t.cpu() for t in self.kde)
+        return dict(kde=kde, hat_eps=self.hat_eps, gen=self.gen.get_state(), history=list(self.history))
+
+    def load_state_dict(self, sd):
+        self.kde = None if sd["kde"] is None else tuple(t.to(self.eng.device).contiguous() for t in sd["kde"])
+        self.hat_eps = float(sd["hat_eps"])
+        self.gen.set_state(sd["gen"])
+        self.history = list(sd["history"])
+
     def fill(self, blk_theta, blk_lq, rnd):
         c, B, d = blk_theta.shape
         s = (self.seed + 0x632BE5AB * (rnd + 1)) & 0x7FFFFFFFFFFFFFFF
@@ -89,9 +100,8 @@ def AGLMCMC(ABCset, num_ite, Initial_theta, Initial_y, Local_Proposal, Initial_I
     """Same positional signature as the reference; keyword extensions as in `GlobalMCMC`.  `pooled=True`: all chains (of
     all ranks of the process group) share ONE KernelDensity fitted on `kde_train` pooled weighted draws instead of one KDE
     per chain — see `PooledKDEProposal`.  `checkpoint=` / `resume=` (per-chain mode): the end-of-run state incl. every chain's
-    candidate block, KernelDensity and eps-hat; a resumed run continues bit-identically (samplers.run_chains)."""
-    if pooled and (checkpoint is not None or resume is not None):
-        raise NotImplementedError("checkpoint / resume: per-chain AGLMCMC (pooled=False)")
+    candidate block, KernelDensity and eps-hat (pooled mode: the shared KDE); a resumed run continues bit-identically."""
+
     if not 1 <= int(batch_size) <= _abi.MAX_K:
         raise ValueError(f"batch_size must be in 1..{_abi.MAX_K}")
     if int(step_size) < 1 or int(step_size) * int(batch_size) > _abi.AG_MAX_BLOCK:
@@ -106,7 +116,8 @@ def AGLMCMC(ABCset, num_ite, Initial_theta, Initial_y, Local_Proposal, Initial_I
         prop = PooledKDEProposal(eng, pod, alpha, hat_eps_T, kde_train, seed, chain_id_base)
         result, rs, _ = run_block_isir(eng, pod, prop, num_ite=num_ite, theta=theta, y=y, K=int(batch_size), S=int(step_size),
                                        gf=global_frequency, seed=seed, chain_id_base=chain_id_base, arith=arith, trace=trace,
-                                       single=num_chains is None and c == 1, filelocation=filelocation, verbose=verbose)
+                                       single=num_chains is None and c == 1, filelocation=filelocation, verbose=verbose,
+                                       checkpoint=checkpoint, resume=resume)
         extra = ((rs,) if return_stats else ()) + ((prop,) if return_proposal else ())
         return (result,) + extra if extra else result
     ag = eng.aglmcmc_params(step_size=step_size, alpha=alpha, hat_eps_T=hat_eps_T)

@@ -59,6 +59,38 @@ class FlowProposal:
             self.opt = torch.optim.Adam(flow.parameters(), lr=lr, weight_decay=weight_decay)
             flow.bind(eng)
 
+    def state_dict(self):
+        """flow weights, Adam moments + step count (glabc_flow_get / glabc_flow_train_state), the generator of the base normals"""
+        eng, flow = self.eng, self.flow
+        sd = dict(train=self.train, params=flow.flat_params().cpu(), gen=self.gen.get_state(), losses=list(self.losses))
+        if self.train == "native":
+            import ctypes as C
+            mom = torch.empty(2 * sd["params"].numel(), device=eng.device)
+            step = C.c_int64(0)
+            eng.ctx.check(eng.lib.glabc_flow_train_state(eng.ctx.handle, eng._ptr(mom), C.byref(step), 0, eng._stream()))
+            sd.update(moments=mom.cpu(), step=int(step.value))
+        else:
+            sd.update(opt=self.opt.state_dict())
+        return sd
+
+    def load_state_dict(self, sd):
+        import ctypes as C
+        eng, flow = self.eng, self.flow
+        if sd["train"] != self.train:
+            raise ValueError(f"the checkpoint was trained with flow_train={sd['train']!r}")
+        flow.load_flat(sd["params"].to(eng.device))
+        self.gen.set_state(sd["gen"])
+        self.losses = list(sd["losses"])
+        if self.train == "native":
+            flow.bind(eng)                                   # the restored weights into the context (moments are kept: same architecture)
+            mom = sd["moments"].to(eng.device).contiguous()
+            step = C.c_int64(sd["step"])
+            eng.ctx.check(eng.lib.glabc_flow_train_state(eng.ctx.handle, eng._ptr(mom), C.byref(step), 1, eng._stream()))
+            torch.cuda.current_stream(eng.device).synchronize()
+        else:
+            self.opt.load_state_dict(sd["opt"])
+            flow.bind(eng)
+
     def fill(self, blk_theta, blk_lq, rnd):     # NF_model.sample, GLMCMC_NFs.py:72,127
         c, B, d = blk_theta.shape
         eps = torch.randn(c * B, d, generator=self.gen, device=self.eng.device)
@@ -102,13 +134,15 @@ def _base_params(base):
 def GLMCMC_NF(ABCset, num_ite, Initial_theta, Initial_y, Local_Proposal, filelocation, global_frequency, step_size, batch_size,
               base, Train_step, *, num_chains=None, seed=None, chain_id_base=0, arith="fast", trace="chain", return_stats=False,
               verbose=None, device=None, n_blocks=32, train_batch=65536, lr=5e-4, weight_decay=1e-5, flow=None,
-              return_flow=False, flow_precision="precise", flow_train="native"):
+              return_flow=False, flow_precision="precise", flow_train="native", checkpoint=None, resume=None):
     """Same positional signature and return value as the reference for one chain; keyword extensions as in `GlobalMCMC`,
     plus `flow` (continue with a given RealNVP), `train_batch` (pooled resample size), `return_flow` and `flow_precision`:
     "precise" (default — the flow's log-densities agree with the reference's float32 network to 1e-5, three tensor-core MMAs per
     hidden layer) or "fast" (single FP16 operands, ~3x the flow throughput, 1e-3-class agreement; importance weights stay exact
     either way because sample() returns the density of the map it applied); `flow_train`: "native" (the training step as
-    kernels of the extension, the default) or "torch" (the fp32 autograd restatement, kept as the tests' checker)."""
+    kernels of the extension, the default) or "torch" (the fp32 autograd restatement, kept as the tests' checker);
+    `checkpoint=` / `resume=`: the end-of-run state incl. the candidate blocks, the flow's weights and its Adam moments — a
+    resumed run continues bit-identically (block_isir.run_block_isir)."""
     if num_ite < 1:
         raise ValueError("num_ite must be at least 1")
     K, S = int(batch_size), int(step_size)
@@ -132,6 +166,7 @@ def GLMCMC_NF(ABCset, num_ite, Initial_theta, Initial_y, Local_Proposal, fileloc
     prop = FlowProposal(flow, eng, seed, chain_id_base, train_batch, lr, weight_decay, precision=flow_precision, train=flow_train)
     result, rs, _ = run_block_isir(eng, pod, prop, num_ite=num_ite, theta=theta, y=y, K=K, S=S, gf=global_frequency, seed=seed,
                                    chain_id_base=chain_id_base, arith=arith, trace=trace, single=single,
-                                   filelocation=filelocation, verbose=verbose, max_adapt=int(Train_step))
+                                   filelocation=filelocation, verbose=verbose, max_adapt=int(Train_step), checkpoint=checkpoint,
+                                   resume=resume)
     extra = ((rs,) if return_stats else ()) + ((flow, prop.losses) if return_flow else ())
     return (result,) + extra if extra else result

@@ -40,12 +40,40 @@ class Block:
                                      lq_cur=self.lq_cur.data_ptr(), lq_valid=self.lq_valid.data_ptr())
 
 
+BLOCK_CHECKPOINT_VERSION = 1
+_BLOCK_TENSORS = ("theta", "x", "w", "lq", "kk", "pending", "lq_valid", "next_step", "lq_cur")
+
+
 def run_block_isir(eng, pod, proposal, *, num_ite, theta, y, K, S, gf, seed, chain_id_base, arith, trace, single,
-                   filelocation, verbose, max_adapt=None):
-    """Advance every chain by num_ite - 1 iterations.  Returns (result, RunStats, rounds)."""
+                   filelocation, verbose, max_adapt=None, checkpoint=None, resume=None):
+    """Advance every chain to iteration num_ite - 1.  Returns (result, RunStats, rounds).
+    `checkpoint=path` writes the end-of-run state: chain state, statistics, every chain's candidate block and counters, the
+    round / adaptation counters, the proposal's own state (`proposal.state_dict()`: flow weights + Adam moments, or the pooled
+    KDE) and the host generators the adaptation draws from; `resume=path` continues from exactly that state (the returned trace
+    then holds only the new rows).  The blocks of ALL chains are refilled when every chain has finished or consumed its block,
+    so the iteration at which a run is cut is part of that schedule: a cut-and-resumed run equals the uncut one when the chains
+    consume their blocks in step (global_frequency = 1; tested), and is a deterministic function of the checkpoint otherwise."""
     c, d = theta.shape
     dev = eng.device
     blk = Block(c, K, S, d, pod.y_dim, dev)
+    done0, rnd, n_adapt = 0, 0, 0
+    stats = torch.zeros(c, _abi.nstats(d), device=dev)
+    if resume is not None:
+        ck = resume if isinstance(resume, dict) else torch.load(resume, map_location="cpu", weights_only=False)
+        if ck.get("version") != BLOCK_CHECKPOINT_VERSION or ck.get("kind") != type(proposal).__name__:
+            raise ValueError("not a block-iSIR checkpoint of this sampler")
+        if ck["theta"].shape != theta.shape or (ck["K"], ck["S"]) != (K, S):
+            raise ValueError("the checkpoint was written for another number of chains / block shape")
+        theta.copy_(ck["theta"])
+        y.copy_(ck["y"])
+        stats.copy_(ck["stats"])
+        for name in _BLOCK_TENSORS:
+            getattr(blk, name).copy_(ck["blk"][name])
+        done0, rnd, n_adapt, seed, chain_id_base = ck["done"], ck["rnd"], ck["n_adapt"], ck["seed"], ck["chain_id_base"]
+        if num_ite - 1 < done0:
+            raise ValueError(f"the checkpoint is already at iteration {done0}")
+        proposal.load_state_dict(ck["proposal"])
+        torch.set_rng_state(ck["torch_rng"])
     common = dict(theta=theta, y=y, gf=gf, seed=seed, chain_id_base=chain_id_base, K=K, blk=blk.pod)
 
     def refill(rnd):    # GLMCMC_NFs.py:70-85,125-140 / AGLMCMC.py:84-112,219-249
@@ -60,20 +88,24 @@ def run_block_isir(eng, pod, proposal, *, num_ite, theta, y, K, S, gf, seed, cha
             blk.lq_cur[idx] = proposal.log_prob(theta[idx])
             blk.lq_valid[idx] = 1
 
-    refill(0)
-    refresh_lq()
+    if resume is None:
+        refill(0)
+        refresh_lq()
     layout = _LAYOUT[trace]
-    n_steps = num_ite - 1
+    n_steps = num_ite - 1                       # absolute index of the last iteration (chains carry their own next_step)
+    rows = num_ite if resume is None else n_steps - done0
+    if rows == 0:
+        layout = _abi.TRACE_NONE
     out = None
     if layout != _abi.TRACE_NONE:
-        out = torch.empty((num_ite, c, d) if layout == _abi.TRACE_TIME_MAJOR else (c, num_ite, d), device=dev)
-    stats = torch.zeros(c, _abi.nstats(d), device=dev)
+        out = torch.empty((rows, c, d) if layout == _abi.TRACE_TIME_MAJOR else (c, rows, d), device=dev)
     world = _world()[1]
     sync = RoundSync(dev)
-    rnd, first, n_adapt = 0, True, 0
+    first = resume is None
+    window = dict(step_base=done0, trace_row_base=0 if resume is None else done0 + 1, trace_rows=rows)
     while True:
-        eng.run("block_isir", n_steps=n_steps, arith=_ARITH[arith], trace_layout=layout, trace=out, trace_rows=num_ite,
-                write_row0=first, stats=stats, **common)
+        eng.run("block_isir", n_steps=n_steps - done0, arith=_ARITH[arith], trace_layout=layout, trace=out,
+                write_row0=first, stats=stats, **window, **common)
         first = False
         need = (blk.pending & 2) != 0
         settled = (blk.next_step > n_steps) | ((blk.pending & 1) != 0)
@@ -94,6 +126,12 @@ def run_block_isir(eng, pod, proposal, *, num_ite, theta, y, K, S, gf, seed, cha
                 refresh_lq()
                 blk.kk.zero_()
                 blk.pending.zero_()
+    if checkpoint is not None:
+        cpu = lambda t: t.detach().cpu()  # noqa: E731
+        torch.save(dict(version=BLOCK_CHECKPOINT_VERSION, kind=type(proposal).__name__, K=K, S=S, done=n_steps, rnd=rnd, n_adapt=n_adapt,
+                        seed=int(seed), chain_id_base=int(chain_id_base), theta=cpu(theta), y=cpu(y), stats=cpu(stats),
+                        blk={name: cpu(getattr(blk, name)) for name in _BLOCK_TENSORS}, proposal=proposal.state_dict(),
+                        torch_rng=torch.get_rng_state()), checkpoint)
     rs = RunStats(stats, d)
     if single:
         chain = (out[0] if layout == _abi.TRACE_CHAIN_MAJOR else out[:, 0]).cpu() if out is not None else None

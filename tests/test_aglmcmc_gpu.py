@@ -318,3 +318,23 @@ def test_checkpoint_resume_and_host_entry_are_bit_identical(tmp_path):
                  stats=h_stats, K=K, ag=ag, chunk_steps=64)
     assert torch.equal(h_trace, full.cpu())
     assert torch.equal(h_stats[:, :4], st_full.raw.cpu()[:, :4]) and torch.allclose(h_stats, st_full.raw.cpu(), rtol=1e-4, atol=1e-3)
+
+
+def test_pooled_checkpoint_resume_is_bit_identical(tmp_path):
+    """the pooled-KDE mode (one KernelDensity shared by all chains): blocks, the KDE, eps-hat and the generators travel in the
+    checkpoint; a run cut in two continues bit-identically through further pooled adaptations"""
+    import glabc_b200 as g
+    model = g.Mixture_set(0.05)
+    lp = g.DiagGaussian(2, torch.zeros(1, 2), torch.log(torch.tensor([0.35, 0.35])))
+    ip = g.DiagGaussian(2, torch.zeros(2), torch.zeros(2))
+    C, T, T1 = 400, 301, 137
+    run = lambda n, **kw: g.AGLMCMC(model, n, torch.zeros(2), None, lp, ip, None, 1.0, 20, 5, 0.8, 0.2, num_chains=C, seed=4,   # noqa: E731
+                                    trace="time", return_stats=True, return_proposal=True, pooled=True, kde_train=4000, **kw)
+    full, st_full, prop_full = run(T)
+    ck = tmp_path / "agp.pt"
+    first, _, prop_1 = run(T1, checkpoint=str(ck))
+    rest, st_rest, prop_rest = run(T, resume=str(ck))
+    assert len(prop_1.history) >= 2 and len(prop_rest.history) > len(prop_1.history)
+    assert torch.equal(first, full[:T1]) and torch.equal(rest, full[T1:])
+    assert prop_rest.history == prop_full.history
+    assert torch.equal(st_rest.raw[:, :4], st_full.raw[:, :4])

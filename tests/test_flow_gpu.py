@@ -214,3 +214,37 @@ def test_public_api_glmcmc_nf(tmp_path):
     chain = runner.run_glmcmc_nf(1500, theta0, y0, 0.5, lp, base, 5, 200, 50, output_file="glmcmc_nf_results.csv", verbose=False)
     assert chain.shape == (1500, 2) and chain.dtype == torch.float32 and torch.equal(chain[0], theta0)
     assert (tmp_path / "glmcmc_nf_results.csv").exists()
+
+
+def test_glmcmc_nf_checkpoint_resume_is_bit_identical(tmp_path):
+    """SURVEY.md 8(f) n4 for GLMCMC-NFs: chain state, candidate blocks, the flow's weights AND its Adam moments (glabc_flow_get /
+    glabc_flow_train_state), the generators.  With every move global the chains consume their blocks in step, so a run cut in
+    two (training steps on both sides of the cut) delivers the same chains, the same losses and the same final flow as the uncut
+    run.  With local moves in between the chains reach the end of a block at different iterations and the blocks are refilled
+    when EVERY chain is finished or has consumed its block — where a run is cut is then part of the schedule; the checkpoint
+    still restores the state exactly: two resumes from one file are bit-identical."""
+    g, model, lp = readme_objects()
+    C, T, T1 = 512, 601, 257
+    kw = dict(num_chains=C, seed=5, trace="time", return_stats=True, return_flow=True, lr=2e-3)
+    run = lambda n, gf, **k: g.GLMCMC_NF(model, n, torch.zeros(2), None, lp, None, gf, 20, 5, None, 50, **kw, **k)   # noqa: E731
+    torch.manual_seed(3)
+    full, st_full, flow_full, loss_full = run(T, 1.0)
+    ck = tmp_path / "nf.pt"
+    torch.manual_seed(3)
+    first, _, _, loss_1 = run(T1, 1.0, checkpoint=str(ck))
+    torch.manual_seed(99)                                    # the resumed run takes its generators from the checkpoint
+    rest, st_rest, flow_rest, loss_2 = run(T, 1.0, resume=str(ck))
+    assert len(loss_1) >= 3 and len(loss_2) > len(loss_1)    # training happened before and after the cut
+    assert torch.equal(first, full[:T1]) and torch.equal(rest, full[T1:])
+    assert loss_2 == loss_full
+    assert torch.equal(flow_rest.flat_params(), flow_full.flat_params())
+    assert torch.equal(st_rest.raw[:, :4], st_full.raw[:, :4])
+    # local moves in between (gf = 0.6): exact restoration = two resumes agree bit for bit, and the chains keep moving
+    ck2 = tmp_path / "nf2.pt"
+    torch.manual_seed(3)
+    run(T1, 0.6, checkpoint=str(ck2))
+    a, st_a, flow_a, loss_a = run(T, 0.6, resume=str(ck2))
+    torch.manual_seed(12345)
+    b, st_b, flow_b, loss_b = run(T, 0.6, resume=str(ck2))
+    assert torch.equal(a, b) and loss_a == loss_b and torch.equal(flow_a.flat_params(), flow_b.flat_params())
+    assert torch.equal(st_a.raw, st_b.raw) and float(st_a.move_rate.mean()) > 0.005
