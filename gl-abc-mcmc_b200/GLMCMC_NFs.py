@@ -51,7 +51,7 @@ class FlowProposal:
     def __init__(self, flow, eng, seed, chain_id_base, train_batch, lr, weight_decay, precision="precise", train="native"):
         self.flow, self.eng, self.train_batch, self.train = flow, eng, int(train_batch), train
         eng.flow_precision(precision)
-        self.gen = torch.Generator(device=eng.device).manual_seed((seed * 0x9E3779B1 + chain_id_base + 0x5F) & 0x7FFFFFFFFFFFFFFF)
+        self.seed = (seed * 0x9E3779B1 + chain_id_base + 0x5F) & 0x7FFFFFFFFFFFFFFF
         self.losses = []
         if train == "native":
             flow.train_init(eng, lr=lr, weight_decay=weight_decay)                                # GLMCMC_NFs.py:63, in the context
@@ -62,7 +62,7 @@ class FlowProposal:
     def state_dict(self):
         """flow weights, Adam moments + step count (glabc_flow_get / glabc_flow_train_state), the generator of the base normals"""
         eng, flow = self.eng, self.flow
-        sd = dict(train=self.train, params=flow.flat_params().cpu(), gen=self.gen.get_state(), losses=list(self.losses))
+        sd = dict(train=self.train, params=flow.flat_params().cpu(), losses=list(self.losses))
         if self.train == "native":
             import ctypes as C
             mom = torch.empty(2 * sd["params"].numel(), device=eng.device)
@@ -79,7 +79,6 @@ class FlowProposal:
         if sd["train"] != self.train:
             raise ValueError(f"the checkpoint was trained with flow_train={sd['train']!r}")
         flow.load_flat(sd["params"].to(eng.device))
-        self.gen.set_state(sd["gen"])
         self.losses = list(sd["losses"])
         if self.train == "native":
             flow.bind(eng)                                   # the restored weights into the context (moments are kept: same architecture)
@@ -93,8 +92,8 @@ class FlowProposal:
 
     def fill(self, blk_theta, blk_lq, rnd):     # NF_model.sample, GLMCMC_NFs.py:72,127
         c, B, d = blk_theta.shape
-        eps = torch.randn(c * B, d, generator=self.gen, device=self.eng.device)
-        self.flow.fused_sample_from(eps, self.eng, theta=blk_theta, log_q=blk_lq)
+        # the base normals are drawn inside the flow kernel (Philox keyed by the proposal's seed and the refill round)
+        self.flow.fused_sample(c * B, (self.seed + 0x632BE5AB * (rnd + 1)) & 0x7FFFFFFFFFFFFFFF, self.eng, theta=blk_theta, log_q=blk_lq)
 
     def log_prob(self, theta):                  # NF_model.log_prob, GLMCMC_NFs.py:98
         return self.flow.fused_log_prob(theta, self.eng)

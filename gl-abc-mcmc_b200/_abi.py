@@ -168,6 +168,7 @@ _SIGNATURES = {
     "glabc_run_aglmcmc_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "glabc_aglmcmc_state": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "glabc_flow_precision": (C.c_int, [C.c_void_p, C.c_int32]),
+    "glabc_flow_sample_native": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "glabc_flow_param_count": (C.c_int64, [C.c_int32]),
     "glabc_flow_train_init": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float]),
     "glabc_flow_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -1077,7 +1077,23 @@ extern "C" int glabc_flow_train_state(glabc_ctx* ctx, float* state, int64_t* ste
 
 extern "C" int glabc_flow_sample(glabc_ctx* ctx, const float* eps, int64_t n, float* theta, float* log_q, void* stream)
 {
+    if (ctx && !eps) return fail(ctx, GLABC_ERR_INVALID, "glabc_flow_sample: null eps (glabc_flow_sample_native draws them in the kernel)");
     return run_flow(ctx, true, eps, n, theta, log_q, stream);
+}
+
+extern "C" int glabc_flow_sample_native(glabc_ctx* ctx, uint64_t seed, int64_t n, float* theta, float* log_q, void* stream)
+{
+    if (!ctx) return GLABC_ERR_INVALID;
+    if (!theta || !log_q || n < 0) return fail(ctx, GLABC_ERR_INVALID, "glabc_flow_sample_native: null pointer / bad n");
+    if (!ctx->has_flow) return fail(ctx, GLABC_ERR_INVALID, "no flow bound: call glabc_flow_set first");
+    if (ctx->cc < 100) return fail(ctx, GLABC_ERR_UNSUPPORTED, "the flow kernels need tcgen05 tensor cores (sm_100a); this device is sm_%d", ctx->cc);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    FlowDev W = ctx->flow;
+    W.seed_lo = static_cast<uint32_t>(seed);
+    W.seed_hi = static_cast<uint32_t>(seed >> 32);
+    CUDA_TRY(ctx, launch_flow(W, true, ctx->flow_precision == GLABC_FLOW_PRECISE, nullptr, n, theta, log_q, ctx->sm_count,
+                              static_cast<cudaStream_t>(stream)));
+    return GLABC_OK;
 }
 
 extern "C" int glabc_flow_log_prob(glabc_ctx* ctx, const float* theta, int64_t n, float* log_q, void* stream)

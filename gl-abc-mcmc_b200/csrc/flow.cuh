@@ -25,6 +25,8 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include "philox.cuh"
+
 namespace glabc {
 
 constexpr int kFlowHidden = 128;
@@ -85,7 +87,11 @@ struct FlowDev {
     const float* b3;   // [L][2]
     float base_loc[2], base_log_scale[2];
     int32_t n_blocks;
+    // sample() without an eps buffer: the base normals of sample i are Box-Muller of Philox4x32-10(counter = (i, kSlotFlowEps), key = seed)
+    uint32_t seed_lo, seed_hi;
 };
+
+constexpr uint32_t kSlotFlowEps = 0x60000000u;
 
 // byte offset of element (row r, k) of a [128][128] fp32 operand in the K-major no-swizzle canonical layout:
 // core matrix = 8 rows x 16 bytes, core matrices contiguous along K (LBO = 128 B), 8-row groups 4 KB apart (SBO)
@@ -344,8 +350,14 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
             const int64_t idx = (chunk * tpc + t) * kFlowTile + row;
             float a = 0.0f, b = 0.0f, lq = 0.0f;
             if (idx < n) {
-                a = in[idx * 2];
-                b = in[idx * 2 + 1];
+                if (SAMPLE && in == nullptr) {   // q0's normals generated here: no eps buffer, no HBM round trip (GLMCMC_NFs.py:72,127)
+                    const RoundKeys rk = expand_key(make_uint2(W.seed_lo, W.seed_hi));
+                    const uint4 w = philox4x32_10(make_uint4(static_cast<uint32_t>(idx), static_cast<uint32_t>(idx >> 32), 0u, kSlotFlowEps), rk);
+                    box_muller(w.x, w.y, a, b);
+                } else {
+                    a = in[idx * 2];
+                    b = in[idx * 2 + 1];
+                }
                 if (SAMPLE) {  // base DiagGaussian.forward: z = loc + exp(log_scale) * eps, log p from eps
                     lq = c2 - ((W.base_log_scale[0] + 0.5f * (a * a)) + (W.base_log_scale[1] + 0.5f * (b * b)));
                     a = W.base_loc[0] + expf(W.base_log_scale[0]) * a;

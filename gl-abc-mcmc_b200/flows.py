@@ -158,6 +158,18 @@ class RealNVP(nn.Module):
         eng.ctx.check(eng.lib.glabc_flow_sample(eng.ctx.handle, eng._ptr(eps), n, eng._ptr(theta), eng._ptr(log_q), eng._stream()))
         return theta, log_q
 
+    def fused_sample(self, n, seed, eng=None, theta=None, log_q=None, precision=None):
+        """NormalizingFlow.sample(n) with the base normals drawn inside the kernel (Philox keyed by `seed`)"""
+        eng = eng or get_engine(self.loc.device)
+        if precision is not None:
+            eng.flow_precision(precision)
+        theta = torch.empty(n, 2, device=eng.device) if theta is None else theta
+        log_q = torch.empty(n, device=eng.device) if log_q is None else log_q
+        assert theta.is_contiguous() and log_q.is_contiguous() and theta.numel() == 2 * n and log_q.numel() == n
+        eng.ctx.check(eng.lib.glabc_flow_sample_native(eng.ctx.handle, int(seed) & 0xFFFFFFFFFFFFFFFF, n, eng._ptr(theta), eng._ptr(log_q),
+                                                       eng._stream()))
+        return theta, log_q
+
     def fused_log_prob(self, x, eng=None, precision=None):
         eng = eng or get_engine(self.loc.device)
         if precision is not None:

@@ -428,6 +428,8 @@ GLABC_API int glabc_block_weights(glabc_ctx* ctx, const glabc_run_t* run, const 
 GLABC_API int glabc_flow_precision(glabc_ctx* ctx, int32_t mode);
 GLABC_API int glabc_flow_set(glabc_ctx* ctx, const glabc_flow_t* flow, size_t nbytes, void* stream);
 GLABC_API int glabc_flow_sample(glabc_ctx* ctx, const float* eps, int64_t n, float* theta, float* log_q, void* stream);
+/* the same with the base normals drawn inside the kernel (Philox4x32-10 keyed by `seed`, counter = sample index): no eps buffer */
+GLABC_API int glabc_flow_sample_native(glabc_ctx* ctx, uint64_t seed, int64_t n, float* theta, float* log_q, void* stream);
 GLABC_API int glabc_flow_log_prob(glabc_ctx* ctx, const float* theta, int64_t n, float* log_q, void* stream);
 
 /* ---- the flow's training step (GLMCMC_NFs.py:63,112-124): loss = NF_model.forward_kld(x) = -mean log q(x), backward through

@@ -93,6 +93,29 @@ def test_precise_mode_invariants():
         eng.flow_precision("fast")
 
 
+def test_native_base_normals(flow):
+    """glabc_flow_sample_native: q0's normals are drawn inside the kernel (Philox keyed by (seed, sample index)).  Through the
+    identity flow they come out as theta: standard normal (KS), different per seed, the same per (seed, index) whatever n;
+    and the trained flow fed those normals through the eps entry gives the identical samples."""
+    from scipy import stats as sst
+    from glabc_b200.flows import RealNVP
+    ident = RealNVP(device="cuda")
+    eng = ident.bind()
+    eps, lq = ident.fused_sample(200000, seed=7, eng=eng, precision="fast")
+    e = eps.cpu().numpy().astype(np.float64)
+    for i in range(2):
+        assert sst.kstest(e[:, i], "norm").statistic < 0.005
+    assert abs(np.corrcoef(e[:, 0], e[:, 1])[0, 1]) < 0.01
+    assert torch.allclose(lq, -np.log(2 * np.pi) - 0.5 * (eps ** 2).sum(1), rtol=0, atol=2e-6)
+    again, _ = ident.fused_sample(1000, seed=7, eng=eng)
+    other, _ = ident.fused_sample(1000, seed=8, eng=eng)
+    assert torch.equal(again, eps[:1000]) and not torch.equal(other, eps[:1000])
+    flow.bind().flow_precision("fast")
+    th_n, lq_n = flow.fused_sample(200000, seed=7)
+    th_e, lq_e = flow.fused_sample_from(eps)
+    assert torch.equal(th_n, th_e) and torch.equal(lq_n, lq_e)
+
+
 def test_identity_at_init():
     """init_zeros=True: the untrained flow is the identity, so sample == base draw and log_prob == base density exactly"""
     from glabc_b200.flows import RealNVP

@@ -53,7 +53,7 @@ def test_gradient_matches_autograd(n, n_blocks):
     f32 = copy.deepcopy(flow)
     l32 = f32.forward_kld(x)
     l32.backward()
-    assert abs(float(loss) - float(l64)) <= 1e-5 * abs(float(l64)), (float(loss), float(l64))
+    assert abs(float(loss) - float(l64.detach())) <= 1e-5 * abs(float(l64.detach())), (float(loss), float(l64.detach()))
     got = groups(flow, g)
     for k in flow._FLAT:
         ref = getattr(f64, k).grad
