@@ -7,6 +7,8 @@ import torch
 
 from . import _abi
 from .engine import get_engine
+from .GlobalMCMC import run_user_model
+from .models import UserModel
 from .samplers import run_chains
 
 
@@ -22,6 +24,11 @@ def GLMALA(ABCset, num_ite, Initial_theta, Initial_y, tau, num_grad, filelocatio
     if not 2 <= int(num_grad) <= _abi.MAX_NUM_GRAD:
         raise ValueError(f"num_grad must be in 2..{_abi.MAX_NUM_GRAD}")
     eng = get_engine(device)
+    if isinstance(ABCset, UserModel):       # run-time compiled model (csrc/user_model.cu: glabc_k_mala_user)
+        eng.bind_proposal(_abi.SLOT_IMPORTANCE, Importance_Proposal)
+        return run_user_model(eng, ABCset, "mala", num_ite, Initial_theta, Initial_y, None, filelocation, global_frequency, num_chains,
+                              seed, chain_id_base, trace, return_stats, verbose, block_threads, K=int(batch_size), num_grad=int(num_grad),
+                              tau=float(tau))
     pod = eng.bind_model(ABCset)
     eng.bind_proposal(_abi.SLOT_IMPORTANCE, Importance_Proposal)
     state64 = None      # resume: the carried float64 state comes from the checkpoint (Initial_theta / Initial_y are not read)

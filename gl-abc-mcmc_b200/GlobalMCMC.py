@@ -41,14 +41,15 @@ def GlobalMCMC(ABCset, num_ite, Initial_theta, Initial_y, Global_Proposal, filel
 
 
 def run_user_model(eng, model, sampler, num_ite, Initial_theta, Initial_y, Local_Proposal, filelocation, gf, num_chains,
-                   seed, chain_id_base, trace, return_stats, verbose, block_threads, K=0):
+                   seed, chain_id_base, trace, return_stats, verbose, block_threads, K=0, num_grad=0, tau=0.0):
     """GlobalMCMC / GLMCMC for a run-time compiled `UserModel` (glabc_run_global_user / glabc_run_isir_user); the caller has
     bound the sampler's state-independent proposal (GLOBAL / IMPORTANCE slot)."""
     if num_ite < 1:
         raise ValueError("num_ite must be at least 1")
     if Initial_y is None:
         raise ValueError("a UserModel run needs Initial_y (the library cannot call the simulator outside the kernel)")
-    eng.bind_proposal(_abi.SLOT_LOCAL, Local_Proposal)
+    if sampler != "mala":
+        eng.bind_proposal(_abi.SLOT_LOCAL, Local_Proposal)
     d, yd = model.theta_dim, model.y_dim
     seed = default_seed() if seed is None else int(seed)
     theta = torch.as_tensor(Initial_theta, dtype=torch.float32).reshape(-1, d)
@@ -62,11 +63,12 @@ def run_user_model(eng, model, sampler, num_ite, Initial_theta, Initial_y, Local
     layout = _LAYOUT[trace]
     stats = torch.zeros(c, _abi.nstats(d), dtype=torch.float32, device=eng.device)
     aux = None
-    if sampler == "isir":
+    if sampler in ("isir", "mala"):
         aux = torch.zeros(c, _abi.AUX_SLOTS, dtype=torch.float32, device=eng.device)
         aux[:, _abi.AUX_LOCAL] = 1.0                        # `local` starts True, GLMCMC.py:49-55
     out = eng.run_user(model, theta=theta, y=y, n_steps=num_ite - 1, gf=gf, seed=seed, chain_id_base=chain_id_base,
-                       trace_layout=layout, stats=stats, block_threads=block_threads, sampler=sampler, K=K, aux=aux)
+                       trace_layout=layout, stats=stats, block_threads=block_threads, sampler=sampler, K=K, aux=aux,
+                       num_grad=num_grad, tau=tau)
     rs = RunStats(stats, d)
     if single:
         result = (out[0] if layout == _abi.TRACE_CHAIN_MAJOR else out[:, 0]).cpu() if out is not None else None

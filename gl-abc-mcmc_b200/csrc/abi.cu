@@ -1214,8 +1214,9 @@ extern "C" int glabc_user_model_check(const glabc_user_model_t* um, int32_t cc, 
     return st;
 }
 
-static int run_user(glabc_ctx* ctx, const glabc_run_t* run, const glabc_user_model_t* um, bool isir)
+static int run_user(glabc_ctx* ctx, const glabc_run_t* run, const glabc_user_model_t* um, int kind)
 {
+    const bool isir = kind >= 1, mala = kind == 2;   // 0 GlobalMCMC, 1 GLMCMC (iSIR), 2 GLMALA
     if (!ctx) return GLABC_ERR_INVALID;
     if (!um || !um->source) return fail(ctx, GLABC_ERR_INVALID, "glabc_run_*_user: null model / source");
     if (um->theta_dim < 1 || um->theta_dim > GLABC_MAX_DIM || um->y_dim < 1 || um->y_dim > 2 * GLABC_MAX_DIM)
@@ -1225,10 +1226,10 @@ static int run_user(glabc_ctx* ctx, const glabc_run_t* run, const glabc_user_mod
     if (!(um->epsilon > 0.0)) return fail(ctx, GLABC_ERR_INVALID, "user model: epsilon must be positive");
     const int d = um->theta_dim;
     const int far_slot = isir ? GLABC_SLOT_IMPORTANCE : GLABC_SLOT_GLOBAL;   // the state-independent proposal of the sampler
-    for (int slot : {static_cast<int>(GLABC_SLOT_LOCAL), far_slot}) {
+    for (int slot : {mala ? far_slot : static_cast<int>(GLABC_SLOT_LOCAL), far_slot}) {
         if (!ctx->has_dist[slot])
-            return fail(ctx, GLABC_ERR_INVALID, "%s needs the LOCAL and %s proposal slots bound", isir ? "glabc_run_isir_user" : "glabc_run_global_user",
-                        isir ? "IMPORTANCE" : "GLOBAL");
+            return fail(ctx, GLABC_ERR_INVALID, "%s needs the %s%s proposal slot(s) bound", mala ? "glabc_run_mala_user" : isir ? "glabc_run_isir_user" : "glabc_run_global_user",
+                        mala ? "" : "LOCAL and ", isir ? "IMPORTANCE" : "GLOBAL");
         if (ctx->dist[slot].kind != GLABC_DIST_DIAG_GAUSSIAN)
             return fail(ctx, GLABC_ERR_UNSUPPORTED, "the user-model kernels are fused for DiagGaussian proposals");
         if (ctx->dist[slot].dim != d) return fail(ctx, GLABC_ERR_INVALID, "proposal dim does not match the user model's theta_dim %d", d);
@@ -1239,6 +1240,11 @@ static int run_user(glabc_ctx* ctx, const glabc_run_t* run, const glabc_user_mod
             return fail(ctx, GLABC_ERR_INVALID, "n_candidates (batch_size) must be in 1..%d", GLABC_MAX_K);
         if (!run->aux) return fail(ctx, GLABC_ERR_INVALID, "glabc_run_isir_user needs the aux state [C][%d] (log-weight, local flag)", GLABC_AUX_SLOTS);
     }
+    if (mala) {
+        if (d > GLABC_AUX_SLOTS - 3) return fail(ctx, GLABC_ERR_UNSUPPORTED, "glabc_run_mala_user: theta_dim at most %d (the cached gradient lives in the aux slots)", GLABC_AUX_SLOTS - 3);
+        if (run->num_grad < 2 || run->num_grad > GLABC_MAX_NUM_GRAD) return fail(ctx, GLABC_ERR_INVALID, "num_grad must be in 2..%d", GLABC_MAX_NUM_GRAD);
+        if (!(run->tau > 0.0f)) return fail(ctx, GLABC_ERR_INVALID, "tau must be positive");
+    }
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     RunParams R;
     int block = 0;
@@ -1248,7 +1254,7 @@ static int run_user(glabc_ctx* ctx, const glabc_run_t* run, const glabc_user_mod
     CUDA_TRY(ctx, cudaFree(nullptr));   // make sure the primary context exists and is current for the driver calls
     void* fn = nullptr;
     std::string err;
-    st = user_model_compile(ctx->device, ctx->cc, *um, isir, &fn, err);
+    st = user_model_compile(ctx->device, ctx->cc, *um, kind, &fn, err);
     if (st) return fail(ctx, st, "%s", err.c_str());
     UserRun U{};
     U.n_chains = R.n_chains;
@@ -1271,8 +1277,13 @@ static int run_user(glabc_ctx* ctx, const glabc_run_t* run, const glabc_user_mod
     U.y = R.y;
     U.trace = R.trace;
     U.stats = R.stats;
-    const glabc_dist_t& lp = ctx->dist[GLABC_SLOT_LOCAL];
+    const glabc_dist_t& lp = ctx->dist[mala ? far_slot : GLABC_SLOT_LOCAL];   // GLMALA has no Local_Proposal
     const glabc_dist_t& gp = ctx->dist[far_slot];
+    if (mala) {
+        U.tau = run->tau;
+        U.eps2 = static_cast<float>(um->epsilon * um->epsilon);
+        U.num_grad = run->num_grad;
+    }
     U.aux = isir ? run->aux : nullptr;
     U.n_candidates = isir ? run->n_candidates : 0;
     for (int k = 0; k < d; ++k) {   // glabc_dist_t DiagGaussian: a = loc, b = log_scale, c = exp(log_scale) in float32
@@ -1286,13 +1297,14 @@ static int run_user(glabc_ctx* ctx, const glabc_run_t* run, const glabc_user_mod
     U.kern_c = static_cast<float>(-0.5 * std::log(2.0 * M_PI)) - std::log(eps);
     U.kern_m = -0.5f / (eps * eps);
     for (int k = 0; k < um->n_params; ++k) U.params[k] = um->params[k];
-    st = user_model_launch(fn, U, block > 128 ? 128 : block, static_cast<cudaStream_t>(run->stream), err);
+    st = user_model_launch(fn, U, mala ? 64 : (block > 128 ? 128 : block), static_cast<cudaStream_t>(run->stream), err);
     if (st) return fail(ctx, st, "%s", err.c_str());
     return GLABC_OK;
 }
 
-extern "C" int glabc_run_global_user(glabc_ctx* ctx, const glabc_run_t* run, const glabc_user_model_t* um) { return run_user(ctx, run, um, false); }
-extern "C" int glabc_run_isir_user(glabc_ctx* ctx, const glabc_run_t* run, const glabc_user_model_t* um) { return run_user(ctx, run, um, true); }
+extern "C" int glabc_run_global_user(glabc_ctx* ctx, const glabc_run_t* run, const glabc_user_model_t* um) { return run_user(ctx, run, um, 0); }
+extern "C" int glabc_run_isir_user(glabc_ctx* ctx, const glabc_run_t* run, const glabc_user_model_t* um) { return run_user(ctx, run, um, 1); }
+extern "C" int glabc_run_mala_user(glabc_ctx* ctx, const glabc_run_t* run, const glabc_user_model_t* um) { return run_user(ctx, run, um, 2); }
 
 
 // ---------------------------------------------------------------------------------------------

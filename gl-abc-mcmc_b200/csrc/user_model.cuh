@@ -21,11 +21,14 @@ struct UserRun {
     float params[GLABC_USER_MAX_PARAMS];
     float* aux;
     int32_t n_candidates, pad2;
+    float tau, eps2;
+    int32_t num_grad, pad3;
 };
 static_assert(GLABC_USER_MAX_PARAMS == 64 && GLABC_MAX_DIM == 8, "the NVRTC prelude hard-codes these sizes");
 
 // compile (or fetch from the process-wide cache) the step kernel specialised for `um`; *fn is a CUfunction
-int user_model_compile(int device, int cc, const glabc_user_model_t& um, bool isir, void** fn, std::string& err);
+// kind: 0 = GlobalMCMC step, 1 = GLMCMC (iSIR) step, 2 = GLMALA step
+int user_model_compile(int device, int cc, const glabc_user_model_t& um, int kind, void** fn, std::string& err);
 // compile only (needs NVRTC, no driver / GPU): validates a model's source; err receives the NVRTC log
 int user_model_check(int cc, const glabc_user_model_t& um, std::string& err);
 int user_model_launch(void* fn, const UserRun& R, int block, cudaStream_t st, std::string& err);

@@ -147,9 +147,10 @@ class Engine:
         return trace
 
     def run_user(self, model, *, theta, y, n_steps, gf, step_base=0, chain_id_base=0, seed=0, trace_layout=_abi.TRACE_CHAIN_MAJOR,
-                 trace=None, trace_rows=None, write_row0=True, stats=None, block_threads=0, sampler="global", K=0, aux=None):
-        """GlobalMCMC (`sampler="global"`, LOCAL / GLOBAL slots) or GLMCMC (`"isir"`, LOCAL / IMPORTANCE slots, K candidates, aux)
-        transitions for a `models.UserModel` (compiled on first use)"""
+                 trace=None, trace_rows=None, write_row0=True, stats=None, block_threads=0, sampler="global", K=0, aux=None,
+                 num_grad=0, tau=0.0):
+        """GlobalMCMC (`sampler="global"`, LOCAL / GLOBAL slots), GLMCMC (`"isir"`, LOCAL / IMPORTANCE slots, K candidates, aux) or
+        GLMALA (`"mala"`, IMPORTANCE slot, K, tau, num_grad, aux) transitions for a `models.UserModel` (compiled on first use)"""
         cn, d = theta.shape
         rows = trace_rows if trace_rows is not None else step_base + n_steps + 1
         if trace is None and trace_layout != _abi.TRACE_NONE:
@@ -159,9 +160,10 @@ class Engine:
                         seed=int(seed) & 0xFFFFFFFFFFFFFFFF, global_frequency=float(gf), rng_mode=_abi.RNG_NATIVE,
                         arith_mode=_abi.ARITH_FAST, trace_layout=trace_layout, write_row0=int(write_row0),
                         block_threads=block_threads, n_candidates=int(K), trace_rows=rows, trace_chains=cn, theta=self._ptr(theta),
-                        y=self._ptr(y), aux=self._ptr(aux), trace=self._ptr(trace), stats=self._ptr(stats), stream=self._stream())
+                        y=self._ptr(y), aux=self._ptr(aux), trace=self._ptr(trace), stats=self._ptr(stats), stream=self._stream(),
+                        num_grad=int(num_grad), tau=float(tau), tau64=float(tau))
         pod = model.user_pod()
-        fn = self.lib.glabc_run_isir_user if sampler == "isir" else self.lib.glabc_run_global_user
+        fn = {"isir": self.lib.glabc_run_isir_user, "mala": self.lib.glabc_run_mala_user}.get(sampler, self.lib.glabc_run_global_user)
         self.ctx.check(fn(self.ctx.handle, C.byref(r), C.byref(pod)))
         return trace
 

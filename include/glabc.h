@@ -384,6 +384,10 @@ GLABC_API int glabc_run_global_user(glabc_ctx* ctx, const glabc_run_t* run, cons
  * exponentiated max-shifted (the reference's un-shifted float32 exp can underflow a whole row to `None`; the shift removes
  * that artefact and nothing else).                                                                                        */
 GLABC_API int glabc_run_isir_user(glabc_ctx* ctx, const glabc_run_t* run, const glabc_user_model_t* model);
+/* GLMALA (GLMALA.py:150-200) for a user model: IMPORTANCE slot, run->n_candidates, run->tau, run->num_grad; aux [C][8] carries
+ * the cached log-weight (slot 0), the `local` flag (1), "gradient cached" (2) and the cached gradient (3 ..): theta_dim <= 5.
+ * A thread per chain; the finite-difference gradient's draws (GLMALA.py:46-95) are dealt over the warp.                    */
+GLABC_API int glabc_run_mala_user(glabc_ctx* ctx, const glabc_run_t* run, const glabc_user_model_t* model);
 /* Compile-only check of a user model for compute capability `cc` (100 = sm_100a): needs NVRTC but neither a GPU nor a
  * context.  The NVRTC log (or "" on success) is copied to log[log_cap].                                              */
 GLABC_API int glabc_user_model_check(const glabc_user_model_t* model, int32_t cc, char* log, size_t log_cap);

@@ -169,3 +169,90 @@ def test_user_model_glmcmc_isir():
     eng.run_user(um, theta=th2, y=yy2, aux=ax2, n_steps=110, step_base=90, gf=0.8, seed=9, K=4, sampler="isir", trace=buf, trace_rows=201,
                  trace_layout=abi.TRACE_TIME_MAJOR, write_row0=False)
     assert torch.equal(buf, full) and torch.equal(th2, th) and torch.equal(ax2[:, :2], ax[:, :2])
+
+
+@pytest.mark.gpu
+def test_user_model_glmala():
+    """run_glmala with a user model (glabc_run_mala_user: a thread per chain, the finite-difference gradient of
+    GLMALA.py:46-95 dealt over the warp): the README model as CUDA source reproduces the closed-form posterior and the
+    statistics of the built-in GLMALA kernel; chunks and shards give the same chains."""
+    from scipy import stats as sst
+    import glabc_b200 as g
+    from glabc_b200 import _abi as abi
+    from glabc_b200.engine import get_engine
+    ip = g.DiagGaussian(2, torch.tensor([0.0, 0.0]), torch.tensor([0.0, 0.0]))
+    um = g.UserModel(MIXTURE_SRC, theta_dim=2, y_dim=2, n_noise=2, epsilon=0.05, params=[1.5, 1.5, 0.05 ** 0.5])
+    Cn, T = 8192, 2501
+    y0 = torch.randn(Cn, 2, generator=torch.Generator().manual_seed(1)) * 0.2236
+    out, st = g.GLMALA(um, T, torch.zeros(2), y0, 0.3, 100, None, 0.8, ip, 5, num_chains=Cn, seed=3, trace="time", return_stats=True)
+    assert out.shape == (T, Cn, 2)
+    a = out[-1].abs().cpu().numpy().astype(np.float64)
+    for i in range(2):
+        assert sst.kstest(a[:, i], sst.norm(1.42518, np.sqrt(0.049881)).cdf).statistic < 0.03
+    _, st2 = g.GLMALA(g.Mixture_set(0.05), T, torch.zeros(2), y0, 0.3, 100, None, 0.8, ip, 5, num_chains=Cn, seed=4, trace="none",
+                      return_stats=True)
+    assert abs(float(st.move_rate.mean()) / float(st2.move_rate.mean()) - 1) < 0.08
+    assert abs(float(st.global_steps.mean()) / (T - 1) - 0.8) < 0.005
+    assert abs(float(st.accepted_local.mean()) / float(st2.accepted_local.mean()) - 1) < 0.15      # the MALA move itself
+    assert abs(float(st.esjd().mean()) / float(st2.esjd().mean()) - 1) < 0.12
+    runner = g.MCMCRunner(um)
+    chain = runner.run_glmala(200, torch.zeros(2), y0[:1], 0.8, ip, 5, 0.3, 100, output_file=None, verbose=False)
+    assert chain.shape == (200, 2)
+    eng = get_engine()
+    eng.bind_proposal(abi.SLOT_IMPORTANCE, ip)
+
+    def fresh(lo, hi):
+        aux = torch.zeros(hi - lo, abi.AUX_SLOTS, device="cuda")
+        aux[:, abi.AUX_LOCAL] = 1.0
+        return torch.zeros(hi - lo, 2, device="cuda"), y0[lo:hi].cuda(), aux
+    kw = dict(gf=0.7, seed=9, K=4, sampler="mala", num_grad=33, tau=0.3, trace_layout=abi.TRACE_TIME_MAJOR)
+    th, yy, ax = fresh(0, 70)
+    full = eng.run_user(um, theta=th, y=yy, aux=ax, n_steps=120, **kw)
+    th2, yy2, ax2 = fresh(0, 70)
+    buf = torch.zeros(121, 70, 2, device="cuda")
+    eng.run_user(um, theta=th2, y=yy2, aux=ax2, n_steps=50, trace=buf, trace_rows=121, **kw)
+    eng.run_user(um, theta=th2, y=yy2, aux=ax2, n_steps=70, step_base=50, trace=buf, trace_rows=121, write_row0=False, **kw)
+    assert torch.equal(buf, full) and torch.equal(th2, th) and torch.equal(ax2, ax)
+    th3, yy3, ax3 = fresh(37, 70)          # a shard: other lanes serve the gradients, the chains are the same
+    part = eng.run_user(um, theta=th3, y=yy3, aux=ax3, n_steps=120, chain_id_base=37, **kw)
+    assert torch.equal(part, full[:, 37:])
+
+
+BOX_SRC = """
+// theta in (0, 2)^2 or "outside the support": the reference's convention for a prior that wants the local proposal redrawn
+__device__ __forceinline__ void glabc_user_simulate(const float* theta, const float* z, const float* p, float* y)
+{
+    y[0] = theta[0] + p[2] * z[0];
+    y[1] = theta[1] + p[2] * z[1];
+}
+__device__ __forceinline__ float glabc_user_prior_log_prob(const float* theta, const float* p)
+{
+    const bool in = theta[0] > 0.f && theta[0] < 2.f && theta[1] > 0.f && theta[1] < 2.f;
+    return in ? -1.3862944f : OUTSIDE;
+}
+__device__ __forceinline__ float glabc_user_discrepancy(const float* y, const float* p)
+{
+    const float a = y[0] - p[0], b = y[1] - p[1];
+    return sqrtf(a * a + b * b);
+}
+"""
+
+
+@pytest.mark.gpu
+def test_prior_sentinel_redraws_the_local_proposal():
+    """GLMCMC.py:92-93: `while prior_log_prob(theta') == 7 * log(1e-10): redraw`.  A box prior that answers with the sentinel
+    never sees a local proposal outside the box simulated or rejected: with observations at the box's corner and a wide
+    random walk the chains move more often than with the same prior answering -inf (which just rejects), and both stay in
+    the box."""
+    import glabc_b200 as g
+    lp = g.DiagGaussian(2, torch.zeros(1, 2), torch.log(torch.tensor([0.5, 0.5])))
+    ip = g.DiagGaussian(2, torch.tensor([1.0, 1.0]), torch.log(torch.tensor([1.0, 1.0])))
+    Cn, T = 8192, 1501
+    th0, y0 = torch.tensor([0.2, 0.2]), torch.tensor([[0.1, 0.1]])
+    res = {}
+    for name, outside in (("sentinel", "GLABC_PRIOR_SENTINEL"), ("minus_inf", "(-INFINITY)")):
+        um = g.UserModel(BOX_SRC.replace("OUTSIDE", outside), theta_dim=2, y_dim=2, n_noise=2, epsilon=0.3, params=[0.1, 0.1, 0.1])
+        out, st = g.GLMCMC(um, T, th0, y0, lp, None, 0.0, ip, 5, num_chains=Cn, seed=3, trace="time", return_stats=True)
+        assert bool(((out > 0) & (out < 2)).all())
+        res[name] = float(st.accepted_local.mean()) / (T - 1)
+    assert res["sentinel"] > 1.25 * res["minus_inf"], res
