@@ -940,9 +940,29 @@ def golden_misc(out_path):
     np.savez_compressed(out_path, **blobs)
 
 
+def probe_torch_sqrt(n=1 << 20):
+    """`python tests/golden/make_golden.py probe`: how torch.sqrt of THIS build rounds float32.  On the build that made the
+    fixtures (torch 2.11.0+cu128 CPU, MKL 2024.2) 0.64 % of the inputs come back one ulp BELOW the correctly rounded root
+    (numpy / IEEE), always when the exact root lies 0.50-0.54 ulp above the lower neighbour; every size from 1 element up.
+    This is why the reference's discrepancies (Mixture.py:36) differ from an IEEE sqrt in the last bit for a few draws per
+    gradient, and what helpers.mala_grad_bound accounts for."""
+    x = (np.random.default_rng(2).random(n) * 4 + 0.001).astype(np.float32)
+    t = torch.sqrt(torch.from_numpy(x)).numpy()
+    r = np.sqrt(x)
+    bad = t != r
+    ulps = (t.view(np.int32).astype(np.int64) - r.view(np.int32))[bad]
+    exact = np.sqrt(x[bad].astype(np.float64))
+    frac = (t[bad].astype(np.float64) - exact) / np.spacing(r[bad]).astype(np.float64)
+    print(f"torch.sqrt != IEEE on {bad.mean():.4%} of {n} float32 inputs; ulp differences {np.unique(ulps).tolist()}; "
+          f"torch's result sits {frac.min():.3f} .. {frac.max():.3f} ulp from the exact root")
+
+
 def main():
     import_reference()
     only = sys.argv[1:]
+    if only == ["probe"]:
+        probe_torch_sqrt()
+        return
     mbase = dict(chains=4, epsilon=0.05, theta0=[0.0, 0.0], ip_loc=[0.0, 0.0], ip_log_scale=[0.0, 0.0])
     mcases = [
         dict(mbase, chains=4, gf=0.8, K=5, tau=0.3, num_grad=100, T=400),       # README.md:128 / config 3
