@@ -409,6 +409,10 @@ static cudaError_t launch_mala_fast_cpw(const MalaConsts& K, const RunParams& R,
 template <int D, int FAMILY, int LAYOUT>
 static cudaError_t launch_mala_fast_one(const MalaConsts& K, const RunParams& R, cudaStream_t st)
 {
+    // Measured and rejected: pooling the 4 left-over blocks per gradient (100 blocks on 32 lanes) of all pending
+    // chains into one joint round — 3 n + 1 rounds instead of 4 n — ran 11.96 ms instead of 9.78 ms at 32,768 chains and 61.5
+    // instead of 50.5 ms at 262,144: the second code path (per-lane owner lookup, hand-over shuffles) costs more instruction
+    // fetch and issue than the nearly empty fourth round it removes.
     // CPW = 16 (twice the warps for the same chains) was measured at 32,768 chains, where only 1.7 warps sit on a scheduler:
     // issue-active rose from 47 % to 63 % but the warp-instructions per chain-step rose from 152 to 193 — the same 9.85 ms
     // (profiles/r2_k3_mala_fast_ncu.md).  Kept behind a build flag for other shapes.
