@@ -459,14 +459,29 @@ static int run_device(glabc_ctx* ctx, SamplerKind kind, const glabc_run_t* run)
         const glabc_dist_t& lp = ctx->dist[GLABC_SLOT_LOCAL];
         const glabc_dist_t& ip = ctx->dist[GLABC_SLOT_IMPORTANCE];
         if (lp.dim != d || ip.dim != d) return fail(ctx, GLABC_ERR_INVALID, "proposal dim does not match theta_dim %d", d);
-        if (!all_gaussian(ctx, {GLABC_SLOT_LOCAL, GLABC_SLOT_IMPORTANCE}))
-            return fail(ctx, GLABC_ERR_UNSUPPORTED, "run_isir is fused for DiagGaussian proposals (other kinds: run_global)");
+        const bool tuned = all_gaussian(ctx, {GLABC_SLOT_LOCAL, GLABC_SLOT_IMPORTANCE});
         if (!run) return fail(ctx, GLABC_ERR_INVALID, "null run description");
         if (run->n_candidates < 1 || run->n_candidates > GLABC_MAX_K)
             return fail(ctx, GLABC_ERR_INVALID, "n_candidates (batch_size) must be in 1..%d", GLABC_MAX_K);
         if (!run->aux) return fail(ctx, GLABC_ERR_INVALID, "run_isir needs the aux state [C][%d] (log-weight, local flag)", GLABC_AUX_SLOTS);
-        int st = make_run_params(ctx, run, d, GLABC_TAPE_ISIR_SLOTS(d, d, run->n_candidates), &R, &block, true);
+        int st = make_run_params(ctx, run, d, GLABC_TAPE_ISIR_SLOTS(d, d, run->n_candidates), &R, &block, tuned);
         if (st) return st;
+        if (!tuned) {
+            // Uniform / Gamma / GaussianMixture in the Local / Importance slots: the general kernel (replay takes the
+            // proposal draws themselves: tape64 [steps][1 + K d][C] = resampling uniform, then the draws)
+            if (run->tape_dump) return fail(ctx, GLABC_ERR_UNSUPPORTED, "tape dump exists for DiagGaussian proposals only");
+            if (run->rng_mode == GLABC_RNG_REPLAY && !run->tape64)
+                return fail(ctx, GLABC_ERR_INVALID, "replay of run_isir with non-Gaussian proposals needs tape64 [n_steps][1 + %d][n_chains]",
+                            run->n_candidates * d);
+            if (R.n_chains == 0) return GLABC_OK;
+            IsirGenericConsts G{};
+            G.model = make_model(ctx->model);
+            G.lp = make_dist(lp);
+            G.ip = make_dist(ip);
+            CUDA_TRY(ctx, launch_isir_generic(G, d, R, run->trace_layout, block, run->rng_mode == GLABC_RNG_REPLAY,
+                                              static_cast<cudaStream_t>(run->stream)));
+            return GLABC_OK;
+        }
         if (run->rng_mode == GLABC_RNG_REPLAY && !run->tape64)
             return fail(ctx, GLABC_ERR_INVALID, "replay of run_isir needs tape64 (the float64 resampling uniforms)");
         if (R.n_chains == 0) return GLABC_OK;

@@ -345,6 +345,126 @@ def golden_global_generic(cases, T, out_path):
     np.savez_compressed(out_path, **blobs)
 
 
+def golden_isir_generic(cases, T, out_path):
+    """GLMCMC (GLMCMC.py:58-104) with Uniform / Gamma / GaussianMixture proposals in the Local / Importance slots.
+    tape32 [T-1][2 + 2K][C] = U_b, eps_sim[K][2] (a local move: eps_sim[2] in the first two), U_a (last slot);
+    tape64 [T-1][1 + 2K][C] = the numpy resampling uniform, then the proposal's own draws in float64 (theta_j of a global
+    move; the increment z of a local one in the first two);
+    rec [T-1][4 + K][C] = flags (global | changed << 1 | (ind + 1) << 8 | float64-weights << 16), then
+    (lw_old, S, w0, lw_1..K) of a global move / (prior', kernel', log_acc) of a local one."""
+    import glabcmcmc.distribution as distribution
+    from Mixture import Mixture_set
+    GLMCMC = sys.modules["glabcmcmc.GLMCMC"].GLMCMC
+    blobs = {}
+    for ci, case in enumerate(cases):
+        C, gf, K = case["chains"], case["gf"], case["K"]
+        model = Mixture_set(case["epsilon"])
+        lp, ip = make_dist(distribution, case["lp"]), make_dist(distribution, case["ip"])
+        tape32 = np.zeros((T - 1, 2 + 2 * K, C), np.float32)
+        tape64 = np.zeros((T - 1, 1 + 2 * K, C), np.float64)
+        trace = np.zeros((T, C, 2), np.float32)
+        theta0s, y0s = np.zeros((C, 2), np.float32), np.zeros((C, 2), np.float32)
+        rec = np.zeros((T - 1, 4 + K, C), np.float64)
+        for c in range(C):
+            torch.manual_seed(7000 + 1000 * ci + c)
+            np.random.seed(7000 + 1000 * ci + c)
+            theta0 = torch.tensor(case["theta0"])
+            y0 = model.generate_samples(theta0)
+            log = []
+            pm = CallLog(model, "model", ("generate_samples", "prior_log_prob", "calculate_log_kernel"), log)
+            plp = CallLog(lp, "lp", ("sample",), log)
+            pip = CallLog(ip, "ip", ("forward", "log_prob"), log)
+            with Tape() as tape, quiet():
+                chain = GLMCMC(pm, T, theta0, y0, plp, None, gf, pip, K)
+            ev = tape.events
+            theta0s[c], y0s[c] = theta0.numpy(), y0.view(-1).numpy()
+            trace[:, c] = chain.detach().numpy()
+            # GLMCMC.py:52-55: the log-weight of the initial state is computed once before the loop (and again at the first global move)
+            assert [x[:2] for x in log[:3]] == [("model", "calculate_log_kernel"), ("model", "prior_log_prob"), ("ip", "log_prob")]
+            li, ei = 3, 0
+            local = True
+            lw_old = None
+            for s in range(T - 1):
+                assert ev[ei][0] == "U32", ev[ei][0]
+                u_b = ev[ei][1][0]
+                ei += 1
+                tape32[s, 0, c] = u_b
+                is_global = bool(np.float32(u_b) < np.float32(gf))
+                changed = bool(np.any(trace[s + 1, c] != trace[s, c]))
+                for kind in N_EVENTS[case["ip" if is_global else "lp"]["kind"]]:
+                    assert ev[ei][0] == kind, (ev[ei][0], kind)
+                    ei += 1
+                if is_global:
+                    assert ev[ei][0] == "N32" and ev[ei][1].shape == (K, 2) and ev[ei + 1][0] == "U64"
+                    tape32[s, 1:1 + 2 * K, c] = ev[ei][1].reshape(-1)
+                    tape64[s, 0, c] = ev[ei + 1][1]
+                    ei += 2
+                    if local:
+                        names = [x[:2] for x in log[li:li + 3]]
+                        assert names == [("model", "calculate_log_kernel"), ("model", "prior_log_prob"), ("ip", "log_prob")], names
+                        lw_old = (log[li + 1][2] + log[li][2] - log[li + 2][2]).reshape(-1)[0]
+                        li += 3
+                    local = False
+                    names = [x[:2] for x in log[li:li + 4]]
+                    assert names == [("ip", "forward"), ("model", "generate_samples"), ("model", "calculate_log_kernel"),
+                                     ("model", "prior_log_prob")], names
+                    (th, lq), x, kern, prior = [v[2] for v in log[li:li + 4]]
+                    li += 4
+                    tape64[s, 1:, c] = np.asarray(th, np.float64).reshape(-1)
+                    lw0 = torch.from_numpy(np.asarray(prior)) + torch.from_numpy(np.asarray(kern)) - torch.from_numpy(np.asarray(lq))
+                    allw = torch.cat((torch.as_tensor(lw_old).view(-1), lw0))
+                    w = torch.exp(allw)
+                    w[torch.isnan(w)] = 0.0
+                    S = torch.sum(w)
+                    wn = (w / S).tolist()
+                    ind, sw = None, 0
+                    for j in range(K + 1):
+                        sw += wn[j]
+                        if float(tape64[s, 0, c]) < sw:
+                            ind = j
+                            break
+                    w64 = allw.dtype == torch.float64
+                    if ind is not None and ind != 0:
+                        assert np.all(np.asarray(th[ind - 1], np.float32) == trace[s + 1, c]), (s, c)
+                        lw_old = allw[ind].clone().numpy()[()]
+                    else:
+                        assert not changed
+                    rec[s, 0, c] = 1 | (int(changed) << 1) | ((0 if ind is None else ind + 1) << 8) | (int(w64) << 16)
+                    rec[s, 1, c], rec[s, 2, c], rec[s, 3, c] = float(allw[0]), S.item(), wn[0]
+                    rec[s, 4:, c] = lw0.numpy().astype(np.float64)
+                else:
+                    assert ev[ei][0] == "N32" and ev[ei][1].shape == (1, 2) and ev[ei + 1][0] == "U32"
+                    tape32[s, 1:3, c] = ev[ei][1].reshape(-1)
+                    tape32[s, 1 + 2 * K, c] = ev[ei + 1][1][0]
+                    ei += 2
+                    names = [x[1] for x in log[li:li + 7]]
+                    assert names == ["sample", "prior_log_prob", "generate_samples", "prior_log_prob", "calculate_log_kernel",
+                                     "prior_log_prob", "calculate_log_kernel"], names
+                    z, _, y_p, pr_p, k_p, pr_o, k_o = [v[2] for v in log[li:li + 7]]
+                    li += 7
+                    tape64[s, 1:3, c] = np.asarray(z, np.float64).reshape(-1)
+                    log_acc = float(pr_p[0]) + float(k_p[0]) - float(pr_o[0]) - float(k_o[0])
+                    if changed:
+                        local = True
+                    rec[s, 0, c] = int(changed) << 1
+                    rec[s, 1, c], rec[s, 2, c], rec[s, 3, c] = float(pr_p[0]), float(k_p[0]), log_acc
+            assert li == len(log) and ei == len(ev), (li, len(log), ei, len(ev))
+        blob = dict(tape32=tape32, tape64=tape64, trace=trace, theta0=theta0s, y0=y0s, rec=rec, gf=np.float64(gf), T=np.int64(T),
+                    K=np.int64(K))
+        blob.update(model_params(model))
+        blob.update(dist_spec_arrays(case["lp"], "lp"))
+        blob.update(dist_spec_arrays(case["ip"], "ip"))
+        for k, v in blob.items():
+            blobs[f"case{ci}/{k}"] = v
+        flags = rec[:, 0].astype(int)
+        glob = (flags & 1) == 1
+        print(f"isir-generic case {ci}: lp={case['lp']['kind']} ip={case['ip']['kind']} gf={gf} K={K} global move rate "
+              f"{np.mean(((flags >> 1) & 1)[glob]):.4f} local accept {np.mean(((flags >> 1) & 1)[~glob]) if (~glob).any() else 0:.4f} "
+              f"None resamples {np.mean(((flags >> 8) & 0xff)[glob] == 0):.4f} float64-weight steps {np.mean(((flags >> 16) & 1)[glob]):.3f}")
+    blobs["n_cases"] = np.int64(len(cases))
+    np.savez_compressed(out_path, **blobs)
+
+
 # ----------------------------------------------------------------------------------------------
 # GLMCMC (GLMCMC.py:58-104)
 # ----------------------------------------------------------------------------------------------
@@ -1004,6 +1124,19 @@ def main():
     ]
     if not only or "generic" in only:
         golden_global_generic(gcases, 800, os.path.join(HERE, "global_generic.npz"))
+    igcases = [
+        dict(chains=4, epsilon=0.2, theta0=[0.0, 0.0], gf=0.8, K=5, lp=gauss,                       # float32 uniform importance proposal
+             ip=dict(kind="uniform", low=[-3.0, -3.0], high=[3.0, 3.0])),
+        dict(chains=4, epsilon=0.2, theta0=[0.0, 0.0], gf=0.7, K=4, lp=dict(kind="uniform", low=[-0.6, -0.6], high=[0.6, 0.6]),
+             ip=dict(kind="mixture", loc=modes, scale=[[0.35, 0.35]] * 4, weights=[1.0, 2.0, 1.0, 1.0])),   # float64 weights
+        dict(chains=4, epsilon=0.2, theta0=[1.0, 1.0], gf=0.6, K=6, lp=dict(kind="gauss", loc=[0.0, 0.0], sigma=[0.3, 0.3]),
+             ip=dict(kind="gamma", shape=[6.0, 6.0], rate=[4.0, 4.0])),                             # support theta > 0 only
+        dict(chains=4, epsilon=0.05, theta0=[0.0, 0.0], gf=0.9, K=5,                                # README tolerance: float32 underflow rows
+             lp=dict(kind="mixture", loc=[[0.3, 0.3], [-0.3, -0.3]], scale=[[0.2, 0.2]] * 2, weights=[1.0, 1.0]),
+             ip=dict(kind="uniform", low=[-2.5, -2.5], high=[2.5, 2.5])),
+    ]
+    if not only or "isir_generic" in only:
+        golden_isir_generic(igcases, 600, os.path.join(HERE, "glmcmc_generic.npz"))
     if only:
         return
     base = dict(chains=4, epsilon=0.05, theta0=[0.0, 0.0], lp_loc=[0.0, 0.0], lp_sigma=[0.35, 0.35],

@@ -119,10 +119,89 @@ def test_global_mcmc_with_mixture_and_uniform_proposals(eng):
 
 
 def test_non_gaussian_proposals_are_refused_where_not_fused(eng):
+    """GLMALA / AGLMCMC are fused for a DiagGaussian importance proposal: any other kind is refused with a message, not run
+    through some other path (run_global_mcmc and run_glmcmc take every kind)"""
     g, model, lp = readme()
     box = g.Uniform(2, torch.tensor([-3.0, -3.0]), torch.tensor([3.0, 3.0]))
     with pytest.raises(abi.GlabcError, match="DiagGaussian"):
-        g.GLMCMC(model, 100, torch.zeros(2), None, lp, None, 0.9, box, 5, num_chains=64)
+        g.GLMALA(model, 100, torch.zeros(2), None, 0.3, 10, None, 0.8, box, 5, num_chains=64)
+    with pytest.raises(abi.GlabcError, match="DiagGaussian"):
+        g.AGLMCMC(model, 100, torch.zeros(2), None, lp, box, None, 1.0, 10, 5, 0.8, 0.2, num_chains=64)
+
+
+def test_glmcmc_with_non_gaussian_proposals(eng):
+    """run_glmcmc (GLMCMC.py:58-104) with a Uniform / GaussianMixture importance proposal and a Uniform local proposal through
+    the general iSIR kernel (k_isir_generic): the closed-form ABC posterior is left invariant, the
+    mode-covering mixture proposal moves far more often than N(0, I), and chunked launches continue bit-identically"""
+    g, model, lp = readme()
+    modes = [[1.425, 1.425], [1.425, -1.425], [-1.425, 1.425], [-1.425, -1.425]]
+    gm = g.GaussianMixture(4, 2, loc=modes, scale=[[0.3, 0.3]] * 4, weights=[1, 1, 1, 1])
+    out, st = g.GLMCMC(model, 1201, torch.zeros(2), None, lp, None, 0.9, gm, 5, num_chains=8192, seed=2, trace="time", return_stats=True)
+    check_posterior(out[-1])
+    assert float(st.move_rate.mean()) > 0.05                      # N(0, I) importance proposal: 0.9 %
+    box = g.Uniform(2, torch.tensor([-3.0, -3.0]), torch.tensor([3.0, 3.0]))
+    rw = g.Uniform(2, torch.tensor([-0.6, -0.6]), torch.tensor([0.6, 0.6]))
+    out = g.GLMCMC(model, 4001, torch.zeros(2), None, rw, None, 0.8, box, 8, num_chains=8192, seed=3, trace="time")
+    check_posterior(out[-1], tol=0.05)
+    # one launch == two launches (aux carries the cached log-weight and the flags)
+    eng.bind_model(model)
+    eng.bind_proposal(abi.SLOT_LOCAL, rw)
+    eng.bind_proposal(abi.SLOT_IMPORTANCE, gm)
+
+    def fresh():
+        aux = torch.zeros(70, abi.AUX_SLOTS, device="cuda")
+        aux[:, abi.AUX_LOCAL] = 1.0
+        y0 = torch.randn(70, 2, generator=torch.Generator().manual_seed(1)).cuda() * 0.2236
+        return torch.zeros(70, 2, device="cuda"), y0, aux
+    th, yy, ax = fresh()
+    full = eng.run("isir", theta=th, y=yy, aux=ax, n_steps=200, gf=0.7, seed=9, K=4, trace_layout=abi.TRACE_TIME_MAJOR)
+    th2, yy2, ax2 = fresh()
+    buf = torch.zeros(201, 70, 2, device="cuda")
+    eng.run("isir", theta=th2, y=yy2, aux=ax2, n_steps=90, gf=0.7, seed=9, K=4, trace=buf, trace_rows=201, trace_layout=abi.TRACE_TIME_MAJOR)
+    eng.run("isir", theta=th2, y=yy2, aux=ax2, n_steps=110, step_base=90, gf=0.7, seed=9, K=4, trace=buf, trace_rows=201,
+            trace_layout=abi.TRACE_TIME_MAJOR, write_row0=False)
+    assert torch.equal(buf, full) and torch.equal(th2, th) and torch.equal(ax2, ax)
+
+
+@pytest.mark.parametrize("ci", [0, 1, 2, 3])
+def test_glmcmc_replay_with_reference_recordings(eng, ci):
+    """tests/golden/glmcmc_generic.npz: the REFERENCE's GLMCMC run with Uniform / GaussianMixture / Gamma proposals in the
+    Local / Importance slots, every draw recorded (incl. float64-weight steps after the state was promoted, and `None`
+    resamples of underflowed float32 weights).  Fed the same draws, the general iSIR kernel must take the same branch, the same
+    resample index (or None) and the same accept decision at every step, evaluate the weights in the same dtype, and write the
+    same float32 trace bit for bit; log-weights / log-densities within 1e-5 of their terms."""
+    import glabc_b200 as g
+    z = np.load(os.path.join(GOLDEN, "glmcmc_generic.npz"))
+    p = lambda k: z[f"case{ci}/{k}"]  # noqa: E731
+    model = g.Mixture_set(float(p("epsilon")))
+    eng.bind_model(model)
+    eng.bind_proposal(abi.SLOT_LOCAL, _dist_from_golden(z, ci, "lp"))
+    eng.bind_proposal(abi.SLOT_IMPORTANCE, _dist_from_golden(z, ci, "ip"))
+    T, Cn, K = int(p("T")), p("theta0").shape[0], int(p("K"))
+    theta, y = torch.from_numpy(p("theta0")).cuda(), torch.from_numpy(p("y0")).cuda()
+    aux = torch.zeros(Cn, abi.AUX_SLOTS, device="cuda")
+    aux[:, abi.AUX_LOCAL] = 1.0
+    tape32, tape64 = torch.from_numpy(p("tape32")).cuda().contiguous(), torch.from_numpy(p("tape64")).cuda().contiguous()
+    debug = torch.zeros(T - 1, abi.DEBUG_SLOTS, Cn, device="cuda")
+    got = eng.run("isir", theta=theta, y=y, aux=aux, n_steps=T - 1, gf=float(p("gf")), K=K, rng_mode=abi.RNG_REPLAY, tape32=tape32,
+                  tape64=tape64, debug=debug, trace_layout=abi.TRACE_TIME_MAJOR).cpu().numpy()
+    dbg, rec = debug.cpu().numpy().astype(np.float64), p("rec")
+    assert np.array_equal(dbg[:, 0], rec[:, 0])                 # branch, move, resample index (+1; 0 = None), weight dtype
+    assert np.array_equal(got, p("trace"))                      # the chains, bit for bit
+    flags = rec[:, 0].astype(int)
+    glob = (flags & 1) == 1
+    for j in range(K):                                          # candidate log-weights: prior + log K - log q, O(1..100) terms
+        a, b = dbg[:, 4 + j][glob], rec[:, 4 + j][glob]
+        fin = np.isfinite(b)
+        assert np.array_equal(np.isneginf(a), np.isneginf(b))
+        assert np.max(np.abs(a[fin] - b[fin]) / np.maximum(np.abs(b[fin]), 10.0)) < 1e-5
+    for slot, name in ((1, "prior'"), (2, "kernel'"), (3, "log_acc")):
+        a, b = dbg[:, slot][~glob], rec[:, slot][~glob]
+        scale = np.maximum(np.abs(b), 1.0) if slot != 3 else np.maximum(np.abs(rec[:, 2][~glob]) + np.abs(b), 1.0)
+        assert np.max(np.abs(a - b) / scale) < 1e-5, name
+    a, b = dbg[:, 1][glob], rec[:, 1][glob]                     # log-weight of the current state
+    assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 10.0)) < 1e-5
+    assert glob.any() and (~glob).any() and ((flags >> 1) & 1).sum() > 20
 
 
 def _dist_from_golden(z, ci, prefix):

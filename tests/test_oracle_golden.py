@@ -178,3 +178,30 @@ def test_generic_proposal_oracle_reproduces_the_reference_recordings():
             fin = np.isfinite(want)
             assert np.array_equal(np.isneginf(rec[:, 1:4]), np.isneginf(want))
             assert np.max(np.abs(rec[:, 1:4][fin] - want[fin]) / np.maximum(np.abs(want[fin]), 1.0)) < 1e-4   # the reference is float32 before promotion
+
+
+def test_generic_isir_oracle_reproduces_the_reference_recordings():
+    """GLMCMC with Uniform / GaussianMixture / Gamma proposals: the numpy restatement (oracle/generic_oracle.py
+    replay_isir_chain), fed the reference's recorded draws, reproduces every branch, resample index (incl. None), weight dtype
+    and its float32 chains bit for bit (tests/golden/glmcmc_generic.npz)"""
+    from oracle import generic_oracle as go
+    kinds = ["gauss", "uniform", "gamma", "mixture"]
+
+    def spec(case, pre):
+        d = {"kind": kinds[int(case[pre + "_kind"])]}
+        d.update({k[len(pre) + 1:]: case[k] for k in case if k.startswith(pre + "_") and k != pre + "_kind"})
+        return d
+    seen64 = seen_none = 0
+    for case in load_cases("glmcmc_generic.npz"):
+        lp, ip = spec(case, "lp"), spec(case, "ip")
+        model = dict(y_obs=case["y_obs"], noise_scale=case["noise_scale"], eps_scale=case["eps_scale"], eps_log_scale=case["eps_log_scale"])
+        K = int(case["K"])
+        for c in range(case["theta0"].shape[0]):
+            tr, rec = go.replay_isir_chain(model, lp, ip, case["theta0"][c], case["y0"][c], float(case["gf"]), K,
+                                           case["tape32"][:, :, c], case["tape64"][:, :, c])
+            assert np.array_equal(tr, case["trace"][:, c])
+            assert np.array_equal(rec[:, 0], case["rec"][:, 0, c])
+            fl = rec[:, 0].astype(int)
+            seen64 += int((((fl >> 16) & 1) == 1).sum())
+            seen_none += int((((fl & 1) == 1) & (((fl >> 8) & 0xff) == 0)).sum())
+    assert seen64 > 100 and seen_none > 0      # the recordings exercise float64 weights and `None` resamples
