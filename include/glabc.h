@@ -358,7 +358,13 @@ GLABC_API int glabc_run_global(glabc_ctx* ctx, const glabc_run_t* run);
 
 /* GLMCMC loop body, GLMCMC.py:58-104, incl. weight_sampling GLMCMC.py:7-22: iSIR global move with
  * `n_candidates` fresh draws from the IMPORTANCE slot, local RW-MH from the LOCAL slot.  `aux` carries
- * the cached log-weight and the `local` flag (init {0, 1}, GLMCMC.py:49-55).                        */
+ * the cached log-weight and the `local` flag (init {0, 1}, GLMCMC.py:49-55).
+ * A Uniform / Gamma / GaussianMixture proposal in either slot selects the general kernel; it follows the reference's dtype
+ * promotion (after a float64 draw is taken the weights are exponentiated in float64: aux slots GLABC_AUX_WIDE / _LW_WIDE).
+ * Its replay mode takes the proposal draws themselves: tape32 [n_steps][2 + K y_dim][C] = U_b, eps_sim[K][y_dim] (a local
+ * move: eps_sim[y_dim] first), U_a (last slot); tape64 [n_steps][1 + K d][C] = the float64 resampling uniform, then the draws
+ * theta_j (a local move: the increment z in the first d); debug slots as for the tuned kernel, + bit 16 of slot 0 = float64
+ * weights.                                                                                                             */
 GLABC_API int glabc_run_isir(glabc_ctx* ctx, const glabc_run_t* run);
 
 /* GLMALA loop body, GLMALA.py:150-200: the iSIR global move of run_isir (GLMALA.py:151-180) and a MALA
