@@ -495,9 +495,11 @@ static int run_device(glabc_ctx* ctx, SamplerKind kind, const glabc_run_t* run)
             return fail(ctx, GLABC_ERR_INVALID, "run_mala needs the IMPORTANCE proposal slot bound");
         const glabc_dist_t& ip = ctx->dist[GLABC_SLOT_IMPORTANCE];
         if (ip.dim != d) return fail(ctx, GLABC_ERR_INVALID, "proposal dim does not match theta_dim %d", d);
-        if (!all_gaussian(ctx, {GLABC_SLOT_IMPORTANCE}))
-            return fail(ctx, GLABC_ERR_UNSUPPORTED, "run_mala is fused for a DiagGaussian importance proposal");
         if (!run) return fail(ctx, GLABC_ERR_INVALID, "null run description");
+        const bool gip = !all_gaussian(ctx, {GLABC_SLOT_IMPORTANCE});
+        if (gip && (run->arith_mode == GLABC_ARITH_STRICT || run->rng_mode == GLABC_RNG_REPLAY || run->tape_dump))
+            return fail(ctx, GLABC_ERR_UNSUPPORTED, "run_mala with a non-Gaussian importance proposal runs FAST arithmetic with the native RNG "
+                                                    "(the STRICT / replay / tape-dump kernel is fused for a DiagGaussian importance proposal)");
         if (run->n_candidates < 1 || run->n_candidates > GLABC_MAX_K)
             return fail(ctx, GLABC_ERR_INVALID, "n_candidates (batch_size) must be in 1..%d", GLABC_MAX_K);
         if (run->num_grad < 2 || run->num_grad > GLABC_MAX_NUM_GRAD)
@@ -515,7 +517,12 @@ static int run_device(glabc_ctx* ctx, SamplerKind kind, const glabc_run_t* run)
         if (run->block_threads == 0) block = 128;  // 4 chains (warps) per block
         MalaConsts K{};
         K.model = make_model(ctx->model);
-        K.ip = make_gauss(ip.a, ip.b, ip.c, d);
+        if (gip) {
+            K.ip_generic = 1;
+            K.ipg = make_dist(ip);
+        } else {
+            K.ip = make_gauss(ip.a, ip.b, ip.c, d);
+        }
         const float zeros[GLABC_MAX_DIM] = {0}, ones[GLABC_MAX_DIM] = {1, 1, 1, 1, 1, 1, 1, 1};
         K.unit = make_gauss(zeros, zeros, ones, d);
         const double eps = ctx->model.epsilon > 0.0 ? ctx->model.epsilon : static_cast<double>(ctx->model.eps_scale);

@@ -17,6 +17,7 @@
 #pragma once
 #include "launch.cuh"
 #include "sampler_common.cuh"
+#include "step_generic.cuh"
 
 namespace glabc {
 
@@ -28,6 +29,8 @@ struct MalaConsts {
     double tau;        // the Python float tau
     float tau_f;       // z * tau is a float32 product
     int32_t num_grad;
+    int32_t ip_generic;   // the Importance_Proposal is a Uniform / Gamma / GaussianMixture: `ipg` (k_mala_fast only), else `ip`
+    DistConsts ipg;
 };
 
 constexpr uint32_t kSlotGrad = 0x10000u;   // gradient normals of theta' (native mode)
@@ -898,6 +901,10 @@ static cudaError_t launch_mala_family(const MalaConsts& K, const RunParams& R, b
 {
     const bool dump = R.tape_dump != nullptr;
     // block_threads == 96 keeps the warp-per-chain kernel for FAST runs too (tests compare the two layouts)
+    if (K.ip_generic) {   // host side has checked: FAST arithmetic, native RNG, no tape dump
+        if (strict || replay || dump) return cudaErrorInvalidValue;
+        return launch_mala_fast<D, FAMILY>(K, R, st);
+    }
     if (!strict && !replay && !dump && block != 96) return launch_mala_fast<D, FAMILY>(K, R, st);
     if (replay)
         return strict ? launch_mala_one<D, FAMILY, true, true, false>(K, R, block, st)

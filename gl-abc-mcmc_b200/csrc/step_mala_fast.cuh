@@ -161,7 +161,9 @@ __device__ __forceinline__ void gradient_from_sums(const MalaConsts& K, const fl
 // CPW = chains per warp: 32, or 16 when there are too few chains to occupy the schedulers (lanes 16..31 then only help with
 // the gradients: the thread-per-chain phases cost twice the issue slots per chain, the gradients — 80 % of the work — the
 // same, and twice as many warps hide the latency of the Philox / MUFU chains).  The chain-major trace tile needs 32.
-template <int D, int FAMILY, int LAYOUT, int CPW>
+// GIP: the Importance_Proposal is one of the non-Gaussian classes (K.ipg, step_generic.cuh): candidate j of a step is
+// dist_forward over the word stream of Philox slots kSlotGeneric + 64 j .., its simulator normals follow in the same stream.
+template <int D, int FAMILY, int LAYOUT, int CPW, bool GIP = false>
 __global__ void __launch_bounds__(GLABC_MALA_BLOCK) k_mala_fast(const __grid_constant__ MalaConsts K, const __grid_constant__ RunParams R)
 {
     using Writer = typename WriterFor<D, LAYOUT>::type;
@@ -210,7 +212,8 @@ __global__ void __launch_bounds__(GLABC_MALA_BLOCK) k_mala_fast(const __grid_con
         if (is_global) {
             // ================= iSIR global move, GLMALA.py:151-180 =================
             if (local) {  // :152-156 — the only place log_weight_old is computed from the state
-                lw_old = (model_prior<D, false>(K.model, theta) + model_log_kernel<D, false>(K.model, y)) - gauss_log_prob<D, false>(K.ip, theta);
+                const float q_old = GIP ? dist_log_prob<D>(K.ipg, theta) : gauss_log_prob<D, false>(K.ip, theta);
+                lw_old = (model_prior<D, false>(K.model, theta) + model_log_kernel<D, false>(K.model, y)) - q_old;
                 lw_wide = wide;
             }
             local = false;
@@ -218,23 +221,35 @@ __global__ void __launch_bounds__(GLABC_MALA_BLOCK) k_mala_fast(const __grid_con
             uint4 wfirst = make_uint4(0, 0, 0, 0);
 GLABC_UNROLL(GLABC_MALA_KUNROLL)
             for (int j = 0; j < NK; ++j) {   // :158-165, candidate j
-                float zc[kGroups * 4];
+                float th_c[D], x_c[D], lw_c;
+                if constexpr (GIP) {
+                    WordStream ws(R.rk, stream, i, kSlotGeneric + 64u * static_cast<uint32_t>(j));
+                    const float lq = dist_forward<D>(K.ipg, ws, th_c);
+                    float eps_s[D];
 #pragma unroll
-                for (int g = 0; g < kGroups; ++g) {
-                    const uint4 w = stream.block(R.rk, i, kSlotNormal + 8u + j * kGroups + g);
-                    if (j == 0 && g == 0) wfirst = w;
-                    box_muller(w.x, w.y, zc[4 * g], zc[4 * g + 1]);
-                    box_muller(w.z, w.w, zc[4 * g + 2], zc[4 * g + 3]);
-                }
-                float eps_p[D], eps_s[D], th_c[D], x_c[D];
+                    for (int k = 0; k < D; ++k) eps_s[k] = ws.normal();
+                    model_simulate<D, false>(K.model, th_c, eps_s, x_c);
+                    lw_c = (model_prior<D, false>(K.model, th_c) + model_log_kernel<D, false>(K.model, x_c)) - lq;
+                    if (j == 0) wfirst = stream.block(R.rk, i, kSlotNormal + 8u);
+                } else {
+                    float zc[kGroups * 4];
 #pragma unroll
-                for (int k = 0; k < D; ++k) {
-                    eps_p[k] = zc[k];
-                    eps_s[k] = zc[D + k];
+                    for (int g = 0; g < kGroups; ++g) {
+                        const uint4 w = stream.block(R.rk, i, kSlotNormal + 8u + j * kGroups + g);
+                        if (j == 0 && g == 0) wfirst = w;
+                        box_muller(w.x, w.y, zc[4 * g], zc[4 * g + 1]);
+                        box_muller(w.z, w.w, zc[4 * g + 2], zc[4 * g + 3]);
+                    }
+                    float eps_p[D], eps_s[D];
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {
+                        eps_p[k] = zc[k];
+                        eps_s[k] = zc[D + k];
+                    }
+                    const float lq = gauss_forward<D, false>(K.ip, eps_p, th_c);
+                    model_simulate<D, false>(K.model, th_c, eps_s, x_c);
+                    lw_c = (model_prior<D, false>(K.model, th_c) + model_log_kernel<D, false>(K.model, x_c)) - lq;
                 }
-                const float lq = gauss_forward<D, false>(K.ip, eps_p, th_c);
-                model_simulate<D, false>(K.model, th_c, eps_s, x_c);
-                const float lw_c = (model_prior<D, false>(K.model, th_c) + model_log_kernel<D, false>(K.model, x_c)) - lq;
                 lw_tab[j * blockDim.x + threadIdx.x] = lw_c;
                 m = fmaxf(m, lw_c == lw_c ? lw_c : -INFINITY);
             }
@@ -244,11 +259,13 @@ GLABC_UNROLL(GLABC_MALA_KUNROLL)
             const double u64 = static_cast<double>(m53) * 0x1p-53;
             // weights: un-shifted float32 exp while the reference's are float32 (all-underflow => None => stay, B-1),
             // max-shifted once they are float64 there (no underflow near -104)
-            const float shift = lw_wide ? m : 0.0f;
+            // (a Gamma / GaussianMixture proposal draws in float64, so with it the reference's weights are float64 from the start)
+            const bool w64 = lw_wide || (GIP && (K.ipg.kind == GLABC_DIST_GAMMA || K.ipg.kind == GLABC_DIST_GAUSSIAN_MIXTURE));
+            const float shift = w64 ? m : 0.0f;
             auto weight = [&](float lw) {
                 float w;
                 asm("ex2.approx.f32 %0, %1;" : "=f"(w) : "f"((lw - shift) * 1.4426950408889634f));
-                return (w != w || (lw_wide && m == -INFINITY)) ? 0.0f : w;
+                return (w != w || (w64 && m == -INFINITY)) ? 0.0f : w;
             };
             const float w_cur = weight(lw_old);
             float S = w_cur;
@@ -262,21 +279,30 @@ GLABC_UNROLL(GLABC_MALA_KUNROLL)
             }
             if (ind > 0) {   // :175-179 — rebuild the chosen candidate (a pure function of (chain, step, j)); the cached gradient is NOT refreshed (B-6)
                 const int j = ind - 1;
-                float zc[kGroups * 4];
+                if constexpr (GIP) {
+                    WordStream ws(R.rk, stream, i, kSlotGeneric + 64u * static_cast<uint32_t>(j));
+                    (void)dist_forward<D>(K.ipg, ws, theta);
+                    float eps_s[D];
 #pragma unroll
-                for (int g = 0; g < kGroups; ++g) {
-                    const uint4 w = stream.block(R.rk, i, kSlotNormal + 8u + j * kGroups + g);
-                    box_muller(w.x, w.y, zc[4 * g], zc[4 * g + 1]);
-                    box_muller(w.z, w.w, zc[4 * g + 2], zc[4 * g + 3]);
-                }
-                float eps_p[D], eps_s[D];
+                    for (int k = 0; k < D; ++k) eps_s[k] = ws.normal();
+                    model_simulate<D, false>(K.model, theta, eps_s, y);
+                } else {
+                    float zc[kGroups * 4];
 #pragma unroll
-                for (int k = 0; k < D; ++k) {
-                    eps_p[k] = zc[k];
-                    eps_s[k] = zc[D + k];
+                    for (int g = 0; g < kGroups; ++g) {
+                        const uint4 w = stream.block(R.rk, i, kSlotNormal + 8u + j * kGroups + g);
+                        box_muller(w.x, w.y, zc[4 * g], zc[4 * g + 1]);
+                        box_muller(w.z, w.w, zc[4 * g + 2], zc[4 * g + 3]);
+                    }
+                    float eps_p[D], eps_s[D];
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {
+                        eps_p[k] = zc[k];
+                        eps_s[k] = zc[D + k];
+                    }
+                    gauss_forward<D, false>(K.ip, eps_p, theta);
+                    model_simulate<D, false>(K.model, theta, eps_s, y);
                 }
-                gauss_forward<D, false>(K.ip, eps_p, theta);
-                model_simulate<D, false>(K.model, theta, eps_s, y);
                 lw_old = lw_tab[j * blockDim.x + threadIdx.x];
 #pragma unroll
                 for (int k = 0; k < D; ++k) changed |= theta[k] != prev[k];
@@ -402,7 +428,8 @@ static cudaError_t launch_mala_fast_cpw(const MalaConsts& K, const RunParams& R,
     const int grid = (R.n_chains + chains_per_block - 1) / chains_per_block;
     const size_t smem = sizeof(float) * (static_cast<size_t>(Writer::smem_floats_per_warp) * (block / 32) +
                                          static_cast<size_t>(R.n_candidates) * block);
-    k_mala_fast<D, FAMILY, LAYOUT, CPW><<<grid, block, smem, st>>>(K, R);
+    if (K.ip_generic) k_mala_fast<D, FAMILY, LAYOUT, CPW, true><<<grid, block, smem, st>>>(K, R);
+    else k_mala_fast<D, FAMILY, LAYOUT, CPW, false><<<grid, block, smem, st>>>(K, R);
     return cudaGetLastError();
 }
 

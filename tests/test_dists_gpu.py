@@ -119,14 +119,47 @@ def test_global_mcmc_with_mixture_and_uniform_proposals(eng):
 
 
 def test_non_gaussian_proposals_are_refused_where_not_fused(eng):
-    """GLMALA / AGLMCMC are fused for a DiagGaussian importance proposal: any other kind is refused with a message, not run
-    through some other path (run_global_mcmc and run_glmcmc take every kind)"""
+    """AGLMCMC and the STRICT / replay GLMALA kernel are fused for a DiagGaussian importance proposal: any other kind is
+    refused with a message, not run through some other path (run_global_mcmc, run_glmcmc and the FAST native run_mala take
+    every kind)"""
     g, model, lp = readme()
     box = g.Uniform(2, torch.tensor([-3.0, -3.0]), torch.tensor([3.0, 3.0]))
     with pytest.raises(abi.GlabcError, match="DiagGaussian"):
-        g.GLMALA(model, 100, torch.zeros(2), None, 0.3, 10, None, 0.8, box, 5, num_chains=64)
+        g.GLMALA(model, 100, torch.zeros(2), None, 0.3, 10, None, 0.8, box, 5, num_chains=64, arith="strict")
     with pytest.raises(abi.GlabcError, match="DiagGaussian"):
         g.AGLMCMC(model, 100, torch.zeros(2), None, lp, box, None, 1.0, 10, 5, 0.8, 0.2, num_chains=64)
+
+
+def test_glmala_with_non_gaussian_importance_proposals(eng):
+    """run_mala (GLMALA.py:151-180) with a GaussianMixture / Uniform Importance_Proposal through k_mala_fast<GIP>: the
+    closed-form ABC posterior is left invariant, the mode-covering mixture moves far more often than
+    N(0, I) does, and two launches continue one launch bit-identically"""
+    g, model, lp = readme()
+    modes = [[1.425, 1.425], [1.425, -1.425], [-1.425, 1.425], [-1.425, -1.425]]
+    gm = g.GaussianMixture(4, 2, loc=modes, scale=[[0.3, 0.3]] * 4, weights=[1, 1, 1, 1])
+    out, st = g.GLMALA(model, 801, torch.zeros(2), None, 0.15, 10, None, 0.5, gm, 5, num_chains=8192, seed=2, trace="time",
+                       return_stats=True)
+    check_posterior(out[-1])
+    assert float(st.move_rate.mean()) > 0.05
+    box = g.Uniform(2, torch.tensor([-3.0, -3.0]), torch.tensor([3.0, 3.0]))
+    out = g.GLMALA(model, 2501, torch.zeros(2), None, 0.15, 10, None, 0.5, box, 8, num_chains=8192, seed=3, trace="time")
+    check_posterior(out[-1], tol=0.05)
+    eng.bind_model(model)
+    eng.bind_proposal(abi.SLOT_IMPORTANCE, gm)
+
+    def fresh():
+        aux = torch.zeros(70, abi.AUX_SLOTS, device="cuda")
+        aux[:, abi.AUX_LOCAL] = 1.0
+        y0 = torch.randn(70, 2, generator=torch.Generator().manual_seed(1)).cuda() * 0.2236
+        return torch.zeros(70, 2, device="cuda"), y0, aux, torch.zeros(70, abi.STATE64_SLOTS, dtype=torch.float64, device="cuda")
+    kw = dict(gf=0.6, seed=9, K=4, num_grad=6, tau=0.2, trace_layout=abi.TRACE_TIME_MAJOR)
+    th, yy, ax, s64 = fresh()
+    full = eng.run("mala", theta=th, y=yy, aux=ax, state64=s64, n_steps=120, **kw)
+    th2, yy2, ax2, s642 = fresh()
+    buf = torch.zeros(121, 70, 2, device="cuda")
+    eng.run("mala", theta=th2, y=yy2, aux=ax2, state64=s642, n_steps=50, trace=buf, trace_rows=121, **kw)
+    eng.run("mala", theta=th2, y=yy2, aux=ax2, state64=s642, n_steps=70, step_base=50, trace=buf, trace_rows=121, write_row0=False, **kw)
+    assert torch.equal(buf, full) and torch.equal(th2, th) and torch.equal(ax2, ax)
 
 
 def test_glmcmc_with_non_gaussian_proposals(eng):

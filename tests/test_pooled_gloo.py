@@ -62,6 +62,10 @@ def _worker(rank, world, port, out_dir):
             p.fill_(0.5)
     lin(torch.full((4, 3), float(rank + 1))).sum().backward()
     pooled.average_gradients(list(lin.parameters()))
+    # the flat gradient buffer of the native flow training step (glabc_flow_grad) and its loss: mean over the ranks, in place
+    flat = torch.arange(7, dtype=torch.float32) * (rank + 1)
+    loss = torch.tensor([2.0 + rank])
+    pooled.average_flat(flat, loss)
     # RoundSync: rank 1 finishes after 2 rounds, rank 0 after 4 — both must leave the loop at round 4
     sync = pooled.RoundSync("cpu")
     mine_done_at = 4 if rank == 0 else 2
@@ -72,7 +76,7 @@ def _worker(rank, world, port, out_dir):
             break
     np.save(os.path.join(out_dir, f"r{rank}.npy"),
             np.array(qs + [eps, float(X.shape[0]), float(ww.sum()), float((X[:, 0] >= 100).sum()), float(ww[0]), float(ww[-1]),
-                           float(lin.weight.grad[0, 0]), float(left_at)], dtype=np.float64))
+                           float(lin.weight.grad[0, 0]), float(left_at), float(flat[3]), float(flat.sum()), float(loss)], dtype=np.float64))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -90,3 +94,4 @@ def test_two_ranks(tmp_path):
     assert abs(r0[7] - 0.6) < 1e-6 and abs(r0[8] - 0.2) < 1e-6          # per-draw weight = rank mass / m
     assert abs(r0[9] - 4 * 1.5) < 1e-6                                   # mean of 4*1 and 4*2
     assert r0[10] == 4
+    assert abs(r0[11] - 3 * 1.5) < 1e-6 and abs(r0[12] - 21 * 1.5) < 1e-6 and abs(r0[13] - 2.5) < 1e-6   # average_flat
