@@ -370,7 +370,10 @@ GLABC_API int glabc_run_isir(glabc_ctx* ctx, const glabc_run_t* run);
 /* GLMALA loop body, GLMALA.py:150-200: the iSIR global move of run_isir (GLMALA.py:151-180) and a MALA
  * local move (Local_proposal_forward :25-44, log_proposal :97-116) whose drift is the finite-difference
  * synthetic-likelihood gradient numberical_gradient_logABC (:46-95) from 2*d*num_grad simulator draws with
- * common random numbers.  run->tau, run->num_grad, run->n_candidates; needs aux and state64.          */
+ * common random numbers.  run->tau, run->num_grad, run->n_candidates; needs aux and state64.
+ * A Uniform / Gamma / GaussianMixture Importance_Proposal runs in the throughput kernel (GLABC_ARITH_FAST, native RNG, no
+ * tape dump; candidates drawn as in glabc_run_isir's general kernel); with GLABC_ARITH_STRICT / GLABC_RNG_REPLAY it is refused
+ * with GLABC_ERR_UNSUPPORTED — the replay kernel is fused for a DiagGaussian importance proposal.     */
 GLABC_API int glabc_run_mala(glabc_ctx* ctx, const glabc_run_t* run);
 
 /* AGLMCMC loop body, AGLMCMC.py:124-272.  LOCAL slot = Local_Proposal, IMPORTANCE slot = Initial_ISIR_prop;
