@@ -919,8 +919,9 @@ extern "C" int glabc_flow_set(glabc_ctx* ctx, const glabc_flow_t* f, size_t nbyt
     cudaStream_t cs = static_cast<cudaStream_t>(stream);
     const size_t L = size_t(f->n_blocks), H = kFlowHidden;
     const FlowParamLayout P(f->n_blocks);
-    // [packed W2: FP16 hi then FP16 lo, L*H*H floats in all][the flat FP32 parameter vector, FlowParamLayout]
-    const size_t need = L * H * H + size_t(P.total);
+    // [packed W2: FP16 hi then FP16 lo, L*H*H floats in all][per-block operand blobs of the pipelined kernel][the flat FP32
+    // parameter vector, FlowParamLayout]
+    const size_t need = L * H * H + L * (kFlowAuxBytes / 4) + size_t(P.total);
     if (need > ctx->flow_floats) {
         if (ctx->flow_mem) cudaFree(ctx->flow_mem);
         ctx->flow_mem = nullptr;
@@ -932,7 +933,8 @@ extern "C" int glabc_flow_set(glabc_ctx* ctx, const glabc_flow_t* f, size_t nbyt
     ctx->flow_blocks = f->n_blocks;
     float* w2p = ctx->flow_mem;                   // first: 16-byte (in fact 256-byte) aligned for cp.async.bulk
     float* w2p_lo = w2p + L * H * H / 2;          // the FP16 remainder W2 - FP16(W2) (PRECISE mode, training)
-    float* par = ctx->flow_mem + L * H * H;
+    uint8_t* aux = reinterpret_cast<uint8_t*>(ctx->flow_mem + L * H * H);
+    float* par = ctx->flow_mem + L * H * H + L * (kFlowAuxBytes / 4);
     CUDA_TRY(ctx, cudaMemcpyAsync(par + P.w1, f->w1, L * H * 4, cudaMemcpyDeviceToDevice, cs));
     CUDA_TRY(ctx, cudaMemcpyAsync(par + P.b1, f->b1, L * H * 4, cudaMemcpyDeviceToDevice, cs));
     CUDA_TRY(ctx, cudaMemcpyAsync(par + P.w2, f->w2, L * H * H * 4, cudaMemcpyDeviceToDevice, cs));
@@ -943,7 +945,9 @@ extern "C" int glabc_flow_set(glabc_ctx* ctx, const glabc_flow_t* f, size_t nbyt
     CUDA_TRY(ctx, cudaMemcpyAsync(par + P.loc, base, sizeof(base), cudaMemcpyHostToDevice, cs));
     CUDA_TRY(ctx, cudaStreamSynchronize(cs));     // `base` is a stack array
     CUDA_TRY(ctx, launch_flow_pack(par + P.w2, w2p, w2p_lo, f->n_blocks, cs));
+    CUDA_TRY(ctx, launch_flow_pack_aux(par + P.w1, par + P.b1, par + P.b2, par + P.w3, par + P.b3, aux, f->n_blocks, cs));
     FlowDev d{};
+    d.aux = aux;
     d.w1 = par + P.w1; d.b1 = par + P.b1; d.w2p = w2p; d.w2p_lo = w2p_lo; d.b2 = par + P.b2; d.w3 = par + P.w3; d.b3 = par + P.b3;
     for (int i = 0; i < 2; ++i) {
         d.base_loc[i] = f->base_loc[i];
@@ -976,7 +980,10 @@ extern "C" int glabc_flow_precision(glabc_ctx* ctx, int32_t mode)
 }
 
 // ---- training step (GLMCMC_NFs.py:63,112-124) ----
-static float* flow_params(glabc_ctx* ctx) { return ctx->flow_mem + size_t(ctx->flow_blocks) * kFlowHidden * kFlowHidden; }
+static float* flow_params(glabc_ctx* ctx)
+{
+    return ctx->flow_mem + size_t(ctx->flow_blocks) * kFlowHidden * kFlowHidden + size_t(ctx->flow_blocks) * (kFlowAuxBytes / 4);
+}
 
 extern "C" int64_t glabc_flow_param_count(int32_t n_blocks) { return n_blocks < 1 ? 0 : FlowParamLayout(n_blocks).total; }
 
@@ -1053,6 +1060,8 @@ extern "C" int glabc_flow_adam_step(glabc_ctx* ctx, const float* grad, const flo
     // the kernels read W2 packed and the base parameters from the launch descriptor: refresh both
     const size_t LHH = size_t(ctx->flow_blocks) * kFlowHidden * kFlowHidden;
     CUDA_TRY(ctx, launch_flow_pack(par + P.w2, ctx->flow_mem, ctx->flow_mem + LHH / 2, ctx->flow_blocks, cs));
+    CUDA_TRY(ctx, launch_flow_pack_aux(par + P.w1, par + P.b1, par + P.b2, par + P.w3, par + P.b3,
+                                       reinterpret_cast<uint8_t*>(ctx->flow_mem + LHH), ctx->flow_blocks, cs));
     float base[4];
     CUDA_TRY(ctx, cudaMemcpyAsync(base, par + P.loc, sizeof(base), cudaMemcpyDeviceToHost, cs));
     CUDA_TRY(ctx, cudaStreamSynchronize(cs));

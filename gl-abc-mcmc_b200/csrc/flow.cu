@@ -1,5 +1,8 @@
 // Host launchers of K4 (RealNVP flow on tcgen05 tensor cores, flow.cuh).
 #include "flow.cuh"
+#include "flow_pipe.cuh"
+
+#include <cstdlib>
 
 namespace glabc {
 
@@ -9,6 +12,24 @@ cudaError_t launch_flow_pack(const float* w2, float* w2p, float* w2p_lo, int n_b
     if (total <= 0) return cudaSuccess;
     k_flow_pack<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(w2, w2p, w2p_lo, total);
     return cudaGetLastError();
+}
+
+cudaError_t launch_flow_pack_aux(const float* w1, const float* b1, const float* b2, const float* w3, const float* b3, uint8_t* aux,
+                                 int n_blocks, cudaStream_t st)
+{
+    if (n_blocks <= 0) return cudaSuccess;
+    k_flow_pack_aux<<<n_blocks, 256, 0, st>>>(w1, b1, b2, w3, b3, aux);
+    return cudaGetLastError();
+}
+
+// GLABC_FLOW_FAST: the warp-specialised pipeline (flow_pipe.cuh); GLABC_FLOW_PIPE=0 in the environment selects k_flow<., false>
+static bool use_pipe()
+{
+    static const bool on = [] {
+        const char* e = std::getenv("GLABC_FLOW_PIPE");
+        return !(e && e[0] == '0');
+    }();
+    return on;
 }
 
 cudaError_t launch_flow(const FlowDev& W, bool sample, bool precise, const float* in, int64_t n, float* out_theta, float* out_lq,
@@ -28,6 +49,12 @@ cudaError_t launch_flow(const FlowDev& W, bool sample, bool precise, const float
             e = cudaFuncSetAttribute(k_flow<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlowSmemBytesPrecise);
             if (e != cudaSuccess) return e;
         }
+        if constexpr (kFlowF16) {
+            e = cudaFuncSetAttribute(k_flow_pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeSmemBytes);
+            if (e != cudaSuccess) return e;
+            e = cudaFuncSetAttribute(k_flow_pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeSmemBytes);
+            if (e != cudaSuccess) return e;
+        }
         configured = true;
     }
     // tiles per chunk: at most what the shared-memory state holds, sized so that the chunks divide evenly over the SMs (an
@@ -38,8 +65,17 @@ cudaError_t launch_flow(const FlowDev& W, bool sample, bool precise, const float
     tpc = (tpc + 1) / 2 * 2;
     if (tpc < 2) tpc = 2;
     if (tpc > kFlowTilesPerCta) tpc = kFlowTilesPerCta;
+    const bool pipe = kFlowF16 && !precise && W.aux != nullptr && use_pipe();
+    if (pipe && tpc < kPipeMinTiles) tpc = kPipeMinTiles;   // the update runs kPipeLag tiles behind layer 1
     const int64_t chunks = (tiles + tpc - 1) / tpc;
     const unsigned grid = static_cast<unsigned>(chunks < sm_count ? chunks : sm_count);  // persistent: one CTA per SM
+    if constexpr (kFlowF16) {
+        if (pipe) {
+            if (sample) k_flow_pipe<true><<<grid, kPipeThreads, kPipeSmemBytes, st>>>(W, in, n, out_theta, out_lq, static_cast<int>(tpc));
+            else k_flow_pipe<false><<<grid, kPipeThreads, kPipeSmemBytes, st>>>(W, in, n, out_theta, out_lq, static_cast<int>(tpc));
+            return cudaGetLastError();
+        }
+    }
     if constexpr (kFlowF16) {
         if (precise) {
             if (sample) k_flow<true, true><<<grid, kFlowThreads, kFlowSmemBytesPrecise, st>>>(W, in, n, out_theta, out_lq, static_cast<int>(tpc));
@@ -53,3 +89,14 @@ cudaError_t launch_flow(const FlowDev& W, bool sample, bool precise, const float
 }
 
 }  // namespace glabc
+
+#ifdef GLABC_FLOW_TRACE
+extern "C" __attribute__((visibility("default"))) int glabc_debug_flow_trace(long long* out)
+{
+    return static_cast<int>(cudaMemcpyFromSymbol(out, glabc::g_flow_trace, sizeof(glabc::g_flow_trace)));
+}
+extern "C" __attribute__((visibility("default"))) int glabc_debug_pipe_trace(long long* out)
+{
+    return static_cast<int>(cudaMemcpyFromSymbol(out, glabc::g_pipe_trace, sizeof(glabc::g_pipe_trace)));
+}
+#endif

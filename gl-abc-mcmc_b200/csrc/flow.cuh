@@ -77,6 +77,9 @@ constexpr uint32_t kFlowTmemCols = 512;                                // per gr
 constexpr int kFlowSmemBytesPrecise = 2 * kFlowW2Bytes + kFlowVecFloats * 4 + 3 * kFlowTilesPerCta * kFlowTile * 4 +
                                       kFlowGroups * 2 * kFlowTile * 8 + 64;
 
+// per coupling block, the small operands pre-packed for the pipelined FAST kernel (flow_pipe.cuh: k_flow_pack_aux)
+constexpr int kFlowAuxBytes = 8832;
+
 struct FlowDev {
     const float* w1;   // [L][128]
     const float* b1;   // [L][128]
@@ -85,6 +88,7 @@ struct FlowDev {
     const float* b2;   // [L][128]
     const float* w3;   // [L][2][128]
     const float* b3;   // [L][2]
+    const uint8_t* aux;   // [L][kFlowAuxBytes]: W3 as a UMMA operand, w1 / b1 as FP16 pairs, b2, b3 (null: the pipelined kernel is not used)
     float base_loc[2], base_log_scale[2];
     int32_t n_blocks;
     // sample() without an eps buffer: the base normals of sample i are Box-Muller of Philox4x32-10(counter = (i, kSlotFlowEps), key = seed)
@@ -219,6 +223,18 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
         : "memory");
 }
 
+// D[tmem] (+)= A[smem] * B[smem]^T with FP16 operands
+__device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // relu(lo), relu(hi) -> saturated, rounded FP16 pair (lo in bits 0..15): one F2FP instruction
 __device__ __forceinline__ uint32_t relu_pack_f16(float lo, float hi)
 {
@@ -276,6 +292,18 @@ static __global__ void __launch_bounds__(256) k_flow_pack(const float* __restric
         w2p[l * kFlowHidden * kFlowHidden + flow_pack_offset(r, k) / 4] = to_tf32(w2[g]);
     }
 }
+
+#ifdef GLABC_FLOW_TRACE
+// phase timeline of CTA 0 (kernel experiments only; read back with glabc_debug_flow_trace): [group][thread 0 / 224][tile][stamp]
+static __device__ long long g_flow_trace[2][2][16][12];
+#define GLABC_TR(i)                                                                                         \
+    do {                                                                                                    \
+        if (blockIdx.x == 0 && li == 4 && chunk == 0 && (gtid == 0 || gtid == 224) && (t >> 1) < 16)        \
+            g_flow_trace[group][gtid != 0][t >> 1][i] = clock64();                                          \
+    } while (0)
+#else
+#define GLABC_TR(i)
+#endif
 
 __device__ __forceinline__ void group_sync(int group)
 {
@@ -486,6 +514,7 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
                     tc_fence_before();
                     group_sync(group);  // (also: half 0 has consumed the previous tile's partial sums)
                 }
+                GLABC_TR(0);
                 // ---- layer 2 (128 x 128 x 128) on the tensor cores ----
                 if (gtid == 0) {
                     tc_fence_after();
@@ -515,12 +544,15 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
                     }
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_m) : "memory");
                 }
+                GLABC_TR(1);
                 if constexpr (kOverlap) {   // the group's next tile: its layer 1 fills the other A buffer while the MMA runs
                     if (t + kFlowGroups < tiles) layer1(t + kFlowGroups, tmem_a0 + (buf ^ 1u) * 64u);
                 }
+                GLABC_TR(2);
                 mbar_wait(bar_m, ph_m);
                 ph_m ^= 1u;
                 tc_fence_after();
+                GLABC_TR(3);
                 float s0 = 0.0f, s1 = 0.0f;
                 float2 o = make_float2(0.0f, 0.0f);
                 if constexpr (kMma2) {
@@ -545,8 +577,10 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
                         tmem_st32(tmem_a + (static_cast<uint32_t>(quad * 32) << 16) + half * (HK / 2), hp);
                         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     }
+                    GLABC_TR(4);
                     tc_fence_before();
                     group_sync(group);  // every thread has read its accumulator columns and written its activations
+                    GLABC_TR(5);
                     // ---- layer 3 (128 x 16 x 128, rows 0 / 1 of W3) on the tensor cores, into accumulator columns 0..15 ----
                     if (gtid == 0) {
                         tc_fence_after();
@@ -559,9 +593,11 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
                         }
                         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_m) : "memory");
                     }
+                    GLABC_TR(6);
                     mbar_wait(bar_m, ph_m);
                     ph_m ^= 1u;
                     tc_fence_after();
+                    GLABC_TR(7);
                     if (half == 0) {   // warp-uniform: warps 0..3 of the group
                         uint32_t r0, r1;
                         asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];"
@@ -572,8 +608,10 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
                         s0 = __uint_as_float(r0);
                         s1 = __uint_as_float(r1);
                     }
+                    GLABC_TR(8);
                     tc_fence_before();
                     group_sync(group);  // the accumulator and both A buffers' roles are free for the group's next tile
+                    GLABC_TR(9);
                 } else {
                 // ---- bias + ReLU + layer 3 (N = 2) from TMEM: this thread's 64 columns, four independent partial sums ----
                 float p0[4] = {0.0f, 0.0f, 0.0f, 0.0f}, p1[4] = {0.0f, 0.0f, 0.0f, 0.0f};
@@ -640,6 +678,7 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
                     }
                     sState[2 * TS + t * kFlowTile + row] = lq;
                 }
+                GLABC_TR(10);
                 buf ^= 1u;
             }
         }
@@ -673,6 +712,8 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
 }
 
 cudaError_t launch_flow_pack(const float* w2, float* w2p, float* w2p_lo, int n_blocks, cudaStream_t st);
+cudaError_t launch_flow_pack_aux(const float* w1, const float* b1, const float* b2, const float* w3, const float* b3, uint8_t* aux,
+                                 int n_blocks, cudaStream_t st);
 cudaError_t launch_flow(const FlowDev& W, bool sample, bool precise, const float* in, int64_t n, float* out_theta, float* out_lq,
                         int sm_count, cudaStream_t st);
 

@@ -1,0 +1,453 @@
+// K4, GLABC_FLOW_FAST mode: the RealNVP flow of flow.cuh as a warp-specialised pipeline.
+//
+// flow.cuh's k_flow gives every tile of 128 samples to one of two thread groups, and the group walks the tile through
+// layer 1 -> MMA -> epilogue -> output-layer MMA -> state update on its own.  A phase timeline of that kernel
+// (profiles/micro/k4_trace.py) shows the two groups in lock-step: both issue their MMAs at the same moment (the issuing
+// threads sit blocked for ~850 cycles while the tensor pipe works through 2 x 512), then both run their CUDA-core phases
+// while the tensor pipe idles — 3,700 cycles per pair of tiles, the tensor pipe busy for a third of them.
+//
+// Here the PHASES own the warps and the tiles flow past them (same arithmetic, same roundings, same results):
+//   * warp 16, one thread  M1: waits on mbarriers, issues the hidden layer's tcgen05.mma (the tensor pipe's queue is a few
+//                              instructions deep: an issuing thread is paced by the MMAs' execution), commits to mbarriers,
+//                              and prefetches the next coupling block's operands (W2 32 KB + a pre-packed 9 KB blob of
+//                              w1 / b1 / b2 / W3 / b3, k_flow_pack_aux) with cp.async.bulk into the other half of a double
+//                              buffer — no CTA-wide barrier and no staging code between coupling blocks;
+//   * warp 17, one thread  M2: issues the output layer's MMAs (its waits overlap M1's issue time);
+//   * warps 8..15           Y: layer 1 of tile q (HFMA2 -> A operand in TMEM) and, three tiles behind, the (shift,
+//                              log-scale) read-back and the affine update of the chain state in shared memory;
+//   * warps 0..7            X: the hidden layer's epilogue: accumulator -> ReLU -> FP16 pairs.
+// b2 is added by the tensor cores: the accumulator of a tile is started by one extra K = 16 MMA of a constant operand (ones
+// in k = 0, 1) against [b2_hi, b2_lo, 0 ...] (both from shared memory), so the epilogue has no bias loads and no adds.
+// The output layer (M128 N16 K128) is eight K = 16 MMAs; chained into ONE accumulator each waits for its predecessor (~100
+// cycles apiece, measured), so they go into four independent 16-column accumulators (two MMAs each) that the update sums.
+// TMEM (512 columns): three 128-column accumulator slots and two 64-column layer-1 operand buffers.  The epilogue writes
+// the packed activations back INTO its accumulator slot (columns 0..31 and 64..95, each thread over columns it has just
+// read) and the output-layer MMA (M128 N16 K128) puts its 16 result columns into the same slot (columns 32..47), so the
+// layer-1 buffer of a tile is free as soon as its first MMA completes and three tiles are in flight instead of two
+// (output-layer partial sums: columns 32..63 and 96..127 of the slot):
+//   window of MMA1(q):  X works on tile q-1, Y on layer 1 of q+1 and the update of q-2, MMA2(q-1) queues behind MMA1(q).
+#pragma once
+#include "flow.cuh"
+
+namespace glabc {
+
+constexpr int kPipeThreads = 18 * 32;
+constexpr int kPipeSlots = 3;        // accumulator slots
+constexpr int kPipeLag = 3;          // Y updates tile q - 3 after layer 1 of tile q (a chunk needs more tiles than this)
+constexpr int kPipeMinTiles = 4;
+// per coupling block, pre-packed in global memory: [W3 as a 16 x 128 FP16 UMMA operand 4096][w1 FP16 pairs 256][b1 FP16 pairs 256]
+// [b3 fp32 8 + pad 120][b2 as a 128 x 16 FP16 UMMA operand: k = 0 FP16(b2), k = 1 FP16(b2 - FP16(b2)), 4096]
+constexpr int kAuxW1 = 4096, kAuxB1 = 4352, kAuxB3 = 4608, kAuxB2Op = 4736;
+static_assert(kAuxB2Op + 4096 == kFlowAuxBytes, "aux blob layout");
+constexpr int kPipeOnesBytes = 4096;   // the constant A operand of the bias MMA: 128 x 16 FP16, ones in k = 0, 1
+constexpr int kPipeStateFloats = 3 * kFlowTilesPerCta * kFlowTile;
+constexpr int kPipeBars = 20;
+constexpr int kPipeSmemBytes = 2 * kFlowW2Bytes + 2 * kFlowAuxBytes + kPipeOnesBytes + kPipeStateFloats * 4 + kPipeBars * 8 + 16;
+enum : int { kBarWFull = 0, kBarAuxEmpty = 2, kBarA1Full = 4, kBarA1Empty = 6, kBarAccFull = 8, kBarActFull = 11, kBarOutFull = 14, kBarAccEmpty = 17 };
+
+static __global__ void __launch_bounds__(256) k_flow_pack_aux(const float* __restrict__ w1, const float* __restrict__ b1,
+                                                              const float* __restrict__ b2, const float* __restrict__ w3,
+                                                              const float* __restrict__ b3, uint8_t* __restrict__ aux)
+{
+    const int l = blockIdx.x, tid = threadIdx.x;
+    uint8_t* a = aux + static_cast<size_t>(l) * kFlowAuxBytes;
+    for (int i = tid; i < kFlowAuxBytes / 4; i += 256) reinterpret_cast<uint32_t*>(a)[i] = 0u;
+    __syncthreads();
+    {   // element (n, k) of the 16 x 128 K-major operand: rows 0 (shift) and 1 (log-scale), rows 2..15 zero
+        const int n = tid >> 7, k = tid & 127;
+        reinterpret_cast<__half*>(a)[((k >> 3) * 128 + n * 16 + (k & 7) * 2) / 2] = __float2half_rn(w3[(l * 2 + n) * kFlowHidden + k]);
+    }
+    if (tid < 64) reinterpret_cast<uint32_t*>(a + kAuxW1)[tid] = pack_half2(w1[l * kFlowHidden + 2 * tid], w1[l * kFlowHidden + 2 * tid + 1]);
+    else if (tid < 128) reinterpret_cast<uint32_t*>(a + kAuxB1)[tid - 64] = pack_half2(b1[l * kFlowHidden + 2 * (tid - 64)], b1[l * kFlowHidden + 2 * (tid - 64) + 1]);
+    else {   // row n of the bias operand (K-major core matrices, 8-row groups 256 B apart): k = 0 hi, k = 1 lo
+        const int nn = tid - 128;
+        const float v = b2[l * kFlowHidden + nn];
+        const __half hi = __float2half_rn(v);
+        __half* row = reinterpret_cast<__half*>(a + kAuxB2Op + (nn >> 3) * 256 + (nn & 7) * 16);
+        row[0] = hi;
+        row[1] = __float2half_rn(v - __half2float(hi));
+    }
+    if (tid < 2) reinterpret_cast<float*>(a + kAuxB3)[tid] = b3[l * 2 + tid];
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// ring position of a running counter: index q % N and the parity of q / N, advanced without a division
+template <int N>
+struct Ring {
+    uint32_t idx = 0, par = 0;
+    __device__ __forceinline__ void next()
+    {
+        if (++idx == N) {
+            idx = 0;
+            par ^= 1u;
+        }
+    }
+};
+
+#ifdef GLABC_FLOW_TRACE
+static __device__ long long g_pipe_trace[5][64][6];   // [role M1 / X (warp 0) / Y (warp 8) / Y (warp 12) / M2][step][stamp]
+#define GLABC_PTR(role, step, i)                                                          \
+    do {                                                                                  \
+        if (blockIdx.x == 0 && lane == 0 && (step) >= 256 && (step) < 320) g_pipe_trace[role][(step)-256][i] = clock64(); \
+    } while (0)
+#else
+#define GLABC_PTR(role, step, i)
+#endif
+
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        :
+        : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+          "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld2_async(uint32_t taddr, uint32_t& r0, uint32_t& r1)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr) : "memory");
+}
+
+template <bool SAMPLE>
+__global__ void __launch_bounds__(kPipeThreads, 1) k_flow_pipe(const __grid_constant__ FlowDev W, const float* __restrict__ in, int64_t n,
+                                                               float* __restrict__ out_theta, float* __restrict__ out_lq, int tpc)
+{
+    static_assert(kFlowF16, "the pipeline is written for FP16 operands");
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sAux = smem + 2 * kFlowW2Bytes;
+    uint8_t* sOnes = sAux + 2 * kFlowAuxBytes;
+    float* sState = reinterpret_cast<float*>(sOnes + kPipeOnesBytes);   // [3][tiles][128]: z1, z2, log q
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sState + kPipeStateFloats);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kPipeBars);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int TS = kFlowTilesPerCta * kFlowTile;
+    const int T = tpc, L = W.n_blocks;
+    const int64_t n_chunks = (n + static_cast<int64_t>(T) * kFlowTile - 1) / (static_cast<int64_t>(T) * kFlowTile);
+    const int my_chunks = blockIdx.x < n_chunks ? static_cast<int>((n_chunks - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
+    const uint32_t bar0 = smem_u32(bars);
+    auto bar = [&](int i) { return bar0 + 8u * static_cast<uint32_t>(i); };
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar(kBarWFull + i), 1);
+            mbar_init(bar(kBarAuxEmpty + i), 256);
+            mbar_init(bar(kBarA1Full + i), 256);
+            mbar_init(bar(kBarA1Empty + i), 1);
+        }
+        for (int i = 0; i < kPipeSlots; ++i) {
+            mbar_init(bar(kBarAccFull + i), 1);
+            mbar_init(bar(kBarActFull + i), 256);
+            mbar_init(bar(kBarOutFull + i), 1);
+            mbar_init(bar(kBarAccEmpty + i), 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // the bias MMA's constant A operand: element (r, k) = (k < 2), K-major core matrices, 8-row groups 256 B apart
+    for (int i = tid; i < kPipeOnesBytes / 4; i += kPipeThreads) {
+        const int byte = i * 4, in_row = byte & 15, kb = (byte >> 7) & 1;   // 16-byte rows: 8 halves; second core matrix: k = 8..15
+        reinterpret_cast<uint32_t*>(sOnes)[i] = (kb == 0 && in_row == 0) ? 0x3C003C00u : 0u;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;            // accumulator slot s: columns 128 s ..; layer-1 operand buffer b: columns 384 + 64 b ..
+    const uint32_t tmem_a1 = tmem + 384u;
+    const float c2 = -1.8378770664093453f;       // -0.5 * 2 * log(2 pi)
+
+    if (warp == 16) {
+        // ------------------------------------------------ M1: hidden-layer MMAs + operand prefetch ------------------------------------------------
+        if (lane == 0) {
+            constexpr uint32_t idesc = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);     // D = F32, A = B = F16, K-major, N = 128, M = 128
+            const uint32_t sW2_addr = smem_u32(smem), sAux_addr = smem_u32(sAux);
+            const uint64_t ones_desc = umma_desc(smem_u32(sOnes), 128, 256);
+            const int total_blocks = my_chunks * L;
+            auto load_block = [&](int gb) {   // coupling block gb of this CTA's sequence -> buffer gb & 1
+                const int li = gb % L, l = SAMPLE ? li : L - 1 - li;
+                const uint32_t b = static_cast<uint32_t>(gb & 1), full = bar(kBarWFull + (gb & 1));
+                mbar_expect_tx(full, kFlowW2Bytes + kFlowAuxBytes);
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd)
+                    bulk_g2s(sW2_addr + b * kFlowW2Bytes + qd * (kFlowW2Bytes / 4),
+                             reinterpret_cast<const uint8_t*>(W.w2p) + static_cast<int64_t>(l) * kFlowW2Bytes + qd * (kFlowW2Bytes / 4),
+                             kFlowW2Bytes / 4, full);
+                bulk_g2s(sAux_addr + b * kFlowAuxBytes, W.aux + static_cast<int64_t>(l) * kFlowAuxBytes, kFlowAuxBytes, full);
+            };
+            if (total_blocks > 0) load_block(0);
+            const int kload = T - 1 < 4 ? T - 1 : 4;
+            Ring<2> a1;            // layer-1 operand buffer of step q
+            Ring<kPipeSlots> sl;   // accumulator slot of step q
+            int gb = 0;
+            [[maybe_unused]] int qs = 0;
+            for (int c = 0; c < my_chunks; ++c) {
+                int t = 0;
+                for (int s = 0; s < L * T; ++s) {
+                    GLABC_PTR(0, qs, 0);
+                    if (t == 0) mbar_wait(bar(kBarWFull + (gb & 1)), (gb >> 1) & 1);
+                    mbar_wait(bar(kBarA1Full + a1.idx), a1.par);
+                    GLABC_PTR(0, qs, 1);
+                    mbar_wait(bar(kBarAccEmpty + sl.idx), sl.par ^ 1u);
+                    GLABC_PTR(0, qs, 2);
+                    tc_fence_after();
+                    const uint32_t d = tmem + sl.idx * 128u, a = tmem_a1 + a1.idx * 64u;
+                    const uint32_t wb = sW2_addr + static_cast<uint32_t>(gb & 1) * kFlowW2Bytes;
+                    // accumulator = b2 (ones x [b2_hi, b2_lo]), then += A W2^T
+                    umma_f16_ss(d, ones_desc, umma_desc(sAux_addr + static_cast<uint32_t>(gb & 1) * kFlowAuxBytes + kAuxB2Op, 128, 256), idesc, 0u);
+#pragma unroll
+                    for (int k = 0; k < kFlowHidden / 16; ++k)
+                        umma_f16_ts(d, a + k * 8, umma_desc(wb + k * 256, 128, 2048), idesc, 1u);
+                    umma_commit(bar(kBarAccFull + sl.idx));
+                    umma_commit(bar(kBarA1Empty + a1.idx));
+                    GLABC_PTR(0, qs, 3);
+                    if (t == kload && gb + 1 < total_blocks) {   // block gb - 1 has drained: its buffer takes block gb + 1
+                        if (gb >= 1) mbar_wait(bar(kBarAuxEmpty + ((gb - 1) & 1)), ((gb - 1) >> 1) & 1);
+                        load_block(gb + 1);
+                    }
+                    a1.next();
+                    sl.next();
+                    if (++t == T) {
+                        t = 0;
+                        ++gb;
+                    }
+                    ++qs;
+                }
+            }
+        }
+    } else if (warp == 17) {
+        // ------------------------------------------------ M2: output-layer MMAs ------------------------------------------------
+        if (lane == 0) {
+            constexpr uint32_t idesc3 = (1u << 4) | ((16u >> 3) << 17) | ((128u >> 4) << 24);     // N = 16
+            const uint32_t sAux_addr = smem_u32(sAux);
+            Ring<kPipeSlots> sl;
+            int gb = 0;
+            [[maybe_unused]] int qs = 0;
+            for (int c = 0; c < my_chunks; ++c) {
+                int t = 0;
+                for (int s = 0; s < L * T; ++s) {
+                    GLABC_PTR(4, qs, 0);
+                    if (t == 0) mbar_wait(bar(kBarWFull + (gb & 1)), (gb >> 1) & 1);
+                    mbar_wait(bar(kBarActFull + sl.idx), sl.par);
+                    GLABC_PTR(4, qs, 1);
+                    tc_fence_after();
+                    // activations: the slot's columns 0..31 (k = 0..63) and 64..95 (k = 64..127); K step k accumulates into partial sum k & 3
+                    const uint32_t d = tmem + sl.idx * 128u;
+                    const uint32_t w3b = sAux_addr + static_cast<uint32_t>(gb & 1) * kFlowAuxBytes;
+#pragma unroll
+                    for (int k = 0; k < kFlowHidden / 16; ++k)
+                        umma_f16_ts(d + ((k & 2) ? 96u : 32u) + ((k & 1) ? 16u : 0u), d + (k < 4 ? k * 8 : 64 + (k - 4) * 8),
+                                    umma_desc(w3b + k * 256, 128, 2048), idesc3, k >= 4 ? 1u : 0u);
+                    umma_commit(bar(kBarOutFull + sl.idx));
+                    GLABC_PTR(4, qs, 2);
+                    sl.next();
+                    if (++t == T) {
+                        t = 0;
+                        ++gb;
+                    }
+                    ++qs;
+                }
+            }
+        }
+    } else if (warp < 8) {
+        // ------------------------------------------------ X: hidden-layer epilogue ------------------------------------------------
+        const int quad = warp & 3, half = warp >> 2;
+        const uint32_t lanebits = static_cast<uint32_t>(quad * 32) << 16;
+        Ring<kPipeSlots> sl;
+        [[maybe_unused]] int qs = 0;
+        for (int c = 0; c < my_chunks; ++c) {
+            for (int s = 0; s < L * T; ++s) {
+                if (warp == 0) GLABC_PTR(1, qs, 0);
+                mbar_wait(bar(kBarAccFull + sl.idx), sl.par);
+                if (warp == 0) GLABC_PTR(1, qs, 1);
+                tc_fence_after();
+                // this thread's 64 accumulator columns -> ReLU -> 32 packed FP16 pairs, written back over columns it has read
+                const uint32_t trow = tmem + sl.idx * 128u + lanebits + half * 64;
+                uint32_t va[32], vb[32], hp[16];
+                tmem_ld32_async(trow, va);
+                tmem_ld_wait();
+                tmem_ld32_async(trow + 32, vb);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) hp[j] = relu_pack_f16(__uint_as_float(va[2 * j]), __uint_as_float(va[2 * j + 1]));
+                tmem_st16(trow, hp);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) hp[j] = relu_pack_f16(__uint_as_float(vb[2 * j]), __uint_as_float(vb[2 * j + 1]));
+                tmem_st16(trow + 16, hp);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                mbar_arrive(bar(kBarActFull + sl.idx));
+                if (warp == 0) GLABC_PTR(1, qs, 2);
+                ++qs;
+                sl.next();
+            }
+        }
+    } else {
+        // ------------------------------------------------ Y: layer 1 and the state update ------------------------------------------------
+        const int w = warp - 8, quad = w & 3, half = w >> 2, row = quad * 32 + lane, ytid = tid - 256;
+        const uint32_t lanebits = static_cast<uint32_t>(quad * 32) << 16;
+        auto y_sync = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+        Ring<2> a1;
+        Ring<kPipeSlots> slu;
+        int gb = 0, gbu = 0;
+        for (int c = 0; c < my_chunks; ++c) {
+            const int64_t chunk = blockIdx.x + static_cast<int64_t>(c) * gridDim.x;
+            for (int r = ytid; r < T * kFlowTile; r += 256) {
+                const int64_t idx = chunk * T * kFlowTile + r;
+                float a = 0.0f, b = 0.0f, lq = 0.0f;
+                if (idx < n) {
+                    if (SAMPLE && in == nullptr) {   // q0's normals generated here (GLMCMC_NFs.py:72,127)
+                        const RoundKeys rk = expand_key(make_uint2(W.seed_lo, W.seed_hi));
+                        const uint4 wd = philox4x32_10(make_uint4(static_cast<uint32_t>(idx), static_cast<uint32_t>(idx >> 32), 0u, kSlotFlowEps), rk);
+                        box_muller(wd.x, wd.y, a, b);
+                    } else {
+                        a = in[idx * 2];
+                        b = in[idx * 2 + 1];
+                    }
+                    if (SAMPLE) {  // base DiagGaussian.forward: z = loc + exp(log_scale) * eps, log p from eps
+                        lq = c2 - ((W.base_log_scale[0] + 0.5f * (a * a)) + (W.base_log_scale[1] + 0.5f * (b * b)));
+                        a = W.base_loc[0] + expf(W.base_log_scale[0]) * a;
+                        b = W.base_loc[1] + expf(W.base_log_scale[1]) * b;
+                    }
+                }
+                sState[0 * TS + r] = a;
+                sState[1 * TS + r] = b;
+                sState[2 * TS + r] = lq;
+            }
+            y_sync();
+            int t = 0, tu = 0;
+            [[maybe_unused]] int qs = c * (L * T + kPipeLag);
+            for (int s = 0; s < L * T + kPipeLag; ++s, ++qs) {
+                if ((w & 3) == 0) GLABC_PTR(2 + half, qs, 0);
+                if (s < L * T) {   // layer 1 (K = 1) of this step's tile: this thread's 64 hidden units -> 32 packed columns of the A operand
+                    if (t == 0) mbar_wait(bar(kBarWFull + (gb & 1)), (gb >> 1) & 1);
+                    mbar_wait(bar(kBarA1Empty + a1.idx), a1.par ^ 1u);
+                    if ((w & 3) == 0) GLABC_PTR(2 + half, qs, 1);
+                    tc_fence_after();
+                    const float z1 = sState[(SAMPLE ? 0 : 1) * TS + t * kFlowTile + row];   // !SAMPLE: Permute(swap)^-1 precedes the inverse
+                    // z1 as an FP16 hi + lo pair (flow.cuh: rounding the INPUT would perturb all hidden units coherently)
+                    const float z_hi = __half2float(__float2half_rn(z1));
+                    const uint32_t zz = pack_half2(z_hi, z_hi), zl = pack_half2(z1 - z_hi, z1 - z_hi);
+                    const uint4* w1h = reinterpret_cast<const uint4*>(sAux + (gb & 1) * kFlowAuxBytes + kAuxW1) + half * 8;
+                    const uint4* b1h = reinterpret_cast<const uint4*>(sAux + (gb & 1) * kFlowAuxBytes + kAuxB1) + half * 8;
+                    uint32_t hv[32];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint4 ww = w1h[j], bb = b1h[j];
+                        hv[4 * j] = hfma2_relu(ww.x, zz, hfma2(ww.x, zl, bb.x));
+                        hv[4 * j + 1] = hfma2_relu(ww.y, zz, hfma2(ww.y, zl, bb.y));
+                        hv[4 * j + 2] = hfma2_relu(ww.z, zz, hfma2(ww.z, zl, bb.z));
+                        hv[4 * j + 3] = hfma2_relu(ww.w, zz, hfma2(ww.w, zl, bb.w));
+                    }
+                    tmem_st32(tmem_a1 + a1.idx * 64u + lanebits + half * 32, hv);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    tc_fence_before();
+                    mbar_arrive(bar(kBarA1Full + a1.idx));
+                    if ((w & 3) == 0) GLABC_PTR(2 + half, qs, 2);
+                    a1.next();
+                    if (++t == T) {
+                        t = 0;
+                        ++gb;
+                    }
+                }
+                if (s >= kPipeLag) {   // (shift, log-scale) of the tile three steps back -> affine update, log-det, Permute(swap)
+                    if (half == 0) {
+                        mbar_wait(bar(kBarOutFull + slu.idx), slu.par);
+                        if ((w & 3) == 0) GLABC_PTR(2 + half, qs, 3);
+                        tc_fence_after();
+                        uint32_t p[8];   // four partial (shift, log-scale) sums: columns 32, 48, 96, 112 of the slot
+                        const uint32_t o = tmem + slu.idx * 128u + lanebits;
+                        tmem_ld2_async(o + 32u, p[0], p[1]);
+                        tmem_ld2_async(o + 48u, p[2], p[3]);
+                        tmem_ld2_async(o + 96u, p[4], p[5]);
+                        tmem_ld2_async(o + 112u, p[6], p[7]);
+                        tmem_ld_wait();
+                        tc_fence_before();
+                        mbar_arrive(bar(kBarAccEmpty + slu.idx));
+                        const float s0 = (__uint_as_float(p[0]) + __uint_as_float(p[2])) + (__uint_as_float(p[4]) + __uint_as_float(p[6]));
+                        const float s1 = (__uint_as_float(p[1]) + __uint_as_float(p[3])) + (__uint_as_float(p[5]) + __uint_as_float(p[7]));
+                        const float* b3 = reinterpret_cast<const float*>(sAux + (gbu & 1) * kFlowAuxBytes + kAuxB3);
+                        float z1 = sState[0 * TS + tu * kFlowTile + row], z2 = sState[1 * TS + tu * kFlowTile + row];
+                        if (!SAMPLE) {  // Permute(swap)^-1 precedes the coupling's inverse
+                            const float tmp = z1;
+                            z1 = z2;
+                            z2 = tmp;
+                        }
+                        const float sh = s0 + b3[0];  // shift     = param[:, 0::2]
+                        const float sc = s1 + b3[1];  // log-scale = param[:, 1::2]
+                        float lq = sState[2 * TS + tu * kFlowTile + row];
+                        if (SAMPLE) {
+                            const float z2n = fmaf(z2, expf(sc), sh);  // z2 * exp(s) + shift; log q -= log det
+                            lq -= sc;
+                            sState[0 * TS + tu * kFlowTile + row] = z2n;  // Permute(swap)
+                            sState[1 * TS + tu * kFlowTile + row] = z1;
+                        } else {
+                            const float z2n = (z2 - sh) * expf(-sc);     // inverse; log det = -s
+                            lq -= sc;
+                            sState[0 * TS + tu * kFlowTile + row] = z1;
+                            sState[1 * TS + tu * kFlowTile + row] = z2n;
+                        }
+                        sState[2 * TS + tu * kFlowTile + row] = lq;
+                    }
+                    slu.next();
+                    if (++tu == T) {   // every read of this coupling block's operands is behind this thread
+                        tu = 0;
+                        mbar_arrive(bar(kBarAuxEmpty + (gbu & 1)));
+                        ++gbu;
+                    }
+                }
+                if ((w & 3) == 0) GLABC_PTR(2 + half, qs, 4);
+                y_sync();   // the state rows written by half 0 are read by half 1 (layer 1 of the same tile, next coupling block)
+            }
+            for (int r = ytid; r < T * kFlowTile; r += 256) {
+                const int64_t idx = chunk * T * kFlowTile + r;
+                if (idx >= n) continue;
+                const float a = sState[0 * TS + r], b = sState[1 * TS + r];
+                float lq = sState[2 * TS + r];
+                if (SAMPLE) {
+                    out_theta[idx * 2] = a;
+                    out_theta[idx * 2 + 1] = b;
+                } else {  // + base.log_prob(z)
+                    if (out_theta != nullptr) {   // the latent z = f^-1(x)
+                        out_theta[idx * 2] = a;
+                        out_theta[idx * 2 + 1] = b;
+                    }
+                    const float r0 = (a - W.base_loc[0]) / expf(W.base_log_scale[0]);
+                    const float r1 = (b - W.base_loc[1]) / expf(W.base_log_scale[1]);
+                    lq += c2 - ((W.base_log_scale[0] + 0.5f * (r0 * r0)) + (W.base_log_scale[1] + 0.5f * (r1 * r1)));
+                }
+                out_lq[idx] = lq;
+            }
+            y_sync();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+}  // namespace glabc

@@ -43,17 +43,6 @@ __device__ __forceinline__ void split_pack(float a, float b, uint32_t& hi, uint3
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - f.y), "f"(a - f.x));
 }
 
-__device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        :
-        : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
 // the three MMAs of one split-precision GEMM: (A_hi + A_lo)(B_hi + B_lo) without the lo x lo term.
 // a_step / b_step: byte advance of the operand per K = 16 step (256 for a K-major view, 4096 for an MN-major view)
 __device__ __forceinline__ void gemm_split(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, bool a_mn, bool b_mn,
