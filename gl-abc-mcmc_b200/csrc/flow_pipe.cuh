@@ -31,9 +31,9 @@
 
 namespace glabc {
 
-constexpr int kPipeThreads = 18 * 32;
+constexpr int kPipeThreads = 19 * 32;
 constexpr int kPipeSlots = 3;        // accumulator slots
-constexpr int kPipeLag = 3;          // Y updates tile q - 3 after layer 1 of tile q (a chunk needs more tiles than this)
+constexpr int kPipeLag = 2;          // X updates tile q - 2 before the epilogue of tile q (a chunk needs more tiles than this + 1)
 constexpr int kPipeMinTiles = 4;
 // per coupling block, pre-packed in global memory: [W3 as a 16 x 128 FP16 UMMA operand 4096][w1 FP16 pairs 256][b1 FP16 pairs 256]
 // [b3 fp32 8 + pad 120][b2 as a 128 x 16 FP16 UMMA operand: k = 0 FP16(b2), k = 1 FP16(b2 - FP16(b2)), 4096]
@@ -41,9 +41,9 @@ constexpr int kAuxW1 = 4096, kAuxB1 = 4352, kAuxB3 = 4608, kAuxB2Op = 4736;
 static_assert(kAuxB2Op + 4096 == kFlowAuxBytes, "aux blob layout");
 constexpr int kPipeOnesBytes = 4096;   // the constant A operand of the bias MMA: 128 x 16 FP16, ones in k = 0, 1
 constexpr int kPipeStateFloats = 3 * kFlowTilesPerCta * kFlowTile;
-constexpr int kPipeBars = 20;
+constexpr int kPipeBars = 20 + kFlowTilesPerCta;
 constexpr int kPipeSmemBytes = 2 * kFlowW2Bytes + 2 * kFlowAuxBytes + kPipeOnesBytes + kPipeStateFloats * 4 + kPipeBars * 8 + 16;
-enum : int { kBarWFull = 0, kBarAuxEmpty = 2, kBarA1Full = 4, kBarA1Empty = 6, kBarAccFull = 8, kBarActFull = 11, kBarOutFull = 14, kBarAccEmpty = 17 };
+enum : int { kBarWFull = 0, kBarAuxEmpty = 2, kBarA1Full = 4, kBarA1Empty = 6, kBarAccFull = 8, kBarActFull = 11, kBarOutFull = 14, kBarAccEmpty = 17, kBarStateFull = 20 };
 
 static __global__ void __launch_bounds__(256) k_flow_pack_aux(const float* __restrict__ w1, const float* __restrict__ b1,
                                                               const float* __restrict__ b2, const float* __restrict__ w3,
@@ -93,7 +93,7 @@ struct Ring {
 };
 
 #ifdef GLABC_FLOW_TRACE
-static __device__ long long g_pipe_trace[5][64][6];   // [role M1 / X (warp 0) / Y (warp 8) / Y (warp 12) / M2][step][stamp]
+static __device__ long long g_pipe_trace[5][64][6];   // [role M1 (both threads) / X (warp 0) / Y (warp 8) / Y (warp 12) / M2][step][stamp]
 #define GLABC_PTR(role, step, i)                                                          \
     do {                                                                                  \
         if (blockIdx.x == 0 && lane == 0 && (step) >= 256 && (step) < 320) g_pipe_trace[role][(step)-256][i] = clock64(); \
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_flow_pipe(const __grid_cons
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar(kBarWFull + i), 1);
-            mbar_init(bar(kBarAuxEmpty + i), 256);
+            mbar_init(bar(kBarAuxEmpty + i), 384);
             mbar_init(bar(kBarA1Full + i), 256);
             mbar_init(bar(kBarA1Empty + i), 1);
         }
@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_flow_pipe(const __grid_cons
             mbar_init(bar(kBarOutFull + i), 1);
             mbar_init(bar(kBarAccEmpty + i), 128);
         }
+        for (int i = 0; i < kFlowTilesPerCta; ++i) mbar_init(bar(kBarStateFull + i), 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // the bias MMA's constant A operand: element (r, k) = (k < 2), K-major core matrices, 8-row groups 256 B apart
@@ -181,9 +182,11 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_flow_pipe(const __grid_cons
     const uint32_t tmem_a1 = tmem + 384u;
     const float c2 = -1.8378770664093453f;       // -0.5 * 2 * log(2 pi)
 
-    if (warp == 16) {
+    if (warp == 16 || warp == 17) {
         // ------------------------------------------------ M1: hidden-layer MMAs + operand prefetch ------------------------------------------------
+        // two issuing threads, even and odd steps: while one sits in the tensor pipe's queue the other gets through its waits
         if (lane == 0) {
+            const uint32_t mine = static_cast<uint32_t>(warp - 16);
             constexpr uint32_t idesc = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);     // D = F32, A = B = F16, K-major, N = 128, M = 128
             const uint32_t sW2_addr = smem_u32(smem), sAux_addr = smem_u32(sAux);
             const uint64_t ones_desc = umma_desc(smem_u32(sOnes), 128, 256);
@@ -199,35 +202,40 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_flow_pipe(const __grid_cons
                              kFlowW2Bytes / 4, full);
                 bulk_g2s(sAux_addr + b * kFlowAuxBytes, W.aux + static_cast<int64_t>(l) * kFlowAuxBytes, kFlowAuxBytes, full);
             };
-            if (total_blocks > 0) load_block(0);
+            if (mine == 0 && total_blocks > 0) load_block(0);
             const int kload = T - 1 < 4 ? T - 1 : 4;
             Ring<2> a1;            // layer-1 operand buffer of step q
             Ring<kPipeSlots> sl;   // accumulator slot of step q
-            int gb = 0;
-            [[maybe_unused]] int qs = 0;
+            int gb = 0, gb_seen = -1;
+            uint32_t q = 0;
             for (int c = 0; c < my_chunks; ++c) {
                 int t = 0;
-                for (int s = 0; s < L * T; ++s) {
-                    GLABC_PTR(0, qs, 0);
-                    if (t == 0) mbar_wait(bar(kBarWFull + (gb & 1)), (gb >> 1) & 1);
-                    mbar_wait(bar(kBarA1Full + a1.idx), a1.par);
-                    GLABC_PTR(0, qs, 1);
-                    mbar_wait(bar(kBarAccEmpty + sl.idx), sl.par ^ 1u);
-                    GLABC_PTR(0, qs, 2);
-                    tc_fence_after();
-                    const uint32_t d = tmem + sl.idx * 128u, a = tmem_a1 + a1.idx * 64u;
-                    const uint32_t wb = sW2_addr + static_cast<uint32_t>(gb & 1) * kFlowW2Bytes;
-                    // accumulator = b2 (ones x [b2_hi, b2_lo]), then += A W2^T
-                    umma_f16_ss(d, ones_desc, umma_desc(sAux_addr + static_cast<uint32_t>(gb & 1) * kFlowAuxBytes + kAuxB2Op, 128, 256), idesc, 0u);
+                for (int s = 0; s < L * T; ++s, ++q) {
+                    if ((q & 1u) == mine) {
+                        GLABC_PTR(0, q, 0);
+                        if (gb != gb_seen) {
+                            mbar_wait(bar(kBarWFull + (gb & 1)), (gb >> 1) & 1);
+                            gb_seen = gb;
+                        }
+                        mbar_wait(bar(kBarA1Full + a1.idx), a1.par);
+                        GLABC_PTR(0, q, 1);
+                        mbar_wait(bar(kBarAccEmpty + sl.idx), sl.par ^ 1u);
+                        GLABC_PTR(0, q, 2);
+                        tc_fence_after();
+                        const uint32_t d = tmem + sl.idx * 128u, a = tmem_a1 + a1.idx * 64u;
+                        const uint32_t wb = sW2_addr + static_cast<uint32_t>(gb & 1) * kFlowW2Bytes;
+                        // accumulator = b2 (ones x [b2_hi, b2_lo]), then += A W2^T
+                        umma_f16_ss(d, ones_desc, umma_desc(sAux_addr + static_cast<uint32_t>(gb & 1) * kFlowAuxBytes + kAuxB2Op, 128, 256), idesc, 0u);
 #pragma unroll
-                    for (int k = 0; k < kFlowHidden / 16; ++k)
-                        umma_f16_ts(d, a + k * 8, umma_desc(wb + k * 256, 128, 2048), idesc, 1u);
-                    umma_commit(bar(kBarAccFull + sl.idx));
-                    umma_commit(bar(kBarA1Empty + a1.idx));
-                    GLABC_PTR(0, qs, 3);
-                    if (t == kload && gb + 1 < total_blocks) {   // block gb - 1 has drained: its buffer takes block gb + 1
-                        if (gb >= 1) mbar_wait(bar(kBarAuxEmpty + ((gb - 1) & 1)), ((gb - 1) >> 1) & 1);
-                        load_block(gb + 1);
+                        for (int k = 0; k < kFlowHidden / 16; ++k)
+                            umma_f16_ts(d, a + k * 8, umma_desc(wb + k * 256, 128, 2048), idesc, 1u);
+                        umma_commit(bar(kBarAccFull + sl.idx));
+                        umma_commit(bar(kBarA1Empty + a1.idx));
+                        GLABC_PTR(0, q, 3);
+                        if (t == kload && gb + 1 < total_blocks) {   // block gb - 1 has drained: its buffer takes block gb + 1
+                            if (gb >= 1) mbar_wait(bar(kBarAuxEmpty + ((gb - 1) & 1)), ((gb - 1) >> 1) & 1);
+                            load_block(gb + 1);
+                        }
                     }
                     a1.next();
                     sl.next();
@@ -235,11 +243,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_flow_pipe(const __grid_cons
                         t = 0;
                         ++gb;
                     }
-                    ++qs;
                 }
             }
         }
-    } else if (warp == 17) {
+    } else if (warp == 18) {
         // ------------------------------------------------ M2: output-layer MMAs ------------------------------------------------
         if (lane == 0) {
             constexpr uint32_t idesc3 = (1u << 4) | ((16u >> 3) << 17) | ((128u >> 4) << 24);     // N = 16
@@ -274,110 +281,19 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_flow_pipe(const __grid_cons
             }
         }
     } else if (warp < 8) {
-        // ------------------------------------------------ X: hidden-layer epilogue ------------------------------------------------
-        const int quad = warp & 3, half = warp >> 2;
+        // ------------------------------------------------ X: state update of tile q - 2, hidden-layer epilogue of tile q ------------------------------------------------
+        const int quad = warp & 3, half = warp >> 2, row = quad * 32 + lane;
         const uint32_t lanebits = static_cast<uint32_t>(quad * 32) << 16;
-        Ring<kPipeSlots> sl;
+        Ring<kPipeSlots> sl, slu;
+        int gbu = 0;
         [[maybe_unused]] int qs = 0;
         for (int c = 0; c < my_chunks; ++c) {
-            for (int s = 0; s < L * T; ++s) {
-                if (warp == 0) GLABC_PTR(1, qs, 0);
-                mbar_wait(bar(kBarAccFull + sl.idx), sl.par);
-                if (warp == 0) GLABC_PTR(1, qs, 1);
-                tc_fence_after();
-                // this thread's 64 accumulator columns -> ReLU -> 32 packed FP16 pairs, written back over columns it has read
-                const uint32_t trow = tmem + sl.idx * 128u + lanebits + half * 64;
-                uint32_t va[32], vb[32], hp[16];
-                tmem_ld32_async(trow, va);
-                tmem_ld_wait();
-                tmem_ld32_async(trow + 32, vb);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) hp[j] = relu_pack_f16(__uint_as_float(va[2 * j]), __uint_as_float(va[2 * j + 1]));
-                tmem_st16(trow, hp);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 16; ++j) hp[j] = relu_pack_f16(__uint_as_float(vb[2 * j]), __uint_as_float(vb[2 * j + 1]));
-                tmem_st16(trow + 16, hp);
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                tc_fence_before();
-                mbar_arrive(bar(kBarActFull + sl.idx));
-                if (warp == 0) GLABC_PTR(1, qs, 2);
-                ++qs;
-                sl.next();
-            }
-        }
-    } else {
-        // ------------------------------------------------ Y: layer 1 and the state update ------------------------------------------------
-        const int w = warp - 8, quad = w & 3, half = w >> 2, row = quad * 32 + lane, ytid = tid - 256;
-        const uint32_t lanebits = static_cast<uint32_t>(quad * 32) << 16;
-        auto y_sync = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
-        Ring<2> a1;
-        Ring<kPipeSlots> slu;
-        int gb = 0, gbu = 0;
-        for (int c = 0; c < my_chunks; ++c) {
-            const int64_t chunk = blockIdx.x + static_cast<int64_t>(c) * gridDim.x;
-            for (int r = ytid; r < T * kFlowTile; r += 256) {
-                const int64_t idx = chunk * T * kFlowTile + r;
-                float a = 0.0f, b = 0.0f, lq = 0.0f;
-                if (idx < n) {
-                    if (SAMPLE && in == nullptr) {   // q0's normals generated here (GLMCMC_NFs.py:72,127)
-                        const RoundKeys rk = expand_key(make_uint2(W.seed_lo, W.seed_hi));
-                        const uint4 wd = philox4x32_10(make_uint4(static_cast<uint32_t>(idx), static_cast<uint32_t>(idx >> 32), 0u, kSlotFlowEps), rk);
-                        box_muller(wd.x, wd.y, a, b);
-                    } else {
-                        a = in[idx * 2];
-                        b = in[idx * 2 + 1];
-                    }
-                    if (SAMPLE) {  // base DiagGaussian.forward: z = loc + exp(log_scale) * eps, log p from eps
-                        lq = c2 - ((W.base_log_scale[0] + 0.5f * (a * a)) + (W.base_log_scale[1] + 0.5f * (b * b)));
-                        a = W.base_loc[0] + expf(W.base_log_scale[0]) * a;
-                        b = W.base_loc[1] + expf(W.base_log_scale[1]) * b;
-                    }
-                }
-                sState[0 * TS + r] = a;
-                sState[1 * TS + r] = b;
-                sState[2 * TS + r] = lq;
-            }
-            y_sync();
-            int t = 0, tu = 0;
-            [[maybe_unused]] int qs = c * (L * T + kPipeLag);
+            int tu = 0;
             for (int s = 0; s < L * T + kPipeLag; ++s, ++qs) {
-                if ((w & 3) == 0) GLABC_PTR(2 + half, qs, 0);
-                if (s < L * T) {   // layer 1 (K = 1) of this step's tile: this thread's 64 hidden units -> 32 packed columns of the A operand
-                    if (t == 0) mbar_wait(bar(kBarWFull + (gb & 1)), (gb >> 1) & 1);
-                    mbar_wait(bar(kBarA1Empty + a1.idx), a1.par ^ 1u);
-                    if ((w & 3) == 0) GLABC_PTR(2 + half, qs, 1);
-                    tc_fence_after();
-                    const float z1 = sState[(SAMPLE ? 0 : 1) * TS + t * kFlowTile + row];   // !SAMPLE: Permute(swap)^-1 precedes the inverse
-                    // z1 as an FP16 hi + lo pair (flow.cuh: rounding the INPUT would perturb all hidden units coherently)
-                    const float z_hi = __half2float(__float2half_rn(z1));
-                    const uint32_t zz = pack_half2(z_hi, z_hi), zl = pack_half2(z1 - z_hi, z1 - z_hi);
-                    const uint4* w1h = reinterpret_cast<const uint4*>(sAux + (gb & 1) * kFlowAuxBytes + kAuxW1) + half * 8;
-                    const uint4* b1h = reinterpret_cast<const uint4*>(sAux + (gb & 1) * kFlowAuxBytes + kAuxB1) + half * 8;
-                    uint32_t hv[32];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const uint4 ww = w1h[j], bb = b1h[j];
-                        hv[4 * j] = hfma2_relu(ww.x, zz, hfma2(ww.x, zl, bb.x));
-                        hv[4 * j + 1] = hfma2_relu(ww.y, zz, hfma2(ww.y, zl, bb.y));
-                        hv[4 * j + 2] = hfma2_relu(ww.z, zz, hfma2(ww.z, zl, bb.z));
-                        hv[4 * j + 3] = hfma2_relu(ww.w, zz, hfma2(ww.w, zl, bb.w));
-                    }
-                    tmem_st32(tmem_a1 + a1.idx * 64u + lanebits + half * 32, hv);
-                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                    tc_fence_before();
-                    mbar_arrive(bar(kBarA1Full + a1.idx));
-                    if ((w & 3) == 0) GLABC_PTR(2 + half, qs, 2);
-                    a1.next();
-                    if (++t == T) {
-                        t = 0;
-                        ++gb;
-                    }
-                }
-                if (s >= kPipeLag) {   // (shift, log-scale) of the tile three steps back -> affine update, log-det, Permute(swap)
+                if (warp == 0) GLABC_PTR(1, qs, 0);
+                if (s >= kPipeLag) {   // (shift, log-scale) of the tile two steps back -> affine update, log-det, Permute(swap)
                     if (half == 0) {
                         mbar_wait(bar(kBarOutFull + slu.idx), slu.par);
-                        if ((w & 3) == 0) GLABC_PTR(2 + half, qs, 3);
                         tc_fence_after();
                         uint32_t p[8];   // four partial (shift, log-scale) sums: columns 32, 48, 96, 112 of the slot
                         const uint32_t o = tmem + slu.idx * 128u + lanebits;
@@ -412,17 +328,113 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_flow_pipe(const __grid_cons
                             sState[1 * TS + tu * kFlowTile + row] = z2n;
                         }
                         sState[2 * TS + tu * kFlowTile + row] = lq;
+                        mbar_arrive(bar(kBarStateFull + tu));   // Y: layer 1 of this tile in the next coupling block / the chunk's output
+                        if (tu == T - 1) mbar_arrive(bar(kBarAuxEmpty + (gbu & 1)));   // b3 of this coupling block is behind this thread
                     }
                     slu.next();
-                    if (++tu == T) {   // every read of this coupling block's operands is behind this thread
+                    if (++tu == T) {
                         tu = 0;
-                        mbar_arrive(bar(kBarAuxEmpty + (gbu & 1)));
                         ++gbu;
                     }
                 }
-                if ((w & 3) == 0) GLABC_PTR(2 + half, qs, 4);
-                y_sync();   // the state rows written by half 0 are read by half 1 (layer 1 of the same tile, next coupling block)
+                if (warp == 0) GLABC_PTR(1, qs, 1);
+                if (s < L * T) {
+                    mbar_wait(bar(kBarAccFull + sl.idx), sl.par);
+                    if (warp == 0) GLABC_PTR(1, qs, 2);
+                    tc_fence_after();
+                    // this thread's 64 accumulator columns -> ReLU -> 32 packed FP16 pairs, written back over columns it has read
+                    const uint32_t trow = tmem + sl.idx * 128u + lanebits + half * 64;
+                    uint32_t va[32], vb[32], hp[16];
+                    tmem_ld32_async(trow, va);
+                    tmem_ld_wait();
+                    tmem_ld32_async(trow + 32, vb);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) hp[j] = relu_pack_f16(__uint_as_float(va[2 * j]), __uint_as_float(va[2 * j + 1]));
+                    tmem_st16(trow, hp);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) hp[j] = relu_pack_f16(__uint_as_float(vb[2 * j]), __uint_as_float(vb[2 * j + 1]));
+                    tmem_st16(trow + 16, hp);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    tc_fence_before();
+                    mbar_arrive(bar(kBarActFull + sl.idx));
+                    if (warp == 0) GLABC_PTR(1, qs, 3);
+                    sl.next();
+                }
             }
+        }
+    } else {
+        // ------------------------------------------------ Y: chunk input / output, layer 1 ------------------------------------------------
+        const int w = warp - 8, quad = w & 3, half = w >> 2, row = quad * 32 + lane, ytid = tid - 256;
+        const uint32_t lanebits = static_cast<uint32_t>(quad * 32) << 16;
+        auto y_sync = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+        Ring<2> a1;
+        int gb = 0;
+        for (int c = 0; c < my_chunks; ++c) {
+            const int64_t chunk = blockIdx.x + static_cast<int64_t>(c) * gridDim.x;
+            for (int r = ytid; r < T * kFlowTile; r += 256) {
+                const int64_t idx = chunk * T * kFlowTile + r;
+                float a = 0.0f, b = 0.0f, lq = 0.0f;
+                if (idx < n) {
+                    if (SAMPLE && in == nullptr) {   // q0's normals generated here (GLMCMC_NFs.py:72,127)
+                        const RoundKeys rk = expand_key(make_uint2(W.seed_lo, W.seed_hi));
+                        const uint4 wd = philox4x32_10(make_uint4(static_cast<uint32_t>(idx), static_cast<uint32_t>(idx >> 32), 0u, kSlotFlowEps), rk);
+                        box_muller(wd.x, wd.y, a, b);
+                    } else {
+                        a = in[idx * 2];
+                        b = in[idx * 2 + 1];
+                    }
+                    if (SAMPLE) {  // base DiagGaussian.forward: z = loc + exp(log_scale) * eps, log p from eps
+                        lq = c2 - ((W.base_log_scale[0] + 0.5f * (a * a)) + (W.base_log_scale[1] + 0.5f * (b * b)));
+                        a = W.base_loc[0] + expf(W.base_log_scale[0]) * a;
+                        b = W.base_loc[1] + expf(W.base_log_scale[1]) * b;
+                    }
+                }
+                sState[0 * TS + r] = a;
+                sState[1 * TS + r] = b;
+                sState[2 * TS + r] = lq;
+            }
+            y_sync();
+            int t = 0;
+            const int gb0 = gb;
+            [[maybe_unused]] int qs = c * (L * T);
+            for (int s = 0; s < L * T; ++s, ++qs) {
+                if ((w & 3) == 0) GLABC_PTR(2 + half, qs, 0);
+                {   // layer 1 (K = 1) of this step's tile: this thread's 64 hidden units -> 32 packed columns of the A operand
+                    if (t == 0) mbar_wait(bar(kBarWFull + (gb & 1)), (gb >> 1) & 1);
+                    if (gb != gb0) mbar_wait(bar(kBarStateFull + t), (gb - 1) & 1);   // X has updated this tile in the previous coupling block
+                    mbar_wait(bar(kBarA1Empty + a1.idx), a1.par ^ 1u);
+                    if ((w & 3) == 0) GLABC_PTR(2 + half, qs, 1);
+                    tc_fence_after();
+                    const float z1 = sState[(SAMPLE ? 0 : 1) * TS + t * kFlowTile + row];   // !SAMPLE: Permute(swap)^-1 precedes the inverse
+                    // z1 as an FP16 hi + lo pair (flow.cuh: rounding the INPUT would perturb all hidden units coherently)
+                    const float z_hi = __half2float(__float2half_rn(z1));
+                    const uint32_t zz = pack_half2(z_hi, z_hi), zl = pack_half2(z1 - z_hi, z1 - z_hi);
+                    const uint4* w1h = reinterpret_cast<const uint4*>(sAux + (gb & 1) * kFlowAuxBytes + kAuxW1) + half * 8;
+                    const uint4* b1h = reinterpret_cast<const uint4*>(sAux + (gb & 1) * kFlowAuxBytes + kAuxB1) + half * 8;
+                    uint32_t hv[32];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint4 ww = w1h[j], bb = b1h[j];
+                        hv[4 * j] = hfma2_relu(ww.x, zz, hfma2(ww.x, zl, bb.x));
+                        hv[4 * j + 1] = hfma2_relu(ww.y, zz, hfma2(ww.y, zl, bb.y));
+                        hv[4 * j + 2] = hfma2_relu(ww.z, zz, hfma2(ww.z, zl, bb.z));
+                        hv[4 * j + 3] = hfma2_relu(ww.w, zz, hfma2(ww.w, zl, bb.w));
+                    }
+                    tmem_st32(tmem_a1 + a1.idx * 64u + lanebits + half * 32, hv);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    tc_fence_before();
+                    mbar_arrive(bar(kBarA1Full + a1.idx));
+                    if ((w & 3) == 0) GLABC_PTR(2 + half, qs, 2);
+                    a1.next();
+                    if (++t == T) {   // w1 / b1 of this coupling block are behind this thread
+                        t = 0;
+                        mbar_arrive(bar(kBarAuxEmpty + (gb & 1)));
+                        ++gb;
+                    }
+                }
+            }
+            for (int tt = 0; tt < T; ++tt) mbar_wait(bar(kBarStateFull + tt), (gb - 1) & 1);   // the last coupling block's updates
             for (int r = ytid; r < T * kFlowTile; r += 256) {
                 const int64_t idx = chunk * T * kFlowTile + r;
                 if (idx >= n) continue;

@@ -35,8 +35,8 @@ if hasattr(lib, "glabc_debug_pipe_trace") and mode == "fast":
     assert rc == 0, rc
     base = buf[buf > 0].min()
     np.set_printoptions(linewidth=250)
-    names = ["M1: top, a1_full, acc_empty, MMA1 issued", "X warp 0: top, acc_full, done",
-             "Y warp 8: top, a1_empty, L1 done, out_full, update done", "Y warp 12: top, a1_empty, L1 done, -, end",
+    names = ["M1 (two threads, alternate steps): top, a1_full, acc_empty, MMA1 issued", "X warp 0: top, update done, acc_full, E1 done",
+             "Y warp 8: top, waits done, L1 done", "Y warp 12: top, waits done, L1 done",
              "M2: top, act_full, MMA2 issued"]
     for r in range(5):
         print(names[r])
