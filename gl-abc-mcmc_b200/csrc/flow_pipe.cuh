@@ -79,6 +79,15 @@ __device__ __forceinline__ void umma_commit(uint32_t bar)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// one lane of a converged warp (the warp runs the issue loops together: a lone diverged thread pays ~45 cycles per
+// tcgen05.mma for the compiler's elect / R2UR.BROADCAST sequence; from a converged warp the MMAs issue back to back)
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t p;
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(p));
+    return p != 0;
+}
+
 // ring position of a running counter: index q % N and the parity of q / N, advanced without a division
 template <int N>
 struct Ring {
@@ -185,7 +194,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_flow_pipe(const __grid_cons
     if (warp == 16 || warp == 17) {
         // ------------------------------------------------ M1: hidden-layer MMAs + operand prefetch ------------------------------------------------
         // two issuing threads, even and odd steps: while one sits in the tensor pipe's queue the other gets through its waits
-        if (lane == 0) {
+        {
+            const bool lead = elect_one();
             const uint32_t mine = static_cast<uint32_t>(warp - 16);
             constexpr uint32_t idesc = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);     // D = F32, A = B = F16, K-major, N = 128, M = 128
             const uint32_t sW2_addr = smem_u32(smem), sAux_addr = smem_u32(sAux);
@@ -194,6 +204,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_flow_pipe(const __grid_cons
             auto load_block = [&](int gb) {   // coupling block gb of this CTA's sequence -> buffer gb & 1
                 const int li = gb % L, l = SAMPLE ? li : L - 1 - li;
                 const uint32_t b = static_cast<uint32_t>(gb & 1), full = bar(kBarWFull + (gb & 1));
+                if (!lead) return;
                 mbar_expect_tx(full, kFlowW2Bytes + kFlowAuxBytes);
 #pragma unroll
                 for (int qd = 0; qd < 4; ++qd)
@@ -224,13 +235,19 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_flow_pipe(const __grid_cons
                         tc_fence_after();
                         const uint32_t d = tmem + sl.idx * 128u, a = tmem_a1 + a1.idx * 64u;
                         const uint32_t wb = sW2_addr + static_cast<uint32_t>(gb & 1) * kFlowW2Bytes;
-                        // accumulator = b2 (ones x [b2_hi, b2_lo]), then += A W2^T
-                        umma_f16_ss(d, ones_desc, umma_desc(sAux_addr + static_cast<uint32_t>(gb & 1) * kFlowAuxBytes + kAuxB2Op, 128, 256), idesc, 0u);
+                        const uint64_t b2_desc = umma_desc(sAux_addr + static_cast<uint32_t>(gb & 1) * kFlowAuxBytes + kAuxB2Op, 128, 256);
+                        const uint64_t w2_desc = umma_desc(wb, 128, 2048);
+                        const uint32_t bar_acc = bar(kBarAccFull + sl.idx), bar_a1 = bar(kBarA1Empty + a1.idx);
+                        if (lead) {
+                            // accumulator = b2 (ones x [b2_hi, b2_lo]), then += A W2^T
+                            umma_f16_ss(d, ones_desc, b2_desc, idesc, 0u);
 #pragma unroll
-                        for (int k = 0; k < kFlowHidden / 16; ++k)
-                            umma_f16_ts(d, a + k * 8, umma_desc(wb + k * 256, 128, 2048), idesc, 1u);
-                        umma_commit(bar(kBarAccFull + sl.idx));
-                        umma_commit(bar(kBarA1Empty + a1.idx));
+                            for (int k = 0; k < kFlowHidden / 16; ++k)
+                                umma_f16_ts(d, a + k * 8, w2_desc + static_cast<uint64_t>(k * (256 >> 4)), idesc, 1u);   // the descriptor's address field: 16-byte units
+                            umma_commit(bar_acc);
+                            umma_commit(bar_a1);
+                        }
+                        __syncwarp();
                         GLABC_PTR(0, q, 3);
                         if (t == kload && gb + 1 < total_blocks) {   // block gb - 1 has drained: its buffer takes block gb + 1
                             if (gb >= 1) mbar_wait(bar(kBarAuxEmpty + ((gb - 1) & 1)), ((gb - 1) >> 1) & 1);
@@ -248,7 +265,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_flow_pipe(const __grid_cons
         }
     } else if (warp == 18) {
         // ------------------------------------------------ M2: output-layer MMAs ------------------------------------------------
-        if (lane == 0) {
+        {
+            const bool lead = elect_one();
             constexpr uint32_t idesc3 = (1u << 4) | ((16u >> 3) << 17) | ((128u >> 4) << 24);     // N = 16
             const uint32_t sAux_addr = smem_u32(sAux);
             Ring<kPipeSlots> sl;
@@ -265,11 +283,16 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_flow_pipe(const __grid_cons
                     // activations: the slot's columns 0..31 (k = 0..63) and 64..95 (k = 64..127); K step k accumulates into partial sum k & 3
                     const uint32_t d = tmem + sl.idx * 128u;
                     const uint32_t w3b = sAux_addr + static_cast<uint32_t>(gb & 1) * kFlowAuxBytes;
+                    const uint64_t w3_desc = umma_desc(w3b, 128, 2048);
+                    const uint32_t bar_out = bar(kBarOutFull + sl.idx);
+                    if (lead) {
 #pragma unroll
-                    for (int k = 0; k < kFlowHidden / 16; ++k)
-                        umma_f16_ts(d + ((k & 2) ? 96u : 32u) + ((k & 1) ? 16u : 0u), d + (k < 4 ? k * 8 : 64 + (k - 4) * 8),
-                                    umma_desc(w3b + k * 256, 128, 2048), idesc3, k >= 4 ? 1u : 0u);
-                    umma_commit(bar(kBarOutFull + sl.idx));
+                        for (int k = 0; k < kFlowHidden / 16; ++k)
+                            umma_f16_ts(d + ((k & 2) ? 96u : 32u) + ((k & 1) ? 16u : 0u), d + (k < 4 ? k * 8 : 64 + (k - 4) * 8),
+                                        w3_desc + static_cast<uint64_t>(k * (256 >> 4)), idesc3, k >= 4 ? 1u : 0u);
+                        umma_commit(bar_out);
+                    }
+                    __syncwarp();
                     GLABC_PTR(4, qs, 2);
                     sl.next();
                     if (++t == T) {
