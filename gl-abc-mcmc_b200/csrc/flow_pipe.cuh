@@ -21,10 +21,9 @@
 // The output layer (M128 N16 K128) is eight K = 16 MMAs; chained into ONE accumulator each waits for its predecessor (~100
 // cycles apiece, measured), so they go into four independent 16-column accumulators (two MMAs each) that the update sums.
 // TMEM (512 columns): three 128-column accumulator slots and two 64-column layer-1 operand buffers.  The epilogue writes
-// the packed activations back INTO its accumulator slot (columns 0..31 and 64..95, each thread over columns it has just
-// read) and the output-layer MMA (M128 N16 K128) puts its 16 result columns into the same slot (columns 32..47), so the
+// the packed activations back INTO its accumulator slot (columns 0..63, each thread behind its own reads) and the output-layer MMA (M128 N16 K128) puts its 16 result columns into the same slot (columns 32..47), so the
 // layer-1 buffer of a tile is free as soon as its first MMA completes and three tiles are in flight instead of two
-// (output-layer partial sums: columns 32..63 and 96..127 of the slot):
+// (output-layer partial sums: columns 64..127 of the slot):
 //   window of MMA1(q):  X works on tile q-1, Y on layer 1 of q+1 and the update of q-2, MMA2(q-1) queues behind MMA1(q).
 #pragma once
 #include "flow.cuh"
@@ -33,8 +32,7 @@ namespace glabc {
 
 constexpr int kPipeThreads = 19 * 32;
 constexpr int kPipeSlots = 3;        // accumulator slots
-constexpr int kPipeLag = 2;          // X updates tile q - 2 before the epilogue of tile q (a chunk needs more tiles than this + 1)
-constexpr int kPipeMinTiles = 4;
+constexpr int kPipeMinTiles = 2;
 // per coupling block, pre-packed in global memory: [W3 as a 16 x 128 FP16 UMMA operand 4096][w1 FP16 pairs 256][b1 FP16 pairs 256]
 // [b3 fp32 8 + pad 120][b2 as a 128 x 16 FP16 UMMA operand: k = 0 FP16(b2), k = 1 FP16(b2 - FP16(b2)), 4096]
 constexpr int kAuxW1 = 4096, kAuxB1 = 4352, kAuxB3 = 4608, kAuxB2Op = 4736;
@@ -88,6 +86,21 @@ __device__ __forceinline__ bool elect_one()
     return p != 0;
 }
 
+// shared-space loads by 32-bit address (a generic pointer into dynamic shared memory costs an S2R + LEA per use)
+__device__ __forceinline__ float lds_f32(uint32_t a)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+
 // ring position of a running counter: index q % N and the parity of q / N, advanced without a division
 template <int N>
 struct Ring {
@@ -102,7 +115,7 @@ struct Ring {
 };
 
 #ifdef GLABC_FLOW_TRACE
-static __device__ long long g_pipe_trace[5][64][6];   // [role M1 (both threads) / X (warp 0) / Y (warp 8) / Y (warp 12) / M2][step][stamp]
+static __device__ long long g_pipe_trace[6][64][6];   // [role M1 (both threads) / U (warp 0) / Y (warp 8) / Y (warp 12) / M2 / E (warp 4)][step][stamp]
 #define GLABC_PTR(role, step, i)                                                          \
     do {                                                                                  \
         if (blockIdx.x == 0 && lane == 0 && (step) >= 256 && (step) < 320) g_pipe_trace[role][(step)-256][i] = clock64(); \
@@ -171,7 +184,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_flow_pipe(const __grid_cons
         }
         for (int i = 0; i < kPipeSlots; ++i) {
             mbar_init(bar(kBarAccFull + i), 1);
-            mbar_init(bar(kBarActFull + i), 256);
+            mbar_init(bar(kBarActFull + i), 128);
             mbar_init(bar(kBarOutFull + i), 1);
             mbar_init(bar(kBarAccEmpty + i), 128);
         }
@@ -280,7 +293,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_flow_pipe(const __grid_cons
                     mbar_wait(bar(kBarActFull + sl.idx), sl.par);
                     GLABC_PTR(4, qs, 1);
                     tc_fence_after();
-                    // activations: the slot's columns 0..31 (k = 0..63) and 64..95 (k = 64..127); K step k accumulates into partial sum k & 3
+                    // activations: the slot's columns 0..63; K step k accumulates into partial sum k & 3 (columns 64 + 16 (k & 3) ..)
                     const uint32_t d = tmem + sl.idx * 128u;
                     const uint32_t w3b = sAux_addr + static_cast<uint32_t>(gb & 1) * kFlowAuxBytes;
                     const uint64_t w3_desc = umma_desc(w3b, 128, 2048);
@@ -288,7 +301,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_flow_pipe(const __grid_cons
                     if (lead) {
 #pragma unroll
                         for (int k = 0; k < kFlowHidden / 16; ++k)
-                            umma_f16_ts(d + ((k & 2) ? 96u : 32u) + ((k & 1) ? 16u : 0u), d + (k < 4 ? k * 8 : 64 + (k - 4) * 8),
+                            umma_f16_ts(d + 64u + static_cast<uint32_t>(k & 3) * 16u, d + k * 8,
                                         w3_desc + static_cast<uint64_t>(k * (256 >> 4)), idesc3, k >= 4 ? 1u : 0u);
                         umma_commit(bar_out);
                     }
@@ -303,87 +316,94 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_flow_pipe(const __grid_cons
                 }
             }
         }
-    } else if (warp < 8) {
-        // ------------------------------------------------ X: state update of tile q - 2, hidden-layer epilogue of tile q ------------------------------------------------
-        const int quad = warp & 3, half = warp >> 2, row = quad * 32 + lane;
+    } else if (warp < 4) {
+        // ------------------------------------------------ U: (shift, log-scale) read-back and the state update ------------------------------------------------
+        const int quad = warp & 3, row = quad * 32 + lane;
+        const uint32_t sState_addr = smem_u32(sState), sAux_addr = smem_u32(sAux);
         const uint32_t lanebits = static_cast<uint32_t>(quad * 32) << 16;
-        Ring<kPipeSlots> sl, slu;
-        int gbu = 0;
+        Ring<kPipeSlots> sl;
+        int gb = 0;
         [[maybe_unused]] int qs = 0;
         for (int c = 0; c < my_chunks; ++c) {
-            int tu = 0;
-            for (int s = 0; s < L * T + kPipeLag; ++s, ++qs) {
+            int t = 0;
+            for (int s = 0; s < L * T; ++s, ++qs) {
                 if (warp == 0) GLABC_PTR(1, qs, 0);
-                if (s >= kPipeLag) {   // (shift, log-scale) of the tile two steps back -> affine update, log-det, Permute(swap)
-                    if (half == 0) {
-                        mbar_wait(bar(kBarOutFull + slu.idx), slu.par);
-                        tc_fence_after();
-                        uint32_t p[8];   // four partial (shift, log-scale) sums: columns 32, 48, 96, 112 of the slot
-                        const uint32_t o = tmem + slu.idx * 128u + lanebits;
-                        tmem_ld2_async(o + 32u, p[0], p[1]);
-                        tmem_ld2_async(o + 48u, p[2], p[3]);
-                        tmem_ld2_async(o + 96u, p[4], p[5]);
-                        tmem_ld2_async(o + 112u, p[6], p[7]);
-                        tmem_ld_wait();
-                        tc_fence_before();
-                        mbar_arrive(bar(kBarAccEmpty + slu.idx));
-                        const float s0 = (__uint_as_float(p[0]) + __uint_as_float(p[2])) + (__uint_as_float(p[4]) + __uint_as_float(p[6]));
-                        const float s1 = (__uint_as_float(p[1]) + __uint_as_float(p[3])) + (__uint_as_float(p[5]) + __uint_as_float(p[7]));
-                        const float* b3 = reinterpret_cast<const float*>(sAux + (gbu & 1) * kFlowAuxBytes + kAuxB3);
-                        float z1 = sState[0 * TS + tu * kFlowTile + row], z2 = sState[1 * TS + tu * kFlowTile + row];
-                        if (!SAMPLE) {  // Permute(swap)^-1 precedes the coupling's inverse
-                            const float tmp = z1;
-                            z1 = z2;
-                            z2 = tmp;
-                        }
-                        const float sh = s0 + b3[0];  // shift     = param[:, 0::2]
-                        const float sc = s1 + b3[1];  // log-scale = param[:, 1::2]
-                        float lq = sState[2 * TS + tu * kFlowTile + row];
-                        if (SAMPLE) {
-                            const float z2n = fmaf(z2, expf(sc), sh);  // z2 * exp(s) + shift; log q -= log det
-                            lq -= sc;
-                            sState[0 * TS + tu * kFlowTile + row] = z2n;  // Permute(swap)
-                            sState[1 * TS + tu * kFlowTile + row] = z1;
-                        } else {
-                            const float z2n = (z2 - sh) * expf(-sc);     // inverse; log det = -s
-                            lq -= sc;
-                            sState[0 * TS + tu * kFlowTile + row] = z1;
-                            sState[1 * TS + tu * kFlowTile + row] = z2n;
-                        }
-                        sState[2 * TS + tu * kFlowTile + row] = lq;
-                        mbar_arrive(bar(kBarStateFull + tu));   // Y: layer 1 of this tile in the next coupling block / the chunk's output
-                        if (tu == T - 1) mbar_arrive(bar(kBarAuxEmpty + (gbu & 1)));   // b3 of this coupling block is behind this thread
-                    }
-                    slu.next();
-                    if (++tu == T) {
-                        tu = 0;
-                        ++gbu;
-                    }
-                }
+                mbar_wait(bar(kBarOutFull + sl.idx), sl.par);   // (this coupling block's operands are resident: its MMAs have run)
                 if (warp == 0) GLABC_PTR(1, qs, 1);
-                if (s < L * T) {
-                    mbar_wait(bar(kBarAccFull + sl.idx), sl.par);
-                    if (warp == 0) GLABC_PTR(1, qs, 2);
-                    tc_fence_after();
-                    // this thread's 64 accumulator columns -> ReLU -> 32 packed FP16 pairs, written back over columns it has read
-                    const uint32_t trow = tmem + sl.idx * 128u + lanebits + half * 64;
-                    uint32_t va[32], vb[32], hp[16];
-                    tmem_ld32_async(trow, va);
-                    tmem_ld_wait();
-                    tmem_ld32_async(trow + 32, vb);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) hp[j] = relu_pack_f16(__uint_as_float(va[2 * j]), __uint_as_float(va[2 * j + 1]));
-                    tmem_st16(trow, hp);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) hp[j] = relu_pack_f16(__uint_as_float(vb[2 * j]), __uint_as_float(vb[2 * j + 1]));
-                    tmem_st16(trow + 16, hp);
-                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                    tc_fence_before();
-                    mbar_arrive(bar(kBarActFull + sl.idx));
-                    if (warp == 0) GLABC_PTR(1, qs, 3);
-                    sl.next();
+                tc_fence_after();
+                uint32_t p[8];   // four partial (shift, log-scale) sums: columns 64, 80, 96, 112 of the slot
+                const uint32_t o = tmem + sl.idx * 128u + lanebits;
+                tmem_ld2_async(o + 64u, p[0], p[1]);
+                tmem_ld2_async(o + 80u, p[2], p[3]);
+                tmem_ld2_async(o + 96u, p[4], p[5]);
+                tmem_ld2_async(o + 112u, p[6], p[7]);
+                // (the chain state after the wait: in a chunk's first coupling block it is Y's input, ordered by the barrier chain)
+                const uint32_t st = sState_addr + static_cast<uint32_t>((t * kFlowTile + row) * 4);
+                const uint32_t b3 = sAux_addr + static_cast<uint32_t>((gb & 1) * kFlowAuxBytes + kAuxB3);
+                float z1 = lds_f32(st), z2 = lds_f32(st + TS * 4), lq = lds_f32(st + 2 * TS * 4);
+                const float b30 = lds_f32(b3), b31 = lds_f32(b3 + 4);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(bar(kBarAccEmpty + sl.idx));
+                const float s0 = (__uint_as_float(p[0]) + __uint_as_float(p[2])) + (__uint_as_float(p[4]) + __uint_as_float(p[6]));
+                const float s1 = (__uint_as_float(p[1]) + __uint_as_float(p[3])) + (__uint_as_float(p[5]) + __uint_as_float(p[7]));
+                if (!SAMPLE) {  // Permute(swap)^-1 precedes the coupling's inverse
+                    const float tmp = z1;
+                    z1 = z2;
+                    z2 = tmp;
                 }
+                const float sh = s0 + b30;  // shift     = param[:, 0::2]
+                const float sc = s1 + b31;  // log-scale = param[:, 1::2]
+                lq -= sc;   // log q -= log det (forward) / += log det of the inverse = -s
+                if (SAMPLE) {
+                    sts_f32(st, fmaf(z2, expf(sc), sh));  // z2 * exp(s) + shift, then Permute(swap)
+                    sts_f32(st + TS * 4, z1);
+                } else {
+                    sts_f32(st, z1);
+                    sts_f32(st + TS * 4, (z2 - sh) * expf(-sc));     // the coupling's inverse
+                }
+                sts_f32(st + 2 * TS * 4, lq);
+                mbar_arrive(bar(kBarStateFull + t));   // Y: layer 1 of this tile in the next coupling block / the chunk's output
+                if (warp == 0) GLABC_PTR(1, qs, 2);
+                sl.next();
+                if (++t == T) {   // b3 of this coupling block is behind this thread
+                    t = 0;
+                    mbar_arrive(bar(kBarAuxEmpty + (gb & 1)));
+                    ++gb;
+                }
+            }
+        }
+    } else if (warp < 8) {
+        // ------------------------------------------------ E: hidden-layer epilogue ------------------------------------------------
+        const int quad = warp & 3;
+        const uint32_t lanebits = static_cast<uint32_t>(quad * 32) << 16;
+        Ring<kPipeSlots> sl;
+        [[maybe_unused]] int qs = 0;
+        for (int c = 0; c < my_chunks; ++c) {
+            for (int s = 0; s < L * T; ++s, ++qs) {
+                if (warp == 4) GLABC_PTR(5, qs, 0);
+                mbar_wait(bar(kBarAccFull + sl.idx), sl.par);
+                if (warp == 4) GLABC_PTR(5, qs, 1);
+                tc_fence_after();
+                // this row's 128 accumulator columns (b2 already added) -> ReLU -> 64 packed FP16 pairs, written back over columns
+                // 0..63 — round r reads columns 32 r .. and writes 16 r .., always behind its own reads
+                const uint32_t trow = tmem + sl.idx * 128u + lanebits;
+                uint32_t v[2][32], hp[16];
+                tmem_ld32_async(trow, v[0]);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    tmem_ld_wait();
+                    if (r + 1 < 4) tmem_ld32_async(trow + (r + 1) * 32, v[(r + 1) & 1]);
+                    const uint32_t* vv = v[r & 1];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) hp[j] = relu_pack_f16(__uint_as_float(vv[2 * j]), __uint_as_float(vv[2 * j + 1]));
+                    tmem_st16(trow + r * 16, hp);
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                mbar_arrive(bar(kBarActFull + sl.idx));
+                if (warp == 4) GLABC_PTR(5, qs, 2);
+                sl.next();
             }
         }
     } else {
@@ -391,6 +411,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_flow_pipe(const __grid_cons
         const int w = warp - 8, quad = w & 3, half = w >> 2, row = quad * 32 + lane, ytid = tid - 256;
         const uint32_t lanebits = static_cast<uint32_t>(quad * 32) << 16;
         auto y_sync = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+        const uint32_t sState_addr = smem_u32(sState), sAux_addr = smem_u32(sAux);
         Ring<2> a1;
         int gb = 0;
         for (int c = 0; c < my_chunks; ++c) {
@@ -425,25 +446,26 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_flow_pipe(const __grid_cons
                 if ((w & 3) == 0) GLABC_PTR(2 + half, qs, 0);
                 {   // layer 1 (K = 1) of this step's tile: this thread's 64 hidden units -> 32 packed columns of the A operand
                     if (t == 0) mbar_wait(bar(kBarWFull + (gb & 1)), (gb >> 1) & 1);
-                    if (gb != gb0) mbar_wait(bar(kBarStateFull + t), (gb - 1) & 1);   // X has updated this tile in the previous coupling block
-                    mbar_wait(bar(kBarA1Empty + a1.idx), a1.par ^ 1u);
-                    if ((w & 3) == 0) GLABC_PTR(2 + half, qs, 1);
-                    tc_fence_after();
-                    const float z1 = sState[(SAMPLE ? 0 : 1) * TS + t * kFlowTile + row];   // !SAMPLE: Permute(swap)^-1 precedes the inverse
+                    if (gb != gb0) mbar_wait(bar(kBarStateFull + t), (gb - 1) & 1);   // U has updated this tile in the previous coupling block
+                    // the arithmetic needs no TMEM: it runs BEFORE the wait for the operand buffer, which leaves only the store behind it
+                    const float z1 = lds_f32(sState_addr + static_cast<uint32_t>(((SAMPLE ? 0 : 1) * TS + t * kFlowTile + row) * 4));   // !SAMPLE: Permute(swap)^-1 precedes the inverse
                     // z1 as an FP16 hi + lo pair (flow.cuh: rounding the INPUT would perturb all hidden units coherently)
                     const float z_hi = __half2float(__float2half_rn(z1));
                     const uint32_t zz = pack_half2(z_hi, z_hi), zl = pack_half2(z1 - z_hi, z1 - z_hi);
-                    const uint4* w1h = reinterpret_cast<const uint4*>(sAux + (gb & 1) * kFlowAuxBytes + kAuxW1) + half * 8;
-                    const uint4* b1h = reinterpret_cast<const uint4*>(sAux + (gb & 1) * kFlowAuxBytes + kAuxB1) + half * 8;
+                    const uint32_t w1h = sAux_addr + static_cast<uint32_t>((gb & 1) * kFlowAuxBytes + kAuxW1 + half * 128);
+                    const uint32_t b1h = sAux_addr + static_cast<uint32_t>((gb & 1) * kFlowAuxBytes + kAuxB1 + half * 128);
                     uint32_t hv[32];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const uint4 ww = w1h[j], bb = b1h[j];
+                        const uint4 ww = lds_v4(w1h + j * 16), bb = lds_v4(b1h + j * 16);
                         hv[4 * j] = hfma2_relu(ww.x, zz, hfma2(ww.x, zl, bb.x));
                         hv[4 * j + 1] = hfma2_relu(ww.y, zz, hfma2(ww.y, zl, bb.y));
                         hv[4 * j + 2] = hfma2_relu(ww.z, zz, hfma2(ww.z, zl, bb.z));
                         hv[4 * j + 3] = hfma2_relu(ww.w, zz, hfma2(ww.w, zl, bb.w));
                     }
+                    mbar_wait(bar(kBarA1Empty + a1.idx), a1.par ^ 1u);
+                    if ((w & 3) == 0) GLABC_PTR(2 + half, qs, 1);
+                    tc_fence_after();
                     tmem_st32(tmem_a1 + a1.idx * 64u + lanebits + half * 32, hv);
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     tc_fence_before();

@@ -23,22 +23,27 @@ mode = sys.argv[1] if len(sys.argv) > 1 else "fast"
 for _ in range(3):
     f.fused_sample_from(eps, eng, precision=mode)
 torch.cuda.synchronize()
-t0 = time.perf_counter()
-for _ in range(5):
-    f.fused_sample_from(eps, eng, precision=mode)
-torch.cuda.synchronize()
-print("samples/s", 5 * eps.shape[0] / (time.perf_counter() - t0))
+best = 0.0
+for rep in range(3):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        f.fused_sample_from(eps, eng, precision=mode)
+    e1.record()
+    torch.cuda.synchronize()
+    best = max(best, 20 * eps.shape[0] / (e0.elapsed_time(e1) * 1e-3))
+print("samples/s", best)
 lib = ctypes.CDLL(_abi.LIB_PATH)
 if hasattr(lib, "glabc_debug_pipe_trace") and mode == "fast":
-    buf = np.zeros((5, 64, 6), dtype=np.int64)
+    buf = np.zeros((6, 64, 6), dtype=np.int64)
     rc = lib.glabc_debug_pipe_trace(buf.ctypes.data_as(ctypes.c_void_p))
     assert rc == 0, rc
     base = buf[buf > 0].min()
     np.set_printoptions(linewidth=250)
-    names = ["M1 (two threads, alternate steps): top, a1_full, acc_empty, MMA1 issued", "X warp 0: top, update done, acc_full, E1 done",
+    names = ["M1 (two threads, alternate steps): top, a1_full, acc_empty, MMA1 issued", "U warp 0: top, out_full, update done",
              "Y warp 8: top, waits done, L1 done", "Y warp 12: top, waits done, L1 done",
-             "M2: top, act_full, MMA2 issued"]
-    for r in range(5):
+             "M2: top, act_full, MMA2 issued", "E warp 4: top, acc_full, done"]
+    for r in range(6):
         print(names[r])
         for st in range(8, 24):
             row = buf[r, st]
