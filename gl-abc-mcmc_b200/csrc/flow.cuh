@@ -235,6 +235,15 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uin
         : "memory");
 }
 
+// one lane of a converged warp (the warp runs the issue loops together: a lone diverged thread pays ~45 cycles per
+// tcgen05.mma for the compiler's elect / R2UR.BROADCAST sequence; from a converged warp the MMAs issue back to back)
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t p;
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(p));
+    return p != 0;
+}
+
 // relu(lo), relu(hi) -> saturated, rounded FP16 pair (lo in bits 0..15): one F2FP instruction
 __device__ __forceinline__ uint32_t relu_pack_f16(float lo, float hi)
 {
@@ -516,7 +525,9 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
                 }
                 GLABC_TR(0);
                 // ---- layer 2 (128 x 128 x 128) on the tensor cores ----
-                if (gtid == 0) {
+                if (gtid < 32) {   // the group's first warp, converged: one elected lane issues (see elect_one)
+                  const bool lead = elect_one();
+                  if (lead) {
                     tc_fence_after();
                     if constexpr (PRECISE) {
                         // A_hi W_hi, then the two cross terms, all into the same FP32 accumulator
@@ -543,6 +554,8 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
                         }
                     }
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_m) : "memory");
+                  }
+                  __syncwarp();
                 }
                 GLABC_TR(1);
                 if constexpr (kOverlap) {   // the group's next tile: its layer 1 fills the other A buffer while the MMA runs
@@ -582,7 +595,9 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
                     group_sync(group);  // every thread has read its accumulator columns and written its activations
                     GLABC_TR(5);
                     // ---- layer 3 (128 x 16 x 128, rows 0 / 1 of W3) on the tensor cores, into accumulator columns 0..15 ----
-                    if (gtid == 0) {
+                    if (gtid < 32) {
+                      const bool lead = elect_one();
+                      if (lead) {
                         tc_fence_after();
                         constexpr uint32_t idesc3 = (1u << 4) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
                         const uint32_t sW3_addr = smem_u32(sW3);
@@ -592,6 +607,8 @@ __global__ void __launch_bounds__(kFlowThreads, 1) k_flow(const __grid_constant_
                             umma_f16_ts(tmem, tmem_a + k * 8, bd, idesc3, k > 0 ? 1u : 0u);
                         }
                         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_m) : "memory");
+                      }
+                      __syncwarp();
                     }
                     GLABC_TR(6);
                     mbar_wait(bar_m, ph_m);

@@ -77,15 +77,6 @@ __device__ __forceinline__ void umma_commit(uint32_t bar)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-// one lane of a converged warp (the warp runs the issue loops together: a lone diverged thread pays ~45 cycles per
-// tcgen05.mma for the compiler's elect / R2UR.BROADCAST sequence; from a converged warp the MMAs issue back to back)
-__device__ __forceinline__ bool elect_one()
-{
-    uint32_t p;
-    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(p));
-    return p != 0;
-}
-
 // shared-space loads by 32-bit address (a generic pointer into dynamic shared memory costs an S2R + LEA per use)
 __device__ __forceinline__ float lds_f32(uint32_t a)
 {
