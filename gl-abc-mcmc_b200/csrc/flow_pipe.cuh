@@ -2,29 +2,38 @@
 //
 // flow.cuh's k_flow gives every tile of 128 samples to one of two thread groups, and the group walks the tile through
 // layer 1 -> MMA -> epilogue -> output-layer MMA -> state update on its own.  A phase timeline of that kernel
-// (profiles/micro/k4_trace.py) shows the two groups in lock-step: both issue their MMAs at the same moment (the issuing
-// threads sit blocked for ~850 cycles while the tensor pipe works through 2 x 512), then both run their CUDA-core phases
-// while the tensor pipe idles — 3,700 cycles per pair of tiles, the tensor pipe busy for a third of them.
+// (profiles/micro/k4_trace.py, profiles/r2_k4_timeline.md) shows the two groups in lock-step: both issue their MMAs at the
+// same moment, then both run their CUDA-core phases while the tensor pipe idles — 3,700 cycles per pair of tiles, the
+// tensor pipe busy for a third of them.
 //
-// Here the PHASES own the warps and the tiles flow past them (same arithmetic, same roundings, same results):
-//   * warp 16, one thread  M1: waits on mbarriers, issues the hidden layer's tcgen05.mma (the tensor pipe's queue is a few
-//                              instructions deep: an issuing thread is paced by the MMAs' execution), commits to mbarriers,
-//                              and prefetches the next coupling block's operands (W2 32 KB + a pre-packed 9 KB blob of
-//                              w1 / b1 / b2 / W3 / b3, k_flow_pack_aux) with cp.async.bulk into the other half of a double
-//                              buffer — no CTA-wide barrier and no staging code between coupling blocks;
-//   * warp 17, one thread  M2: issues the output layer's MMAs (its waits overlap M1's issue time);
-//   * warps 8..15           Y: layer 1 of tile q (HFMA2 -> A operand in TMEM) and, three tiles behind, the (shift,
-//                              log-scale) read-back and the affine update of the chain state in shared memory;
-//   * warps 0..7            X: the hidden layer's epilogue: accumulator -> ReLU -> FP16 pairs.
-// b2 is added by the tensor cores: the accumulator of a tile is started by one extra K = 16 MMA of a constant operand (ones
-// in k = 0, 1) against [b2_hi, b2_lo, 0 ...] (both from shared memory), so the epilogue has no bias loads and no adds.
-// The output layer (M128 N16 K128) is eight K = 16 MMAs; chained into ONE accumulator each waits for its predecessor (~100
-// cycles apiece, measured), so they go into four independent 16-column accumulators (two MMAs each) that the update sums.
+// Here the PHASES own the warps and the tiles flow past them (same arithmetic and roundings as k_flow's FAST path, except
+// that b2 is added inside the accumulator and the output layer is summed from four partial accumulators):
+//   * warps 16, 17        M1: wait on mbarriers and issue the hidden layer's tcgen05.mma for alternate tiles (one warp gets
+//                            through its waits while the other's MMAs are in the tensor pipe's queue), commit to mbarriers,
+//                            and prefetch the next coupling block's operands (W2 32 KB + a pre-packed 9 KB blob of w1 / b1 /
+//                            b2 / W3 / b3, k_flow_pack_aux) with cp.async.bulk into the other half of a double buffer — no
+//                            CTA-wide barrier and no staging code between coupling blocks;
+//   * warp 18             M2: the output layer's MMAs;
+//   * warps 8..15          Y: chunk input / output; layer 1 of every tile (HFMA2 -> A operand in TMEM), computed BEFORE the
+//                            wait for the operand buffer so that only the tcgen05.st sits behind it;
+//   * warps 4..7           E: the hidden layer's epilogue: accumulator -> ReLU -> FP16 pairs, written back into the slot;
+//   * warps 0..3           U: (shift, log-scale) read-back and the affine update of the chain state in shared memory.
+// What the measurements behind this layout say (profiles/micro/mma_cost.cu, B200):
+//   * a tcgen05.mma issued by ONE diverged thread costs ~45 cycles of issue (the compiler's elect / R2UR.BROADCAST sequence
+//     per instruction); issued by an elected lane of a CONVERGED warp with its operands prepared outside the branch, M128
+//     N128 K16 runs at 64 cycles and M128 N16 K16 (A in TMEM) at 11.5 — the issuing warps therefore run their loops
+//     converged (elect_one) — and the same N16 MMA with A in shared memory takes 39 cycles;
+//   * b2 is added by the tensor cores: the accumulator of a tile is started by one extra K = 16 MMA of a constant operand
+//     (ones in k = 0, 1) against [b2_hi, b2_lo, 0 ...] (both from shared memory): no bias loads or adds in the epilogue;
+//   * the output layer (M128 N16 K128, eight K = 16 MMAs) goes into four independent 16-column accumulators (two MMAs
+//     each), which the update sums;
+//   * the same contraction on the CUDA cores (FFMA2) made the epilogue the bottleneck (7.2e8 samples/s against 1.2e9).
 // TMEM (512 columns): three 128-column accumulator slots and two 64-column layer-1 operand buffers.  The epilogue writes
-// the packed activations back INTO its accumulator slot (columns 0..63, each thread behind its own reads) and the output-layer MMA (M128 N16 K128) puts its 16 result columns into the same slot (columns 32..47), so the
-// layer-1 buffer of a tile is free as soon as its first MMA completes and three tiles are in flight instead of two
-// (output-layer partial sums: columns 64..127 of the slot):
-//   window of MMA1(q):  X works on tile q-1, Y on layer 1 of q+1 and the update of q-2, MMA2(q-1) queues behind MMA1(q).
+// the packed activations back INTO its accumulator slot (columns 0..63, each thread behind its own reads) and the
+// output-layer MMAs put their partial sums into the same slot (columns 64..127), so the layer-1 buffer of a tile is free as
+// soon as its first MMA completes and three tiles are in flight instead of two.
+// Synchronisation is mbarriers only (full / empty pairs per resource, one state barrier per tile of the chunk); the two
+// M1 warps and M2 interleave in the tensor pipe's queue in arrival order.
 #pragma once
 #include "flow.cuh"
 

@@ -152,6 +152,26 @@ def test_matches_fp32_torch(flow, n):
             assert float(err.quantile(0.999)) < 0.3
 
 
+def test_fast_pipeline_many_chunks_per_cta(flow):
+    """more chunks than SMs (the pipelined kernel's persistent loop, double-buffered operands and barrier phases run on
+    across chunk boundaries) and a ragged last tile: every row's result is independent of where its tile sits, so rows of
+    the big launch equal the same rows run as a small batch bit for bit; and the big launch agrees with PRECISE"""
+    n = 148 * 32 * 128 + 148 * 8 * 128 + 77
+    eps = torch.randn(n, 2, device="cuda", generator=torch.Generator(device="cuda").manual_seed(11))
+    th, lq = flow.fused_sample_from(eps)
+    pick = torch.cat([torch.arange(0, 300), torch.arange(606_000, 606_600), torch.arange(n - 300, n)]).cuda()
+    th_s, lq_s = flow.fused_sample_from(eps[pick].contiguous())
+    assert torch.equal(th[pick], th_s) and torch.equal(lq[pick], lq_s)
+    lp = flow.fused_log_prob(th)
+    lp_s = flow.fused_log_prob(th[pick].contiguous())
+    assert torch.equal(lp[pick], lp_s)
+    th_p, lq_p = flow.fused_sample_from(eps, precision="precise")
+    flow.bind().flow_precision("fast")
+    e_th = ((th - th_p).abs() / (1 + th_p.abs())).max(1).values
+    assert float(e_th.median()) < 1.5e-3 and float(e_th.quantile(0.99)) < 1e-2, (float(e_th.median()), float(e_th.quantile(0.99)))
+    assert float((lq - lq_p).abs().median()) < 2e-3
+
+
 def test_sample_log_prob_consistency(flow):
     """the kernel's own pair: log_prob(sample(eps)) reproduces the log q returned with the sample.  sample()'s log q is the
     exact density of the map that produced theta (same s values in the transform and the log-det); log_prob() re-derives
