@@ -54,6 +54,10 @@ cudaError_t launch_flow(const FlowDev& W, bool sample, bool precise, const float
             if (e != cudaSuccess) return e;
             e = cudaFuncSetAttribute(k_flow_pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeSmemBytes);
             if (e != cudaSuccess) return e;
+            e = cudaFuncSetAttribute(k_flow_pipe_precise<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipePSmemBytes);
+            if (e != cudaSuccess) return e;
+            e = cudaFuncSetAttribute(k_flow_pipe_precise<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipePSmemBytes);
+            if (e != cudaSuccess) return e;
         }
         configured = true;
     }
@@ -65,11 +69,16 @@ cudaError_t launch_flow(const FlowDev& W, bool sample, bool precise, const float
     tpc = (tpc + 1) / 2 * 2;
     if (tpc < 2) tpc = 2;
     if (tpc > kFlowTilesPerCta) tpc = kFlowTilesPerCta;
-    const bool pipe = kFlowF16 && !precise && W.aux != nullptr && use_pipe();
+    const bool pipe = kFlowF16 && W.aux != nullptr && use_pipe();
     if (pipe && tpc < kPipeMinTiles) tpc = kPipeMinTiles;   // the update runs kPipeLag tiles behind layer 1
     const int64_t chunks = (tiles + tpc - 1) / tpc;
     const unsigned grid = static_cast<unsigned>(chunks < sm_count ? chunks : sm_count);  // persistent: one CTA per SM
     if constexpr (kFlowF16) {
+        if (pipe && precise) {
+            if (sample) k_flow_pipe_precise<true><<<grid, 18 * 32, kPipePSmemBytes, st>>>(W, in, n, out_theta, out_lq, static_cast<int>(tpc));
+            else k_flow_pipe_precise<false><<<grid, 18 * 32, kPipePSmemBytes, st>>>(W, in, n, out_theta, out_lq, static_cast<int>(tpc));
+            return cudaGetLastError();
+        }
         if (pipe) {
             if (sample) k_flow_pipe<true><<<grid, kPipeThreads, kPipeSmemBytes, st>>>(W, in, n, out_theta, out_lq, static_cast<int>(tpc));
             else k_flow_pipe<false><<<grid, kPipeThreads, kPipeSmemBytes, st>>>(W, in, n, out_theta, out_lq, static_cast<int>(tpc));

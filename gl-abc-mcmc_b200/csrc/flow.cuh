@@ -78,7 +78,7 @@ constexpr int kFlowSmemBytesPrecise = 2 * kFlowW2Bytes + kFlowVecFloats * 4 + 3 
                                       kFlowGroups * 2 * kFlowTile * 8 + 64;
 
 // per coupling block, the small operands pre-packed for the pipelined FAST kernel (flow_pipe.cuh: k_flow_pack_aux)
-constexpr int kFlowAuxBytes = 8832;
+constexpr int kFlowAuxBytes = 10880;   // FAST reads bytes [0, 8832), PRECISE bytes [4608, 10880) of a block's blob
 
 struct FlowDev {
     const float* w1;   // [L][128]
