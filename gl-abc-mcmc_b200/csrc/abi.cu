@@ -758,8 +758,12 @@ extern "C" int glabc_run_aglmcmc(glabc_ctx* ctx, const glabc_run_t* run, const g
     const glabc_dist_t& lp = ctx->dist[GLABC_SLOT_LOCAL];
     const glabc_dist_t& ip = ctx->dist[GLABC_SLOT_IMPORTANCE];
     if (lp.dim != d || ip.dim != d) return fail(ctx, GLABC_ERR_INVALID, "proposal dim does not match theta_dim %d", d);
-    if (!all_gaussian(ctx, {GLABC_SLOT_LOCAL, GLABC_SLOT_IMPORTANCE}))
-        return fail(ctx, GLABC_ERR_UNSUPPORTED, "run_aglmcmc is fused for DiagGaussian Local_Proposal / Initial_ISIR_prop");
+    if (!all_gaussian(ctx, {GLABC_SLOT_LOCAL}))
+        return fail(ctx, GLABC_ERR_UNSUPPORTED, "run_aglmcmc is fused for a DiagGaussian Local_Proposal");
+    const bool gip = !all_gaussian(ctx, {GLABC_SLOT_IMPORTANCE});
+    if (gip && (run->arith_mode == GLABC_ARITH_STRICT || run->rng_mode == GLABC_RNG_REPLAY || ag->ad_rec || ag->ad_blk || ag->init_w))
+        return fail(ctx, GLABC_ERR_UNSUPPORTED, "run_aglmcmc with a non-Gaussian Initial_ISIR_prop runs FAST arithmetic with the native RNG "
+                                                "(the STRICT / replay / recording kernels are fused for a DiagGaussian Initial_ISIR_prop)");
     if (run->n_candidates < 1 || run->n_candidates > GLABC_MAX_K)
         return fail(ctx, GLABC_ERR_INVALID, "n_candidates (batch_size) must be in 1..%d", GLABC_MAX_K);
     if (ag->step_size < 1 || int64_t(ag->step_size) * run->n_candidates > GLABC_AG_MAX_BLOCK)
@@ -783,7 +787,12 @@ extern "C" int glabc_run_aglmcmc(glabc_ctx* ctx, const glabc_run_t* run, const g
     AgConsts K{};
     K.model = make_model(ctx->model);
     K.lp = make_gauss(lp.a, lp.b, lp.c, d);
-    K.ip = make_gauss(ip.a, ip.b, ip.c, d);
+    if (gip) {
+        K.ip_generic = 1;
+        K.ipg = make_dist(ip);
+    } else {
+        K.ip = make_gauss(ip.a, ip.b, ip.c, d);
+    }
     K.S = ag->step_size;
     K.alpha = ag->alpha;
     K.hat_eps_T = ag->hat_eps_T;

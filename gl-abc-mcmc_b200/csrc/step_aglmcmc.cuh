@@ -18,6 +18,7 @@
 #include "kde.cuh"
 #include "launch.cuh"
 #include "sampler_common.cuh"
+#include "step_generic.cuh"
 
 namespace glabc {
 
@@ -39,6 +40,8 @@ struct AgConsts {
     int32_t S;            // step_size
     float alpha, hat_eps_T;
     float log_prior_floor;  // float32(log(1e-10)), AGLMCMC.py:223-224
+    int32_t ip_generic;     // Initial_ISIR_prop is a Uniform / Gamma / GaussianMixture (`ipg`; FAST arithmetic, native RNG), else `ip`
+    DistConsts ipg;
 };
 
 struct AgTapes {
@@ -108,7 +111,14 @@ __global__ void __launch_bounds__(256) k_ag_block(const __grid_constant__ AgCons
                 eps_s[k] = z[D + k];
             }
         }
-        lq = gauss_forward<D, true>(K.ip, eps_p, th);
+        if (!REPLAY && K.ip_generic) {   // candidate b's draw and its simulator normals from one word stream (as k_isir_generic's)
+            WordStream ws(R.rk, st, 0u, kSlotGeneric + 64u * static_cast<uint32_t>(b));
+            lq = dist_forward<D>(K.ipg, ws, th);
+#pragma unroll
+            for (int k = 0; k < D; ++k) eps_s[k] = ws.normal();
+        } else {
+            lq = gauss_forward<D, true>(K.ip, eps_p, th);
+        }
 #pragma unroll
         for (int k = 0; k < D; ++k) W.blk_theta[(c * W.B + b) * D + k] = th[k];
         W.blk_lq[c * W.B + b] = lq;
@@ -482,7 +492,7 @@ __global__ void __launch_bounds__(128) k_ag_step(const __grid_constant__ AgConst
             const float kern_old = model_log_kernel<D, STRICT>(K.model, y);
             if (is_global) {
                 // :137-149: weight of the current state under the current importance proposal
-                const float lq_old = n_adapt == 0 ? gauss_log_prob<D, STRICT>(K.ip, theta) : lq_cur;
+                const float lq_old = n_adapt == 0 ? (K.ip_generic ? dist_log_prob<D>(K.ipg, theta) : gauss_log_prob<D, STRICT>(K.ip, theta)) : lq_cur;
                 const float lw = STRICT ? __fsub_rn(__fadd_rn(prior_old, kern_old), lq_old) : (prior_old + kern_old) - lq_old;
                 float w_old;
                 if constexpr (STRICT) {

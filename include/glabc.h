@@ -380,7 +380,10 @@ GLABC_API int glabc_run_mala(glabc_ctx* ctx, const glabc_run_t* run);
  * run->n_candidates = batch_size.  Chains pause individually when they reach an adaptation; the call runs
  * step / adapt rounds until every chain has performed run->n_steps iterations.  Debug slots (float32, `debug`):
  * 0 flags as run_isir; global move: 1 proposal log-density of the current state, 2 its weight, 3 sum of the
- * K+1 weights; local move: as run_global.                                                                    */
+ * K+1 weights; local move: as run_global.
+ * A Uniform / Gamma / GaussianMixture Initial_ISIR_prop (the initial candidate block, AGLMCMC.py:84-112, and the weight
+ * of the current state before the first adaptation, :137-149) is taken with GLABC_ARITH_FAST and the native RNG; STRICT /
+ * replay / recording runs and a non-Gaussian Local_Proposal are refused with GLABC_ERR_UNSUPPORTED.           */
 GLABC_API int glabc_run_aglmcmc(glabc_ctx* ctx, const glabc_run_t* run, const glabc_aglmcmc_t* ag);
 
 /* GlobalMCMC loop body (GlobalMCMC.py:37-68) for a user-supplied model: LOCAL / GLOBAL slots must hold DiagGaussian

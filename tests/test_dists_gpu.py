@@ -119,15 +119,33 @@ def test_global_mcmc_with_mixture_and_uniform_proposals(eng):
 
 
 def test_non_gaussian_proposals_are_refused_where_not_fused(eng):
-    """AGLMCMC and the STRICT / replay GLMALA kernel are fused for a DiagGaussian importance proposal: any other kind is
-    refused with a message, not run through some other path (run_global_mcmc, run_glmcmc and the FAST native run_mala take
-    every kind)"""
+    """the STRICT / replay GLMALA and AGLMCMC kernels are fused for a DiagGaussian importance proposal, and AGLMCMC for a
+    DiagGaussian Local_Proposal: any other kind is refused with a message, not run through some other path
+    (run_global_mcmc, run_glmcmc and the FAST native run_mala / run_aglmcmc take every kind of importance proposal)"""
     g, model, lp = readme()
     box = g.Uniform(2, torch.tensor([-3.0, -3.0]), torch.tensor([3.0, 3.0]))
     with pytest.raises(abi.GlabcError, match="DiagGaussian"):
         g.GLMALA(model, 100, torch.zeros(2), None, 0.3, 10, None, 0.8, box, 5, num_chains=64, arith="strict")
     with pytest.raises(abi.GlabcError, match="DiagGaussian"):
-        g.AGLMCMC(model, 100, torch.zeros(2), None, lp, box, None, 1.0, 10, 5, 0.8, 0.2, num_chains=64)
+        g.AGLMCMC(model, 100, torch.zeros(2), None, lp, box, None, 1.0, 10, 5, 0.8, 0.2, num_chains=64, arith="strict")
+    with pytest.raises(abi.GlabcError, match="DiagGaussian"):
+        g.AGLMCMC(model, 100, torch.zeros(2), None, box, lp, None, 0.5, 10, 5, 0.8, 0.2, num_chains=64)
+
+
+def test_aglmcmc_with_non_gaussian_initial_proposal(eng):
+    """run_aglmcmc (AGLMCMC.py:84-112,137-149) with a Uniform / GaussianMixture Initial_ISIR_prop: the initial candidate
+    block and the first rounds' weights use it, the per-chain KDEs take over afterwards; the closed-form ABC posterior
+     is left invariant"""
+    g, model, lp = readme()
+    box = g.Uniform(2, torch.tensor([-3.0, -3.0]), torch.tensor([3.0, 3.0]))
+    out = g.AGLMCMC(model, 3001, torch.zeros(2), None, lp, box, None, 1.0, 200, 5, 0.8, 0.2, num_chains=4096, seed=2, trace="time")
+    check_posterior(out[-1], tol=0.04)
+    modes = [[1.425, 1.425], [1.425, -1.425], [-1.425, 1.425], [-1.425, -1.425]]
+    gm = g.GaussianMixture(4, 2, loc=modes, scale=[[0.5, 0.5]] * 4, weights=[1, 1, 1, 1])
+    out, st = g.AGLMCMC(model, 2001, torch.zeros(2), None, lp, gm, None, 0.9, 100, 5, 0.8, 0.2, num_chains=4096, seed=3, trace="time",
+                        return_stats=True)
+    check_posterior(out[-1], tol=0.04)
+    assert float(st.move_rate.mean()) > 0.005
 
 
 def test_glmala_with_non_gaussian_importance_proposals(eng):
