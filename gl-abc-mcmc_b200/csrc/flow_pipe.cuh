@@ -108,6 +108,14 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t a)
 }
 __device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 
+// keep a computed address in its register: without this the compiler re-derives shared-window addresses at every use
+// (S2R SR_CgaCtaId + LEA, ~20 cycles of latency in front of each mbarrier wait)
+__device__ __forceinline__ uint32_t opaque(uint32_t v)
+{
+    asm volatile("" : "+r"(v));
+    return v;
+}
+
 // ring position of a running counter: index q % N and the parity of q / N, advanced without a division
 template <int N>
 struct Ring {
@@ -199,7 +207,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_flow_pipe(const __grid_cons
     const int T = tpc, L = W.n_blocks;
     const int64_t n_chunks = (n + static_cast<int64_t>(T) * kFlowTile - 1) / (static_cast<int64_t>(T) * kFlowTile);
     const int my_chunks = blockIdx.x < n_chunks ? static_cast<int>((n_chunks - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
-    const uint32_t bar0 = smem_u32(bars);
+    const uint32_t bar0 = opaque(smem_u32(bars));
     auto bar = [&](int i) { return bar0 + 8u * static_cast<uint32_t>(i); };
 
     if (warp == 0) {
@@ -231,7 +239,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_flow_pipe(const __grid_cons
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;            // accumulator slot s: columns 128 s ..; layer-1 operand buffer b: columns 384 + 64 b ..
+    const uint32_t tmem = opaque(*tmem_slot);    // accumulator slot s: columns 128 s ..; layer-1 operand buffer b: columns 384 + 64 b ..
     const uint32_t tmem_a1 = tmem + 384u;
     const float c2 = -1.8378770664093453f;       // -0.5 * 2 * log(2 pi)
 
@@ -350,7 +358,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_flow_pipe(const __grid_cons
     } else if (warp < 4) {
         // ------------------------------------------------ U: (shift, log-scale) read-back and the state update ------------------------------------------------
         const int quad = warp & 3, row = quad * 32 + lane;
-        const uint32_t sState_addr = smem_u32(sState), sAux_addr = smem_u32(sAux);
+        const uint32_t sState_addr = opaque(smem_u32(sState)), sAux_addr = opaque(smem_u32(sAux));
         const uint32_t lanebits = static_cast<uint32_t>(quad * 32) << 16;
         Ring<kPipeSlots> sl;
         int gb = 0;
@@ -442,7 +450,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_flow_pipe(const __grid_cons
         const int w = warp - 8, quad = w & 3, half = w >> 2, row = quad * 32 + lane, ytid = tid - 256;
         const uint32_t lanebits = static_cast<uint32_t>(quad * 32) << 16;
         auto y_sync = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
-        const uint32_t sState_addr = smem_u32(sState), sAux_addr = smem_u32(sAux);
+        const uint32_t sState_addr = opaque(smem_u32(sState)), sAux_addr = opaque(smem_u32(sAux));
         Ring<2> a1;
         int gb = 0;
         for (int c = 0; c < my_chunks; ++c) {
@@ -574,7 +582,7 @@ __global__ void __launch_bounds__(18 * 32, 1) k_flow_pipe_precise(const __grid_c
     const int T = tpc, L = W.n_blocks;
     const int64_t n_chunks = (n + static_cast<int64_t>(T) * kFlowTile - 1) / (static_cast<int64_t>(T) * kFlowTile);
     const int my_chunks = blockIdx.x < n_chunks ? static_cast<int>((n_chunks - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
-    const uint32_t bar0 = smem_u32(bars);
+    const uint32_t bar0 = opaque(smem_u32(bars));
     auto bar = [&](int i) { return bar0 + 8u * static_cast<uint32_t>(i); };
     // offsets inside the staged part of a block's blob
     constexpr int oB3 = kAuxB3 - kAuxPreciseOff, oB2Op = kAuxB2Op - kAuxPreciseOff, oW3 = kAuxW3F - kAuxPreciseOff,
@@ -605,9 +613,9 @@ __global__ void __launch_bounds__(18 * 32, 1) k_flow_pipe_precise(const __grid_c
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = opaque(*tmem_slot);
     const float c2 = -1.8378770664093453f;       // -0.5 * 2 * log(2 pi)
-    const uint32_t sState_addr = smem_u32(sState), sAux_addr = smem_u32(sAux);
+    const uint32_t sState_addr = opaque(smem_u32(sState)), sAux_addr = opaque(smem_u32(sAux));
 
     if (warp == 16 || warp == 17) {
         // ------------------------------------------------ M1 ------------------------------------------------
