@@ -22,8 +22,10 @@
 #ifndef GLABC_MALA_KUNROLL
 #define GLABC_MALA_KUNROLL 5
 #endif
+// one warp per CTA: at 32,768 chains 64-thread CTAs are 512 CTAs = 3.46 per SM (a 4 : 3 imbalance over the SMs); 32-thread
+// CTAs measured 5 % faster there and 2 % faster at 262,144 chains (profiles/micro/k3_block.sh)
 #ifndef GLABC_MALA_BLOCK
-#define GLABC_MALA_BLOCK 64
+#define GLABC_MALA_BLOCK 32
 #endif
 #define GLABC_PRAGMA(x) _Pragma(#x)
 #define GLABC_UNROLL(n) GLABC_PRAGMA(unroll n)
