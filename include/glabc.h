@@ -13,7 +13,13 @@
  *     (pinned memory makes the copies asynchronous, pageable memory works too).
  *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Device entry
  *     points only enqueue work; host entry points return when the result is in the host buffers.
- *   - no hidden global state: one context per (thread, device); a context is not thread-safe.
+ *   - no hidden global state: one context per (thread, device); a context is not thread-safe and it is
+ *     single-stream: its scratch buffers (KDE partial sums, resample scans, the host entry points' staging,
+ *     the flow's packed operands and training state) are reused by consecutive calls without cross-stream
+ *     ordering — issue the calls of one context on ONE stream (or order the streams with events yourself).
+ *   - the per-chain statistics (`stats`) are float32 running sums: exact counters up to 2^24 steps per
+ *     chain, and moments meant for diagnostics over <= ~1e6 steps; accumulate longer runs on the host in
+ *     float64 from per-launch (or per-checkpoint) stats buffers.
  *   - all floating-point parameters are float32 values the host evaluated the way the reference
  *     does (e.g. scale = exp(log_scale) in float32, distribution.py:170), so device code never has to
  *     re-derive a constant with a different libm.
