@@ -148,6 +148,16 @@ def test_aglmcmc_with_non_gaussian_initial_proposal(eng):
     assert float(st.move_rate.mean()) > 0.005
 
 
+def test_pooled_aglmcmc_with_uniform_initial_proposal(eng):
+    """AGLMCMC(pooled=True) (BASELINE config 5) with a Uniform Initial_ISIR_prop: the pooled path draws the initial blocks
+    through glabc_dist_sample / glabc_dist_log_prob, which take every class; posterior check as the DiagGaussian case"""
+    g, model, lp = readme()
+    box = g.Uniform(2, torch.tensor([-3.0, -3.0]), torch.tensor([3.0, 3.0]))
+    out = g.AGLMCMC(model, 1001, torch.zeros(2), None, lp, box, None, 0.9, 50, 5, 0.8, 0.2, num_chains=2048, seed=5, trace="time",
+                    pooled=True, kde_train=20000)
+    check_posterior(out[-1], tol=0.05)
+
+
 def test_glmala_with_non_gaussian_importance_proposals(eng):
     """run_mala (GLMALA.py:151-180) with a GaussianMixture / Uniform Importance_Proposal through k_mala_fast<GIP>: the
     closed-form ABC posterior is left invariant, the mode-covering mixture moves far more often than
