@@ -172,6 +172,33 @@ def test_fast_pipeline_many_chunks_per_cta(flow):
     assert float((lq - lq_p).abs().median()) < 2e-3
 
 
+@pytest.mark.parametrize("n_blocks", [1, 2, 3, 5])
+def test_pipeline_kernels_with_few_coupling_blocks(n_blocks):
+    """the pipelined kernels prefetch the next coupling block's operands into a double buffer and carry their barrier
+    phases across blocks and chunks: 1, 2, 3 and 5 blocks (odd and even, fewer than the buffer depth) over one and over
+    several chunks per CTA, both precisions, against the fp32 torch module"""
+    from glabc_b200.flows import RealNVP
+    torch.manual_seed(n_blocks)
+    f = RealNVP(n_blocks=n_blocks, device="cuda")
+    with torch.no_grad():
+        f.w3.copy_(0.05 * torch.randn_like(f.w3))
+        f.b3.copy_(0.02 * torch.randn_like(f.b3))
+    eng = f.bind()
+    try:
+        for n in (300, 148 * 32 * 128 * 2 + 1000):
+            eps = torch.randn(n, 2, device="cuda", generator=torch.Generator(device="cuda").manual_seed(n_blocks))
+            with torch.no_grad():
+                th_r, lq_r = f.sample_from(eps)
+            for mode, tol in (("fast", 2e-3), ("precise", 2e-5)):
+                th, lq = f.fused_sample_from(eps, eng, precision=mode)
+                assert float(((th - th_r).abs() / (1 + th_r.abs())).max()) < 10 * tol, (mode, n)
+                assert float((lq - lq_r).abs().median()) < tol and float((lq - lq_r).abs().max()) < 50 * tol, (mode, n)
+                lp = f.fused_log_prob(th, eng, precision=mode)
+                assert float((lp - lq).abs().median()) < tol, (mode, n)
+    finally:
+        eng.flow_precision("fast")
+
+
 def test_sample_log_prob_consistency(flow):
     """the kernel's own pair: log_prob(sample(eps)) reproduces the log q returned with the sample.  sample()'s log q is the
     exact density of the map that produced theta (same s values in the transform and the log-det); log_prob() re-derives
