@@ -10,5 +10,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-fil
     python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e --no-ref-python > $o/r2_ncu_launches.log 2>&1
 N="ncu --set full --clock-control none --import-source on -c 1 -f"
 $N -k regex:k_flow_pipe_precise -o $o/r2_k4_flow_pipe_precise python profiles/flow_ncu_target.py precise > $o/r2_ncu_k4pp.log 2>&1
-$N -k regex:'k_flow_pipe<' -o $o/r2_k4_flow_pipe python profiles/flow_ncu_target.py fast > $o/r2_ncu_k4p.log 2>&1
+$N -k 'regex:k_flow_pipe$' -o $o/r2_k4_flow_pipe python profiles/flow_ncu_target.py fast > $o/r2_ncu_k4p.log 2>&1
 ls -la $o/*.ncu-rep $o/r2_launches.csv
