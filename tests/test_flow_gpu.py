@@ -261,9 +261,12 @@ def test_glmcmc_nf_training_improves_the_proposal():
     onto the four posterior modes, and the chains still target the posterior"""
     from scipy import stats as sst
     g, model, lp = readme_objects()
+    # `resample` takes its offset from torch's GLOBAL generator, one torch.rand(1) per training batch (GLMCMC_NFs.py:33, as the
+    # reference does): seeded here so that the 50-step trajectory does not depend on what earlier tests drew
+    torch.manual_seed(1234)
     res, st, flow, losses = g.GLMCMC_NF(model, 4001, torch.zeros(2), None, lp, None, 0.5, 25, 5, None, 50, num_chains=2048,
                                         seed=1, trace="time", return_stats=True, return_flow=True, lr=3e-3)
-    assert len(losses) == 50 and np.mean(losses[-5:]) < np.mean(losses[:3]) - 0.3, losses
+    assert len(losses) == 50 and np.mean(losses[-10:]) < np.mean(losses[:5]) - 0.3, losses
     th, _ = flow.fused_sample_from(torch.randn(50000, 2, device="cuda"))
     near_mode = ((th.abs() - 1.425).abs() < 0.7).all(1).float().mean()
     assert float(near_mode) > 0.25, float(near_mode)            # N(0, I) puts ~9 % there
