@@ -455,6 +455,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_flow_pipe(const __grid_cons
         const uint32_t sState_addr = opaque(smem_u32(sState)), sAux_addr = opaque(smem_u32(sAux));
         Ring<2> a1;
         int gb = 0;
+        uint32_t wreg[32];   // w1 of this thread's 64 hidden units as FP16 pairs, reloaded once per coupling block
         for (int c = 0; c < my_chunks; ++c) {
             const int64_t chunk = blockIdx.x + static_cast<int64_t>(c) * gridDim.x;
             for (int r = ytid; r < T * kFlowTile; r += 256) {
@@ -486,23 +487,30 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_flow_pipe(const __grid_cons
             for (int s = 0; s < L * T; ++s, ++qs) {
                 if ((w & 3) == 0) GLABC_PTR(2 + half, qs, 0);
                 {   // layer 1 (K = 1) of this step's tile: this thread's 64 hidden units -> 32 packed columns of the A operand
-                    if (t == 0) mbar_wait(bar(kBarWFull + (gb & 1)), (gb >> 1) & 1);
+                    if (t == 0) {   // a new coupling block: its operands have landed; this thread's 64 units of w1 stay in registers
+                        mbar_wait(bar(kBarWFull + (gb & 1)), (gb >> 1) & 1);
+                        const uint32_t w1h = sAux_addr + static_cast<uint32_t>((gb & 1) * kAuxFastBytes + kAuxW1 + half * 128);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const uint4 ww = lds_v4(w1h + j * 16);
+                            wreg[4 * j] = ww.x; wreg[4 * j + 1] = ww.y; wreg[4 * j + 2] = ww.z; wreg[4 * j + 3] = ww.w;
+                        }
+                    }
                     if (gb != gb0) mbar_wait(bar(kBarStateFull + t), (gb - 1) & 1);   // U has updated this tile in the previous coupling block
                     // the arithmetic needs no TMEM: it runs BEFORE the wait for the operand buffer, which leaves only the store behind it
                     const float z1 = lds_f32(sState_addr + static_cast<uint32_t>(((SAMPLE ? 0 : 1) * TS + t * kFlowTile + row) * 4));   // !SAMPLE: Permute(swap)^-1 precedes the inverse
                     // z1 as an FP16 hi + lo pair (flow.cuh: rounding the INPUT would perturb all hidden units coherently)
                     const float z_hi = __half2float(__float2half_rn(z1));
                     const uint32_t zz = pack_half2(z_hi, z_hi), zl = pack_half2(z1 - z_hi, z1 - z_hi);
-                    const uint32_t w1h = sAux_addr + static_cast<uint32_t>((gb & 1) * kAuxFastBytes + kAuxW1 + half * 128);
                     const uint32_t b1h = sAux_addr + static_cast<uint32_t>((gb & 1) * kAuxFastBytes + kAuxB1 + half * 128);
                     uint32_t hv[32];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const uint4 ww = lds_v4(w1h + j * 16), bb = lds_v4(b1h + j * 16);
-                        hv[4 * j] = hfma2_relu(ww.x, zz, hfma2(ww.x, zl, bb.x));
-                        hv[4 * j + 1] = hfma2_relu(ww.y, zz, hfma2(ww.y, zl, bb.y));
-                        hv[4 * j + 2] = hfma2_relu(ww.z, zz, hfma2(ww.z, zl, bb.z));
-                        hv[4 * j + 3] = hfma2_relu(ww.w, zz, hfma2(ww.w, zl, bb.w));
+                        const uint4 bb = lds_v4(b1h + j * 16);
+                        hv[4 * j] = hfma2_relu(wreg[4 * j], zz, hfma2(wreg[4 * j], zl, bb.x));
+                        hv[4 * j + 1] = hfma2_relu(wreg[4 * j + 1], zz, hfma2(wreg[4 * j + 1], zl, bb.y));
+                        hv[4 * j + 2] = hfma2_relu(wreg[4 * j + 2], zz, hfma2(wreg[4 * j + 2], zl, bb.z));
+                        hv[4 * j + 3] = hfma2_relu(wreg[4 * j + 3], zz, hfma2(wreg[4 * j + 3], zl, bb.w));
                     }
                     mbar_wait(bar(kBarA1Empty + a1.idx), a1.par ^ 1u);
                     if ((w & 3) == 0) GLABC_PTR(2 + half, qs, 1);
