@@ -27,7 +27,8 @@
 //     (ones in k = 0, 1) against [b2_hi, b2_lo, 0 ...] (both from shared memory): no bias loads or adds in the epilogue;
 //   * the output layer (M128 N16 K128, eight K = 16 MMAs) goes into four independent 16-column accumulators (two MMAs
 //     each), which the update sums;
-//   * the same contraction on the CUDA cores (FFMA2) made the epilogue the bottleneck (7.2e8 samples/s against 1.2e9).
+//   * the same contraction on the CUDA cores (FFMA2) made the epilogue the bottleneck (7.2e8 samples/s against 1.2e9);
+//   * Y is the critical role (layer 1: 64 HFMA2 per thread and tile): its w1 stays in registers across a block's tiles.
 // TMEM (512 columns): three 128-column accumulator slots and two 64-column layer-1 operand buffers.  The epilogue writes
 // the packed activations back INTO its accumulator slot (columns 0..63, each thread behind its own reads) and the
 // output-layer MMAs put their partial sums into the same slot (columns 64..127), so the layer-1 buffer of a tile is free as
